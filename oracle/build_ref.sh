@@ -1,0 +1,29 @@
+#!/bin/bash
+# Build oracle/_ref/libref.so from the UNMODIFIED reference sources where they
+# lie under $REF (default /root/reference).  Nothing is copied: headers come in
+# through -I, and the two line ranges that live inside larger, unbuildable
+# files (JACK / Pd glue around them) are piped from sed straight into gcc.
+# The reference's own build system (uc_tools build.sh, nix) is NOT run.
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${REF:-/root/reference}"
+if [ ! -d "$REF" ]; then
+    echo "build_ref: $REF not present, keeping prebuilt oracle/_ref" >&2
+    exit 0
+fi
+mkdir -p "$HERE/_ref"
+OBJ="$(mktemp -d /tmp/cproc_ref_obj.XXXXXX)"
+CFLAGS="-std=gnu99 -O2 -fwrapv -ffp-contract=off -fPIC -fopenmp -w"
+# (1) generic/cproc.h + linux/test_cproc.c (whole file; main renamed)
+gcc $CFLAGS -I"$HERE/shim" -I"$REF/generic" -c "$HERE/ref/ref_cproc.c" -o "$OBJ/ref_cproc.o"
+gcc $CFLAGS -I"$HERE/shim" -I"$REF/generic" -Dmain=ref_test_cproc_main -c "$REF/linux/test_cproc.c" -o "$OBJ/test_cproc.o"
+# (2) stm32f103/pdm.h
+gcc $CFLAGS -I"$REF/stm32f103" -c "$HERE/ref/ref_pdm.c" -o "$OBJ/ref_pdm.o"
+# (3) linux/synth.c:29-206 (voice bank DSP; JACK glue excluded)
+( echo '#include <stdint.h>'; echo '#include <strings.h>'; sed -n 29,206p "$REF/linux/synth.c"; cat "$HERE/ref/ref_synth_tail.c" ) \
+  | gcc $CFLAGS -x c -c - -o "$OBJ/ref_synth.o"
+# (4) linux/synth_tools.c:78-100 (struct square_grain + square_grain_proc)
+( cat "$HERE/ref/ref_pre_pd.h"; sed -n 78,100p "$REF/linux/synth_tools.c"; cat "$HERE/ref/ref_grain_tail.c" ) \
+  | gcc $CFLAGS -x c -c - -o "$OBJ/ref_grain.o"
+gcc -shared -fopenmp -o "$HERE/_ref/libref.so" "$OBJ/ref_cproc.o" "$OBJ/test_cproc.o" "$OBJ/ref_pdm.o" "$OBJ/ref_synth.o" "$OBJ/ref_grain.o" -lm
+echo "built $HERE/_ref/libref.so"
