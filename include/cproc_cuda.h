@@ -1,0 +1,239 @@
+/* cproc_cuda.h -- C-ABI of the B200 batched renderer for the synth_tools
+ * per-sample DSP hot path.  Plain C99 (includable from the linux/ C hosts built with
+ * -std=gnu99, rules.mk:304); no CUDA or C++ types cross this boundary.
+ *
+ * The library renders N independent instances of one reference processor for
+ * F frames per call ("N instances x F frames").  Every processor keeps the
+ * reference's state / param / input / output record layouts, so a host that
+ * owns reference structs uploads them as they are (base pointer + stride).
+ *
+ *   reference interface                         entry point that replaces it
+ *   ------------------------------------------  -----------------------------
+ *   NAME_update(state*,config*,param*,input*)   cproc_cuda_alloc + _run
+ *     generic/cproc.h:89-95
+ *   void cproc_update(w *input, w changed)      CPROC_CUDA_GRAPH batch
+ *     linux/test_cproc.c:13-17,
+ *     stm32f103/mod_cproc_plugin.c:20-38
+ *   uint32_t pdmK_update(struct pdmK*, in,      CPROC_CUDA_PDM batch
+ *     out_shift[, dither]) stm32f103/pdm.h:13-77
+ *   pdm_channels_update / channel_update_dither CPROC_CUDA_PDM_V1 batch
+ *     stm32f103/mod_pdm.c:230-264
+ *   HW_TIM_ISR(TIM_PDM) + control_update        CPROC_CUDA_PDM_V2 batch
+ *     stm32f103/mod_pdm_pwm.c:123-143,
+ *     stm32f103/mod_controlrate.c:28-57
+ *   pwm_update  stm32f103/mod_pdm.c:167-175     CPROC_CUDA_PWM batch
+ *   synth_run / sum_tick_saw / sum_tick_square  CPROC_CUDA_VOICE_BANK batch
+ *     linux/synth.c:169-202
+ *   square_grain_proc linux/synth_tools.c:85-100 CPROC_CUDA_SQUARE_GRAIN batch
+ *
+ * The reference hot path is `void` and cannot fail; its surroundings return
+ * int 0 / negative (stm32f103/mod_synth.c:89-137).  Every function here
+ * returns 0 or a negative CPROC_CUDA_E* code and never aborts.  There is no
+ * CPU fallback: without a CUDA device cproc_cuda_open fails with
+ * CPROC_CUDA_ENODEV.
+ *
+ * Threading: like the reference (one JACK RT thread / one ISR per graph), a
+ * context and its batches have a single caller at a time.
+ */
+#ifndef CPROC_CUDA_H
+#define CPROC_CUDA_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPROC_CUDA_ABI_VERSION 1
+
+/* ---- error codes -------------------------------------------------------- */
+#define CPROC_CUDA_OK        0
+#define CPROC_CUDA_EINVAL   (-1)  /* bad argument / unsupported combination   */
+#define CPROC_CUDA_ENODEV   (-2)  /* no usable CUDA device                    */
+#define CPROC_CUDA_ENOMEM   (-3)  /* device or pinned-host allocation failed  */
+#define CPROC_CUDA_ECUDA    (-4)  /* CUDA runtime error (see _last_error)     */
+#define CPROC_CUDA_ESTATE   (-5)  /* call order violated (e.g. run w/o state) */
+
+typedef struct cproc_cuda_ctx   cproc_cuda_ctx;    /* one device + stream   */
+typedef struct cproc_cuda_batch cproc_cuda_batch;  /* N instances of a proc */
+
+/* ---- processors --------------------------------------------------------- */
+enum cproc_cuda_proc {
+    /* Generated cproc graph of acc/edge nodes == cproc_update(w *input, w
+     * changed).  state record: node states concatenated in ANF order
+     * (acc_state {w out}, edge_state {w out; w last}; cproc.h:134,145).
+     * in:  uint32 [inst][n_inputs][F]; in2: changed mask uint32 [inst][F] or
+     * NULL (= -1, mod_cproc_plugin.c:32); out: uint32 [inst][F], the value
+     * passed to cproc_output() each tick (test_cproc.c:16). */
+    CPROC_CUDA_GRAPH = 1,
+    /* pdmK_update, K = cfg.order (pdm.h).  state record: struct pdmK.
+     * param record: {uint32 input} used when in == NULL.  in: uint32
+     * [inst][F] or NULL; in2: dither uint32 [F] shared by all instances or
+     * NULL (0); out: uint32 [inst][F] quantiser output. */
+    CPROC_CUDA_PDM = 2,
+    /* mod_pdm.c v1 carry-bit PDM.  state record: struct channel {uint32
+     * setpoint; uint32 accu} (mod_pdm.c:198-201).  Banks of cfg.bank_size
+     * channels share one dither word per tick (mod_pdm.c:261):
+     * dither = (in2 ? in2[bank][t] : xorshift32(&prng[bank])) & dither_mask.
+     * out: packed bits, uint32 words, sample t at bit (t & 31) of word t>>5:
+     * PLANAR [ch][F/32], INTERLEAVED [F/32][ch].  F % 32 == 0. */
+    CPROC_CUDA_PDM_V1 = 3,
+    /* mod_pdm_pwm.c v2 (glide + pdmK + control-rate line).  state record:
+     * struct channel {uint32 setpoint; struct line {uint32 position; int32
+     * velocity} line[2]; struct pdmK pdm} (mod_pdm_pwm.c:80-93) = 5+K words.
+     * ctl: setpoints uint32 [n_ctl][ch] (one row latched at every control
+     * boundary met during the run, before the line copy) or NULL.
+     * in2: external dither uint32 [bank][F] or NULL (xorshift32 per bank).
+     * out: uint8 duty.  PLANAR [ch][F], TILED [F/16][ch][16]. */
+    CPROC_CUDA_PDM_V2 = 4,
+    /* pwm_update (mod_pdm.c:167-175).  state {uint32 phase}; param {uint32
+     * speed}; out uint8 duty [inst][F]. */
+    CPROC_CUDA_PWM = 5,
+    /* linux/synth.c voice bank.  state record: struct voice {uint32 note_inc;
+     * uint32 note_state} (synth.c:33-36).  Consecutive groups of
+     * cfg.voices_per_bus voices feed one bus (reference: 64, synth.c:39).
+     * cfg.mode: CPROC_CUDA_MIX_SAW (sum_tick_saw) / _SQUARE.
+     * out: float [bus][F] (what synth_run writes to vec); mix: int32
+     * [bus][F] raw integer mix before the float scale (synth.c:171,184) --
+     * the buffer a multi-GPU host all-reduces.  Either may be NULL. */
+    CPROC_CUDA_VOICE_BANK = 6,
+    /* square_grain_proc (synth_tools.c:85-100).  state {float state}; param
+     * {float threshold}; in/out float [inst][F]; in may alias out. */
+    CPROC_CUDA_SQUARE_GRAIN = 7,
+    /* square_grain fed by a per-grain phasor (acc -> signed saw) and mixed
+     * to stereo with dyadic pan gains k/64, integer mix in units of 2^-7.
+     * state {float state; uint32 phase}; param {float threshold; uint32 inc;
+     * uint32 gl; uint32 gr}; out float [2][F]; mix int32 [2][F]. */
+    CPROC_CUDA_SQUARE_GRAIN_MIX = 8,
+    /* Extension voice (not in the reference): phasor -> Chamberlin SVF ->
+     * linear AR envelope -> pan.  state {uint32 phase; float lp, bp, env;
+     * uint32 t}; param {uint32 inc; float f, q, env_attack, env_release;
+     * uint32 gate_frames; float gl, gr}.  out: raw float [inst][F][2]
+     * (PLANAR) / [F/2][inst][2][2] (TILED) or NULL; mix: float [2][F] or NULL. */
+    CPROC_CUDA_XVOICE = 9,
+    /* one-pole low-pass y += a*(x-y) (extension).  state {float y}; param
+     * {float a}; in/out float [inst][F]. */
+    CPROC_CUDA_ONEPOLE = 10
+};
+
+enum { CPROC_CUDA_NODE_ACC = 0, CPROC_CUDA_NODE_EDGE = 1 };
+enum { CPROC_CUDA_MIX_SAW = 0, CPROC_CUDA_MIX_SQUARE = 1 };
+
+/* Stream layouts (per-instance streams `x[inst][frame]`). */
+enum {
+    CPROC_CUDA_PLANAR = 0,      /* [inst][F]: what the reference hosts hand over
+                                   (float *vec, t_float *in/out)              */
+    CPROC_CUDA_INTERLEAVED = 1, /* [F][inst]: voice-interleaved frames        */
+    CPROC_CUDA_TILED = 2        /* [F/T][inst][T], T*elem = 16 bytes: native,
+                                   one 128-bit store per thread               */
+};
+
+/* One PROC_COND statement of a generated graph (cproc.h:72-77). */
+typedef struct {
+    uint32_t type;       /* CPROC_CUDA_NODE_*                                */
+    int32_t  src;        /* >=0: .in = n<src>.out; <0: .in = input[-(src+1)] */
+    uint32_t cond_mask;  /* node runs iff (changed & cond_mask) != 0         */
+} cproc_cuda_node;
+
+typedef struct {
+    uint32_t proc;            /* enum cproc_cuda_proc                        */
+    uint32_t layout;          /* default stream layout for in/out            */
+    /* PDM family */
+    uint32_t order;           /* 1..4  (PDM_ORDER, mod_pdm_pwm.c:85)         */
+    uint32_t out_shift;       /* 32 - PDM_DIV_LOG = 24 (mod_pdm_pwm.c:115)   */
+    uint32_t bank_size;       /* channels sharing one dither word per tick   */
+    uint32_t dither_mask;     /* 0x3FF (mod_pdm_pwm.c:127) / 0x0FFFFFFF (mod_pdm.c:261) */
+    uint32_t ctl_div_log;     /* CONTROL_DIV_LOG = 12 (mod_pdm_pwm.c:76)     */
+    /* voice bank */
+    uint32_t mode;            /* CPROC_CUDA_MIX_*                            */
+    uint64_t voices_per_bus;  /* 0 = all instances on one bus                */
+    /* graph */
+    const cproc_cuda_node *nodes;
+    uint32_t n_nodes, n_inputs, out_node;
+    uint32_t reserved;
+} cproc_cuda_config;
+
+/* Buffers of one run.  Host pointers for cproc_cuda_run, device pointers for
+ * cproc_cuda_run_dev.  Unused members are NULL. */
+typedef struct {
+    const void *in;     /* per-instance input stream                        */
+    const void *in2;    /* second input: changed mask / dither              */
+    const void *ctl;    /* control-rate input rows (setpoints)              */
+    void       *out;    /* per-instance (or per-bus) output stream          */
+    void       *mix;    /* mix bus                                          */
+    uint32_t    layout; /* CPROC_CUDA_* layout of in/out for this run       */
+    uint32_t    n_ctl;  /* rows available in ctl                            */
+} cproc_cuda_io;
+
+/* ---- context ------------------------------------------------------------ */
+/* stream: a cudaStream_t the caller owns (e.g. the host framework's current
+ * stream) or NULL to let the context create its own. */
+int  cproc_cuda_open(int device, void *stream, cproc_cuda_ctx **ctx);
+int  cproc_cuda_close(cproc_cuda_ctx *ctx);
+int  cproc_cuda_sync(cproc_cuda_ctx *ctx);
+/* Last error text of this context (ctx may be NULL: process-wide last). */
+const char *cproc_cuda_last_error(const cproc_cuda_ctx *ctx);
+int  cproc_cuda_abi_version(void);
+int  cproc_cuda_device_count(void);
+/* Number of kernels this context has launched (bench accounting). */
+uint64_t cproc_cuda_launch_count(const cproc_cuda_ctx *ctx);
+
+/* ---- batches ------------------------------------------------------------ */
+int  cproc_cuda_alloc(cproc_cuda_ctx *ctx, const cproc_cuda_config *cfg,
+                      uint64_t n_instances, cproc_cuda_batch **batch);
+int  cproc_cuda_free(cproc_cuda_batch *batch);
+/* Bytes of one state / param record as laid out by the reference. */
+size_t cproc_cuda_state_bytes(const cproc_cuda_batch *batch);
+size_t cproc_cuda_param_bytes(const cproc_cuda_batch *batch);
+/* Records are read/written at `aos + i*stride` (stride 0 = packed).  State
+ * starts zeroed (cproc.h:65-66).  These are the checkpoint/resume calls. */
+int  cproc_cuda_upload_state(cproc_cuda_batch *b, const void *aos, size_t stride);
+int  cproc_cuda_download_state(cproc_cuda_batch *b, void *aos, size_t stride);
+int  cproc_cuda_upload_param(cproc_cuda_batch *b, const void *aos, size_t stride);
+/* Per-bank dither PRNG words (n_banks = ceil(N / bank_size)) and the shared
+ * control divider counter (control_div_count, mod_pdm_pwm.c:78). */
+int  cproc_cuda_upload_bank(cproc_cuda_batch *b, const uint32_t *prng, uint32_t count);
+int  cproc_cuda_download_bank(cproc_cuda_batch *b, uint32_t *prng, uint32_t *count);
+
+/* Render F frames.  _run: host buffers, synchronous (copies in, renders,
+ * copies out, returns when `out` is valid) -- the drop-in path.
+ * _run_dev: device buffers, asynchronous on the context stream. */
+int  cproc_cuda_run(cproc_cuda_batch *b, uint64_t n_frames, const cproc_cuda_io *io);
+int  cproc_cuda_run_dev(cproc_cuda_batch *b, uint64_t n_frames, const cproc_cuda_io *io);
+/* Long renders into host memory: F_total frames in chunks of F_chunk, the
+ * device->host copy of chunk k overlapped with the render of chunk k+1.
+ * io->out is a PINNED host buffer (cproc_cuda_host_alloc) of `ring_chunks`
+ * slabs, each one chunk in io->layout with F = F_chunk; chunk k lands in slab
+ * k % ring_chunks.  ring_chunks == 0 means one slab per chunk (the whole
+ * render is kept).  `on_chunk` (may be NULL) is called on the calling thread
+ * once chunk k is in host memory -- the equivalent of the JACK process
+ * callback handing over a period -- and must be done with the slab when it
+ * returns.  ring_chunks must be 0 or >= 2.  Synchronous. */
+typedef void (*cproc_cuda_chunk_fn)(void *user, uint64_t chunk_index, const void *slab, size_t slab_bytes);
+int  cproc_cuda_run_stream(cproc_cuda_batch *b, uint64_t n_frames_total,
+                           uint64_t n_frames_chunk, const cproc_cuda_io *io,
+                           uint32_t ring_chunks, cproc_cuda_chunk_fn on_chunk, void *user);
+/* Integer mix bus -> float, after a multi-GPU all-reduce of the raw mix:
+ * VOICE_BANK saw: (float)(int)x * 2^-32 (synth.c:180); square: (float)(unsigned)x
+ * * 2^-32 (:194); SQUARE_GRAIN_MIX: (float)x * 2^-7.  Device pointers. */
+int  cproc_cuda_mix_to_float(cproc_cuda_batch *b, const void *imix_dev, float *out_dev, uint64_t count);
+
+/* ---- memory + timing helpers (plumbing for C hosts) ---------------------- */
+int  cproc_cuda_dev_alloc(cproc_cuda_ctx *ctx, size_t bytes, void **dev);
+int  cproc_cuda_dev_free(cproc_cuda_ctx *ctx, void *dev);
+int  cproc_cuda_host_alloc(cproc_cuda_ctx *ctx, size_t bytes, void **pinned);
+int  cproc_cuda_host_free(cproc_cuda_ctx *ctx, void *pinned);
+int  cproc_cuda_memcpy_h2d(cproc_cuda_ctx *ctx, void *dev, const void *host, size_t bytes);
+int  cproc_cuda_memcpy_d2h(cproc_cuda_ctx *ctx, void *host, const void *dev, size_t bytes);
+int  cproc_cuda_memset(cproc_cuda_ctx *ctx, void *dev, int value, size_t bytes);
+/* CUDA-event stopwatch on the context stream. */
+int  cproc_cuda_timer_start(cproc_cuda_ctx *ctx);
+int  cproc_cuda_timer_stop(cproc_cuda_ctx *ctx, float *elapsed_ms);
+/* Tuning knob (block size etc.) by name; unknown names return EINVAL. */
+int  cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPROC_CUDA_H */

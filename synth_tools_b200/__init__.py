@@ -1,0 +1,16 @@
+"""synth_tools_b200 -- B200-native batched renderer for the synth_tools
+per-sample DSP hot path (cproc graphs, PDM modulators, phasor voice bank,
+square_grain).  The product is libcproc_cuda.so behind include/cproc_cuda.h;
+this package is the thin Python host binding over that C-ABI.
+
+Importing the package loads the CUDA library and fails loudly when it has not
+been built: there is no CPU fallback.
+"""
+from . import abi  # noqa: F401  (raises ImportError if libcproc_cuda.so is missing)
+from .abi import (Batch, Context, CprocCudaError, GRAPH, INTERLEAVED, MIX_SAW, MIX_SQUARE, NODE_ACC, NODE_EDGE,
+                  ONEPOLE, PDM, PDM_V1, PDM_V2, PLANAR, PWM, SQUARE_GRAIN, SQUARE_GRAIN_MIX, TILED, VOICE_BANK,
+                  XVOICE)
+
+__all__ = ["abi", "Batch", "Context", "CprocCudaError", "GRAPH", "PDM", "PDM_V1", "PDM_V2", "PWM", "VOICE_BANK",
+           "SQUARE_GRAIN", "SQUARE_GRAIN_MIX", "XVOICE", "ONEPOLE", "NODE_ACC", "NODE_EDGE", "MIX_SAW",
+           "MIX_SQUARE", "PLANAR", "INTERLEAVED", "TILED"]

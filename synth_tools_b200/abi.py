@@ -1,0 +1,257 @@
+"""ctypes binding of include/cproc_cuda.h (libcproc_cuda.so).
+
+This is plumbing for tests, bench.py and Python hosts; the product is the
+shared library.  There is no CPU fallback anywhere: if the library is missing
+the import fails, and without a CUDA device `Context()` raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcproc_cuda.so")
+
+# enum cproc_cuda_proc
+GRAPH, PDM, PDM_V1, PDM_V2, PWM, VOICE_BANK, SQUARE_GRAIN, SQUARE_GRAIN_MIX, XVOICE, ONEPOLE = range(1, 11)
+NODE_ACC, NODE_EDGE = 0, 1
+MIX_SAW, MIX_SQUARE = 0, 1
+PLANAR, INTERLEAVED, TILED = 0, 1, 2
+OK, EINVAL, ENODEV, ENOMEM, ECUDA, ESTATE = 0, -1, -2, -3, -4, -5
+
+
+class Node(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("src", C.c_int32), ("cond_mask", C.c_uint32)]
+
+
+class Config(C.Structure):
+    _fields_ = [("proc", C.c_uint32), ("layout", C.c_uint32), ("order", C.c_uint32), ("out_shift", C.c_uint32),
+                ("bank_size", C.c_uint32), ("dither_mask", C.c_uint32), ("ctl_div_log", C.c_uint32),
+                ("mode", C.c_uint32), ("voices_per_bus", C.c_uint64), ("nodes", C.POINTER(Node)),
+                ("n_nodes", C.c_uint32), ("n_inputs", C.c_uint32), ("out_node", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class IO(C.Structure):
+    _fields_ = [("in_", C.c_void_p), ("in2", C.c_void_p), ("ctl", C.c_void_p), ("out", C.c_void_p),
+                ("mix", C.c_void_p), ("layout", C.c_uint32), ("n_ctl", C.c_uint32)]
+
+
+CHUNK_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t)
+
+# name -> (restype, argtypes): every symbol include/cproc_cuda.h declares
+SYMBOLS = {
+    "cproc_cuda_open": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cproc_cuda_close": (C.c_int, [C.c_void_p]),
+    "cproc_cuda_sync": (C.c_int, [C.c_void_p]),
+    "cproc_cuda_last_error": (C.c_char_p, [C.c_void_p]),
+    "cproc_cuda_abi_version": (C.c_int, []),
+    "cproc_cuda_device_count": (C.c_int, []),
+    "cproc_cuda_launch_count": (C.c_uint64, [C.c_void_p]),
+    "cproc_cuda_alloc": (C.c_int, [C.c_void_p, C.POINTER(Config), C.c_uint64, C.POINTER(C.c_void_p)]),
+    "cproc_cuda_free": (C.c_int, [C.c_void_p]),
+    "cproc_cuda_state_bytes": (C.c_size_t, [C.c_void_p]),
+    "cproc_cuda_param_bytes": (C.c_size_t, [C.c_void_p]),
+    "cproc_cuda_upload_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cproc_cuda_download_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cproc_cuda_upload_param": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cproc_cuda_upload_bank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "cproc_cuda_download_bank": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
+    "cproc_cuda_run": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(IO)]),
+    "cproc_cuda_run_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(IO)]),
+    "cproc_cuda_run_stream": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(IO), C.c_uint32, CHUNK_FN, C.c_void_p]),
+    "cproc_cuda_mix_to_float": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "cproc_cuda_dev_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "cproc_cuda_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cproc_cuda_host_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "cproc_cuda_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cproc_cuda_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cproc_cuda_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cproc_cuda_memset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
+    "cproc_cuda_timer_start": (C.c_int, [C.c_void_p]),
+    "cproc_cuda_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "cproc_cuda_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+}
+
+
+class CprocCudaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("cproc_cuda error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load(path=LIB_PATH):
+    if not os.path.exists(path):
+        raise ImportError("%s is missing: build it with `python -m synth_tools_b200.build` "
+                          "(there is no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        f = getattr(lib, name)          # AttributeError if the ABI symbol is missing
+        f.restype = res
+        f.argtypes = args
+    return lib
+
+
+lib = load()
+
+
+def _vp(a):
+    """numpy array / int device pointer / None -> c_void_p value."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return int(a)
+
+
+class Context:
+    """cproc_cuda_ctx: one device + stream."""
+
+    def __init__(self, device=0, stream=None):
+        h = C.c_void_p()
+        rc = lib.cproc_cuda_open(device, stream, C.byref(h))
+        if rc:
+            raise CprocCudaError(rc, (lib.cproc_cuda_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+
+    def _ck(self, rc):
+        if rc:
+            raise CprocCudaError(rc, (lib.cproc_cuda_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if self.h:
+            lib.cproc_cuda_close(self.h)
+            self.h = None
+
+    def sync(self):
+        self._ck(lib.cproc_cuda_sync(self.h))
+
+    def set_option(self, name, value):
+        self._ck(lib.cproc_cuda_set_option(self.h, name.encode(), int(value)))
+
+    @property
+    def launches(self):
+        return lib.cproc_cuda_launch_count(self.h)
+
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._ck(lib.cproc_cuda_dev_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def dev_free(self, p):
+        self._ck(lib.cproc_cuda_dev_free(self.h, p))
+
+    def host_alloc(self, nbytes, dtype=np.uint8):
+        """Pinned host buffer as a numpy array (keeps the raw pointer in .base_ptr)."""
+        p = C.c_void_p()
+        self._ck(lib.cproc_cuda_host_alloc(self.h, nbytes, C.byref(p)))
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        a = np.frombuffer(buf, dtype=np.uint8).view(dtype)
+        return a, p.value
+
+    def host_free(self, p):
+        self._ck(lib.cproc_cuda_host_free(self.h, p))
+
+    def h2d(self, dev, arr):
+        self._ck(lib.cproc_cuda_memcpy_h2d(self.h, dev, _vp(arr), arr.nbytes))
+
+    def d2h(self, arr, dev):
+        self._ck(lib.cproc_cuda_memcpy_d2h(self.h, _vp(arr), dev, arr.nbytes))
+
+    def memset(self, dev, value, nbytes):
+        self._ck(lib.cproc_cuda_memset(self.h, dev, value, nbytes))
+
+    def timer_start(self):
+        self._ck(lib.cproc_cuda_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(lib.cproc_cuda_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def batch(self, proc, n, **kw):
+        return Batch(self, proc, n, **kw)
+
+
+class Batch:
+    """cproc_cuda_batch: N instances of one reference processor."""
+
+    def __init__(self, ctx, proc, n, layout=PLANAR, order=2, out_shift=24, bank_size=1, dither_mask=0x3FF,
+                 ctl_div_log=12, mode=MIX_SAW, voices_per_bus=0, nodes=None, n_inputs=1, out_node=None):
+        self.ctx = ctx
+        cfg = Config()
+        cfg.proc, cfg.layout, cfg.order, cfg.out_shift = proc, layout, order, out_shift
+        cfg.bank_size, cfg.dither_mask, cfg.ctl_div_log = bank_size, dither_mask, ctl_div_log
+        cfg.mode, cfg.voices_per_bus = mode, voices_per_bus
+        self._nodes = None
+        if nodes is not None:
+            arr = (Node * len(nodes))(*[Node(t, s, m) for t, s, m in nodes])
+            self._nodes = arr
+            cfg.nodes = arr
+            cfg.n_nodes = len(nodes)
+            cfg.n_inputs = n_inputs
+            cfg.out_node = len(nodes) - 1 if out_node is None else out_node
+        h = C.c_void_p()
+        ctx._ck(lib.cproc_cuda_alloc(ctx.h, C.byref(cfg), n, C.byref(h)))
+        self.h = h
+        self.n = n
+        self.proc = proc
+        self.layout = layout
+        self.state_bytes = lib.cproc_cuda_state_bytes(h)
+        self.param_bytes = lib.cproc_cuda_param_bytes(h)
+        self.bank_size = min(bank_size, n)
+        self.n_banks = (n + self.bank_size - 1) // self.bank_size
+
+    def free(self):
+        if self.h:
+            lib.cproc_cuda_free(self.h)
+            self.h = None
+
+    def upload_state(self, aos, stride=0):
+        self.ctx._ck(lib.cproc_cuda_upload_state(self.h, _vp(aos), stride))
+
+    def download_state(self, aos=None, stride=0):
+        if aos is None:
+            aos = np.zeros((self.n, self.state_bytes // 4), np.uint32)
+        self.ctx._ck(lib.cproc_cuda_download_state(self.h, _vp(aos), stride))
+        return aos
+
+    def upload_param(self, aos, stride=0):
+        self.ctx._ck(lib.cproc_cuda_upload_param(self.h, _vp(aos), stride))
+
+    def upload_bank(self, prng=None, count=0):
+        self.ctx._ck(lib.cproc_cuda_upload_bank(self.h, _vp(prng), count))
+
+    def download_bank(self):
+        prng = np.zeros(self.n_banks, np.uint32)
+        cnt = C.c_uint32()
+        self.ctx._ck(lib.cproc_cuda_download_bank(self.h, _vp(prng), C.byref(cnt)))
+        return prng, cnt.value
+
+    def _io(self, inp, in2, ctl, out, mix, layout, n_ctl):
+        io = IO()
+        io.in_, io.in2, io.ctl, io.out, io.mix = _vp(inp), _vp(in2), _vp(ctl), _vp(out), _vp(mix)
+        io.layout = self.layout if layout is None else layout
+        if n_ctl is None:
+            n_ctl = ctl.shape[0] if isinstance(ctl, np.ndarray) else 0
+        io.n_ctl = n_ctl
+        return io
+
+    def run(self, F, inp=None, in2=None, ctl=None, out=None, mix=None, layout=None, n_ctl=None):
+        """Host buffers (numpy), synchronous."""
+        io = self._io(inp, in2, ctl, out, mix, layout, n_ctl)
+        self.ctx._ck(lib.cproc_cuda_run(self.h, F, C.byref(io)))
+
+    def run_dev(self, F, inp=None, in2=None, ctl=None, out=None, mix=None, layout=None, n_ctl=0):
+        """Device pointers (ints), asynchronous on the context stream."""
+        io = self._io(inp, in2, ctl, out, mix, layout, n_ctl)
+        self.ctx._ck(lib.cproc_cuda_run_dev(self.h, F, C.byref(io)))
+
+    def run_stream(self, F_total, F_chunk, out, ctl=None, layout=None, n_ctl=None, ring_chunks=0, on_chunk=None):
+        io = self._io(None, None, ctl, out, None, layout, n_ctl)
+        cb = CHUNK_FN(on_chunk) if on_chunk is not None else C.cast(None, CHUNK_FN)
+        self.ctx._ck(lib.cproc_cuda_run_stream(self.h, F_total, F_chunk, C.byref(io), ring_chunks, cb, None))
+
+    def mix_to_float(self, imix_dev, out_dev, count):
+        self.ctx._ck(lib.cproc_cuda_mix_to_float(self.h, imix_dev, out_dev, count))

@@ -1,0 +1,94 @@
+// common.cuh -- shared internals of libcproc_cuda (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/cproc_cuda.h"
+
+#define CPROC_N_SM 148  // B200
+
+struct cproc_cuda_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;      // render stream (caller's or ours)
+    cudaStream_t copy_stream = nullptr; // D2H overlap in run_stream
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    // tuning knobs (cproc_cuda_set_option)
+    int pdm_block = 64;       // threads per block of the PDM kernels
+    int pdm_tpb = 1;          // 1: thread-per-bank when bank_size <= 4, 0: thread-per-channel
+    int pdm_stage = 1;        // 1: smem-staged full-line stores for PLANAR
+    int voice_block = 256;
+    int grain_block = 128;
+    int xvoice_block = 128;
+};
+
+struct cproc_cuda_batch {
+    cproc_cuda_ctx *ctx = nullptr;
+    cproc_cuda_config cfg{};
+    std::vector<cproc_cuda_node> nodes;     // copy of cfg.nodes
+    std::vector<uint32_t> node_off;         // state word offset per node
+    uint64_t n = 0;                         // instances
+    uint64_t npad = 0;                      // SoA row length (>= n)
+    uint64_t n_banks = 0;
+    uint64_t n_bus = 0;
+    uint32_t state_words = 0, param_words = 0;
+    uint32_t *d_state = nullptr;            // [state_words][npad]
+    uint32_t *d_param = nullptr;            // [param_words][npad]
+    uint32_t *d_prng = nullptr;             // [n_banks]
+    cproc_cuda_node *d_nodes = nullptr;
+    uint32_t count = 0;                     // control_div_count
+    // staging for host-buffer runs (grown on demand)
+    void *d_in = nullptr, *d_in2 = nullptr, *d_ctl = nullptr, *d_out = nullptr, *d_mix = nullptr;
+    size_t cap_in = 0, cap_in2 = 0, cap_ctl = 0, cap_out = 0, cap_mix = 0;
+    void *d_out2 = nullptr; size_t cap_out2 = 0;   // second slab for run_stream
+};
+
+int cproc_set_err(cproc_cuda_ctx *ctx, int code, const char *fmt, ...);
+int cproc_check(cproc_cuda_ctx *ctx, cudaError_t e, const char *what);
+
+#define CK(ctx, call) do { int _rc = cproc_check((ctx), (call), #call); if (_rc) return _rc; } while (0)
+#define CK_LAUNCH(ctx, name) do { (ctx)->launches++; int _rc = cproc_check((ctx), cudaGetLastError(), name); if (_rc) return _rc; } while (0)
+
+static inline uint64_t ceil_div_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// Element sizes / stream sizes per processor (bytes for F frames).
+struct cproc_io_sizes { size_t in, in2, ctl, out, mix; };
+int cproc_io_bytes(const cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io, cproc_io_sizes *s);
+
+// Kernel launchers (one translation unit per family).
+int launch_graph(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
+int launch_pdm(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
+int launch_pdm_v1(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
+int launch_pdm_v2(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
+int launch_pwm(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
+int launch_voice_bank(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
+int launch_square_grain(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
+int launch_square_grain_mix(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
+int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
+int launch_onepole(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
+
+// small conversion kernels shared across translation units
+__global__ void k_imix_to_float(const int32_t *imix, float *mix, uint64_t count, float scale);
+__global__ void k_voice_finish(const int32_t *isum, float *vec, uint64_t count, uint32_t mode);
+
+// ---- device helpers -------------------------------------------------------
+__device__ __forceinline__ uint32_t xorshift32_step(uint32_t x) {
+    // uc_tools random_u32 stand-in (parity unpinned): Marsaglia (13,17,5)
+    x ^= x << 13;
+    x ^= x >> 17;
+    x ^= x << 5;
+    return x;
+}
+
+__device__ __forceinline__ void st_v4_stream(void *p, uint4 v) {
+    // write-once output streams: keep them out of L1, evict-first in L2
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_v4_stream(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}

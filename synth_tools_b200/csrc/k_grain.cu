@@ -1,0 +1,177 @@
+// k_grain.cu -- square_grain~ (linux/synth_tools.c:85-100): a Schmitt-trigger
+// squarer with a one-sample output delay.
+//
+//   out[i] = state;
+//   if (state >= 0 && in[i] < -thresh) state = -0.5f;
+//   else if (state < 0 && in[i] > thresh) state = +0.5f;
+//
+// Outputs are exactly {0, +0.5, -0.5}, so the result is bit-exact.  The
+// hysteresis makes the recurrence a 3-state machine that is serial in time;
+// the grain axis carries the parallelism (one thread per grain).
+//
+// k_grain_planar: hosts hand over planar [grain][F] vectors.  A warp owns 32
+//   grains and walks the frame axis in 32-frame tiles: the tile is loaded with
+//   32 coalesced 128-byte row reads into padded shared memory, each lane then
+//   runs its own grain along its row IN PLACE (in may alias out, as in Pd),
+//   and the tile is written back with 32 coalesced row stores.
+// k_grain_interleaved: [F][grain] streams are already coalesced.
+// k_grain_mix: config C3b -- input from a per-grain phasor, integer stereo mix.
+#include "common.cuh"
+
+struct GrainParams {
+    float *state;            // SoA [1][npad]
+    const float *thresh;     // SoA [1][npad]
+    uint64_t n, F;
+    const float *in;
+    float *out;
+};
+
+__device__ __forceinline__ float grain_step(float &state, float val, float thresh) {
+    const float o = state;                                   // :91
+    if (state >= 0.0f && val < -thresh) state = -0.5f;       // :92-94
+    else if (state < 0.0f && val > thresh) state = 0.5f;     // :95-97
+    return o;
+}
+
+#define GRAIN_WARPS 4
+__global__ void __launch_bounds__(GRAIN_WARPS * 32) k_grain_planar(const GrainParams p) {
+    __shared__ float tile[GRAIN_WARPS][32][33];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t g0 = ((uint64_t)blockIdx.x * GRAIN_WARPS + warp) * 32;
+    if (g0 >= p.n) return;
+    const uint32_t rows = p.n - g0 < 32 ? (uint32_t)(p.n - g0) : 32u;
+    float (*tl)[33] = tile[warp];
+    const bool mine = lane < rows;
+    float state = mine ? p.state[g0 + lane] : 0.0f;
+    const float th = mine ? p.thresh[g0 + lane] : 0.0f;
+    for (uint64_t t0 = 0; t0 < p.F; t0 += 32) {
+        const uint32_t cols = p.F - t0 < 32 ? (uint32_t)(p.F - t0) : 32u;
+        if (lane < cols)
+            for (uint32_t r = 0; r < rows; ++r) tl[r][lane] = __ldcs(p.in + (g0 + r) * p.F + t0 + lane);
+        __syncwarp();
+        if (mine)
+            for (uint32_t i = 0; i < cols; ++i) tl[lane][i] = grain_step(state, tl[lane][i], th);
+        __syncwarp();
+        if (lane < cols)
+            for (uint32_t r = 0; r < rows; ++r) __stcs(p.out + (g0 + r) * p.F + t0 + lane, tl[r][lane]);
+        __syncwarp();
+    }
+    if (mine) p.state[g0 + lane] = state;
+}
+
+__global__ void k_grain_interleaved(const GrainParams p) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.n) return;
+    float state = p.state[g];
+    const float th = p.thresh[g];
+    for (uint64_t t = 0; t < p.F; ++t) {
+        const float v = __ldcs(p.in + t * p.n + g);
+        __stcs(p.out + t * p.n + g, grain_step(state, v, th));
+    }
+    p.state[g] = state;
+}
+
+int launch_square_grain(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
+    cproc_cuda_ctx *ctx = b->ctx;
+    if (!io->in || !io->out) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "square_grain: in/out is NULL");
+    if (io->layout == CPROC_CUDA_TILED) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "square_grain: TILED layout not supported");
+    if (F == 0) return 0;
+    GrainParams p;
+    p.state = (float *)b->d_state; p.thresh = (const float *)b->d_param; p.n = b->n; p.F = F;
+    p.in = (const float *)io->in; p.out = (float *)io->out;
+    if (io->layout == CPROC_CUDA_INTERLEAVED)
+        k_grain_interleaved<<<(unsigned)ceil_div_u64(p.n, 128), 128, 0, ctx->stream>>>(p);
+    else
+        k_grain_planar<<<(unsigned)ceil_div_u64(p.n, GRAIN_WARPS * 32), GRAIN_WARPS * 32, 0, ctx->stream>>>(p);
+    CK_LAUNCH(ctx, "k_grain");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// C3b: per-grain phasor input, dyadic pan, integer stereo mix (units of 2^-7).
+struct GrainMixParams {
+    uint32_t *st;            // SoA [2][npad]: state (float bits), phase
+    const uint32_t *prm;     // SoA [4][npad]: threshold (float bits), inc, gl, gr
+    uint64_t npad, n, F;
+    int32_t *imix;           // [2][F], zeroed by the launcher
+};
+
+#define GMIX_BLOCK 256
+#define GMIX_CHUNK 32
+__global__ void __launch_bounds__(GMIX_BLOCK) k_grain_mix(const GrainMixParams p) {
+    // Each lane keeps one grain in registers.  Left and right gains (0..64) are
+    // packed into one word so one REDUX.SUM per frame reduces both channels
+    // over the warp; warp sums are accumulated per block in shared memory and
+    // flushed to the global integer mix once per chunk of frames.
+    __shared__ int32_t acc[2][GMIX_CHUNK];
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool mine = g < p.n;
+    const uint32_t lane = threadIdx.x & 31;
+    float state = 0.0f, th = 0.0f;
+    uint32_t ph = 0, inc = 0;
+    int32_t pk = 0;
+    if (mine) {
+        state = __uint_as_float(p.st[g]); ph = p.st[p.npad + g];
+        th = __uint_as_float(p.prm[g]); inc = p.prm[p.npad + g];
+        pk = (int32_t)((p.prm[3 * p.npad + g] << 16) + p.prm[2 * p.npad + g]);
+    }
+    for (uint64_t t0 = 0; t0 < p.F; t0 += GMIX_CHUNK) {
+        if (threadIdx.x < 2 * GMIX_CHUNK) (&acc[0][0])[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t cols = p.F - t0 < GMIX_CHUNK ? (uint32_t)(p.F - t0) : GMIX_CHUNK;
+        int32_t keep = 0;
+        for (uint32_t i = 0; i < cols; ++i) {
+            const float val = __int2float_rn((int32_t)ph) * 0x1p-31f;   // acc -> signed saw
+            ph += inc;                                                  // cproc.h:141
+            const float o = grain_step(state, val, th);
+            const int32_t c = o > 0.0f ? pk : (o < 0.0f ? -pk : 0);
+            const int32_t s = __reduce_add_sync(0xFFFFFFFFu, c);
+            if (lane == (i & 31)) keep = s;
+        }
+        if (lane < cols) {
+            const int32_t l = (int32_t)(int16_t)(keep & 0xFFFF);        // |sum L| <= 32*64
+            const int32_t r = (keep - l) >> 16;
+            atomicAdd(&acc[0][lane], l);
+            atomicAdd(&acc[1][lane], r);
+        }
+        __syncthreads();
+        if (threadIdx.x < cols) {
+            atomicAdd(p.imix + t0 + threadIdx.x, acc[0][threadIdx.x]);
+            atomicAdd(p.imix + p.F + t0 + threadIdx.x, acc[1][threadIdx.x]);
+        }
+        __syncthreads();
+    }
+    if (mine) { p.st[g] = __float_as_uint(state); p.st[p.npad + g] = ph; }
+}
+
+__global__ void k_imix_to_float(const int32_t *imix, float *mix, uint64_t count, float scale) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) mix[i] = __int2float_rn(imix[i]) * scale;
+}
+
+int launch_square_grain_mix(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
+    cproc_cuda_ctx *ctx = b->ctx;
+    if (!io->out && !io->mix) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "square_grain_mix: out and mix are both NULL");
+    if (F == 0) return 0;
+    int32_t *imix = (int32_t *)io->mix;
+    if (!imix) {
+        size_t need = sizeof(int32_t) * 2 * F;
+        if (b->cap_mix < need) {
+            if (b->d_mix) cudaFree(b->d_mix);
+            b->d_mix = nullptr; b->cap_mix = 0;
+            CK(ctx, cudaMalloc(&b->d_mix, need));
+            b->cap_mix = need;
+        }
+        imix = (int32_t *)b->d_mix;
+    }
+    CK(ctx, cudaMemsetAsync(imix, 0, sizeof(int32_t) * 2 * F, ctx->stream));
+    GrainMixParams p;
+    p.st = b->d_state; p.prm = b->d_param; p.npad = b->npad; p.n = b->n; p.F = F; p.imix = imix;
+    k_grain_mix<<<(unsigned)ceil_div_u64(p.n, GMIX_BLOCK), GMIX_BLOCK, 0, ctx->stream>>>(p);
+    CK_LAUNCH(ctx, "k_grain_mix");
+    if (io->out) {
+        k_imix_to_float<<<(unsigned)ceil_div_u64(2 * F, 256), 256, 0, ctx->stream>>>(imix, (float *)io->out, 2 * F, 0x1p-7f);
+        CK_LAUNCH(ctx, "k_imix_to_float");
+    }
+    return 0;
+}

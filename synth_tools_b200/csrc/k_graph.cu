@@ -1,0 +1,117 @@
+// k_graph.cu -- generated cproc graphs of acc / edge nodes.
+//
+// Replaces `void cproc_update(w *input, w changed)` (linux/test_cproc.c:13-17,
+// stm32f103/bp5_plugin.c:4-9): a straight-line sequence of PROC_COND
+// statements (generic/cproc.h:72-77), one tick per call, state in
+// function-static structs.  Here: one thread per graph instance, the whole
+// node-state vector in registers across the frame block, the node table in
+// shared memory, F ticks per launch.
+#include "common.cuh"
+
+#define GRAPH_MAX_NODES 16
+#define GRAPH_MAX_STATE 32
+
+struct GraphParams {
+    uint32_t *st;                  // SoA [state_words][npad]
+    uint64_t npad, n;
+    const cproc_cuda_node *nodes;
+    uint32_t n_nodes, n_inputs, out_node, state_words;
+    const uint32_t *in;            // PLANAR [inst][n_inputs][F] / INTERLEAVED [F][n_inputs][inst]
+    const uint32_t *changed;       // [inst][F] / [F][inst] or null
+    uint32_t *out;                 // [inst][F] / [F][inst]
+    uint64_t F;
+    uint32_t layout;
+};
+
+// acc_update (cproc.h:140-142) / edge_update (cproc.h:151-154) on register state
+__device__ __forceinline__ void node_tick(uint32_t type, uint32_t *s, uint32_t x) {
+    if (type == CPROC_CUDA_NODE_EDGE) { s[0] = (x != s[1]); s[1] = x; }
+    else s[0] += x;
+}
+
+// Specialisation for the two graphs the reference ships: edge -> acc [-> acc],
+// all nodes under one mask bit.  DEPTH = number of acc nodes after the edge.
+template <int DEPTH>
+__global__ void k_graph_edge_acc(const GraphParams p, uint32_t mask) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    uint32_t e_out = p.st[i], e_last = p.st[p.npad + i], a[DEPTH];
+#pragma unroll
+    for (int k = 0; k < DEPTH; ++k) a[k] = p.st[(2 + k) * p.npad + i];
+    const bool il = p.layout == CPROC_CUDA_INTERLEAVED;
+    for (uint64_t t = 0; t < p.F; ++t) {
+        const uint64_t idx = il ? t * p.n + i : i * p.F + t;
+        const uint32_t x = p.in[idx];
+        const uint32_t g = p.changed ? p.changed[idx] : 0xFFFFFFFFu;
+        if (g & mask) {
+            e_out = (x != e_last); e_last = x;        // n1 = edge(input[0])
+            a[0] += e_out;                            // n2 = acc(n1.out)
+#pragma unroll
+            for (int k = 1; k < DEPTH; ++k) a[k] += a[k - 1];
+        }
+        p.out[idx] = a[DEPTH - 1];                    // cproc_output(.., nK.out)
+    }
+    p.st[i] = e_out; p.st[p.npad + i] = e_last;
+#pragma unroll
+    for (int k = 0; k < DEPTH; ++k) p.st[(2 + k) * p.npad + i] = a[k];
+}
+
+// General table-driven graph.
+__global__ void k_graph_table(const GraphParams p) {
+    __shared__ cproc_cuda_node nodes[GRAPH_MAX_NODES];
+    __shared__ uint32_t off[GRAPH_MAX_NODES];
+    if (threadIdx.x == 0) {
+        uint32_t o = 0;
+        for (uint32_t k = 0; k < p.n_nodes; ++k) {
+            nodes[k] = p.nodes[k]; off[k] = o;
+            o += nodes[k].type == CPROC_CUDA_NODE_EDGE ? 2u : 1u;
+        }
+    }
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    uint32_t s[GRAPH_MAX_STATE];
+    for (uint32_t w = 0; w < p.state_words; ++w) s[w] = p.st[w * p.npad + i];
+    const bool il = p.layout == CPROC_CUDA_INTERLEAVED;
+    for (uint64_t t = 0; t < p.F; ++t) {
+        const uint64_t oidx = il ? t * p.n + i : i * p.F + t;
+        const uint32_t g = p.changed ? p.changed[oidx] : 0xFFFFFFFFu;
+        for (uint32_t k = 0; k < p.n_nodes; ++k) {
+            if (!(g & nodes[k].cond_mask)) continue;
+            uint32_t x;
+            if (nodes[k].src >= 0) x = s[off[nodes[k].src]];
+            else {
+                const uint32_t j = (uint32_t)(-(nodes[k].src + 1));
+                x = p.in[il ? (t * p.n_inputs + j) * p.n + i : (i * p.n_inputs + j) * p.F + t];
+            }
+            node_tick(nodes[k].type, s + off[k], x);
+        }
+        p.out[oidx] = s[off[p.out_node]];
+    }
+    for (uint32_t w = 0; w < p.state_words; ++w) p.st[w * p.npad + i] = s[w];
+}
+
+int launch_graph(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
+    cproc_cuda_ctx *ctx = b->ctx;
+    if (!io->out || !io->in) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "graph: in/out is NULL");
+    if (io->layout == CPROC_CUDA_TILED) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "graph: TILED layout not supported");
+    if (F == 0) return 0;
+    GraphParams p;
+    p.st = b->d_state; p.npad = b->npad; p.n = b->n; p.nodes = b->d_nodes;
+    p.n_nodes = b->cfg.n_nodes; p.n_inputs = b->cfg.n_inputs; p.out_node = b->cfg.out_node;
+    p.state_words = b->state_words;
+    p.in = (const uint32_t *)io->in; p.changed = (const uint32_t *)io->in2; p.out = (uint32_t *)io->out;
+    p.F = F; p.layout = io->layout;
+    const unsigned grid = (unsigned)ceil_div_u64(p.n, 128);
+    // recognise edge -> acc [-> acc] chains under a single mask
+    const std::vector<cproc_cuda_node> &nd = b->nodes;
+    bool chain = nd.size() >= 2 && nd.size() <= 3 && nd[0].type == CPROC_CUDA_NODE_EDGE && nd[0].src == -1 &&
+                 p.n_inputs == 1 && p.out_node == nd.size() - 1;
+    for (size_t k = 1; chain && k < nd.size(); ++k)
+        chain = nd[k].type == CPROC_CUDA_NODE_ACC && nd[k].src == (int32_t)k - 1 && nd[k].cond_mask == nd[0].cond_mask;
+    if (chain && nd.size() == 2) k_graph_edge_acc<1><<<grid, 128, 0, ctx->stream>>>(p, nd[0].cond_mask);
+    else if (chain) k_graph_edge_acc<2><<<grid, 128, 0, ctx->stream>>>(p, nd[0].cond_mask);
+    else k_graph_table<<<grid, 128, 0, ctx->stream>>>(p);
+    CK_LAUNCH(ctx, "k_graph");
+    return 0;
+}

@@ -1,0 +1,467 @@
+"""GPU parity: every CUDA path, called through the C-ABI (ctypes over
+libcproc_cuda.so), against the CPU oracle on the same seeded inputs.
+Integer / index / exactly-representable float work is compared bit for bit."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+rng = np.random.default_rng(20261018)
+
+
+@pytest.fixture(scope="module")
+def st():
+    import synth_tools_b200 as st_
+    return st_
+
+
+@pytest.fixture(scope="module")
+def ctx(st):
+    c = st.Context(0)
+    yield c
+    c.close()
+
+
+def tiled16_to_planar(a, N, F):
+    return a.reshape(F // 16, N, 16).transpose(1, 0, 2).reshape(N, F)
+
+
+def pack_bits(bits):
+    """[N][F] 0/1 -> uint32 words [N][F/32], sample t at bit t&31."""
+    N, F = bits.shape
+    return np.packbits(bits.reshape(N, F // 32, 32), axis=2, bitorder="little").view("<u4").reshape(N, F // 32)
+
+
+# --------------------------------------------------------------------------- v2
+def _v2_case(st, ctx, oracle, order, bank, N, F, layout, count0, use_setp, use_dext, ctl=6, opts=None, split=None):
+    nb = (N + bank - 1) // bank
+    chan0 = rng.integers(0, 2**32, (N, 5 + order), dtype=np.uint32)
+    prng0 = rng.integers(1, 2**32, nb, dtype=np.uint32)
+    n_rows = F // (1 << ctl) + 2
+    sp = po.pdm_setpoints(N, n_rows) if use_setp else None
+    dext = rng.integers(0, 2**32, (nb, F), dtype=np.uint32) if use_dext else None
+    ca, pa = chan0.copy(), prng0.copy()
+    want, want_cnt = oracle.pdm_v2_run(ca, order, N, bank, pa, dext, 0x3FF, count0, ctl, 24, sp, F)
+    for k, v in (opts or {}).items():
+        ctx.set_option(k, v)
+    b = ctx.batch(st.PDM_V2, N, order=order, bank_size=bank, ctl_div_log=ctl, out_shift=24, dither_mask=0x3FF, layout=layout)
+    try:
+        b.upload_state(chan0)
+        b.upload_bank(prng0, count0)
+        if split is None:
+            out = np.zeros(N * F, np.uint8)
+            b.run(F, in2=dext, ctl=sp, out=out)
+            got = tiled16_to_planar(out, N, F) if layout == st.TILED else out.reshape(N, F)
+        else:
+            # the same render in several calls must continue seamlessly (checkpoint semantics)
+            assert dext is None
+            got = np.zeros((N, F), np.uint8)
+            t = 0
+            row = 0
+            cnt = count0
+            for f in split:
+                o = np.zeros(N * f, np.uint8)
+                first = 0 if cnt == 0 else (1 << ctl) - cnt
+                rows = 1 + (f - first - 1) // (1 << ctl) if f > first else 0
+                b.run(f, ctl=None if sp is None else np.ascontiguousarray(sp[row:row + max(rows, 1)]), out=o)
+                got[:, t:t + f] = tiled16_to_planar(o, N, f) if layout == st.TILED else o.reshape(N, f)
+                t += f
+                row += rows
+                cnt = (cnt + f) % (1 << ctl)
+            assert t == F
+        assert np.array_equal(got, want)
+        assert np.array_equal(b.download_state(), ca)
+        p, c = b.download_bank()
+        assert c == want_cnt
+        if not use_dext:
+            assert np.array_equal(p, pa)
+    finally:
+        b.free()
+        ctx.set_option("pdm_tpb", 1)
+        ctx.set_option("pdm_block", 64)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+@pytest.mark.parametrize("bank", [1, 2, 3, 4, 7])
+def test_pdm_v2_orders_banks(st, ctx, oracle, order, bank):
+    _v2_case(st, ctx, oracle, order, bank, N=203, F=512, layout=st.TILED, count0=0, use_setp=True, use_dext=False)
+
+
+@pytest.mark.parametrize("layout", ["PLANAR", "TILED"])
+@pytest.mark.parametrize("tpb", [0, 1])
+@pytest.mark.parametrize("blk", [32, 128])
+def test_pdm_v2_layouts_and_mappings(st, ctx, oracle, layout, tpb, blk):
+    _v2_case(st, ctx, oracle, 2, 3, N=1000, F=1024, layout=getattr(st, layout), count0=16, use_setp=True,
+             use_dext=False, opts={"pdm_tpb": tpb, "pdm_block": blk})
+
+
+def test_pdm_v2_external_dither(st, ctx, oracle):
+    _v2_case(st, ctx, oracle, 2, 3, N=100, F=256, layout=st.TILED, count0=0, use_setp=False, use_dext=True)
+    _v2_case(st, ctx, oracle, 3, 2, N=64, F=160, layout=st.PLANAR, count0=32, use_setp=True, use_dext=True)
+
+
+def test_pdm_v2_ragged(st, ctx, oracle):
+    """F / count not multiples of 16, single channel, bank larger than N."""
+    _v2_case(st, ctx, oracle, 2, 3, N=10, F=77, layout=st.PLANAR, count0=5, use_setp=True, use_dext=False)
+    _v2_case(st, ctx, oracle, 2, 3, N=1, F=1, layout=st.PLANAR, count0=63, use_setp=True, use_dext=False)
+    _v2_case(st, ctx, oracle, 4, 64, N=5, F=100, layout=st.PLANAR, count0=0, use_setp=False, use_dext=False)
+    _v2_case(st, ctx, oracle, 2, 3, N=33, F=130, layout=st.PLANAR, count0=3, use_setp=False, use_dext=True)
+
+
+def test_pdm_v2_split_runs(st, ctx, oracle):
+    _v2_case(st, ctx, oracle, 2, 3, N=96, F=640, layout=st.TILED, count0=0, use_setp=True, use_dext=False, split=[64, 16, 320, 240])
+    _v2_case(st, ctx, oracle, 2, 3, N=50, F=200, layout=st.PLANAR, count0=7, use_setp=True, use_dext=False, split=[1, 9, 100, 90])
+
+
+def test_pdm_v2_reference_config(st, ctx, oracle):
+    """The firmware configuration itself: 3 channels, PDM_ORDER 2, control divider
+    4096, dither mask 0x3FF, zero-initialised state, setpoints as pdm_init
+    (mod_pdm_pwm.c:147-161)."""
+    N, F = 3, 3 * 4096
+    chan = np.zeros((N, 7), np.uint32)
+    chan[:, 0] = [2000000000, 0x40000000, 0x40000000]
+    prng = np.array([2463534242], np.uint32)
+    ca, pa = chan.copy(), prng.copy()
+    want, _ = oracle.pdm_v2_run(ca, 2, N, 3, pa, None, 0x3FF, 0, 12, 24, None, F)
+    b = ctx.batch(st.PDM_V2, N, order=2, bank_size=3, ctl_div_log=12)
+    b.upload_state(chan); b.upload_bank(prng, 0)
+    out = np.zeros((N, F), np.uint8)
+    b.run(F, out=out)
+    assert np.array_equal(out, want) and np.array_equal(b.download_state(), ca)
+    b.free()
+
+
+def test_pdm_v2_errors(st, ctx):
+    with pytest.raises(st.CprocCudaError):
+        ctx.batch(st.PDM_V2, 8, order=5)
+    with pytest.raises(st.CprocCudaError):
+        ctx.batch(st.PDM_V2, 8, order=2, out_shift=16)
+    b = ctx.batch(st.PDM_V2, 8, order=2, bank_size=3, ctl_div_log=4)
+    with pytest.raises(st.CprocCudaError):     # not enough setpoint rows for the boundaries crossed
+        b.run(64, ctl=np.zeros((1, 8), np.uint32), out=np.zeros(8 * 64, np.uint8))
+    with pytest.raises(st.CprocCudaError):     # TILED needs F % 16 == 0
+        b.run(24, out=np.zeros(8 * 24, np.uint8), layout=st.TILED)
+    with pytest.raises(st.CprocCudaError):
+        b.run(16, out=None)
+    b.run(0, out=np.zeros(1, np.uint8))        # empty run is a no-op
+    b.free()
+
+
+# --------------------------------------------------------------------------- v1
+@pytest.mark.parametrize("bank,tpb", [(1, 1), (2, 1), (2, 0), (3, 1), (4, 1), (9, 1)])
+@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED", "TILED"])
+def test_pdm_v1(st, ctx, oracle, bank, tpb, layout):
+    N, F = 301, 512
+    nb = (N + bank - 1) // bank
+    ch0 = rng.integers(0, 2**32, (N, 2), dtype=np.uint32)
+    prng0 = rng.integers(1, 2**32, nb, dtype=np.uint32)
+    ca, pa = ch0.copy(), prng0.copy()
+    bits = oracle.pdm_v1_run(ca, N, bank, pa, None, 0x0FFFFFFF, F)
+    want = pack_bits(bits)
+    ctx.set_option("pdm_tpb", tpb)
+    b = ctx.batch(st.PDM_V1, N, bank_size=bank, dither_mask=0x0FFFFFFF, layout=getattr(st, layout))
+    b.upload_state(ch0); b.upload_bank(prng0)
+    out = np.zeros(N * F // 32, np.uint32)
+    b.run(F, out=out)
+    if layout == "PLANAR":
+        got = out.reshape(N, F // 32)
+    elif layout == "INTERLEAVED":
+        got = out.reshape(F // 32, N).T
+    else:
+        got = out.reshape(F // 128, N, 4).transpose(1, 0, 2).reshape(N, F // 32)
+    assert np.array_equal(got, want)
+    assert np.array_equal(b.download_state(), ca)
+    assert np.array_equal(b.download_bank()[0], pa)
+    b.free()
+    ctx.set_option("pdm_tpb", 1)
+
+
+def test_pdm_v1_external_dither_and_density(st, ctx, oracle):
+    N, F, bank = 64, 1024, 2
+    ch0 = np.zeros((N, 2), np.uint32)
+    ch0[:, 0] = np.linspace(0x40000000, 0xC0000000, N).astype(np.uint32)
+    dext = rng.integers(0, 2**32, (N // bank, F), dtype=np.uint32)
+    ca = ch0.copy()
+    want = pack_bits(oracle.pdm_v1_run(ca, N, bank, None, dext, 0x0FFFFFFF, F))
+    b = ctx.batch(st.PDM_V1, N, bank_size=bank, dither_mask=0x0FFFFFFF)
+    b.upload_state(ch0)
+    out = np.zeros((N, F // 32), np.uint32)
+    b.run(F, in2=dext, out=out)
+    assert np.array_equal(out, want) and np.array_equal(b.download_state(), ca)
+    # pulse density tracks setpoint / 2^32 (dither mean 2^27 adds 1/32)
+    dens = np.unpackbits(out.view(np.uint8), axis=1).mean(axis=1)
+    assert np.allclose(dens, ch0[:, 0] / 2.0**32 + 1 / 32, atol=0.02)
+    with pytest.raises(st.CprocCudaError):
+        b.run(48, out=out)
+    b.free()
+
+
+# --------------------------------------------------------------------- pdm raw, pwm
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
+def test_pdm_raw(st, ctx, oracle, order, layout):
+    N, F, sh = 130, 300, 24
+    s0 = rng.integers(0, 2**32, (N, order), dtype=np.uint32)
+    inp = rng.integers(0, 2**32, (N, F), dtype=np.uint32)
+    dith = rng.integers(0, 1024, F, dtype=np.uint32)
+    cst = rng.integers(0x40000000, 0xC0000000, (N, 1), dtype=np.uint32)
+    sa = s0.copy()
+    want1 = oracle.pdm_run(order, sa, N, F, inp, None, sh, dith)
+    want2 = oracle.pdm_run(order, sa, N, F, None, cst[:, 0].copy(), sh, None)
+    b = ctx.batch(st.PDM, N, order=order, out_shift=sh, layout=getattr(st, layout))
+    b.upload_state(s0); b.upload_param(cst)
+    il = layout == "INTERLEAVED"
+    out = np.zeros((F, N) if il else (N, F), np.uint32)
+    b.run(F, inp=np.ascontiguousarray(inp.T) if il else inp, in2=dith, out=out)
+    assert np.array_equal(out.T if il else out, want1)
+    b.run(F, out=out)
+    assert np.array_equal(out.T if il else out, want2)
+    assert np.array_equal(b.download_state(), sa)
+    b.free()
+
+
+def test_pwm(st, ctx, oracle):
+    N, F = 77, 500
+    ph0 = rng.integers(0, 1 << 24, (N, 1), dtype=np.uint32)
+    sp = rng.integers(0, 1 << 16, (N, 1), dtype=np.uint32)
+    sp[0] = 256 * 13                                   # mod_pdm.c:161
+    pa = ph0[:, 0].copy()
+    want = oracle.pwm_run(pa, sp[:, 0].copy(), N, F)
+    b = ctx.batch(st.PWM, N)
+    b.upload_state(ph0); b.upload_param(sp)
+    out = np.zeros((N, F), np.uint8)
+    b.run(F, out=out)
+    assert np.array_equal(out, want) and np.array_equal(b.download_state()[:, 0], pa)
+    b.free()
+
+
+# ------------------------------------------------------------------------- graphs
+@pytest.mark.parametrize("rows", [po.GRAPH_TEST_CPROC, po.GRAPH_BP5,
+                                  [(po.NODE_ACC, -1, 1), (po.NODE_ACC, -2, 2), (po.NODE_EDGE, 1, 4), (po.NODE_ACC, 2, 3)],
+                                  [(po.NODE_ACC, -1, 0xFFFFFFFF)]])
+@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
+@pytest.mark.parametrize("masked", [False, True])
+def test_graph(st, ctx, oracle, rows, layout, masked):
+    N, F = 150, 64
+    n_in = max(1, max(-s for _, s, _ in rows))
+    inp = rng.integers(0, 2, (N, n_in, F), dtype=np.uint32)
+    inp[::7] = rng.integers(0, 2**32, inp[::7].shape, dtype=np.uint32)
+    changed = rng.integers(0, 8, (N, F), dtype=np.uint32) if masked else None
+    sw = sum(2 if t == po.NODE_EDGE else 1 for t, _, _ in rows)
+    s0 = rng.integers(0, 2**32, (N, sw), dtype=np.uint32)
+    sa = s0.copy()
+    want = oracle.graph_run(rows, n_in, len(rows) - 1, sa, N, F, inp, changed)
+    b = ctx.batch(st.GRAPH, N, nodes=rows, n_inputs=n_in, layout=getattr(st, layout))
+    assert b.state_bytes == 4 * sw
+    b.upload_state(s0)
+    il = layout == "INTERLEAVED"
+    out = np.zeros((F, N) if il else (N, F), np.uint32)
+    b.run(F, inp=np.ascontiguousarray(inp.transpose(2, 1, 0)) if il else inp,
+          in2=None if changed is None else (np.ascontiguousarray(changed.T) if il else changed), out=out)
+    assert np.array_equal(out.T if il else out, want)
+    assert np.array_equal(b.download_state(), sa)
+    b.free()
+
+
+def test_graph_test_cproc_anchor(st, ctx):
+    """SURVEY 8c anchor through the CUDA path: zero-initialised edge->acc graph,
+    one instance, tick by tick (F=1 per call, like cproc_update)."""
+    b = ctx.batch(st.GRAPH, 1, nodes=po.GRAPH_TEST_CPROC)
+    got = []
+    for x in [0, 1, 1, 0, 0, 1, 0, 1, 1, 1, 0]:
+        out = np.zeros((1, 1), np.uint32)
+        b.run(1, inp=np.array([[[x]]], np.uint32), out=out)
+        got.append(int(out[0, 0]))
+    assert got == [0, 1, 1, 2, 2, 3, 4, 5, 5, 5, 6]
+    b.free()
+    with pytest.raises(st.CprocCudaError):     # ANF: forward reference
+        ctx.batch(st.GRAPH, 1, nodes=[(po.NODE_ACC, 1, 1), (po.NODE_ACC, -1, 1)])
+
+
+# --------------------------------------------------------------------- voice bank
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("N,G,F", [(64, 64, 64), (64 * 37, 64, 64), (5000, 0, 512), (20000, 0, 700), (1000, 300, 129)])
+def test_voice_bank(st, ctx, oracle, mode, N, G, F):
+    v0 = np.zeros((N, 2), np.uint32)
+    v0[:, 1] = rng.integers(0, 2**32, N, dtype=np.uint32)
+    tab = np.array([oracle.note_to_inc(n) for n in range(128)], np.uint32)
+    v0[:, 0] = np.where(rng.random(N) < 0.8, tab[rng.integers(0, 128, N)], 0)
+    v0[: N // 8, 0] = 0x7FFFFFF1                     # loud voices: integer sum wraps
+    va = v0.copy()
+    Gq = G if G else N
+    want_i, want_f = oracle.voice_bank_run(va, N, Gq, mode, F)
+    b = ctx.batch(st.VOICE_BANK, N, mode=mode, voices_per_bus=G)
+    b.upload_state(v0)
+    n_bus = (N + Gq - 1) // Gq
+    out = np.zeros((n_bus, F), np.float32)
+    mix = np.zeros((n_bus, F), np.int32)
+    b.run(F, out=out, mix=mix)
+    assert np.array_equal(mix, want_i)
+    assert np.array_equal(out.view(np.uint32), want_f.view(np.uint32))
+    assert np.array_equal(b.download_state(), va)
+    # float only, continuing from the advanced state
+    want_i2, want_f2 = oracle.voice_bank_run(va, N, Gq, mode, F)
+    b.run(F, out=out)
+    assert np.array_equal(out.view(np.uint32), want_f2.view(np.uint32))
+    b.free()
+
+
+def test_voice_bank_synth_anchor(st, ctx):
+    # notes 69,60,127,0 on -> first 8 saw-mix samples of synth_run
+    v = np.zeros((64, 2), np.uint32)
+    v[:4, 0] = [39370533, 23409859, 1122405051, 731558]
+    b = ctx.batch(st.VOICE_BANK, 64, voices_per_bus=64)
+    b.upload_state(v)
+    out = np.zeros((1, 8), np.float32)
+    b.run(8, out=out)
+    want = [0.0, float.fromhex("0x1.1abeap-6"), float.fromhex("-0x1.ca82bep-6"), float.fromhex("-0x1.5f883ap-7"),
+            float.fromhex("0x1.abea1p-8"), float.fromhex("0x1.85b924p-6"), float.fromhex("-0x1.5f883ap-6"),
+            float.fromhex("-0x1.132662p-8")]
+    assert out[0].tolist() == want
+    b.free()
+
+
+# -------------------------------------------------------------------- square_grain
+@pytest.mark.parametrize("N,F", [(1, 64), (33, 257), (1000, 256), (129, 31)])
+@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
+def test_square_grain(st, ctx, oracle, N, F, layout):
+    inp = rng.uniform(-1, 1, (N, F)).astype(np.float32)
+    th = rng.uniform(0.05, 0.5, (N, 1)).astype(np.float32)
+    th[0] = 0.0
+    s0 = rng.choice(np.array([0.0, 0.5, -0.5], np.float32), (N, 1))
+    sa = s0[:, 0].copy()
+    want = oracle.square_grain_run(sa, th[:, 0].copy(), N, F, inp)
+    b = ctx.batch(st.SQUARE_GRAIN, N, layout=getattr(st, layout))
+    b.upload_state(s0); b.upload_param(th)
+    il = layout == "INTERLEAVED"
+    out = np.zeros((F, N) if il else (N, F), np.float32)
+    b.run(F, inp=np.ascontiguousarray(inp.T) if il else inp, out=out)
+    got = out.T if il else out
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(b.download_state().view(np.float32)[:, 0], sa)
+    # in place (Pd hands the same vector as in and out)
+    b.upload_state(s0)
+    io = np.ascontiguousarray(inp.T) if il else inp.copy()
+    b.run(F, inp=io, out=io)
+    assert np.array_equal((io.T if il else io).view(np.uint32), want.view(np.uint32))
+    b.free()
+
+
+def test_square_grain_mix(st, ctx, oracle):
+    N, F = 3000, 256
+    state = rng.choice(np.array([0.0, 0.5, -0.5], np.float32), N)
+    th = rng.uniform(0.05, 0.5, N).astype(np.float32)
+    phase = rng.integers(0, 2**32, N, dtype=np.uint32)
+    inc = np.array([oracle.note_to_inc(n) for n in rng.integers(36, 97, N)], np.uint32)
+    gl = rng.integers(0, 65, N).astype(np.uint8); gr = (64 - gl).astype(np.uint8)
+    sa, pa = state.copy(), phase.copy()
+    want_i, want_f = oracle.square_grain_mix_run(sa, th, pa, inc, gl, gr, N, F)
+    b = ctx.batch(st.SQUARE_GRAIN_MIX, N)
+    s_rec = np.zeros((N, 2), np.uint32); s_rec[:, 0] = state.view(np.uint32); s_rec[:, 1] = phase
+    p_rec = np.zeros((N, 4), np.uint32); p_rec[:, 0] = th.view(np.uint32); p_rec[:, 1] = inc; p_rec[:, 2] = gl; p_rec[:, 3] = gr
+    b.upload_state(s_rec); b.upload_param(p_rec)
+    out = np.zeros((2, F), np.float32); mix = np.zeros((2, F), np.int32)
+    b.run(F, out=out, mix=mix)
+    assert np.array_equal(mix, want_i)
+    assert np.array_equal(out.view(np.uint32), want_f.view(np.uint32))
+    s1 = b.download_state()
+    assert np.array_equal(s1[:, 0].view(np.float32), sa) and np.array_equal(s1[:, 1], pa)
+    b.free()
+
+
+# ------------------------------------------------------------- extension processors
+def _xvoice_inputs(oracle, N):
+    prm = np.zeros(N, po.xvoice_param_dtype)
+    prm["inc"] = [oracle.note_to_inc(n) for n in rng.integers(24, 109, N)]
+    prm["f"] = rng.uniform(0.01, 0.3, N); prm["q"] = rng.uniform(0.5, 2.0, N)
+    prm["env_attack"] = rng.uniform(1e-3, 1e-1, N); prm["env_release"] = rng.uniform(1e-3, 1e-2, N)
+    prm["gate_frames"] = rng.integers(0, 400, N)
+    prm["gl"] = rng.uniform(0, 1, N); prm["gr"] = 1.0 - prm["gl"]
+    stt = np.zeros(N, po.xvoice_state_dtype)
+    stt["phase"] = rng.integers(0, 2**32, N, dtype=np.uint32)
+    return stt, prm
+
+
+@pytest.mark.parametrize("layout", ["PLANAR", "TILED"])
+def test_xvoice_raw_bit_exact_and_mix(st, ctx, oracle, layout):
+    N, F = 1000, 512
+    s0, prm = _xvoice_inputs(oracle, N)
+    sa = s0.copy()
+    want_raw, want_mix = oracle.xvoice_run(sa, prm, N, F)
+    b = ctx.batch(st.XVOICE, N, layout=getattr(st, layout))
+    b.upload_state(s0.view(np.uint32).reshape(N, 5)); b.upload_param(prm.view(np.uint32).reshape(N, 8))
+    raw = np.zeros(N * F * 2, np.float32); mix = np.zeros((2, F), np.float32)
+    b.run(F, out=raw, mix=mix)
+    got = raw.reshape(F // 2, N, 2, 2).transpose(1, 0, 2, 3).reshape(N, F, 2) if layout == "TILED" else raw.reshape(N, F, 2)
+    assert np.array_equal(got.view(np.uint32), want_raw.view(np.uint32))       # bit-exact per voice
+    assert np.array_equal(b.download_state(), sa.view(np.uint32).reshape(N, 5))
+    # mix: float sum over voices, order differs from the oracle's double accumulation.
+    # Tolerance (BASELINE.json north_star): <= 1e-5 relative to the mix peak, SNR >= 120 dB.
+    err = np.abs(mix.astype(np.float64) - want_mix.astype(np.float64)).max()
+    peak = np.abs(want_mix).max()
+    assert err <= 1e-5 * peak
+    snr = 10 * np.log10((want_mix.astype(np.float64) ** 2).sum() / max(((mix.astype(np.float64) - want_mix) ** 2).sum(), 1e-300))
+    assert snr >= 120.0
+    # deterministic run to run
+    b.upload_state(s0.view(np.uint32).reshape(N, 5))
+    mix2 = np.zeros((2, F), np.float32)
+    b.run(F, mix=mix2)
+    assert np.array_equal(mix.view(np.uint32), mix2.view(np.uint32))
+    b.free()
+
+
+def test_onepole(st, ctx, oracle):
+    N, F = 300, 200
+    inp = rng.uniform(-1, 1, (N, F)).astype(np.float32)
+    a = rng.uniform(0.001, 0.9, (N, 1)).astype(np.float32)
+    y0 = rng.uniform(-1, 1, (N, 1)).astype(np.float32)
+    ya = y0[:, 0].copy()
+    want = oracle.onepole_run(ya, a[:, 0].copy(), N, F, inp)
+    b = ctx.batch(st.ONEPOLE, N)
+    b.upload_state(y0); b.upload_param(a)
+    out = np.zeros((N, F), np.float32)
+    b.run(F, inp=inp, out=out)
+    assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
+    b.free()
+
+
+# ------------------------------------------------------------ device-resident path
+def test_run_dev_and_stream(st, ctx, oracle):
+    """Device-pointer API and the chunked host stream give the same bytes as run()."""
+    N, F, ctl, order, bank = 300, 2048, 8, 2, 3
+    nb = (N + bank - 1) // bank
+    chan0 = rng.integers(0, 2**32, (N, 5 + order), dtype=np.uint32)
+    prng0 = rng.integers(1, 2**32, nb, dtype=np.uint32)
+    sp = po.pdm_setpoints(N, F // (1 << ctl))
+    ca, pa = chan0.copy(), prng0.copy()
+    want, _ = oracle.pdm_v2_run(ca, order, N, bank, pa, None, 0x3FF, 0, ctl, 24, sp, F)
+    b = ctx.batch(st.PDM_V2, N, order=order, bank_size=bank, ctl_div_log=ctl, layout=st.TILED)
+    # (1) device pointers
+    b.upload_state(chan0); b.upload_bank(prng0, 0)
+    d_out = ctx.dev_alloc(N * F); d_sp = ctx.dev_alloc(sp.nbytes)
+    ctx.h2d(d_sp, sp)
+    l0 = ctx.launches
+    b.run_dev(F, ctl=d_sp, n_ctl=sp.shape[0], out=d_out)
+    assert ctx.launches == l0 + 1
+    got = np.zeros(N * F, np.uint8)
+    ctx.d2h(got, d_out)
+    assert np.array_equal(tiled16_to_planar(got, N, F), want)
+    ctx.dev_free(d_out); ctx.dev_free(d_sp)
+    # (2) chunked stream into pinned host memory, ring of 2 slabs + callback
+    b.upload_state(chan0); b.upload_bank(prng0, 0)
+    Fc = 512
+    ring, ring_ptr = ctx.host_alloc(2 * N * Fc)
+    seen = []
+
+    def on_chunk(user, k, slab, nbytes):
+        a = np.ctypeslib.as_array((__import__("ctypes").c_uint8 * nbytes).from_address(slab)).copy()
+        seen.append((k, tiled16_to_planar(a, N, Fc)))
+
+    b.run_stream(F, Fc, out=ring_ptr, ctl=sp, ring_chunks=2, on_chunk=on_chunk)
+    assert [k for k, _ in seen] == list(range(F // Fc))
+    assert np.array_equal(np.concatenate([a for _, a in seen], axis=1), want)
+    assert np.array_equal(b.download_state(), ca)
+    ctx.host_free(ring_ptr)
+    b.free()
