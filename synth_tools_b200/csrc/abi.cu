@@ -63,6 +63,7 @@ int cproc_cuda_open(int device, void *stream, cproc_cuda_ctx **out) {
         rc = cproc_set_err(nullptr, CPROC_CUDA_ENODEV, "open: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
         delete ctx; return rc;
     }
+    ctx->n_sm = prop.multiProcessorCount;
     if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
     else {
         if ((rc = cproc_check(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate"))) { g_last_err = ctx->err; delete ctx; return rc; }
@@ -98,6 +99,8 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     if (!strcmp(name, "pdm_block")) { if (value < 32 || value > 128 || (value & 31)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_block must be 32, 64, 96 or 128"); ctx->pdm_block = (int)value; }
     else if (!strcmp(name, "pdm_tpb")) ctx->pdm_tpb = value != 0;
     else if (!strcmp(name, "pdm_stage")) ctx->pdm_stage = value != 0;
+    else if (!strcmp(name, "pdm_persist")) ctx->pdm_persist = value != 0;
+    else if (!strcmp(name, "pdm_warps_per_smsp")) { if (value < 1 || value > 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_warps_per_smsp must be 1..4"); ctx->pdm_warps_per_smsp = (int)value; }
     else return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "set_option: unknown option '%s'", name);
     return 0;
 }
@@ -200,7 +203,7 @@ int cproc_cuda_free(cproc_cuda_batch *b) {
     if (!b) return 0;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    void *ptrs[] = { b->d_state, b->d_param, b->d_prng, b->d_nodes, b->d_in, b->d_in2, b->d_ctl, b->d_out, b->d_out2, b->d_mix };
+    void *ptrs[] = { b->d_state, b->d_param, b->d_prng, b->d_nodes, b->d_in, b->d_in2, b->d_ctl, b->d_out, b->d_out2, b->d_mix, b->d_flags };
     for (void *q : ptrs) if (q) cudaFree(q);
     delete b;
     return 0;

@@ -20,6 +20,9 @@ struct cproc_cuda_ctx {
     int pdm_block = 64;       // threads per block of the PDM kernels
     int pdm_tpb = 1;          // 1: thread-per-bank when bank_size <= 4, 0: thread-per-channel
     int pdm_stage = 1;        // 1: smem-staged full-line stores for PLANAR
+    int pdm_persist = 1;      // 1: persistent McNaughton-scheduled kernels when thread == bank
+    int pdm_warps_per_smsp = 1;
+    int n_sm = CPROC_N_SM;
     int voice_block = 256;
     int grain_block = 128;
     int xvoice_block = 128;
@@ -44,6 +47,9 @@ struct cproc_cuda_batch {
     void *d_in = nullptr, *d_in2 = nullptr, *d_ctl = nullptr, *d_out = nullptr, *d_mix = nullptr;
     size_t cap_in = 0, cap_in2 = 0, cap_ctl = 0, cap_out = 0, cap_mix = 0;
     void *d_out2 = nullptr; size_t cap_out2 = 0;   // second slab for run_stream
+    unsigned long long *d_flags = nullptr;         // persistent-kernel progress words
+    uint64_t n_flags = 0;
+    unsigned long long epoch = 0;
 };
 
 int cproc_set_err(cproc_cuda_ctx *ctx, int code, const char *fmt, ...);

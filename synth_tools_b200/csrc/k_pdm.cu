@@ -1,17 +1,119 @@
 // k_pdm.cu -- sigma-delta / PDM kernels (integer, serial in time, bit-exact).
 //
-//   k_pdm_v2      stm32f103/mod_pdm_pwm.c:101-141 (glide + pdmK_update) with the
+//   k_pdm_v2_*    stm32f103/mod_pdm_pwm.c:101-141 (glide + pdmK_update) with the
 //                 control-rate line generator of mod_controlrate.c:28-40
-//   k_pdm_v1      stm32f103/mod_pdm.c:230-264 (carry-bit PDM, shared dither)
+//   k_pdm_v1_*    stm32f103/mod_pdm.c:230-264 (carry-bit PDM, shared dither)
 //   k_pdm_raw     stm32f103/pdm.h:13-77 (pdmK_update on an input stream)
 //   k_pwm         stm32f103/mod_pdm.c:167-175
 //
-// Mapping: the recurrence is nonlinear (quantiser in the loop), so time stays
-// serial and the batch axis carries the parallelism.  One thread owns one
-// dither bank (B channels that share one random word per tick, exactly like
-// one MCU of the reference) and keeps every state word in registers for the
-// whole run; 16 ticks of 8-bit duty are packed into one 128-bit store.
+// Mapping.  The recurrence is nonlinear (quantiser in the loop), so time stays
+// serial and the batch axis carries the parallelism.  One lane owns one dither
+// bank -- the B channels that share one random word per tick, i.e. one MCU of
+// the reference -- so the PRNG is computed once per bank, and keeps every state
+// word in registers for the whole segment; 16 ticks of 8-bit duty leave as one
+// 128-bit store per channel.
+//
+// Scheduling.  A warp of 32 banks is a "chain" of G time groups that must run
+// in order.  With 65,536 channels in banks of 3 there are 683 chains for 592
+// warp schedulers (148 SMs x 4): a plain grid leaves 91 schedulers with two
+// chains and finishes in 2T.  The persistent kernels instead run W <= C worker
+// warps and cut the C*G work units into W equal contiguous pieces (McNaughton's
+// wrap-around rule for preemptive scheduling): a worker runs the HEAD of its
+// last chain first, then its whole chains, then the TAIL of its first chain,
+// whose head was run first thing by the previous worker.  The hand-over goes
+// through the state arrays in L2 plus a release/acquire progress word; by
+// construction the producer is always ahead, so the wait is a safety net.
 #include "common.cuh"
+
+// ---------------------------------------------------------------------------
+// shared helpers
+
+template <int K>
+__device__ __forceinline__ uint32_t pdm_step(uint32_t (&s)[K], uint32_t in, uint32_t sh, uint32_t d) {
+    // pdm.h:13-24 / 32-40 / 48-57 / 67-77
+    uint32_t q = s[K - 1] >> sh;
+    uint32_t a = (q << sh) + (K == 1 ? 0u : d);
+    s[0] += in - a;
+#pragma unroll
+    for (int k = 1; k < K; ++k) s[k] += s[k - 1] - a;
+    return q;
+}
+
+// out_shift == 24 and dither below bit 24: out_a = (s & 0xFF000000) | d is the
+// same number as (out_q << 24) + d (no carries), and out_q is its top byte.
+template <int K>
+__device__ __forceinline__ uint32_t pdm_step_q24(uint32_t (&s)[K], uint32_t in, uint32_t d) {
+    uint32_t a;
+    if (K == 1) a = s[0] & 0xFF000000u;
+    else asm("lop3.b32 %0, %1, 0xFF000000, %2, 0xEA;" : "=r"(a) : "r"(s[K - 1]), "r"(d));   // (s & M) | d, one LOP3
+    s[0] += in - a;
+#pragma unroll
+    for (int k = 1; k < K; ++k) s[k] += s[k - 1] - a;
+    return a;       // byte 3 = out_q
+}
+
+// byte 3 of four words -> one little-endian word (3 PRMT per 4 samples)
+__device__ __forceinline__ uint32_t pack_top_bytes(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3) {
+    uint32_t lo = __byte_perm(a0, a1, 0x0073);
+    uint32_t hi = __byte_perm(a2, a3, 0x0073);
+    return __byte_perm(lo, hi, 0x5410);
+}
+// low bytes of four words -> one word
+__device__ __forceinline__ uint32_t pack_low_bytes(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
+    uint32_t lo = __byte_perm(q0, q1, 0x0040);
+    uint32_t hi = __byte_perm(q2, q3, 0x0040);
+    return __byte_perm(lo, hi, 0x5410);
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// McNaughton wrap-around schedule over C chains x G groups for W workers.
+struct Sched {
+    uint64_t C, G, W, Lg;            // Lg = ceil(C*G / W) >= G
+    unsigned long long *flags;       // [C] progress words: (epoch << 32) | groups done
+    unsigned long long epoch;
+};
+
+struct Segment { uint64_t chain, g0, g1; bool wait, signal; };
+
+// Segment k of worker w in execution order (k < sched_count(s, w)).
+__device__ __forceinline__ uint32_t sched_count(const Sched &s, uint64_t w, uint64_t *ca, uint64_t *ga, uint64_t *cb, uint64_t *gb) {
+    const uint64_t total = s.C * s.G;
+    const uint64_t u0 = w * s.Lg;
+    if (u0 >= total) return 0;
+    const uint64_t u1 = u0 + s.Lg < total ? u0 + s.Lg : total;
+    *ca = u0 / s.G; *ga = u0 % s.G;
+    *cb = (u1 - 1) / s.G; *gb = (u1 - 1) % s.G + 1;
+    return (uint32_t)(*cb - *ca + 1);
+}
+__device__ __forceinline__ Segment sched_segment(const Sched &s, uint32_t k, uint32_t nseg, uint64_t ca, uint64_t ga, uint64_t cb, uint64_t gb) {
+    if (nseg == 1) return Segment{ca, ga, gb, ga > 0, gb < s.G};
+    if (k == 0) return Segment{cb, 0, gb, false, gb < s.G};          // head of the last chain: no dependency
+    if (k == nseg - 1) return Segment{ca, ga, s.G, ga > 0, false};   // tail of the first chain
+    return Segment{ca + k, 0, s.G, false, false};                    // whole chains in between
+}
+
+__device__ __forceinline__ void sched_wait(const Sched &s, const Segment &sg, uint32_t lane) {
+    if (!sg.wait) return;
+    if (lane == 0) {
+        const unsigned long long want = (s.epoch << 32) | sg.g0;
+        while (ld_acquire_u64(s.flags + sg.chain) != want) __nanosleep(100);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void sched_signal(const Sched &s, const Segment &sg, uint32_t lane) {
+    if (!sg.signal) return;
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release_u64(s.flags + sg.chain, (s.epoch << 32) | sg.g1);
+}
 
 // ---------------------------------------------------------------------------
 // v2
@@ -25,118 +127,153 @@ struct PdmV2Params {
     uint8_t *out;
     uint64_t F;
     uint32_t count0, ctl_div_log, sh, dmask, layout;
+    Sched sched;
 };
 
-template <int K>
-__device__ __forceinline__ uint32_t pdm_step(uint32_t (&s)[K], uint32_t in, uint32_t sh, uint32_t d) {
-    // pdm.h:13-24 / 32-40 / 48-57 / 67-77
-    uint32_t q = s[K - 1] >> sh;
-    uint32_t a = (q << sh) + (K == 1 ? 0u : d);
-    s[0] += in - a;
-#pragma unroll
-    for (int k = 1; k < K; ++k) s[k] += s[k - 1] - a;
-    return q;
-}
-
-// Insert byte `q` (0..255) at byte position j of w.
-template <int J>
-__device__ __forceinline__ uint32_t put_byte(uint32_t w, uint32_t q) {
-    // selector nibbles pick from {w.b0..b3 = 0..3, q.b0..b3 = 4..7}
-    constexpr uint32_t sel = J == 0 ? 0x3214u : J == 1 ? 0x3240u : J == 2 ? 0x3410u : 0x4210u;
-    return __byte_perm(w, q, sel);
-}
-
-template <int K, int B, bool TPB>
-__global__ void __launch_bounds__(128) k_pdm_v2(const PdmV2Params p) {
-    // TPB: thread == bank of B channels.  !TPB: thread == channel (B == 1),
-    // bank = channel / bank_size, every thread of a bank replays the bank PRNG.
-    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t c0 = tid * B;
-    if (c0 >= p.npad) return;
-    const uint64_t bank = TPB ? tid : tid / p.bank_size;
-    const bool rng_owner = TPB ? true : (tid % p.bank_size == 0);
-
+template <int K, int B>
+struct V2Regs {
     uint32_t sp[B], p0[B], v0[B], p1[B], v1[B], s[B][K];
+    __device__ __forceinline__ void load(const uint32_t *st, uint64_t npad, uint64_t c0) {
 #pragma unroll
-    for (int j = 0; j < B; ++j) {
-        const uint32_t *x = p.st + c0 + j;
-        sp[j] = x[0]; p0[j] = x[p.npad]; v0[j] = x[2 * p.npad]; p1[j] = x[3 * p.npad]; v1[j] = x[4 * p.npad];
+        for (int j = 0; j < B; ++j) {
+            const uint32_t *x = st + c0 + j;
+            sp[j] = __ldcg(x); p0[j] = __ldcg(x + npad); v0[j] = __ldcg(x + 2 * npad);
+            p1[j] = __ldcg(x + 3 * npad); v1[j] = __ldcg(x + 4 * npad);
 #pragma unroll
-        for (int k = 0; k < K; ++k) s[j][k] = x[(5 + k) * p.npad];
-    }
-    uint32_t rng = p.prng[bank];
-    const uint32_t L = p.ctl_div_log, div_mask = (1u << L) - 1u, sh = p.sh, dmask = p.dmask;
-    uint32_t cnt = p.count0;
-    uint64_t row = 0;
-    const uint64_t groups = p.F >> 4;
-    const uint32_t *dext = p.dither_ext ? p.dither_ext + bank * p.F : nullptr;
-
-    for (uint64_t g = 0; g < groups; ++g) {
-        if (cnt == 0) {
-            // mod_pdm_pwm.c:129-137 + mod_controlrate.c:28-40
-#pragma unroll
-            for (int j = 0; j < B; ++j) {
-                if (p.setpoints && c0 + j < p.n) sp[j] = p.setpoints[row * p.n + c0 + j];
-                p0[j] = p1[j]; v0[j] = v1[j];
-                p1[j] += v1[j] << L;
-                v1[j] = (uint32_t)((int32_t)(sp[j] - p1[j]) >> L);
-            }
-            ++row;
+            for (int k = 0; k < K; ++k) s[j][k] = __ldcg(x + (5 + k) * npad);
         }
-        uint32_t w[B][4];
+    }
+    __device__ __forceinline__ void store(uint32_t *st, uint64_t npad, uint64_t c0) const {
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            uint32_t *x = st + c0 + j;
+            __stcg(x, sp[j]); __stcg(x + npad, p0[j]); __stcg(x + 2 * npad, v0[j]);
+            __stcg(x + 3 * npad, p1[j]); __stcg(x + 4 * npad, v1[j]);
+#pragma unroll
+            for (int k = 0; k < K; ++k) __stcg(x + (5 + k) * npad, s[j][k]);
+        }
+    }
+    // mod_pdm_pwm.c:129-137 (line[0] = line[1]) + mod_controlrate.c:28-40
+    __device__ __forceinline__ void boundary(const uint32_t *row, uint64_t c0, uint64_t n, uint32_t L) {
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            if (row && c0 + j < n) sp[j] = __ldg(row + c0 + j);
+            p0[j] = p1[j]; v0[j] = v1[j];
+            p1[j] += v1[j] << L;
+            v1[j] = (uint32_t)((int32_t)(sp[j] - p1[j]) >> L);
+        }
+    }
+    // 16 ticks -> 4 packed words per channel
+    template <bool FASTQ, bool DEXT>
+    __device__ __forceinline__ void group(uint32_t &rng, const uint32_t *dext16, uint32_t sh, uint32_t dmask, uint32_t (&w)[B][4]) {
         uint32_t dbuf[16];
-        if (dext) {
+        if (DEXT) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                uint4 v = *reinterpret_cast<const uint4 *>(dext + g * 16 + i * 4);
+                uint4 v = *reinterpret_cast<const uint4 *>(dext16 + i * 4);
                 dbuf[4 * i] = v.x; dbuf[4 * i + 1] = v.y; dbuf[4 * i + 2] = v.z; dbuf[4 * i + 3] = v.w;
             }
         }
+        uint32_t a[B][4];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             uint32_t d;
-            if (dext) d = dbuf[i] & dmask;
-            else { rng = xorshift32_step(rng); d = rng & dmask; }   // mod_pdm_pwm.c:127
+            if (DEXT) d = dbuf[i] & dmask;
+            else { rng = xorshift32_step(rng); asm("and.b32 %0, %1, %2;" : "=r"(d) : "r"(rng), "r"(dmask)); }   // mod_pdm_pwm.c:127 (asm: keep the mask out of the per-channel LOP3)
 #pragma unroll
             for (int j = 0; j < B; ++j) {
-                p0[j] += v0[j];                                      // :101-104
-                uint32_t q = pdm_step<K>(s[j], p0[j], sh, d);        // :108-116
-                uint32_t &ww = w[j][i >> 2];
-                switch (i & 3) {
-                case 0: ww = q; break;
-                case 1: ww = put_byte<1>(ww, q); break;
-                case 2: ww = put_byte<2>(ww, q); break;
-                default: ww = put_byte<3>(ww, q); break;
-                }
+                p0[j] += v0[j];                                       // :101-104
+                if (FASTQ) a[j][i & 3] = pdm_step_q24<K>(s[j], p0[j], d);   // :108-116
+                else a[j][i & 3] = pdm_step<K>(s[j], p0[j], sh, d);
+                if ((i & 3) == 3)
+                    w[j][i >> 2] = FASTQ ? pack_top_bytes(a[j][0], a[j][1], a[j][2], a[j][3])
+                                         : pack_low_bytes(a[j][0], a[j][1], a[j][2], a[j][3]);
             }
         }
+    }
+};
+
+__device__ __forceinline__ uint64_t v2_rows_before(uint32_t count0, uint32_t div, uint64_t t0) {
+    // control boundaries at ticks t in [0, t0) with (count0 + t) % div == 0
+    const uint64_t first = count0 == 0 ? 0 : div - count0;
+    return t0 > first ? 1 + (t0 - first - 1) / div : 0;
+}
+
+// One segment [g0, g1) of one thread's B channels.
+template <int K, int B, bool FASTQ, bool DEXT>
+__device__ __forceinline__ void v2_run_segment(const PdmV2Params &p, V2Regs<K, B> &r, uint32_t &rng, uint64_t c0,
+                                               uint64_t bank, uint64_t g0, uint64_t g1) {
+    const uint32_t L = p.ctl_div_log, div_mask = (1u << L) - 1u;
+    uint32_t cnt = (p.count0 + (uint32_t)(g0 << 4)) & div_mask;
+    uint64_t row = v2_rows_before(p.count0, 1u << L, g0 << 4);
+    const uint32_t *dext = DEXT ? p.dither_ext + bank * p.F : nullptr;
+    const bool tiled = p.layout == CPROC_CUDA_TILED;
+    for (uint64_t g = g0; g < g1; ++g) {
+        if (cnt == 0) {
+            r.boundary(p.setpoints ? p.setpoints + row * p.n : nullptr, c0, p.n, L);
+            ++row;
+        }
+        uint32_t w[B][4];
+        r.template group<FASTQ, DEXT>(rng, DEXT ? dext + (g << 4) : nullptr, p.sh, p.dmask, w);
 #pragma unroll
         for (int j = 0; j < B; ++j) {
             if (c0 + j < p.n) {
-                uint4 v = make_uint4(w[j][0], w[j][1], w[j][2], w[j][3]);
-                uint8_t *dst = p.layout == CPROC_CUDA_TILED
-                    ? p.out + ((g * p.n + c0 + j) << 4)
-                    : p.out + (c0 + j) * p.F + (g << 4);
-                st_v4_stream(dst, v);
+                uint8_t *dst = tiled ? p.out + ((g * p.n + c0 + j) << 4) : p.out + (c0 + j) * p.F + (g << 4);
+                st_v4_stream(dst, make_uint4(w[j][0], w[j][1], w[j][2], w[j][3]));
             }
         }
         cnt = (cnt + 16) & div_mask;
     }
-#pragma unroll
-    for (int j = 0; j < B; ++j) {
-        uint32_t *x = p.st + c0 + j;
-        x[0] = sp[j]; x[p.npad] = p0[j]; x[2 * p.npad] = v0[j]; x[3 * p.npad] = p1[j]; x[4 * p.npad] = v1[j];
-#pragma unroll
-        for (int k = 0; k < K; ++k) x[(5 + k) * p.npad] = s[j][k];
+}
+
+// Persistent, McNaughton-scheduled, thread == bank.
+template <int K, int B, bool FASTQ>
+__global__ void __launch_bounds__(128, 4) k_pdm_v2_persist(const PdmV2Params p) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t worker = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (worker >= p.sched.W) return;
+    uint64_t ca, ga, cb, gb;
+    const uint32_t nseg = sched_count(p.sched, worker, &ca, &ga, &cb, &gb);
+    for (uint32_t k = 0; k < nseg; ++k) {
+        const Segment sg = sched_segment(p.sched, k, nseg, ca, ga, cb, gb);
+        const uint64_t bank = sg.chain * 32 + lane;
+        const bool live = bank < p.n_banks;
+        sched_wait(p.sched, sg, lane);
+        if (live) {
+            const uint64_t c0 = bank * B;
+            V2Regs<K, B> r;
+            r.load(p.st, p.npad, c0);
+            uint32_t rng = __ldcg(p.prng + bank);
+            v2_run_segment<K, B, FASTQ, false>(p, r, rng, c0, bank, sg.g0, sg.g1);
+            r.store(p.st, p.npad, c0);
+            __stcg(p.prng + bank, rng);
+        }
+        sched_signal(p.sched, sg, lane);
     }
-    if (rng_owner && !dext) p.prng[bank] = rng;
+}
+
+// Plain grid: thread == bank (TPB) or thread == channel (B == 1, any bank size:
+// every thread of a bank replays the bank PRNG), optional external dither.
+template <int K, int B, bool TPB, bool FASTQ, bool DEXT>
+__global__ void __launch_bounds__(128) k_pdm_v2_simple(const PdmV2Params p) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (TPB ? p.n_banks : p.n_banks * p.bank_size)) return;
+    const uint64_t c0 = tid * B;
+    const uint64_t bank = TPB ? tid : tid / p.bank_size;
+    const bool rng_owner = TPB ? true : (tid % p.bank_size == 0);
+    V2Regs<K, B> r;
+    r.load(p.st, p.npad, c0);
+    uint32_t rng = p.prng[bank];
+    v2_run_segment<K, B, FASTQ, DEXT>(p, r, rng, c0, bank, 0, p.F >> 4);
+    r.store(p.st, p.npad, c0);
+    if (rng_owner && !DEXT) p.prng[bank] = rng;
 }
 
 // Any F, any count alignment, byte stores: the conformance path.
 template <int K>
 __global__ void k_pdm_v2_any(const PdmV2Params p) {
     const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= p.npad) return;
+    if (c >= p.n_banks * p.bank_size) return;
     const uint64_t bank = c / p.bank_size;
     uint32_t *x = p.st + c;
     uint32_t sp = x[0], p0 = x[p.npad], v0 = x[2 * p.npad], p1 = x[3 * p.npad], v1 = x[4 * p.npad], s[K];
@@ -173,25 +310,60 @@ __global__ void k_pdm_v2_any(const PdmV2Params p) {
     if (!dext && c % p.bank_size == 0) p.prng[bank] = rng;
 }
 
-template <int K>
-static void launch_v2_order(cproc_cuda_batch *b, const PdmV2Params &p, bool fast, bool tpb) {
+// Workers for C chains: as many warps as there are chains, up to `per_sm` warps
+// on each of the SMs; always W <= C so that Lg >= G.
+static int sched_setup(cproc_cuda_batch *b, Sched *s, uint64_t C, uint64_t G, int per_sm) {
     cproc_cuda_ctx *ctx = b->ctx;
-    int blk = ctx->pdm_block;
+    if (b->n_flags < C) {
+        if (b->d_flags) cudaFree(b->d_flags);
+        b->d_flags = nullptr; b->n_flags = 0;
+        CK(ctx, cudaMalloc(&b->d_flags, sizeof(unsigned long long) * C));
+        CK(ctx, cudaMemsetAsync(b->d_flags, 0, sizeof(unsigned long long) * C, ctx->stream));
+        b->n_flags = C;
+    }
+    uint64_t W = (uint64_t)ctx->n_sm * per_sm;
+    if (W > C) W = C;
+    s->C = C; s->G = G; s->W = W; s->Lg = ceil_div_u64(C * G, W);
+    s->flags = b->d_flags;
+    s->epoch = ++b->epoch;
+    return 0;
+}
+
+template <int K, bool FASTQ>
+static int launch_v2_order(cproc_cuda_batch *b, PdmV2Params &p, bool fast, bool tpb, bool dext) {
+    cproc_cuda_ctx *ctx = b->ctx;
+    const int blk = ctx->pdm_block;
     if (!fast) {
         k_pdm_v2_any<K><<<(unsigned)ceil_div_u64(p.npad, 128), 128, 0, ctx->stream>>>(p);
-        return;
+        return 0;
     }
-    if (tpb) {
-        unsigned grid = (unsigned)ceil_div_u64(p.n_banks, blk);
+    if (tpb && !dext && ctx->pdm_persist) {
+        const uint64_t C = ceil_div_u64(p.n_banks, 32);
+        int rc = sched_setup(b, &p.sched, C, p.F >> 4, 4 * ctx->pdm_warps_per_smsp);
+        if (rc) return rc;
+        const unsigned grid = (unsigned)ceil_div_u64(p.sched.W, 4);
         switch (p.bank_size) {
-        case 1: k_pdm_v2<K, 1, true><<<grid, blk, 0, ctx->stream>>>(p); break;
-        case 2: k_pdm_v2<K, 2, true><<<grid, blk, 0, ctx->stream>>>(p); break;
-        case 3: k_pdm_v2<K, 3, true><<<grid, blk, 0, ctx->stream>>>(p); break;
-        default: k_pdm_v2<K, 4, true><<<grid, blk, 0, ctx->stream>>>(p); break;
+        case 1: k_pdm_v2_persist<K, 1, FASTQ><<<grid, 128, 0, ctx->stream>>>(p); break;
+        case 2: k_pdm_v2_persist<K, 2, FASTQ><<<grid, 128, 0, ctx->stream>>>(p); break;
+        case 3: k_pdm_v2_persist<K, 3, FASTQ><<<grid, 128, 0, ctx->stream>>>(p); break;
+        default: k_pdm_v2_persist<K, 4, FASTQ><<<grid, 128, 0, ctx->stream>>>(p); break;
         }
-    } else {
-        k_pdm_v2<K, 1, false><<<(unsigned)ceil_div_u64(p.npad, blk), blk, 0, ctx->stream>>>(p);
+        return 0;
     }
+#define V2_SIMPLE(BB, TT) do { \
+        const unsigned grid = (unsigned)ceil_div_u64((TT) ? p.n_banks : p.n_banks * p.bank_size, blk); \
+        if (dext) k_pdm_v2_simple<K, BB, TT, FASTQ, true><<<grid, blk, 0, ctx->stream>>>(p); \
+        else k_pdm_v2_simple<K, BB, TT, FASTQ, false><<<grid, blk, 0, ctx->stream>>>(p); } while (0)
+    if (tpb) {
+        switch (p.bank_size) {
+        case 1: V2_SIMPLE(1, true); break;
+        case 2: V2_SIMPLE(2, true); break;
+        case 3: V2_SIMPLE(3, true); break;
+        default: V2_SIMPLE(4, true); break;
+        }
+    } else V2_SIMPLE(1, false);
+#undef V2_SIMPLE
+    return 0;
 }
 
 int launch_pdm_v2(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
@@ -202,9 +374,11 @@ int launch_pdm_v2(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     if (F == 0) return 0;
     uint32_t div = 1u << c.ctl_div_log;
     if (io->ctl) {
-        // rows consumed = control boundaries met in [count, count+F)
-        uint64_t first = b->count == 0 ? 0 : div - b->count;
-        uint64_t rows = F > first ? 1 + (F - first - 1) / div : 0;
+        uint64_t rows = 0;
+        {   // rows consumed = control boundaries met in [count, count+F)
+            uint64_t first = b->count == 0 ? 0 : div - b->count;
+            rows = F > first ? 1 + (F - first - 1) / div : 0;
+        }
         if (rows > io->n_ctl) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_v2: run crosses %llu control boundaries but ctl has %u rows", (unsigned long long)rows, io->n_ctl);
     }
     PdmV2Params p;
@@ -212,16 +386,23 @@ int launch_pdm_v2(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     p.prng = b->d_prng; p.dither_ext = (const uint32_t *)io->in2; p.setpoints = (const uint32_t *)io->ctl;
     p.out = (uint8_t *)io->out; p.F = F; p.count0 = b->count; p.ctl_div_log = c.ctl_div_log; p.sh = c.out_shift;
     p.dmask = c.dither_mask; p.layout = io->layout;
-    bool aligned_ptr = ((uintptr_t)io->out & 15) == 0 && (!io->in2 || ((uintptr_t)io->in2 & 15) == 0);
-    bool fast = (F & 15) == 0 && (b->count & 15) == 0 && c.ctl_div_log >= 4 && aligned_ptr &&
-                (io->layout == CPROC_CUDA_TILED || io->layout == CPROC_CUDA_PLANAR);
-    bool tpb = ctx->pdm_tpb && c.bank_size <= 4;
+    p.sched = Sched{};
+    const bool aligned_ptr = ((uintptr_t)io->out & 15) == 0 && (!io->in2 || ((uintptr_t)io->in2 & 15) == 0);
+    const bool fast = (F & 15) == 0 && (b->count & 15) == 0 && c.ctl_div_log >= 4 && aligned_ptr &&
+                      (io->layout == CPROC_CUDA_TILED || io->layout == CPROC_CUDA_PLANAR);
+    const bool tpb = ctx->pdm_tpb && c.bank_size <= 4;
+    const bool fastq = c.out_shift == 24 && (c.dither_mask & 0xFF000000u) == 0;
+    const bool dext = io->in2 != nullptr;
+    int rc;
+#define V2_ORDER(KK) (fastq ? launch_v2_order<KK, true>(b, p, fast, tpb, dext) : launch_v2_order<KK, false>(b, p, fast, tpb, dext))
     switch (c.order) {
-    case 1: launch_v2_order<1>(b, p, fast, tpb); break;
-    case 2: launch_v2_order<2>(b, p, fast, tpb); break;
-    case 3: launch_v2_order<3>(b, p, fast, tpb); break;
-    default: launch_v2_order<4>(b, p, fast, tpb); break;
+    case 1: rc = V2_ORDER(1); break;
+    case 2: rc = V2_ORDER(2); break;
+    case 3: rc = V2_ORDER(3); break;
+    default: rc = V2_ORDER(4); break;
     }
+#undef V2_ORDER
+    if (rc) return rc;
     CK_LAUNCH(ctx, "k_pdm_v2");
     b->count = (uint32_t)((b->count + F) & (div - 1));
     return 0;
@@ -238,60 +419,103 @@ struct PdmV1Params {
     uint32_t *out;
     uint64_t F;
     uint32_t dmask, layout;
+    Sched sched;
 };
 
-// accu += x with carry out shifted into the LSB of bits (ARM: adds + adc;
+// accu += x with the carry out shifted into the LSB of bits (ARM: adds + adc;
 // mod_pdm.c:236-240 uses rrx, i.e. the MSB: the final __brev gives the same
 // time order LSB-first).
 __device__ __forceinline__ void add_carry_shift(uint32_t &accu, uint32_t &bits, uint32_t x) {
     asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %1;" : "+r"(accu), "+r"(bits) : "r"(x));
 }
 
-template <int B, bool TPB>
-__global__ void __launch_bounds__(128) k_pdm_v1(const PdmV1Params p) {
+// 32 ticks of B channels -> one packed word per channel
+template <int B, bool DEXT>
+__device__ __forceinline__ void v1_word(const uint32_t (&sp)[B], uint32_t (&acc)[B], uint32_t &rng, const uint32_t *dext32,
+                                        uint32_t dmask, uint32_t (&wv)[B]) {
+    uint32_t bits[B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) bits[j] = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        uint32_t d;
+        if (DEXT) d = dext32[i] & dmask;
+        else { rng = xorshift32_step(rng); d = rng & dmask; }       // mod_pdm.c:261
+#pragma unroll
+        for (int j = 0; j < B; ++j) add_carry_shift(acc[j], bits[j], sp[j] + d);   // :235-240
+    }
+#pragma unroll
+    for (int j = 0; j < B; ++j) wv[j] = __brev(bits[j]);
+}
+
+// words [w0, w1) of one thread's B channels
+template <int B, bool DEXT>
+__device__ __forceinline__ void v1_run_segment(const PdmV1Params &p, const uint32_t (&sp)[B], uint32_t (&acc)[B], uint32_t &rng,
+                                               uint64_t c0, uint64_t bank, uint64_t w0, uint64_t w1) {
+    const uint64_t words = p.F >> 5;
+    const uint32_t *dext = DEXT ? p.dither_ext + bank * p.F : nullptr;
+    if (p.layout == CPROC_CUDA_TILED) {
+        for (uint64_t g = w0; g < w1; g += 4) {
+            uint32_t q[4][B];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v1_word<B, DEXT>(sp, acc, rng, DEXT ? dext + ((g + k) << 5) : nullptr, p.dmask, q[k]);
+#pragma unroll
+            for (int j = 0; j < B; ++j)
+                if (c0 + j < p.n) st_v4_stream(p.out + (((g >> 2) * p.n + c0 + j) << 2), make_uint4(q[0][j], q[1][j], q[2][j], q[3][j]));
+        }
+    } else {
+        const bool il = p.layout == CPROC_CUDA_INTERLEAVED;
+        for (uint64_t g = w0; g < w1; ++g) {
+            uint32_t wv[B];
+            v1_word<B, DEXT>(sp, acc, rng, DEXT ? dext + (g << 5) : nullptr, p.dmask, wv);
+#pragma unroll
+            for (int j = 0; j < B; ++j)
+                if (c0 + j < p.n) __stcs(p.out + (il ? g * p.n + c0 + j : (c0 + j) * words + g), wv[j]);
+        }
+    }
+}
+
+template <int B>
+__global__ void __launch_bounds__(128, 4) k_pdm_v1_persist(const PdmV1Params p, uint32_t unit_words) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t worker = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (worker >= p.sched.W) return;
+    uint64_t ca, ga, cb, gb;
+    const uint32_t nseg = sched_count(p.sched, worker, &ca, &ga, &cb, &gb);
+    for (uint32_t k = 0; k < nseg; ++k) {
+        const Segment sg = sched_segment(p.sched, k, nseg, ca, ga, cb, gb);
+        const uint64_t bank = sg.chain * 32 + lane;
+        sched_wait(p.sched, sg, lane);
+        if (bank < p.n_banks) {
+            const uint64_t c0 = bank * B;
+            uint32_t sp[B], acc[B];
+#pragma unroll
+            for (int j = 0; j < B; ++j) { sp[j] = __ldcg(p.st + c0 + j); acc[j] = __ldcg(p.st + p.npad + c0 + j); }
+            uint32_t rng = __ldcg(p.prng + bank);
+            v1_run_segment<B, false>(p, sp, acc, rng, c0, bank, sg.g0 * unit_words, sg.g1 * unit_words);
+#pragma unroll
+            for (int j = 0; j < B; ++j) __stcg(p.st + p.npad + c0 + j, acc[j]);
+            __stcg(p.prng + bank, rng);
+        }
+        sched_signal(p.sched, sg, lane);
+    }
+}
+
+template <int B, bool TPB, bool DEXT>
+__global__ void __launch_bounds__(128) k_pdm_v1_simple(const PdmV1Params p) {
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (TPB ? p.n_banks : p.n_banks * p.bank_size)) return;
     const uint64_t c0 = tid * B;
-    if (c0 >= p.npad) return;
     const uint64_t bank = TPB ? tid : tid / p.bank_size;
     const bool rng_owner = TPB ? true : (tid % p.bank_size == 0);
     uint32_t sp[B], acc[B];
 #pragma unroll
     for (int j = 0; j < B; ++j) { sp[j] = p.st[c0 + j]; acc[j] = p.st[p.npad + c0 + j]; }
     uint32_t rng = p.prng[bank];
-    const uint32_t dmask = p.dmask;
-    const uint32_t *dext = p.dither_ext ? p.dither_ext + bank * p.F : nullptr;
-    const uint64_t words = p.F >> 5;
-    const bool tiled = p.layout == CPROC_CUDA_TILED;
-    uint32_t w0[B], w1[B], w2[B];
-    for (uint64_t g = 0; g < words; ++g) {
-        uint32_t bits[B];
-#pragma unroll
-        for (int j = 0; j < B; ++j) bits[j] = 0;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            uint32_t d;
-            if (dext) d = dext[g * 32 + i] & dmask;
-            else { rng = xorshift32_step(rng); d = rng & dmask; }   // mod_pdm.c:261
-#pragma unroll
-            for (int j = 0; j < B; ++j) add_carry_shift(acc[j], bits[j], sp[j] + d);  // :235-240
-        }
-        const uint32_t q = (uint32_t)g & 3u;
-#pragma unroll
-        for (int j = 0; j < B; ++j) {
-            uint32_t wv = __brev(bits[j]);
-            if (tiled) {
-                if (q == 0) w0[j] = wv; else if (q == 1) w1[j] = wv; else if (q == 2) w2[j] = wv;
-                else if (c0 + j < p.n)
-                    st_v4_stream(p.out + (((g >> 2) * p.n + c0 + j) << 2), make_uint4(w0[j], w1[j], w2[j], wv));
-            } else if (c0 + j < p.n) {
-                uint64_t idx = p.layout == CPROC_CUDA_INTERLEAVED ? g * p.n + c0 + j : (c0 + j) * words + g;
-                p.out[idx] = wv;
-            }
-        }
-    }
+    v1_run_segment<B, DEXT>(p, sp, acc, rng, c0, bank, 0, p.F >> 5);
 #pragma unroll
     for (int j = 0; j < B; ++j) p.st[p.npad + c0 + j] = acc[j];
-    if (rng_owner && !dext) p.prng[bank] = rng;
+    if (rng_owner && !DEXT) p.prng[bank] = rng;
 }
 
 int launch_pdm_v1(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
@@ -300,22 +524,41 @@ int launch_pdm_v1(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     if (!io->out) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_v1: out is NULL");
     if (F & 31) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_v1: F must be a multiple of 32 (packed bit output)");
     if (io->layout == CPROC_CUDA_TILED && (F & 127)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_v1: TILED needs F %% 128 == 0");
+    if (io->layout == CPROC_CUDA_TILED && ((uintptr_t)io->out & 15)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_v1: TILED needs a 16-byte aligned out");
     if (F == 0) return 0;
     PdmV1Params p;
     p.st = b->d_state; p.npad = b->npad; p.n = b->n; p.n_banks = b->n_banks; p.bank_size = c.bank_size;
     p.prng = b->d_prng; p.dither_ext = (const uint32_t *)io->in2; p.out = (uint32_t *)io->out; p.F = F;
     p.dmask = c.dither_mask; p.layout = io->layout;
-    int blk = ctx->pdm_block;
-    if (ctx->pdm_tpb && c.bank_size <= 4) {
-        unsigned grid = (unsigned)ceil_div_u64(p.n_banks, blk);
+    p.sched = Sched{};
+    const int blk = ctx->pdm_block;
+    const bool dext = io->in2 != nullptr;
+    const bool tpb = ctx->pdm_tpb && c.bank_size <= 4;
+    if (tpb && !dext && ctx->pdm_persist && (F & 127) == 0) {
+        const uint64_t C = ceil_div_u64(p.n_banks, 32);
+        int rc = sched_setup(b, &p.sched, C, F >> 7, 4 * ctx->pdm_warps_per_smsp);   // unit = 128 ticks = 4 words
+        if (rc) return rc;
+        const unsigned grid = (unsigned)ceil_div_u64(p.sched.W, 4);
         switch (c.bank_size) {
-        case 1: k_pdm_v1<1, true><<<grid, blk, 0, ctx->stream>>>(p); break;
-        case 2: k_pdm_v1<2, true><<<grid, blk, 0, ctx->stream>>>(p); break;
-        case 3: k_pdm_v1<3, true><<<grid, blk, 0, ctx->stream>>>(p); break;
-        default: k_pdm_v1<4, true><<<grid, blk, 0, ctx->stream>>>(p); break;
+        case 1: k_pdm_v1_persist<1><<<grid, 128, 0, ctx->stream>>>(p, 4); break;
+        case 2: k_pdm_v1_persist<2><<<grid, 128, 0, ctx->stream>>>(p, 4); break;
+        case 3: k_pdm_v1_persist<3><<<grid, 128, 0, ctx->stream>>>(p, 4); break;
+        default: k_pdm_v1_persist<4><<<grid, 128, 0, ctx->stream>>>(p, 4); break;
         }
     } else {
-        k_pdm_v1<1, false><<<(unsigned)ceil_div_u64(p.npad, blk), blk, 0, ctx->stream>>>(p);
+#define V1_SIMPLE(BB, TT) do { \
+        const unsigned grid = (unsigned)ceil_div_u64((TT) ? p.n_banks : p.n_banks * p.bank_size, blk); \
+        if (dext) k_pdm_v1_simple<BB, TT, true><<<grid, blk, 0, ctx->stream>>>(p); \
+        else k_pdm_v1_simple<BB, TT, false><<<grid, blk, 0, ctx->stream>>>(p); } while (0)
+        if (tpb) {
+            switch (c.bank_size) {
+            case 1: V1_SIMPLE(1, true); break;
+            case 2: V1_SIMPLE(2, true); break;
+            case 3: V1_SIMPLE(3, true); break;
+            default: V1_SIMPLE(4, true); break;
+            }
+        } else V1_SIMPLE(1, false);
+#undef V1_SIMPLE
     }
     CK_LAUNCH(ctx, "k_pdm_v1");
     return 0;

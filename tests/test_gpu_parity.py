@@ -81,6 +81,8 @@ def _v2_case(st, ctx, oracle, order, bank, N, F, layout, count0, use_setp, use_d
         b.free()
         ctx.set_option("pdm_tpb", 1)
         ctx.set_option("pdm_block", 64)
+        ctx.set_option("pdm_persist", 1)
+        ctx.set_option("pdm_warps_per_smsp", 1)
 
 
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
@@ -90,11 +92,20 @@ def test_pdm_v2_orders_banks(st, ctx, oracle, order, bank):
 
 
 @pytest.mark.parametrize("layout", ["PLANAR", "TILED"])
-@pytest.mark.parametrize("tpb", [0, 1])
+@pytest.mark.parametrize("tpb,persist", [(0, 0), (1, 0), (1, 1)])
 @pytest.mark.parametrize("blk", [32, 128])
-def test_pdm_v2_layouts_and_mappings(st, ctx, oracle, layout, tpb, blk):
+def test_pdm_v2_layouts_and_mappings(st, ctx, oracle, layout, tpb, persist, blk):
     _v2_case(st, ctx, oracle, 2, 3, N=1000, F=1024, layout=getattr(st, layout), count0=16, use_setp=True,
-             use_dext=False, opts={"pdm_tpb": tpb, "pdm_block": blk})
+             use_dext=False, opts={"pdm_tpb": tpb, "pdm_block": blk, "pdm_persist": persist})
+
+
+@pytest.mark.parametrize("N,bank,F,wps", [(65536, 3, 512, 1), (65536, 4, 256, 1), (3 * 32 * 1300 + 5, 3, 160, 1),
+                                          (3 * 32 * 1300 + 5, 3, 160, 2), (200000, 2, 64, 4), (32 * 593, 1, 1024, 1)])
+def test_pdm_v2_persistent_schedule(st, ctx, oracle, N, bank, F, wps):
+    """More chains than warp schedulers: the wrap-around schedule splits chains
+    between workers (head on one, tail on the next) and must stay bit-exact."""
+    _v2_case(st, ctx, oracle, 2, bank, N=N, F=F, layout=st.TILED, count0=48, use_setp=True, use_dext=False, ctl=6,
+             opts={"pdm_warps_per_smsp": wps})
 
 
 def test_pdm_v2_external_dither(st, ctx, oracle):
@@ -150,10 +161,11 @@ def test_pdm_v2_errors(st, ctx):
 
 
 # --------------------------------------------------------------------------- v1
-@pytest.mark.parametrize("bank,tpb", [(1, 1), (2, 1), (2, 0), (3, 1), (4, 1), (9, 1)])
+@pytest.mark.parametrize("bank,tpb,persist,N", [(1, 1, 1, 301), (2, 1, 1, 301), (2, 1, 0, 301), (2, 0, 0, 301), (3, 1, 1, 301),
+                                               (4, 1, 0, 301), (9, 1, 1, 301), (2, 1, 1, 65536), (1, 1, 1, 32 * 700 + 3)])
 @pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED", "TILED"])
-def test_pdm_v1(st, ctx, oracle, bank, tpb, layout):
-    N, F = 301, 512
+def test_pdm_v1(st, ctx, oracle, bank, tpb, persist, N, layout):
+    F = 512
     nb = (N + bank - 1) // bank
     ch0 = rng.integers(0, 2**32, (N, 2), dtype=np.uint32)
     prng0 = rng.integers(1, 2**32, nb, dtype=np.uint32)
@@ -161,6 +173,7 @@ def test_pdm_v1(st, ctx, oracle, bank, tpb, layout):
     bits = oracle.pdm_v1_run(ca, N, bank, pa, None, 0x0FFFFFFF, F)
     want = pack_bits(bits)
     ctx.set_option("pdm_tpb", tpb)
+    ctx.set_option("pdm_persist", persist)
     b = ctx.batch(st.PDM_V1, N, bank_size=bank, dither_mask=0x0FFFFFFF, layout=getattr(st, layout))
     b.upload_state(ch0); b.upload_bank(prng0)
     out = np.zeros(N * F // 32, np.uint32)
@@ -176,6 +189,7 @@ def test_pdm_v1(st, ctx, oracle, bank, tpb, layout):
     assert np.array_equal(b.download_bank()[0], pa)
     b.free()
     ctx.set_option("pdm_tpb", 1)
+    ctx.set_option("pdm_persist", 1)
 
 
 def test_pdm_v1_external_dither_and_density(st, ctx, oracle):

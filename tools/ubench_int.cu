@@ -15,6 +15,7 @@ __global__ void k(uint32_t *out, uint32_t a0, uint32_t b0) {
 #pragma unroll
     for (int i = 0; i < ILP; ++i) x[i] = a0 + threadIdx.x * (i + 1);
     uint32_t b = b0 + threadIdx.x, c = b0 * 3 + 1;
+    asm volatile(".reg .pred p;");
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
         for (int i = 0; i < ILP; ++i) {
@@ -31,6 +32,21 @@ __global__ void k(uint32_t *out, uint32_t a0, uint32_t b0) {
             if (OP == 9) { asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(b));                   // IADD + FFMA mix
                            asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+r"(x[(i + 1) % ILP]) : "r"(b), "r"(c)); }
             if (OP == 10) asm volatile("cvt.rn.f32.s32 %0, %0;" : "+r"(x[i]));                          // I2F
+            if (OP == 11) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(b), "r"(c));  // LOP3 + IMAD mix
+                            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[(i + 1) % ILP]) : "r"(b), "r"(c)); }
+            if (OP == 12) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(b), "r"(c));  // LOP3 + SHF mix
+                            asm volatile("shf.l.wrap.b32 %0, %0, %1, %2;" : "+r"(x[(i + 1) % ILP]) : "r"(b), "r"(c)); }
+            if (OP == 13) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(b), "r"(c));  // LOP3 + PRMT mix
+                            asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(x[(i + 1) % ILP]) : "r"(b), "r"(c)); }
+            if (OP == 14) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(b), "r"(c));  // LOP3 + IADD3 mix
+                            asm volatile("add.u32 %0, %0, %1;" : "+r"(x[(i + 1) % ILP]) : "r"(b)); }
+            if (OP == 15) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(b), "r"(c));  // LOP3 + FFMA mix
+                            asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+r"(x[(i + 1) % ILP]) : "r"(b), "r"(c)); }
+            if (OP == 16) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(b), "r"(c));  // LOP3 + 2x IADD3
+                            asm volatile("add.u32 %0, %0, %1;" : "+r"(x[(i + 1) % ILP]) : "r"(b));
+                            asm volatile("add.u32 %0, %0, %1;" : "+r"(x[(i + 2) % ILP]) : "r"(c)); }
+            if (OP == 17) asm volatile("add.f32 %0, %0, %1;" : "+r"(x[i]) : "r"(b));                     // FADD
+            if (OP == 18) asm volatile("setp.lt.f32 p, %0, %1;\n\tselp.b32 %0, %1, %2, p;" : "+r"(x[i]) : "r"(b), "r"(c)); // FSETP+SEL
         }
     }
     uint32_t s = b + c;
@@ -72,5 +88,13 @@ int main() {
     run<7>("FFMA", 1, d, sms, clk);
     run<9>("IADD3+FFMA", 2, d, sms, clk);
     run<10>("I2F", 1, d, sms, clk);
+    run<11>("LOP3+IMAD", 2, d, sms, clk);
+    run<12>("LOP3+SHF", 2, d, sms, clk);
+    run<13>("LOP3+PRMT", 2, d, sms, clk);
+    run<14>("LOP3+IADD3", 2, d, sms, clk);
+    run<15>("LOP3+FFMA", 2, d, sms, clk);
+    run<16>("LOP3+2IADD3", 3, d, sms, clk);
+    run<17>("FADD", 1, d, sms, clk);
+    run<18>("FSETP+SEL", 2, d, sms, clk);
     return 0;
 }
