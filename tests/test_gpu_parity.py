@@ -92,7 +92,7 @@ def test_pdm_v2_orders_banks(st, ctx, oracle, order, bank):
 
 
 @pytest.mark.parametrize("layout", ["PLANAR", "TILED"])
-@pytest.mark.parametrize("tpb,persist", [(0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("tpb,persist", [(0, 0), (1, 0), (1, 2), (1, 1)])
 @pytest.mark.parametrize("blk", [32, 128])
 def test_pdm_v2_layouts_and_mappings(st, ctx, oracle, layout, tpb, persist, blk):
     _v2_case(st, ctx, oracle, 2, 3, N=1000, F=1024, layout=getattr(st, layout), count0=16, use_setp=True,
@@ -105,7 +105,7 @@ def test_pdm_v2_persistent_schedule(st, ctx, oracle, N, bank, F, wps):
     """More chains than warp schedulers: the wrap-around schedule splits chains
     between workers (head on one, tail on the next) and must stay bit-exact."""
     _v2_case(st, ctx, oracle, 2, bank, N=N, F=F, layout=st.TILED, count0=48, use_setp=True, use_dext=False, ctl=6,
-             opts={"pdm_warps_per_smsp": wps})
+             opts={"pdm_warps_per_smsp": wps, "pdm_persist": 2})
 
 
 def test_pdm_v2_external_dither(st, ctx, oracle):
@@ -161,8 +161,8 @@ def test_pdm_v2_errors(st, ctx):
 
 
 # --------------------------------------------------------------------------- v1
-@pytest.mark.parametrize("bank,tpb,persist,N", [(1, 1, 1, 301), (2, 1, 1, 301), (2, 1, 0, 301), (2, 0, 0, 301), (3, 1, 1, 301),
-                                               (4, 1, 0, 301), (9, 1, 1, 301), (2, 1, 1, 65536), (1, 1, 1, 32 * 700 + 3)])
+@pytest.mark.parametrize("bank,tpb,persist,N", [(1, 1, 2, 301), (2, 1, 2, 301), (2, 1, 0, 301), (2, 0, 0, 301), (3, 1, 1, 301),
+                                               (4, 1, 0, 301), (9, 1, 2, 301), (2, 1, 2, 65536), (1, 1, 2, 32 * 700 + 3)])
 @pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED", "TILED"])
 def test_pdm_v1(st, ctx, oracle, bank, tpb, persist, N, layout):
     F = 512

@@ -22,7 +22,7 @@ def t_run(b, reps=3, **kw):
 
 print("v2 (pdm2 glide), N=%d F=%d" % (N, F))
 for bank in (3, 4, 1):
-    for tpb, persist, wps, blk in ((1, 1, 1, 64), (1, 1, 2, 64), (1, 0, 1, 64), (0, 0, 1, 64), (0, 0, 1, 128)):
+    for tpb, persist, wps, blk in ((1, 2, 1, 64), (1, 2, 2, 64), (1, 0, 1, 64), (0, 0, 1, 64)):
             for layout in (st.TILED, st.PLANAR):
                 ctx.set_option("pdm_tpb", tpb); ctx.set_option("pdm_block", blk); ctx.set_option("pdm_persist", persist); ctx.set_option("pdm_warps_per_smsp", wps)
                 b = ctx.batch(st.PDM_V2, N, order=2, bank_size=bank, ctl_div_log=12, layout=layout)
@@ -37,7 +37,7 @@ for order in (1, 3, 4):
     b.free()
 print("v1 (carry-bit)")
 for bank in (2, 1):
-    for tpb, persist, wps, blk in ((1, 1, 1, 64), (1, 1, 2, 64), (1, 0, 1, 64), (0, 0, 1, 64)):
+    for tpb, persist, wps, blk in ((1, 2, 1, 64), (1, 2, 2, 64), (1, 0, 1, 64), (0, 0, 1, 64)):
             for layout in (st.TILED, st.INTERLEAVED, st.PLANAR):
                 ctx.set_option("pdm_tpb", tpb); ctx.set_option("pdm_block", blk); ctx.set_option("pdm_persist", persist); ctx.set_option("pdm_warps_per_smsp", wps)
                 b = ctx.batch(st.PDM_V1, N, bank_size=bank, dither_mask=0x0FFFFFFF, layout=layout)
