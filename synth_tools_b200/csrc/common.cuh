@@ -20,6 +20,7 @@ struct cproc_cuda_ctx {
     int pdm_block = 64;       // threads per block of the PDM kernels
     int pdm_tpb = 1;          // 1: thread-per-bank when bank_size <= 4, 0: thread-per-channel
     int pdm_stage = 1;        // 1: smem-staged full-line stores for PLANAR
+    int pdm_ws = 1;           // 1: warp-specialised v2 kernel (PRNG producer warp + channel consumer warps)
     int pdm_persist = 1;      // 1: persistent McNaughton-scheduled kernels when thread == bank
     int pdm_warps_per_smsp = 1;
     int n_sm = CPROC_N_SM;

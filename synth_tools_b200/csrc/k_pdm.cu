@@ -310,6 +310,104 @@ __global__ void k_pdm_v2_any(const PdmV2Params p) {
     if (!dext && c % p.bank_size == 0) p.prng[bank] = rng;
 }
 
+// Warp-specialised: one block = 32 banks = 32*B channels.  One PRODUCER warp
+// (lane == bank) runs the bank PRNGs and stages masked dither words in shared
+// memory, 64 ticks ahead, double buffered; B CONSUMER warps (lane == channel)
+// run the modulators and read their bank's dither as a 128-bit broadcast load
+// per 4 ticks.  The PRNG is still computed once per bank, but the chip now holds
+// (B+1)/B warps per 32 channels instead of 1/B, which is what the issue slots
+// need: a single warp per scheduler only reaches IPC ~0.4 on this loop
+// (profiles/r1_k_pdm_v2_persist_details.txt).  Hand-off: named barriers
+// FULL[s] / EMPTY[s] per buffer slot.
+#define WS_T 64                  // ticks per dither batch
+#define WS_BAR_FULL 1            // barrier ids 1,2
+#define WS_BAR_EMPTY 3           // barrier ids 3,4
+template <int ID, int N> __device__ __forceinline__ void bar_sync_i() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+template <int ID, int N> __device__ __forceinline__ void bar_arrive_i() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+// slot s in {0,1}: immediate barrier ids so the CTA only reserves barriers 0..4
+template <int BASE, int N> __device__ __forceinline__ void bar_sync_n(uint32_t s) { if (s) bar_sync_i<BASE + 1, N>(); else bar_sync_i<BASE, N>(); }
+template <int BASE, int N> __device__ __forceinline__ void bar_arrive_n(uint32_t s) { if (s) bar_arrive_i<BASE + 1, N>(); else bar_arrive_i<BASE, N>(); }
+
+template <int K, int B, bool FASTQ>
+__global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws(const PdmV2Params p) {
+    __shared__ __align__(16) uint32_t dbuf[2][WS_T / 4][32][4];
+    constexpr int NT = 32 * (B + 1);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t prod_warp = blockIdx.x % (B + 1);      // spread producers over the 4 schedulers
+    const uint64_t bank0 = (uint64_t)blockIdx.x * 32;
+    const uint64_t batches = p.F / WS_T;
+    if (warp == prod_warp) {
+        const uint64_t bank = bank0 + lane;
+        const bool live = bank < p.n_banks;
+        uint32_t rng = live ? p.prng[bank] : 1u;
+        const uint32_t dmask = p.dmask;
+        for (uint64_t bt = 0; bt < batches; ++bt) {
+            const uint32_t s = (uint32_t)bt & 1u;
+            if (bt >= 2) bar_sync_n<WS_BAR_EMPTY, NT>(s);            // slot drained by the consumers
+#pragma unroll
+            for (int q = 0; q < WS_T / 4; ++q) {
+                uint4 v;
+                rng = xorshift32_step(rng); v.x = rng & dmask;          // mod_pdm_pwm.c:127
+                rng = xorshift32_step(rng); v.y = rng & dmask;
+                rng = xorshift32_step(rng); v.z = rng & dmask;
+                rng = xorshift32_step(rng); v.w = rng & dmask;
+                *reinterpret_cast<uint4 *>(&dbuf[s][q][lane][0]) = v;
+            }
+            __threadfence_block();
+            bar_arrive_n<WS_BAR_FULL, NT>(s);
+        }
+        if (live) p.prng[bank] = rng;
+        return;
+    }
+    const uint32_t cw = warp - (warp > prod_warp ? 1u : 0u);          // consumer index 0..B-1
+    const uint32_t cl = cw * 32 + lane;                               // channel within the block
+    const uint32_t bl = cl / B;                                       // its bank within the block
+    const uint64_t c = bank0 * B + cl;
+    const bool live = c < p.n_banks * B;                              // inside the padded SoA rows
+    V2Regs<K, 1> r;
+    if (live) r.load(p.st, p.npad, c);
+    else { r.sp[0] = r.p0[0] = r.v0[0] = r.p1[0] = r.v1[0] = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) r.s[0][k] = 0; }
+    const uint32_t L = p.ctl_div_log, div_mask = (1u << L) - 1u;
+    uint32_t cnt = p.count0;
+    uint64_t row = 0;
+    const bool tiled = p.layout == CPROC_CUDA_TILED;
+    const bool store = c < p.n;
+    for (uint64_t bt = 0; bt < batches; ++bt) {
+        const uint32_t s = (uint32_t)bt & 1u;
+        bar_sync_n<WS_BAR_FULL, NT>(s);
+#pragma unroll
+        for (int gq = 0; gq < WS_T / 16; ++gq) {
+            if (cnt == 0) {
+                r.boundary(p.setpoints ? p.setpoints + row * p.n : nullptr, c, p.n, L);
+                ++row;
+            }
+            uint32_t w[4];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+                const uint4 dv = *reinterpret_cast<const uint4 *>(&dbuf[s][gq * 4 + i4][bl][0]);
+                const uint32_t d[4] = {dv.x, dv.y, dv.z, dv.w};
+                uint32_t a[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    r.p0[0] += r.v0[0];                               // :101-104
+                    a[i] = FASTQ ? pdm_step_q24<K>(r.s[0], r.p0[0], d[i]) : pdm_step<K>(r.s[0], r.p0[0], p.sh, d[i]);
+                }
+                w[i4] = FASTQ ? pack_top_bytes(a[0], a[1], a[2], a[3]) : pack_low_bytes(a[0], a[1], a[2], a[3]);
+            }
+            if (store) {
+                const uint64_t g = bt * (WS_T / 16) + gq;
+                uint8_t *dst = tiled ? p.out + ((g * p.n + c) << 4) : p.out + c * p.F + (g << 4);
+                st_v4_stream(dst, make_uint4(w[0], w[1], w[2], w[3]));
+            }
+            cnt = (cnt + 16) & div_mask;
+        }
+        if (bt + 2 < batches) bar_arrive_n<WS_BAR_EMPTY, NT>(s);
+    }
+    if (live) r.store(p.st, p.npad, c);
+}
+
 // Workers for C chains: as many warps as there are chains, up to `per_sm` warps
 // on each of the SMs; always W <= C so that Lg >= G.
 static int sched_setup(cproc_cuda_batch *b, Sched *s, uint64_t C, uint64_t G, int per_sm) {
@@ -348,6 +446,16 @@ static int launch_v2_order(cproc_cuda_batch *b, PdmV2Params &p, bool fast, bool 
         return 0;
     }
     const uint64_t C = ceil_div_u64(p.n_banks, 32);
+    if (tpb && !dext && ctx->pdm_ws && (p.F % WS_T) == 0) {
+        const unsigned grid = (unsigned)C;
+        switch (p.bank_size) {
+        case 1: k_pdm_v2_ws<K, 1, FASTQ><<<grid, 64, 0, ctx->stream>>>(p); break;
+        case 2: k_pdm_v2_ws<K, 2, FASTQ><<<grid, 96, 0, ctx->stream>>>(p); break;
+        case 3: k_pdm_v2_ws<K, 3, FASTQ><<<grid, 128, 0, ctx->stream>>>(p); break;
+        default: k_pdm_v2_ws<K, 4, FASTQ><<<grid, 160, 0, ctx->stream>>>(p); break;
+        }
+        return 0;
+    }
     if (tpb && !dext && persist_wanted(ctx, C)) {
         int rc = sched_setup(b, &p.sched, C, p.F >> 4, 4 * ctx->pdm_warps_per_smsp);
         if (rc) return rc;

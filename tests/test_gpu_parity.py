@@ -83,6 +83,7 @@ def _v2_case(st, ctx, oracle, order, bank, N, F, layout, count0, use_setp, use_d
         ctx.set_option("pdm_block", 64)
         ctx.set_option("pdm_persist", 1)
         ctx.set_option("pdm_warps_per_smsp", 1)
+        ctx.set_option("pdm_ws", 1)
 
 
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
@@ -92,11 +93,20 @@ def test_pdm_v2_orders_banks(st, ctx, oracle, order, bank):
 
 
 @pytest.mark.parametrize("layout", ["PLANAR", "TILED"])
-@pytest.mark.parametrize("tpb,persist", [(0, 0), (1, 0), (1, 2), (1, 1)])
+@pytest.mark.parametrize("tpb,persist,ws", [(0, 0, 0), (1, 0, 0), (1, 2, 0), (1, 1, 0), (1, 1, 1)])
 @pytest.mark.parametrize("blk", [32, 128])
-def test_pdm_v2_layouts_and_mappings(st, ctx, oracle, layout, tpb, persist, blk):
+def test_pdm_v2_layouts_and_mappings(st, ctx, oracle, layout, tpb, persist, ws, blk):
     _v2_case(st, ctx, oracle, 2, 3, N=1000, F=1024, layout=getattr(st, layout), count0=16, use_setp=True,
-             use_dext=False, opts={"pdm_tpb": tpb, "pdm_block": blk, "pdm_persist": persist})
+             use_dext=False, opts={"pdm_tpb": tpb, "pdm_block": blk, "pdm_persist": persist, "pdm_ws": ws})
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+@pytest.mark.parametrize("bank", [1, 2, 3, 4])
+def test_pdm_v2_warp_specialised(st, ctx, oracle, order, bank):
+    """Producer/consumer kernel: ragged channel count, several dither batches,
+    control boundaries inside a batch."""
+    _v2_case(st, ctx, oracle, order, bank, N=3001, F=448, layout=st.TILED, count0=32, use_setp=True, use_dext=False,
+             ctl=5, opts={"pdm_ws": 1})
 
 
 @pytest.mark.parametrize("N,bank,F,wps", [(65536, 3, 512, 1), (65536, 4, 256, 1), (3 * 32 * 1300 + 5, 3, 160, 1),
@@ -105,7 +115,7 @@ def test_pdm_v2_persistent_schedule(st, ctx, oracle, N, bank, F, wps):
     """More chains than warp schedulers: the wrap-around schedule splits chains
     between workers (head on one, tail on the next) and must stay bit-exact."""
     _v2_case(st, ctx, oracle, 2, bank, N=N, F=F, layout=st.TILED, count0=48, use_setp=True, use_dext=False, ctl=6,
-             opts={"pdm_warps_per_smsp": wps, "pdm_persist": 2})
+             opts={"pdm_warps_per_smsp": wps, "pdm_persist": 2, "pdm_ws": 0})
 
 
 def test_pdm_v2_external_dither(st, ctx, oracle):

@@ -22,15 +22,16 @@ def t_run(b, reps=3, **kw):
 
 print("v2 (pdm2 glide), N=%d F=%d" % (N, F))
 for bank in (3, 4, 1):
-    for tpb, persist, wps, blk in ((1, 2, 1, 64), (1, 2, 2, 64), (1, 0, 1, 64), (0, 0, 1, 64)):
+    for tpb, persist, wps, blk in ((1, 3, 1, 64), (1, 2, 1, 64), (1, 0, 1, 64), (0, 0, 1, 64)):
             for layout in (st.TILED, st.PLANAR):
+                ctx.set_option("pdm_ws", 1 if persist == 3 else 0); persist = min(persist, 2)
                 ctx.set_option("pdm_tpb", tpb); ctx.set_option("pdm_block", blk); ctx.set_option("pdm_persist", persist); ctx.set_option("pdm_warps_per_smsp", wps)
                 b = ctx.batch(st.PDM_V2, N, order=2, bank_size=bank, ctl_div_log=12, layout=layout)
                 ms = t_run(b, ctl=d_sp, n_ctl=rows, out=d_out)
                 print("bank=%d tpb=%d persist=%d wps=%d blk=%3d layout=%d : %8.3f ms  %7.3f Gsamples/s" % (bank, tpb, persist, wps, blk, layout, ms, N * F / ms / 1e6))
                 b.free()
 for order in (1, 3, 4):
-    ctx.set_option("pdm_tpb", 1); ctx.set_option("pdm_block", 64); ctx.set_option("pdm_persist", 1); ctx.set_option("pdm_warps_per_smsp", 1)
+    ctx.set_option("pdm_tpb", 1); ctx.set_option("pdm_block", 64); ctx.set_option("pdm_persist", 1); ctx.set_option("pdm_warps_per_smsp", 1); ctx.set_option("pdm_ws", 1)
     b = ctx.batch(st.PDM_V2, N, order=order, bank_size=3, ctl_div_log=12, layout=st.TILED)
     ms = t_run(b, ctl=d_sp, n_ctl=rows, out=d_out)
     print("order=%d bank=3 tpb=1 blk=64 tiled: %8.3f ms %7.3f Gsamples/s" % (order, ms, N * F / ms / 1e6))
