@@ -41,12 +41,18 @@ __device__ __forceinline__ uint32_t pdm_step(uint32_t (&s)[K], uint32_t in, uint
 
 // out_shift == 24 and dither below bit 24: out_a = (s & 0xFF000000) | d is the
 // same number as (out_q << 24) + d (no carries), and out_q is its top byte.
+// `m1` is the constant 0xFFFFFFFF passed through a kernel parameter so that
+// ptxas keeps `in - a` as an IMAD (in + a * m1) on the FMA pipe: the loop is
+// bound by the ALU pipe (LOP3 / PRMT / IADD3 share 64 lanes/clk/SM, measured in
+// tools/ubench_int.cu), the FMA pipe has slack.
 template <int K>
-__device__ __forceinline__ uint32_t pdm_step_q24(uint32_t (&s)[K], uint32_t in, uint32_t d) {
+__device__ __forceinline__ uint32_t pdm_step_q24(uint32_t (&s)[K], uint32_t in, uint32_t d, uint32_t m1) {
     uint32_t a;
     if (K == 1) a = s[0] & 0xFF000000u;
     else asm("lop3.b32 %0, %1, 0xFF000000, %2, 0xEA;" : "=r"(a) : "r"(s[K - 1]), "r"(d));   // (s & M) | d, one LOP3
-    s[0] += in - a;
+    uint32_t t;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(a), "r"(m1), "r"(in));                 // in - a
+    s[0] += t;
 #pragma unroll
     for (int k = 1; k < K; ++k) s[k] += s[k - 1] - a;
     return a;       // byte 3 = out_q
@@ -127,6 +133,7 @@ struct PdmV2Params {
     uint8_t *out;
     uint64_t F;
     uint32_t count0, ctl_div_log, sh, dmask, layout;
+    uint32_t m1;               // 0xFFFFFFFF, opaque to the compiler (see pdm_step_q24)
     Sched sched;
 };
 
@@ -165,7 +172,7 @@ struct V2Regs {
     }
     // 16 ticks -> 4 packed words per channel
     template <bool FASTQ, bool DEXT>
-    __device__ __forceinline__ void group(uint32_t &rng, const uint32_t *dext16, uint32_t sh, uint32_t dmask, uint32_t (&w)[B][4]) {
+    __device__ __forceinline__ void group(uint32_t &rng, const uint32_t *dext16, uint32_t sh, uint32_t dmask, uint32_t m1, uint32_t (&w)[B][4]) {
         uint32_t dbuf[16];
         if (DEXT) {
 #pragma unroll
@@ -183,7 +190,7 @@ struct V2Regs {
 #pragma unroll
             for (int j = 0; j < B; ++j) {
                 p0[j] += v0[j];                                       // :101-104
-                if (FASTQ) a[j][i & 3] = pdm_step_q24<K>(s[j], p0[j], d);   // :108-116
+                if (FASTQ) a[j][i & 3] = pdm_step_q24<K>(s[j], p0[j], d, m1);   // :108-116
                 else a[j][i & 3] = pdm_step<K>(s[j], p0[j], sh, d);
                 if ((i & 3) == 3)
                     w[j][i >> 2] = FASTQ ? pack_top_bytes(a[j][0], a[j][1], a[j][2], a[j][3])
@@ -214,7 +221,7 @@ __device__ __forceinline__ void v2_run_segment(const PdmV2Params &p, V2Regs<K, B
             ++row;
         }
         uint32_t w[B][4];
-        r.template group<FASTQ, DEXT>(rng, DEXT ? dext + (g << 4) : nullptr, p.sh, p.dmask, w);
+        r.template group<FASTQ, DEXT>(rng, DEXT ? dext + (g << 4) : nullptr, p.sh, p.dmask, p.m1, w);
 #pragma unroll
         for (int j = 0; j < B; ++j) {
             if (c0 + j < p.n) {
@@ -374,6 +381,7 @@ __global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws(const PdmV2Params p)
     uint64_t row = 0;
     const bool tiled = p.layout == CPROC_CUDA_TILED;
     const bool store = c < p.n;
+    const uint32_t m1 = p.m1;
     for (uint64_t bt = 0; bt < batches; ++bt) {
         const uint32_t s = (uint32_t)bt & 1u;
         bar_sync_n<WS_BAR_FULL, NT>(s);
@@ -384,17 +392,19 @@ __global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws(const PdmV2Params p)
                 ++row;
             }
             uint32_t w[4];
+            {
 #pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-                const uint4 dv = *reinterpret_cast<const uint4 *>(&dbuf[s][gq * 4 + i4][bl][0]);
-                const uint32_t d[4] = {dv.x, dv.y, dv.z, dv.w};
-                uint32_t a[4];
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    const uint4 dv = *reinterpret_cast<const uint4 *>(&dbuf[s][gq * 4 + i4][bl][0]);
+                    const uint32_t d[4] = {dv.x, dv.y, dv.z, dv.w};
+                    uint32_t a[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    r.p0[0] += r.v0[0];                               // :101-104
-                    a[i] = FASTQ ? pdm_step_q24<K>(r.s[0], r.p0[0], d[i]) : pdm_step<K>(r.s[0], r.p0[0], p.sh, d[i]);
+                    for (int i = 0; i < 4; ++i) {
+                        r.p0[0] += r.v0[0];                           // :101-104
+                        a[i] = FASTQ ? pdm_step_q24<K>(r.s[0], r.p0[0], d[i], m1) : pdm_step<K>(r.s[0], r.p0[0], p.sh, d[i]);
+                    }
+                    w[i4] = FASTQ ? pack_top_bytes(a[0], a[1], a[2], a[3]) : pack_low_bytes(a[0], a[1], a[2], a[3]);
                 }
-                w[i4] = FASTQ ? pack_top_bytes(a[0], a[1], a[2], a[3]) : pack_low_bytes(a[0], a[1], a[2], a[3]);
             }
             if (store) {
                 const uint64_t g = bt * (WS_T / 16) + gq;
@@ -503,7 +513,7 @@ int launch_pdm_v2(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     p.st = b->d_state; p.npad = b->npad; p.n = b->n; p.n_banks = b->n_banks; p.bank_size = c.bank_size;
     p.prng = b->d_prng; p.dither_ext = (const uint32_t *)io->in2; p.setpoints = (const uint32_t *)io->ctl;
     p.out = (uint8_t *)io->out; p.F = F; p.count0 = b->count; p.ctl_div_log = c.ctl_div_log; p.sh = c.out_shift;
-    p.dmask = c.dither_mask; p.layout = io->layout;
+    p.dmask = c.dither_mask; p.layout = io->layout; p.m1 = 0xFFFFFFFFu;
     p.sched = Sched{};
     const bool aligned_ptr = ((uintptr_t)io->out & 15) == 0 && (!io->in2 || ((uintptr_t)io->in2 & 15) == 0);
     const bool fast = (F & 15) == 0 && (b->count & 15) == 0 && c.ctl_div_log >= 4 && aligned_ptr &&

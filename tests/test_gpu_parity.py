@@ -105,7 +105,7 @@ def test_pdm_v2_layouts_and_mappings(st, ctx, oracle, layout, tpb, persist, ws, 
 def test_pdm_v2_warp_specialised(st, ctx, oracle, order, bank):
     """Producer/consumer kernel: ragged channel count, several dither batches,
     control boundaries inside a batch."""
-    _v2_case(st, ctx, oracle, order, bank, N=3001, F=448, layout=st.TILED, count0=32, use_setp=True, use_dext=False,
+    _v2_case(st, ctx, oracle, order, bank, N=3001, F=448, layout=st.TILED, count0=16, use_setp=True, use_dext=False,
              ctl=5, opts={"pdm_ws": 1})
 
 
