@@ -1,0 +1,60 @@
+"""GPU: a plain-C host calls the reference's own entry points (synth_run,
+cproc_update/cproc_output, square_grain) through libcproc_dropin.so and the
+batched C-ABI directly; results are compared with the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def xs(s):
+    s ^= (s << 13) & 0xFFFFFFFF
+    s ^= s >> 17
+    s ^= (s << 5) & 0xFFFFFFFF
+    return s
+
+
+def test_c_host_through_dropin_and_abi(tmp_path, oracle):
+    pkg = os.path.join(ROOT, "synth_tools_b200")
+    exe = str(tmp_path / "test_dropin")
+    subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "test_dropin.c"), "-o", exe, "-L", pkg,
+                           "-lcproc_dropin", "-lcproc_cuda", "-Wl,-rpath," + pkg])
+    out = subprocess.check_output([exe], text=True).splitlines()
+    tag = lambda t: [l.split()[1:] for l in out if l.split()[0] == t]
+    # (1) synth_run: two 64-frame periods of the 4-note chord
+    v = np.zeros((64, 2), np.uint32)
+    v[:4, 0] = [39370533, 23409859, 1122405051, 731558]
+    _, want = oracle.voice_bank_run(v, 64, 64, po.MIX_SAW, 128)
+    got = np.array([float.fromhex(x[0]) for x in tag("synth")], np.float32)
+    assert np.array_equal(got.view(np.uint32), want[0].view(np.uint32))
+    assert [int(x[0]) for x in tag("phase")] == v[:4, 1].tolist()
+    # (2) cproc_update upcalls cproc_output(2, n2.out)
+    assert [(int(a), int(b)) for a, b in tag("output")] == [(2, x) for x in [0, 1, 1, 2, 2, 3, 4, 5, 5, 5, 6, 6, 7]]
+    # (3) square_grain in place
+    s = 12345
+    inp = np.zeros((1, 128), np.float32)
+    for i in range(128):
+        s = xs(s)
+        inp[0, i] = np.float32(np.int32(np.uint32(s))) * np.float32(1.0 / 2147483648.0)
+    st = np.zeros(1, np.float32)
+    wantg = oracle.square_grain_run(st, np.array([0.25], np.float32), 1, 128, inp)
+    gotg = np.array([float.fromhex(x[0]) for x in tag("grain")], np.float32)
+    assert np.array_equal(gotg.view(np.uint32), wantg[0].view(np.uint32))
+    assert tag("status") == [["0"]]
+    # (4) batched ABI from C
+    F = 4096 + 32
+    chan = np.zeros((6, 7), np.uint32)
+    chan[:, 0] = 0x40000000 + 0x10000000 * np.arange(6)
+    prng = np.array([2463534242, 7], np.uint32)
+    duty, _ = oracle.pdm_v2_run(chan, 2, 6, 3, prng, None, 0x3FF, 0, 12, 24, None, F)
+    wsum = (duty.astype(np.uint64) * (np.arange(F, dtype=np.uint64) + 1)).sum(axis=1)
+    assert tag("pdm") == [["rc", "0"]] + [[str(c), str(int(wsum[c]))] for c in range(6)]
+    assert [[int(x) for x in r] for r in tag("pdmstate")] == chan.tolist()
+    assert tag("err") == [["rc", "-1"]]
