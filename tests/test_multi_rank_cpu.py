@@ -76,6 +76,6 @@ def test_shard_range_is_a_bank_aligned_partition():
         for a, b in zip(edges, edges[1:]):
             assert a[1] == b[0]
         for lo, hi in edges:
-            assert lo % m == 0 and (hi % m == 0 or hi == n) and lo <= hi
+            assert (lo % m == 0 or lo == n) and (hi % m == 0 or hi == n) and lo <= hi
         sizes = [hi - lo for lo, hi in edges]
         assert max(sizes) - min(sizes) <= 2 * m
