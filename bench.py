@@ -311,7 +311,7 @@ def run_native(args, rank, local_rank, world):
                     "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_pdm_v2_persist<2,3>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_pdm_v2_ws2<K=2,B=3,FORM=1,P=2,NS=2>",
                          "launch_ms": launch_ms, "algorithmic_bytes_per_launch": algo_bytes,
                          "issue": {"achieved_tinstr_s": issue_ach / 1e12, "peak_tinstr_s": issue_peak / 1e12,
                                    "frac": issue_ach / issue_peak,

@@ -84,6 +84,8 @@ int cproc_cuda_close(cproc_cuda_ctx *ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (uint32_t *j : ctx->d_jump) if (j) cudaFree(j);
+    if (ctx->d_sm_rank) cudaFree(ctx->d_sm_rank);
     delete ctx;
     return 0;
 }
@@ -99,7 +101,10 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     if (!strcmp(name, "pdm_block")) { if (value < 32 || value > 128 || (value & 31)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_block must be 32, 64, 96 or 128"); ctx->pdm_block = (int)value; }
     else if (!strcmp(name, "pdm_tpb")) ctx->pdm_tpb = value != 0;
     else if (!strcmp(name, "pdm_stage")) ctx->pdm_stage = value != 0;
-    else if (!strcmp(name, "pdm_ws")) ctx->pdm_ws = value != 0;
+    else if (!strcmp(name, "pdm_ws")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_ws must be 0, 1 or 2"); ctx->pdm_ws = (int)value; }
+    else if (!strcmp(name, "pdm_form")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_form must be 0..2"); ctx->pdm_form = (int)value; }
+    else if (!strcmp(name, "pdm_slots")) { if (value != 2 && value != 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_slots must be 2 or 4"); ctx->pdm_slots = (int)value; }
+    else if (!strcmp(name, "pdm_chains")) { if (value != 1 && value != 2 && value != 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_chains must be 1, 2 or 4"); ctx->pdm_chains = (int)value; }
     else if (!strcmp(name, "pdm_persist")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_persist must be 0 (never), 1 (auto) or 2 (always)"); ctx->pdm_persist = (int)value; }
     else if (!strcmp(name, "pdm_warps_per_smsp")) { if (value < 1 || value > 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_warps_per_smsp must be 1..4"); ctx->pdm_warps_per_smsp = (int)value; }
     else return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "set_option: unknown option '%s'", name);

@@ -20,7 +20,12 @@ struct cproc_cuda_ctx {
     int pdm_block = 64;       // threads per block of the PDM kernels
     int pdm_tpb = 1;          // 1: thread-per-bank when bank_size <= 4, 0: thread-per-channel
     int pdm_stage = 1;        // 1: smem-staged full-line stores for PLANAR
-    int pdm_ws = 1;           // 1: warp-specialised v2 kernel (PRNG producer warp + channel consumer warps)
+    int pdm_ws = 2;           // 1: warp-specialised v2 kernel (PRNG producer warp + channel consumer warps); 2: second generation
+    int pdm_form = 1;         // ws2: order-2 tick formulation (see v2_tick_q24)
+    uint32_t *d_sm_rank = nullptr;   // per-SM block arrival counters (ws2 producer placement)
+    int pdm_slots = 2;        // ws2: dither ring slots (2 or 4)
+    int pdm_chains = 2;       // ws2: independent PRNG chains per producer lane (1, 2 or 4)
+    uint32_t *d_jump[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // xorshift32 jump LUTs per chain count
     int pdm_persist = 1;      // 1: persistent McNaughton-scheduled kernels when thread == bank
     int pdm_warps_per_smsp = 1;
     int n_sm = CPROC_N_SM;

@@ -418,6 +418,240 @@ __global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws(const PdmV2Params p)
     if (live) r.store(p.st, p.npad, c);
 }
 
+
+// ---------------------------------------------------------------------------
+// Warp-specialised, second generation.  Same block shape as k_pdm_v2_ws; two
+// changes, both about dependency depth (the first-generation kernel sat at 65 %
+// of the issue slots with 1.1 eligible warps per scheduler: every warp is a
+// serial chain of 4-cycle ALU ops and there are only ~4.6 warps per scheduler
+// at 65,536 channels):
+//
+//  * consumer (order 2): with x = s1 + p and u = x + s2 formed off the critical
+//    path, the tick is  a = (s2 & 0xFF000000) | d;  s1' = x - a;  s2' = u - 2a
+//    (pdm.h:32-40 with the two subtractions of out_a folded): the loop-carried
+//    chain is LOP3 -> IMAD (FORM 2) instead of LOP3 -> IMAD -> IADD -> IADD3.
+//  * producer: xorshift32 is a 6-deep chain per tick.  Each producer lane runs
+//    P independent chains of its bank's generator, T/P ticks apart; the start
+//    of chain j+1 is the state T/P steps after chain j, obtained with a GF(2)
+//    jump table (xorshift is linear: M^(T/P) as 4 byte-indexed LUTs in smem).
+#define WS2_T 64
+#define WS2_BAR_FULL 1           // barrier ids 1..NS
+#define WS2_BAR_EMPTY 5          // barrier ids 5..4+NS  (NS <= 4)
+template <int BASE, int N, int NS> __device__ __forceinline__ void bar_sync_slot(uint32_t s) {
+    if (NS > 3 && s == 3) bar_sync_i<BASE + 3, N>();
+    else if (NS > 2 && s == 2) bar_sync_i<BASE + 2, N>();
+    else if (s == 1) bar_sync_i<BASE + 1, N>();
+    else bar_sync_i<BASE, N>();
+}
+template <int BASE, int N, int NS> __device__ __forceinline__ void bar_arrive_slot(uint32_t s) {
+    if (NS > 3 && s == 3) bar_arrive_i<BASE + 3, N>();
+    else if (NS > 2 && s == 2) bar_arrive_i<BASE + 2, N>();
+    else if (s == 1) bar_arrive_i<BASE + 1, N>();
+    else bar_arrive_i<BASE, N>();
+}
+struct PdmV2Ws2Extra { const uint32_t *jump; uint32_t *sm_rank; uint32_t m2; };   // jump: [P-1][4][256], M^(T/P * j)
+
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t s, uint32_t d) {   // (s & 0xFF000000) | d
+    uint32_t a;
+    asm("lop3.b32 %0, %1, 0xFF000000, %2, 0xEA;" : "=r"(a) : "r"(s), "r"(d));
+    return a;
+}
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t t;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(a), "r"(b), "r"(c));
+    return t;
+}
+
+// An add that ptxas must issue as IADD3 (ALU pipe): the carry-out form has no
+// IMAD.IADD equivalent.  Left to itself ptxas turns every add of this loop into
+// IMAD.IADD and the FMA pipe (one warp instruction per 2 clk per scheduler)
+// becomes the limiter.
+__device__ __forceinline__ uint32_t add_alu(uint32_t a, uint32_t b) {
+    uint32_t t;
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(t) : "r"(a), "r"(b));
+    return t;
+}
+__device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t t;
+    asm("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3; }" : "=r"(t) : "r"(a), "r"(b), "r"(c));
+    return t;
+}
+
+// one tick of glide + pdmK (out_shift 24, dither below bit 24); returns out_a (byte 3 = out_q)
+template <int K, int FORM>
+__device__ __forceinline__ uint32_t v2_tick_q24(uint32_t &p0, uint32_t v0, uint32_t (&s)[K], uint32_t d, uint32_t m1, uint32_t m2) {
+    p0 += v0;                                                      // mod_pdm_pwm.c:101-104
+    if constexpr (K == 2 && FORM == 1) {                           // chain LOP3 -> IMAD -> IADD3
+        const uint32_t x = s[0] + p0;
+        const uint32_t a = lop3_and_or(s[1], d);
+        s[0] = imad(a, m1, x);
+        s[1] = s[1] + s[0] - a;
+        return a;
+    } else if constexpr (K == 2 && FORM == 2) {                    // chain LOP3 -> IMAD; u on the ALU pipe
+        const uint32_t x = s[0] + p0;
+        const uint32_t u = add3(s[1], s[0], p0);
+        const uint32_t a = lop3_and_or(s[1], d);
+        s[0] = imad(a, m1, x);
+        s[1] = imad(a, m2, u);
+        return a;
+    } else {
+        return pdm_step_q24<K>(s, p0, d, m1);
+    }
+}
+
+__device__ __forceinline__ uint32_t jump_apply(const uint32_t (*jt)[256], uint32_t x) {
+    return jt[0][x & 255u] ^ jt[1][(x >> 8) & 255u] ^ jt[2][(x >> 16) & 255u] ^ jt[3][x >> 24];
+}
+
+// The producer is a separate (noinline) function on purpose: ptxas balances the
+// ALU and FMA pipes by static instruction counts per function; inlined, the
+// LOP3-heavy PRNG pushes every add of the consumer loop onto the FMA pipe
+// (IMAD.IADD), which then limits the consumer warps.
+template <int NT, int P, int NS>
+__device__ __noinline__ void ws2_producer(uint32_t (*dbuf)[WS2_T / 4][32][4], const uint32_t (*jt)[4][256], uint32_t *prng_slot,
+                                          uint32_t dmask, uint64_t batches, uint32_t lane) {
+    constexpr int QC = WS2_T / 4 / P;                     // uint4 groups per chain per batch
+    uint32_t x[P];
+    x[0] = prng_slot ? *prng_slot : 1u;
+    uint32_t s = 0;
+    for (uint64_t bt = 0; bt < batches; ++bt) {
+#pragma unroll
+        for (int j = 1; j < P; ++j) x[j] = jump_apply(jt[j - 1], x[0]);   // state (T/P)*j ticks ahead
+        if (bt >= NS) bar_sync_slot<WS2_BAR_EMPTY, NT, NS>(s);       // slot drained by the consumers
+#pragma unroll
+        for (int q = 0; q < QC; ++q) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                uint4 v;
+                x[j] = xorshift32_step(x[j]); v.x = x[j] & dmask;      // mod_pdm_pwm.c:127
+                x[j] = xorshift32_step(x[j]); v.y = x[j] & dmask;
+                x[j] = xorshift32_step(x[j]); v.z = x[j] & dmask;
+                x[j] = xorshift32_step(x[j]); v.w = x[j] & dmask;
+                *reinterpret_cast<uint4 *>(&dbuf[s][j * QC + q][lane][0]) = v;
+            }
+        }
+        x[0] = x[P - 1];                                         // the last chain ends at tick T
+        __threadfence_block();
+        bar_arrive_slot<WS2_BAR_FULL, NT, NS>(s);
+        s = (s + 1 == NS) ? 0 : s + 1;
+    }
+    if (prng_slot) *prng_slot = x[0];
+}
+
+// NS dither slots of WS2_T ticks; barrier ids WS2_BAR_FULL + slot, WS2_BAR_EMPTY + slot.
+// Requires count0 % WS2_T == 0 (a control boundary can only fall on a batch start).
+template <int K, int B, int FORM, int P, int NS>
+__global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws2(const PdmV2Params p, const PdmV2Ws2Extra ex) {
+    __shared__ __align__(16) uint32_t dbuf[NS][WS2_T / 4][32][4];
+    __shared__ uint32_t jt[P > 1 ? P - 1 : 1][4][256];
+    constexpr int NT = 32 * (B + 1);
+    if constexpr (P > 1) {
+        for (uint32_t i = threadIdx.x; i < (P - 1) * 1024; i += NT) (&jt[0][0][0])[i] = __ldg(ex.jump + i);
+    }
+    // Producer placement.  A warp runs on scheduler (%warpid % 4), and the hardware
+    // staggers the warp slots of successive blocks on one SM (measured with
+    // tools/probe_place.cu: warp 0 of the 1st..5th block sits in slot 0, 5, 10, 15, 16),
+    // so a fixed producer warp index piles the producers of an SM onto one or two
+    // schedulers.  Instead the producer is the warp that sits on scheduler
+    // (rank % 4), rank = arrival order of this block on its SM (never-reset per-SM
+    // counter).  Any choice is correct; this one spreads the load.
+    __shared__ uint32_t rank_s, smsp_s[B + 1];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        rank_s = atomicAdd(ex.sm_rank + smid, 1u);
+    }
+    if (lane == 0) {
+        uint32_t wid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        smsp_s[warp] = wid & 3u;
+    }
+    __syncthreads();
+    uint32_t prod_warp = 0;
+#pragma unroll
+    for (int w = B; w >= 0; --w) if (smsp_s[w] == (rank_s & 3u)) prod_warp = w;
+    const uint64_t bank0 = (uint64_t)blockIdx.x * 32;
+    const uint64_t batches = p.F / WS2_T;
+    if (warp == prod_warp) {
+        const uint64_t bank = bank0 + lane;
+        ws2_producer<NT, P, NS>(dbuf, jt, bank < p.n_banks ? p.prng + bank : nullptr, p.dmask, batches, lane);
+        return;
+    }
+    const uint32_t cw = warp - (warp > prod_warp ? 1u : 0u);          // consumer index 0..B-1
+    const uint32_t cl = cw * 32 + lane;                               // channel within the block
+    const uint32_t bl = cl / B;                                       // its bank within the block
+    const uint64_t c = bank0 * B + cl;
+    const bool live = c < p.n_banks * B;                              // inside the padded SoA rows
+    V2Regs<K, 1> r;
+    if (live) r.load(p.st, p.npad, c);
+    else { r.sp[0] = r.p0[0] = r.v0[0] = r.p1[0] = r.v1[0] = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) r.s[0][k] = 0; }
+    const uint32_t L = p.ctl_div_log;
+    const uint32_t period = 1u << (L - 6);                            // batches per control period (L >= 6)
+    uint32_t until = (p.count0 >> 6) == 0 ? 0 : period - (p.count0 >> 6);   // batches until the next boundary
+    const uint32_t *sp_row = p.setpoints;
+    const bool store = c < p.n;
+    const uint32_t m1 = p.m1, m2 = ex.m2;
+    uint8_t *dst = p.layout == CPROC_CUDA_TILED ? p.out + (c << 4) : p.out + c * p.F;
+    const uint64_t dstep = p.layout == CPROC_CUDA_TILED ? p.n << 4 : 16;
+    const uint32_t *dbase = &dbuf[0][0][bl][0];
+    uint32_t s = 0;
+    for (uint64_t bt = 0; bt < batches; ++bt) {
+        if (until == 0) {                                             // uniform over the grid
+            r.boundary(sp_row, c, p.n, L);
+            if (sp_row) sp_row += p.n;
+            until = period;
+        }
+        --until;
+        bar_sync_slot<WS2_BAR_FULL, NT, NS>(s);
+        const uint32_t *dslot = dbase + s * (WS2_T / 4 * 32 * 4);
+#pragma unroll
+        for (int gq = 0; gq < WS2_T / 16; ++gq) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+                const uint4 dv = *reinterpret_cast<const uint4 *>(dslot + (gq * 4 + i4) * (32 * 4));
+                const uint32_t d[4] = {dv.x, dv.y, dv.z, dv.w};
+                uint32_t a[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = v2_tick_q24<K, FORM>(r.p0[0], r.v0[0], r.s[0], d[i], m1, m2);   // :108-116
+                w[i4] = pack_top_bytes(a[0], a[1], a[2], a[3]);
+            }
+            if (store) st_v4_stream(dst, make_uint4(w[0], w[1], w[2], w[3]));
+            dst += dstep;
+        }
+        if (bt + NS < batches) bar_arrive_slot<WS2_BAR_EMPTY, NT, NS>(s);
+        s = (s + 1 == NS) ? 0 : s + 1;
+    }
+    if (live) r.store(p.st, p.npad, c);
+}
+
+// host: M^steps of xorshift32 as 4 byte-indexed LUTs (linear over GF(2))
+static void jump_table_fill(uint32_t *t, uint32_t steps) {
+    for (int k = 0; k < 4; ++k)
+        for (uint32_t b = 0; b < 256; ++b) {
+            uint32_t x = b << (8 * k);
+            for (uint32_t i = 0; i < steps; ++i) { x ^= x << 13; x ^= x >> 17; x ^= x << 5; }
+            t[k * 256 + b] = x;
+        }
+}
+
+static int jump_tables(cproc_cuda_ctx *ctx, int P, const uint32_t **out) {
+    if (P < 2) { *out = nullptr; return 0; }
+    uint32_t *&d = ctx->d_jump[P];
+    if (!d) {
+        std::vector<uint32_t> h((size_t)(P - 1) * 1024);
+        for (int j = 1; j < P; ++j) jump_table_fill(h.data() + (size_t)(j - 1) * 1024, (uint32_t)(WS2_T / P) * j);
+        CK(ctx, cudaMalloc(&d, h.size() * 4));
+        CK(ctx, cudaMemcpyAsync(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    *out = d;
+    return 0;
+}
+
 // Workers for C chains: as many warps as there are chains, up to `per_sm` warps
 // on each of the SMs; always W <= C so that Lg >= G.
 static int sched_setup(cproc_cuda_batch *b, Sched *s, uint64_t C, uint64_t G, int per_sm) {
@@ -456,6 +690,38 @@ static int launch_v2_order(cproc_cuda_batch *b, PdmV2Params &p, bool fast, bool 
         return 0;
     }
     const uint64_t C = ceil_div_u64(p.n_banks, 32);
+    if (FASTQ && tpb && !dext && ctx->pdm_ws >= 2 && (p.F % WS2_T) == 0 && (p.count0 % WS2_T) == 0 && p.ctl_div_log >= 6) {
+        const unsigned grid = (unsigned)C;
+        PdmV2Ws2Extra ex;
+        ex.m2 = 0xFFFFFFFEu;
+        const int P = ctx->pdm_chains, form = (K == 2) ? ctx->pdm_form : 0;
+        int rc = jump_tables(ctx, P, &ex.jump);
+        if (rc) return rc;
+        if (!ctx->d_sm_rank) {
+            CK(ctx, cudaMalloc(&ctx->d_sm_rank, 1024 * sizeof(uint32_t)));
+            CK(ctx, cudaMemsetAsync(ctx->d_sm_rank, 0, 1024 * sizeof(uint32_t), ctx->stream));
+        }
+        ex.sm_rank = ctx->d_sm_rank;
+#define WS2_GO(BB, FF, PP) do { if (ctx->pdm_slots >= 4) k_pdm_v2_ws2<K, BB, FF, PP, 4><<<grid, 32 * (BB + 1), 0, ctx->stream>>>(p, ex); \
+                                else k_pdm_v2_ws2<K, BB, FF, PP, 2><<<grid, 32 * (BB + 1), 0, ctx->stream>>>(p, ex); } while (0)
+#define WS2_P(BB, FF) do { if (P == 4) WS2_GO(BB, FF, 4); else if (P == 2) WS2_GO(BB, FF, 2); else WS2_GO(BB, FF, 1); } while (0)
+#define WS2_F(BB) do { if constexpr (K == 2) { if (form == 1) WS2_P(BB, 1); else if (form == 2) WS2_P(BB, 2); else WS2_P(BB, 0); } \
+                       else WS2_P(BB, 0); } while (0)
+#ifdef PDM_DEV_FAST
+        WS2_F(3);
+#else
+        switch (p.bank_size) {
+        case 1: WS2_F(1); break;
+        case 2: WS2_F(2); break;
+        case 3: WS2_F(3); break;
+        default: WS2_F(4); break;
+        }
+#endif
+#undef WS2_F
+#undef WS2_P
+#undef WS2_GO
+        return 0;
+    }
     if (tpb && !dext && ctx->pdm_ws && (p.F % WS_T) == 0) {
         const unsigned grid = (unsigned)C;
         switch (p.bank_size) {
@@ -523,12 +789,16 @@ int launch_pdm_v2(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     const bool dext = io->in2 != nullptr;
     int rc;
 #define V2_ORDER(KK) (fastq ? launch_v2_order<KK, true>(b, p, fast, tpb, dext) : launch_v2_order<KK, false>(b, p, fast, tpb, dext))
+#ifdef PDM_DEV_FAST     // development builds (SASS inspection): the firmware's order only
+    rc = V2_ORDER(2);
+#else
     switch (c.order) {
     case 1: rc = V2_ORDER(1); break;
     case 2: rc = V2_ORDER(2); break;
     case 3: rc = V2_ORDER(3); break;
     default: rc = V2_ORDER(4); break;
     }
+#endif
 #undef V2_ORDER
     if (rc) return rc;
     CK_LAUNCH(ctx, "k_pdm_v2");

@@ -83,7 +83,10 @@ def _v2_case(st, ctx, oracle, order, bank, N, F, layout, count0, use_setp, use_d
         ctx.set_option("pdm_block", 64)
         ctx.set_option("pdm_persist", 1)
         ctx.set_option("pdm_warps_per_smsp", 1)
-        ctx.set_option("pdm_ws", 1)
+        ctx.set_option("pdm_ws", 2)
+        ctx.set_option("pdm_form", 1)
+        ctx.set_option("pdm_chains", 2)
+        ctx.set_option("pdm_slots", 2)
 
 
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
@@ -107,6 +110,32 @@ def test_pdm_v2_warp_specialised(st, ctx, oracle, order, bank):
     control boundaries inside a batch."""
     _v2_case(st, ctx, oracle, order, bank, N=3001, F=448, layout=st.TILED, count0=16, use_setp=True, use_dext=False,
              ctl=5, opts={"pdm_ws": 1})
+
+
+@pytest.mark.parametrize("form", [0, 1, 2])
+@pytest.mark.parametrize("chains", [1, 2, 4])
+@pytest.mark.parametrize("slots", [2, 4])
+def test_pdm_v2_ws2_variants(st, ctx, oracle, form, chains, slots):
+    """Second-generation producer/consumer kernel: every tick formulation, PRNG chain
+    count (jump tables) and ring depth; a control boundary on every batch start."""
+    _v2_case(st, ctx, oracle, 2, 3, N=3001, F=64 * 13, layout=st.TILED, count0=0, use_setp=True, use_dext=False,
+             ctl=6, opts={"pdm_ws": 2, "pdm_form": form, "pdm_chains": chains, "pdm_slots": slots})
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+@pytest.mark.parametrize("bank", [1, 2, 3, 4])
+@pytest.mark.parametrize("layout", ["PLANAR", "TILED"])
+def test_pdm_v2_ws2_orders_banks(st, ctx, oracle, order, bank, layout):
+    """ws2 for every order / bank size, ragged channel count, counter starting inside a
+    control period (count0 = 3 batches into a period of 4 batches)."""
+    _v2_case(st, ctx, oracle, order, bank, N=2999, F=64 * 11, layout=getattr(st, layout), count0=192, use_setp=True,
+             use_dext=False, ctl=8, opts={"pdm_ws": 2})
+
+
+def test_pdm_v2_ws2_split_runs(st, ctx, oracle):
+    """Consecutive ws2 launches continue seamlessly (state, PRNG, control counter)."""
+    _v2_case(st, ctx, oracle, 2, 3, N=96 * 5 + 7, F=64 * 20, layout=st.TILED, count0=0, use_setp=True, use_dext=False,
+             ctl=7, split=[64 * 3, 64, 64 * 10, 64 * 6], opts={"pdm_ws": 2})
 
 
 @pytest.mark.parametrize("N,bank,F,wps", [(65536, 3, 512, 1), (65536, 4, 256, 1), (3 * 32 * 1300 + 5, 3, 160, 1),

@@ -8,6 +8,9 @@ import synth_tools_b200 as st
 N, F = 65536, int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 which = sys.argv[2] if len(sys.argv) > 2 else "v2"
 ctx = st.Context(0)
+for kv in sys.argv[3:]:                      # name=value tuning options
+    k, v = kv.split("=")
+    ctx.set_option(k, int(v))
 d_out = ctx.dev_alloc(N * F)
 rows = F // 4096
 sp = np.random.default_rng(0).integers(0x40000000, 0xC0000000, (rows, N), dtype=np.uint32)
