@@ -71,6 +71,48 @@ __device__ __forceinline__ uint32_t pack_low_bytes(uint32_t q0, uint32_t q1, uin
     return __byte_perm(lo, hi, 0x5410);
 }
 
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t s, uint32_t d) {   // (s & 0xFF000000) | d
+    uint32_t a;
+    asm("lop3.b32 %0, %1, 0xFF000000, %2, 0xEA;" : "=r"(a) : "r"(s), "r"(d));
+    return a;
+}
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t t;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(a), "r"(b), "r"(c));
+    return t;
+}
+
+// Three-input add as one IADD3 (ALU pipe).  Left to itself ptxas turns every add of
+// the tick loop into IMAD.IADD and the FMA pipe (one warp instruction per 2 clk per
+// scheduler, like the ALU pipe: tools/ubench_int3.cu) becomes the limiter.
+__device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t t;
+    asm("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3; }" : "=r"(t) : "r"(a), "r"(b), "r"(c));
+    return t;
+}
+
+// one tick of glide + pdmK (out_shift 24, dither below bit 24); returns out_a (byte 3 = out_q)
+template <int K, int FORM>
+__device__ __forceinline__ uint32_t v2_tick_q24(uint32_t &p0, uint32_t v0, uint32_t (&s)[K], uint32_t d, uint32_t m1, uint32_t m2) {
+    p0 += v0;                                                      // mod_pdm_pwm.c:101-104
+    if constexpr (K == 2 && FORM == 1) {                           // chain LOP3 -> IMAD -> IADD3
+        const uint32_t x = s[0] + p0;
+        const uint32_t a = lop3_and_or(s[1], d);
+        s[0] = imad(a, m1, x);
+        s[1] = s[1] + s[0] - a;
+        return a;
+    } else if constexpr (K == 2 && FORM == 2) {                    // chain LOP3 -> IMAD; u on the ALU pipe
+        const uint32_t x = s[0] + p0;
+        const uint32_t u = add3(s[1], s[0], p0);
+        const uint32_t a = lop3_and_or(s[1], d);
+        s[0] = imad(a, m1, x);
+        s[1] = imad(a, m2, u);
+        return a;
+    } else {
+        return pdm_step_q24<K>(s, p0, d, m1);
+    }
+}
+
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -189,9 +231,8 @@ struct V2Regs {
             else { rng = xorshift32_step(rng); asm("and.b32 %0, %1, %2;" : "=r"(d) : "r"(rng), "r"(dmask)); }   // mod_pdm_pwm.c:127 (asm: keep the mask out of the per-channel LOP3)
 #pragma unroll
             for (int j = 0; j < B; ++j) {
-                p0[j] += v0[j];                                       // :101-104
-                if (FASTQ) a[j][i & 3] = pdm_step_q24<K>(s[j], p0[j], d, m1);   // :108-116
-                else a[j][i & 3] = pdm_step<K>(s[j], p0[j], sh, d);
+                if (FASTQ) a[j][i & 3] = v2_tick_q24<K, 1>(p0[j], v0[j], s[j], d, m1, 0u);   // :101-104, :108-116
+                else { p0[j] += v0[j]; a[j][i & 3] = pdm_step<K>(s[j], p0[j], sh, d); }
                 if ((i & 3) == 3)
                     w[j][i >> 2] = FASTQ ? pack_top_bytes(a[j][0], a[j][1], a[j][2], a[j][3])
                                          : pack_low_bytes(a[j][0], a[j][1], a[j][2], a[j][3]);
@@ -450,54 +491,6 @@ template <int BASE, int N, int NS> __device__ __forceinline__ void bar_arrive_sl
     else bar_arrive_i<BASE, N>();
 }
 struct PdmV2Ws2Extra { const uint32_t *jump; uint32_t *sm_rank; uint32_t m2; };   // jump: [P-1][4][256], M^(T/P * j)
-
-__device__ __forceinline__ uint32_t lop3_and_or(uint32_t s, uint32_t d) {   // (s & 0xFF000000) | d
-    uint32_t a;
-    asm("lop3.b32 %0, %1, 0xFF000000, %2, 0xEA;" : "=r"(a) : "r"(s), "r"(d));
-    return a;
-}
-__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t t;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(a), "r"(b), "r"(c));
-    return t;
-}
-
-// An add that ptxas must issue as IADD3 (ALU pipe): the carry-out form has no
-// IMAD.IADD equivalent.  Left to itself ptxas turns every add of this loop into
-// IMAD.IADD and the FMA pipe (one warp instruction per 2 clk per scheduler)
-// becomes the limiter.
-__device__ __forceinline__ uint32_t add_alu(uint32_t a, uint32_t b) {
-    uint32_t t;
-    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(t) : "r"(a), "r"(b));
-    return t;
-}
-__device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t t;
-    asm("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3; }" : "=r"(t) : "r"(a), "r"(b), "r"(c));
-    return t;
-}
-
-// one tick of glide + pdmK (out_shift 24, dither below bit 24); returns out_a (byte 3 = out_q)
-template <int K, int FORM>
-__device__ __forceinline__ uint32_t v2_tick_q24(uint32_t &p0, uint32_t v0, uint32_t (&s)[K], uint32_t d, uint32_t m1, uint32_t m2) {
-    p0 += v0;                                                      // mod_pdm_pwm.c:101-104
-    if constexpr (K == 2 && FORM == 1) {                           // chain LOP3 -> IMAD -> IADD3
-        const uint32_t x = s[0] + p0;
-        const uint32_t a = lop3_and_or(s[1], d);
-        s[0] = imad(a, m1, x);
-        s[1] = s[1] + s[0] - a;
-        return a;
-    } else if constexpr (K == 2 && FORM == 2) {                    // chain LOP3 -> IMAD; u on the ALU pipe
-        const uint32_t x = s[0] + p0;
-        const uint32_t u = add3(s[1], s[0], p0);
-        const uint32_t a = lop3_and_or(s[1], d);
-        s[0] = imad(a, m1, x);
-        s[1] = imad(a, m2, u);
-        return a;
-    } else {
-        return pdm_step_q24<K>(s, p0, d, m1);
-    }
-}
 
 __device__ __forceinline__ uint32_t jump_apply(const uint32_t (*jt)[256], uint32_t x) {
     return jt[0][x & 255u] ^ jt[1][(x >> 8) & 255u] ^ jt[2][(x >> 16) & 255u] ^ jt[3][x >> 24];

@@ -27,11 +27,39 @@ struct XV {
     float lp, bp, env, f, q, att, rel, gl, gr;
 };
 
-__device__ __forceinline__ float xvoice_tick(XV &v) {
-    const float x = __fmul_rn(__int2float_rn((int32_t)v.phase), 0x1p-31f);
+// x = (float)(int)phase * 2^-31 is exact (a power-of-two scale of a 24-bit float, no
+// underflow), so hp = x - lp (one rounding) is computed as fma(xi, 2^-31, -lp): the
+// same bits, one instruction less.
+__device__ __forceinline__ void xvoice_svf(XV &v, float &lp_out) {
+    const float xi = __int2float_rn((int32_t)v.phase);
     v.phase += v.inc;
     const float lp = __fmaf_rn(v.f, v.bp, v.lp);
-    float hp = __fsub_rn(x, lp);
+    float hp = __fmaf_rn(xi, 0x1p-31f, -lp);
+    hp = __fmaf_rn(-v.q, v.bp, hp);
+    v.bp = __fmaf_rn(v.f, hp, v.bp);
+    v.lp = lp;
+    lp_out = lp;
+}
+
+// Tick with the attack/release decision supplied by the caller (mix kernel: bit k of a
+// per-chunk mask, so the frame counter is advanced once per chunk).  Same float
+// operations as xvoice_tick except that a -0.0 envelope in release becomes +0.0
+// (fmaxf); a -0.0 envelope can only come from an uploaded state.
+__device__ __forceinline__ float xvoice_tick_flag(XV &v, bool attack) {
+    float lp;
+    xvoice_svf(v, lp);
+    float e = v.env;
+    if (attack) { e = __fadd_rn(e, v.att); if (e > 1.0f) e = 1.0f; }
+    else { e = fmaxf(__fsub_rn(e, v.rel), 0.0f); }
+    v.env = e;
+    return __fmul_rn(lp, e);
+}
+
+__device__ __forceinline__ float xvoice_tick(XV &v) {
+    const float xi = __int2float_rn((int32_t)v.phase);
+    v.phase += v.inc;
+    const float lp = __fmaf_rn(v.f, v.bp, v.lp);
+    float hp = __fmaf_rn(xi, 0x1p-31f, -lp);
     hp = __fmaf_rn(-v.q, v.bp, hp);
     v.bp = __fmaf_rn(v.f, hp, v.bp);
     v.lp = lp;
@@ -108,6 +136,92 @@ __global__ void __launch_bounds__(XV_BLOCK) k_xvoice(const XVoiceParams p) {
     }
 }
 
+// Mix-only render (C4: millions of voices -> one stereo bus).  The SVF is a
+// recurrence in time, so a voice stays on one thread; the reduction over voices is
+// taken out of the inner loop instead of being paid per voice-sample: a thread keeps
+// 2 x 32 bus accumulators (32 frames, left/right) in registers and walks ITS voices
+// (tid, tid + T, ...) through the same 32 frames one after the other, so the pan
+// multiply and the mix add fuse into one FFMA per channel and nothing crosses lanes
+// until all of the thread's voices are done.  Only then: one block reduction per 32
+// frames (smem columns, fixed order) and one partial row per block; k_xvoice_final
+// adds the block rows in a fixed order, so the result is deterministic run to run.
+// Voice state travels through HBM once per 32 frames (13 words in, 5 out per voice:
+// 2.25 B per voice-sample); the tick itself is the bit-exact xvoice_tick, so the
+// downloaded state equals the oracle's.
+#define XM_BLOCK 128
+#define XM_CHUNK 32
+__device__ __forceinline__ void xv_load(XV &v, const XVoiceParams &p, uint64_t i) {
+    const uint32_t *s = p.st + i; const uint32_t *r = p.prm + i;
+    v.phase = __ldcg(s); v.lp = __uint_as_float(__ldcg(s + p.npad)); v.bp = __uint_as_float(__ldcg(s + 2 * p.npad));
+    v.env = __uint_as_float(__ldcg(s + 3 * p.npad)); v.t = __ldcg(s + 4 * p.npad);
+    v.inc = __ldg(r); v.f = __uint_as_float(__ldg(r + p.npad)); v.q = __uint_as_float(__ldg(r + 2 * p.npad));
+    v.att = __uint_as_float(__ldg(r + 3 * p.npad)); v.rel = __uint_as_float(__ldg(r + 4 * p.npad)); v.gate = __ldg(r + 5 * p.npad);
+    v.gl = __uint_as_float(__ldg(r + 6 * p.npad)); v.gr = __uint_as_float(__ldg(r + 7 * p.npad));
+}
+__global__ void __launch_bounds__(XM_BLOCK, 4) k_xvoice_mix(const XVoiceParams p) {
+    __shared__ float red[2 * XM_CHUNK][XM_BLOCK + 1];
+    const uint64_t T = (uint64_t)gridDim.x * XM_BLOCK;
+    const uint64_t tid = (uint64_t)blockIdx.x * XM_BLOCK + threadIdx.x;
+    for (uint64_t t0 = 0; t0 < p.F; t0 += XM_CHUNK) {
+        const uint32_t cols = p.F - t0 < XM_CHUNK ? (uint32_t)(p.F - t0) : XM_CHUNK;
+        float aL[XM_CHUNK], aR[XM_CHUNK];
+#pragma unroll
+        for (int k = 0; k < XM_CHUNK; ++k) { aL[k] = 0.f; aR[k] = 0.f; }
+        // software pipeline: the 13 words of the thread's next voice are in flight
+        // while the current one renders its 32 frames
+        XV nx = {};
+        if (tid < p.n) xv_load(nx, p, tid);
+        for (uint64_t i = tid; i < p.n; i += T) {
+            XV v = nx;
+            if (i + T < p.n) xv_load(nx, p, i + T);
+            // bit k: tick k of this chunk is in the attack phase, (t + k) mod 2^32 < gate
+            uint32_t amask;
+            if (v.t <= 0xFFFFFFFFu - XM_CHUNK) {
+                const uint32_t rem = v.t < v.gate ? v.gate - v.t : 0u;
+                amask = rem >= 32u ? 0xFFFFFFFFu : (1u << rem) - 1u;
+            } else {                                       // the frame counter wraps inside the chunk
+                amask = 0;
+                for (uint32_t k = 0; k < XM_CHUNK; ++k) amask |= (uint32_t)(v.t + k < v.gate) << k;
+            }
+            if (cols == XM_CHUNK) {
+#pragma unroll
+                for (int k = 0; k < XM_CHUNK; ++k) {
+                    const float y = xvoice_tick_flag(v, (amask >> k) & 1u);
+                    aL[k] = __fmaf_rn(v.gl, y, aL[k]);
+                    aR[k] = __fmaf_rn(v.gr, y, aR[k]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < XM_CHUNK; ++k) {
+                    if (k < (int)cols) {
+                        const float y = xvoice_tick_flag(v, (amask >> k) & 1u);
+                        aL[k] = __fmaf_rn(v.gl, y, aL[k]);
+                        aR[k] = __fmaf_rn(v.gr, y, aR[k]);
+                    }
+                }
+            }
+            v.t += cols;
+            uint32_t *w = p.st + i;
+            w[0] = v.phase; w[p.npad] = __float_as_uint(v.lp); w[2 * p.npad] = __float_as_uint(v.bp);
+            w[3 * p.npad] = __float_as_uint(v.env); w[4 * p.npad] = v.t;
+        }
+#pragma unroll
+        for (int k = 0; k < XM_CHUNK; ++k) { red[k][threadIdx.x] = aL[k]; red[XM_CHUNK + k][threadIdx.x] = aR[k]; }
+        __syncthreads();
+        if (threadIdx.x < 2 * XM_CHUNK) {
+            const uint32_t ch = threadIdx.x / XM_CHUNK, f = threadIdx.x % XM_CHUNK;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < XM_BLOCK; j += 4) {
+                s0 = __fadd_rn(s0, red[threadIdx.x][j]); s1 = __fadd_rn(s1, red[threadIdx.x][j + 1]);
+                s2 = __fadd_rn(s2, red[threadIdx.x][j + 2]); s3 = __fadd_rn(s3, red[threadIdx.x][j + 3]);
+            }
+            if (f < cols) p.partial[((uint64_t)blockIdx.x * 2 + ch) * p.F + t0 + f] = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+        }
+        __syncthreads();
+    }
+}
+
 // mix[c][t] = SUM_b partial[b][c][t], fixed order, 4 independent chains
 __global__ void k_xvoice_final(const float *partial, float *mix, uint64_t n_blocks, uint64_t cols) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -128,7 +242,8 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     if (io->out && io->layout == CPROC_CUDA_INTERLEAVED) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice: INTERLEAVED layout not supported");
     if (io->out && io->layout == CPROC_CUDA_TILED && (F & 1)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice: TILED needs even F");
     if (F == 0) return 0;
-    const uint64_t n_blocks = ceil_div_u64(b->n, XV_BLOCK);
+    const bool mix_only = io->mix && !io->out;
+    const uint64_t n_blocks = mix_only ? (uint64_t)ctx->n_sm * 4 : ceil_div_u64(b->n, XV_BLOCK);
     XVoiceParams p;
     p.st = b->d_state; p.prm = b->d_param; p.npad = b->npad; p.n = b->n; p.F = F;
     p.raw = (float *)io->out; p.layout = io->layout; p.partial = nullptr;
@@ -144,7 +259,7 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     }
     if (io->out && io->mix) k_xvoice<true, true><<<(unsigned)n_blocks, XV_BLOCK, 0, ctx->stream>>>(p);
     else if (io->out) k_xvoice<true, false><<<(unsigned)n_blocks, XV_BLOCK, 0, ctx->stream>>>(p);
-    else k_xvoice<false, true><<<(unsigned)n_blocks, XV_BLOCK, 0, ctx->stream>>>(p);
+    else k_xvoice_mix<<<(unsigned)n_blocks, XM_BLOCK, 0, ctx->stream>>>(p);
     CK_LAUNCH(ctx, "k_xvoice");
     if (io->mix) {
         k_xvoice_final<<<(unsigned)ceil_div_u64(2 * F, 128), 128, 0, ctx->stream>>>(p.partial, (float *)io->mix, n_blocks, 2 * F);

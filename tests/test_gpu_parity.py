@@ -460,8 +460,43 @@ def test_xvoice_raw_bit_exact_and_mix(st, ctx, oracle, layout):
     # deterministic run to run
     b.upload_state(s0.view(np.uint32).reshape(N, 5))
     mix2 = np.zeros((2, F), np.float32)
+    b.run(F, out=raw, mix=mix2)
+    assert np.array_equal(mix.view(np.uint32), mix2.view(np.uint32))
+    b.free()
+
+
+def _mix_close(mix, want_mix):
+    err = np.abs(mix.astype(np.float64) - want_mix.astype(np.float64)).max()
+    peak = np.abs(want_mix).max()
+    assert err <= 1e-5 * peak
+    snr = 10 * np.log10((want_mix.astype(np.float64) ** 2).sum() / max(((mix.astype(np.float64) - want_mix) ** 2).sum(), 1e-300))
+    assert snr >= 120.0
+
+
+@pytest.mark.parametrize("N,F", [(1000, 512), (77, 45), (148 * 4 * 128 + 333, 96), (1, 32)])
+def test_xvoice_mix_only(st, ctx, oracle, N, F):
+    """Mix-only render (register accumulators per thread, voices walked per 32-frame
+    chunk): mix within the stated tolerance of the oracle's double-accumulated mix
+    (<= 1e-5 of the peak, >= 120 dB SNR), voice state bit-exact, deterministic."""
+    s0, prm = _xvoice_inputs(oracle, N)
+    sa = s0.copy()
+    _, want_mix = oracle.xvoice_run(sa, prm, N, F)
+    b = ctx.batch(st.XVOICE, N)
+    b.upload_state(s0.view(np.uint32).reshape(N, 5)); b.upload_param(prm.view(np.uint32).reshape(N, 8))
+    mix = np.zeros((2, F), np.float32)
+    b.run(F, mix=mix)
+    _mix_close(mix, want_mix)
+    assert np.array_equal(b.download_state(), sa.view(np.uint32).reshape(N, 5))
+    b.upload_state(s0.view(np.uint32).reshape(N, 5))
+    mix2 = np.zeros((2, F), np.float32)
     b.run(F, mix=mix2)
     assert np.array_equal(mix.view(np.uint32), mix2.view(np.uint32))
+    # the same render in two calls continues seamlessly
+    if F >= 64:
+        b.upload_state(s0.view(np.uint32).reshape(N, 5))
+        ma = np.zeros((2, 32), np.float32); mb = np.zeros((2, F - 32), np.float32)
+        b.run(32, mix=ma); b.run(F - 32, mix=mb)
+        assert np.array_equal(np.concatenate([ma, mb], axis=1).view(np.uint32), mix.view(np.uint32))
     b.free()
 
 
