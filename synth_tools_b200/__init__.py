@@ -9,8 +9,8 @@ been built: there is no CPU fallback.
 from . import abi  # noqa: F401  (raises ImportError if libcproc_cuda.so is missing)
 from .abi import (Batch, Context, CprocCudaError, GRAPH, INTERLEAVED, MIX_SAW, MIX_SQUARE, NODE_ACC, NODE_EDGE,
                   ONEPOLE, PDM, PDM_V1, PDM_V2, PLANAR, PWM, SQUARE_GRAIN, SQUARE_GRAIN_MIX, TILED, VOICE_BANK,
-                  XVOICE)
+                  XVOICE, XVOICE_SCAN, XVOICE_SEQ)
 
 __all__ = ["abi", "Batch", "Context", "CprocCudaError", "GRAPH", "PDM", "PDM_V1", "PDM_V2", "PWM", "VOICE_BANK",
            "SQUARE_GRAIN", "SQUARE_GRAIN_MIX", "XVOICE", "ONEPOLE", "NODE_ACC", "NODE_EDGE", "MIX_SAW",
-           "MIX_SQUARE", "PLANAR", "INTERLEAVED", "TILED"]
+           "MIX_SQUARE", "XVOICE_SEQ", "XVOICE_SCAN", "PLANAR", "INTERLEAVED", "TILED"]

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "libcproc_cuda.so")
 GRAPH, PDM, PDM_V1, PDM_V2, PWM, VOICE_BANK, SQUARE_GRAIN, SQUARE_GRAIN_MIX, XVOICE, ONEPOLE = range(1, 11)
 NODE_ACC, NODE_EDGE = 0, 1
 MIX_SAW, MIX_SQUARE = 0, 1
+XVOICE_SEQ, XVOICE_SCAN = 0, 1
 PLANAR, INTERLEAVED, TILED = 0, 1, 2
 OK, EINVAL, ENODEV, ENOMEM, ECUDA, ESTATE = 0, -1, -2, -3, -4, -5
 

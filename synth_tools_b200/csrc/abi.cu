@@ -103,6 +103,8 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     else if (!strcmp(name, "pdm_stage")) ctx->pdm_stage = value != 0;
     else if (!strcmp(name, "pdm_ws")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_ws must be 0, 1 or 2"); ctx->pdm_ws = (int)value; }
     else if (!strcmp(name, "pdm_form")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_form must be 0..2"); ctx->pdm_form = (int)value; }
+    else if (!strcmp(name, "grain_mix2")) ctx->grain_mix2 = value != 0;
+    else if (!strcmp(name, "xvoice_chunk")) { if (value < 0) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice_chunk must be >= 0"); ctx->xvoice_chunk = (int)value; }
     else if (!strcmp(name, "pdm_slots")) { if (value != 2 && value != 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_slots must be 2 or 4"); ctx->pdm_slots = (int)value; }
     else if (!strcmp(name, "pdm_chains")) { if (value != 1 && value != 2 && value != 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_chains must be 1, 2 or 4"); ctx->pdm_chains = (int)value; }
     else if (!strcmp(name, "pdm_persist")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_persist must be 0 (never), 1 (auto) or 2 (always)"); ctx->pdm_persist = (int)value; }
@@ -209,7 +211,7 @@ int cproc_cuda_free(cproc_cuda_batch *b) {
     if (!b) return 0;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    void *ptrs[] = { b->d_state, b->d_param, b->d_prng, b->d_nodes, b->d_in, b->d_in2, b->d_ctl, b->d_out, b->d_out2, b->d_mix, b->d_flags };
+    void *ptrs[] = { b->d_state, b->d_param, b->d_prng, b->d_nodes, b->d_in, b->d_in2, b->d_ctl, b->d_out, b->d_out2, b->d_mix, b->d_flags, b->d_scratch, b->d_aux };
     for (void *q : ptrs) if (q) cudaFree(q);
     delete b;
     return 0;
@@ -246,6 +248,7 @@ int cproc_cuda_upload_state(cproc_cuda_batch *b, const void *aos, size_t stride)
 int cproc_cuda_upload_param(cproc_cuda_batch *b, const void *aos, size_t stride) {
     if (!b) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "upload_param: batch is NULL");
     if (b->param_words == 0) return cproc_set_err(b->ctx, CPROC_CUDA_EINVAL, "upload_param: processor has no param record");
+    b->aux_dirty = true;
     return aos_to_dev(b, b->d_param, b->param_words, aos, stride);
 }
 

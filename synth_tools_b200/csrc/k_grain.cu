@@ -144,6 +144,112 @@ __global__ void __launch_bounds__(GMIX_BLOCK) k_grain_mix(const GrainMixParams p
     if (mine) { p.st[g] = __float_as_uint(state); p.st[p.npad + g] = ph; }
 }
 
+// ---------------------------------------------------------------------------
+// C3b, second generation.  Two changes against k_grain_mix:
+//  * the comparisons run on the integer phase.  val = (float)(int)ph * 2^-31 is a
+//    monotone function of the signed phase, so `val < -thresh` is `x < lo` and
+//    `val > thresh` is `x > hi` for two per-grain integers found once per parameter
+//    upload by bisection with the very same I2F / FMUL / FSETP (k_grain_thresholds):
+//    no conversion, no multiply in the loop, and still bit-exact.
+//  * the mix leaves the inner loop: a thread keeps 32 packed (right << 16) + left
+//    accumulators for a 32-frame chunk in registers and walks ITS grains through the
+//    chunk one after the other; the state machine output m in {-1, 0, +1} enters the
+//    bus as one IMAD (acc += m * pk).  One warp reduction per frame per chunk instead
+//    of one per grain-sample.
+// State on the device stays the reference float (0, +0.5, -0.5); other magnitudes are
+// treated by their sign, as the integer mix always did, and come back as +-0.5.
+__global__ void k_grain_thresholds(const uint32_t *prm, uint64_t n, int32_t *lo, int32_t *hi, uint32_t *weird) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const float th = __uint_as_float(prm[g]);
+    auto val = [](int64_t x) { return __int2float_rn((int32_t)x) * 0x1p-31f; };
+    // lo: smallest x with !(val(x) < -th); the predicate is true below, false from lo on
+    int64_t a = INT32_MIN, b = INT32_MAX;
+    if (!(val(a) < -th)) lo[g] = INT32_MIN;
+    else if (val(b) < -th) { lo[g] = INT32_MAX; atomicOr(weird, 1u); }       // true for every phase: not representable
+    else {
+        while (b - a > 1) { const int64_t m = a + (b - a) / 2; if (val(m) < -th) a = m; else b = m; }
+        lo[g] = (int32_t)b;
+    }
+    // hi: largest x with !(val(x) > th); the predicate is false up to hi, true above
+    a = INT32_MIN; b = INT32_MAX;
+    if (!(val(b) > th)) hi[g] = INT32_MAX;
+    else if (val(a) > th) { hi[g] = INT32_MIN; atomicOr(weird, 1u); }
+    else {
+        while (b - a > 1) { const int64_t m = a + (b - a) / 2; if (val(m) > th) b = m; else a = m; }
+        hi[g] = (int32_t)a;
+    }
+}
+
+#define GM2_BLOCK 128
+#define GM2_CHUNK 32
+struct GrainMix2Params {
+    GrainMixParams g;
+    const int32_t *lo, *hi;
+};
+
+__device__ __forceinline__ void gm2_tick(int32_t &m, uint32_t &ph, uint32_t inc, int32_t pk, int32_t lo, int32_t hi, int32_t &acc) {
+    const int32_t x = (int32_t)ph;
+    ph += inc;                                              // cproc.h:141
+    acc = m * pk + acc;                                     // out = state (synth_tools.c:91), panned into the bus
+    // if (state >= 0 && in < -thresh) state = -0.5; else if (state < 0 && in > thresh) state = +0.5;   (:92-97)
+    // three compares with the sign predicate folded in, two selects (ptxas makes 8+ of the C form)
+    asm("{ .reg .pred pn, pd, pu;\n\t"
+        "setp.lt.s32 pn, %0, 0;\n\t"
+        "setp.lt.and.s32 pd, %1, %2, !pn;\n\t"
+        "setp.gt.and.s32 pu, %1, %3, pn;\n\t"
+        "selp.s32 %0, -1, %0, pd;\n\t"
+        "selp.s32 %0, 1, %0, pu; }" : "+r"(m) : "r"(x), "r"(lo), "r"(hi));
+}
+
+__global__ void __launch_bounds__(GM2_BLOCK) k_grain_mix2(const GrainMix2Params p) {
+    __shared__ int32_t sacc[2][GM2_CHUNK];
+    const uint64_t T = (uint64_t)gridDim.x * GM2_BLOCK;
+    const uint64_t tid = (uint64_t)blockIdx.x * GM2_BLOCK + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n = p.g.n, npad = p.g.npad;
+    for (uint64_t t0 = 0; t0 < p.g.F; t0 += GM2_CHUNK) {
+        const uint32_t cols = p.g.F - t0 < GM2_CHUNK ? (uint32_t)(p.g.F - t0) : GM2_CHUNK;
+        if (threadIdx.x < 2 * GM2_CHUNK) (&sacc[0][0])[threadIdx.x] = 0;
+        __syncthreads();
+        int32_t acc[GM2_CHUNK];
+#pragma unroll
+        for (int k = 0; k < GM2_CHUNK; ++k) acc[k] = 0;
+        for (uint64_t g = tid; g < n; g += T) {
+            const float st = __uint_as_float(__ldcg(p.g.st + g));
+            int32_t m = st > 0.0f ? 1 : (st < 0.0f ? -1 : 0);
+            uint32_t ph = __ldcg(p.g.st + npad + g);
+            const uint32_t inc = __ldg(p.g.prm + npad + g);
+            const int32_t pk = (int32_t)((__ldg(p.g.prm + 3 * npad + g) << 16) + __ldg(p.g.prm + 2 * npad + g));
+            const int32_t lo = __ldg(p.lo + g), hi = __ldg(p.hi + g);
+            if (cols == GM2_CHUNK) {
+#pragma unroll
+                for (int k = 0; k < GM2_CHUNK; ++k) gm2_tick(m, ph, inc, pk, lo, hi, acc[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < GM2_CHUNK; ++k) if (k < (int)cols) gm2_tick(m, ph, inc, pk, lo, hi, acc[k]);
+            }
+            if (m != 0) p.g.st[g] = __float_as_uint(0.5f * (float)m);    // never flipped from 0.0: unchanged
+            p.g.st[npad + g] = ph;
+        }
+        int32_t keepl = 0, keepr = 0;
+#pragma unroll
+        for (int k = 0; k < GM2_CHUNK; ++k) {
+            const int32_t l = (int32_t)(int16_t)(acc[k] & 0xFFFF);       // |sum L| <= grains_per_thread * 64 < 2^15
+            const int32_t r = (acc[k] - l) >> 16;
+            const int32_t sl = __reduce_add_sync(0xFFFFFFFFu, l), sr = __reduce_add_sync(0xFFFFFFFFu, r);
+            if (lane == k) { keepl = sl; keepr = sr; }
+        }
+        if (lane < cols) { atomicAdd(&sacc[0][lane], keepl); atomicAdd(&sacc[1][lane], keepr); }
+        __syncthreads();
+        if (threadIdx.x < cols) {
+            atomicAdd(p.g.imix + t0 + threadIdx.x, sacc[0][threadIdx.x]);
+            atomicAdd(p.g.imix + p.g.F + t0 + threadIdx.x, sacc[1][threadIdx.x]);
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void k_imix_to_float(const int32_t *imix, float *mix, uint64_t count, float scale) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) mix[i] = __int2float_rn(imix[i]) * scale;
@@ -167,8 +273,32 @@ int launch_square_grain_mix(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io
     CK(ctx, cudaMemsetAsync(imix, 0, sizeof(int32_t) * 2 * F, ctx->stream));
     GrainMixParams p;
     p.st = b->d_state; p.prm = b->d_param; p.npad = b->npad; p.n = b->n; p.F = F; p.imix = imix;
-    k_grain_mix<<<(unsigned)ceil_div_u64(p.n, GMIX_BLOCK), GMIX_BLOCK, 0, ctx->stream>>>(p);
-    CK_LAUNCH(ctx, "k_grain_mix");
+    if (b->aux_dirty) {                                   // integer thresholds, once per parameter upload
+        if (!b->d_aux) CK(ctx, cudaMalloc(&b->d_aux, sizeof(uint32_t) * (2 * b->npad + 4)));
+        uint32_t *weird = b->d_aux + 2 * b->npad;
+        CK(ctx, cudaMemsetAsync(weird, 0, sizeof(uint32_t), ctx->stream));
+        k_grain_thresholds<<<(unsigned)ceil_div_u64(b->n, 128), 128, 0, ctx->stream>>>(b->d_param, b->n, (int32_t *)b->d_aux, (int32_t *)b->d_aux + b->npad, weird);
+        CK_LAUNCH(ctx, "k_grain_thresholds");
+        uint32_t h = 0;
+        CK(ctx, cudaMemcpyAsync(&h, weird, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        b->aux_weird = h != 0;
+        b->aux_dirty = false;
+    }
+    if (ctx->grain_mix2 && !b->aux_weird) {
+        GrainMix2Params q;
+        q.g = p; q.lo = (const int32_t *)b->d_aux; q.hi = (const int32_t *)b->d_aux + b->npad;
+        uint64_t blocks = ceil_div_u64(p.n, GM2_BLOCK);
+        const uint64_t cap = (uint64_t)ctx->n_sm * 4;                       // ~16+ grains per thread at 1 Mi grains
+        if (blocks > cap) blocks = cap;
+        const uint64_t min_blocks = ceil_div_u64(p.n, (uint64_t)GM2_BLOCK * 500);   // packed 16-bit bus fields: <= 500 grains per thread
+        if (blocks < min_blocks) blocks = min_blocks;
+        k_grain_mix2<<<(unsigned)blocks, GM2_BLOCK, 0, ctx->stream>>>(q);
+        CK_LAUNCH(ctx, "k_grain_mix2");
+    } else {
+        k_grain_mix<<<(unsigned)ceil_div_u64(p.n, GMIX_BLOCK), GMIX_BLOCK, 0, ctx->stream>>>(p);
+        CK_LAUNCH(ctx, "k_grain_mix");
+    }
     if (io->out) {
         k_imix_to_float<<<(unsigned)ceil_div_u64(2 * F, 256), 256, 0, ctx->stream>>>(imix, (float *)io->out, 2 * F, 0x1p-7f);
         CK_LAUNCH(ctx, "k_imix_to_float");

@@ -236,12 +236,214 @@ __global__ void k_xvoice_final(const float *partial, float *mix, uint64_t n_bloc
     mix[i] = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
 }
 
+// ---------------------------------------------------------------------------
+// Time-parallel raw render (C5: few thousand variants x hundreds of thousands of
+// frames, 8 B of output per variant-frame -> HBM-write bound).  A thread per variant
+// would leave the chip idle (2,048 threads), so the time axis is cut into C chunks of
+// L frames and every (variant, chunk) pair is a thread.  What a chunk needs at its
+// first frame:
+//   phase  closed form, phase0 + c*L*inc mod 2^32 (acc, cproc.h:141)         exact
+//   t      t0 + c*L                                                           exact
+//   env    piecewise linear with clamps; walked in time by one thread per variant,
+//          skipping fixed points (e == 1 in attack, e == 0 in release,
+//          e + rate == e), same float operations                              exact
+//   lp,bp  the SVF is linear time-invariant: s' = A s + B x.  Pass 1 (k_sweep_zsr)
+//          runs the recurrence from zero state over each chunk in fp64 (zero-state
+//          response z_c); pass 2 (k_sweep_scan) forms A^L by squaring and walks
+//          s_{c+1} = A^L s_c + z_c in fp64 -- the associative scan of the affine
+//          maps, sequential over the C chunks of a variant because C is small.
+// Pass 3 (k_sweep_render) then runs the ordinary bit-exact float tick from each start
+// state.  The start states come from exact arithmetic rather than from the float
+// trajectory, so raw output matches the sequential path to rounding noise of the
+// float recurrence, not bit for bit: tolerance <= 1e-5 of peak, >= 120 dB SNR
+// (tests/test_gpu_parity.py::test_xvoice_scan).  phase, t and env stay bit-exact.
+struct SweepParams {
+    XVoiceParams x;
+    uint64_t L, C;
+    double2 *z;              // [C-1][n] zero-state response of chunk c
+    float2 *s0;              // [C][n]   (lp, bp) at the first frame of chunk c
+    float *e0;               // [C][n]   env at the first frame of chunk c
+    uint32_t *ph0, *t0;      // [n] snapshot of the initial phase / frame counter
+};
+
+__global__ void __launch_bounds__(128) k_sweep_zsr(const SweepParams p) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t c = blockIdx.y;
+    if (i >= p.x.n) return;
+    const uint32_t inc = p.x.prm[i];
+    const double f = (double)__uint_as_float(p.x.prm[p.x.npad + i]);
+    const double q = (double)__uint_as_float(p.x.prm[2 * p.x.npad + i]);
+    uint32_t phase = p.x.st[i] + (uint32_t)(c * p.L) * inc;
+    double lp = 0.0, bp = 0.0;
+    for (uint64_t k = 0; k < p.L; ++k) {                        // chunks 0..C-2 are full
+        const double x = (double)__int2float_rn((int32_t)phase) * 0x1p-31;   // the float path's x, exactly
+        phase += inc;
+        lp = fma(f, bp, lp);
+        const double hp = fma(-q, bp, x - lp);
+        bp = fma(f, hp, bp);
+    }
+    p.z[c * p.x.n + i] = make_double2(lp, bp);
+}
+
+// env after `count` more ticks, same operations as xvoice_tick, fixed points skipped
+__device__ __forceinline__ void env_advance(float &e, uint32_t &t, uint32_t gate, float att, float rel, uint64_t count) {
+    while (count) {
+        if (t < gate) {
+            float n = __fadd_rn(e, att); if (n > 1.0f) n = 1.0f;
+            if (n == e) { const uint64_t left = gate - t, skip = left < count ? left : count; t += (uint32_t)skip; count -= skip; }
+            else { e = n; t += 1; count -= 1; }
+        } else {
+            float n = __fsub_rn(e, rel); if (n < 0.0f) n = 0.0f;
+            if (n == e) { const uint64_t left = 0x100000000ull - t, skip = left < count ? left : count; t += (uint32_t)skip; count -= skip; }   // up to the counter wrap
+            else { e = n; t += 1; count -= 1; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_sweep_scan(const SweepParams p) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.x.n) return;
+    const uint64_t n = p.x.n, npad = p.x.npad;
+    const double f = (double)__uint_as_float(p.x.prm[npad + i]), q = (double)__uint_as_float(p.x.prm[2 * npad + i]);
+    // one tick: lp' = lp + f bp;  bp' = -f lp + (1 - f q - f^2) bp + f x
+    double a11 = 1.0, a12 = f, a21 = -f, a22 = 1.0 - f * q - f * f;
+    double m11 = 1.0, m12 = 0.0, m21 = 0.0, m22 = 1.0;            // A^L by squaring
+    for (uint64_t e = p.L; e; e >>= 1) {
+        if (e & 1) {
+            const double t11 = m11 * a11 + m12 * a21, t12 = m11 * a12 + m12 * a22, t21 = m21 * a11 + m22 * a21, t22 = m21 * a12 + m22 * a22;
+            m11 = t11; m12 = t12; m21 = t21; m22 = t22;
+        }
+        const double t11 = a11 * a11 + a12 * a21, t12 = a11 * a12 + a12 * a22, t21 = a21 * a11 + a22 * a21, t22 = a21 * a12 + a22 * a22;
+        a11 = t11; a12 = t12; a21 = t21; a22 = t22;
+    }
+    double lp = (double)__uint_as_float(p.x.st[npad + i]), bp = (double)__uint_as_float(p.x.st[2 * npad + i]);
+    float e = __uint_as_float(p.x.st[3 * npad + i]);
+    uint32_t t = p.x.st[4 * npad + i];
+    const uint32_t gate = p.x.prm[5 * npad + i];
+    const float att = __uint_as_float(p.x.prm[3 * npad + i]), rel = __uint_as_float(p.x.prm[4 * npad + i]);
+    p.ph0[i] = p.x.st[i]; p.t0[i] = t;
+    for (uint64_t c = 0; c < p.C; ++c) {
+        p.s0[c * n + i] = make_float2((float)lp, (float)bp);
+        p.e0[c * n + i] = e;
+        if (c + 1 < p.C) {
+            const double2 z = p.z[c * n + i];
+            const double nl = m11 * lp + m12 * bp + z.x, nb = m21 * lp + m22 * bp + z.y;
+            lp = nl; bp = nb;
+            env_advance(e, t, gate, att, rel, p.L);
+        }
+    }
+}
+
+template <bool TILED>
+__global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) {
+    __shared__ __align__(16) float2 tile[TILED ? 1 : XV_WARPS][TILED ? 1 : 32][TILED ? 1 : 33];   // PLANAR: [warp][stream][frame]
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t c = blockIdx.y, n = p.x.n, npad = p.x.npad, F = p.x.F;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool mine = i < n;
+    const uint64_t f0 = c * p.L, f1 = f0 + p.L < F ? f0 + p.L : F;
+    XV v = {};
+    if (mine) {
+        const uint32_t *r = p.x.prm + i;
+        v.inc = r[0]; v.f = __uint_as_float(r[npad]); v.q = __uint_as_float(r[2 * npad]);
+        v.att = __uint_as_float(r[3 * npad]); v.rel = __uint_as_float(r[4 * npad]); v.gate = r[5 * npad];
+        v.gl = __uint_as_float(r[6 * npad]); v.gr = __uint_as_float(r[7 * npad]);
+        v.phase = p.ph0[i] + (uint32_t)f0 * v.inc;
+        v.t = p.t0[i] + (uint32_t)f0;
+        const float2 s = p.s0[c * n + i];
+        v.lp = s.x; v.bp = s.y; v.env = p.e0[c * n + i];
+    }
+    if (TILED) {                                         // [F/2][inst][2][2]: 16 B per lane, 512 B per warp
+        for (uint64_t t = f0; t < f1; t += 2) {
+            const float y0 = xvoice_tick(v);
+            const float l0 = __fmul_rn(v.gl, y0), r0 = __fmul_rn(v.gr, y0);
+            const float y1 = xvoice_tick(v);
+            const float l1 = __fmul_rn(v.gl, y1), r1 = __fmul_rn(v.gr, y1);
+            if (mine) st_v4_stream(p.x.raw + (((t >> 1) * n + i) << 2),
+                                   make_uint4(__float_as_uint(l0), __float_as_uint(r0), __float_as_uint(l1), __float_as_uint(r1)));
+        }
+    } else {                                             // [inst][F][2]: 32 frames staged per warp, rows written as 256 B runs
+        const uint64_t iw = i - lane;                    // first stream of this warp
+        for (uint64_t t = f0; t < f1; t += 32) {
+            const uint32_t cols = f1 - t < 32 ? (uint32_t)(f1 - t) : 32;
+            for (uint32_t k = 0; k < cols; ++k) {
+                const float y = xvoice_tick(v);
+                tile[warp][lane][k] = make_float2(__fmul_rn(v.gl, y), __fmul_rn(v.gr, y));
+            }
+            __syncwarp();
+            // 16 lanes x 16 B cover the 32 frames of one stream; a warp instruction writes two streams
+            const uint32_t half = lane >> 4, fp = (lane & 15) * 2;
+            for (uint32_t j = 0; j < 32; j += 2) {
+                const uint32_t sidx = j + half;
+                if (iw + sidx < n) {
+                    float *dst = p.x.raw + (((iw + sidx) * F + t + fp) << 1);
+                    if (fp + 1 < cols) {
+                        const float2 a = tile[warp][sidx][fp], b2 = tile[warp][sidx][fp + 1];
+                        if ((((uintptr_t)dst) & 15) == 0) st_v4_stream(dst, make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(b2.x), __float_as_uint(b2.y)));
+                        else { *reinterpret_cast<float2 *>(dst) = a; *reinterpret_cast<float2 *>(dst + 2) = b2; }
+                    } else if (fp < cols) *reinterpret_cast<float2 *>(dst) = tile[warp][sidx][fp];
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (mine && c == p.C - 1) {                          // the last chunk leaves the voice state
+        uint32_t *s = p.x.st + i;
+        s[0] = v.phase; s[npad] = __float_as_uint(v.lp); s[2 * npad] = __float_as_uint(v.bp);
+        s[3 * npad] = __float_as_uint(v.env); s[4 * npad] = v.t;
+    }
+}
+
+static int launch_xvoice_scan(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io, uint64_t L) {
+    cproc_cuda_ctx *ctx = b->ctx;
+    const uint64_t n = b->n, C = ceil_div_u64(F, L);
+    const size_t bz = sizeof(double2) * (C - 1) * n, bs = sizeof(float2) * C * n, be = sizeof(float) * C * n, bw = sizeof(uint32_t) * n;
+    const size_t need = bz + bs + be + 2 * bw + 64;
+    if (b->cap_scratch < need) {
+        if (b->d_scratch) cudaFree(b->d_scratch);
+        b->d_scratch = nullptr; b->cap_scratch = 0;
+        CK(ctx, cudaMalloc(&b->d_scratch, need));
+        b->cap_scratch = need;
+    }
+    SweepParams p;
+    p.x.st = b->d_state; p.x.prm = b->d_param; p.x.npad = b->npad; p.x.n = n; p.x.F = F;
+    p.x.raw = (float *)io->out; p.x.layout = io->layout; p.x.partial = nullptr;
+    p.L = L; p.C = C;
+    uint8_t *w = (uint8_t *)b->d_scratch;
+    p.z = (double2 *)w; w += (bz + 15) & ~(size_t)15;
+    p.s0 = (float2 *)w; w += (bs + 15) & ~(size_t)15;
+    p.e0 = (float *)w; w += (be + 15) & ~(size_t)15;
+    p.ph0 = (uint32_t *)w; w += (bw + 15) & ~(size_t)15;
+    p.t0 = (uint32_t *)w;
+    const unsigned gx = (unsigned)ceil_div_u64(n, 128);
+    if (C > 1) {
+        k_sweep_zsr<<<dim3(gx, (unsigned)(C - 1)), 128, 0, ctx->stream>>>(p);
+        CK_LAUNCH(ctx, "k_sweep_zsr");
+    }
+    k_sweep_scan<<<gx, 128, 0, ctx->stream>>>(p);
+    CK_LAUNCH(ctx, "k_sweep_scan");
+    if (io->layout == CPROC_CUDA_TILED) k_sweep_render<true><<<dim3(gx, (unsigned)C), XV_BLOCK, 0, ctx->stream>>>(p);
+    else k_sweep_render<false><<<dim3(gx, (unsigned)C), XV_BLOCK, 0, ctx->stream>>>(p);
+    CK_LAUNCH(ctx, "k_sweep_render");
+    return 0;
+}
+
 int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     cproc_cuda_ctx *ctx = b->ctx;
     if (!io->out && !io->mix) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice: out and mix are both NULL");
     if (io->out && io->layout == CPROC_CUDA_INTERLEAVED) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice: INTERLEAVED layout not supported");
     if (io->out && io->layout == CPROC_CUDA_TILED && (F & 1)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice: TILED needs even F");
     if (F == 0) return 0;
+    if (b->cfg.mode == CPROC_CUDA_XVOICE_SCAN && io->out && !io->mix) {
+        // chunk length: enough (variant, chunk) threads to fill the chip, multiple of 32 frames
+        const uint64_t want_threads = (uint64_t)ctx->n_sm * 2048 * 2;
+        uint64_t C = ceil_div_u64(want_threads, b->n);
+        if (C > 65535) C = 65535;
+        uint64_t L = ceil_div_u64(ceil_div_u64(F, C), 32) * 32;
+        if (ctx->xvoice_chunk > 0) L = ceil_div_u64((uint64_t)ctx->xvoice_chunk, 32) * 32;
+        if (ceil_div_u64(F, L) > 65535) L = ceil_div_u64(ceil_div_u64(F, 65535), 32) * 32;
+        if (L < F) return launch_xvoice_scan(b, F, io, L);
+    }
     const bool mix_only = io->mix && !io->out;
     const uint64_t n_blocks = mix_only ? (uint64_t)ctx->n_sm * 4 : ceil_div_u64(b->n, XV_BLOCK);
     XVoiceParams p;

@@ -500,6 +500,44 @@ def test_xvoice_mix_only(st, ctx, oracle, N, F):
     b.free()
 
 
+@pytest.mark.parametrize("layout", ["PLANAR", "TILED"])
+@pytest.mark.parametrize("N,F,chunk", [(64, 4096, 256), (200, 3000, 96), (33, 8192, 0), (5, 1000, 32)])
+def test_xvoice_scan(st, ctx, oracle, layout, N, F, chunk):
+    """Time-parallel raw render: chunk start states from the fp64 scan of the SVF's affine
+    recurrence.  phase / t / env bit-exact; lp, bp and the output within <= 1e-5 of the
+    peak and >= 120 dB SNR of the sequential oracle (stated tolerance of BASELINE.json)."""
+    s0, prm = _xvoice_inputs(oracle, N)
+    prm["gate_frames"] = rng.integers(0, F, N)
+    prm["env_release"] = rng.uniform(2e-4, 1e-2, N)
+    s0["lp"] = rng.uniform(-0.5, 0.5, N); s0["bp"] = rng.uniform(-0.5, 0.5, N)
+    s0["env"] = rng.uniform(0, 1, N); s0["t"] = rng.integers(0, 100, N)
+    sa = s0.copy()
+    want_raw, _ = oracle.xvoice_run(sa, prm, N, F)
+    ctx.set_option("xvoice_chunk", chunk)
+    b = ctx.batch(st.XVOICE, N, layout=getattr(st, layout), mode=st.XVOICE_SCAN)
+    try:
+        b.upload_state(s0.view(np.uint32).reshape(N, 5)); b.upload_param(prm.view(np.uint32).reshape(N, 8))
+        raw = np.zeros(N * F * 2, np.float32)
+        l0 = ctx.launches
+        b.run(F, out=raw)
+        assert ctx.launches - l0 == 3                      # zsr, scan, render
+        got = raw.reshape(F // 2, N, 2, 2).transpose(1, 0, 2, 3).reshape(N, F, 2) if layout == "TILED" else raw.reshape(N, F, 2)
+        w64, g64 = want_raw.astype(np.float64), got.astype(np.float64)
+        peak = np.abs(w64).max()
+        assert np.abs(g64 - w64).max() <= 1e-5 * peak
+        snr = 10 * np.log10((w64 ** 2).sum() / max(((g64 - w64) ** 2).sum(), 1e-300))
+        assert snr >= 120.0, snr
+        got_state = b.download_state().view(po.xvoice_state_dtype).reshape(N)
+        for k in ("phase", "t"):
+            assert np.array_equal(got_state[k], sa[k])
+        assert np.array_equal(got_state["env"].view(np.uint32), sa["env"].view(np.uint32))
+        for k in ("lp", "bp"):
+            assert np.abs(got_state[k].astype(np.float64) - sa[k]).max() <= 1e-5 * max(1.0, np.abs(sa[k]).max())
+    finally:
+        b.free()
+        ctx.set_option("xvoice_chunk", 0)
+
+
 def test_onepole(st, ctx, oracle):
     N, F = 300, 200
     inp = rng.uniform(-1, 1, (N, F)).astype(np.float32)

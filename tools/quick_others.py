@@ -102,3 +102,16 @@ if "sweep" in which:
     print("C5 sweep raw (thread per variant): N=%d F=%d  %.3f ms  %.3f G variant-frames/s  %.1f GB/s = %.2f%% of HBM" %
           (N, F, ms, N * F / ms / 1e6, 8 * N * F / ms / 1e6, 100 * 8 * N * F / ms / 1e6 / HBM))
     b.free()
+    ctx.dev_free(d_out)
+    # the full C5 shard: 2,048 variants x 480,000 frames (10 s at 48 kHz), time-parallel scan path
+    F = 480000
+    d_out = ctx.dev_alloc(8 * N * F)
+    for layout, lname in ((st.TILED, "TILED"), (st.PLANAR, "PLANAR")):
+        for chunk in (0, 1024, 4096):
+            ctx.set_option("xvoice_chunk", chunk)
+            b = ctx.batch(st.XVOICE, N, layout=layout, mode=st.XVOICE_SCAN); b.upload_state(stt); b.upload_param(prm)
+            ms = timeit(lambda: b.run_dev(F, out=d_out), reps=2)
+            print("C5 sweep raw (time-parallel scan, %s, chunk=%d): N=%d F=%d  %.3f ms  %.3f G variant-frames/s  %.1f GB/s = %.2f%% of HBM" %
+                  (lname, chunk, N, F, ms, N * F / ms / 1e6, 8 * N * F / ms / 1e6, 100 * 8 * N * F / ms / 1e6 / HBM))
+            b.free()
+    ctx.set_option("xvoice_chunk", 0)
