@@ -31,6 +31,7 @@ struct cproc_cuda_ctx {
     int n_sm = CPROC_N_SM;
     int voice_block = 256;
     int grain_block = 128;
+    int grain_blocks_per_sm = 4;
     int grain_mix2 = 1;       // 1: register-accumulator / integer-threshold grain mix kernel
     int xvoice_block = 128;
     int xvoice_chunk = 0;     // XVOICE_SCAN: frames per time chunk (0 = automatic)

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(GMIX_BLOCK) k_grain_mix(const GrainMixParams p
 //    upload by bisection with the very same I2F / FMUL / FSETP (k_grain_thresholds):
 //    no conversion, no multiply in the loop, and still bit-exact.
 //  * the mix leaves the inner loop: a thread keeps 32 packed (right << 16) + left
-//    accumulators for a 32-frame chunk in registers and walks ITS grains through the
+//    accumulators for a 64-frame chunk in registers and walks ITS grains through the
 //    chunk one after the other; the state machine output m in {-1, 0, +1} enters the
 //    bus as one IMAD (acc += m * pk).  One warp reduction per frame per chunk instead
 //    of one per grain-sample.
@@ -182,7 +182,7 @@ __global__ void k_grain_thresholds(const uint32_t *prm, uint64_t n, int32_t *lo,
 }
 
 #define GM2_BLOCK 128
-#define GM2_CHUNK 32
+#define GM2_CHUNK 64
 struct GrainMix2Params {
     GrainMixParams g;
     const int32_t *lo, *hi;
@@ -202,6 +202,16 @@ __device__ __forceinline__ void gm2_tick(int32_t &m, uint32_t &ph, uint32_t inc,
         "selp.s32 %0, 1, %0, pu; }" : "+r"(m) : "r"(x), "r"(lo), "r"(hi));
 }
 
+struct GM2Grain { float st; uint32_t ph, inc; int32_t pk, lo, hi; };
+__device__ __forceinline__ void gm2_load(GM2Grain &v, const GrainMix2Params &p, uint64_t g) {
+    const uint64_t npad = p.g.npad;
+    v.st = __uint_as_float(__ldcg(p.g.st + g));
+    v.ph = __ldcg(p.g.st + npad + g);
+    v.inc = __ldg(p.g.prm + npad + g);
+    v.pk = (int32_t)((__ldg(p.g.prm + 3 * npad + g) << 16) + __ldg(p.g.prm + 2 * npad + g));
+    v.lo = __ldg(p.lo + g); v.hi = __ldg(p.hi + g);
+}
+
 __global__ void __launch_bounds__(GM2_BLOCK) k_grain_mix2(const GrainMix2Params p) {
     __shared__ int32_t sacc[2][GM2_CHUNK];
     const uint64_t T = (uint64_t)gridDim.x * GM2_BLOCK;
@@ -215,13 +225,16 @@ __global__ void __launch_bounds__(GM2_BLOCK) k_grain_mix2(const GrainMix2Params 
         int32_t acc[GM2_CHUNK];
 #pragma unroll
         for (int k = 0; k < GM2_CHUNK; ++k) acc[k] = 0;
+        // software pipeline: the next grain's seven words are in flight while this one runs its 32 frames
+        GM2Grain nx = {};
+        if (tid < n) gm2_load(nx, p, tid);
         for (uint64_t g = tid; g < n; g += T) {
-            const float st = __uint_as_float(__ldcg(p.g.st + g));
-            int32_t m = st > 0.0f ? 1 : (st < 0.0f ? -1 : 0);
-            uint32_t ph = __ldcg(p.g.st + npad + g);
-            const uint32_t inc = __ldg(p.g.prm + npad + g);
-            const int32_t pk = (int32_t)((__ldg(p.g.prm + 3 * npad + g) << 16) + __ldg(p.g.prm + 2 * npad + g));
-            const int32_t lo = __ldg(p.lo + g), hi = __ldg(p.hi + g);
+            const GM2Grain cur = nx;
+            if (g + T < n) gm2_load(nx, p, g + T);
+            int32_t m = cur.st > 0.0f ? 1 : (cur.st < 0.0f ? -1 : 0);
+            uint32_t ph = cur.ph;
+            const uint32_t inc = cur.inc;
+            const int32_t pk = cur.pk, lo = cur.lo, hi = cur.hi;
             if (cols == GM2_CHUNK) {
 #pragma unroll
                 for (int k = 0; k < GM2_CHUNK; ++k) gm2_tick(m, ph, inc, pk, lo, hi, acc[k]);
@@ -232,15 +245,19 @@ __global__ void __launch_bounds__(GM2_BLOCK) k_grain_mix2(const GrainMix2Params 
             if (m != 0) p.g.st[g] = __float_as_uint(0.5f * (float)m);    // never flipped from 0.0: unchanged
             p.g.st[npad + g] = ph;
         }
-        int32_t keepl = 0, keepr = 0;
 #pragma unroll
-        for (int k = 0; k < GM2_CHUNK; ++k) {
-            const int32_t l = (int32_t)(int16_t)(acc[k] & 0xFFFF);       // |sum L| <= grains_per_thread * 64 < 2^15
-            const int32_t r = (acc[k] - l) >> 16;
-            const int32_t sl = __reduce_add_sync(0xFFFFFFFFu, l), sr = __reduce_add_sync(0xFFFFFFFFu, r);
-            if (lane == k) { keepl = sl; keepr = sr; }
+        for (int h = 0; h < GM2_CHUNK / 32; ++h) {
+            int32_t keepl = 0, keepr = 0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const int32_t a = acc[h * 32 + k];
+                const int32_t l = (int32_t)(int16_t)(a & 0xFFFF);        // |sum L| <= grains_per_thread * 64 < 2^15
+                const int32_t r = (a - l) >> 16;
+                const int32_t sl = __reduce_add_sync(0xFFFFFFFFu, l), sr = __reduce_add_sync(0xFFFFFFFFu, r);
+                if (lane == k) { keepl = sl; keepr = sr; }
+            }
+            if (h * 32 + lane < cols) { atomicAdd(&sacc[0][h * 32 + lane], keepl); atomicAdd(&sacc[1][h * 32 + lane], keepr); }
         }
-        if (lane < cols) { atomicAdd(&sacc[0][lane], keepl); atomicAdd(&sacc[1][lane], keepr); }
         __syncthreads();
         if (threadIdx.x < cols) {
             atomicAdd(p.g.imix + t0 + threadIdx.x, sacc[0][threadIdx.x]);
@@ -289,7 +306,7 @@ int launch_square_grain_mix(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io
         GrainMix2Params q;
         q.g = p; q.lo = (const int32_t *)b->d_aux; q.hi = (const int32_t *)b->d_aux + b->npad;
         uint64_t blocks = ceil_div_u64(p.n, GM2_BLOCK);
-        const uint64_t cap = (uint64_t)ctx->n_sm * 4;                       // ~16+ grains per thread at 1 Mi grains
+        const uint64_t cap = (uint64_t)ctx->n_sm * (uint64_t)ctx->grain_blocks_per_sm;
         if (blocks > cap) blocks = cap;
         const uint64_t min_blocks = ceil_div_u64(p.n, (uint64_t)GM2_BLOCK * 500);   // packed 16-bit bus fields: <= 500 grains per thread
         if (blocks < min_blocks) blocks = min_blocks;
