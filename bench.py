@@ -117,6 +117,8 @@ def run_reference(args, rank, world):
     all host cores, on a bounded sample of the same workload per step."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import numpy as np
     from oracle import pyoracle as po
     kind = "reference"
@@ -126,6 +128,7 @@ def run_reference(args, rank, world):
         lib = po.Oracle()
         kind = "port"
     cores = os.cpu_count() or 1
+    po.set_threads(cores)
     n_ch = 3 * 2048 * max(1, cores // 8)           # multiple of the bank size
     ticks = 256 * 1024
     chan = np.zeros((n_ch, 7), np.uint32)
@@ -163,6 +166,7 @@ def workload_config():
 def cpu_baseline_sample():
     import numpy as np
     from oracle import pyoracle as po
+    po.set_threads(os.cpu_count() or 1)
     kind = "reference"
     try:
         lib = po.Ref()

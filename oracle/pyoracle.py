@@ -31,6 +31,15 @@ xvoice_state_dtype = np.dtype([("phase", np.uint32), ("lp", np.float32), ("bp", 
                                ("env", np.float32), ("t", np.uint32)])
 
 
+def set_threads(n):
+    """OpenMP thread count of the oracle / reference libraries (torchrun exports
+    OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core)."""
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
 def build(force=False):
     """Compile the oracle (always possible) and oracle/_ref (only where the
     reference tree is present; elsewhere the prebuilt .so is used)."""
