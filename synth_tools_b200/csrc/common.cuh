@@ -31,8 +31,8 @@ struct cproc_cuda_ctx {
     int n_sm = CPROC_N_SM;
     int voice_block = 256;
     int grain_block = 128;
-    int grain_blocks_per_sm = 4;
-    int grain_mix2 = 1;       // 1: register-accumulator / integer-threshold grain mix kernel
+    int grain_blocks_per_sm = 2;
+    int grain_mix2 = 2;       // 0: float kernel; 1: register-accumulator / integer-threshold kernel; 2: predicate-state kernel
     int xvoice_block = 128;
     int xvoice_chunk = 0;     // XVOICE_SCAN: frames per time chunk (0 = automatic)
 };
@@ -56,7 +56,7 @@ struct cproc_cuda_batch {
     void *d_in = nullptr, *d_in2 = nullptr, *d_ctl = nullptr, *d_out = nullptr, *d_mix = nullptr;
     size_t cap_in = 0, cap_in2 = 0, cap_ctl = 0, cap_out = 0, cap_mix = 0;
     void *d_out2 = nullptr; size_t cap_out2 = 0;   // second slab for run_stream
-    uint32_t *d_aux = nullptr; bool aux_dirty = true, aux_weird = false;   // derived parameter rows (grain mix integer thresholds)
+    uint32_t *d_aux = nullptr; bool aux_dirty = true; uint32_t aux_weird = 0;   // derived parameter rows (grain mix integer thresholds)
     void *d_scratch = nullptr; size_t cap_scratch = 0;   // per-chunk start-state tables (XVOICE_SCAN)
     unsigned long long *d_flags = nullptr;         // persistent-kernel progress words
     uint64_t n_flags = 0;

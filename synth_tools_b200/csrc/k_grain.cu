@@ -158,10 +158,14 @@ __global__ void __launch_bounds__(GMIX_BLOCK) k_grain_mix(const GrainMixParams p
 //    of one per grain-sample.
 // State on the device stays the reference float (0, +0.5, -0.5); other magnitudes are
 // treated by their sign, as the integer mix always did, and come back as +-0.5.
-__global__ void k_grain_thresholds(const uint32_t *prm, uint64_t n, int32_t *lo, int32_t *hi, uint32_t *weird) {
+__global__ void k_grain_thresholds(const uint32_t *prm, uint64_t n, uint64_t npad, int32_t *lo, int32_t *hi, int32_t *pk, uint32_t *weird) {
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     const float th = __uint_as_float(prm[g]);
+    pk[g] = (int32_t)((prm[3 * npad + g] << 16) + prm[2 * npad + g]);
+    // a negative threshold lets both flip conditions hold at once; only the literal
+    // two-branch form (k_grain_mix / k_grain_mix2) orders them like the reference
+    if (th < 0.0f) atomicOr(weird, 2u);
     auto val = [](int64_t x) { return __int2float_rn((int32_t)x) * 0x1p-31f; };
     // lo: smallest x with !(val(x) < -th); the predicate is true below, false from lo on
     int64_t a = INT32_MIN, b = INT32_MAX;
@@ -267,6 +271,100 @@ __global__ void __launch_bounds__(GM2_BLOCK) k_grain_mix2(const GrainMix2Params 
     }
 }
 
+// ---------------------------------------------------------------------------
+// C3b, third generation: the trigger state lives in a predicate.  For thresh >= 0
+// (lo <= hi) the two-branch update of synth_tools.c:92-97 is the Schmitt trigger
+//     neg' = (x < lo) | (neg & (x <= hi))
+// which is two ISETP with a predicate operand (ISETP.LE.AND, ISETP.LT.OR); the bus
+// term is `neg ? -pk : pk` (one SEL) added by an IMAD.IADD, the phasor a second
+// IMAD.IADD: 5 instructions per grain-sample, 3 on the ALU pipe, 2 on the FMA pipe
+// (k_grain_mix2: 7 and 5).  A grain whose state is still the initial 0.0 outputs 0
+// until its first flip (synth_tools.c:91: out = state), so it walks its chunk with
+// the literal form; once flipped it never returns to 0.
+#define GM3_BLOCK 128
+#define GM3_CHUNK 64
+struct GrainMix3Params {
+    GrainMixParams g;
+    const int32_t *lo, *hi, *pk;
+};
+struct GM3Grain { float st; uint32_t ph, inc; int32_t pk, lo, hi; };
+__device__ __forceinline__ void gm3_load(GM3Grain &v, const GrainMix3Params &p, uint64_t g) {
+    v.st = __uint_as_float(__ldcg(p.g.st + g));
+    v.ph = __ldcg(p.g.st + p.g.npad + g);
+    v.inc = __ldg(p.g.prm + p.g.npad + g);
+    v.pk = __ldg(p.pk + g); v.lo = __ldg(p.lo + g); v.hi = __ldg(p.hi + g);
+}
+
+__device__ __forceinline__ void gm3_chunk(const GM3Grain &cur, uint32_t cols, int32_t (&acc)[GM3_CHUNK], float &st_out, uint32_t &ph_out) {
+    uint32_t ph = cur.ph;
+    const uint32_t inc = cur.inc;
+    const int32_t pk = cur.pk, npk = -cur.pk, lo = cur.lo, hi = cur.hi;
+    if (cols == GM3_CHUNK && cur.st != 0.0f) {
+        bool neg = cur.st < 0.0f;
+#pragma unroll
+        for (int k = 0; k < GM3_CHUNK; ++k) {
+            const int32_t x = (int32_t)ph;
+            ph += inc;                                       // cproc.h:141
+            acc[k] += neg ? npk : pk;                        // out = state (:91), panned into the bus
+            neg = (x < lo) | (neg & (x <= hi));              // :92-97
+        }
+        st_out = neg ? -0.5f : 0.5f;
+    } else {
+        // initial 0.0 state or a ragged last chunk: the literal form, tick by tick
+        int32_t m = cur.st > 0.0f ? 1 : (cur.st < 0.0f ? -1 : 0);
+#pragma unroll
+        for (int k = 0; k < GM3_CHUNK; ++k)
+            if (k < (int)cols) gm2_tick(m, ph, inc, pk, lo, hi, acc[k]);
+        st_out = m != 0 ? 0.5f * (float)m : cur.st;
+    }
+    ph_out = ph;
+}
+
+__global__ void __launch_bounds__(GM3_BLOCK) k_grain_mix3(const GrainMix3Params p) {
+    __shared__ int32_t sacc[2][GM3_CHUNK];
+    const uint64_t T = (uint64_t)gridDim.x * GM3_BLOCK;
+    const uint64_t tid = (uint64_t)blockIdx.x * GM3_BLOCK + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n = p.g.n, npad = p.g.npad;
+    for (uint64_t t0 = 0; t0 < p.g.F; t0 += GM3_CHUNK) {
+        const uint32_t cols = p.g.F - t0 < GM3_CHUNK ? (uint32_t)(p.g.F - t0) : GM3_CHUNK;
+        if (threadIdx.x < 2 * GM3_CHUNK) (&sacc[0][0])[threadIdx.x] = 0;
+        __syncthreads();
+        int32_t acc[GM3_CHUNK];
+#pragma unroll
+        for (int k = 0; k < GM3_CHUNK; ++k) acc[k] = 0;
+        GM3Grain nx = {};
+        if (tid < n) gm3_load(nx, p, tid);
+        for (uint64_t g = tid; g < n; g += T) {
+            const GM3Grain cur = nx;
+            if (g + T < n) gm3_load(nx, p, g + T);               // in flight while this grain runs its chunk
+            float st; uint32_t ph;
+            gm3_chunk(cur, cols, acc, st, ph);
+            p.g.st[g] = __float_as_uint(st);
+            p.g.st[npad + g] = ph;
+        }
+#pragma unroll
+        for (int h = 0; h < GM3_CHUNK / 32; ++h) {
+            int32_t keepl = 0, keepr = 0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const int32_t a = acc[h * 32 + k];
+                const int32_t l = (int32_t)(int16_t)(a & 0xFFFF);        // |sum L| <= grains_per_thread * 64 < 2^15
+                const int32_t r = (a - l) >> 16;
+                const int32_t sl = __reduce_add_sync(0xFFFFFFFFu, l), sr = __reduce_add_sync(0xFFFFFFFFu, r);
+                if (lane == k) { keepl = sl; keepr = sr; }
+            }
+            if (h * 32 + lane < cols) { atomicAdd(&sacc[0][h * 32 + lane], keepl); atomicAdd(&sacc[1][h * 32 + lane], keepr); }
+        }
+        __syncthreads();
+        if (threadIdx.x < cols) {
+            atomicAdd(p.g.imix + t0 + threadIdx.x, sacc[0][threadIdx.x]);
+            atomicAdd(p.g.imix + p.g.F + t0 + threadIdx.x, sacc[1][threadIdx.x]);
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void k_imix_to_float(const int32_t *imix, float *mix, uint64_t count, float scale) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) mix[i] = __int2float_rn(imix[i]) * scale;
@@ -291,18 +389,28 @@ int launch_square_grain_mix(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io
     GrainMixParams p;
     p.st = b->d_state; p.prm = b->d_param; p.npad = b->npad; p.n = b->n; p.F = F; p.imix = imix;
     if (b->aux_dirty) {                                   // integer thresholds, once per parameter upload
-        if (!b->d_aux) CK(ctx, cudaMalloc(&b->d_aux, sizeof(uint32_t) * (2 * b->npad + 4)));
-        uint32_t *weird = b->d_aux + 2 * b->npad;
+        if (!b->d_aux) CK(ctx, cudaMalloc(&b->d_aux, sizeof(uint32_t) * (3 * b->npad + 4)));
+        uint32_t *weird = b->d_aux + 3 * b->npad;
         CK(ctx, cudaMemsetAsync(weird, 0, sizeof(uint32_t), ctx->stream));
-        k_grain_thresholds<<<(unsigned)ceil_div_u64(b->n, 128), 128, 0, ctx->stream>>>(b->d_param, b->n, (int32_t *)b->d_aux, (int32_t *)b->d_aux + b->npad, weird);
+        k_grain_thresholds<<<(unsigned)ceil_div_u64(b->n, 128), 128, 0, ctx->stream>>>(b->d_param, b->n, b->npad, (int32_t *)b->d_aux, (int32_t *)b->d_aux + b->npad, (int32_t *)b->d_aux + 2 * b->npad, weird);
         CK_LAUNCH(ctx, "k_grain_thresholds");
         uint32_t h = 0;
         CK(ctx, cudaMemcpyAsync(&h, weird, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
-        b->aux_weird = h != 0;
+        b->aux_weird = h;
         b->aux_dirty = false;
     }
-    if (ctx->grain_mix2 && !b->aux_weird) {
+    if (ctx->grain_mix2 >= 2 && !b->aux_weird) {
+        GrainMix3Params q;
+        q.g = p; q.lo = (const int32_t *)b->d_aux; q.hi = q.lo + b->npad; q.pk = q.lo + 2 * b->npad;
+        uint64_t blocks = ceil_div_u64(p.n, GM3_BLOCK);
+        const uint64_t cap = (uint64_t)ctx->n_sm * (uint64_t)ctx->grain_blocks_per_sm;
+        if (blocks > cap) blocks = cap;
+        const uint64_t min_blocks = ceil_div_u64(p.n, (uint64_t)GM3_BLOCK * 500);   // packed 16-bit bus fields: <= 500 grains per thread
+        if (blocks < min_blocks) blocks = min_blocks;
+        k_grain_mix3<<<(unsigned)blocks, GM3_BLOCK, 0, ctx->stream>>>(q);
+        CK_LAUNCH(ctx, "k_grain_mix3");
+    } else if (ctx->grain_mix2 && !(b->aux_weird & 1u)) {
         GrainMix2Params q;
         q.g = p; q.lo = (const int32_t *)b->d_aux; q.hi = (const int32_t *)b->d_aux + b->npad;
         uint64_t blocks = ceil_div_u64(p.n, GM2_BLOCK);

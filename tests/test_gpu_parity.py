@@ -402,26 +402,40 @@ def test_square_grain(st, ctx, oracle, N, F, layout):
     b.free()
 
 
-def test_square_grain_mix(st, ctx, oracle):
-    N, F = 3000, 256
+@pytest.mark.parametrize("gen", [0, 1, 2])
+@pytest.mark.parametrize("N,F,neg_th", [(3000, 256, False), (70000, 200, False), (517, 37, False), (3000, 128, True)])
+def test_square_grain_mix(st, ctx, oracle, gen, N, F, neg_th):
     state = rng.choice(np.array([0.0, 0.5, -0.5], np.float32), N)
     th = rng.uniform(0.05, 0.5, N).astype(np.float32)
+    th[0] = 0.0
+    if neg_th:
+        th[5::7] = -th[5::7]          # both flip conditions can hold: the literal two-branch kernels must take over
     phase = rng.integers(0, 2**32, N, dtype=np.uint32)
     inc = np.array([oracle.note_to_inc(n) for n in rng.integers(36, 97, N)], np.uint32)
     gl = rng.integers(0, 65, N).astype(np.uint8); gr = (64 - gl).astype(np.uint8)
     sa, pa = state.copy(), phase.copy()
     want_i, want_f = oracle.square_grain_mix_run(sa, th, pa, inc, gl, gr, N, F)
-    b = ctx.batch(st.SQUARE_GRAIN_MIX, N)
-    s_rec = np.zeros((N, 2), np.uint32); s_rec[:, 0] = state.view(np.uint32); s_rec[:, 1] = phase
-    p_rec = np.zeros((N, 4), np.uint32); p_rec[:, 0] = th.view(np.uint32); p_rec[:, 1] = inc; p_rec[:, 2] = gl; p_rec[:, 3] = gr
-    b.upload_state(s_rec); b.upload_param(p_rec)
-    out = np.zeros((2, F), np.float32); mix = np.zeros((2, F), np.int32)
-    b.run(F, out=out, mix=mix)
-    assert np.array_equal(mix, want_i)
-    assert np.array_equal(out.view(np.uint32), want_f.view(np.uint32))
-    s1 = b.download_state()
-    assert np.array_equal(s1[:, 0].view(np.float32), sa) and np.array_equal(s1[:, 1], pa)
-    b.free()
+    ctx.set_option("grain_mix2", gen)
+    try:
+        b = ctx.batch(st.SQUARE_GRAIN_MIX, N)
+        s_rec = np.zeros((N, 2), np.uint32); s_rec[:, 0] = state.view(np.uint32); s_rec[:, 1] = phase
+        p_rec = np.zeros((N, 4), np.uint32); p_rec[:, 0] = th.view(np.uint32); p_rec[:, 1] = inc; p_rec[:, 2] = gl; p_rec[:, 3] = gr
+        b.upload_state(s_rec); b.upload_param(p_rec)
+        out = np.zeros((2, F), np.float32); mix = np.zeros((2, F), np.int32)
+        b.run(F, out=out, mix=mix)
+        assert np.array_equal(mix, want_i)
+        assert np.array_equal(out.view(np.uint32), want_f.view(np.uint32))
+        s1 = b.download_state()
+        assert np.array_equal(s1[:, 0].view(np.float32), sa) and np.array_equal(s1[:, 1], pa)
+        # a second block continues from the device state (split run == one run)
+        want_i2, _ = oracle.square_grain_mix_run(sa, th, pa, inc, gl, gr, N, F)
+        b.run(F, out=out, mix=mix)
+        assert np.array_equal(mix, want_i2)
+        s1 = b.download_state()
+        assert np.array_equal(s1[:, 0].view(np.float32), sa) and np.array_equal(s1[:, 1], pa)
+        b.free()
+    finally:
+        ctx.set_option("grain_mix2", 2)
 
 
 # ------------------------------------------------------------- extension processors

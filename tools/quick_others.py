@@ -65,12 +65,15 @@ if "gmix" in which:
     gl = rng.integers(0, 65, N); p_rec[:, 2] = gl; p_rec[:, 3] = 64 - gl
     b = ctx.batch(st.SQUARE_GRAIN_MIX, N); b.upload_state(s_rec); b.upload_param(p_rec)
     d_out = ctx.dev_alloc(8 * F); d_mix = ctx.dev_alloc(8 * F)
-    for bps in (4, 6, 8, 12):
-        ctx.set_option("grain_blocks_per_sm", bps)
-        ms = timeit(lambda: b.run_dev(F, out=d_out, mix=d_mix), reps=5)
-        print("C3b square_grain mix (blocks/SM=%d): N=%d F=%d  %.3f ms  %.2f G grain-samples/s  (issue: %.1f%% of 37.2 T at 9 instr/grain-sample)" %
-              (bps, N, F, ms, N * F / ms / 1e6, 100 * 9 * N * F / (ms * 1e-3) / 37.2e12))
-    ctx.set_option("grain_blocks_per_sm", 4)
+    b.run_dev(F, out=d_out, mix=d_mix)      # leave the initial 0.0 state behind (steady state: every grain has flipped)
+    for gen in (1, 2):
+        ctx.set_option("grain_mix2", gen)
+        for bps in (2, 3, 4, 6, 8):
+            ctx.set_option("grain_blocks_per_sm", bps)
+            ms = timeit(lambda: b.run_dev(F, out=d_out, mix=d_mix), reps=5)
+            print("C3b square_grain mix gen %d (blocks/SM=%d): N=%d F=%d  %.3f ms  %.2f G grain-samples/s  (issue: %.1f%% of 37.2 T at 9 instr/grain-sample)" %
+                  (gen + 1, bps, N, F, ms, N * F / ms / 1e6, 100 * 9 * N * F / (ms * 1e-3) / 37.2e12))
+    ctx.set_option("grain_blocks_per_sm", 2); ctx.set_option("grain_mix2", 2)
     b.free()
 
 def xvoice_records(N):
