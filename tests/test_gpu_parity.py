@@ -377,13 +377,15 @@ def test_voice_bank_synth_anchor(st, ctx):
 
 
 # -------------------------------------------------------------------- square_grain
-@pytest.mark.parametrize("N,F", [(1, 64), (33, 257), (1000, 256), (129, 31)])
-@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
-def test_square_grain(st, ctx, oracle, N, F, layout):
+def _square_grain_case(st, ctx, oracle, N, F, layout, neg_th=False, odd_state=False):
     inp = rng.uniform(-1, 1, (N, F)).astype(np.float32)
     th = rng.uniform(0.05, 0.5, (N, 1)).astype(np.float32)
     th[0] = 0.0
+    if neg_th:
+        th[3::5] = -th[3::5]
     s0 = rng.choice(np.array([0.0, 0.5, -0.5], np.float32), (N, 1))
+    if odd_state:
+        s0[1::4] = rng.choice(np.array([0.25, -0.125, 2.0], np.float32), s0[1::4].shape)   # output = state until the first flip
     sa = s0[:, 0].copy()
     want = oracle.square_grain_run(sa, th[:, 0].copy(), N, F, inp)
     b = ctx.batch(st.SQUARE_GRAIN, N, layout=getattr(st, layout))
@@ -399,7 +401,43 @@ def test_square_grain(st, ctx, oracle, N, F, layout):
     io = np.ascontiguousarray(inp.T) if il else inp.copy()
     b.run(F, inp=io, out=io)
     assert np.array_equal((io.T if il else io).view(np.uint32), want.view(np.uint32))
+    # a second block continues from the device state
+    inp2 = rng.uniform(-1, 1, (N, F)).astype(np.float32)
+    want2 = oracle.square_grain_run(sa, th[:, 0].copy(), N, F, inp2)
+    b.run(F, inp=np.ascontiguousarray(inp2.T) if il else inp2, out=out)
+    assert np.array_equal((out.T if il else out).view(np.uint32), want2.view(np.uint32))
+    assert np.array_equal(b.download_state().view(np.float32)[:, 0], sa)
     b.free()
+
+
+@pytest.mark.parametrize("N,F", [(1, 64), (33, 257), (1000, 256), (129, 31)])
+@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
+def test_square_grain(st, ctx, oracle, N, F, layout):
+    _square_grain_case(st, ctx, oracle, N, F, layout)
+
+
+@pytest.mark.parametrize("vec4", [0, 1])
+@pytest.mark.parametrize("N,F", [(1000, 256), (64, 7), (4100, 40), (1001, 33)])
+def test_square_grain_interleaved_variants(st, ctx, oracle, vec4, N, F):
+    ctx.set_option("grain_vec4", vec4)
+    try:
+        _square_grain_case(st, ctx, oracle, N, F, "INTERLEAVED", True, True)
+    finally:
+        ctx.set_option("grain_vec4", 1)
+
+
+@pytest.mark.parametrize("bulk", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("N,F,neg_th,odd", [(1000, 256, False, False), (77, 100, False, False), (300, 1024, True, False),
+                                            (64, 4, False, True), (4097, 64, True, True), (31, 392, False, False)])
+def test_square_grain_bulk_variants(st, ctx, oracle, bulk, N, F, neg_th, odd):
+    """k_grain_bulk tile/stage shapes against the register-transpose kernel's cases: ragged
+    last tiles, ragged last warp, negative thresholds and non-reference state values
+    (both take the literal two-branch form)."""
+    ctx.set_option("grain_bulk", bulk)
+    try:
+        _square_grain_case(st, ctx, oracle, N, F, "PLANAR", neg_th, odd)
+    finally:
+        ctx.set_option("grain_bulk", 1)
 
 
 @pytest.mark.parametrize("gen", [0, 1, 2])

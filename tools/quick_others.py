@@ -47,8 +47,12 @@ if "grain" in which:
     for k in range(N // 65536):
         ctx.h2d(d_in + k * chunk.nbytes, chunk)
     th = rng.uniform(0.05, 0.5, (N, 1)).astype(np.float32)
-    for layout, label in ((st.PLANAR, "planar"), (st.INTERLEAVED, "interleaved")):
+    for layout, label, bulk in ((st.PLANAR, "planar (register transpose)", 0), (st.PLANAR, "planar (bulk 64x3)", 1), (st.PLANAR, "planar (bulk 128x3)", 2),
+                                (st.PLANAR, "planar (bulk 64x4)", 3), (st.PLANAR, "planar (bulk 32x4)", 4), (st.INTERLEAVED, "interleaved (1 grain/thread)", -1), (st.INTERLEAVED, "interleaved (4 grains/thread)", -2)):
+        if bulk >= 0: ctx.set_option("grain_bulk", bulk)
+        else: ctx.set_option("grain_vec4", -bulk - 1)
         b = ctx.batch(st.SQUARE_GRAIN, N, layout=layout); b.upload_param(th)
+        b.run_dev(F, inp=d_in, out=d_out)       # leave the initial 0.0 state behind
         ms = timeit(lambda: b.run_dev(F, inp=d_in, out=d_out))
         print("C3a square_grain %s: N=%d F=%d  %.3f ms  %.2f G grain-samples/s  %.0f GB/s = %.1f%% of HBM (8 B/sample)" %
               (label, N, F, ms, N * F / ms / 1e6, 8 * N * F / ms / 1e6, 100 * 8 * N * F / ms / 1e6 / HBM))
