@@ -12,6 +12,8 @@ struct cproc_cuda_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;      // render stream (caller's or ours)
     cudaStream_t copy_stream = nullptr; // D2H overlap in run_stream
+    cudaStream_t aux_stream = nullptr;  // high-priority side stream (XVOICE_SCAN pre-passes), created on first use
+    cudaEvent_t aux_ev[17] = {};        // scan-done[8], render-done[8], fork
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
@@ -36,6 +38,7 @@ struct cproc_cuda_ctx {
     int grain_vec4 = 1;       // interleaved square_grain: four grains per thread when n % 4 == 0
     int grain_mix2 = 2;       // 0: float kernel; 1: register-accumulator / integer-threshold kernel; 2: predicate-state kernel
     int xvoice_block = 128;
+    int xvoice_groups = 0;    // XVOICE_SCAN: variant groups pipelined over the two streams (0 = automatic)
     int xvoice_chunk = 0;     // XVOICE_SCAN: frames per time chunk (0 = automatic)
 };
 

@@ -260,29 +260,43 @@ __global__ void k_xvoice_final(const float *partial, float *mix, uint64_t n_bloc
 struct SweepParams {
     XVoiceParams x;
     uint64_t L, C;
+    uint64_t i0, i1;         // variants [i0, i1) of this launch (variant groups are pipelined over two streams)
+    uint64_t zoff, zi1;      // fused render: thread (i, c) also runs the zero-state pass of variant i + zoff (< zi1)
     double2 *z;              // [C-1][n] zero-state response of chunk c
     float2 *s0;              // [C][n]   (lp, bp) at the first frame of chunk c
     float *e0;               // [C][n]   env at the first frame of chunk c
     uint32_t *ph0, *t0;      // [n] snapshot of the initial phase / frame counter
+    uint32_t *cst;           // [n] first chunk from which the envelope never changes again (C if none)
+    float *est;              // [n] that final envelope value
 };
 
+// One fp64 tick of the zero-state recurrence on the integer-valued input.
+//   lp' = lp + f bp;  bp' = bp + f (x - lp' - q bp), with the x - q bp term off the lp -> bp chain
+__device__ __forceinline__ void zsr_tick(uint32_t &phase, uint32_t inc, double f, double nq, double &lp, double &bp) {
+    const double x = (double)__int2float_rn((int32_t)phase);              // the float path's x * 2^31, exactly
+    phase += inc;
+    const double u = fma(nq, bp, x);
+    lp = fma(f, bp, lp);
+    bp = fma(f, u - lp, bp);
+}
+
+// Zero-state response of every full chunk, fp64.  The SVF is linear, so the recurrence is
+// run on the integer-valued input X = (float)(int)phase (what the float path multiplies
+// by 2^-31) and the result is scaled by 2^-31 once: one DP multiply less per tick.
 __global__ void __launch_bounds__(128) k_sweep_zsr(const SweepParams p) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t i = p.i0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t c = blockIdx.y;
-    if (i >= p.x.n) return;
-    const uint32_t inc = p.x.prm[i];
-    const double f = (double)__uint_as_float(p.x.prm[p.x.npad + i]);
-    const double q = (double)__uint_as_float(p.x.prm[2 * p.x.npad + i]);
+    if (i >= p.i1) return;
+    const uint32_t inc = __ldg(p.x.prm + i);
+    const double f = (double)__uint_as_float(__ldg(p.x.prm + p.x.npad + i));
+    const double nq = -(double)__uint_as_float(__ldg(p.x.prm + 2 * p.x.npad + i));
     uint32_t phase = p.x.st[i] + (uint32_t)(c * p.L) * inc;
     double lp = 0.0, bp = 0.0;
+#pragma unroll 4
     for (uint64_t k = 0; k < p.L; ++k) {                        // chunks 0..C-2 are full
-        const double x = (double)__int2float_rn((int32_t)phase) * 0x1p-31;   // the float path's x, exactly
-        phase += inc;
-        lp = fma(f, bp, lp);
-        const double hp = fma(-q, bp, x - lp);
-        bp = fma(f, hp, bp);
+        zsr_tick(phase, inc, f, nq, lp, bp);
     }
-    p.z[c * p.x.n + i] = make_double2(lp, bp);
+    p.z[c * p.x.n + i] = make_double2(lp * 0x1p-31, bp * 0x1p-31);
 }
 
 // env after `count` more ticks, same operations as xvoice_tick, fixed points skipped
@@ -300,14 +314,53 @@ __device__ __forceinline__ void env_advance(float &e, uint32_t &t, uint32_t gate
     }
 }
 
-__global__ void __launch_bounds__(128) k_sweep_scan(const SweepParams p) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.x.n) return;
+// Envelope and counters at the chunk starts: one thread per variant walks time (the
+// envelope is piecewise linear with clamps, same float operations as xvoice_tick).  The
+// walk stops at the first chunk start where the envelope sits on a fixed point that
+// nothing can leave before the render ends (release: e - rel == e or clamped at 0, no
+// counter wrap ahead; attack: e + att == e or clamped at 1, gate beyond the end): from
+// chunk cst[i] on every chunk starts with est[i] and the render kernel needs no table.
+__global__ void __launch_bounds__(128) k_sweep_env(const SweepParams p) {
+    const uint64_t i = p.i0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.i1) return;
+    const uint64_t n = p.x.n, npad = p.x.npad;
+    float e = __uint_as_float(p.x.st[3 * npad + i]);
+    uint32_t t = p.x.st[4 * npad + i];
+    const uint32_t gate = p.x.prm[5 * npad + i];
+    const float att = __uint_as_float(p.x.prm[3 * npad + i]), rel = __uint_as_float(p.x.prm[4 * npad + i]);
+    p.ph0[i] = p.x.st[i]; p.t0[i] = t;
+    uint64_t c = 0;
+    for (; c < p.C; ++c) {
+        const uint64_t remaining = p.x.F - c * p.L;
+        bool fixed;
+        if (t < gate) { float nx = __fadd_rn(e, att); if (nx > 1.0f) nx = 1.0f; fixed = nx == e && (uint64_t)(gate - t) >= remaining; }
+        else { float nx = __fsub_rn(e, rel); if (nx < 0.0f) nx = 0.0f; fixed = nx == e && (uint64_t)t + remaining <= 0x100000000ull; }
+        if (fixed) break;
+        p.e0[c * n + i] = e;
+        if (c + 1 < p.C) env_advance(e, t, gate, att, rel, p.L);
+    }
+    p.cst[i] = (uint32_t)c; p.est[i] = e;
+}
+
+// Filter state at every chunk start: the associative scan of the affine maps
+// s -> A^L s + z_c over the chunk axis, one warp per variant.  Lane l owns a run of
+// consecutive chunks: it composes its run into one map (P, w), the warp scans the 32
+// maps (Kogge-Stone over shuffles, 2x2 fp64 matrices), and the lane walks its run again
+// from its start state writing s0[c].  The z loads of a lane are independent, so they
+// are all in flight at once (the former per-variant loop paid one L2 round trip per
+// chunk).
+struct Aff { double p11, p12, p21, p22, w1, w2; };
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xFFFFFFFFu, v, d); }
+#define SCAN_WARPS 4
+__global__ void __launch_bounds__(SCAN_WARPS * 32) k_sweep_scan(const SweepParams p) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t i = p.i0 + (uint64_t)blockIdx.x * SCAN_WARPS + (threadIdx.x >> 5);
+    if (i >= p.i1) return;                                   // whole warp
     const uint64_t n = p.x.n, npad = p.x.npad;
     const double f = (double)__uint_as_float(p.x.prm[npad + i]), q = (double)__uint_as_float(p.x.prm[2 * npad + i]);
     // one tick: lp' = lp + f bp;  bp' = -f lp + (1 - f q - f^2) bp + f x
     double a11 = 1.0, a12 = f, a21 = -f, a22 = 1.0 - f * q - f * f;
-    double m11 = 1.0, m12 = 0.0, m21 = 0.0, m22 = 1.0;            // A^L by squaring
+    double m11 = 1.0, m12 = 0.0, m21 = 0.0, m22 = 1.0;            // M = A^L by squaring
     for (uint64_t e = p.L; e; e >>= 1) {
         if (e & 1) {
             const double t11 = m11 * a11 + m12 * a21, t12 = m11 * a12 + m12 * a22, t21 = m21 * a11 + m22 * a21, t22 = m21 * a12 + m22 * a22;
@@ -316,31 +369,58 @@ __global__ void __launch_bounds__(128) k_sweep_scan(const SweepParams p) {
         const double t11 = a11 * a11 + a12 * a21, t12 = a11 * a12 + a12 * a22, t21 = a21 * a11 + a22 * a21, t22 = a21 * a12 + a22 * a22;
         a11 = t11; a12 = t12; a21 = t21; a22 = t22;
     }
-    double lp = (double)__uint_as_float(p.x.st[npad + i]), bp = (double)__uint_as_float(p.x.st[2 * npad + i]);
-    float e = __uint_as_float(p.x.st[3 * npad + i]);
-    uint32_t t = p.x.st[4 * npad + i];
-    const uint32_t gate = p.x.prm[5 * npad + i];
-    const float att = __uint_as_float(p.x.prm[3 * npad + i]), rel = __uint_as_float(p.x.prm[4 * npad + i]);
-    p.ph0[i] = p.x.st[i]; p.t0[i] = t;
-    for (uint64_t c = 0; c < p.C; ++c) {
+    // lane l: chunks [c0, c1); the map of chunk c exists for c < C-1
+    const uint64_t K = (p.C + 31) / 32;
+    const uint64_t c0 = lane * K < p.C ? lane * K : p.C, c1 = c0 + K < p.C ? c0 + K : p.C;
+    Aff t = {1.0, 0.0, 0.0, 1.0, 0.0, 0.0};
+    for (uint64_t c = c0; c < c1 && c + 1 < p.C; ++c) {
+        const double2 z = p.z[c * n + i];
+        const double w1 = m11 * t.w1 + m12 * t.w2 + z.x, w2 = m21 * t.w1 + m22 * t.w2 + z.y;
+        const double p11 = m11 * t.p11 + m12 * t.p21, p12 = m11 * t.p12 + m12 * t.p22;
+        const double p21 = m21 * t.p11 + m22 * t.p21, p22 = m21 * t.p12 + m22 * t.p22;
+        t.w1 = w1; t.w2 = w2; t.p11 = p11; t.p12 = p12; t.p21 = p21; t.p22 = p22;
+    }
+    // inclusive scan: t_l <- t_l o t_{l-1} o ... o t_0  (later map applied after the earlier)
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Aff u;
+        u.p11 = shfl_up_d(t.p11, d); u.p12 = shfl_up_d(t.p12, d); u.p21 = shfl_up_d(t.p21, d); u.p22 = shfl_up_d(t.p22, d);
+        u.w1 = shfl_up_d(t.w1, d); u.w2 = shfl_up_d(t.w2, d);
+        if ((int)lane >= d) {
+            const double w1 = t.p11 * u.w1 + t.p12 * u.w2 + t.w1, w2 = t.p21 * u.w1 + t.p22 * u.w2 + t.w2;
+            const double p11 = t.p11 * u.p11 + t.p12 * u.p21, p12 = t.p11 * u.p12 + t.p12 * u.p22;
+            const double p21 = t.p21 * u.p11 + t.p22 * u.p21, p22 = t.p21 * u.p12 + t.p22 * u.p22;
+            t.w1 = w1; t.w2 = w2; t.p11 = p11; t.p12 = p12; t.p21 = p21; t.p22 = p22;
+        }
+    }
+    // exclusive prefix applied to the initial state
+    Aff e;
+    e.p11 = shfl_up_d(t.p11, 1); e.p12 = shfl_up_d(t.p12, 1); e.p21 = shfl_up_d(t.p21, 1); e.p22 = shfl_up_d(t.p22, 1);
+    e.w1 = shfl_up_d(t.w1, 1); e.w2 = shfl_up_d(t.w2, 1);
+    const double lp0 = (double)__uint_as_float(p.x.st[npad + i]), bp0 = (double)__uint_as_float(p.x.st[2 * npad + i]);
+    double lp = lp0, bp = bp0;
+    if (lane) { lp = e.p11 * lp0 + e.p12 * bp0 + e.w1; bp = e.p21 * lp0 + e.p22 * bp0 + e.w2; }
+    for (uint64_t c = c0; c < c1; ++c) {
         p.s0[c * n + i] = make_float2((float)lp, (float)bp);
-        p.e0[c * n + i] = e;
         if (c + 1 < p.C) {
             const double2 z = p.z[c * n + i];
             const double nl = m11 * lp + m12 * bp + z.x, nb = m21 * lp + m22 * bp + z.y;
             lp = nl; bp = nb;
-            env_advance(e, t, gate, att, rel, p.L);
         }
     }
 }
 
-template <bool TILED>
+// ZSR: the thread also runs the fp64 zero-state pass of chunk c of variant i + zoff (a
+// variant of the group two renders ahead).  The render is HBM-write bound and leaves
+// ~40% of the issue slots and the whole DP pipe idle; the zero-state pass is pure
+// arithmetic, so inside the same instruction stream it is hidden behind the stores.
+template <bool TILED, bool ZSR>
 __global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) {
     __shared__ __align__(16) float2 tile[TILED ? 1 : XV_WARPS][TILED ? 1 : 32][TILED ? 1 : 33];   // PLANAR: [warp][stream][frame]
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t i = p.i0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t c = blockIdx.y, n = p.x.n, npad = p.x.npad, F = p.x.F;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool mine = i < n;
+    const bool mine = i < p.i1;
     const uint64_t f0 = c * p.L, f1 = f0 + p.L < F ? f0 + p.L : F;
     XV v = {};
     if (mine) {
@@ -351,7 +431,18 @@ __global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) 
         v.phase = p.ph0[i] + (uint32_t)f0 * v.inc;
         v.t = p.t0[i] + (uint32_t)f0;
         const float2 s = p.s0[c * n + i];
-        v.lp = s.x; v.bp = s.y; v.env = p.e0[c * n + i];
+        v.lp = s.x; v.bp = s.y; v.env = c >= p.cst[i] ? p.est[i] : p.e0[c * n + i];
+    }
+    // zero-state duty: chunk c of variant j (chunks 0..C-2 are full, the last one needs no response)
+    const uint64_t j = i + p.zoff;
+    const bool zmine = ZSR && mine && j < p.zi1 && c + 1 < p.C;
+    uint32_t zph = 0, zinc = 0;
+    double zf = 0.0, znq = 0.0, zlp = 0.0, zbp = 0.0;
+    if (zmine) {
+        zinc = __ldg(p.x.prm + j);
+        zf = (double)__uint_as_float(__ldg(p.x.prm + npad + j));
+        znq = -(double)__uint_as_float(__ldg(p.x.prm + 2 * npad + j));
+        zph = p.x.st[j] + (uint32_t)f0 * zinc;
     }
     if (TILED) {                                         // [F/2][inst][2][2]: 16 B per lane, 512 B per warp
         for (uint64_t t = f0; t < f1; t += 2) {
@@ -359,6 +450,7 @@ __global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) 
             const float l0 = __fmul_rn(v.gl, y0), r0 = __fmul_rn(v.gr, y0);
             const float y1 = xvoice_tick(v);
             const float l1 = __fmul_rn(v.gl, y1), r1 = __fmul_rn(v.gr, y1);
+            if (ZSR) { zsr_tick(zph, zinc, zf, znq, zlp, zbp); zsr_tick(zph, zinc, zf, znq, zlp, zbp); }   // L is even
             if (mine) st_v4_stream(p.x.raw + (((t >> 1) * n + i) << 2),
                                    make_uint4(__float_as_uint(l0), __float_as_uint(r0), __float_as_uint(l1), __float_as_uint(r1)));
         }
@@ -369,13 +461,14 @@ __global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) 
             for (uint32_t k = 0; k < cols; ++k) {
                 const float y = xvoice_tick(v);
                 tile[warp][lane][k] = make_float2(__fmul_rn(v.gl, y), __fmul_rn(v.gr, y));
+                if (ZSR) zsr_tick(zph, zinc, zf, znq, zlp, zbp);
             }
             __syncwarp();
             // 16 lanes x 16 B cover the 32 frames of one stream; a warp instruction writes two streams
             const uint32_t half = lane >> 4, fp = (lane & 15) * 2;
-            for (uint32_t j = 0; j < 32; j += 2) {
-                const uint32_t sidx = j + half;
-                if (iw + sidx < n) {
+            for (uint32_t jj = 0; jj < 32; jj += 2) {
+                const uint32_t sidx = jj + half;
+                if (iw + sidx < p.i1) {
                     float *dst = p.x.raw + (((iw + sidx) * F + t + fp) << 1);
                     if (fp + 1 < cols) {
                         const float2 a = tile[warp][sidx][fp], b2 = tile[warp][sidx][fp + 1];
@@ -387,6 +480,7 @@ __global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) 
             __syncwarp();
         }
     }
+    if (zmine) p.z[c * n + j] = make_double2(zlp * 0x1p-31, zbp * 0x1p-31);
     if (mine && c == p.C - 1) {                          // the last chunk leaves the voice state
         uint32_t *s = p.x.st + i;
         s[0] = v.phase; s[npad] = __float_as_uint(v.lp); s[2 * npad] = __float_as_uint(v.bp);
@@ -394,11 +488,16 @@ __global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) 
     }
 }
 
-static int launch_xvoice_scan(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io, uint64_t L) {
+// Variant groups are pipelined with a look-ahead of two: the render of group g (HBM-write
+// bound, main stream) also computes the zero-state responses of group g+2; the scan of
+// group g+2 (tiny) then runs on the auxiliary high-priority stream beside the render of
+// group g+1.  Only the zero-state passes of the first two groups run as kernels of their
+// own.  With fewer than three groups the pre-passes simply precede the render.
+static int launch_xvoice_scan(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io, uint64_t L, uint64_t groups) {
     cproc_cuda_ctx *ctx = b->ctx;
     const uint64_t n = b->n, C = ceil_div_u64(F, L);
     const size_t bz = sizeof(double2) * (C - 1) * n, bs = sizeof(float2) * C * n, be = sizeof(float) * C * n, bw = sizeof(uint32_t) * n;
-    const size_t need = bz + bs + be + 2 * bw + 64;
+    const size_t need = bz + bs + be + 4 * bw + 96;
     if (b->cap_scratch < need) {
         if (b->d_scratch) cudaFree(b->d_scratch);
         b->d_scratch = nullptr; b->cap_scratch = 0;
@@ -408,23 +507,75 @@ static int launch_xvoice_scan(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_
     SweepParams p;
     p.x.st = b->d_state; p.x.prm = b->d_param; p.x.npad = b->npad; p.x.n = n; p.x.F = F;
     p.x.raw = (float *)io->out; p.x.layout = io->layout; p.x.partial = nullptr;
-    p.L = L; p.C = C;
+    p.L = L; p.C = C; p.zoff = 0; p.zi1 = 0;
     uint8_t *w = (uint8_t *)b->d_scratch;
     p.z = (double2 *)w; w += (bz + 15) & ~(size_t)15;
     p.s0 = (float2 *)w; w += (bs + 15) & ~(size_t)15;
     p.e0 = (float *)w; w += (be + 15) & ~(size_t)15;
     p.ph0 = (uint32_t *)w; w += (bw + 15) & ~(size_t)15;
-    p.t0 = (uint32_t *)w;
-    const unsigned gx = (unsigned)ceil_div_u64(n, 128);
-    if (C > 1) {
-        k_sweep_zsr<<<dim3(gx, (unsigned)(C - 1)), 128, 0, ctx->stream>>>(p);
-        CK_LAUNCH(ctx, "k_sweep_zsr");
+    p.t0 = (uint32_t *)w; w += (bw + 15) & ~(size_t)15;
+    p.cst = (uint32_t *)w; w += (bw + 15) & ~(size_t)15;
+    p.est = (float *)w;
+    if (groups > 8) groups = 8;
+    if (groups < 1) groups = 1;
+    const uint64_t per = ceil_div_u64(ceil_div_u64(n, groups), 128) * 128;
+    groups = ceil_div_u64(n, per);
+    const bool piped = groups >= 3 && C > 1;
+    if (piped && !ctx->aux_stream) {
+        int lo = 0, hi = 0;
+        CK(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(ctx, cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi));
+        for (cudaEvent_t &e : ctx->aux_ev) CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    k_sweep_scan<<<gx, 128, 0, ctx->stream>>>(p);
-    CK_LAUNCH(ctx, "k_sweep_scan");
-    if (io->layout == CPROC_CUDA_TILED) k_sweep_render<true><<<dim3(gx, (unsigned)C), XV_BLOCK, 0, ctx->stream>>>(p);
-    else k_sweep_render<false><<<dim3(gx, (unsigned)C), XV_BLOCK, 0, ctx->stream>>>(p);
-    CK_LAUNCH(ctx, "k_sweep_render");
+    cudaStream_t pre = piped ? ctx->aux_stream : ctx->stream;
+    cudaEvent_t *ev_scan = ctx->aux_ev, *ev_render = ctx->aux_ev + 8, ev_fork = ctx->aux_ev[16];
+    if (piped) {                                             // fork: the aux stream starts after everything queued so far
+        CK(ctx, cudaEventRecord(ev_fork, ctx->stream));
+        CK(ctx, cudaStreamWaitEvent(pre, ev_fork, 0));
+    }
+    auto range = [&](uint64_t g, uint64_t *i0, uint64_t *i1) { *i0 = g * per; *i1 = *i0 + per < n ? *i0 + per : n; };
+    p.i0 = 0; p.i1 = n;
+    k_sweep_env<<<(unsigned)ceil_div_u64(n, 128), 128, 0, ctx->stream>>>(p);   // only the renders need it: beside the aux-stream passes
+    CK_LAUNCH(ctx, "k_sweep_env");
+    // zero-state pass as its own kernel: every group when not pipelined, else the first two
+    for (uint64_t g = 0; g < groups; ++g) {
+        range(g, &p.i0, &p.i1);
+        const unsigned gx = (unsigned)ceil_div_u64(p.i1 - p.i0, 128);
+        if (C > 1 && (!piped || g < 2)) {
+            k_sweep_zsr<<<dim3(gx, (unsigned)(C - 1)), 128, 0, pre>>>(p);
+            CK_LAUNCH(ctx, "k_sweep_zsr");
+        }
+        if (!piped || g < 2) {
+            k_sweep_scan<<<(unsigned)ceil_div_u64(p.i1 - p.i0, SCAN_WARPS), SCAN_WARPS * 32, 0, pre>>>(p);
+            CK_LAUNCH(ctx, "k_sweep_scan");
+            if (piped) CK(ctx, cudaEventRecord(ev_scan[g], pre));
+        }
+    }
+    for (uint64_t g = 0; g < groups; ++g) {
+        range(g, &p.i0, &p.i1);
+        const unsigned gx = (unsigned)ceil_div_u64(p.i1 - p.i0, 128);
+        const bool duty = piped && g + 2 < groups;
+        if (duty) { uint64_t z0; range(g + 2, &z0, &p.zi1); p.zoff = z0 - p.i0; } else { p.zoff = 0; p.zi1 = 0; }
+        if (piped) CK(ctx, cudaStreamWaitEvent(ctx->stream, ev_scan[g], 0));     // join: start states of this group
+        const dim3 grid(gx, (unsigned)C);
+        if (io->layout == CPROC_CUDA_TILED) {
+            if (duty) k_sweep_render<true, true><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
+            else k_sweep_render<true, false><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
+        } else {
+            if (duty) k_sweep_render<false, true><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
+            else k_sweep_render<false, false><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
+        }
+        CK_LAUNCH(ctx, "k_sweep_render");
+        if (duty) {                                          // scan of group g+2 beside the render of group g+1
+            CK(ctx, cudaEventRecord(ev_render[g], ctx->stream));
+            CK(ctx, cudaStreamWaitEvent(pre, ev_render[g], 0));
+            SweepParams q = p;
+            range(g + 2, &q.i0, &q.i1);
+            k_sweep_scan<<<(unsigned)ceil_div_u64(q.i1 - q.i0, SCAN_WARPS), SCAN_WARPS * 32, 0, pre>>>(q);
+            CK_LAUNCH(ctx, "k_sweep_scan");
+            CK(ctx, cudaEventRecord(ev_scan[g + 2], pre));
+        }
+    }
     return 0;
 }
 
@@ -435,14 +586,18 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     if (io->out && io->layout == CPROC_CUDA_TILED && (F & 1)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice: TILED needs even F");
     if (F == 0) return 0;
     if (b->cfg.mode == CPROC_CUDA_XVOICE_SCAN && io->out && !io->mix) {
-        // chunk length: enough (variant, chunk) threads to fill the chip, multiple of 32 frames
-        const uint64_t want_threads = (uint64_t)ctx->n_sm * 2048 * 2;
-        uint64_t C = ceil_div_u64(want_threads, b->n);
+        // variant groups of >= 128; chunk length: enough (variant, chunk) threads per group to
+        // fill the chip, multiple of 32 frames
+        uint64_t groups = ctx->xvoice_groups > 0 ? (uint64_t)ctx->xvoice_groups : 8;
+        if (groups > ceil_div_u64(b->n, 128)) groups = ceil_div_u64(b->n, 128);
+        // (one wave of the fused render, 1536 threads per SM, when the groups are pipelined)
+        const uint64_t want_threads = groups >= 3 ? (uint64_t)ctx->n_sm * 1536 : (uint64_t)ctx->n_sm * 2048 * 2;
+        uint64_t C = ceil_div_u64(want_threads, ceil_div_u64(b->n, groups));
         if (C > 65535) C = 65535;
         uint64_t L = ceil_div_u64(ceil_div_u64(F, C), 32) * 32;
         if (ctx->xvoice_chunk > 0) L = ceil_div_u64((uint64_t)ctx->xvoice_chunk, 32) * 32;
         if (ceil_div_u64(F, L) > 65535) L = ceil_div_u64(ceil_div_u64(F, 65535), 32) * 32;
-        if (L < F) return launch_xvoice_scan(b, F, io, L);
+        if (L < F) return launch_xvoice_scan(b, F, io, L, groups);
     }
     const bool mix_only = io->mix && !io->out;
     const uint64_t n_blocks = mix_only ? (uint64_t)ctx->n_sm * 4 : ceil_div_u64(b->n, XV_BLOCK);

@@ -553,8 +553,9 @@ def test_xvoice_mix_only(st, ctx, oracle, N, F):
 
 
 @pytest.mark.parametrize("layout", ["PLANAR", "TILED"])
-@pytest.mark.parametrize("N,F,chunk", [(64, 4096, 256), (200, 3000, 96), (33, 8192, 0), (5, 1000, 32)])
-def test_xvoice_scan(st, ctx, oracle, layout, N, F, chunk):
+@pytest.mark.parametrize("N,F,chunk,groups", [(64, 4096, 256, 0), (200, 3000, 96, 0), (33, 8192, 0, 0), (5, 1000, 32, 0),
+                                              (700, 2048, 64, 0), (700, 2048, 32, 3), (300, 1024, 512, 1), (129, 640, 64, 8), (1100, 1056, 96, 0), (1100, 1056, 96, 5)])
+def test_xvoice_scan(st, ctx, oracle, layout, N, F, chunk, groups):
     """Time-parallel raw render: chunk start states from the fp64 scan of the SVF's affine
     recurrence.  phase / t / env bit-exact; lp, bp and the output within <= 1e-5 of the
     peak and >= 120 dB SNR of the sequential oracle (stated tolerance of BASELINE.json)."""
@@ -566,13 +567,18 @@ def test_xvoice_scan(st, ctx, oracle, layout, N, F, chunk):
     sa = s0.copy()
     want_raw, _ = oracle.xvoice_run(sa, prm, N, F)
     ctx.set_option("xvoice_chunk", chunk)
+    ctx.set_option("xvoice_groups", groups)
     b = ctx.batch(st.XVOICE, N, layout=getattr(st, layout), mode=st.XVOICE_SCAN)
     try:
         b.upload_state(s0.view(np.uint32).reshape(N, 5)); b.upload_param(prm.view(np.uint32).reshape(N, 8))
         raw = np.zeros(N * F * 2, np.float32)
         l0 = ctx.launches
         b.run(F, out=raw)
-        assert ctx.launches - l0 == 3                      # zsr, scan, render
+        g_req = min(groups or 8, -(-N // 128))
+        per = -(-(-(-N // g_req)) // 128) * 128              # variants per group, multiple of 128
+        g_eff = -(-N // per)
+        piped = g_eff >= 3                                   # look-ahead-2 pipeline: zero-state passes fused into the renders
+        assert ctx.launches - l0 == 1 + (2 if piped else g_eff) + 2 * g_eff    # env; zsr; scan + render per group
         got = raw.reshape(F // 2, N, 2, 2).transpose(1, 0, 2, 3).reshape(N, F, 2) if layout == "TILED" else raw.reshape(N, F, 2)
         w64, g64 = want_raw.astype(np.float64), got.astype(np.float64)
         peak = np.abs(w64).max()
@@ -588,6 +594,7 @@ def test_xvoice_scan(st, ctx, oracle, layout, N, F, chunk):
     finally:
         b.free()
         ctx.set_option("xvoice_chunk", 0)
+        ctx.set_option("xvoice_groups", 0)
 
 
 def test_onepole(st, ctx, oracle):

@@ -117,11 +117,11 @@ if "sweep" in which:
     F = 480000
     d_out = ctx.dev_alloc(8 * N * F)
     for layout, lname in ((st.TILED, "TILED"), (st.PLANAR, "PLANAR")):
-        for chunk in (0, 1024, 4096):
-            ctx.set_option("xvoice_chunk", chunk)
+        for chunk, groups in ((0, 1), (0, 4), (0, 8), (128, 8), (512, 8), (1024, 8)):
+            ctx.set_option("xvoice_chunk", chunk); ctx.set_option("xvoice_groups", groups)
             b = ctx.batch(st.XVOICE, N, layout=layout, mode=st.XVOICE_SCAN); b.upload_state(stt); b.upload_param(prm)
             ms = timeit(lambda: b.run_dev(F, out=d_out), reps=2)
-            print("C5 sweep raw (time-parallel scan, %s, chunk=%d): N=%d F=%d  %.3f ms  %.3f G variant-frames/s  %.1f GB/s = %.2f%% of HBM" %
-                  (lname, chunk, N, F, ms, N * F / ms / 1e6, 8 * N * F / ms / 1e6, 100 * 8 * N * F / ms / 1e6 / HBM))
+            print("C5 sweep raw (time-parallel scan, %s, chunk=%d, groups=%d): N=%d F=%d  %.3f ms  %.3f G variant-frames/s  %.1f GB/s = %.2f%% of HBM" %
+                  (lname, chunk, groups, N, F, ms, N * F / ms / 1e6, 8 * N * F / ms / 1e6, 100 * 8 * N * F / ms / 1e6 / HBM))
             b.free()
-    ctx.set_option("xvoice_chunk", 0)
+    ctx.set_option("xvoice_chunk", 0); ctx.set_option("xvoice_groups", 0)
