@@ -88,6 +88,7 @@ int cproc_cuda_close(cproc_cuda_ctx *ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (uint32_t *j : ctx->d_jump) if (j) cudaFree(j);
     if (ctx->d_sm_rank) cudaFree(ctx->d_sm_rank);
+    if (ctx->d_work) cudaFree(ctx->d_work);
     delete ctx;
     return 0;
 }
@@ -103,7 +104,9 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     if (!strcmp(name, "pdm_block")) { if (value < 32 || value > 128 || (value & 31)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_block must be 32, 64, 96 or 128"); ctx->pdm_block = (int)value; }
     else if (!strcmp(name, "pdm_tpb")) ctx->pdm_tpb = value != 0;
     else if (!strcmp(name, "pdm_stage")) ctx->pdm_stage = value != 0;
-    else if (!strcmp(name, "pdm_ws")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_ws must be 0, 1 or 2"); ctx->pdm_ws = (int)value; }
+    else if (!strcmp(name, "pdm_ws")) { if (value < 0 || value > 3) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_ws must be 0..3"); ctx->pdm_ws = (int)value; }
+    else if (!strcmp(name, "pdm_ctas_per_sm")) { if (value < 1 || value > 8) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_ctas_per_sm must be 1..8"); ctx->pdm_ctas_per_sm = (int)value; }
+    else if (!strcmp(name, "pdm_slice_batches")) { if (value < 2 || value > 65536) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_slice_batches must be 2..65536"); ctx->pdm_slice_batches = (int)value; }
     else if (!strcmp(name, "pdm_form")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_form must be 0..2"); ctx->pdm_form = (int)value; }
     else if (!strcmp(name, "grain_blocks_per_sm")) { if (value < 1 || value > 16) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "grain_blocks_per_sm must be 1..16"); ctx->grain_blocks_per_sm = (int)value; }
     else if (!strcmp(name, "grain_bulk")) { if (value < 0 || value > 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "grain_bulk must be 0..4"); ctx->grain_bulk = (int)value; }

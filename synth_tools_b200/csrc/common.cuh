@@ -22,7 +22,10 @@ struct cproc_cuda_ctx {
     int pdm_block = 64;       // threads per block of the PDM kernels
     int pdm_tpb = 1;          // 1: thread-per-bank when bank_size <= 4, 0: thread-per-channel
     int pdm_stage = 1;        // 1: smem-staged full-line stores for PLANAR
-    int pdm_ws = 2;           // 1: warp-specialised v2 kernel (PRNG producer warp + channel consumer warps); 2: second generation
+    int pdm_ws = 3;           // 1: warp-specialised v2 kernel (PRNG producer warp + channel consumer warps); 2: second generation; 3: + dynamic (group, slice) schedule
+    int pdm_ctas_per_sm = 4;  // ws3: persistent blocks per SM
+    int pdm_slice_batches = 64;   // ws3: dither batches (64 ticks each) per work item
+    uint32_t *d_work = nullptr;   // ws3: work counter + exit counter
     int pdm_form = 1;         // ws2: order-2 tick formulation (see v2_tick_q24)
     uint32_t *d_sm_rank = nullptr;   // per-SM block arrival counters (ws2 producer placement)
     int pdm_slots = 2;        // ws2: dither ring slots (2 or 4)

@@ -621,6 +621,133 @@ __global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws2(const PdmV2Params p
     if (live) r.store(p.st, p.npad, c);
 }
 
+// ---------------------------------------------------------------------------
+// Third generation: the ws2 block (producer warp + B consumer warps per 32 banks) under
+// a dynamic schedule.  65,536 channels in banks of 3 are 683 blocks for 148 SMs: a plain
+// grid puts 5 blocks on 91 SMs and 4 on the other 57, and the launch lasts as long as
+// the 5-block SMs (ncu, ws2: sm__cycles_active max/avg = 1.17).  Here the launch is cut
+// into work items (32-bank group g, time slice sl of `bps` dither batches), numbered
+// slice-major; a persistent grid of exactly `ctas_per_sm` blocks per SM takes items
+// from an atomic counter.  Item (sl, g) continues item (sl-1, g): the channel and PRNG
+// state go through the SoA rows in L2 (7 words per channel per slice) and a
+// release/acquire progress word per group.  A predecessor always has a smaller item
+// number, i.e. is held by a running block or finished, so waiting cannot deadlock.
+struct PdmV2Work {
+    uint32_t *counter;             // [2]: next item, blocks finished (both reset by the last block to leave)
+    unsigned long long *flags;     // [groups]: (epoch << 32) | slices done
+    unsigned long long epoch;
+    uint32_t groups, slices, bps;  // bps: batches of WS2_T ticks per slice
+};
+
+template <int K, int B, int FORM, int P, int NS>
+__global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws3(const PdmV2Params p, const PdmV2Ws2Extra ex, const PdmV2Work wk) {
+    __shared__ __align__(16) uint32_t dbuf[NS][WS2_T / 4][32][4];
+    __shared__ uint32_t jt[P > 1 ? P - 1 : 1][4][256];
+    constexpr int NT = 32 * (B + 1);
+    if constexpr (P > 1) {
+        for (uint32_t i = threadIdx.x; i < (P - 1) * 1024; i += NT) (&jt[0][0][0])[i] = __ldg(ex.jump + i);
+    }
+    __shared__ uint32_t rank_s, smsp_s[B + 1], item_s;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        rank_s = atomicAdd(ex.sm_rank + smid, 1u);
+    }
+    if (lane == 0) {
+        uint32_t wid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        smsp_s[warp] = wid & 3u;
+    }
+    __syncthreads();
+    uint32_t prod_warp = 0;                                           // see k_pdm_v2_ws2: the warp on scheduler (rank % 4)
+#pragma unroll
+    for (int w = B; w >= 0; --w) if (smsp_s[w] == (rank_s & 3u)) prod_warp = w;
+    const uint32_t cw = warp - (warp > prod_warp ? 1u : 0u);          // consumer index 0..B-1
+    const uint32_t cl = cw * 32 + lane;                               // channel within the block
+    const uint32_t bl = cl / B;                                       // its bank within the block
+    const uint32_t L = p.ctl_div_log, period = 1u << (L - 6);         // batches per control period (L >= 6)
+    const uint32_t m1 = p.m1, m2 = ex.m2;
+    const uint64_t batches_total = p.F / WS2_T;
+    const uint32_t total = wk.groups * wk.slices;
+    const uint32_t *dbase = &dbuf[0][0][bl][0];
+    for (;;) {
+        if (threadIdx.x == 0) {
+            const uint32_t idx = atomicAdd(wk.counter, 1u);
+            item_s = idx;
+            if (idx < total) {
+                const uint32_t g = idx % wk.groups, sl = idx / wk.groups;
+                const unsigned long long want = (wk.epoch << 32) | sl;
+                if (sl) while (ld_acquire_u64(wk.flags + g) != want) __nanosleep(64);
+            }
+        }
+        __syncthreads();
+        const uint32_t idx = item_s;
+        if (idx >= total) break;
+        const uint32_t g = idx % wk.groups, sl = idx / wk.groups;
+        const uint64_t bt0 = (uint64_t)sl * wk.bps;
+        const uint64_t nb = batches_total - bt0 < wk.bps ? batches_total - bt0 : wk.bps;
+        const uint64_t bank0 = (uint64_t)g * 32;
+        if (warp == prod_warp) {
+            const uint64_t bank = bank0 + lane;
+            ws2_producer<NT, P, NS>(dbuf, jt, bank < p.n_banks ? p.prng + bank : nullptr, p.dmask, nb, lane);
+        } else {
+            const uint64_t c = bank0 * B + cl;
+            const bool live = c < p.n_banks * B;                      // inside the padded SoA rows
+            V2Regs<K, 1> r;
+            if (live) r.load(p.st, p.npad, c);
+            else { r.sp[0] = r.p0[0] = r.v0[0] = r.p1[0] = r.v1[0] = 0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) r.s[0][k] = 0; }
+            // control divider at the first batch of the slice (count0 % WS2_T == 0)
+            const uint32_t cb = (uint32_t)(((p.count0 >> 6) + bt0) & (period - 1));
+            uint32_t until = cb == 0 ? 0 : period - cb;               // batches until the next boundary
+            const uint32_t *sp_row = p.setpoints ? p.setpoints + v2_rows_before(p.count0, 1u << L, bt0 * WS2_T) * p.n : nullptr;
+            const bool store = c < p.n;
+            uint8_t *dst = p.layout == CPROC_CUDA_TILED ? p.out + ((bt0 * (WS2_T / 16) * p.n + c) << 4) : p.out + c * p.F + bt0 * WS2_T;
+            const uint64_t dstep = p.layout == CPROC_CUDA_TILED ? p.n << 4 : 16;
+            uint32_t s = 0;
+            for (uint64_t bt = 0; bt < nb; ++bt) {
+                if (until == 0) {                                     // uniform over the block
+                    r.boundary(sp_row, c, p.n, L);
+                    if (sp_row) sp_row += p.n;
+                    until = period;
+                }
+                --until;
+                bar_sync_slot<WS2_BAR_FULL, NT, NS>(s);
+                const uint32_t *dslot = dbase + s * (WS2_T / 4 * 32 * 4);
+#pragma unroll
+                for (int gq = 0; gq < WS2_T / 16; ++gq) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const uint4 dv = *reinterpret_cast<const uint4 *>(dslot + (gq * 4 + i4) * (32 * 4));
+                        const uint32_t d[4] = {dv.x, dv.y, dv.z, dv.w};
+                        uint32_t a[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) a[i] = v2_tick_q24<K, FORM>(r.p0[0], r.v0[0], r.s[0], d[i], m1, m2);   // :108-116
+                        w[i4] = pack_top_bytes(a[0], a[1], a[2], a[3]);
+                    }
+                    if (store) st_v4_stream(dst, make_uint4(w[0], w[1], w[2], w[3]));
+                    dst += dstep;
+                }
+                if (bt + NS < nb) bar_arrive_slot<WS2_BAR_EMPTY, NT, NS>(s);
+                s = (s + 1 == NS) ? 0 : s + 1;
+            }
+            if (live) r.store(p.st, p.npad, c);
+        }
+        __syncthreads();                                              // every state word of the item is written
+        if (threadIdx.x == 0) {
+            __threadfence();
+            st_release_u64(wk.flags + g, (wk.epoch << 32) | (sl + 1));
+        }
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t left = atomicAdd(wk.counter + 1, 1u);
+        if (left == gridDim.x - 1) { wk.counter[0] = 0; wk.counter[1] = 0; __threadfence(); }   // ready for the next launch
+    }
+}
+
 // host: M^steps of xorshift32 as 4 byte-indexed LUTs (linear over GF(2))
 static void jump_table_fill(uint32_t *t, uint32_t steps) {
     for (int k = 0; k < 4; ++k)
@@ -695,6 +822,35 @@ static int launch_v2_order(cproc_cuda_batch *b, PdmV2Params &p, bool fast, bool 
             CK(ctx, cudaMemsetAsync(ctx->d_sm_rank, 0, 1024 * sizeof(uint32_t), ctx->stream));
         }
         ex.sm_rank = ctx->d_sm_rank;
+        // dynamic schedule: only where the plain grid is unbalanced (more blocks than one
+        // even layer over the SMs) and the run is long enough to be cut into slices
+        const uint64_t batches = p.F / WS2_T;
+        const uint64_t ctas = (uint64_t)ctx->n_sm * ctx->pdm_ctas_per_sm;
+        const bool dyn = ctx->pdm_ws >= 3 && K == 2 && p.bank_size == 3 && C > ctas && C < 65536 && batches >= 2 * (uint64_t)ctx->pdm_slice_batches;
+        if constexpr (K == 2) if (dyn) {
+            if (b->n_flags < C) {
+                if (b->d_flags) cudaFree(b->d_flags);
+                b->d_flags = nullptr; b->n_flags = 0;
+                CK(ctx, cudaMalloc(&b->d_flags, sizeof(unsigned long long) * C));
+                CK(ctx, cudaMemsetAsync(b->d_flags, 0, sizeof(unsigned long long) * C, ctx->stream));
+                b->n_flags = C;
+            }
+            if (!ctx->d_work) {
+                CK(ctx, cudaMalloc(&ctx->d_work, 2 * sizeof(uint32_t)));
+                CK(ctx, cudaMemsetAsync(ctx->d_work, 0, 2 * sizeof(uint32_t), ctx->stream));
+            }
+            PdmV2Work wk;
+            wk.counter = ctx->d_work; wk.flags = b->d_flags; wk.epoch = ++b->epoch;
+            wk.groups = (uint32_t)C; wk.bps = (uint32_t)ctx->pdm_slice_batches;
+            wk.slices = (uint32_t)ceil_div_u64(batches, wk.bps);
+            const int f = form;
+#define WS3_GO(FF, PP) k_pdm_v2_ws3<2, 3, FF, PP, 2><<<(unsigned)ctas, 128, 0, ctx->stream>>>(p, ex, wk)
+            if (P == 4) { if (f == 1) WS3_GO(1, 4); else if (f == 2) WS3_GO(2, 4); else WS3_GO(0, 4); }
+            else if (P == 2) { if (f == 1) WS3_GO(1, 2); else if (f == 2) WS3_GO(2, 2); else WS3_GO(0, 2); }
+            else { if (f == 1) WS3_GO(1, 1); else if (f == 2) WS3_GO(2, 1); else WS3_GO(0, 1); }
+#undef WS3_GO
+            return 0;
+        }
 #define WS2_GO(BB, FF, PP) do { if (ctx->pdm_slots >= 4) k_pdm_v2_ws2<K, BB, FF, PP, 4><<<grid, 32 * (BB + 1), 0, ctx->stream>>>(p, ex); \
                                 else k_pdm_v2_ws2<K, BB, FF, PP, 2><<<grid, 32 * (BB + 1), 0, ctx->stream>>>(p, ex); } while (0)
 #define WS2_P(BB, FF) do { if (P == 4) WS2_GO(BB, FF, 4); else if (P == 2) WS2_GO(BB, FF, 2); else WS2_GO(BB, FF, 1); } while (0)

@@ -416,7 +416,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_sweep_scan(const SweepParam
 // arithmetic, so inside the same instruction stream it is hidden behind the stores.
 template <bool TILED, bool ZSR>
 __global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) {
-    __shared__ __align__(16) float2 tile[TILED ? 1 : XV_WARPS][TILED ? 1 : 32][TILED ? 1 : 33];   // PLANAR: [warp][stream][frame]
+    constexpr int PT = 32;                               // PLANAR: frames staged per pass (256-byte runs per stream; 128-byte runs cost 20% of the bandwidth)
+    __shared__ __align__(16) float2 tile[TILED ? 1 : XV_WARPS][TILED ? 1 : 32][TILED ? 1 : PT + 1];   // [warp][stream][frame]
     const uint64_t i = p.i0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t c = blockIdx.y, n = p.x.n, npad = p.x.npad, F = p.x.F;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -454,20 +455,22 @@ __global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) 
             if (mine) st_v4_stream(p.x.raw + (((t >> 1) * n + i) << 2),
                                    make_uint4(__float_as_uint(l0), __float_as_uint(r0), __float_as_uint(l1), __float_as_uint(r1)));
         }
-    } else {                                             // [inst][F][2]: 32 frames staged per warp, rows written as 256 B runs
+    } else {                                             // [inst][F][2]: PT frames staged per warp, rows written as PT*8 B runs
         const uint64_t iw = i - lane;                    // first stream of this warp
-        for (uint64_t t = f0; t < f1; t += 32) {
-            const uint32_t cols = f1 - t < 32 ? (uint32_t)(f1 - t) : 32;
+        for (uint64_t t = f0; t < f1; t += PT) {
+            const uint32_t cols = f1 - t < PT ? (uint32_t)(f1 - t) : PT;
             for (uint32_t k = 0; k < cols; ++k) {
                 const float y = xvoice_tick(v);
                 tile[warp][lane][k] = make_float2(__fmul_rn(v.gl, y), __fmul_rn(v.gr, y));
                 if (ZSR) zsr_tick(zph, zinc, zf, znq, zlp, zbp);
             }
             __syncwarp();
-            // 16 lanes x 16 B cover the 32 frames of one stream; a warp instruction writes two streams
-            const uint32_t half = lane >> 4, fp = (lane & 15) * 2;
-            for (uint32_t jj = 0; jj < 32; jj += 2) {
-                const uint32_t sidx = jj + half;
+            // PT/2 lanes x 16 B cover the PT frames of one stream; a warp instruction writes 64/PT streams
+            constexpr uint32_t LPS = PT / 2, SPI = 32 / LPS;
+            const uint32_t sub = lane / LPS, fp = (lane % LPS) * 2;
+#pragma unroll 4
+            for (uint32_t jj = 0; jj < 32; jj += SPI) {
+                const uint32_t sidx = jj + sub;
                 if (iw + sidx < p.i1) {
                     float *dst = p.x.raw + (((iw + sidx) * F + t + fp) << 1);
                     if (fp + 1 < cols) {
@@ -588,7 +591,9 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     if (b->cfg.mode == CPROC_CUDA_XVOICE_SCAN && io->out && !io->mix) {
         // variant groups of >= 128; chunk length: enough (variant, chunk) threads per group to
         // fill the chip, multiple of 32 frames
-        uint64_t groups = ctx->xvoice_groups > 0 ? (uint64_t)ctx->xvoice_groups : 8;
+        // (PLANAR stages rows through shared memory, which caps its occupancy: the fused render
+        // does not pay there, measured, so its pre-passes simply run first)
+        uint64_t groups = ctx->xvoice_groups > 0 ? (uint64_t)ctx->xvoice_groups : (io->layout == CPROC_CUDA_TILED ? 8 : 1);
         if (groups > ceil_div_u64(b->n, 128)) groups = ceil_div_u64(b->n, 128);
         // (one wave of the fused render, 1536 threads per SM, when the groups are pipelined)
         const uint64_t want_threads = groups >= 3 ? (uint64_t)ctx->n_sm * 1536 : (uint64_t)ctx->n_sm * 2048 * 2;

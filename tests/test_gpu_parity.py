@@ -83,10 +83,12 @@ def _v2_case(st, ctx, oracle, order, bank, N, F, layout, count0, use_setp, use_d
         ctx.set_option("pdm_block", 64)
         ctx.set_option("pdm_persist", 1)
         ctx.set_option("pdm_warps_per_smsp", 1)
-        ctx.set_option("pdm_ws", 2)
+        ctx.set_option("pdm_ws", 3)
         ctx.set_option("pdm_form", 1)
         ctx.set_option("pdm_chains", 2)
         ctx.set_option("pdm_slots", 2)
+        ctx.set_option("pdm_ctas_per_sm", 4)
+        ctx.set_option("pdm_slice_batches", 64)
 
 
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
@@ -136,6 +138,31 @@ def test_pdm_v2_ws2_split_runs(st, ctx, oracle):
     """Consecutive ws2 launches continue seamlessly (state, PRNG, control counter)."""
     _v2_case(st, ctx, oracle, 2, 3, N=96 * 5 + 7, F=64 * 20, layout=st.TILED, count0=0, use_setp=True, use_dext=False,
              ctl=7, split=[64 * 3, 64, 64 * 10, 64 * 6], opts={"pdm_ws": 2})
+
+
+@pytest.mark.parametrize("form", [0, 1, 2])
+@pytest.mark.parametrize("chains", [1, 2, 4])
+@pytest.mark.parametrize("layout", ["PLANAR", "TILED"])
+def test_pdm_v2_ws3_dynamic_schedule(st, ctx, oracle, form, chains, layout):
+    """Dynamic (group, slice) schedule: more 32-bank groups (151) than persistent blocks
+    (148 x 1), slices of 2 dither batches with a ragged last slice (9 batches), the control
+    counter starting one batch into a 4-batch period, setpoint rows latched inside slices."""
+    _v2_case(st, ctx, oracle, 2, 3, N=96 * 150 + 5, F=64 * 9, layout=getattr(st, layout), count0=64, use_setp=True,
+             use_dext=False, ctl=8, opts={"pdm_ws": 3, "pdm_form": form, "pdm_chains": chains, "pdm_ctas_per_sm": 1,
+                                          "pdm_slice_batches": 2})
+
+
+@pytest.mark.parametrize("ctas,slice_b,F", [(4, 2, 64 * 8), (4, 3, 64 * 8), (2, 4, 64 * 8), (4, 64, 64 * 128)])
+def test_pdm_v2_ws3_c2_shape(st, ctx, oracle, ctas, slice_b, F):
+    """The C2 channel count (65,536 channels = 683 groups for 148 x ctas blocks)."""
+    _v2_case(st, ctx, oracle, 2, 3, N=65536, F=F, layout=st.TILED, count0=0, use_setp=True, use_dext=False, ctl=7,
+             opts={"pdm_ws": 3, "pdm_ctas_per_sm": ctas, "pdm_slice_batches": slice_b})
+
+
+def test_pdm_v2_ws3_split_runs(st, ctx, oracle):
+    """Consecutive dynamic launches (work counter, epochs and progress words are reused)."""
+    _v2_case(st, ctx, oracle, 2, 3, N=96 * 150 + 5, F=64 * 22, layout=st.TILED, count0=0, use_setp=True, use_dext=False,
+             ctl=7, split=[64 * 5, 64 * 4, 64 * 9, 64 * 4], opts={"pdm_ws": 3, "pdm_ctas_per_sm": 1, "pdm_slice_batches": 2})
 
 
 @pytest.mark.parametrize("N,bank,F,wps", [(65536, 3, 512, 1), (65536, 4, 256, 1), (3 * 32 * 1300 + 5, 3, 160, 1),
@@ -574,7 +601,7 @@ def test_xvoice_scan(st, ctx, oracle, layout, N, F, chunk, groups):
         raw = np.zeros(N * F * 2, np.float32)
         l0 = ctx.launches
         b.run(F, out=raw)
-        g_req = min(groups or 8, -(-N // 128))
+        g_req = min(groups or (8 if layout == "TILED" else 1), -(-N // 128))
         per = -(-(-(-N // g_req)) // 128) * 128              # variants per group, multiple of 128
         g_eff = -(-N // per)
         piped = g_eff >= 3                                   # look-ahead-2 pipeline: zero-state passes fused into the renders
