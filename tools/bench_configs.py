@@ -1,0 +1,148 @@
+"""Device-resident timing of the non-headline BASELINE.json configurations at their full
+shapes (C3a, C3b, C4, C4', C5), each against the roofline that bounds it.
+Used by bench.py (key "other_configs", N=1 only) and by tools/quick_others.py.
+
+Timing: CUDA events on the context stream (cproc_cuda_timer_*), best of `reps` after one
+warm-up run; every buffer is larger than L2 or the kernel is issue bound (stated per row).
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+ISSUE_PEAK = 128.0 * 148 * 1.965e9       # thread-instr/s at sm_max_mhz (tools/ubench_int.cu: 128 /clk/SM)
+TAB12 = np.array([594573364, 629928536, 667386036, 707070875, 749115497, 793660223, 840853716, 890853479,
+                  943826384, 999949221, 1059409296, 1122405051], np.uint32)     # linux/synth.c:78-95 (gcc, verified)
+
+
+def note_incs(rng, n, lo=24, hi=109):
+    notes = rng.integers(lo, hi, n)
+    octave = np.where(notes < 8, 10, 9 - (notes - 8) // 12)
+    idx = np.where(notes < 8, notes + 4, (notes - 8) % 12)
+    return (TAB12[idx] >> octave.astype(np.uint32)).astype(np.uint32)
+
+
+def xvoice_records(rng, N):
+    prm = np.zeros((N, 8), np.uint32)
+    prm[:, 0] = note_incs(rng, N)
+    prm[:, 1] = rng.uniform(0.01, 0.3, N).astype(np.float32).view(np.uint32)
+    prm[:, 2] = rng.uniform(0.5, 2.0, N).astype(np.float32).view(np.uint32)
+    prm[:, 3] = rng.uniform(1e-3, 1e-1, N).astype(np.float32).view(np.uint32)
+    prm[:, 4] = rng.uniform(1e-3, 1e-2, N).astype(np.float32).view(np.uint32)
+    prm[:, 5] = rng.integers(0, 400, N)
+    g = rng.uniform(0, 1, N).astype(np.float32)
+    prm[:, 6] = g.view(np.uint32); prm[:, 7] = (1 - g).astype(np.float32).view(np.uint32)
+    stt = np.zeros((N, 5), np.uint32); stt[:, 0] = rng.integers(0, 2**32, N, dtype=np.uint32)
+    return stt, prm
+
+
+def _time(ctx, fn, reps):
+    fn(); ctx.sync()
+    best = 1e9
+    for _ in range(reps):
+        ctx.timer_start(); fn(); best = min(best, ctx.timer_stop())
+    return best
+
+
+def _hbm(name, units, unit_name, ms, bytes_per_unit, hbm_peak, note):
+    gbs = bytes_per_unit * units / ms / 1e6
+    return {"config": name, "value": units / (ms * 1e-3), "unit": unit_name + "/s", "ms": ms, "bound": "hbm",
+            "achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": gbs / hbm_peak, "algorithmic_bytes_per_unit": bytes_per_unit,
+            "note": note}
+
+
+def _issue(name, units, unit_name, ms, instr_per_unit, note):
+    rate = instr_per_unit * units / (ms * 1e-3)
+    return {"config": name, "value": units / (ms * 1e-3), "unit": unit_name + "/s", "ms": ms, "bound": "issue",
+            "achieved_tinstr_s": rate / 1e12, "peak_tinstr_s": ISSUE_PEAK / 1e12, "frac": rate / ISSUE_PEAK,
+            "algorithmic_instr_per_unit": instr_per_unit, "note": note}
+
+
+def c3a(st, ctx, hbm_peak, reps=5, layout="planar"):
+    rng = np.random.default_rng(3)
+    N, F = 1024 * 1024, 256
+    d_in = ctx.dev_alloc(4 * N * F); d_out = ctx.dev_alloc(4 * N * F)
+    chunk = rng.uniform(-1, 1, (65536, F)).astype(np.float32)
+    for k in range(N // 65536):
+        ctx.h2d(d_in + k * chunk.nbytes, chunk)
+    b = ctx.batch(st.SQUARE_GRAIN, N, layout=st.PLANAR if layout == "planar" else st.INTERLEAVED)
+    b.upload_param(rng.uniform(0.05, 0.5, (N, 1)).astype(np.float32))
+    ms = _time(ctx, lambda: b.run_dev(F, inp=d_in, out=d_out), reps)
+    b.free(); ctx.dev_free(d_in); ctx.dev_free(d_out)
+    return _hbm("C3a square_grain raw, 1 Mi grains x 256 frames, %s float in/out" % layout, N * F, "grain-samples", ms, 8.0, hbm_peak,
+                "4 B in + 4 B out per grain-sample; 1 GiB in + 1 GiB out, larger than L2")
+
+
+def c3b(st, ctx, reps=5):
+    rng = np.random.default_rng(4)
+    N, F = 1024 * 1024, 256
+    s_rec = np.zeros((N, 2), np.uint32); s_rec[:, 1] = rng.integers(0, 2**32, N, dtype=np.uint32)
+    p_rec = np.zeros((N, 4), np.uint32)
+    p_rec[:, 0] = rng.uniform(0.05, 0.5, N).astype(np.float32).view(np.uint32); p_rec[:, 1] = note_incs(rng, N, 36, 97)
+    gl = rng.integers(0, 65, N); p_rec[:, 2] = gl; p_rec[:, 3] = 64 - gl
+    b = ctx.batch(st.SQUARE_GRAIN_MIX, N); b.upload_state(s_rec); b.upload_param(p_rec)
+    d_out = ctx.dev_alloc(8 * F); d_mix = ctx.dev_alloc(8 * F)
+    b.run_dev(F, out=d_out, mix=d_mix)          # leave the initial 0.0 state behind (steady state)
+    ms = _time(ctx, lambda: b.run_dev(F, out=d_out, mix=d_mix), reps)
+    b.free(); ctx.dev_free(d_out); ctx.dev_free(d_mix)
+    return _issue("C3b square_grain phasor -> trigger -> stereo integer mix, 1 Mi grains x 256 frames", N * F, "grain-samples", ms, 9.0,
+                  "SURVEY 8d: 9 algorithmic instr per grain-sample; timed region = memset + mix kernel + int->float kernel")
+
+
+def c4(st, ctx, reps=3):
+    rng = np.random.default_rng(5)
+    N, F = 4 * 1024 * 1024, 512
+    stt, prm = xvoice_records(rng, N)
+    b = ctx.batch(st.XVOICE, N); b.upload_state(stt); b.upload_param(prm)
+    d_mix = ctx.dev_alloc(8 * F)
+    ms = _time(ctx, lambda: b.run_dev(F, mix=d_mix), reps)
+    b.free(); ctx.dev_free(d_mix)
+    return _issue("C4 poly voice (phasor + SVF + AR envelope + pan), 4 Mi voices x 512 frames, float stereo mix", N * F, "voice-samples", ms, 18.0,
+                  "SURVEY 8d: 18 algorithmic instr per voice-sample; deterministic fixed-order mix")
+
+
+def c4p(st, ctx, reps=5):
+    rng = np.random.default_rng(6)
+    N, F = 4 * 1024 * 1024, 512
+    v = np.zeros((N, 2), np.uint32); v[:, 0] = note_incs(rng, N); v[:, 1] = rng.integers(0, 2**32, N, dtype=np.uint32)
+    b = ctx.batch(st.VOICE_BANK, N, voices_per_bus=0); b.upload_state(v)
+    d_out = ctx.dev_alloc(4 * F); d_mix = ctx.dev_alloc(4 * F)
+    ms = _time(ctx, lambda: b.run_dev(F, out=d_out, mix=d_mix), reps)
+    b.free(); ctx.dev_free(d_out); ctx.dev_free(d_mix)
+    return _issue("C4' reference voice bank (sum_tick_saw, linux/synth.c:169-181), 4 Mi voices x 512 frames, int32 mix", N * F, "voice-samples", ms, 4.0,
+                  "SURVEY 8d a-7: 4 int ops per voice-sample; bit-exact at any reduction order")
+
+
+def c5(st, ctx, hbm_peak, reps=3, layout="tiled"):
+    rng = np.random.default_rng(7)
+    N, F = 2048, 480000
+    stt, prm = xvoice_records(rng, N)
+    d_out = ctx.dev_alloc(8 * N * F)
+    b = ctx.batch(st.XVOICE, N, layout=st.TILED if layout == "tiled" else st.PLANAR, mode=st.XVOICE_SCAN)
+    b.upload_state(stt); b.upload_param(prm)
+    ms = _time(ctx, lambda: b.run_dev(F, out=d_out), reps)
+    b.free(); ctx.dev_free(d_out)
+    return _hbm("C5 patch sweep shard, 2,048 variants x 480,000 frames (10 s @ 48 kHz) stereo float raw out, %s, time-parallel scan" % layout,
+                N * F, "variant-frames", ms, 8.0, hbm_peak, "8 B out per variant-frame (7.86 GB per launch, larger than L2); "
+                "timed region = envelope walk + zero-state passes + scans + renders")
+
+
+def run_all(st, ctx, hbm_peak):
+    rows = []
+    for fn in (lambda: c3a(st, ctx, hbm_peak, layout="planar"), lambda: c3a(st, ctx, hbm_peak, layout="interleaved"),
+               lambda: c3b(st, ctx), lambda: c4(st, ctx), lambda: c4p(st, ctx),
+               lambda: c5(st, ctx, hbm_peak, layout="tiled"), lambda: c5(st, ctx, hbm_peak, layout="planar")):
+        try:
+            rows.append(fn())
+        except Exception as e:                       # never lose the headline line over a secondary row
+            rows.append({"error": "%s: %s" % (type(e).__name__, e)})
+    return rows
+
+
+if __name__ == "__main__":
+    import json
+    import synth_tools_b200 as st
+    ctx = st.Context(0)
+    for r in run_all(st, ctx, 6538.0):
+        print(json.dumps(r))
