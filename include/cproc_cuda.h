@@ -122,6 +122,7 @@ enum cproc_cuda_proc {
 };
 
 enum { CPROC_CUDA_NODE_ACC = 0, CPROC_CUDA_NODE_EDGE = 1 };
+#define CPROC_CUDA_GRAPH_MAX_NODES 64
 enum { CPROC_CUDA_MIX_SAW = 0, CPROC_CUDA_MIX_SQUARE = 1 };
 enum { CPROC_CUDA_XVOICE_SEQ = 0, CPROC_CUDA_XVOICE_SCAN = 1 };
 
@@ -158,6 +159,19 @@ typedef struct {
     uint32_t n_nodes, n_inputs, out_node;
     uint32_t reserved;
 } cproc_cuda_config;
+
+/* Front end for the generated graph text.  `text` is what
+ * epid_cproc.erl emits and the reference compiles as C (linux/test_cproc.c:11-17,
+ * stm32f103/bp5_plugin.c:1-9): `#define CPROC_NB_INPUTS n`, a sequence of
+ *   PROC_COND(<changed> & <mask>, <inst>, acc|edge, NULL, NULL, .in = input[k] | <inst>.out);
+ * (or PROC(<inst>, ...), cproc.h:81) and one `cproc_output(<index>, <inst>.out);`.
+ * Fills `nodes` (at most max_nodes rows) and `info`; the rows go into
+ * cproc_cuda_config.nodes / n_nodes / n_inputs / out_node unchanged.  Needs no device. */
+typedef struct {
+    uint32_t n_nodes, n_inputs, out_node;
+    uint32_t out_index;       /* first argument of cproc_output (the TAG_U32 index, mod_cproc_plugin.c:40-43) */
+} cproc_cuda_graph_info;
+int  cproc_cuda_graph_parse(const char *text, cproc_cuda_node *nodes, uint32_t max_nodes, cproc_cuda_graph_info *info);
 
 /* Buffers of one run.  Host pointers for cproc_cuda_run, device pointers for
  * cproc_cuda_run_dev.  Unused members are NULL. */
@@ -219,6 +233,15 @@ typedef void (*cproc_cuda_chunk_fn)(void *user, uint64_t chunk_index, const void
 int  cproc_cuda_run_stream(cproc_cuda_batch *b, uint64_t n_frames_total,
                            uint64_t n_frames_chunk, const cproc_cuda_io *io,
                            uint32_t ring_chunks, cproc_cuda_chunk_fn on_chunk, void *user);
+/* Graph batches are compiled for their node table with NVRTC when first run (one
+ * kernel per graph: node states in registers, sources and masks as literals).  The
+ * compiler log (warnings, or the reason the table-driven kernel is used instead) and
+ * the generated CUDA source for a node table (returns its length; copies at most
+ * cap-1 bytes; needs no device). */
+const char *cproc_cuda_graph_jit_log(const cproc_cuda_batch *b);
+int  cproc_cuda_graph_jit_source(const cproc_cuda_node *nodes, uint32_t n_nodes, uint32_t n_inputs, uint32_t out_node,
+                                 int has_changed, char *dst, size_t cap);
+
 /* Integer mix bus -> float, after a multi-GPU all-reduce of the raw mix:
  * VOICE_BANK saw: (float)(int)x * 2^-32 (synth.c:180); square: (float)(unsigned)x
  * * 2^-32 (:194); SQUARE_GRAIN_MIX: (float)x * 2^-7.  Device pointers. */

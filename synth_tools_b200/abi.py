@@ -32,6 +32,13 @@ class Config(C.Structure):
                 ("n_nodes", C.c_uint32), ("n_inputs", C.c_uint32), ("out_node", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class GraphInfo(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint32), ("n_inputs", C.c_uint32), ("out_node", C.c_uint32), ("out_index", C.c_uint32)]
+
+
+GRAPH_MAX_NODES = 64
+
+
 class IO(C.Structure):
     _fields_ = [("in_", C.c_void_p), ("in2", C.c_void_p), ("ctl", C.c_void_p), ("out", C.c_void_p),
                 ("mix", C.c_void_p), ("layout", C.c_uint32), ("n_ctl", C.c_uint32)]
@@ -71,6 +78,9 @@ SYMBOLS = {
     "cproc_cuda_timer_start": (C.c_int, [C.c_void_p]),
     "cproc_cuda_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "cproc_cuda_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "cproc_cuda_graph_parse": (C.c_int, [C.c_char_p, C.POINTER(Node), C.c_uint32, C.POINTER(GraphInfo)]),
+    "cproc_cuda_graph_jit_log": (C.c_char_p, [C.c_void_p]),
+    "cproc_cuda_graph_jit_source": (C.c_int, [C.POINTER(Node), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_char_p, C.c_size_t]),
 }
 
 
@@ -93,6 +103,29 @@ def load(path=LIB_PATH):
 
 
 lib = load()
+
+
+def graph_parse(text):
+    """Generated cproc graph text (epid_cproc.erl output, linux/test_cproc.c:11-17) ->
+    ([(type, src, cond_mask)], n_inputs, out_node, out_index).  Needs no device."""
+    nodes = (Node * GRAPH_MAX_NODES)()
+    info = GraphInfo()
+    rc = lib.cproc_cuda_graph_parse(text.encode(), nodes, GRAPH_MAX_NODES, C.byref(info))
+    if rc:
+        raise CprocCudaError(rc, (lib.cproc_cuda_last_error(None) or b"").decode())
+    rows = [(nodes[k].type, nodes[k].src, nodes[k].cond_mask) for k in range(info.n_nodes)]
+    return rows, info.n_inputs, info.out_node, info.out_index
+
+
+def graph_jit_source(rows, n_inputs, out_node, has_changed=False):
+    """The CUDA source the library generates (and NVRTC-compiles) for a node table."""
+    arr = (Node * len(rows))(*[Node(t, s, m) for t, s, m in rows])
+    n = lib.cproc_cuda_graph_jit_source(arr, len(rows), n_inputs, out_node, int(has_changed), None, 0)
+    if n < 0:
+        raise CprocCudaError(n, (lib.cproc_cuda_last_error(None) or b"").decode())
+    buf = C.create_string_buffer(n + 1)
+    lib.cproc_cuda_graph_jit_source(arr, len(rows), n_inputs, out_node, int(has_changed), buf, n + 1)
+    return buf.value.decode()
 
 
 def _vp(a):
@@ -253,6 +286,10 @@ class Batch:
         io = self._io(None, None, ctl, out, None, layout, n_ctl)
         cb = CHUNK_FN(on_chunk) if on_chunk is not None else C.cast(None, CHUNK_FN)
         self.ctx._ck(lib.cproc_cuda_run_stream(self.h, F_total, F_chunk, C.byref(io), ring_chunks, cb, None))
+
+    @property
+    def jit_log(self):
+        return (lib.cproc_cuda_graph_jit_log(self.h) or b"").decode()
 
     def mix_to_float(self, imix_dev, out_dev, count):
         self.ctx._ck(lib.cproc_cuda_mix_to_float(self.h, imix_dev, out_dev, count))

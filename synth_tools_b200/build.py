@@ -54,7 +54,7 @@ def build(force=False, verbose=False, ptxas_v=False):
         for s, p in procs:
             if p.wait() != 0:
                 raise RuntimeError("nvcc failed on %s" % s)
-        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "static"]
+        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "static", "-ldl"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

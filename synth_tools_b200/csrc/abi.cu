@@ -109,6 +109,7 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     else if (!strcmp(name, "pdm_slice_batches")) { if (value < 2 || value > 65536) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_slice_batches must be 2..65536"); ctx->pdm_slice_batches = (int)value; }
     else if (!strcmp(name, "pdm_form")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_form must be 0..2"); ctx->pdm_form = (int)value; }
     else if (!strcmp(name, "grain_blocks_per_sm")) { if (value < 1 || value > 16) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "grain_blocks_per_sm must be 1..16"); ctx->grain_blocks_per_sm = (int)value; }
+    else if (!strcmp(name, "graph_jit")) ctx->graph_jit = value != 0;
     else if (!strcmp(name, "grain_bulk")) { if (value < 0 || value > 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "grain_bulk must be 0..4"); ctx->grain_bulk = (int)value; }
     else if (!strcmp(name, "grain_vec4")) ctx->grain_vec4 = value != 0;
     else if (!strcmp(name, "grain_mix2")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "grain_mix2 must be 0..2"); ctx->grain_mix2 = (int)value; }
@@ -152,7 +153,7 @@ int cproc_cuda_alloc(cproc_cuda_ctx *ctx, const cproc_cuda_config *cfg, uint64_t
     std::vector<cproc_cuda_node> nodes;
     bool pdm_family = c.proc == CPROC_CUDA_PDM || c.proc == CPROC_CUDA_PDM_V1 || c.proc == CPROC_CUDA_PDM_V2;
     if (c.proc == CPROC_CUDA_GRAPH) {
-        if (!c.nodes || c.n_nodes == 0 || c.n_nodes > 16) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph needs 1..16 nodes");
+        if (!c.nodes || c.n_nodes == 0 || c.n_nodes > CPROC_CUDA_GRAPH_MAX_NODES) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph needs 1..%d nodes", CPROC_CUDA_GRAPH_MAX_NODES);
         if (c.n_inputs == 0 || c.out_node >= c.n_nodes) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph n_inputs/out_node invalid");
         nodes.assign(c.nodes, c.nodes + c.n_nodes);
         for (uint32_t k = 0; k < c.n_nodes; ++k) {
@@ -173,7 +174,7 @@ int cproc_cuda_alloc(cproc_cuda_ctx *ctx, const cproc_cuda_config *cfg, uint64_t
     if (c.layout > CPROC_CUDA_TILED) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: unknown layout %u", c.layout);
     uint32_t sw = 0, pw = 0;
     if (proc_words(c, nodes, &sw, &pw)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: unknown processor %u", c.proc);
-    if (sw > 32) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph state too large (%u words)", sw);
+    if (sw > 2 * CPROC_CUDA_GRAPH_MAX_NODES) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph state too large (%u words)", sw);
 
     CK(ctx, cudaSetDevice(ctx->device));
     cproc_cuda_batch *b = new cproc_cuda_batch();
@@ -222,6 +223,7 @@ int cproc_cuda_free(cproc_cuda_batch *b) {
     cudaStreamSynchronize(b->ctx->stream);
     void *ptrs[] = { b->d_state, b->d_param, b->d_prng, b->d_nodes, b->d_in, b->d_in2, b->d_ctl, b->d_out, b->d_out2, b->d_mix, b->d_flags, b->d_scratch, b->d_aux };
     for (void *q : ptrs) if (q) cudaFree(q);
+    for (cproc_graph_jit &j : b->jit) if (j.lib) cudaLibraryUnload(j.lib);
     delete b;
     return 0;
 }
@@ -239,7 +241,7 @@ static int aos_to_dev(cproc_cuda_batch *b, uint32_t *d_rows, uint32_t words, con
     std::vector<uint32_t> soa((size_t)words * b->npad, 0u);
     const uint8_t *src = (const uint8_t *)aos;
     for (uint64_t i = 0; i < b->n; ++i) {
-        uint32_t rec[40];
+        uint32_t rec[2 * CPROC_CUDA_GRAPH_MAX_NODES + 8];
         memcpy(rec, src + i * stride, 4u * words);
         for (uint32_t w = 0; w < words; ++w) soa[(size_t)w * b->npad + i] = rec[w];
     }
@@ -274,7 +276,7 @@ int cproc_cuda_download_state(cproc_cuda_batch *b, void *aos, size_t stride) {
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     uint8_t *dst = (uint8_t *)aos;
     for (uint64_t i = 0; i < b->n; ++i) {
-        uint32_t rec[40];
+        uint32_t rec[2 * CPROC_CUDA_GRAPH_MAX_NODES + 8];
         for (uint32_t w = 0; w < words; ++w) rec[w] = soa[(size_t)w * b->npad + i];
         memcpy(dst + i * stride, rec, 4u * words);
     }

@@ -40,9 +40,19 @@ struct cproc_cuda_ctx {
     int grain_bulk = 1;       // planar square_grain: 0 register-transpose kernel; 1..4 bulk-copy kernel (tile/stage shapes)
     int grain_vec4 = 1;       // interleaved square_grain: four grains per thread when n % 4 == 0
     int grain_mix2 = 2;       // 0: float kernel; 1: register-accumulator / integer-threshold kernel; 2: predicate-state kernel
+    int graph_jit = 1;        // 1: generated graphs are compiled with NVRTC; 0: table-driven kernel
     int xvoice_block = 128;
     int xvoice_groups = 0;    // XVOICE_SCAN: variant groups pipelined over the two streams (0 = automatic)
     int xvoice_chunk = 0;     // XVOICE_SCAN: frames per time chunk (0 = automatic)
+};
+
+// NVRTC-compiled kernels of one graph (graph_front.cu); state 0 = not tried, 1 = ready, 2 = failed
+struct cproc_graph_jit {
+    int state = 0;
+    std::vector<char> cubin;
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t k_il = nullptr, k_pl = nullptr, k_ps = nullptr;
+    uint32_t pl_smem = 0, pl_block = 0;
 };
 
 struct cproc_cuda_batch {
@@ -69,6 +79,8 @@ struct cproc_cuda_batch {
     unsigned long long *d_flags = nullptr;         // persistent-kernel progress words
     uint64_t n_flags = 0;
     unsigned long long epoch = 0;
+    cproc_graph_jit jit[2];                        // [changed stream present]
+    std::string jit_log;
 };
 
 int cproc_set_err(cproc_cuda_ctx *ctx, int code, const char *fmt, ...);
@@ -85,6 +97,7 @@ int cproc_io_bytes(const cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *i
 
 // Kernel launchers (one translation unit per family).
 int launch_graph(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
+int cproc_graph_jit_get(cproc_cuda_batch *b, bool has_changed, cproc_graph_jit **out);
 int launch_pdm(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
 int launch_pdm_v1(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
 int launch_pdm_v2(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);

@@ -1,0 +1,505 @@
+// graph_front.cu -- front end of the generated cproc graphs.
+//
+//  * cproc_cuda_graph_parse: reads the C text that epid_cproc.erl generates -- the wire
+//    format between the Erlang side and the C side of the reference
+//    (linux/test_cproc.c:11-17, stm32f103/bp5_plugin.c:1-9):
+//        #define CPROC_NB_INPUTS 1
+//        void cproc_update(w *input, w g) {
+//            PROC_COND(g&0b1, n1, edge, NULL, NULL, .in = input[0]);
+//            PROC_COND(g&0b1, n2, acc,  NULL, NULL, .in = n1.out);
+//            cproc_output(2, n2.out);
+//        }
+//    into the node table of CPROC_CUDA_GRAPH (one row per PROC_COND / PROC statement,
+//    generic/cproc.h:72-81).
+//  * graph JIT: a graph is straight-line code over its node states, so the renderer
+//    generates CUDA source for exactly this graph (every node state word a named
+//    register, every source a literal register name, masks as immediates) and compiles
+//    it with NVRTC for sm_100a when the batch is created.  PLANAR streams are staged
+//    with per-lane bulk copies as in k_grain_bulk; INTERLEAVED streams are read in
+//    16-frame batches.  libnvrtc is loaded with dlopen: without it (or with graph_jit=0)
+//    graphs of up to 16 nodes run on the table-driven kernel of k_graph.cu.
+#include "common.cuh"
+#include <ctype.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+// ---------------------------------------------------------------------------
+// parser
+
+namespace {
+
+struct Cursor {
+    const char *p;
+    std::string err;
+    void ws() { while (*p && isspace((unsigned char)*p)) ++p; }
+    bool lit(const char *s) { ws(); size_t n = strlen(s); if (strncmp(p, s, n) == 0) { p += n; return true; } return false; }
+    bool ident(std::string *out) {
+        ws();
+        if (!(isalpha((unsigned char)*p) || *p == '_')) return false;
+        const char *b = p;
+        while (isalnum((unsigned char)*p) || *p == '_') ++p;
+        out->assign(b, p);
+        return true;
+    }
+    bool number(uint64_t *out) {                       // decimal, 0x.., 0b.. (gcc extension used by the generator)
+        ws();
+        if (!isdigit((unsigned char)*p)) return false;
+        uint64_t v = 0;
+        if (p[0] == '0' && (p[1] == 'b' || p[1] == 'B')) {
+            p += 2;
+            if (*p != '0' && *p != '1') return false;
+            while (*p == '0' || *p == '1') v = (v << 1) | (uint64_t)(*p++ - '0');
+        } else if (p[0] == '0' && (p[1] == 'x' || p[1] == 'X')) {
+            p += 2;
+            if (!isxdigit((unsigned char)*p)) return false;
+            while (isxdigit((unsigned char)*p)) { const char c = *p++; v = (v << 4) | (uint64_t)(isdigit((unsigned char)c) ? c - '0' : (tolower(c) - 'a' + 10)); }
+        } else {
+            while (isdigit((unsigned char)*p)) v = v * 10 + (uint64_t)(*p++ - '0');
+        }
+        while (*p == 'u' || *p == 'U' || *p == 'l' || *p == 'L') ++p;
+        *out = v;
+        return true;
+    }
+};
+
+std::string strip_comments(const char *s) {
+    std::string o;
+    while (*s) {
+        if (s[0] == '/' && s[1] == '/') { while (*s && *s != '\n') ++s; }
+        else if (s[0] == '/' && s[1] == '*') { s += 2; while (*s && !(s[0] == '*' && s[1] == '/')) ++s; if (*s) s += 2; o += ' '; }
+        else o += *s++;
+    }
+    return o;
+}
+
+// top-level comma split of a parenthesised argument list starting after '('; leaves c.p after ')'
+bool split_args(Cursor &c, std::vector<std::string> *args) {
+    int depth = 1;
+    std::string cur;
+    while (*c.p) {
+        const char ch = *c.p++;
+        if (ch == '(' || ch == '[' || ch == '{') ++depth;
+        if (ch == ')' || ch == ']' || ch == '}') { if (--depth == 0) { args->push_back(cur); return true; } }
+        if (ch == ',' && depth == 1) { args->push_back(cur); cur.clear(); continue; }
+        cur += ch;
+    }
+    return false;
+}
+
+std::string trim(const std::string &s) {
+    size_t a = 0, b = s.size();
+    while (a < b && isspace((unsigned char)s[a])) ++a;
+    while (b > a && isspace((unsigned char)s[b - 1])) --b;
+    return s.substr(a, b - a);
+}
+
+// condition of a PROC_COND: `g & MASK`, `MASK & g`, a constant, optionally parenthesised
+bool parse_cond(std::string s, uint32_t *mask, std::string *why) {
+    s = trim(s);
+    while (s.size() >= 2 && s.front() == '(' && s.back() == ')') s = trim(s.substr(1, s.size() - 2));
+    Cursor c{s.c_str(), ""};
+    std::string id; uint64_t v = 0;
+    if (c.number(&v)) {
+        c.ws();
+        if (*c.p == 0) { *mask = v ? 0xFFFFFFFFu : 0u; return true; }          // PROC(...) == PROC_COND(1, ...)
+        if (*c.p == '&') { ++c.p; if (c.ident(&id)) { c.ws(); if (*c.p == 0) { *mask = (uint32_t)v; return true; } } }
+    } else if (c.ident(&id)) {
+        c.ws();
+        if (*c.p == '&') { ++c.p; if (c.number(&v)) { c.ws(); if (*c.p == 0) { *mask = (uint32_t)v; return true; } } }
+    }
+    *why = "condition '" + s + "' is not of the form <changed> & <mask>";
+    return false;
+}
+
+}  // namespace
+
+extern "C" int cproc_cuda_graph_parse(const char *text, cproc_cuda_node *nodes, uint32_t max_nodes, cproc_cuda_graph_info *info) {
+    if (!text || !nodes || !info) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: NULL argument");
+    memset(info, 0, sizeof(*info));
+    const std::string src = strip_comments(text);
+    std::vector<std::string> names;
+    uint32_t max_input = 0; bool any_input = false;
+    uint32_t n_out = 0;
+    // #define CPROC_NB_INPUTS n
+    {
+        const char *d = strstr(src.c_str(), "CPROC_NB_INPUTS");
+        while (d) {
+            const char *ls = d; while (ls > src.c_str() && ls[-1] != '\n') --ls;
+            Cursor c{ls, ""};
+            if (c.lit("#") && c.lit("define") && c.lit("CPROC_NB_INPUTS")) { uint64_t v; if (c.number(&v)) { info->n_inputs = (uint32_t)v; break; } }
+            d = strstr(d + 1, "CPROC_NB_INPUTS");
+        }
+    }
+    const char *p = src.c_str();
+    while (*p) {
+        if (!(isalpha((unsigned char)*p) || *p == '_')) { ++p; continue; }
+        Cursor c{p, ""};
+        std::string id;
+        c.ident(&id);
+        p = c.p;
+        const bool is_cond = id == "PROC_COND", is_proc = id == "PROC";
+        if (!is_cond && !is_proc && id != "cproc_output") continue;
+        c.ws();
+        if (*c.p != '(') continue;                      // e.g. the definition `static inline void cproc_output(`... has '(' too, handled below
+        ++c.p;
+        std::vector<std::string> a;
+        if (!split_args(c, &a)) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: unbalanced parentheses after %s", id.c_str());
+        p = c.p;
+        if (id == "cproc_output") {
+            // a call has two expression arguments; the definition `cproc_output(uint32_t index, w value)` is skipped
+            if (a.size() != 2) continue;
+            Cursor n{a[0].c_str(), ""}; uint64_t idx;
+            if (!n.number(&idx)) continue;
+            std::string e = trim(a[1]);
+            const size_t dot = e.find('.');
+            if (dot == std::string::npos || trim(e.substr(dot + 1)) != "out")
+                return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: cproc_output value '%s' is not <node>.out", e.c_str());
+            const std::string nm = trim(e.substr(0, dot));
+            size_t k = 0;
+            while (k < names.size() && names[k] != nm) ++k;
+            if (k == names.size()) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: cproc_output reads unknown node '%s'", nm.c_str());
+            if (n_out++ == 0) { info->out_node = (uint32_t)k; info->out_index = (uint32_t)idx; }
+            continue;
+        }
+        const size_t base = is_cond ? 1 : 0;             // PROC(inst, type, cfg, prm, inits...)
+        if (a.size() < base + 5) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: %s needs an instance, a type, config, param and the inputs", id.c_str());
+        cproc_cuda_node nd;
+        std::string why;
+        if (is_cond) { if (!parse_cond(a[0], &nd.cond_mask, &why)) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: %s", why.c_str()); }
+        else nd.cond_mask = 0xFFFFFFFFu;
+        const std::string inst = trim(a[base]), type = trim(a[base + 1]), cfg = trim(a[base + 2]), prm = trim(a[base + 3]);
+        if (type == "acc") nd.type = CPROC_CUDA_NODE_ACC;
+        else if (type == "edge") nd.type = CPROC_CUDA_NODE_EDGE;
+        else return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s' has unknown processor type '%s' (acc, edge)", inst.c_str(), type.c_str());
+        if ((cfg != "NULL" && cfg != "0") || (prm != "NULL" && prm != "0"))
+            return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': %s has empty config and param records, expected NULL", inst.c_str(), type.c_str());
+        for (const std::string &nm : names) if (nm == inst) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s' bound twice", inst.c_str());
+        if (a.size() != base + 5) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': %s has exactly one input (.in)", inst.c_str(), type.c_str());
+        // .in = input[k]  |  .in = <node>.out
+        Cursor b{a[base + 4].c_str(), ""};
+        std::string f;
+        if (!b.lit(".") || !b.ident(&f) || f != "in" || !b.lit("=")) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': expected '.in = ...'", inst.c_str());
+        std::string s0;
+        if (!b.ident(&s0)) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': input expression not understood", inst.c_str());
+        if (b.lit("[")) {
+            uint64_t k;
+            if (s0 != "input" || !b.number(&k) || !b.lit("]")) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': expected input[<k>]", inst.c_str());
+            nd.src = -(int32_t)k - 1;
+            if (!any_input || k > max_input) max_input = (uint32_t)k;
+            any_input = true;
+        } else {
+            std::string fo;
+            if (!b.lit(".") || !b.ident(&fo) || fo != "out") return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': expected <node>.out", inst.c_str());
+            size_t k = 0;
+            while (k < names.size() && names[k] != s0) ++k;
+            if (k == names.size()) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s' reads '%s', which is not bound yet (ANF)", inst.c_str(), s0.c_str());
+            nd.src = (int32_t)k;
+        }
+        b.ws();
+        if (*b.p) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': trailing text in the input expression", inst.c_str());
+        if (names.size() >= max_nodes) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: more than %u nodes", max_nodes);
+        nodes[names.size()] = nd;
+        names.push_back(inst);
+    }
+    if (names.empty()) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: no PROC_COND / PROC statement found");
+    if (n_out == 0) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: no cproc_output(index, node.out) statement found");
+    if (n_out > 1) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: %u cproc_output statements; a batch renders one output stream", n_out);
+    const uint32_t need = any_input ? max_input + 1 : 0;
+    if (info->n_inputs == 0) info->n_inputs = need ? need : 1;
+    if (info->n_inputs < need) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: input[%u] used but CPROC_NB_INPUTS is %u", max_input, info->n_inputs);
+    info->n_nodes = (uint32_t)names.size();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// JIT
+
+namespace {
+
+typedef int (*nvrtcCreateProgram_t)(void **, const char *, const char *, int, const char *const *, const char *const *);
+typedef int (*nvrtcCompileProgram_t)(void *, int, const char *const *);
+typedef int (*nvrtcGetSize_t)(void *, size_t *);
+typedef int (*nvrtcGetData_t)(void *, char *);
+typedef int (*nvrtcDestroyProgram_t)(void **);
+
+struct Nvrtc {
+    void *h = nullptr;
+    nvrtcCreateProgram_t create = nullptr;
+    nvrtcCompileProgram_t compile = nullptr;
+    nvrtcGetSize_t cubin_size = nullptr, log_size = nullptr;
+    nvrtcGetData_t cubin = nullptr, log = nullptr;
+    nvrtcDestroyProgram_t destroy = nullptr;
+    bool tried = false;
+};
+Nvrtc g_nvrtc;
+
+bool nvrtc_load() {
+    if (g_nvrtc.tried) return g_nvrtc.h != nullptr;
+    g_nvrtc.tried = true;
+    const char *names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+    void *h = nullptr;
+    for (const char *n : names) if ((h = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
+    if (!h) {
+        // the wheel layout: nvidia/cuda_nvrtc/lib next to torch (searched through the loaded process image)
+        return false;
+    }
+    Nvrtc &r = g_nvrtc;
+    r.create = (nvrtcCreateProgram_t)dlsym(h, "nvrtcCreateProgram");
+    r.compile = (nvrtcCompileProgram_t)dlsym(h, "nvrtcCompileProgram");
+    r.cubin_size = (nvrtcGetSize_t)dlsym(h, "nvrtcGetCUBINSize");
+    r.cubin = (nvrtcGetData_t)dlsym(h, "nvrtcGetCUBIN");
+    r.log_size = (nvrtcGetSize_t)dlsym(h, "nvrtcGetProgramLogSize");
+    r.log = (nvrtcGetData_t)dlsym(h, "nvrtcGetProgramLog");
+    r.destroy = (nvrtcDestroyProgram_t)dlsym(h, "nvrtcDestroyProgram");
+    if (!r.create || !r.compile || !r.cubin_size || !r.cubin || !r.log_size || !r.log || !r.destroy) { dlclose(h); return false; }
+    r.h = h;
+    return true;
+}
+
+// The fixed part of the generated translation unit.  GRAPH_* macros and the two
+// generated code blocks (GRAPH_DECL_STATE .. GRAPH_TICK) come first.
+const char *k_jit_tail = R"SRC(
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef int int32_t;
+
+struct GraphParams {                       // must match k_graph.cu
+    uint32_t *st;
+    uint64_t npad, n;
+    const void *nodes;
+    uint32_t n_nodes, n_inputs, out_node, state_words;
+    const uint32_t *in;
+    const uint32_t *changed;
+    uint32_t *out;
+    uint64_t F;
+    uint32_t layout;
+};
+
+// one tick: x[] = this tick's inputs, g = changed mask; returns the output word
+#define TICK(x, g, o) do { GRAPH_TICK(x, g) o = GRAPH_OUT; } while (0)
+
+// [F][n_inputs][inst] in, [F][inst] changed / out: coalesced as they are; 16-frame batches
+// make the independent loads explicit (in may alias out).
+extern "C" __global__ void __launch_bounds__(128) graph_interleaved(const GraphParams p) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    GRAPH_DECL_STATE
+    GRAPH_LOAD_STATE(p.st, p.npad, i)
+    const uint32_t *src = p.in + i;
+    const uint32_t *chg = GRAPH_HAS_CHANGED ? p.changed + i : 0;
+    uint32_t *dst = p.out + i;
+    const uint64_t n = p.n;
+    uint64_t t = 0;
+    for (; t + 16 <= p.F; t += 16) {
+        uint32_t x[16][GRAPH_NIN], g[16], o[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+#pragma unroll
+            for (int j = 0; j < GRAPH_NIN; ++j) x[k][j] = __ldcs(src + ((t + k) * GRAPH_NIN + j) * n);
+            g[k] = GRAPH_HAS_CHANGED ? __ldcs(chg + (t + k) * n) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) TICK(x[k], g[k], o[k]);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) __stcs(dst + (t + k) * n, o[k]);
+    }
+    for (; t < p.F; ++t) {
+        uint32_t x[GRAPH_NIN], g, o;
+#pragma unroll
+        for (int j = 0; j < GRAPH_NIN; ++j) x[j] = __ldcs(src + (t * GRAPH_NIN + j) * n);
+        g = GRAPH_HAS_CHANGED ? __ldcs(chg + t * n) : 0xFFFFFFFFu;
+        TICK(x, g, o);
+        __stcs(dst + t * n, o);
+    }
+    GRAPH_STORE_STATE(p.st, p.npad, i)
+}
+
+// [inst][n_inputs][F] in, [inst][F] changed / out (what a host hands over): lane r of a warp
+// owns instance r of the warp's 32 and stages ITS rows through shared memory with bulk
+// copies (cp.async.bulk + mbarrier), one row segment of TF frames per stream per tile;
+// the output overwrites the row of input 0 in place and leaves with one bulk store.
+__device__ __forceinline__ uint32_t smem_u32(const void *q) { return (uint32_t)__cvta_generic_to_shared(q); }
+#define TF 64
+#define ROWS (GRAPH_NIN + (GRAPH_HAS_CHANGED ? 1 : 0))
+#define ROWB (TF * 4 + 16)
+#define STAGEB (32 * ROWS * ROWB)
+#define STAGES 3
+#define WARPS 2
+extern "C" __global__ void __launch_bounds__(WARPS * 32) graph_planar(const GraphParams p) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t g0 = ((uint64_t)blockIdx.x * WARPS + warp) * 32;
+    if (g0 >= p.n) return;
+    const uint32_t rows = p.n - g0 < 32 ? (uint32_t)(p.n - g0) : 32u;
+    const bool mine = lane < rows;
+    const uint64_t i = g0 + lane;
+    const uint32_t base = smem_u32(sm) + warp * (STAGES * STAGEB);
+    const uint32_t bar0 = smem_u32(sm) + WARPS * STAGES * STAGEB + warp * (STAGES * 8);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * s), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    GRAPH_DECL_STATE
+    if (mine) { GRAPH_LOAD_STATE(p.st, p.npad, i) }
+    const uint32_t n_tiles = (uint32_t)((p.F + TF - 1) / TF);
+    auto cols_of = [&](uint32_t k) { const uint64_t left = p.F - (uint64_t)k * TF; return left < TF ? (uint32_t)left : (uint32_t)TF; };
+    auto issue = [&](uint32_t k) {
+        const uint32_t s = k % STAGES, bytes = cols_of(k) * 4;
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * s), "r"(rows * ROWS * bytes) : "memory");
+        if (mine) {
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) {
+                const uint32_t *srow = j < GRAPH_NIN ? p.in + (i * GRAPH_NIN + j) * p.F : p.changed + i * p.F;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(base + s * STAGEB + (j * 32 + lane) * ROWB), "l"(srow + (uint64_t)k * TF), "r"(bytes), "r"(bar0 + 8 * s) : "memory");
+            }
+        }
+    };
+#pragma unroll 1
+    for (uint32_t k = 0; k < STAGES - 2 && k < n_tiles; ++k) issue(k);
+#pragma unroll 1
+    for (uint32_t k = 0; k < n_tiles; ++k) {
+        if (k + STAGES - 2 < n_tiles) {                   // that stage last held tile k-2: its bulk store must have read it out
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+            issue(k + STAGES - 2);
+        }
+        const uint32_t s = k % STAGES, cols = cols_of(k);
+        asm volatile("{\n\t.reg .pred q;\n\tW: mbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n\t@q bra D;\n\tbra W;\n\tD:\n\t}"
+                     ::"r"(bar0 + 8 * s), "r"((k / STAGES) & 1) : "memory");
+        const uint32_t row = base + s * STAGEB + lane * ROWB;      // stream j of this lane: row + j * 32 * ROWB
+        if (mine) {
+            for (uint32_t c = 0; c < cols / 4; ++c) {
+                uint32_t x[4][GRAPH_NIN], g[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, o[4];
+#pragma unroll
+                for (int j = 0; j < GRAPH_NIN; ++j)
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x[0][j]), "=r"(x[1][j]), "=r"(x[2][j]), "=r"(x[3][j]) : "r"(row + j * (32 * ROWB) + 16 * c));
+                if (GRAPH_HAS_CHANGED)
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(g[0]), "=r"(g[1]), "=r"(g[2]), "=r"(g[3]) : "r"(row + GRAPH_NIN * (32 * ROWB) + 16 * c));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) TICK(x[q], g[q], o[q]);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(row + 16 * c), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out + i * p.F + (uint64_t)k * TF), "r"(row), "r"(cols * 4) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (mine) { GRAPH_STORE_STATE(p.st, p.npad, i) }
+}
+
+// planar streams of any length / alignment: one thread per instance, scalar accesses
+extern "C" __global__ void __launch_bounds__(128) graph_planar_simple(const GraphParams p) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    GRAPH_DECL_STATE
+    GRAPH_LOAD_STATE(p.st, p.npad, i)
+    for (uint64_t t = 0; t < p.F; ++t) {
+        uint32_t x[GRAPH_NIN], g, o;
+#pragma unroll
+        for (int j = 0; j < GRAPH_NIN; ++j) x[j] = p.in[(i * GRAPH_NIN + j) * p.F + t];
+        g = GRAPH_HAS_CHANGED ? p.changed[i * p.F + t] : 0xFFFFFFFFu;
+        TICK(x, g, o);
+        p.out[i * p.F + t] = o;
+    }
+    GRAPH_STORE_STATE(p.st, p.npad, i)
+}
+
+extern "C" __global__ void graph_planar_smem(uint32_t *out) { out[0] = WARPS * STAGES * STAGEB + WARPS * STAGES * 8; out[1] = WARPS * 32; }
+)SRC";
+
+}  // namespace
+
+// Source for one graph: state words s0..s{W-1} in node order (acc {out}; edge {out, last}).
+std::string cproc_graph_jit_source(const std::vector<cproc_cuda_node> &nodes, uint32_t n_inputs, uint32_t out_node, bool has_changed) {
+    std::vector<uint32_t> off(nodes.size());
+    uint32_t words = 0;
+    for (size_t k = 0; k < nodes.size(); ++k) { off[k] = words; words += nodes[k].type == CPROC_CUDA_NODE_EDGE ? 2u : 1u; }
+    char buf[256];
+    std::string decl = "#define GRAPH_DECL_STATE uint32_t", load = "#define GRAPH_LOAD_STATE(st, npad, i)", store = "#define GRAPH_STORE_STATE(st, npad, i)";
+    for (uint32_t w = 0; w < words; ++w) {
+        snprintf(buf, sizeof(buf), "%s s%u = 0", w ? "," : "", w); decl += buf;
+        snprintf(buf, sizeof(buf), " s%u = (st)[%uull * (npad) + (i)];", w, w); load += buf;
+        snprintf(buf, sizeof(buf), " (st)[%uull * (npad) + (i)] = s%u;", w, w); store += buf;
+    }
+    decl += ";\n"; load += "\n"; store += "\n";
+    std::string tick = "#define GRAPH_TICK(x, g)";
+    for (size_t k = 0; k < nodes.size(); ++k) {
+        const cproc_cuda_node &nd = nodes[k];
+        std::string in;
+        if (nd.src >= 0) { snprintf(buf, sizeof(buf), "s%u", off[nd.src]); in = buf; }
+        else { snprintf(buf, sizeof(buf), "(x)[%d]", -(nd.src + 1)); in = buf; }
+        std::string cond;
+        if (nd.cond_mask == 0xFFFFFFFFu && !has_changed) cond = "";
+        else { snprintf(buf, sizeof(buf), "if ((g) & 0x%xu) ", nd.cond_mask); cond = buf; }
+        if (nd.type == CPROC_CUDA_NODE_EDGE) snprintf(buf, sizeof(buf), " %s{ const uint32_t v = %s; s%u = (v != s%u); s%u = v; }", cond.c_str(), in.c_str(), off[k], off[k] + 1, off[k] + 1);   // cproc.h:151-154
+        else snprintf(buf, sizeof(buf), " %s{ s%u += %s; }", cond.c_str(), off[k], in.c_str());                                                                                                     // cproc.h:140-142
+        tick += buf;
+    }
+    tick += "\n";
+    snprintf(buf, sizeof(buf), "#define GRAPH_OUT s%u\n#define GRAPH_NIN %u\n#define GRAPH_HAS_CHANGED %d\n", off[out_node], n_inputs, has_changed ? 1 : 0);
+    return decl + load + store + tick + buf + k_jit_tail;
+}
+
+// Compile (once per batch and `changed` presence) and return the two kernels.
+int cproc_graph_jit_get(cproc_cuda_batch *b, bool has_changed, cproc_graph_jit **out) {
+    cproc_cuda_ctx *ctx = b->ctx;
+    cproc_graph_jit &j = b->jit[has_changed ? 1 : 0];
+    if (j.state == 2) return -1;                           // failed before: stay on the table kernel
+    if (j.state == 0) {
+        j.state = 2;
+        if (!nvrtc_load()) { b->jit_log = "libnvrtc not found"; return -1; }
+        const std::string src = cproc_graph_jit_source(b->nodes, b->cfg.n_inputs, b->cfg.out_node, has_changed);
+        void *prog = nullptr;
+        if (g_nvrtc.create(&prog, src.c_str(), "cproc_graph.cu", 0, nullptr, nullptr)) { b->jit_log = "nvrtcCreateProgram failed"; return -1; }
+        const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+        const int rc = g_nvrtc.compile(prog, 4, opts);
+        size_t ls = 0;
+        g_nvrtc.log_size(prog, &ls);
+        if (ls > 1) { b->jit_log.resize(ls); g_nvrtc.log(prog, &b->jit_log[0]); }
+        if (rc) { g_nvrtc.destroy(&prog); return -1; }
+        size_t cs = 0;
+        g_nvrtc.cubin_size(prog, &cs);
+        j.cubin.resize(cs);
+        g_nvrtc.cubin(prog, j.cubin.data());
+        g_nvrtc.destroy(&prog);
+        if (cudaLibraryLoadData(&j.lib, j.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) { cudaGetLastError(); b->jit_log = "cudaLibraryLoadData failed"; return -1; }
+        cudaKernel_t kq = nullptr;
+        if (cudaLibraryGetKernel(&j.k_il, j.lib, "graph_interleaved") != cudaSuccess || cudaLibraryGetKernel(&j.k_pl, j.lib, "graph_planar") != cudaSuccess ||
+            cudaLibraryGetKernel(&j.k_ps, j.lib, "graph_planar_simple") != cudaSuccess ||
+            cudaLibraryGetKernel(&kq, j.lib, "graph_planar_smem") != cudaSuccess) { cudaGetLastError(); b->jit_log = "cudaLibraryGetKernel failed"; return -1; }
+        // shared-memory size and block size of the planar kernel are defined by the generated source: ask it
+        uint32_t *d = nullptr, h[2] = {0, 0};
+        if (cudaMalloc(&d, 8) != cudaSuccess) { cudaGetLastError(); return -1; }
+        void *args[] = {&d};
+        cudaError_t e = cudaLaunchKernel((const void *)kq, dim3(1), dim3(1), args, 0, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d);
+        if (e != cudaSuccess) { cudaGetLastError(); b->jit_log = "graph_planar_smem query failed"; return -1; }
+        j.pl_smem = h[0]; j.pl_block = h[1];
+        if (j.pl_smem > 227 * 1024) { b->jit_log = "planar staging does not fit shared memory (too many input streams)"; j.k_pl = nullptr; }
+        else if (cudaFuncSetAttribute((const void *)j.k_pl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)j.pl_smem) != cudaSuccess) { cudaGetLastError(); j.k_pl = nullptr; }
+        j.state = 1;
+    }
+    *out = &j;
+    return 0;
+}
+
+extern "C" const char *cproc_cuda_graph_jit_log(const cproc_cuda_batch *b) { return b ? b->jit_log.c_str() : ""; }
+extern "C" int cproc_cuda_graph_jit_source(const cproc_cuda_node *nodes, uint32_t n_nodes, uint32_t n_inputs, uint32_t out_node,
+                                           int has_changed, char *dst, size_t cap) {
+    if (!nodes || n_nodes == 0 || n_nodes > CPROC_CUDA_GRAPH_MAX_NODES || out_node >= n_nodes || n_inputs == 0)
+        return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_jit_source: bad node table");
+    for (uint32_t k = 0; k < n_nodes; ++k)
+        if (nodes[k].type > CPROC_CUDA_NODE_EDGE || nodes[k].src >= (int32_t)k || (nodes[k].src < 0 && (uint32_t)(-(nodes[k].src + 1)) >= n_inputs))
+            return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_jit_source: node %u invalid", k);
+    const std::string s = cproc_graph_jit_source(std::vector<cproc_cuda_node>(nodes, nodes + n_nodes), n_inputs, out_node, has_changed != 0);
+    if (dst && cap) { const size_t n = s.size() < cap - 1 ? s.size() : cap - 1; memcpy(dst, s.data(), n); dst[n] = 0; }
+    return (int)s.size();
+}

@@ -103,6 +103,20 @@ int launch_graph(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     p.in = (const uint32_t *)io->in; p.changed = (const uint32_t *)io->in2; p.out = (uint32_t *)io->out;
     p.F = F; p.layout = io->layout;
     const unsigned grid = (unsigned)ceil_div_u64(p.n, 128);
+    // the kernel generated for this graph (graph_front.cu)
+    cproc_graph_jit *j = nullptr;
+    if (ctx->graph_jit && cproc_graph_jit_get(b, p.changed != nullptr, &j) == 0) {
+        void *args[] = {&p};
+        cudaError_t e;
+        const bool aligned = F % 4 == 0 && ((uintptr_t)p.in & 15) == 0 && ((uintptr_t)p.out & 15) == 0 && (!p.changed || ((uintptr_t)p.changed & 15) == 0);
+        if (io->layout == CPROC_CUDA_INTERLEAVED) e = cudaLaunchKernel((const void *)j->k_il, dim3(grid), dim3(128), args, 0, ctx->stream);
+        else if (j->k_pl && aligned) e = cudaLaunchKernel((const void *)j->k_pl, dim3((unsigned)ceil_div_u64(p.n, j->pl_block)), dim3(j->pl_block), args, j->pl_smem, ctx->stream);
+        else e = cudaLaunchKernel((const void *)j->k_ps, dim3(grid), dim3(128), args, 0, ctx->stream);
+        ctx->launches++;
+        return cproc_check(ctx, e, "graph (jit)");
+    }
+    if (b->nodes.size() > GRAPH_MAX_NODES || b->state_words > GRAPH_MAX_STATE)
+        return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "graph: %zu nodes need the NVRTC path, which is unavailable (%s)", b->nodes.size(), b->jit_log.c_str());
     // recognise edge -> acc [-> acc] chains under a single mask
     const std::vector<cproc_cuda_node> &nd = b->nodes;
     bool chain = nd.size() >= 2 && nd.size() <= 3 && nd[0].type == CPROC_CUDA_NODE_EDGE && nd[0].src == -1 &&

@@ -318,31 +318,98 @@ def test_pwm(st, ctx, oracle):
 
 
 # ------------------------------------------------------------------------- graphs
-@pytest.mark.parametrize("rows", [po.GRAPH_TEST_CPROC, po.GRAPH_BP5,
-                                  [(po.NODE_ACC, -1, 1), (po.NODE_ACC, -2, 2), (po.NODE_EDGE, 1, 4), (po.NODE_ACC, 2, 3)],
-                                  [(po.NODE_ACC, -1, 0xFFFFFFFF)]])
-@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
-@pytest.mark.parametrize("masked", [False, True])
-def test_graph(st, ctx, oracle, rows, layout, masked):
-    N, F = 150, 64
+def _graph_case(st, ctx, oracle, rows, layout, masked, N=150, F=64, out_node=None, jit=1):
     n_in = max(1, max(-s for _, s, _ in rows))
+    out_node = len(rows) - 1 if out_node is None else out_node
     inp = rng.integers(0, 2, (N, n_in, F), dtype=np.uint32)
     inp[::7] = rng.integers(0, 2**32, inp[::7].shape, dtype=np.uint32)
     changed = rng.integers(0, 8, (N, F), dtype=np.uint32) if masked else None
     sw = sum(2 if t == po.NODE_EDGE else 1 for t, _, _ in rows)
     s0 = rng.integers(0, 2**32, (N, sw), dtype=np.uint32)
     sa = s0.copy()
-    want = oracle.graph_run(rows, n_in, len(rows) - 1, sa, N, F, inp, changed)
-    b = ctx.batch(st.GRAPH, N, nodes=rows, n_inputs=n_in, layout=getattr(st, layout))
-    assert b.state_bytes == 4 * sw
-    b.upload_state(s0)
-    il = layout == "INTERLEAVED"
-    out = np.zeros((F, N) if il else (N, F), np.uint32)
-    b.run(F, inp=np.ascontiguousarray(inp.transpose(2, 1, 0)) if il else inp,
-          in2=None if changed is None else (np.ascontiguousarray(changed.T) if il else changed), out=out)
-    assert np.array_equal(out.T if il else out, want)
-    assert np.array_equal(b.download_state(), sa)
-    b.free()
+    want = oracle.graph_run(rows, n_in, out_node, sa, N, F, inp, changed)
+    ctx.set_option("graph_jit", jit)
+    try:
+        b = ctx.batch(st.GRAPH, N, nodes=rows, n_inputs=n_in, out_node=out_node, layout=getattr(st, layout))
+        assert b.state_bytes == 4 * sw
+        b.upload_state(s0)
+        il = layout == "INTERLEAVED"
+        out = np.zeros((F, N) if il else (N, F), np.uint32)
+        b.run(F, inp=np.ascontiguousarray(inp.transpose(2, 1, 0)) if il else inp,
+              in2=None if changed is None else (np.ascontiguousarray(changed.T) if il else changed), out=out)
+        if jit:
+            assert "not found" not in b.jit_log and "failed" not in b.jit_log, b.jit_log    # the generated kernel ran
+        assert np.array_equal(out.T if il else out, want)
+        assert np.array_equal(b.download_state(), sa)
+        # a second block continues from the device state
+        inp2 = rng.integers(0, 3, (N, n_in, F), dtype=np.uint32)
+        want2 = oracle.graph_run(rows, n_in, out_node, sa, N, F, inp2, changed)
+        b.run(F, inp=np.ascontiguousarray(inp2.transpose(2, 1, 0)) if il else inp2,
+              in2=None if changed is None else (np.ascontiguousarray(changed.T) if il else changed), out=out)
+        assert np.array_equal(out.T if il else out, want2)
+        assert np.array_equal(b.download_state(), sa)
+        b.free()
+    finally:
+        ctx.set_option("graph_jit", 1)
+
+
+@pytest.mark.parametrize("rows", [po.GRAPH_TEST_CPROC, po.GRAPH_BP5,
+                                  [(po.NODE_ACC, -1, 1), (po.NODE_ACC, -2, 2), (po.NODE_EDGE, 1, 4), (po.NODE_ACC, 2, 3)],
+                                  [(po.NODE_ACC, -1, 0xFFFFFFFF)]])
+@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
+@pytest.mark.parametrize("masked", [False, True])
+@pytest.mark.parametrize("jit", [0, 1])
+def test_graph(st, ctx, oracle, rows, layout, masked, jit):
+    _graph_case(st, ctx, oracle, rows, layout, masked, jit=jit)
+
+
+def _random_graph(n_nodes, n_in, seed):
+    r = np.random.default_rng(seed)
+    rows = []
+    for k in range(n_nodes):
+        src = int(r.integers(-n_in, k)) if k else -int(r.integers(1, n_in + 1))
+        rows.append((int(r.integers(0, 2)), src, int(r.choice([1, 2, 3, 4, 6, 0xFFFFFFFF]))))
+    return rows
+
+
+@pytest.mark.parametrize("n_nodes,n_in,N,F", [(16, 2, 300, 256), (40, 3, 97, 100), (64, 1, 70, 33), (7, 4, 1000, 192), (3, 1, 5000, 1024)])
+@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
+@pytest.mark.parametrize("masked", [False, True])
+def test_graph_generated_kernels(st, ctx, oracle, n_nodes, n_in, N, F, layout, masked):
+    """NVRTC-generated kernels for random ANF graphs up to the 64-node limit: several input
+    streams, every mask, an inner node as the output, frame counts that are not multiples of
+    the staging tile (and F = 33: the unaligned planar path)."""
+    rows = _random_graph(n_nodes, n_in, seed=n_nodes * 131 + n_in)
+    _graph_case(st, ctx, oracle, rows, layout, masked, N=N, F=F, out_node=n_nodes // 2)
+
+
+def test_graph_from_generated_text(st, ctx, oracle):
+    """The wire format end to end: the generated C text of the reference's two graphs
+    (linux/test_cproc.c:11-17, stm32f103/bp5_plugin.c:1-9) -> parser -> batch -> render."""
+    for text, want_rows in ((GEN_TEST_CPROC, po.GRAPH_TEST_CPROC), (GEN_BP5, po.GRAPH_BP5)):
+        rows, n_in, out_node, _ = st.abi.graph_parse(text)
+        assert rows == want_rows
+        _graph_case(st, ctx, oracle, rows, "PLANAR", True, N=200, F=128, out_node=out_node)
+
+
+# the statements epid_cproc.erl generated for the reference's two shipped graphs
+GEN_TEST_CPROC = """
+#define CPROC_NB_INPUTS 1
+void cproc_update(w *input, w g) {
+    PROC_COND(g&0b1, n1, edge, NULL, NULL, .in = input[0]);
+    PROC_COND(g&0b1, n2, acc,  NULL, NULL, .in = n1.out);
+    cproc_output(2, n2.out);
+}
+"""
+GEN_BP5 = """
+#define CPROC_NB_INPUTS 1
+void cproc_update(w *input, w g) {
+    PROC_COND(g&0b1, n1, edge, NULL, NULL, .in = input[0]);
+    PROC_COND(g&0b1, n2, acc, NULL, NULL, .in = n1.out);
+    PROC_COND(g&0b1, n3, acc, NULL, NULL, .in = n2.out);
+    cproc_output(3, n3.out);
+}
+"""
 
 
 def test_graph_test_cproc_anchor(st, ctx):

@@ -83,3 +83,14 @@ elif which == "voice":
     d_out = ctx.dev_alloc(4 * F); d_mix = ctx.dev_alloc(4 * F)
     ms = timed(lambda: b.run_dev(F, out=d_out, mix=d_mix))
     print("voice: %.3f ms  %.1f G voice-samples/s" % (ms, N * F / ms / 1e6))
+elif which in ("graph", "graph_il"):
+    # the reference's bp5 graph (edge -> acc -> acc), 4 Mi instances x 256 ticks: 4 B in + 4 B out per tick
+    N, F = 4 * 1024 * 1024, 256
+    rows = [(st.NODE_EDGE, -1, 1), (st.NODE_ACC, 0, 1), (st.NODE_ACC, 1, 1)]
+    d_in = ctx.dev_alloc(4 * N * F); d_out = ctx.dev_alloc(4 * N * F)
+    chunk = rng.integers(0, 2, (65536, F), dtype=np.uint32)
+    for k in range(N // 65536):
+        ctx.h2d(d_in + k * chunk.nbytes, chunk)
+    b = ctx.batch(st.GRAPH, N, nodes=rows, layout=st.INTERLEAVED if which == "graph_il" else st.PLANAR)
+    ms = timed(lambda: b.run_dev(F, inp=d_in, out=d_out))
+    print("%s: %.3f ms  %.0f GB/s  %.1f G ticks/s  [%s]" % (which, ms, 8 * N * F / ms / 1e6, N * F / ms / 1e6, b.jit_log.strip()))
