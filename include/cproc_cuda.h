@@ -62,7 +62,7 @@ typedef struct cproc_cuda_batch cproc_cuda_batch;  /* N instances of a proc */
 enum cproc_cuda_proc {
     /* Generated cproc graph of acc/edge nodes == cproc_update(w *input, w
      * changed).  state record: node states concatenated in ANF order
-     * (acc_state {w out}, edge_state {w out; w last}; cproc.h:134,145).
+     * (acc_state {w out}, edge_state {w out; w last}; cproc.h:134,145; glide: 5 words).
      * in:  uint32 [inst][n_inputs][F]; in2: changed mask uint32 [inst][F] or
      * NULL (= -1, mod_cproc_plugin.c:32); out: uint32 [inst][F], the value
      * passed to cproc_output() each tick (test_cproc.c:16). */
@@ -121,7 +121,16 @@ enum cproc_cuda_proc {
     CPROC_CUDA_ONEPOLE = 10
 };
 
-enum { CPROC_CUDA_NODE_ACC = 0, CPROC_CUDA_NODE_EDGE = 1 };
+/* Node kinds (bits 0..7 of cproc_cuda_node.type; bits 8..15 carry the node's config word).
+ * GLIDE is the firmware's control-rate -> audio-rate parameter interpolation
+ * (struct line[2] of mod_pdm_pwm.c:80-93, pdm_update_line of mod_controlrate.c:28-40,
+ * the "representative example" of doc/combinators.org:28-34) as a processor: .in is
+ * read once per 2^L ticks, .out is the interpolated line; state record {out, vel0,
+ * pos1, vel1, count}; L = CPROC_CUDA_NODE_ARG(type) = CONTROL_DIV_LOG. */
+enum { CPROC_CUDA_NODE_ACC = 0, CPROC_CUDA_NODE_EDGE = 1, CPROC_CUDA_NODE_GLIDE = 2 };
+#define CPROC_CUDA_NODE_KIND(t) ((t) & 0xFFu)
+#define CPROC_CUDA_NODE_ARG(t)  (((t) >> 8) & 0xFFu)
+#define CPROC_CUDA_NODE_GLIDE_L(L) (CPROC_CUDA_NODE_GLIDE | ((uint32_t)(L) << 8))
 #define CPROC_CUDA_GRAPH_MAX_NODES 64
 enum { CPROC_CUDA_MIX_SAW = 0, CPROC_CUDA_MIX_SQUARE = 1 };
 enum { CPROC_CUDA_XVOICE_SEQ = 0, CPROC_CUDA_XVOICE_SCAN = 1 };
@@ -164,6 +173,7 @@ typedef struct {
  * epid_cproc.erl emits and the reference compiles as C (linux/test_cproc.c:11-17,
  * stm32f103/bp5_plugin.c:1-9): `#define CPROC_NB_INPUTS n`, a sequence of
  *   PROC_COND(<changed> & <mask>, <inst>, acc|edge, NULL, NULL, .in = input[k] | <inst>.out);
+ *   PROC_COND(<changed> & <mask>, <inst>, glide, &(glide_config){.div_log = L}, NULL, .in = ...);
  * (or PROC(<inst>, ...), cproc.h:81) and one `cproc_output(<index>, <inst>.out);`.
  * Fills `nodes` (at most max_nodes rows) and `info`; the rows go into
  * cproc_cuda_config.nodes / n_nodes / n_inputs / out_node unchanged.  Needs no device. */

@@ -19,9 +19,21 @@ void orc_edge_update(orc_edge_state *s, orc_w in) {
     s->last = in;
 }
 
+/* mod_pdm_pwm.c:129-143 + mod_controlrate.c:28-40 on one parameter (see cproc_oracle.h) */
+void orc_glide_update(orc_glide_state *s, orc_w in, uint32_t div_log) {
+    if (s->count == 0) {
+        s->out = s->pos1; s->vel0 = s->vel1;                      /* PDM_COPY_LINE */
+        s->pos1 += s->vel1 << div_log;                            /* pdm_update_line */
+        int32_t span = (int32_t)(in - s->pos1);
+        s->vel1 = (uint32_t)(span >> div_log);
+    }
+    s->out += s->vel0;                                            /* pdm_update_glide */
+    s->count = (s->count + 1) & ((1u << div_log) - 1u);
+}
+
 uint32_t orc_node_state_words(uint32_t type) {
-    /* sizeof(acc_state)=4, sizeof(edge_state)=8 (cproc.h:134,145) */
-    return type == ORC_NODE_EDGE ? 2u : 1u;
+    /* sizeof(acc_state)=4, sizeof(edge_state)=8 (cproc.h:134,145); glide: 5 words */
+    switch (type & 0xFF) { case ORC_NODE_EDGE: return 2u; case ORC_NODE_GLIDE: return 5u; default: return 1u; }
 }
 uint32_t orc_graph_state_words(const orc_node *nodes, uint32_t n_nodes) {
     uint32_t w = 0;
@@ -50,8 +62,11 @@ void orc_graph_run(const orc_node *nodes, uint32_t n_nodes, uint32_t n_inputs,
                 uint32_t x = nodes[i].src >= 0
                     ? st[off[nodes[i].src]] /* .out is the first state word */
                     : in[((uint64_t)n * n_inputs + (uint32_t)(-(nodes[i].src + 1))) * F + t];
-                if (nodes[i].type == ORC_NODE_EDGE) orc_edge_update((orc_edge_state *)(st + off[i]), x);
-                else orc_acc_update((orc_acc_state *)(st + off[i]), x);
+                switch (nodes[i].type & 0xFF) {
+                case ORC_NODE_EDGE: orc_edge_update((orc_edge_state *)(st + off[i]), x); break;
+                case ORC_NODE_GLIDE: orc_glide_update((orc_glide_state *)(st + off[i]), x, (nodes[i].type >> 8) & 0xFF); break;
+                default: orc_acc_update((orc_acc_state *)(st + off[i]), x); break;
+                }
             }
             out[(uint64_t)n * F + t] = st[off[out_node]];
         }

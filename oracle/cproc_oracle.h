@@ -43,9 +43,22 @@ void orc_edge_update(orc_edge_state *s, orc_w in);      /* cproc.h:151-154 */
 
 /* A generated cproc graph (linux/test_cproc.c:12-17, stm32f103/bp5_plugin.c:4-9)
  * as a table: one row per PROC_COND statement, in ANF order. */
-enum { ORC_NODE_ACC = 0, ORC_NODE_EDGE = 1 };
+enum { ORC_NODE_ACC = 0, ORC_NODE_EDGE = 1, ORC_NODE_GLIDE = 2 };
+/* glide: the control-rate -> audio-rate parameter interpolation of the firmware
+ * (doc/combinators.org:28-34 "representative example") as a processor.  State is the
+ * two line segments of struct channel (mod_pdm_pwm.c:80-93) plus the divider count
+ * (:78); .in is the control-rate value (the setpoint), read once per 2^L ticks;
+ * .out is line[0].position.  One tick = the ISR order of mod_pdm_pwm.c:129-143:
+ *   if (count == 0) { line[0] = line[1];                      (:108-109, :133)
+ *                     line[1].position += line[1].velocity << L;     (mod_controlrate.c:32)
+ *                     line[1].velocity = (int32)(in - line[1].position) >> L; }  (:33-34)
+ *   line[0].position += line[0].velocity;                     (:97-100)
+ *   count = (count + 1) % 2^L                                 (:141)
+ * L = bits 8..15 of the node type. */
+typedef struct { orc_w out; orc_w vel0; orc_w pos1; orc_w vel1; orc_w count; } orc_glide_state;
+void orc_glide_update(orc_glide_state *s, orc_w in, uint32_t div_log);
 typedef struct {
-    uint32_t type;      /* ORC_NODE_* */
+    uint32_t type;      /* ORC_NODE_* | (argument << 8) */
     int32_t  src;       /* >=0: .in = n<src>.out ; <0: .in = input[-(src+1)] */
     uint32_t cond_mask; /* executed iff (changed & cond_mask) != 0 */
 } orc_node;

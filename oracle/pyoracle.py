@@ -20,7 +20,17 @@ u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 VP = C.c_void_p
 
-NODE_ACC, NODE_EDGE = 0, 1
+NODE_ACC, NODE_EDGE, NODE_GLIDE = 0, 1, 2
+
+
+def node_glide(div_log):
+    """glide node type word: kind | (control divider log2 << 8)."""
+    return NODE_GLIDE | (div_log << 8)
+
+
+def node_words(t):
+    return {NODE_EDGE: 2, NODE_GLIDE: 5}.get(t & 0xFF, 1)
+
 MIX_SAW, MIX_SQUARE = 0, 1
 
 node_dtype = np.dtype([("type", np.uint32), ("src", np.int32), ("cond_mask", np.uint32)])

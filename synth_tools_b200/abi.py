@@ -14,7 +14,13 @@ LIB_PATH = os.path.join(HERE, "libcproc_cuda.so")
 
 # enum cproc_cuda_proc
 GRAPH, PDM, PDM_V1, PDM_V2, PWM, VOICE_BANK, SQUARE_GRAIN, SQUARE_GRAIN_MIX, XVOICE, ONEPOLE = range(1, 11)
-NODE_ACC, NODE_EDGE = 0, 1
+NODE_ACC, NODE_EDGE, NODE_GLIDE = 0, 1, 2
+
+
+def node_glide(div_log):
+    """CPROC_CUDA_NODE_GLIDE_L(L)"""
+    return NODE_GLIDE | (div_log << 8)
+
 MIX_SAW, MIX_SQUARE = 0, 1
 XVOICE_SEQ, XVOICE_SCAN = 0, 1
 PLANAR, INTERLEAVED, TILED = 0, 1, 2

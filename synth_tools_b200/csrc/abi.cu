@@ -129,7 +129,7 @@ static int proc_words(const cproc_cuda_config &c, const std::vector<cproc_cuda_n
     switch (c.proc) {
     case CPROC_CUDA_GRAPH: {
         uint32_t w = 0;
-        for (auto &nd : nodes) w += nd.type == CPROC_CUDA_NODE_EDGE ? 2u : 1u;
+        for (auto &nd : nodes) w += cproc_node_words(nd.type);
         *sw = w; *pw = 0; return 0;
     }
     case CPROC_CUDA_PDM: *sw = c.order; *pw = 1; return 0;
@@ -158,7 +158,10 @@ int cproc_cuda_alloc(cproc_cuda_ctx *ctx, const cproc_cuda_config *cfg, uint64_t
         nodes.assign(c.nodes, c.nodes + c.n_nodes);
         for (uint32_t k = 0; k < c.n_nodes; ++k) {
             const cproc_cuda_node &nd = nodes[k];
-            if (nd.type > CPROC_CUDA_NODE_EDGE) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: node %u has unknown type %u", k, nd.type);
+            if (CPROC_CUDA_NODE_KIND(nd.type) > CPROC_CUDA_NODE_GLIDE || (nd.type >> 16)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: node %u has unknown type %u", k, nd.type);
+            if (CPROC_CUDA_NODE_KIND(nd.type) == CPROC_CUDA_NODE_GLIDE && (CPROC_CUDA_NODE_ARG(nd.type) < 1 || CPROC_CUDA_NODE_ARG(nd.type) > 24))
+                return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: glide node %u needs a control divider log2 of 1..24", k);
+            if (CPROC_CUDA_NODE_KIND(nd.type) != CPROC_CUDA_NODE_GLIDE && CPROC_CUDA_NODE_ARG(nd.type)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: node %u: acc / edge take no config word", k);
             // ANF: a node may only read nodes bound before it (cproc.h:51-68)
             if (nd.src >= (int32_t)k) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: node %u reads node %d which is not bound yet", k, nd.src);
             if (nd.src < 0 && (uint32_t)(-(nd.src + 1)) >= c.n_inputs) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: node %u reads input %d of %u", k, -(nd.src + 1), c.n_inputs);
@@ -174,7 +177,7 @@ int cproc_cuda_alloc(cproc_cuda_ctx *ctx, const cproc_cuda_config *cfg, uint64_t
     if (c.layout > CPROC_CUDA_TILED) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: unknown layout %u", c.layout);
     uint32_t sw = 0, pw = 0;
     if (proc_words(c, nodes, &sw, &pw)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: unknown processor %u", c.proc);
-    if (sw > 2 * CPROC_CUDA_GRAPH_MAX_NODES) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph state too large (%u words)", sw);
+    if (sw > 5 * CPROC_CUDA_GRAPH_MAX_NODES) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph state too large (%u words)", sw);
 
     CK(ctx, cudaSetDevice(ctx->device));
     cproc_cuda_batch *b = new cproc_cuda_batch();
@@ -241,7 +244,7 @@ static int aos_to_dev(cproc_cuda_batch *b, uint32_t *d_rows, uint32_t words, con
     std::vector<uint32_t> soa((size_t)words * b->npad, 0u);
     const uint8_t *src = (const uint8_t *)aos;
     for (uint64_t i = 0; i < b->n; ++i) {
-        uint32_t rec[2 * CPROC_CUDA_GRAPH_MAX_NODES + 8];
+        uint32_t rec[5 * CPROC_CUDA_GRAPH_MAX_NODES + 8];
         memcpy(rec, src + i * stride, 4u * words);
         for (uint32_t w = 0; w < words; ++w) soa[(size_t)w * b->npad + i] = rec[w];
     }
@@ -276,7 +279,7 @@ int cproc_cuda_download_state(cproc_cuda_batch *b, void *aos, size_t stride) {
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     uint8_t *dst = (uint8_t *)aos;
     for (uint64_t i = 0; i < b->n; ++i) {
-        uint32_t rec[2 * CPROC_CUDA_GRAPH_MAX_NODES + 8];
+        uint32_t rec[5 * CPROC_CUDA_GRAPH_MAX_NODES + 8];
         for (uint32_t w = 0; w < words; ++w) rec[w] = soa[(size_t)w * b->npad + i];
         memcpy(dst + i * stride, rec, 4u * words);
     }

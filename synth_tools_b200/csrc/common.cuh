@@ -89,6 +89,9 @@ int cproc_check(cproc_cuda_ctx *ctx, cudaError_t e, const char *what);
 #define CK(ctx, call) do { int _rc = cproc_check((ctx), (call), #call); if (_rc) return _rc; } while (0)
 #define CK_LAUNCH(ctx, name) do { (ctx)->launches++; int _rc = cproc_check((ctx), cudaGetLastError(), name); if (_rc) return _rc; } while (0)
 
+static inline uint32_t cproc_node_words(uint32_t type) {   // acc {out}; edge {out, last}; glide {out, vel0, pos1, vel1, count}
+    switch (CPROC_CUDA_NODE_KIND(type)) { case CPROC_CUDA_NODE_EDGE: return 2u; case CPROC_CUDA_NODE_GLIDE: return 5u; default: return 1u; }
+}
 static inline uint64_t ceil_div_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
 // Element sizes / stream sizes per processor (bytes for F frames).

@@ -170,10 +170,21 @@ extern "C" int cproc_cuda_graph_parse(const char *text, cproc_cuda_node *nodes, 
         if (is_cond) { if (!parse_cond(a[0], &nd.cond_mask, &why)) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: %s", why.c_str()); }
         else nd.cond_mask = 0xFFFFFFFFu;
         const std::string inst = trim(a[base]), type = trim(a[base + 1]), cfg = trim(a[base + 2]), prm = trim(a[base + 3]);
+        bool cfg_null = cfg == "NULL" || cfg == "0";
         if (type == "acc") nd.type = CPROC_CUDA_NODE_ACC;
         else if (type == "edge") nd.type = CPROC_CUDA_NODE_EDGE;
-        else return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s' has unknown processor type '%s' (acc, edge)", inst.c_str(), type.c_str());
-        if ((cfg != "NULL" && cfg != "0") || (prm != "NULL" && prm != "0"))
+        else if (type == "glide") {
+            // const glide_config: &(glide_config){ .div_log = L }  (any spelling that names div_log = <number>)
+            const size_t f = cfg.find("div_log");
+            uint64_t L = 0;
+            bool ok = f != std::string::npos;
+            if (ok) { Cursor q{cfg.c_str() + f + 7, ""}; ok = q.lit("=") && q.number(&L) && L >= 1 && L <= 24; }
+            if (!ok) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': glide needs a config with .div_log = 1..24", inst.c_str());
+            nd.type = CPROC_CUDA_NODE_GLIDE_L(L);
+            cfg_null = true;
+        }
+        else return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s' has unknown processor type '%s' (acc, edge, glide)", inst.c_str(), type.c_str());
+        if (!cfg_null || (prm != "NULL" && prm != "0"))
             return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': %s has empty config and param records, expected NULL", inst.c_str(), type.c_str());
         for (const std::string &nm : names) if (nm == inst) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s' bound twice", inst.c_str());
         if (a.size() != base + 5) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': %s has exactly one input (.in)", inst.c_str(), type.c_str());
@@ -419,8 +430,8 @@ extern "C" __global__ void graph_planar_smem(uint32_t *out) { out[0] = WARPS * S
 std::string cproc_graph_jit_source(const std::vector<cproc_cuda_node> &nodes, uint32_t n_inputs, uint32_t out_node, bool has_changed) {
     std::vector<uint32_t> off(nodes.size());
     uint32_t words = 0;
-    for (size_t k = 0; k < nodes.size(); ++k) { off[k] = words; words += nodes[k].type == CPROC_CUDA_NODE_EDGE ? 2u : 1u; }
-    char buf[256];
+    for (size_t k = 0; k < nodes.size(); ++k) { off[k] = words; words += cproc_node_words(nodes[k].type); }
+    char buf[512];
     std::string decl = "#define GRAPH_DECL_STATE uint32_t", load = "#define GRAPH_LOAD_STATE(st, npad, i)", store = "#define GRAPH_STORE_STATE(st, npad, i)";
     for (uint32_t w = 0; w < words; ++w) {
         snprintf(buf, sizeof(buf), "%s s%u = 0", w ? "," : "", w); decl += buf;
@@ -437,7 +448,12 @@ std::string cproc_graph_jit_source(const std::vector<cproc_cuda_node> &nodes, ui
         std::string cond;
         if (nd.cond_mask == 0xFFFFFFFFu && !has_changed) cond = "";
         else { snprintf(buf, sizeof(buf), "if ((g) & 0x%xu) ", nd.cond_mask); cond = buf; }
-        if (nd.type == CPROC_CUDA_NODE_EDGE) snprintf(buf, sizeof(buf), " %s{ const uint32_t v = %s; s%u = (v != s%u); s%u = v; }", cond.c_str(), in.c_str(), off[k], off[k] + 1, off[k] + 1);   // cproc.h:151-154
+        if (CPROC_CUDA_NODE_KIND(nd.type) == CPROC_CUDA_NODE_GLIDE) {
+            const uint32_t o = off[k], L = CPROC_CUDA_NODE_ARG(nd.type);                  // mod_pdm_pwm.c:129-143, mod_controlrate.c:28-40
+            snprintf(buf, sizeof(buf), " %s{ if (s%u == 0) { s%u = s%u; s%u = s%u; s%u += s%u << %u; s%u = (uint32_t)((int32_t)(%s - s%u) >> %u); } s%u += s%u; s%u = (s%u + 1) & 0x%xu; }",
+                     cond.c_str(), o + 4, o, o + 2, o + 1, o + 3, o + 2, o + 3, L, o + 3, in.c_str(), o + 2, L, o, o + 1, o + 4, o + 4, (1u << L) - 1u);
+        }
+        else if (CPROC_CUDA_NODE_KIND(nd.type) == CPROC_CUDA_NODE_EDGE) snprintf(buf, sizeof(buf), " %s{ const uint32_t v = %s; s%u = (v != s%u); s%u = v; }", cond.c_str(), in.c_str(), off[k], off[k] + 1, off[k] + 1);   // cproc.h:151-154
         else snprintf(buf, sizeof(buf), " %s{ s%u += %s; }", cond.c_str(), off[k], in.c_str());                                                                                                     // cproc.h:140-142
         tick += buf;
     }
@@ -497,7 +513,9 @@ extern "C" int cproc_cuda_graph_jit_source(const cproc_cuda_node *nodes, uint32_
     if (!nodes || n_nodes == 0 || n_nodes > CPROC_CUDA_GRAPH_MAX_NODES || out_node >= n_nodes || n_inputs == 0)
         return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_jit_source: bad node table");
     for (uint32_t k = 0; k < n_nodes; ++k)
-        if (nodes[k].type > CPROC_CUDA_NODE_EDGE || nodes[k].src >= (int32_t)k || (nodes[k].src < 0 && (uint32_t)(-(nodes[k].src + 1)) >= n_inputs))
+        if (CPROC_CUDA_NODE_KIND(nodes[k].type) > CPROC_CUDA_NODE_GLIDE || (nodes[k].type >> 16) ||
+            (CPROC_CUDA_NODE_KIND(nodes[k].type) == CPROC_CUDA_NODE_GLIDE) != (CPROC_CUDA_NODE_ARG(nodes[k].type) != 0) || CPROC_CUDA_NODE_ARG(nodes[k].type) > 24 ||
+            nodes[k].src >= (int32_t)k || (nodes[k].src < 0 && (uint32_t)(-(nodes[k].src + 1)) >= n_inputs))
             return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_jit_source: node %u invalid", k);
     const std::string s = cproc_graph_jit_source(std::vector<cproc_cuda_node>(nodes, nodes + n_nodes), n_inputs, out_node, has_changed != 0);
     if (dst && cap) { const size_t n = s.size() < cap - 1 ? s.size() : cap - 1; memcpy(dst, s.data(), n); dst[n] = 0; }

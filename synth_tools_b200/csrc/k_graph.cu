@@ -9,7 +9,7 @@
 #include "common.cuh"
 
 #define GRAPH_MAX_NODES 16
-#define GRAPH_MAX_STATE 32
+#define GRAPH_MAX_STATE 48
 
 struct GraphParams {
     uint32_t *st;                  // SoA [state_words][npad]
@@ -24,8 +24,20 @@ struct GraphParams {
 };
 
 // acc_update (cproc.h:140-142) / edge_update (cproc.h:151-154) on register state
+// glide: mod_pdm_pwm.c:129-143 + mod_controlrate.c:28-40 on one parameter (see cproc_cuda.h)
 __device__ __forceinline__ void node_tick(uint32_t type, uint32_t *s, uint32_t x) {
-    if (type == CPROC_CUDA_NODE_EDGE) { s[0] = (x != s[1]); s[1] = x; }
+    const uint32_t kind = type & 0xFFu;
+    if (kind == CPROC_CUDA_NODE_EDGE) { s[0] = (x != s[1]); s[1] = x; }
+    else if (kind == CPROC_CUDA_NODE_GLIDE) {
+        const uint32_t L = (type >> 8) & 0xFFu;
+        if (s[4] == 0) {
+            s[0] = s[2]; s[1] = s[3];
+            s[2] += s[3] << L;
+            s[3] = (uint32_t)((int32_t)(x - s[2]) >> L);
+        }
+        s[0] += s[1];
+        s[4] = (s[4] + 1) & ((1u << L) - 1u);
+    }
     else s[0] += x;
 }
 
@@ -64,7 +76,8 @@ __global__ void k_graph_table(const GraphParams p) {
         uint32_t o = 0;
         for (uint32_t k = 0; k < p.n_nodes; ++k) {
             nodes[k] = p.nodes[k]; off[k] = o;
-            o += nodes[k].type == CPROC_CUDA_NODE_EDGE ? 2u : 1u;
+            const uint32_t kind = nodes[k].type & 0xFFu;
+            o += kind == CPROC_CUDA_NODE_EDGE ? 2u : (kind == CPROC_CUDA_NODE_GLIDE ? 5u : 1u);
         }
     }
     __syncthreads();

@@ -324,8 +324,13 @@ def _graph_case(st, ctx, oracle, rows, layout, masked, N=150, F=64, out_node=Non
     inp = rng.integers(0, 2, (N, n_in, F), dtype=np.uint32)
     inp[::7] = rng.integers(0, 2**32, inp[::7].shape, dtype=np.uint32)
     changed = rng.integers(0, 8, (N, F), dtype=np.uint32) if masked else None
-    sw = sum(2 if t == po.NODE_EDGE else 1 for t, _, _ in rows)
+    sw = sum(po.node_words(t) for t, _, _ in rows)
     s0 = rng.integers(0, 2**32, (N, sw), dtype=np.uint32)
+    o = 0
+    for t, _, _ in rows:                                   # glide: the divider count lives below 2^L
+        if t & 0xFF == po.NODE_GLIDE:
+            s0[:, o + 4] &= (1 << (t >> 8)) - 1
+        o += po.node_words(t)
     sa = s0.copy()
     want = oracle.graph_run(rows, n_in, out_node, sa, N, F, inp, changed)
     ctx.set_option("graph_jit", jit)
@@ -363,12 +368,15 @@ def test_graph(st, ctx, oracle, rows, layout, masked, jit):
     _graph_case(st, ctx, oracle, rows, layout, masked, jit=jit)
 
 
-def _random_graph(n_nodes, n_in, seed):
+def _random_graph(n_nodes, n_in, seed, glide=False):
     r = np.random.default_rng(seed)
     rows = []
     for k in range(n_nodes):
         src = int(r.integers(-n_in, k)) if k else -int(r.integers(1, n_in + 1))
-        rows.append((int(r.integers(0, 2)), src, int(r.choice([1, 2, 3, 4, 6, 0xFFFFFFFF]))))
+        t = int(r.integers(0, 3 if glide else 2))
+        if t == po.NODE_GLIDE:
+            t = po.node_glide(int(r.integers(1, 7)))
+        rows.append((t, src, int(r.choice([1, 2, 3, 4, 6, 0xFFFFFFFF]))))
     return rows
 
 
@@ -381,6 +389,42 @@ def test_graph_generated_kernels(st, ctx, oracle, n_nodes, n_in, N, F, layout, m
     the staging tile (and F = 33: the unaligned planar path)."""
     rows = _random_graph(n_nodes, n_in, seed=n_nodes * 131 + n_in)
     _graph_case(st, ctx, oracle, rows, layout, masked, N=N, F=F, out_node=n_nodes // 2)
+
+
+@pytest.mark.parametrize("n_nodes,n_in,N,F,jit", [(12, 2, 300, 256, 1), (9, 2, 100, 96, 0), (40, 3, 97, 100, 1), (5, 1, 2000, 512, 1)])
+@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
+@pytest.mark.parametrize("masked", [False, True])
+def test_graph_with_glide_nodes(st, ctx, oracle, n_nodes, n_in, N, F, jit, layout, masked):
+    """Graphs that contain glide nodes (control-rate -> audio-rate line interpolation,
+    mod_pdm_pwm.c:97-143 / mod_controlrate.c:28-40) with dividers 2..64, JIT and table kernels."""
+    rows = _random_graph(n_nodes, n_in, seed=n_nodes * 17 + n_in, glide=True)
+    assert any(t & 0xFF == po.NODE_GLIDE for t, _, _ in rows)
+    _graph_case(st, ctx, oracle, rows, layout, masked, N=N, F=F, out_node=n_nodes - 1, jit=jit)
+
+
+def test_glide_node_is_the_pdm_v2_line(st, ctx, oracle):
+    """A glide node fed with the setpoint rows reproduces line[0].position of the PDM v2
+    channels tick for tick: glide -> (raw) pdm2 by hand equals the v2 duty stream."""
+    N, F, L = 64, 1024, 6
+    sp = po.pdm_setpoints(N, F >> L)                                     # [rows][N]
+    # the v2 oracle on zero state, one bank per channel, external dither 0
+    chan = np.zeros((N, 7), np.uint32); prng = np.ones(N, np.uint32)
+    dext = np.zeros((N, F), np.uint32)
+    want_duty, _ = oracle.pdm_v2_run(chan, 2, N, 1, prng, dext, 0x3FF, 0, L, 24, sp, F)
+    # glide node over the same setpoints held for 2^L ticks each
+    inp = np.repeat(sp.T[:, None, :], 1 << L, axis=2).astype(np.uint32)  # [N][1][F]
+    inp = np.ascontiguousarray(inp)
+    b = ctx.batch(st.GRAPH, N, nodes=[(st.node_glide(L), -1, 0xFFFFFFFF)])
+    pos = np.zeros((N, F), np.uint32)
+    b.run(F, inp=inp, out=pos)
+    gl = b.download_state()
+    assert np.array_equal(gl[:, 0:4], chan[:, 1:5])                      # line[0], line[1] after F ticks
+    # pdm2_update on the glide output (CPROC_CUDA_PDM takes an input stream)
+    bp = ctx.batch(st.PDM, N, order=2, out_shift=24)
+    q = np.zeros((N, F), np.uint32)
+    bp.run(F, inp=pos, out=q)
+    assert np.array_equal(q.astype(np.uint8), want_duty)
+    b.free(); bp.free()
 
 
 def test_graph_from_generated_text(st, ctx, oracle):
