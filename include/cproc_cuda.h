@@ -252,6 +252,31 @@ const char *cproc_cuda_graph_jit_log(const cproc_cuda_batch *b);
 int  cproc_cuda_graph_jit_source(const cproc_cuda_node *nodes, uint32_t n_nodes, uint32_t n_inputs, uint32_t out_node,
                                  int has_changed, char *dst, size_t cap);
 
+/* ---- dynamic patcher ---------------------------------------- */
+/* The run-time way to build a graph: the RPC tree of stm32f103/mod_bpmodular.c
+ * (class/<c>/apply, inst/<node>/state/<k>/get|set, patch/reset, patch/tick) with the
+ * instances held as N-wide batches on the device.  Classes: 0 acc, 1 edge, 2 glide
+ * (config = div_log), 3 input (config = external stream index; the role gpin has on
+ * the microcontroller).  Field names as in the proc_meta tables (cproc.h:107-122).
+ * kind: 0 param, 1 state (PARAM / STATE, mod_bpmodular.c:126-127), 2 input, 3 config. */
+typedef struct cproc_cuda_patch cproc_cuda_patch;
+int  cproc_cuda_patch_class_count(void);
+const char *cproc_cuda_patch_class_name(uint32_t cls);
+int  cproc_cuda_patch_class_field(uint32_t cls, uint32_t kind, uint32_t k, const char **name);
+int  cproc_cuda_patch_open(cproc_cuda_ctx *ctx, uint64_t n_instances, uint32_t n_inputs, uint32_t layout, cproc_cuda_patch **patch);
+int  cproc_cuda_patch_close(cproc_cuda_patch *patch);
+int  cproc_cuda_patch_reset(cproc_cuda_patch *patch);
+int  cproc_cuda_patch_node_count(const cproc_cuda_patch *patch);
+/* Returns the new node index (>= 0) or a negative CPROC_CUDA_E* code. */
+int  cproc_cuda_patch_apply(cproc_cuda_patch *patch, uint32_t cls, const uint32_t *in_nodes, uint32_t n_in, uint32_t config);
+int  cproc_cuda_patch_output(cproc_cuda_patch *patch, uint32_t node);
+/* F ticks of every node; io->in [inst][n_inputs][F], io->out the output node's .out.
+ * device_buffers != 0: device pointers, asynchronous (cproc_cuda_run_dev). */
+int  cproc_cuda_patch_tick(cproc_cuda_patch *patch, uint64_t n_frames, const cproc_cuda_io *io, int device_buffers);
+int  cproc_cuda_patch_get(cproc_cuda_patch *patch, uint32_t node, uint32_t kind, uint32_t field, uint64_t instance, uint32_t *value);
+int  cproc_cuda_patch_set(cproc_cuda_patch *patch, uint32_t node, uint32_t kind, uint32_t field, uint64_t instance, uint32_t value);
+cproc_cuda_batch *cproc_cuda_patch_batch(cproc_cuda_patch *patch);
+
 /* Integer mix bus -> float, after a multi-GPU all-reduce of the raw mix:
  * VOICE_BANK saw: (float)(int)x * 2^-32 (synth.c:180); square: (float)(unsigned)x
  * * 2^-32 (:194); SQUARE_GRAIN_MIX: (float)x * 2^-7.  Device pointers. */

@@ -84,6 +84,19 @@ SYMBOLS = {
     "cproc_cuda_timer_start": (C.c_int, [C.c_void_p]),
     "cproc_cuda_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "cproc_cuda_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "cproc_cuda_patch_class_count": (C.c_int, []),
+    "cproc_cuda_patch_class_name": (C.c_char_p, [C.c_uint32]),
+    "cproc_cuda_patch_class_field": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p)]),
+    "cproc_cuda_patch_open": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "cproc_cuda_patch_close": (C.c_int, [C.c_void_p]),
+    "cproc_cuda_patch_reset": (C.c_int, [C.c_void_p]),
+    "cproc_cuda_patch_node_count": (C.c_int, [C.c_void_p]),
+    "cproc_cuda_patch_apply": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32]),
+    "cproc_cuda_patch_output": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "cproc_cuda_patch_tick": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(IO), C.c_int]),
+    "cproc_cuda_patch_get": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32)]),
+    "cproc_cuda_patch_set": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32]),
+    "cproc_cuda_patch_batch": (C.c_void_p, [C.c_void_p]),
     "cproc_cuda_graph_parse": (C.c_int, [C.c_char_p, C.POINTER(Node), C.c_uint32, C.POINTER(GraphInfo)]),
     "cproc_cuda_graph_jit_log": (C.c_char_p, [C.c_void_p]),
     "cproc_cuda_graph_jit_source": (C.c_int, [C.POINTER(Node), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_char_p, C.c_size_t]),
@@ -132,6 +145,23 @@ def graph_jit_source(rows, n_inputs, out_node, has_changed=False):
     buf = C.create_string_buffer(n + 1)
     lib.cproc_cuda_graph_jit_source(arr, len(rows), n_inputs, out_node, int(has_changed), buf, n + 1)
     return buf.value.decode()
+
+
+def patch_classes():
+    """The class map of the patcher: [{name, state: [...], input: [...], param: [...], config: [...]}]."""
+    out = []
+    for c in range(lib.cproc_cuda_patch_class_count()):
+        d = {"name": lib.cproc_cuda_patch_class_name(c).decode()}
+        for kind, key in ((0, "param"), (1, "state"), (2, "input"), (3, "config")):
+            n = lib.cproc_cuda_patch_class_field(c, kind, 0, None)
+            names = []
+            for k in range(n):
+                s = C.c_char_p()
+                lib.cproc_cuda_patch_class_field(c, kind, k, C.byref(s))
+                names.append(s.value.decode())
+            d[key] = names
+        out.append(d)
+    return out
 
 
 def _vp(a):
@@ -299,3 +329,53 @@ class Batch:
 
     def mix_to_float(self, imix_dev, out_dev, count):
         self.ctx._ck(lib.cproc_cuda_mix_to_float(self.h, imix_dev, out_dev, count))
+
+
+class Patch:
+    """cproc_cuda_patch: the dynamic patcher (mod_bpmodular.c RPC tree) on device state."""
+    PARAM, STATE = 0, 1
+
+    def __init__(self, ctx, n, n_inputs=1, layout=PLANAR):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._ck(lib.cproc_cuda_patch_open(ctx.h, n, n_inputs, layout, C.byref(h)))
+        self.h = h
+        self.n = n
+        self.layout = layout
+        self.classes = {d["name"]: i for i, d in enumerate(patch_classes())}
+
+    def close(self):
+        if self.h:
+            lib.cproc_cuda_patch_close(self.h)
+            self.h = None
+
+    def apply(self, cls, *in_nodes, config=0):
+        c = self.classes[cls] if isinstance(cls, str) else cls
+        arr = (C.c_uint32 * max(1, len(in_nodes)))(*in_nodes)
+        rc = lib.cproc_cuda_patch_apply(self.h, c, arr, len(in_nodes), config)
+        if rc < 0:
+            self.ctx._ck(rc)
+        return rc
+
+    def output(self, node):
+        self.ctx._ck(lib.cproc_cuda_patch_output(self.h, node))
+
+    def reset(self):
+        self.ctx._ck(lib.cproc_cuda_patch_reset(self.h))
+
+    def tick(self, F, inp, out, device=False):
+        io = IO()
+        io.in_, io.out, io.layout = _vp(inp), _vp(out), self.layout
+        self.ctx._ck(lib.cproc_cuda_patch_tick(self.h, F, C.byref(io), int(device)))
+
+    def get(self, node, field, instance=0, kind=1):
+        v = C.c_uint32()
+        self.ctx._ck(lib.cproc_cuda_patch_get(self.h, node, kind, field, instance, C.byref(v)))
+        return v.value
+
+    def set(self, node, field, value, instance=0, kind=1):
+        self.ctx._ck(lib.cproc_cuda_patch_set(self.h, node, kind, field, instance, value))
+
+    @property
+    def node_count(self):
+        return lib.cproc_cuda_patch_node_count(self.h)

@@ -1,0 +1,216 @@
+// patch.cu -- the dynamic patcher boundary on device state.
+//
+// The reference's second way to build a graph is at run time, over the TAG_U32 RPC tree
+// of stm32f103/mod_bpmodular.c:
+//     class/<c>/apply(in...)            -> allocate an instance of processor class c whose
+//                                          inputs read the .out of existing nodes (:85-117,
+//                                          :261-276); the reply is the node index
+//     inst/<node>/state|param/<k>/get|set  (:152-189)
+//     patch/reset, patch/tick           (:245-256)
+// with the field names coming from the proc_meta tables (generic/cproc.h:107-122).
+// Here the node list is the ANF node table of CPROC_CUDA_GRAPH, instances are N-wide
+// batches, state lives in the SoA rows on the device, and `tick` renders F ticks with
+// the NVRTC-compiled kernel of the current table.  Nodes can only be appended
+// (balloci has no free either: "Individual node deletion is not supported", :243), so a
+// rebuilt batch keeps every existing state row.
+#include "common.cuh"
+#include <string.h>
+
+namespace {
+struct ClassMeta {
+    const char *name;
+    uint32_t n_state; const char *state[5];
+    uint32_t n_input; const char *input[1];
+    uint32_t n_param;
+    uint32_t n_config; const char *config[1];
+};
+// for_acc_state / for_edge_state (cproc.h:134-148); glide: cproc_cuda.h; input: an external
+// stream as a source node (the role gpin plays on the microcontroller, hw_cproc_stm32f103.h:8-14)
+const ClassMeta k_classes[] = {
+    {"acc",   1, {"out"},                                 1, {"in"}, 0, 0, {nullptr}},
+    {"edge",  2, {"out", "last"},                         1, {"in"}, 0, 0, {nullptr}},
+    {"glide", 5, {"out", "vel0", "pos1", "vel1", "count"}, 1, {"in"}, 0, 1, {"div_log"}},
+    {"input", 0, {nullptr},                               0, {nullptr}, 0, 1, {"index"}},
+};
+const uint32_t k_n_classes = sizeof(k_classes) / sizeof(k_classes[0]);
+enum { CLS_ACC = 0, CLS_EDGE = 1, CLS_GLIDE = 2, CLS_INPUT = 3 };
+}  // namespace
+
+struct cproc_cuda_patch {
+    cproc_cuda_ctx *ctx = nullptr;
+    uint64_t n = 0;
+    uint32_t n_inputs = 0;
+    struct PNode { uint32_t cls; int32_t table; uint32_t input; };   // table: row in `rows` (or -1 for an input node)
+    std::vector<PNode> nodes;
+    std::vector<cproc_cuda_node> rows;
+    std::vector<uint32_t> off;          // state word offset per table row
+    int32_t out_node = -1;              // patch node index
+    cproc_cuda_batch *batch = nullptr;
+    bool dirty = true;
+    uint32_t layout = CPROC_CUDA_PLANAR;
+};
+
+extern "C" {
+
+int cproc_cuda_patch_class_count(void) { return (int)k_n_classes; }
+const char *cproc_cuda_patch_class_name(uint32_t cls) { return cls < k_n_classes ? k_classes[cls].name : nullptr; }
+
+// kind: 0 param, 1 state (PARAM / STATE of mod_bpmodular.c:126-127), 2 input, 3 config.  Returns the
+// number of fields (or -1); name k through `name` when it is non-NULL.
+int cproc_cuda_patch_class_field(uint32_t cls, uint32_t kind, uint32_t k, const char **name) {
+    if (cls >= k_n_classes) return -1;
+    const ClassMeta &m = k_classes[cls];
+    uint32_t n = 0; const char *const *names = nullptr;
+    switch (kind) {
+    case 0: n = m.n_param; break;
+    case 1: n = m.n_state; names = m.state; break;
+    case 2: n = m.n_input; names = m.input; break;
+    case 3: n = m.n_config; names = m.config; break;
+    default: return -1;
+    }
+    if (name) *name = (names && k < n) ? names[k] : nullptr;
+    return (int)n;
+}
+
+int cproc_cuda_patch_open(cproc_cuda_ctx *ctx, uint64_t n_instances, uint32_t n_inputs, uint32_t layout, cproc_cuda_patch **out) {
+    if (!ctx || !out) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch_open: NULL argument");
+    *out = nullptr;
+    if (n_instances == 0 || n_inputs == 0) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch_open: n_instances / n_inputs is 0");
+    if (layout != CPROC_CUDA_PLANAR && layout != CPROC_CUDA_INTERLEAVED) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch_open: layout must be PLANAR or INTERLEAVED");
+    cproc_cuda_patch *p = new cproc_cuda_patch();
+    p->ctx = ctx; p->n = n_instances; p->n_inputs = n_inputs; p->layout = layout;
+    *out = p;
+    return 0;
+}
+
+// patch/reset (mod_bpmodular.c:245-249: balloci_clear)
+int cproc_cuda_patch_reset(cproc_cuda_patch *p) {
+    if (!p) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "patch_reset: patch is NULL");
+    if (p->batch) { cproc_cuda_free(p->batch); p->batch = nullptr; }
+    p->nodes.clear(); p->rows.clear(); p->off.clear(); p->out_node = -1; p->dirty = true;
+    return 0;
+}
+
+int cproc_cuda_patch_close(cproc_cuda_patch *p) {
+    if (!p) return 0;
+    cproc_cuda_patch_reset(p);
+    delete p;
+    return 0;
+}
+
+int cproc_cuda_patch_node_count(const cproc_cuda_patch *p) { return p ? (int)p->nodes.size() : 0; }
+
+// class/<cls>/apply: returns the new node index (>= 0) or a negative error ("bad_node" /
+// "bad_ref" / "alloc_fail" of the reference are EINVAL / EINVAL / ENOMEM here).
+int cproc_cuda_patch_apply(cproc_cuda_patch *p, uint32_t cls, const uint32_t *in_nodes, uint32_t n_in, uint32_t config) {
+    if (!p) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "patch_apply: patch is NULL");
+    cproc_cuda_ctx *ctx = p->ctx;
+    if (cls >= k_n_classes) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch_apply: bad_ref: class %u", cls);
+    const ClassMeta &m = k_classes[cls];
+    if (n_in != m.n_input) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch_apply: bad_ref: %s takes %u inputs, got %u", m.name, m.n_input, n_in);   // :263
+    if (n_in && !in_nodes) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch_apply: inputs are NULL");
+    cproc_cuda_patch::PNode pn{cls, -1, 0};
+    if (cls == CLS_INPUT) {
+        if (config >= p->n_inputs) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch_apply: bad_ref: input stream %u of %u", config, p->n_inputs);
+        pn.input = config;
+    } else {
+        if (p->rows.size() >= CPROC_CUDA_GRAPH_MAX_NODES) return cproc_set_err(ctx, CPROC_CUDA_ENOMEM, "patch_apply: alloc_fail: %d nodes", CPROC_CUDA_GRAPH_MAX_NODES);   // :94-97
+        if (in_nodes[0] >= p->nodes.size()) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch_apply: bad_node: %u", in_nodes[0]);                                    // :106-110
+        const cproc_cuda_patch::PNode &src = p->nodes[in_nodes[0]];
+        cproc_cuda_node row;
+        row.cond_mask = 0xFFFFFFFFu;                        // tick() runs every instance (:71-77)
+        row.src = src.table >= 0 ? src.table : -(int32_t)src.input - 1;
+        if (cls == CLS_GLIDE) {
+            if (config < 1 || config > 24) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch_apply: glide div_log must be 1..24");
+            row.type = CPROC_CUDA_NODE_GLIDE_L(config);
+        } else row.type = cls == CLS_EDGE ? CPROC_CUDA_NODE_EDGE : CPROC_CUDA_NODE_ACC;
+        uint32_t o = p->off.empty() ? 0 : p->off.back() + cproc_node_words(p->rows.back().type);
+        pn.table = (int32_t)p->rows.size();
+        p->rows.push_back(row); p->off.push_back(o);
+        p->dirty = true;
+    }
+    p->nodes.push_back(pn);
+    return (int)p->nodes.size() - 1;
+}
+
+// The node whose .out the tick renders into io->out (the reference's graphs end in gpout / cproc_output).
+int cproc_cuda_patch_output(cproc_cuda_patch *p, uint32_t node) {
+    if (!p) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "patch_output: patch is NULL");
+    if (node >= p->nodes.size() || p->nodes[node].table < 0) return cproc_set_err(p->ctx, CPROC_CUDA_EINVAL, "patch_output: bad_ref: node %u has no state", node);
+    if (p->out_node != (int32_t)node) { p->out_node = (int32_t)node; p->dirty = true; }
+    return 0;
+}
+
+static int patch_build(cproc_cuda_patch *p) {
+    cproc_cuda_ctx *ctx = p->ctx;
+    if (!p->dirty && p->batch) return 0;
+    if (p->rows.empty()) return cproc_set_err(ctx, CPROC_CUDA_ESTATE, "patch: no processor instance yet");
+    if (p->out_node < 0) return cproc_set_err(ctx, CPROC_CUDA_ESTATE, "patch: no output node selected (cproc_cuda_patch_output)");
+    cproc_cuda_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.proc = CPROC_CUDA_GRAPH; cfg.layout = p->layout;
+    cfg.nodes = p->rows.data(); cfg.n_nodes = (uint32_t)p->rows.size(); cfg.n_inputs = p->n_inputs;
+    cfg.out_node = (uint32_t)p->nodes[p->out_node].table;
+    cproc_cuda_batch *nb = nullptr;
+    int rc = cproc_cuda_alloc(ctx, &cfg, p->n, &nb);
+    if (rc) return rc;
+    if (p->batch) {                                          // append-only: the old rows are a prefix of the new ones
+        const size_t bytes = sizeof(uint32_t) * p->batch->state_words * p->batch->npad;
+        rc = cproc_check(ctx, cudaMemcpyAsync(nb->d_state, p->batch->d_state, bytes, cudaMemcpyDeviceToDevice, ctx->stream), "patch: carry state");
+        if (rc) { cproc_cuda_free(nb); return rc; }
+        cproc_cuda_free(p->batch);
+    }
+    p->batch = nb; p->dirty = false;
+    return 0;
+}
+
+// patch/tick, F ticks at once (mod_bpmodular.c:251-255 runs one): io->in external streams, io->out the output node
+int cproc_cuda_patch_tick(cproc_cuda_patch *p, uint64_t n_frames, const cproc_cuda_io *io, int device_buffers) {
+    if (!p || !io) return cproc_set_err(p ? p->ctx : nullptr, CPROC_CUDA_EINVAL, "patch_tick: NULL argument");
+    int rc = patch_build(p);
+    if (rc) return rc;
+    return device_buffers ? cproc_cuda_run_dev(p->batch, n_frames, io) : cproc_cuda_run(p->batch, n_frames, io);
+}
+
+static int patch_word(cproc_cuda_patch *p, uint32_t node, uint32_t kind, uint32_t field, uint64_t instance, uint32_t **dev) {
+    cproc_cuda_ctx *ctx = p->ctx;
+    if (node >= p->nodes.size()) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch: bad_ref: node %u", node);
+    const cproc_cuda_patch::PNode &pn = p->nodes[node];
+    if (kind != 1) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch: bad_ref: %s has no param fields", k_classes[pn.cls].name);   // params are not stored in the reference either (:166, :184)
+    if (field >= k_classes[pn.cls].n_state) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch: bad_ref: %s state field %u", k_classes[pn.cls].name, field);
+    if (instance >= p->n) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch: bad_ref: instance %llu", (unsigned long long)instance);
+    int rc = patch_build(p);
+    if (rc) return rc;
+    *dev = p->batch->d_state + (uint64_t)(p->off[pn.table] + field) * p->batch->npad + instance;
+    return 0;
+}
+
+// inst/<node>/state/<field>/get  (mod_bpmodular.c:152-170)
+int cproc_cuda_patch_get(cproc_cuda_patch *p, uint32_t node, uint32_t kind, uint32_t field, uint64_t instance, uint32_t *value) {
+    if (!p || !value) return cproc_set_err(p ? p->ctx : nullptr, CPROC_CUDA_EINVAL, "patch_get: NULL argument");
+    uint32_t *d = nullptr;
+    int rc = patch_word(p, node, kind, field, instance, &d);
+    if (rc) return rc;
+    CK(p->ctx, cudaMemcpyAsync(value, d, 4, cudaMemcpyDeviceToHost, p->ctx->stream));
+    CK(p->ctx, cudaStreamSynchronize(p->ctx->stream));
+    return 0;
+}
+
+// inst/<node>/state/<field>/set  (:172-189)
+int cproc_cuda_patch_set(cproc_cuda_patch *p, uint32_t node, uint32_t kind, uint32_t field, uint64_t instance, uint32_t value) {
+    if (!p) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "patch_set: patch is NULL");
+    uint32_t *d = nullptr;
+    int rc = patch_word(p, node, kind, field, instance, &d);
+    if (rc) return rc;
+    CK(p->ctx, cudaMemcpyAsync(d, &value, 4, cudaMemcpyHostToDevice, p->ctx->stream));
+    CK(p->ctx, cudaStreamSynchronize(p->ctx->stream));
+    return 0;
+}
+
+// the batch behind the patch (state checkpoint: cproc_cuda_download_state / upload_state on it)
+cproc_cuda_batch *cproc_cuda_patch_batch(cproc_cuda_patch *p) {
+    if (!p || patch_build(p)) return nullptr;
+    return p->batch;
+}
+
+}  // extern "C"
