@@ -111,7 +111,7 @@ class CprocCudaError(RuntimeError):
 
 def load(path=LIB_PATH):
     if not os.path.exists(path):
-        raise ImportError("%s is missing: build it with `python -m synth_tools_b200.build` "
+        raise ImportError("%s is missing: build it with `python synth_tools_b200/build.py` "
                           "(there is no CPU fallback)" % path)
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():

@@ -1,6 +1,6 @@
 """Build libcproc_cuda.so (sm_100a only) and the C drop-in shims, in-tree.
 
-    python -m synth_tools_b200.build [--force] [--ptxas-v]
+    python synth_tools_b200/build.py [--force] [--ptxas-v]   (run by path: importing the package dlopens the library)
 
 nvcc cross-compiles without a GPU.  The built .so files stay in the package
 directory (git-ignored) so they travel with the tree.

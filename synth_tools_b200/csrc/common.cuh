@@ -23,6 +23,7 @@ struct cproc_cuda_ctx {
     int pdm_tpb = 1;          // 1: thread-per-bank when bank_size <= 4, 0: thread-per-channel
     int pdm_stage = 1;        // 1: smem-staged full-line stores for PLANAR
     int pdm_ws = 3;           // 1: warp-specialised v2 kernel (PRNG producer warp + channel consumer warps); 2: second generation; 3: + dynamic (group, slice) schedule
+    int pdm_prng_fma = 0;     // ws3 producer: 1 = xorshift shifts as IMAD / IMAD.HI (FMA pipe) instead of SHF (ALU pipe); measured slower (1.54 vs 1.50 ms: the producer chain is latency bound)
     int pdm_ctas_per_sm = 4;  // ws3: persistent blocks per SM
     int pdm_slice_batches = 64;   // ws3: dither batches (64 ticks each) per work item
     uint32_t *d_work = nullptr;   // ws3: work counter + exit counter
@@ -40,6 +41,7 @@ struct cproc_cuda_ctx {
     int grain_bulk = 1;       // planar square_grain: 0 register-transpose kernel; 1..4 bulk-copy kernel (tile/stage shapes)
     int grain_vec4 = 1;       // interleaved square_grain: four grains per thread when n % 4 == 0
     int grain_mix2 = 2;       // 0: float kernel; 1: register-accumulator / integer-threshold kernel; 2: predicate-state kernel
+    int planar_bulk = 1;      // PLANAR pdm_raw / onepole streams through the bulk-staged template (planar_bulk.cuh)
     int graph_jit = 1;        // 1: generated graphs are compiled with NVRTC; 0: table-driven kernel
     int xvoice_block = 128;
     int xvoice_groups = 0;    // XVOICE_SCAN: variant groups pipelined over the two streams (0 = automatic)

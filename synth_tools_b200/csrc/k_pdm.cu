@@ -24,6 +24,7 @@
 // through the state arrays in L2 plus a release/acquire progress word; by
 // construction the producer is always ahead, so the wait is a safety net.
 #include "common.cuh"
+#include "planar_bulk.cuh"
 
 // ---------------------------------------------------------------------------
 // shared helpers
@@ -490,7 +491,18 @@ template <int BASE, int N, int NS> __device__ __forceinline__ void bar_arrive_sl
     else if (s == 1) bar_arrive_i<BASE + 1, N>();
     else bar_arrive_i<BASE, N>();
 }
-struct PdmV2Ws2Extra { const uint32_t *jump; uint32_t *sm_rank; uint32_t m2; };   // jump: [P-1][4][256], M^(T/P * j)
+struct PdmV2Ws2Extra { const uint32_t *jump; uint32_t *sm_rank; uint32_t m2; uint32_t k13, k15, k5; };   // jump: [P-1][4][256], M^(T/P * j); k*: 2^13, 2^15, 2^5 or 0
+
+// xorshift32 with its three shifts on the FMA pipe: x << 13 = x * 2^13 (IMAD), x >> 17 = hi32(x * 2^15)
+// (IMAD.HI), x << 5 = x * 2^5.  The multipliers arrive through kernel parameters so that ptxas cannot
+// turn them back into shifts: the producer is bound by the ALU pipe (SHF, LOP3), the FMA pipe has slack.
+__device__ __forceinline__ uint32_t xorshift32_step_fma(uint32_t x, uint32_t k13, uint32_t k15, uint32_t k5) {
+    uint32_t t;
+    asm("mad.lo.u32 %0, %1, %2, 0;" : "=r"(t) : "r"(x), "r"(k13)); x ^= t;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(t) : "r"(x), "r"(k15)); x ^= t;
+    asm("mad.lo.u32 %0, %1, %2, 0;" : "=r"(t) : "r"(x), "r"(k5)); x ^= t;
+    return x;
+}
 
 __device__ __forceinline__ uint32_t jump_apply(const uint32_t (*jt)[256], uint32_t x) {
     return jt[0][x & 255u] ^ jt[1][(x >> 8) & 255u] ^ jt[2][(x >> 16) & 255u] ^ jt[3][x >> 24];
@@ -500,6 +512,37 @@ __device__ __forceinline__ uint32_t jump_apply(const uint32_t (*jt)[256], uint32
 // ALU and FMA pipes by static instruction counts per function; inlined, the
 // LOP3-heavy PRNG pushes every add of the consumer loop onto the FMA pipe
 // (IMAD.IADD), which then limits the consumer warps.
+template <int NT, int P, int NS>
+__device__ __noinline__ void ws2_producer_fma(uint32_t (*dbuf)[WS2_T / 4][32][4], const uint32_t (*jt)[4][256], uint32_t *prng_slot,
+                                              uint32_t dmask, uint64_t batches, uint32_t lane, uint32_t k13, uint32_t k15, uint32_t k5) {
+    constexpr int QC = WS2_T / 4 / P;
+    uint32_t x[P];
+    x[0] = prng_slot ? *prng_slot : 1u;
+    uint32_t s = 0;
+    for (uint64_t bt = 0; bt < batches; ++bt) {
+#pragma unroll
+        for (int j = 1; j < P; ++j) x[j] = jump_apply(jt[j - 1], x[0]);
+        if (bt >= NS) bar_sync_slot<WS2_BAR_EMPTY, NT, NS>(s);
+#pragma unroll
+        for (int q = 0; q < QC; ++q) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                uint4 v;
+                x[j] = xorshift32_step_fma(x[j], k13, k15, k5); v.x = x[j] & dmask;      // mod_pdm_pwm.c:127
+                x[j] = xorshift32_step_fma(x[j], k13, k15, k5); v.y = x[j] & dmask;
+                x[j] = xorshift32_step_fma(x[j], k13, k15, k5); v.z = x[j] & dmask;
+                x[j] = xorshift32_step_fma(x[j], k13, k15, k5); v.w = x[j] & dmask;
+                *reinterpret_cast<uint4 *>(&dbuf[s][j * QC + q][lane][0]) = v;
+            }
+        }
+        x[0] = x[P - 1];
+        __threadfence_block();
+        bar_arrive_slot<WS2_BAR_FULL, NT, NS>(s);
+        s = (s + 1 == NS) ? 0 : s + 1;
+    }
+    if (prng_slot) *prng_slot = x[0];
+}
+
 template <int NT, int P, int NS>
 __device__ __noinline__ void ws2_producer(uint32_t (*dbuf)[WS2_T / 4][32][4], const uint32_t (*jt)[4][256], uint32_t *prng_slot,
                                           uint32_t dmask, uint64_t batches, uint32_t lane) {
@@ -690,7 +733,9 @@ __global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws3(const PdmV2Params p
         const uint64_t bank0 = (uint64_t)g * 32;
         if (warp == prod_warp) {
             const uint64_t bank = bank0 + lane;
-            ws2_producer<NT, P, NS>(dbuf, jt, bank < p.n_banks ? p.prng + bank : nullptr, p.dmask, nb, lane);
+            uint32_t *slot = bank < p.n_banks ? p.prng + bank : nullptr;
+            if (ex.k13) ws2_producer_fma<NT, P, NS>(dbuf, jt, slot, p.dmask, nb, lane, ex.k13, ex.k15, ex.k5);
+            else ws2_producer<NT, P, NS>(dbuf, jt, slot, p.dmask, nb, lane);
         } else {
             const uint64_t c = bank0 * B + cl;
             const bool live = c < p.n_banks * B;                      // inside the padded SoA rows
@@ -814,6 +859,7 @@ static int launch_v2_order(cproc_cuda_batch *b, PdmV2Params &p, bool fast, bool 
         const unsigned grid = (unsigned)C;
         PdmV2Ws2Extra ex;
         ex.m2 = 0xFFFFFFFEu;
+        ex.k13 = ctx->pdm_prng_fma ? 1u << 13 : 0u; ex.k15 = 1u << 15; ex.k5 = 1u << 5;
         const int P = ctx->pdm_chains, form = (K == 2) ? ctx->pdm_form : 0;
         int rc = jump_tables(ctx, P, &ex.jump);
         if (rc) return rc;
@@ -1143,6 +1189,38 @@ __global__ void k_pdm_raw(const PdmRawParams p) {
     for (int k = 0; k < K; ++k) p.st[k * p.npad + c] = s[k];
 }
 
+// PLANAR streams through the bulk-staged template (planar_bulk.cuh): the per-thread row walk of
+// k_pdm_raw touches 32 different lines per warp instruction.
+template <int K, int HAS_IN>
+struct PdmRawOp {
+    static constexpr int NIN = HAS_IN;
+    uint32_t *st; const uint32_t *param; const uint32_t *dither;
+    uint64_t npad; uint32_t sh;
+    uint32_t s[K], cst;
+    __device__ __forceinline__ void load(uint64_t i) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) s[k] = st[k * npad + i];
+        cst = param[i];
+    }
+    __device__ __forceinline__ void store(uint64_t i) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) st[k * npad + i] = s[k];
+    }
+    __device__ __forceinline__ uint32_t tick(uint32_t x, uint64_t t) {
+        return pdm_step<K>(s, HAS_IN ? x : cst, sh, dither ? __ldg(dither + t) : 0u);    // pdm.h:13-77
+    }
+};
+
+template <int K>
+static int launch_pdm_raw_bulk(cproc_cuda_ctx *ctx, const PdmRawParams &p) {
+    if (p.in) {
+        PdmRawOp<K, 1> op; op.st = p.st; op.param = p.param; op.dither = p.dither; op.npad = p.npad; op.sh = p.sh;
+        return pbulk::launch<64, 3>(ctx, op, p.in, p.out, p.n, p.F);
+    }
+    PdmRawOp<K, 0> op; op.st = p.st; op.param = p.param; op.dither = p.dither; op.npad = p.npad; op.sh = p.sh;
+    return pbulk::launch<64, 3>(ctx, op, p.out, p.out, p.n, p.F);
+}
+
 int launch_pdm(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     cproc_cuda_ctx *ctx = b->ctx;
     if (!io->out) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm: out is NULL");
@@ -1153,6 +1231,18 @@ int launch_pdm(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     p.in = (const uint32_t *)io->in; p.dither = (const uint32_t *)io->in2; p.out = (uint32_t *)io->out;
     p.F = F; p.sh = b->cfg.out_shift; p.layout = io->layout;
     unsigned grid = (unsigned)ceil_div_u64(p.n, 128);
+    if (ctx->planar_bulk && io->layout == CPROC_CUDA_PLANAR && pbulk::usable(F, p.in, p.out)) {
+        int rc;
+        switch (b->cfg.order) {
+        case 1: rc = launch_pdm_raw_bulk<1>(ctx, p); break;
+        case 2: rc = launch_pdm_raw_bulk<2>(ctx, p); break;
+        case 3: rc = launch_pdm_raw_bulk<3>(ctx, p); break;
+        default: rc = launch_pdm_raw_bulk<4>(ctx, p); break;
+        }
+        if (rc) return rc;
+        CK_LAUNCH(ctx, "k_pdm_raw (bulk)");
+        return 0;
+    }
     switch (b->cfg.order) {
     case 1: k_pdm_raw<1><<<grid, 128, 0, ctx->stream>>>(p); break;
     case 2: k_pdm_raw<2><<<grid, 128, 0, ctx->stream>>>(p); break;

@@ -12,6 +12,7 @@
 // reduced in a fixed order (lane tree -> warp rows -> block partials -> final
 // pass), deterministic run to run, and compared with tolerance.
 #include "common.cuh"
+#include "planar_bulk.cuh"
 
 struct XVoiceParams {
     uint32_t *st;            // SoA [5][npad]: phase, lp, bp, env, t
@@ -645,11 +646,30 @@ __global__ void k_onepole(float *y, const float *a, uint64_t n, uint64_t F, cons
     y[i] = s;
 }
 
+struct OnepoleOp {
+    static constexpr int NIN = 1;
+    float *y; const float *a;
+    float s, c;
+    __device__ __forceinline__ void load(uint64_t i) { s = y[i]; c = a[i]; }
+    __device__ __forceinline__ void store(uint64_t i) { y[i] = s; }
+    __device__ __forceinline__ uint32_t tick(uint32_t x, uint64_t) {
+        s = __fmaf_rn(c, __fsub_rn(__uint_as_float(x), s), s);
+        return __float_as_uint(s);
+    }
+};
+
 int launch_onepole(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     cproc_cuda_ctx *ctx = b->ctx;
     if (!io->in || !io->out) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "onepole: in/out is NULL");
     if (io->layout == CPROC_CUDA_TILED) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "onepole: TILED layout not supported");
     if (F == 0) return 0;
+    if (ctx->planar_bulk && io->layout == CPROC_CUDA_PLANAR && pbulk::usable(F, io->in, io->out)) {
+        OnepoleOp op; op.y = (float *)b->d_state; op.a = (const float *)b->d_param; op.s = 0.f; op.c = 0.f;
+        int rc = pbulk::launch<64, 3>(ctx, op, (const uint32_t *)io->in, (uint32_t *)io->out, b->n, F);
+        if (rc) return rc;
+        CK_LAUNCH(ctx, "k_onepole (bulk)");
+        return 0;
+    }
     k_onepole<<<(unsigned)ceil_div_u64(b->n, 128), 128, 0, ctx->stream>>>((float *)b->d_state, (const float *)b->d_param, b->n, F,
                                                                        (const float *)io->in, (float *)io->out, io->layout);
     CK_LAUNCH(ctx, "k_onepole");

@@ -15,8 +15,9 @@ spf = np.random.default_rng(0).integers(0x40000000, 0xC0000000, (rows, N), dtype
 d_sp = ctx.dev_alloc(spf.nbytes); ctx.h2d(d_sp, spf)
 host = np.zeros(N * min(F, 4096), np.uint8)
 ref_crc = None
-variants = [(2, 4, 64, 1, 2)] + [(3, c, sb, form, ch) for form, ch in ((1, 2), (2, 2), (1, 4)) for c in (4, 5, 6) for sb in (16, 64, 256)]
-for ws, ctas, sb, form, chains in variants:
+variants = [(2, 4, 64, 1, 2, 0)] + [(3, 4, sb, form, ch, fma) for fma in (0, 1) for form, ch in ((1, 2), (2, 2), (1, 4), (1, 1)) for sb in (32, 64, 128)]
+for ws, ctas, sb, form, chains, fma in variants:
+    ctx.set_option("pdm_prng_fma", fma)
     ctx.set_option("pdm_ws", ws); ctx.set_option("pdm_ctas_per_sm", ctas); ctx.set_option("pdm_slice_batches", sb)
     ctx.set_option("pdm_form", form); ctx.set_option("pdm_chains", chains)
     b = ctx.batch(st.PDM_V2, N, order=2, bank_size=3, ctl_div_log=12, layout=st.TILED)
@@ -28,6 +29,6 @@ for ws, ctas, sb, form, chains in variants:
     best = 1e9
     for _ in range(5):
         ctx.timer_start(); b.run_dev(F, ctl=d_sp, n_ctl=rows, out=d_out); best = min(best, ctx.timer_stop())
-    print("ws=%d ctas/SM=%d slice=%d batches form=%d chains=%d : %8.3f ms  %8.1f Gsamples/s  %s" %
-          (ws, ctas, sb, form, chains, best, N * F / best / 1e6, "same as ws2" if crc == ref_crc else "DIFFERS from ws2"), flush=True)
+    print("ws=%d ctas/SM=%d slice=%d batches form=%d chains=%d prng_fma=%d : %8.3f ms  %8.1f Gsamples/s  %s" %
+          (ws, ctas, sb, form, chains, fma, best, N * F / best / 1e6, "same as ws2" if crc == ref_crc else "DIFFERS from ws2"), flush=True)
     b.free()
