@@ -277,6 +277,33 @@ int  cproc_cuda_patch_get(cproc_cuda_patch *patch, uint32_t node, uint32_t kind,
 int  cproc_cuda_patch_set(cproc_cuda_patch *patch, uint32_t node, uint32_t kind, uint32_t field, uint64_t instance, uint32_t value);
 cproc_cuda_batch *cproc_cuda_patch_batch(cproc_cuda_patch *patch);
 
+/* ---- multi-GPU mix bus over NVLink peer memory ------------------- */
+/* One process per GPU.  The only exchange of the path is the shared mix bus: the
+ * integer mixes of the shards (io.mix) are summed (square: ORed) and scaled to float
+ * once (synth.c:180,194).  Instead of an NCCL all-reduce plus a conversion kernel this
+ * is ONE kernel per rank: push the local mix into every peer's bus buffer with stores
+ * through the NVLink peer mapping, publish a flag, wait for the peers' flags, add the
+ * slots in rank order, write the float bus.  Setup: every rank creates a bus, exports
+ * its handle (cproc_cuda_bus_handle_bytes() bytes), the host gathers the handles of
+ * all ranks in rank order over its own transport and passes them to _connect.  Every
+ * rank must then make the same sequence of _allreduce calls.
+ * op: 0 wrap-around sum, 1 OR.  scale: 0 none, 1 saw (float)(int)x*2^-32, 2 square
+ * (float)(unsigned)x*2^-32, 3 grain mix (float)x*2^-7 (out_dev required unless 0). */
+typedef struct cproc_cuda_bus cproc_cuda_bus;
+int  cproc_cuda_bus_create(cproc_cuda_ctx *ctx, uint64_t max_words, int world, int rank, cproc_cuda_bus **bus);
+size_t cproc_cuda_bus_handle_bytes(void);
+int  cproc_cuda_bus_handle(cproc_cuda_bus *bus, void *handle);
+int  cproc_cuda_bus_connect(cproc_cuda_bus *bus, const void *handles);
+int  cproc_cuda_bus_allreduce(cproc_cuda_bus *bus, int32_t *imix_dev, float *out_dev, uint64_t count, uint32_t op, uint32_t scale);
+/* Overlapped form: the exchange of block k runs on the bus's own high-priority stream
+ * (after everything queued on the context stream so far) while the context stream renders
+ * block k+1 into the other mix buffer.  slot 0/1 names the buffer pair; _wait(slot) makes
+ * the context stream wait for that slot's last exchange. */
+int  cproc_cuda_bus_allreduce_begin(cproc_cuda_bus *bus, uint32_t slot, int32_t *imix_dev, float *out_dev, uint64_t count, uint32_t op, uint32_t scale);
+int  cproc_cuda_bus_wait(cproc_cuda_bus *bus, uint32_t slot);
+int  cproc_cuda_bus_status(cproc_cuda_bus *bus, uint32_t *failed_epoch);
+int  cproc_cuda_bus_destroy(cproc_cuda_bus *bus);
+
 /* Integer mix bus -> float, after a multi-GPU all-reduce of the raw mix:
  * VOICE_BANK saw: (float)(int)x * 2^-32 (synth.c:180); square: (float)(unsigned)x
  * * 2^-32 (:194); SQUARE_GRAIN_MIX: (float)x * 2^-7.  Device pointers. */

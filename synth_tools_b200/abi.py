@@ -97,6 +97,15 @@ SYMBOLS = {
     "cproc_cuda_patch_get": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32)]),
     "cproc_cuda_patch_set": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32]),
     "cproc_cuda_patch_batch": (C.c_void_p, [C.c_void_p]),
+    "cproc_cuda_bus_create": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "cproc_cuda_bus_handle_bytes": (C.c_size_t, []),
+    "cproc_cuda_bus_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cproc_cuda_bus_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cproc_cuda_bus_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]),
+    "cproc_cuda_bus_allreduce_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]),
+    "cproc_cuda_bus_wait": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "cproc_cuda_bus_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    "cproc_cuda_bus_destroy": (C.c_int, [C.c_void_p]),
     "cproc_cuda_graph_parse": (C.c_int, [C.c_char_p, C.POINTER(Node), C.c_uint32, C.POINTER(GraphInfo)]),
     "cproc_cuda_graph_jit_log": (C.c_char_p, [C.c_void_p]),
     "cproc_cuda_graph_jit_source": (C.c_int, [C.POINTER(Node), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_char_p, C.c_size_t]),
@@ -379,3 +388,45 @@ class Patch:
     @property
     def node_count(self):
         return lib.cproc_cuda_patch_node_count(self.h)
+
+
+class Bus:
+    """cproc_cuda_bus: the shared mix bus of the ranks of one box over NVLink peer memory."""
+    SUM, OR = 0, 1
+    SCALE_NONE, SCALE_SAW, SCALE_SQUARE, SCALE_GRAIN = 0, 1, 2, 3
+
+    def __init__(self, ctx, max_words, world, rank):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._ck(lib.cproc_cuda_bus_create(ctx.h, max_words, world, rank, C.byref(h)))
+        self.h = h
+        self.world, self.rank = world, rank
+
+    def handle(self):
+        buf = np.zeros(lib.cproc_cuda_bus_handle_bytes(), np.uint8)
+        self.ctx._ck(lib.cproc_cuda_bus_handle(self.h, _vp(buf)))
+        return buf
+
+    def connect(self, handles):
+        handles = np.ascontiguousarray(handles, np.uint8)
+        assert handles.size == self.world * lib.cproc_cuda_bus_handle_bytes()
+        self.ctx._ck(lib.cproc_cuda_bus_connect(self.h, _vp(handles)))
+
+    def allreduce(self, imix_dev, count, out_dev=None, op=0, scale=0):
+        self.ctx._ck(lib.cproc_cuda_bus_allreduce(self.h, imix_dev, out_dev, count, op, scale))
+
+    def begin(self, slot, imix_dev, count, out_dev=None, op=0, scale=0):
+        self.ctx._ck(lib.cproc_cuda_bus_allreduce_begin(self.h, slot, imix_dev, out_dev, count, op, scale))
+
+    def wait(self, slot):
+        self.ctx._ck(lib.cproc_cuda_bus_wait(self.h, slot))
+
+    def status(self):
+        v = C.c_uint32()
+        self.ctx._ck(lib.cproc_cuda_bus_status(self.h, C.byref(v)))
+        return v.value
+
+    def destroy(self):
+        if self.h:
+            lib.cproc_cuda_bus_destroy(self.h)
+            self.h = None

@@ -39,3 +39,17 @@ def allreduce_mix(imix, mode=abi.MIX_SAW, group=None):
     # int32 SUM wraps modulo 2^32 on both backends (two's complement adds)
     dist.all_reduce(imix, op=dist.ReduceOp.SUM, group=group)
     return imix
+
+
+def connect_bus(bus, group=None):
+    """Exchange the cudaIpc handles of a cproc_cuda_bus over torch.distributed (any backend)
+    and connect it: after this, Bus.allreduce is one kernel per rank over NVLink peer memory."""
+    world = dist.get_world_size(group)
+    mine = torch.from_numpy(bus.handle().copy())
+    if dist.get_backend(group) == "nccl":
+        mine = mine.cuda()
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    bus.connect(torch.stack([h.cpu() for h in allh]).numpy())
+    dist.barrier(group=group)
+    return bus

@@ -1,0 +1,94 @@
+"""GPU: the mix-bus exchange entry points on one device (world = 1: push to the own slot, reduce,
+fused float scale; the overlapped begin/wait form; argument checks).  The multi-rank run over
+NVLink peer memory is tools/multi_gpu_mix.py under torchrun (results: profiles/r1_multi_gpu_mix_*.json);
+the sharding / reduction logic itself is covered on CPU with gloo (tests/test_multi_rank_cpu.py)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+rng = np.random.default_rng(3)
+
+
+@pytest.fixture(scope="module")
+def st():
+    import synth_tools_b200 as st_
+    return st_
+
+
+@pytest.fixture(scope="module")
+def ctx(st):
+    c = st.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_bus_world_1_equals_mix_to_float(st, ctx, oracle, mode):
+    N, F = 5000, 512
+    v = np.zeros((N, 2), np.uint32)
+    v[:, 0] = [oracle.note_to_inc(int(n)) for n in rng.integers(0, 128, N)]
+    v[:, 1] = rng.integers(0, 2**32, N, dtype=np.uint32)
+    va = v.copy()
+    want_i, want_f = oracle.voice_bank_run(va, N, N, mode, F)
+    b = ctx.batch(st.VOICE_BANK, N, voices_per_bus=0, mode=mode)
+    b.upload_state(v)
+    d_mix = ctx.dev_alloc(4 * F); d_out = ctx.dev_alloc(4 * F)
+    b.run_dev(F, mix=d_mix)
+    bus = st.Bus(ctx, F, 1, 0)
+    assert len(bus.handle()) == st.abi.lib.cproc_cuda_bus_handle_bytes() == 64
+    bus.allreduce(d_mix, F, out_dev=d_out, op=st.Bus.OR if mode else st.Bus.SUM, scale=st.Bus.SCALE_SQUARE if mode else st.Bus.SCALE_SAW)
+    mix = np.zeros(F, np.int32); out = np.zeros(F, np.float32)
+    ctx.d2h(mix, d_mix); ctx.d2h(out, d_out)
+    assert np.array_equal(mix.view(np.uint32), want_i[0].view(np.uint32))
+    assert np.array_equal(out.view(np.uint32), want_f[0].view(np.uint32))
+    # overlapped form, two slots, consecutive epochs
+    d_mix2 = [ctx.dev_alloc(4 * F) for _ in range(2)]; d_out2 = [ctx.dev_alloc(4 * F) for _ in range(2)]
+    wants = []
+    for k in range(5):
+        s = k & 1
+        bus.wait(s)
+        wants.append(oracle.voice_bank_run(va, N, N, mode, F)[1][0].copy())
+        b.run_dev(F, mix=d_mix2[s])
+        bus.begin(s, d_mix2[s], F, out_dev=d_out2[s], op=st.Bus.OR if mode else st.Bus.SUM, scale=st.Bus.SCALE_SQUARE if mode else st.Bus.SCALE_SAW)
+    bus.wait(0); bus.wait(1)
+    ctx.d2h(out, d_out2[0]); assert np.array_equal(out.view(np.uint32), wants[4].view(np.uint32))
+    ctx.d2h(out, d_out2[1]); assert np.array_equal(out.view(np.uint32), wants[3].view(np.uint32))
+    assert bus.status() == 0
+    # grain-mix scale
+    g = rng.integers(-5000, 5000, F).astype(np.int32)
+    ctx.h2d(d_mix, g)
+    bus.allreduce(d_mix, F, out_dev=d_out, scale=st.Bus.SCALE_GRAIN)
+    ctx.d2h(out, d_out)
+    assert np.array_equal(out, g.astype(np.float32) * np.float32(2.0 ** -7))
+    bus.destroy(); b.free()
+    for p in [d_mix, d_out] + d_mix2 + d_out2:
+        ctx.dev_free(p)
+
+
+def test_bus_errors(st, ctx):
+    with pytest.raises(st.CprocCudaError):
+        st.Bus(ctx, 16, 0, 0)
+    with pytest.raises(st.CprocCudaError):
+        st.Bus(ctx, 16, 2, 2)
+    with pytest.raises(st.CprocCudaError):
+        st.Bus(ctx, 0, 1, 0)
+    with pytest.raises(st.CprocCudaError):
+        st.Bus(ctx, 16, 17, 0)
+    d = ctx.dev_alloc(4096)
+    two = st.Bus(ctx, 16, 2, 0)
+    with pytest.raises(st.CprocCudaError) as e:            # peers not connected yet
+        two.allreduce(d, 16)
+    assert e.value.code == st.abi.ESTATE
+    two.destroy()
+    one = st.Bus(ctx, 16, 1, 0)
+    with pytest.raises(st.CprocCudaError):                 # larger than the bus
+        one.allreduce(d, 64)
+    with pytest.raises(st.CprocCudaError):                 # scale without an output buffer
+        one.allreduce(d, 16, scale=st.Bus.SCALE_SAW)
+    with pytest.raises(st.CprocCudaError):
+        one.begin(2, d, 16)
+    one.allreduce(d, 0)                                    # empty exchange is a no-op
+    one.destroy()
+    ctx.dev_free(d)

@@ -1,7 +1,7 @@
 """CPU, gloo, world_size 2: the multi-GPU host logic (contiguous bank-aligned
 shards + integer mix-bus all-reduce) reproduces the single-device result bit
 for bit.  The per-shard render is done by the oracle here (no GPU); on the GPU
-box the same logic drives libcproc_cuda (tests/test_gpu_multi.py, bench.py)."""
+box the same logic drives libcproc_cuda (tools/multi_gpu_mix.py under torchrun; bench.py)."""
 import os
 import socket
 

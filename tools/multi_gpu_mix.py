@@ -1,0 +1,162 @@
+"""Multi-GPU mix bus check + timing (BASELINE.json config 4: 4 Mi voices x 512-frame blocks, the
+mix bus reduced across the GPUs of one box).  Run under torchrun, one rank per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/multi_gpu_mix.py
+
+Voices are sharded in contiguous ranges; each rank renders the INTEGER mix of its shard
+(k_voice_mix).  The bus is then formed twice: (A) NCCL all-reduce of the int32 mix + the
+conversion kernel, (B) cproc_cuda_bus_allreduce -- one kernel per rank over NVLink peer
+memory, reduce and float scale fused.  Both must equal the single-device oracle bit for bit.
+Prints one JSON line per measurement (rank 0)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import synth_tools_b200 as st
+from synth_tools_b200 import shard
+from oracle import pyoracle as po
+
+rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+stream = torch.cuda.Stream(device=dev)
+torch.cuda.set_stream(stream)
+ctx = st.Context(local, stream.cuda_stream)
+orc = po.Oracle()
+tab = np.array([orc.note_to_inc(k) for k in range(128)], np.uint32)
+
+
+def voices(N, seed):
+    r = np.random.default_rng(seed)
+    v = np.zeros((N, 2), np.uint32)
+    v[:, 0] = tab[r.integers(0, 128, N)]
+    v[::53, 0] = 0
+    v[:, 1] = r.integers(0, 2**32, N, dtype=np.uint32)
+    return v
+
+
+def check(N, F, mode):
+    v = voices(N, 1234)                                   # same on every rank
+    lo, hi = shard.shard_range(N, rank, world)
+    full = v.copy()
+    want_i, want_f = orc.voice_bank_run(full, N, N, mode, F)
+    b = ctx.batch(st.VOICE_BANK, hi - lo, voices_per_bus=0, mode=mode)
+    b.upload_state(np.ascontiguousarray(v[lo:hi]))
+    imix = torch.zeros(F, dtype=torch.int32, device=dev)
+    out = torch.zeros(F, dtype=torch.float32, device=dev)
+    b.run_dev(F, mix=imix.data_ptr())
+    keep = imix.clone()
+    # (A) NCCL + conversion kernel
+    shard.allreduce_mix(imix, mode)
+    b.mix_to_float(imix.data_ptr(), out.data_ptr(), F)
+    torch.cuda.synchronize()
+    ok_a = np.array_equal(imix.cpu().numpy().view(np.uint32), want_i[0].view(np.uint32)) and \
+        np.array_equal(out.cpu().numpy().view(np.uint32), want_f[0].view(np.uint32))
+    # (B) one kernel over peer memory
+    bus = shard.connect_bus(st.Bus(ctx, 4096, world, rank))
+    imix.copy_(keep); out.zero_()
+    for _ in range(3):                                    # consecutive epochs reuse the double-buffered slots
+        imix.copy_(keep)
+        bus.allreduce(imix.data_ptr(), F, out_dev=out.data_ptr(), op=st.Bus.OR if mode == 1 else st.Bus.SUM,
+                      scale=st.Bus.SCALE_SQUARE if mode == 1 else st.Bus.SCALE_SAW)
+    torch.cuda.synchronize()
+    ok_b = bus.status() == 0 and np.array_equal(imix.cpu().numpy().view(np.uint32), want_i[0].view(np.uint32)) and \
+        np.array_equal(out.cpu().numpy().view(np.uint32), want_f[0].view(np.uint32))
+    # overlapped form: four blocks in flight over the two slots, every block continues the phases
+    outs = [torch.zeros(F, dtype=torch.float32, device=dev) for _ in range(2)]
+    mixes = [torch.zeros(F, dtype=torch.int32, device=dev) for _ in range(2)]
+    b.upload_state(np.ascontiguousarray(v[lo:hi]))
+    full2 = v.copy()
+    wants = []
+    for k in range(4):
+        s = k & 1
+        bus.wait(s)
+        if k >= 2:
+            ok_b = ok_b and np.array_equal(outs[s].cpu().numpy().view(np.uint32), wants[k - 2].view(np.uint32))
+        wants.append(orc.voice_bank_run(full2, N, N, mode, F)[1][0].copy())
+        b.run_dev(F, mix=mixes[s].data_ptr())
+        bus.begin(s, mixes[s].data_ptr(), F, out_dev=outs[s].data_ptr(), op=st.Bus.OR if mode == 1 else st.Bus.SUM,
+                  scale=st.Bus.SCALE_SQUARE if mode == 1 else st.Bus.SCALE_SAW)
+    bus.wait(0); bus.wait(1)
+    torch.cuda.synchronize()
+    ok_b = ok_b and bus.status() == 0 and np.array_equal(outs[0].cpu().numpy().view(np.uint32), wants[2].view(np.uint32)) and \
+        np.array_equal(outs[1].cpu().numpy().view(np.uint32), wants[3].view(np.uint32))
+    bus.destroy(); b.free()
+    t = torch.tensor([int(ok_a), int(ok_b)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t[0].item()), bool(t[1].item())
+
+
+def timing(N, F, reps=50):
+    v = voices(N, 99)
+    lo, hi = shard.shard_range(N, rank, world)
+    b = ctx.batch(st.VOICE_BANK, hi - lo, voices_per_bus=0)
+    b.upload_state(np.ascontiguousarray(v[lo:hi]))
+    imix = torch.zeros(F, dtype=torch.int32, device=dev)
+    out = torch.zeros(F, dtype=torch.float32, device=dev)
+    bus = shard.connect_bus(st.Bus(ctx, 4096, world, rank))
+    res = {}
+
+    def block_nccl():
+        b.run_dev(F, mix=imix.data_ptr())
+        dist.all_reduce(imix)
+        b.mix_to_float(imix.data_ptr(), out.data_ptr(), F)
+
+    def block_bus():
+        b.run_dev(F, mix=imix.data_ptr())
+        bus.allreduce(imix.data_ptr(), F, out_dev=out.data_ptr(), scale=st.Bus.SCALE_SAW)
+
+    def block_render_only():
+        b.run_dev(F, mix=imix.data_ptr())
+
+    imix2 = [torch.zeros(F, dtype=torch.int32, device=dev) for _ in range(2)]
+    out2 = [torch.zeros(F, dtype=torch.float32, device=dev) for _ in range(2)]
+    kblk = [0]
+
+    def block_bus_overlapped():
+        s = kblk[0] & 1
+        kblk[0] += 1
+        bus.wait(s)                                        # the exchange that last used this buffer pair
+        b.run_dev(F, mix=imix2[s].data_ptr())
+        bus.begin(s, imix2[s].data_ptr(), F, out_dev=out2[s].data_ptr(), scale=st.Bus.SCALE_SAW)
+
+    for name, fn in (("render_only", block_render_only), ("nccl_allreduce_plus_convert", block_nccl), ("peer_memory_bus_kernel", block_bus),
+                     ("peer_memory_bus_overlapped", block_bus_overlapped)):
+        for _ in range(5):
+            fn()
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        bus.wait(0); bus.wait(1)
+        e1.record(stream)
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[name] = float(t.item())
+    ok = bus.status() == 0
+    bus.destroy(); b.free()
+    return res, ok
+
+
+for mode in (0, 1):
+    a, bb = check(256 * 1024 + 77, 512, mode)
+    if rank == 0:
+        print(json.dumps({"check": "voice bank mix bus, mode %d" % mode, "n_gpus": world, "nccl_bit_exact": a, "peer_bus_bit_exact": bb}), flush=True)
+res, ok = timing(4 * 1024 * 1024, 512)
+if rank == 0:
+    N, F = 4 * 1024 * 1024, 512
+    print(json.dumps({"config": "C4' voice bank 4 Mi voices x 512 frames sharded over %d GPUs, int32 mix bus" % world, "n_gpus": world, "bus_ok": ok,
+                      "ms_per_block": res, "voice_samples_per_s": {k: N * F / (v * 1e-3) for k, v in res.items()},
+                      "exchange_cost_us": {"nccl": 1e3 * (res["nccl_allreduce_plus_convert"] - res["render_only"]),
+                                           "peer_bus": 1e3 * (res["peer_memory_bus_kernel"] - res["render_only"]),
+                                           "peer_bus_overlapped": 1e3 * (res["peer_memory_bus_overlapped"] - res["render_only"])}}), flush=True)
+ctx.close()
+dist.destroy_process_group()
