@@ -22,6 +22,7 @@ struct VoiceParams {
     uint32_t tile;           // voices per tile
     uint64_t F;
     uint32_t mode;
+    uint32_t advance;        // 1: the block also writes note_state += F * note_inc for its tile (one block per tile)
     int32_t *isum;           // [n_bus][F]
     float *vec;              // [n_bus][F] or null
 };
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(256) k_voice_mix(const VoiceParams p) {
         uint32_t inc = p.st[v_lo + k], s0 = p.st[p.npad + v_lo + k];
         // voices that are off contribute nothing and do not advance (synth.c:173)
         sv[k] = inc ? make_uint2(inc, s0) : make_uint2(0u, 0u);
+        if (p.advance) p.st[p.npad + v_lo + k] = s0 + (uint32_t)p.F * inc;      // synth.c:177 applied F times
     }
     __syncthreads();
     const uint64_t t0 = (uint64_t)blockIdx.y * (blockDim.x * FPT) + threadIdx.x;
@@ -94,8 +96,22 @@ int launch_voice_bank(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) 
     p.st = b->d_state; p.npad = b->npad; p.n = b->n;
     p.G = b->cfg.voices_per_bus ? b->cfg.voices_per_bus : b->n;
     p.n_bus = b->n_bus; p.F = F; p.mode = b->cfg.mode;
-    p.tile = (uint32_t)(p.G < 4096 ? p.G : 4096);
+    int blk, fpt;
+    if (F <= 64) { blk = 64; fpt = 1; } else if (F <= 128) { blk = 128; fpt = 1; }
+    else if (F <= 256) { blk = 256; fpt = 1; } else if (F <= 512) { blk = 256; fpt = 2; } else { blk = 256; fpt = 4; }
+    const uint64_t gy = ceil_div_u64(F, (uint64_t)blk * fpt);
+    // voices per tile: 4096 when there is enough work, smaller (down to 256) when that would leave
+    // fewer than ~4 blocks per SM (a shard of a multi-GPU run: 512 Ki voices are only 128 tiles of 4096)
+    {
+        const uint64_t want_blocks = (uint64_t)ctx->n_sm * 4;
+        const uint64_t tiles_needed = ceil_div_u64(want_blocks, p.n_bus * gy);
+        uint64_t tile = ceil_div_u64(ceil_div_u64(p.G, tiles_needed), 256) * 256;
+        if (tile > 4096) tile = 4096;
+        if (tile > p.G) tile = p.G;
+        p.tile = (uint32_t)tile;
+    }
     p.tiles_per_bus = (uint32_t)ceil_div_u64(p.G, p.tile);
+    p.advance = gy == 1;
     p.vec = (float *)io->out;
     // the integer mix always exists on the device: it is what gets reduced
     int32_t *isum = (int32_t *)io->mix;
@@ -112,10 +128,7 @@ int launch_voice_bank(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) 
     p.isum = isum;
     if (p.tiles_per_bus > 1) CK(ctx, cudaMemsetAsync(isum, 0, sizeof(int32_t) * p.n_bus * F, ctx->stream));
     const bool sq = p.mode == CPROC_CUDA_MIX_SQUARE;
-    int blk, fpt;
-    if (F <= 64) { blk = 64; fpt = 1; } else if (F <= 128) { blk = 128; fpt = 1; }
-    else if (F <= 256) { blk = 256; fpt = 1; } else if (F <= 512) { blk = 256; fpt = 2; } else { blk = 256; fpt = 4; }
-    dim3 grid((unsigned)(p.n_bus * p.tiles_per_bus), (unsigned)ceil_div_u64(F, (uint64_t)blk * fpt));
+    dim3 grid((unsigned)(p.n_bus * p.tiles_per_bus), (unsigned)gy);
     size_t smem = sizeof(uint2) * p.tile;
 #define VOICE_LAUNCH(FPT) do { \
         if (sq) k_voice_mix<FPT, true><<<grid, blk, smem, ctx->stream>>>(p); \
@@ -128,7 +141,9 @@ int launch_voice_bank(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) 
         k_voice_finish<<<(unsigned)ceil_div_u64(cnt, 256), 256, 0, ctx->stream>>>(isum, p.vec, cnt, p.mode);
         CK_LAUNCH(ctx, "k_voice_finish");
     }
-    k_voice_advance<<<(unsigned)ceil_div_u64(b->n, 256), 256, 0, ctx->stream>>>(b->d_state, b->npad, b->n, (uint32_t)F);
-    CK_LAUNCH(ctx, "k_voice_advance");
+    if (!p.advance) {
+        k_voice_advance<<<(unsigned)ceil_div_u64(b->n, 256), 256, 0, ctx->stream>>>(b->d_state, b->npad, b->n, (uint32_t)F);
+        CK_LAUNCH(ctx, "k_voice_advance");
+    }
     return 0;
 }

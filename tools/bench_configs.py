@@ -110,8 +110,9 @@ def c4p(st, ctx, reps=5):
     d_out = ctx.dev_alloc(4 * F); d_mix = ctx.dev_alloc(4 * F)
     ms = _time(ctx, lambda: b.run_dev(F, out=d_out, mix=d_mix), reps)
     b.free(); ctx.dev_free(d_out); ctx.dev_free(d_mix)
-    return _issue("C4' reference voice bank (sum_tick_saw, linux/synth.c:169-181), 4 Mi voices x 512 frames, int32 mix", N * F, "voice-samples", ms, 4.0,
-                  "SURVEY 8d a-7: 4 int ops per voice-sample; bit-exact at any reduction order")
+    return _issue("C4' reference voice bank (sum_tick_saw, linux/synth.c:169-181), 4 Mi voices x 512 frames, int32 mix", N * F, "voice-samples", ms, 3.0,
+                  "3 instr per voice-sample in the closed-form kernel (IMAD state + t*inc, SHF >> 4, IADD; SURVEY 8d a-7 counts 4 for the "
+                  "reference's read-modify-write loop); bit-exact at any reduction order")
 
 
 def c5(st, ctx, hbm_peak, reps=3, layout="tiled"):

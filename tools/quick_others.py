@@ -36,8 +36,8 @@ if "voice" in which:
         nb = 1 if G == 0 else N // G
         d_out = ctx.dev_alloc(4 * nb * F); d_mix = ctx.dev_alloc(4 * nb * F)
         ms = timeit(lambda: b.run_dev(F, out=d_out, mix=d_mix))
-        print("C4' voice bank %s: N=%d F=%d  %.3f ms  %.2f G voice-samples/s  (issue: %.1f%% of 37.2 T at 4 instr/voice-sample)" %
-              (label, N, F, ms, N * F / ms / 1e6, 100 * 4 * N * F / (ms * 1e-3) / 37.2e12))
+        print("C4' voice bank %s: N=%d F=%d  %.3f ms  %.2f G voice-samples/s  (issue: %.1f%% of 37.2 T at 3 instr/voice-sample)" %
+              (label, N, F, ms, N * F / ms / 1e6, 100 * 3 * N * F / (ms * 1e-3) / 37.2e12))
         ctx.dev_free(d_out); ctx.dev_free(d_mix); b.free()
 
 if "grain" in which:
