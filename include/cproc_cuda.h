@@ -287,7 +287,8 @@ cproc_cuda_batch *cproc_cuda_patch_batch(cproc_cuda_patch *patch);
  * its handle (cproc_cuda_bus_handle_bytes() bytes), the host gathers the handles of
  * all ranks in rank order over its own transport and passes them to _connect.  Every
  * rank must then make the same sequence of _allreduce calls.
- * op: 0 wrap-around sum, 1 OR.  scale: 0 none, 1 saw (float)(int)x*2^-32, 2 square
+ * op: 0 wrap-around sum, 1 OR, 2 float sum in rank order (words are float bits: the float
+ * mix of the extension voices; deterministic, scale must be 0).  scale: 0 none, 1 saw (float)(int)x*2^-32, 2 square
  * (float)(unsigned)x*2^-32, 3 grain mix (float)x*2^-7 (out_dev required unless 0). */
 typedef struct cproc_cuda_bus cproc_cuda_bus;
 int  cproc_cuda_bus_create(cproc_cuda_ctx *ctx, uint64_t max_words, int world, int rank, cproc_cuda_bus **bus);

@@ -392,7 +392,7 @@ class Patch:
 
 class Bus:
     """cproc_cuda_bus: the shared mix bus of the ranks of one box over NVLink peer memory."""
-    SUM, OR = 0, 1
+    SUM, OR, FSUM = 0, 1, 2
     SCALE_NONE, SCALE_SAW, SCALE_SQUARE, SCALE_GRAIN = 0, 1, 2, 3
 
     def __init__(self, ctx, max_words, world, rank):

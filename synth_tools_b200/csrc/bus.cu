@@ -75,9 +75,15 @@ __global__ void __launch_bounds__(256) k_bus_allreduce(const BusParams p) {
     const int32_t *mine = p.slots[p.rank] + (uint64_t)par * p.world * p.cap;
     for (uint64_t i = threadIdx.x; i < p.count; i += blockDim.x) {
         uint32_t acc = 0;
-        for (int q = 0; q < p.world; ++q) {
-            const uint32_t v = (uint32_t)mine[(uint64_t)q * p.cap + i];
-            acc = p.op ? (acc | v) : (acc + v);
+        if (p.op == 2) {                                   // float bus (extension voices): fixed rank order, one rounding per add
+            float fa = 0.0f;
+            for (int q = 0; q < p.world; ++q) fa = __fadd_rn(fa, __int_as_float(mine[(uint64_t)q * p.cap + i]));
+            acc = __float_as_uint(fa);
+        } else {
+            for (int q = 0; q < p.world; ++q) {
+                const uint32_t v = (uint32_t)mine[(uint64_t)q * p.cap + i];
+                acc = p.op ? (acc | v) : (acc + v);
+            }
         }
         p.imix[i] = (int32_t)acc;
         if (p.out) {
@@ -140,7 +146,8 @@ int cproc_cuda_bus_connect(cproc_cuda_bus *b, const void *handles) {
     return 0;
 }
 
-// In place on device memory, asynchronous on the context stream.  op: 0 wrap-around sum, 1 OR.
+// In place on device memory, asynchronous on the context stream.  op: 0 wrap-around sum, 1 OR,
+// 2 float sum in rank order (the words are float bits: the float mix of the extension voices).
 // scale: 0 none (out_dev may be NULL), 1 saw (float)(int)x * 2^-32, 2 square (float)(unsigned)x * 2^-32,
 // 3 grain mix (float)x * 2^-7.  Every rank of the bus must make the same sequence of calls.
 static int bus_launch(cproc_cuda_bus *b, int32_t *imix_dev, float *out_dev, uint64_t count, uint32_t op, uint32_t scale, cudaStream_t st);
@@ -187,7 +194,7 @@ static int bus_launch(cproc_cuda_bus *b, int32_t *imix_dev, float *out_dev, uint
     cproc_cuda_ctx *ctx = b->ctx;
     if (!b->connected) return cproc_set_err(ctx, CPROC_CUDA_ESTATE, "bus_allreduce: bus not connected (cproc_cuda_bus_connect)");
     if (count > b->cap) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "bus_allreduce: %llu words, bus holds %llu", (unsigned long long)count, (unsigned long long)b->cap);
-    if (op > 1 || scale > 3 || (scale && !out_dev)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "bus_allreduce: bad op / scale");
+    if (op > 2 || scale > 3 || (scale && !out_dev) || (op == 2 && scale)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "bus_allreduce: bad op / scale");
     if (count == 0) return 0;
     CK(ctx, cudaSetDevice(ctx->device));
     BusParams p;

@@ -62,6 +62,14 @@ def test_bus_world_1_equals_mix_to_float(st, ctx, oracle, mode):
     bus.allreduce(d_mix, F, out_dev=d_out, scale=st.Bus.SCALE_GRAIN)
     ctx.d2h(out, d_out)
     assert np.array_equal(out, g.astype(np.float32) * np.float32(2.0 ** -7))
+    # float bus (op 2): identity at world 1
+    fl = rng.uniform(-3, 3, F).astype(np.float32)
+    ctx.h2d(d_mix, fl)
+    bus.allreduce(d_mix, F, op=st.Bus.FSUM)
+    got = np.zeros(F, np.float32); ctx.d2h(got, d_mix)
+    assert np.array_equal(got.view(np.uint32), (np.float32(0.0) + fl).view(np.uint32))
+    with pytest.raises(st.CprocCudaError):
+        bus.allreduce(d_mix, F, out_dev=d_out, op=st.Bus.FSUM, scale=st.Bus.SCALE_SAW)
     bus.destroy(); b.free()
     for p in [d_mix, d_out] + d_mix2 + d_out2:
         ctx.dev_free(p)

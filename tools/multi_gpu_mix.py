@@ -146,6 +146,83 @@ def timing(N, F, reps=50):
     return res, ok
 
 
+def xvoice_records(N, seed):
+    r = np.random.default_rng(seed)
+    prm = np.zeros(N, po.xvoice_param_dtype)
+    prm["inc"] = tab[r.integers(24, 109, N)]
+    prm["f"] = r.uniform(0.01, 0.3, N); prm["q"] = r.uniform(0.5, 2.0, N)
+    prm["env_attack"] = r.uniform(1e-3, 1e-1, N); prm["env_release"] = r.uniform(1e-3, 1e-2, N)
+    prm["gate_frames"] = r.integers(0, 400, N)
+    prm["gl"] = r.uniform(0, 1, N); prm["gr"] = 1.0 - prm["gl"]
+    s0 = np.zeros(N, po.xvoice_state_dtype)
+    s0["phase"] = r.integers(0, 2**32, N, dtype=np.uint32)
+    return s0, prm
+
+
+def xvoice_check_and_timing(N_check, N, F, reps=20):
+    """C4: float stereo mix of the extension voices; the bus is a float sum in rank order."""
+    s0, prm = xvoice_records(N_check, 5)
+    lo, hi = shard.shard_range(N_check, rank, world)
+    sa = s0.copy()
+    _, want = orc.xvoice_run(sa, prm, N_check, F, want_raw=False)
+    b = ctx.batch(st.XVOICE, hi - lo)
+    b.upload_state(np.ascontiguousarray(s0[lo:hi]).view(np.uint32).reshape(hi - lo, 5))
+    b.upload_param(np.ascontiguousarray(prm[lo:hi]).view(np.uint32).reshape(hi - lo, 8))
+    mix = torch.zeros(2 * F, dtype=torch.float32, device=dev)
+    bus = shard.connect_bus(st.Bus(ctx, 4096, world, rank))
+    b.run_dev(F, mix=mix.data_ptr())
+    bus.allreduce(mix.data_ptr(), 2 * F, op=st.Bus.FSUM)
+    torch.cuda.synchronize()
+    g64, w64 = mix.cpu().numpy().astype(np.float64), np.asarray(want, np.float64).reshape(-1)
+    ok = bus.status() == 0 and np.abs(g64 - w64).max() <= 1e-5 * np.abs(w64).max() and \
+        10 * np.log10((w64 ** 2).sum() / max(((g64 - w64) ** 2).sum(), 1e-300)) >= 120.0
+    allmix = [torch.empty_like(mix) for _ in range(world)]
+    dist.all_gather(allmix, mix)
+    ok = ok and all(torch.equal(allmix[0], m) for m in allmix)          # every rank holds the same bits
+    b.free()
+    # timing at the full size
+    s0, prm = xvoice_records(N, 6)
+    lo, hi = shard.shard_range(N, rank, world)
+    b = ctx.batch(st.XVOICE, hi - lo)
+    b.upload_state(np.ascontiguousarray(s0[lo:hi]).view(np.uint32).reshape(hi - lo, 5))
+    b.upload_param(np.ascontiguousarray(prm[lo:hi]).view(np.uint32).reshape(hi - lo, 8))
+    mixes = [torch.zeros(2 * F, dtype=torch.float32, device=dev) for _ in range(2)]
+    k = [0]
+
+    def render_only():
+        b.run_dev(F, mix=mixes[0].data_ptr())
+
+    def nccl():
+        b.run_dev(F, mix=mixes[0].data_ptr())
+        dist.all_reduce(mixes[0])
+
+    def overlapped():
+        s = k[0] & 1
+        k[0] += 1
+        bus.wait(s)
+        b.run_dev(F, mix=mixes[s].data_ptr())
+        bus.begin(s, mixes[s].data_ptr(), 2 * F, op=st.Bus.FSUM)
+
+    res = {}
+    for name, fn in (("render_only", render_only), ("nccl_allreduce", nccl), ("peer_memory_bus_overlapped", overlapped)):
+        for _ in range(3):
+            fn()
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        bus.wait(0); bus.wait(1)
+        e1.record(stream)
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[name] = float(t.item())
+    ok = ok and bus.status() == 0
+    bus.destroy(); b.free()
+    return ok, res
+
+
 for mode in (0, 1):
     a, bb = check(256 * 1024 + 77, 512, mode)
     if rank == 0:
@@ -158,5 +235,11 @@ if rank == 0:
                       "exchange_cost_us": {"nccl": 1e3 * (res["nccl_allreduce_plus_convert"] - res["render_only"]),
                                            "peer_bus": 1e3 * (res["peer_memory_bus_kernel"] - res["render_only"]),
                                            "peer_bus_overlapped": 1e3 * (res["peer_memory_bus_overlapped"] - res["render_only"])}}), flush=True)
+okx, resx = xvoice_check_and_timing(64 * 1024 + 5, 4 * 1024 * 1024, 512)
+if rank == 0:
+    N, F = 4 * 1024 * 1024, 512
+    print(json.dumps({"config": "C4 poly voice 4 Mi voices x 512 frames sharded over %d GPUs, float stereo mix bus" % world, "n_gpus": world,
+                      "float_bus_within_tolerance_and_identical_on_all_ranks": bool(okx), "ms_per_block": resx,
+                      "voice_samples_per_s": {k: N * F / (v * 1e-3) for k, v in resx.items()}}), flush=True)
 ctx.close()
 dist.destroy_process_group()
