@@ -59,6 +59,27 @@ def _issue(name, units, unit_name, ms, instr_per_unit, note):
             "algorithmic_instr_per_unit": instr_per_unit, "note": note}
 
 
+def c1(st, ctx):
+    """BASELINE.json configs[0]: the linux/test_cproc.c chain (edge -> acc), 1 voice, 64-frame blocks,
+    750 blocks (1 s at 48 kHz) through the host-buffer call a JACK period makes: latency, not throughput."""
+    import time
+    rng = np.random.default_rng(1)
+    F, blocks = 64, 750
+    b = ctx.batch(st.GRAPH, 1, nodes=[(st.NODE_EDGE, -1, 1), (st.NODE_ACC, 0, 1)])
+    inp = rng.integers(0, 2, (blocks, 1, 1, F), dtype=np.uint32)
+    out = np.zeros((1, F), np.uint32)
+    for k in range(20):
+        b.run(F, inp=inp[k], out=out)
+    t0 = time.perf_counter()
+    for k in range(blocks):
+        b.run(F, inp=inp[k], out=out)
+    us = (time.perf_counter() - t0) / blocks * 1e6
+    b.free()
+    return {"config": "C1 test_cproc chain (edge -> acc), 1 voice x 64-frame blocks, 750 blocks through cproc_cuda_run (host buffers)",
+            "value": us, "unit": "us/block", "bound": "launch latency", "block_period_us": 64 / 48000 * 1e6,
+            "note": "H2D 256 B + generated kernel + D2H 256 B + stream sync per block; a 64-frame period at 48 kHz is 1333 us"}
+
+
 def c3a(st, ctx, hbm_peak, reps=5, layout="planar"):
     rng = np.random.default_rng(3)
     N, F = 1024 * 1024, 256
@@ -131,7 +152,7 @@ def c5(st, ctx, hbm_peak, reps=3, layout="tiled"):
 
 def run_all(st, ctx, hbm_peak):
     rows = []
-    for fn in (lambda: c3a(st, ctx, hbm_peak, layout="planar"), lambda: c3a(st, ctx, hbm_peak, layout="interleaved"),
+    for fn in (lambda: c1(st, ctx), lambda: c3a(st, ctx, hbm_peak, layout="planar"), lambda: c3a(st, ctx, hbm_peak, layout="interleaved"),
                lambda: c3b(st, ctx), lambda: c4(st, ctx), lambda: c4p(st, ctx),
                lambda: c5(st, ctx, hbm_peak, layout="tiled"), lambda: c5(st, ctx, hbm_peak, layout="planar")):
         try:
