@@ -117,7 +117,10 @@ enum cproc_cuda_proc {
      * match the sequential render to <= 1e-5 of peak / >= 120 dB SNR. */
     CPROC_CUDA_XVOICE = 9,
     /* one-pole low-pass y += a*(x-y) (extension).  state {float y}; param
-     * {float a}; in/out float [inst][F]. */
+     * {float a}; in/out float [inst][F].  cfg.mode = CPROC_CUDA_ONEPOLE_SCAN: few
+     * instances, long streams -- time-parallel render from a block scan of the affine
+     * recurrence (fp64 chunk start states; <= 1e-5 of peak / >= 120 dB SNR against the
+     * sequential render; in must not alias out). */
     CPROC_CUDA_ONEPOLE = 10
 };
 
@@ -134,6 +137,7 @@ enum { CPROC_CUDA_NODE_ACC = 0, CPROC_CUDA_NODE_EDGE = 1, CPROC_CUDA_NODE_GLIDE 
 #define CPROC_CUDA_GRAPH_MAX_NODES 64
 enum { CPROC_CUDA_MIX_SAW = 0, CPROC_CUDA_MIX_SQUARE = 1 };
 enum { CPROC_CUDA_XVOICE_SEQ = 0, CPROC_CUDA_XVOICE_SCAN = 1 };
+enum { CPROC_CUDA_ONEPOLE_SEQ = 0, CPROC_CUDA_ONEPOLE_SCAN = 1 };
 
 /* Stream layouts (per-instance streams `x[inst][frame]`). */
 enum {

@@ -750,6 +750,37 @@ def test_onepole(st, ctx, oracle):
     b.free()
 
 
+@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
+@pytest.mark.parametrize("N,F,chunk", [(1, 100000, 0), (3, 65536, 0), (40, 5000, 96), (130, 777, 50), (2, 64, 0)])
+def test_onepole_scan(st, ctx, oracle, layout, N, F, chunk):
+    """Time-parallel one-pole (block scan of the affine recurrence over the time axis): within the
+    stated tolerance of the sequential oracle, final state included."""
+    inp = rng.uniform(-1, 1, (N, F)).astype(np.float32)
+    inp += np.sin(np.arange(F) * 0.001).astype(np.float32)            # slow component: the filter output is not just noise
+    a = rng.uniform(0.0005, 0.5, (N, 1)).astype(np.float32)
+    y0 = rng.uniform(-1, 1, (N, 1)).astype(np.float32)
+    ya = y0[:, 0].copy()
+    want = oracle.onepole_run(ya, a[:, 0].copy(), N, F, inp)
+    ctx.set_option("xvoice_chunk", chunk)
+    try:
+        b = ctx.batch(st.ONEPOLE, N, layout=getattr(st, layout), mode=1)
+        b.upload_state(y0); b.upload_param(a)
+        il = layout == "INTERLEAVED"
+        out = np.zeros((F, N) if il else (N, F), np.float32)
+        l0 = ctx.launches
+        b.run(F, inp=np.ascontiguousarray(inp.T) if il else inp, out=out)
+        if F > 64:
+            assert ctx.launches - l0 == 3                  # zero-state pass, scan, render
+        got = (out.T if il else out).astype(np.float64)
+        w64 = want.astype(np.float64)
+        assert np.abs(got - w64).max() <= 1e-5 * np.abs(w64).max()
+        assert 10 * np.log10((w64 ** 2).sum() / max(((got - w64) ** 2).sum(), 1e-300)) >= 120.0
+        assert np.abs(b.download_state().view(np.float32)[:, 0].astype(np.float64) - ya).max() <= 1e-5 * max(1.0, np.abs(ya).max())
+        b.free()
+    finally:
+        ctx.set_option("xvoice_chunk", 0)
+
+
 # ------------------------------------------------------------ device-resident path
 def test_run_dev_and_stream(st, ctx, oracle):
     """Device-pointer API and the chunked host stream give the same bytes as run()."""

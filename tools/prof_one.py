@@ -94,3 +94,15 @@ elif which in ("graph", "graph_il"):
     b = ctx.batch(st.GRAPH, N, nodes=rows, layout=st.INTERLEAVED if which == "graph_il" else st.PLANAR)
     ms = timed(lambda: b.run_dev(F, inp=d_in, out=d_out))
     print("%s: %.3f ms  %.0f GB/s  %.1f G ticks/s  [%s]" % (which, ms, 8 * N * F / ms / 1e6, N * F / ms / 1e6, b.jit_log.strip()))
+elif which == "onepole_long":
+    # 4 instances x 16 Mi frames: sequential kernel vs time-parallel scan
+    N, F = 4, 16 * 1024 * 1024
+    d_in = ctx.dev_alloc(4 * N * F); d_out = ctx.dev_alloc(4 * N * F)
+    x = rng.uniform(-1, 1, (N, F)).astype(np.float32)
+    ctx.h2d(d_in, x)
+    for mode, label in ((0, "sequential"), (1, "time-parallel scan")):
+        b = ctx.batch(st.ONEPOLE, N, mode=mode)
+        b.upload_param(np.full((N, 1), 0.01, np.float32))
+        ms = timed(lambda: b.run_dev(F, inp=d_in, out=d_out))
+        print("onepole %d x %d (%s): %.3f ms  %.2f G samples/s  %.0f GB/s" % (N, F, label, ms, N * F / ms / 1e6, 8 * N * F / ms / 1e6))
+        b.free()
