@@ -88,7 +88,8 @@ enum cproc_cuda_proc {
      * out: uint8 duty.  PLANAR [ch][F], TILED [F/16][ch][16]. */
     CPROC_CUDA_PDM_V2 = 4,
     /* pwm_update (mod_pdm.c:167-175).  state {uint32 phase}; param {uint32
-     * speed}; out uint8 duty [inst][F]. */
+     * speed}; out uint8 duty: PLANAR [inst][F], INTERLEAVED [F][inst], TILED
+     * [F/16][inst][16]. */
     CPROC_CUDA_PWM = 5,
     /* linux/synth.c voice bank.  state record: struct voice {uint32 note_inc;
      * uint32 note_state} (synth.c:33-36).  Consecutive groups of

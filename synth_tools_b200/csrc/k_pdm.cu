@@ -1268,11 +1268,64 @@ __global__ void k_pwm(uint32_t *phase, const uint32_t *speed, uint64_t n, uint64
     phase[c] = ph;
 }
 
+// PLANAR duty bytes through the bulk-staged template: one "frame" of the template is a 32-bit word
+// = four ticks (duty is 8 bit), so a lane's 64-word tile is 256 ticks of its channel.
+struct PwmOp {
+    static constexpr int NIN = 0;
+    uint32_t *phase; const uint32_t *speed;
+    uint32_t ph, sp;
+    __device__ __forceinline__ void load(uint64_t i) { ph = phase[i]; sp = speed[i]; }
+    __device__ __forceinline__ void store(uint64_t i) { phase[i] = ph; }
+    __device__ __forceinline__ uint32_t tick(uint32_t, uint64_t) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            w |= ((ph >> 16) & 0xFFu) << (8 * k);              // mod_pdm.c:170
+            ph = (ph + sp + (ph >> 9)) & 0xFFFFFFu;            // :171-174
+        }
+        return w;
+    }
+};
+
+// TILED [F/16][ch][16]: one 128-bit store per 16 ticks, like the PDM v2 duty stream
+__global__ void __launch_bounds__(128) k_pwm_tiled(uint32_t *phase, const uint32_t *speed, uint64_t n, uint64_t F, uint8_t *out) {
+    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    uint32_t ph = phase[c];
+    const uint32_t sp = speed[c];
+    for (uint64_t g = 0; g < F / 16; ++g) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            w[q] = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                w[q] |= ((ph >> 16) & 0xFFu) << (8 * k);
+                ph = (ph + sp + (ph >> 9)) & 0xFFFFFFu;
+            }
+        }
+        st_v4_stream(out + ((g * n + c) << 4), make_uint4(w[0], w[1], w[2], w[3]));
+    }
+    phase[c] = ph;
+}
+
 int launch_pwm(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     cproc_cuda_ctx *ctx = b->ctx;
     if (!io->out) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pwm: out is NULL");
-    if (io->layout == CPROC_CUDA_TILED) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pwm: TILED layout not supported");
+    if (io->layout == CPROC_CUDA_TILED && ((F & 15) || ((uintptr_t)io->out & 15))) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pwm: TILED needs F %% 16 == 0 and a 16-byte aligned buffer");
     if (F == 0) return 0;
+    if (io->layout == CPROC_CUDA_TILED) {
+        k_pwm_tiled<<<(unsigned)ceil_div_u64(b->n, 128), 128, 0, ctx->stream>>>(b->d_state, b->d_param, b->n, F, (uint8_t *)io->out);
+        CK_LAUNCH(ctx, "k_pwm_tiled");
+        return 0;
+    }
+    if (ctx->planar_bulk && io->layout == CPROC_CUDA_PLANAR && F % 16 == 0 && pbulk::usable(F / 4, io->out, io->out)) {
+        PwmOp op; op.phase = b->d_state; op.speed = b->d_param; op.ph = 0; op.sp = 0;
+        int rc = pbulk::launch<64, 3>(ctx, op, (const uint32_t *)io->out, (uint32_t *)io->out, b->n, F / 4);
+        if (rc) return rc;
+        CK_LAUNCH(ctx, "k_pwm (bulk)");
+        return 0;
+    }
     k_pwm<<<(unsigned)ceil_div_u64(b->n, 128), 128, 0, ctx->stream>>>(b->d_state, b->d_param, b->n, F, (uint8_t *)io->out, io->layout);
     CK_LAUNCH(ctx, "k_pwm");
     return 0;

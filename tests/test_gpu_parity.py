@@ -302,6 +302,25 @@ def test_pdm_raw(st, ctx, oracle, order, layout):
     b.free()
 
 
+@pytest.mark.parametrize("N,F,layout", [(77, 512, "PLANAR"), (1000, 4096, "PLANAR"), (33, 48, "PLANAR"), (300, 1024, "TILED"),
+                                        (65, 16, "TILED"), (50, 200, "INTERLEAVED")])
+def test_pwm_layouts(st, ctx, oracle, N, F, layout):
+    """pwm_update through the bulk-staged PLANAR kernel (four ticks per staged word), the TILED
+    kernel and the scalar one; a second block continues from the device state."""
+    ph0 = rng.integers(0, 1 << 24, (N, 1), dtype=np.uint32)
+    sp = rng.integers(0, 1 << 16, (N, 1), dtype=np.uint32)
+    pa = ph0[:, 0].copy()
+    b = ctx.batch(st.PWM, N, layout=getattr(st, layout))
+    b.upload_state(ph0); b.upload_param(sp)
+    for _ in range(2):
+        want = oracle.pwm_run(pa, sp[:, 0].copy(), N, F)
+        out = np.zeros(N * F, np.uint8)
+        b.run(F, out=out)
+        got = tiled16_to_planar(out, N, F) if layout == "TILED" else (out.reshape(F, N).T if layout == "INTERLEAVED" else out.reshape(N, F))
+        assert np.array_equal(got, want) and np.array_equal(b.download_state()[:, 0], pa)
+    b.free()
+
+
 def test_pwm(st, ctx, oracle):
     N, F = 77, 500
     ph0 = rng.integers(0, 1 << 24, (N, 1), dtype=np.uint32)

@@ -80,6 +80,20 @@ def c1(st, ctx):
             "note": "H2D 256 B + generated kernel + D2H 256 B + stream sync per block; a 64-frame period at 48 kHz is 1333 us"}
 
 
+def c2_v1(st, ctx, reps=3):
+    """SURVEY 8d C2 variant v1: the carry-bit PDM of mod_pdm.c:198-264, banks of 2 sharing dither, 1 bit per sample."""
+    N, F = 65536, 512 * 1024
+    d_out = ctx.dev_alloc(N * F // 8)
+    b = ctx.batch(st.PDM_V1, N, bank_size=2, dither_mask=0x0FFFFFFF, layout=st.TILED)
+    sp = np.random.default_rng(2).integers(0x40000000, 0xC0000000, (N, 2), dtype=np.uint32)
+    sp[:, 1] = 0
+    b.upload_state(sp)
+    ms = _time(ctx, lambda: b.run_dev(F, out=d_out), reps)
+    b.free(); ctx.dev_free(d_out)
+    return _issue("C2 v1 carry-bit PDM (mod_pdm.c), 65,536 ch x 512 Ki ticks, banks of 2, packed bits out (4 GiB)", N * F, "samples", ms, 7.0,
+                  "SURVEY 8d: 4 int instr per channel-sample + 6 PRNG instr per bank-tick / 2 channels; 1/8 B per sample out")
+
+
 def c3a(st, ctx, hbm_peak, reps=5, layout="planar"):
     rng = np.random.default_rng(3)
     N, F = 1024 * 1024, 256
@@ -152,7 +166,7 @@ def c5(st, ctx, hbm_peak, reps=3, layout="tiled"):
 
 def run_all(st, ctx, hbm_peak):
     rows = []
-    for fn in (lambda: c1(st, ctx), lambda: c3a(st, ctx, hbm_peak, layout="planar"), lambda: c3a(st, ctx, hbm_peak, layout="interleaved"),
+    for fn in (lambda: c1(st, ctx), lambda: c2_v1(st, ctx), lambda: c3a(st, ctx, hbm_peak, layout="planar"), lambda: c3a(st, ctx, hbm_peak, layout="interleaved"),
                lambda: c3b(st, ctx), lambda: c4(st, ctx), lambda: c4p(st, ctx),
                lambda: c5(st, ctx, hbm_peak, layout="tiled"), lambda: c5(st, ctx, hbm_peak, layout="planar")):
         try:
