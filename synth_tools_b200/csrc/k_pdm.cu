@@ -1012,6 +1012,7 @@ struct PdmV1Params {
     uint32_t *out;
     uint64_t F;
     uint32_t dmask, layout;
+    const uint32_t *jump16;    // M^16 of xorshift32 as 4 byte-indexed LUTs (two-chain PRNG) or null
     Sched sched;
 };
 
@@ -1041,15 +1042,50 @@ __device__ __forceinline__ void v1_word(const uint32_t (&sp)[B], uint32_t (&acc)
     for (int j = 0; j < B; ++j) wv[j] = __brev(bits[j]);
 }
 
+// The same word with the bank's generator run as TWO interleaved chains: xorshift32 is a 6-deep
+// dependent chain per tick and there are fewer than two warps per scheduler at the C2 shape, so
+// one chain leaves the issue slots idle.  Chain A produces ticks 0..15, chain B -- started 16
+// steps ahead with the GF(2) jump table M^16 -- ticks 16..31 into registers; the accumulators
+// then consume them in time order.
+template <int B>
+__device__ __forceinline__ void v1_word2(const uint32_t (&sp)[B], uint32_t (&acc)[B], uint32_t &rng, const uint32_t (*jt)[256],
+                                         uint32_t dmask, uint32_t (&wv)[B]) {
+    uint32_t bits[B], late[16];
+#pragma unroll
+    for (int j = 0; j < B; ++j) bits[j] = 0;
+    uint32_t xa = rng, xb = jump_apply(jt, rng);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        xa = xorshift32_step(xa);
+        xb = xorshift32_step(xb);
+        late[i] = xb & dmask;
+        const uint32_t d = xa & dmask;                                             // mod_pdm.c:261
+#pragma unroll
+        for (int j = 0; j < B; ++j) add_carry_shift(acc[j], bits[j], sp[j] + d);   // :235-240
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+#pragma unroll
+        for (int j = 0; j < B; ++j) add_carry_shift(acc[j], bits[j], sp[j] + late[i]);
+    }
+    rng = xb;
+#pragma unroll
+    for (int j = 0; j < B; ++j) wv[j] = __brev(bits[j]);
+}
+
 // words [w0, w1) of one thread's B channels
 template <int B, bool DEXT>
 __device__ __forceinline__ void v1_run_segment(const PdmV1Params &p, const uint32_t (&sp)[B], uint32_t (&acc)[B], uint32_t &rng,
-                                               uint64_t c0, uint64_t bank, uint64_t w0, uint64_t w1) {
+                                               uint64_t c0, uint64_t bank, uint64_t w0, uint64_t w1, const uint32_t (*jt)[256] = nullptr) {
     const uint64_t words = p.F >> 5;
     const uint32_t *dext = DEXT ? p.dither_ext + bank * p.F : nullptr;
     if (p.layout == CPROC_CUDA_TILED) {
         for (uint64_t g = w0; g < w1; g += 4) {
             uint32_t q[4][B];
+            if (!DEXT && jt) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v1_word2<B>(sp, acc, rng, jt, p.dmask, q[k]);
+            } else
 #pragma unroll
             for (int k = 0; k < 4; ++k) v1_word<B, DEXT>(sp, acc, rng, DEXT ? dext + ((g + k) << 5) : nullptr, p.dmask, q[k]);
 #pragma unroll
@@ -1070,6 +1106,11 @@ __device__ __forceinline__ void v1_run_segment(const PdmV1Params &p, const uint3
 
 template <int B>
 __global__ void __launch_bounds__(128, 4) k_pdm_v1_persist(const PdmV1Params p, uint32_t unit_words) {
+    __shared__ uint32_t jt[4][256];
+    if (p.jump16) {
+        for (uint32_t k = threadIdx.x; k < 1024; k += blockDim.x) (&jt[0][0])[k] = __ldg(p.jump16 + k);
+        __syncthreads();
+    }
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t worker = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (worker >= p.sched.W) return;
@@ -1085,7 +1126,7 @@ __global__ void __launch_bounds__(128, 4) k_pdm_v1_persist(const PdmV1Params p, 
 #pragma unroll
             for (int j = 0; j < B; ++j) { sp[j] = __ldcg(p.st + c0 + j); acc[j] = __ldcg(p.st + p.npad + c0 + j); }
             uint32_t rng = __ldcg(p.prng + bank);
-            v1_run_segment<B, false>(p, sp, acc, rng, c0, bank, sg.g0 * unit_words, sg.g1 * unit_words);
+            v1_run_segment<B, false>(p, sp, acc, rng, c0, bank, sg.g0 * unit_words, sg.g1 * unit_words, p.jump16 ? jt : nullptr);
 #pragma unroll
             for (int j = 0; j < B; ++j) __stcg(p.st + p.npad + c0 + j, acc[j]);
             __stcg(p.prng + bank, rng);
@@ -1096,6 +1137,12 @@ __global__ void __launch_bounds__(128, 4) k_pdm_v1_persist(const PdmV1Params p, 
 
 template <int B, bool TPB, bool DEXT>
 __global__ void __launch_bounds__(128) k_pdm_v1_simple(const PdmV1Params p) {
+    __shared__ uint32_t jt[(TPB && !DEXT) ? 4 : 1][256];
+    const bool two = TPB && !DEXT && p.jump16 != nullptr;
+    if (two) {
+        for (uint32_t k = threadIdx.x; k < 1024; k += blockDim.x) (&jt[0][0])[k] = __ldg(p.jump16 + k);
+        __syncthreads();
+    }
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (TPB ? p.n_banks : p.n_banks * p.bank_size)) return;
     const uint64_t c0 = tid * B;
@@ -1105,7 +1152,7 @@ __global__ void __launch_bounds__(128) k_pdm_v1_simple(const PdmV1Params p) {
 #pragma unroll
     for (int j = 0; j < B; ++j) { sp[j] = p.st[c0 + j]; acc[j] = p.st[p.npad + c0 + j]; }
     uint32_t rng = p.prng[bank];
-    v1_run_segment<B, DEXT>(p, sp, acc, rng, c0, bank, 0, p.F >> 5);
+    v1_run_segment<B, DEXT>(p, sp, acc, rng, c0, bank, 0, p.F >> 5, two ? jt : nullptr);
 #pragma unroll
     for (int j = 0; j < B; ++j) p.st[p.npad + c0 + j] = acc[j];
     if (rng_owner && !DEXT) p.prng[bank] = rng;
@@ -1124,10 +1171,17 @@ int launch_pdm_v1(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     p.prng = b->d_prng; p.dither_ext = (const uint32_t *)io->in2; p.out = (uint32_t *)io->out; p.F = F;
     p.dmask = c.dither_mask; p.layout = io->layout;
     p.sched = Sched{};
+    p.jump16 = nullptr;
     const int blk = ctx->pdm_block;
     const bool dext = io->in2 != nullptr;
     const bool tpb = ctx->pdm_tpb && c.bank_size <= 4;
     const uint64_t C = ceil_div_u64(p.n_banks, 32);
+    if (ctx->pdm_v1_chains == 2 && tpb && !dext && io->layout == CPROC_CUDA_TILED) {
+        const uint32_t *jt4 = nullptr;                        // jump_tables(4): tables for 16, 32, 48 steps; the first is M^16
+        int rc = jump_tables(ctx, 4, &jt4);
+        if (rc) return rc;
+        p.jump16 = jt4;
+    }
     if (tpb && !dext && (F & 127) == 0 && persist_wanted(ctx, C)) {
         int rc = sched_setup(b, &p.sched, C, F >> 7, 4 * ctx->pdm_warps_per_smsp);   // unit = 128 ticks = 4 words
         if (rc) return rc;

@@ -230,7 +230,11 @@ def test_pdm_v2_errors(st, ctx):
 @pytest.mark.parametrize("bank,tpb,persist,N", [(1, 1, 2, 301), (2, 1, 2, 301), (2, 1, 0, 301), (2, 0, 0, 301), (3, 1, 1, 301),
                                                (4, 1, 0, 301), (9, 1, 2, 301), (2, 1, 2, 65536), (1, 1, 2, 32 * 700 + 3)])
 @pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED", "TILED"])
-def test_pdm_v1(st, ctx, oracle, bank, tpb, persist, N, layout):
+@pytest.mark.parametrize("chains", [1, 2])
+def test_pdm_v1(st, ctx, oracle, bank, tpb, persist, N, layout, chains):
+    if chains == 1 and layout != "TILED":
+        pytest.skip("the chain count only applies to the TILED thread-per-bank kernels")
+    ctx.set_option("pdm_v1_chains", chains)
     F = 512
     nb = (N + bank - 1) // bank
     ch0 = rng.integers(0, 2**32, (N, 2), dtype=np.uint32)
@@ -256,6 +260,7 @@ def test_pdm_v1(st, ctx, oracle, bank, tpb, persist, N, layout):
     b.free()
     ctx.set_option("pdm_tpb", 1)
     ctx.set_option("pdm_persist", 1)
+    ctx.set_option("pdm_v1_chains", 2)
 
 
 def test_pdm_v1_external_dither_and_density(st, ctx, oracle):
