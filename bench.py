@@ -325,7 +325,17 @@ def run_native(args, rank, local_rank, world):
         if world == 1:
             line["cpu_baseline"] = cpu_baseline_sample()
     batch.free()
+    mix_bus = None
+    if world > 1 and not args.no_other_configs:
+        # the one exchange step of the path, outside every timed region above; all ranks take part
+        try:
+            from tools import bench_configs
+            mix_bus = bench_configs.mix_bus_scaling(st, ctx, torch, dist, stream, dev, rank, world)
+        except Exception as e:
+            mix_bus = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:
+        if mix_bus is not None:
+            line["mix_bus"] = mix_bus
         if world == 1 and not args.no_other_configs:
             # the other BASELINE.json configurations at full size (parity-test cases; reported for the
             # raw-output >= 70 % HBM / mixed-down >= 60 % issue targets), outside every timed region above

@@ -164,6 +164,59 @@ def c5(st, ctx, hbm_peak, reps=3, layout="tiled"):
                 "timed region = envelope walk + zero-state passes + scans + renders")
 
 
+def mix_bus_scaling(st, ctx, torch, dist, stream, dev, rank, world, reps=40):
+    """BASELINE.json config 4 at N > 1: 4 Mi reference voices x 512-frame blocks sharded over the ranks,
+    the int32 mix bus formed (a) by NCCL all-reduce + conversion kernel, (b) by the one-kernel
+    peer-memory bus overlapped with the next block's render.  Strong scaling (total work fixed).
+    Device time, max over ranks."""
+    from synth_tools_b200 import shard
+    rng = np.random.default_rng(99)
+    N, F = 4 * 1024 * 1024, 512
+    lo, hi = shard.shard_range(N, rank, world)
+    v = np.zeros((hi - lo, 2), np.uint32)
+    v[:, 0] = note_incs(rng, hi - lo, 0, 128); v[:, 1] = rng.integers(0, 2**32, hi - lo, dtype=np.uint32)
+    b = ctx.batch(st.VOICE_BANK, hi - lo, voices_per_bus=0)
+    b.upload_state(v)
+    imix = [torch.zeros(F, dtype=torch.int32, device=dev) for _ in range(2)]
+    out = [torch.zeros(F, dtype=torch.float32, device=dev) for _ in range(2)]
+    bus = shard.connect_bus(st.Bus(ctx, 4096, world, rank))
+    k = [0]
+
+    def nccl():
+        b.run_dev(F, mix=imix[0].data_ptr())
+        dist.all_reduce(imix[0])
+        b.mix_to_float(imix[0].data_ptr(), out[0].data_ptr(), F)
+
+    def peer():
+        s = k[0] & 1
+        k[0] += 1
+        bus.wait(s)
+        b.run_dev(F, mix=imix[s].data_ptr())
+        bus.begin(s, imix[s].data_ptr(), F, out_dev=out[s].data_ptr(), scale=st.Bus.SCALE_SAW)
+
+    res = {}
+    for name, fn in (("nccl_allreduce_plus_convert", nccl), ("peer_memory_bus_overlapped", peer)):
+        for _ in range(5):
+            fn()
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        bus.wait(0); bus.wait(1)
+        e1.record(stream)
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[name] = float(t.item())
+    ok = bus.status() == 0
+    bus.destroy(); b.free()
+    return {"config": "C4' reference voice bank, 4 Mi voices x 512-frame blocks sharded over %d GPUs (strong scaling), int32 mix bus" % world,
+            "n_gpus": world, "bus_ok": ok, "ms_per_block": res,
+            "voice_samples_per_s": {kk: N * F / (vv * 1e-3) for kk, vv in res.items()},
+            "note": "bit-exactness of both bus forms against the single-device oracle: tools/multi_gpu_mix.py"}
+
+
 def run_all(st, ctx, hbm_peak):
     rows = []
     for fn in (lambda: c1(st, ctx), lambda: c2_v1(st, ctx), lambda: c3a(st, ctx, hbm_peak, layout="planar"), lambda: c3a(st, ctx, hbm_peak, layout="interleaved"),
