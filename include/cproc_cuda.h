@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CPROC_CUDA_ABI_VERSION 1
+#define CPROC_CUDA_ABI_VERSION 2
 
 /* ---- error codes -------------------------------------------------------- */
 #define CPROC_CUDA_OK        0
@@ -62,7 +62,8 @@ typedef struct cproc_cuda_batch cproc_cuda_batch;  /* N instances of a proc */
 enum cproc_cuda_proc {
     /* Generated cproc graph of acc/edge nodes == cproc_update(w *input, w
      * changed).  state record: node states concatenated in ANF order
-     * (acc_state {w out}, edge_state {w out; w last}; cproc.h:134,145; glide: 5 words).
+     * (acc_state {w out}, edge_state {w out; w last}; cproc.h:134,145; glide: 5 words;
+     * pdm: K+1 words).
      * in:  uint32 [inst][n_inputs][F]; in2: changed mask uint32 [inst][F] or
      * NULL (= -1, mod_cproc_plugin.c:32); out: uint32 [inst][F], the value
      * passed to cproc_output() each tick (test_cproc.c:16). */
@@ -130,11 +131,16 @@ enum cproc_cuda_proc {
  * (struct line[2] of mod_pdm_pwm.c:80-93, pdm_update_line of mod_controlrate.c:28-40,
  * the "representative example" of doc/combinators.org:28-34) as a processor: .in is
  * read once per 2^L ticks, .out is the interpolated line; state record {out, vel0,
- * pos1, vel1, count}; L = CPROC_CUDA_NODE_ARG(type) = CONTROL_DIV_LOG. */
-enum { CPROC_CUDA_NODE_ACC = 0, CPROC_CUDA_NODE_EDGE = 1, CPROC_CUDA_NODE_GLIDE = 2 };
+ * pos1, vel1, count}; L = CPROC_CUDA_NODE_ARG(type) = CONTROL_DIV_LOG.
+ * PDM is pdmK_update (stm32f103/pdm.h:13-77) as a processor: .in the modulator input,
+ * .dither the second input (src2), .out the quantiser output; state record {out, s1..sK};
+ * config word = K | out_shift << 3.  glide -> pdm2 is the firmware's whole v2 channel
+ * (mod_pdm_pwm.c:97-116) as a graph. */
+enum { CPROC_CUDA_NODE_ACC = 0, CPROC_CUDA_NODE_EDGE = 1, CPROC_CUDA_NODE_GLIDE = 2, CPROC_CUDA_NODE_PDM = 3 };
 #define CPROC_CUDA_NODE_KIND(t) ((t) & 0xFFu)
 #define CPROC_CUDA_NODE_ARG(t)  (((t) >> 8) & 0xFFu)
 #define CPROC_CUDA_NODE_GLIDE_L(L) (CPROC_CUDA_NODE_GLIDE | ((uint32_t)(L) << 8))
+#define CPROC_CUDA_NODE_PDM_K(K, SH) (CPROC_CUDA_NODE_PDM | (((uint32_t)(K) | ((uint32_t)(SH) << 3)) << 8))
 #define CPROC_CUDA_GRAPH_MAX_NODES 64
 enum { CPROC_CUDA_MIX_SAW = 0, CPROC_CUDA_MIX_SQUARE = 1 };
 enum { CPROC_CUDA_XVOICE_SEQ = 0, CPROC_CUDA_XVOICE_SCAN = 1 };
@@ -151,9 +157,10 @@ enum {
 
 /* One PROC_COND statement of a generated graph (cproc.h:72-77). */
 typedef struct {
-    uint32_t type;       /* CPROC_CUDA_NODE_*                                */
+    uint32_t type;       /* CPROC_CUDA_NODE_* | config word << 8             */
     int32_t  src;        /* >=0: .in = n<src>.out; <0: .in = input[-(src+1)] */
     uint32_t cond_mask;  /* node runs iff (changed & cond_mask) != 0         */
+    int32_t  src2;       /* second input (pdm: .dither), same encoding; ignored by one-input processors */
 } cproc_cuda_node;
 
 typedef struct {
@@ -179,6 +186,7 @@ typedef struct {
  * stm32f103/bp5_plugin.c:1-9): `#define CPROC_NB_INPUTS n`, a sequence of
  *   PROC_COND(<changed> & <mask>, <inst>, acc|edge, NULL, NULL, .in = input[k] | <inst>.out);
  *   PROC_COND(<changed> & <mask>, <inst>, glide, &(glide_config){.div_log = L}, NULL, .in = ...);
+ *   PROC_COND(<changed> & <mask>, <inst>, pdm1..pdm4, &(pdm_config){.out_shift = S}, NULL, .in = ..., .dither = ...);
  * (or PROC(<inst>, ...), cproc.h:81) and one `cproc_output(<index>, <inst>.out);`.
  * Fills `nodes` (at most max_nodes rows) and `info`; the rows go into
  * cproc_cuda_config.nodes / n_nodes / n_inputs / out_node unchanged.  Needs no device. */
@@ -262,7 +270,7 @@ int  cproc_cuda_graph_jit_source(const cproc_cuda_node *nodes, uint32_t n_nodes,
  * (class/<c>/apply, inst/<node>/state/<k>/get|set, patch/reset, patch/tick) with the
  * instances held as N-wide batches on the device.  Classes: 0 acc, 1 edge, 2 glide
  * (config = div_log), 3 input (config = external stream index; the role gpin has on
- * the microcontroller).  Field names as in the proc_meta tables (cproc.h:107-122).
+ * the microcontroller), 4 pdm (inputs in, dither; config = order | out_shift << 3).  Field names as in the proc_meta tables (cproc.h:107-122).
  * kind: 0 param, 1 state (PARAM / STATE, mod_bpmodular.c:126-127), 2 input, 3 config. */
 typedef struct cproc_cuda_patch cproc_cuda_patch;
 int  cproc_cuda_patch_class_count(void);

@@ -33,7 +33,12 @@ void orc_glide_update(orc_glide_state *s, orc_w in, uint32_t div_log) {
 
 uint32_t orc_node_state_words(uint32_t type) {
     /* sizeof(acc_state)=4, sizeof(edge_state)=8 (cproc.h:134,145); glide: 5 words */
-    switch (type & 0xFF) { case ORC_NODE_EDGE: return 2u; case ORC_NODE_GLIDE: return 5u; default: return 1u; }
+    switch (type & 0xFF) {
+    case ORC_NODE_EDGE: return 2u;
+    case ORC_NODE_GLIDE: return 5u;
+    case ORC_NODE_PDM: return 1u + ((type >> 8) & 7u);
+    default: return 1u;
+    }
 }
 uint32_t orc_graph_state_words(const orc_node *nodes, uint32_t n_nodes) {
     uint32_t w = 0;
@@ -62,6 +67,13 @@ void orc_graph_run(const orc_node *nodes, uint32_t n_nodes, uint32_t n_inputs,
                 uint32_t x = nodes[i].src >= 0
                     ? st[off[nodes[i].src]] /* .out is the first state word */
                     : in[((uint64_t)n * n_inputs + (uint32_t)(-(nodes[i].src + 1))) * F + t];
+                if ((nodes[i].type & 0xFF) == ORC_NODE_PDM) {
+                    uint32_t d = nodes[i].src2 >= 0 ? st[off[nodes[i].src2]]
+                        : in[((uint64_t)n * n_inputs + (uint32_t)(-(nodes[i].src2 + 1))) * F + t];
+                    uint32_t order = (nodes[i].type >> 8) & 7u, sh = (nodes[i].type >> 11) & 31u;
+                    st[off[i]] = orc_pdm_update(st + off[i] + 1, order, x, sh, d);   /* pdm.h:13-77 */
+                    continue;
+                }
                 switch (nodes[i].type & 0xFF) {
                 case ORC_NODE_EDGE: orc_edge_update((orc_edge_state *)(st + off[i]), x); break;
                 case ORC_NODE_GLIDE: orc_glide_update((orc_glide_state *)(st + off[i]), x, (nodes[i].type >> 8) & 0xFF); break;

@@ -43,7 +43,9 @@ void orc_edge_update(orc_edge_state *s, orc_w in);      /* cproc.h:151-154 */
 
 /* A generated cproc graph (linux/test_cproc.c:12-17, stm32f103/bp5_plugin.c:4-9)
  * as a table: one row per PROC_COND statement, in ANF order. */
-enum { ORC_NODE_ACC = 0, ORC_NODE_EDGE = 1, ORC_NODE_GLIDE = 2 };
+enum { ORC_NODE_ACC = 0, ORC_NODE_EDGE = 1, ORC_NODE_GLIDE = 2, ORC_NODE_PDM = 3 };
+/* pdm node: pdmK_update (pdm.h:13-77) as a processor, state {out, s1..sK}; .in = src, .dither = src2;
+ * type = 3 | (K | out_shift << 3) << 8. */
 /* glide: the control-rate -> audio-rate parameter interpolation of the firmware
  * (doc/combinators.org:28-34 "representative example") as a processor.  State is the
  * two line segments of struct channel (mod_pdm_pwm.c:80-93) plus the divider count
@@ -61,6 +63,7 @@ typedef struct {
     uint32_t type;      /* ORC_NODE_* | (argument << 8) */
     int32_t  src;       /* >=0: .in = n<src>.out ; <0: .in = input[-(src+1)] */
     uint32_t cond_mask; /* executed iff (changed & cond_mask) != 0 */
+    int32_t  src2;      /* second input (pdm: dither), same encoding */
 } orc_node;
 uint32_t orc_node_state_words(uint32_t type);
 uint32_t orc_graph_state_words(const orc_node *nodes, uint32_t n_nodes);

@@ -20,7 +20,7 @@ u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 VP = C.c_void_p
 
-NODE_ACC, NODE_EDGE, NODE_GLIDE = 0, 1, 2
+NODE_ACC, NODE_EDGE, NODE_GLIDE, NODE_PDM = 0, 1, 2, 3
 
 
 def node_glide(div_log):
@@ -28,12 +28,19 @@ def node_glide(div_log):
     return NODE_GLIDE | (div_log << 8)
 
 
+def node_pdm(order, out_shift):
+    """pdm node type word: kind | (order | out_shift << 3) << 8."""
+    return NODE_PDM | ((order | (out_shift << 3)) << 8)
+
+
 def node_words(t):
+    if t & 0xFF == NODE_PDM:
+        return 1 + ((t >> 8) & 7)
     return {NODE_EDGE: 2, NODE_GLIDE: 5}.get(t & 0xFF, 1)
 
 MIX_SAW, MIX_SQUARE = 0, 1
 
-node_dtype = np.dtype([("type", np.uint32), ("src", np.int32), ("cond_mask", np.uint32)])
+node_dtype = np.dtype([("type", np.uint32), ("src", np.int32), ("cond_mask", np.uint32), ("src2", np.int32)])
 xvoice_param_dtype = np.dtype([("inc", np.uint32), ("f", np.float32), ("q", np.float32),
                                ("env_attack", np.float32), ("env_release", np.float32),
                                ("gate_frames", np.uint32), ("gl", np.float32), ("gr", np.float32)])
@@ -67,8 +74,8 @@ def _ptr(a):
 def make_nodes(rows):
     """rows: [(type, src, cond_mask)] -> structured array for *_graph_run."""
     a = np.zeros(len(rows), node_dtype)
-    for i, (t, s, m) in enumerate(rows):
-        a[i] = (t, s, m)
+    for i, r in enumerate(rows):                 # (type, src, cond_mask[, src2])
+        a[i] = (r[0], r[1], r[2], r[3] if len(r) > 3 else 0)
     return a
 
 

@@ -43,8 +43,8 @@ uint32_t ref_sizeof(int what) {
 }
 
 /* Table-driven graphs calling the real DEF_PROC bodies; same table format as
- * the oracle (type 0 = acc, 1 = edge). */
-typedef struct { uint32_t type; int32_t src; uint32_t cond_mask; } ref_node;
+ * the oracle (type 0 = acc, 1 = edge; the reference has no two-input processor, src2 is unused). */
+typedef struct { uint32_t type; int32_t src; uint32_t cond_mask; int32_t src2; } ref_node;
 void ref_graph_run(const ref_node *nodes, uint32_t n_nodes, uint32_t n_inputs,
                    uint32_t out_node, uint32_t *state, uint64_t N, uint64_t F,
                    const uint32_t *in, const uint32_t *changed, uint32_t *out) {

@@ -7,10 +7,10 @@ Importing the package loads the CUDA library and fails loudly when it has not
 been built: there is no CPU fallback.
 """
 from . import abi  # noqa: F401  (raises ImportError if libcproc_cuda.so is missing)
-from .abi import (Batch, Bus, Context, Patch, CprocCudaError, GRAPH, INTERLEAVED, MIX_SAW, MIX_SQUARE, NODE_ACC, NODE_EDGE, NODE_GLIDE,
+from .abi import (Batch, Bus, Context, Patch, CprocCudaError, GRAPH, INTERLEAVED, MIX_SAW, MIX_SQUARE, NODE_ACC, NODE_EDGE, NODE_GLIDE, NODE_PDM,
                   ONEPOLE, PDM, PDM_V1, PDM_V2, PLANAR, PWM, SQUARE_GRAIN, SQUARE_GRAIN_MIX, TILED, VOICE_BANK,
-                  XVOICE, XVOICE_SCAN, XVOICE_SEQ, graph_parse, node_glide)
+                  XVOICE, XVOICE_SCAN, XVOICE_SEQ, graph_parse, node_glide, node_pdm)
 
 __all__ = ["abi", "Batch", "Bus", "Context", "Patch", "CprocCudaError", "GRAPH", "PDM", "PDM_V1", "PDM_V2", "PWM", "VOICE_BANK",
-           "SQUARE_GRAIN", "SQUARE_GRAIN_MIX", "XVOICE", "ONEPOLE", "NODE_ACC", "NODE_EDGE", "NODE_GLIDE", "node_glide", "graph_parse", "MIX_SAW",
+           "SQUARE_GRAIN", "SQUARE_GRAIN_MIX", "XVOICE", "ONEPOLE", "NODE_ACC", "NODE_EDGE", "NODE_GLIDE", "NODE_PDM", "node_glide", "node_pdm", "graph_parse", "MIX_SAW",
            "MIX_SQUARE", "XVOICE_SEQ", "XVOICE_SCAN", "PLANAR", "INTERLEAVED", "TILED"]

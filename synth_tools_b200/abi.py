@@ -14,12 +14,26 @@ LIB_PATH = os.path.join(HERE, "libcproc_cuda.so")
 
 # enum cproc_cuda_proc
 GRAPH, PDM, PDM_V1, PDM_V2, PWM, VOICE_BANK, SQUARE_GRAIN, SQUARE_GRAIN_MIX, XVOICE, ONEPOLE = range(1, 11)
-NODE_ACC, NODE_EDGE, NODE_GLIDE = 0, 1, 2
+NODE_ACC, NODE_EDGE, NODE_GLIDE, NODE_PDM = 0, 1, 2, 3
 
 
 def node_glide(div_log):
     """CPROC_CUDA_NODE_GLIDE_L(L)"""
     return NODE_GLIDE | (div_log << 8)
+
+
+def node_pdm(order, out_shift):
+    """CPROC_CUDA_NODE_PDM_K(K, SH)"""
+    return NODE_PDM | ((order | (out_shift << 3)) << 8)
+
+
+def _node(r):
+    return Node(r[0], r[1], r[2], r[3] if len(r) > 3 else 0)
+
+
+def _row(n):
+    """Node -> (type, src, cond_mask) for one-input kinds, (type, src, cond_mask, src2) for pdm."""
+    return (n.type, n.src, n.cond_mask, n.src2) if n.type & 0xFF == NODE_PDM else (n.type, n.src, n.cond_mask)
 
 MIX_SAW, MIX_SQUARE = 0, 1
 XVOICE_SEQ, XVOICE_SCAN = 0, 1
@@ -28,7 +42,7 @@ OK, EINVAL, ENODEV, ENOMEM, ECUDA, ESTATE = 0, -1, -2, -3, -4, -5
 
 
 class Node(C.Structure):
-    _fields_ = [("type", C.c_uint32), ("src", C.c_int32), ("cond_mask", C.c_uint32)]
+    _fields_ = [("type", C.c_uint32), ("src", C.c_int32), ("cond_mask", C.c_uint32), ("src2", C.c_int32)]
 
 
 class Config(C.Structure):
@@ -141,13 +155,13 @@ def graph_parse(text):
     rc = lib.cproc_cuda_graph_parse(text.encode(), nodes, GRAPH_MAX_NODES, C.byref(info))
     if rc:
         raise CprocCudaError(rc, (lib.cproc_cuda_last_error(None) or b"").decode())
-    rows = [(nodes[k].type, nodes[k].src, nodes[k].cond_mask) for k in range(info.n_nodes)]
+    rows = [_row(nodes[k]) for k in range(info.n_nodes)]
     return rows, info.n_inputs, info.out_node, info.out_index
 
 
 def graph_jit_source(rows, n_inputs, out_node, has_changed=False):
     """The CUDA source the library generates (and NVRTC-compiles) for a node table."""
-    arr = (Node * len(rows))(*[Node(t, s, m) for t, s, m in rows])
+    arr = (Node * len(rows))(*[_node(r) for r in rows])
     n = lib.cproc_cuda_graph_jit_source(arr, len(rows), n_inputs, out_node, int(has_changed), None, 0)
     if n < 0:
         raise CprocCudaError(n, (lib.cproc_cuda_last_error(None) or b"").decode())
@@ -265,7 +279,7 @@ class Batch:
         cfg.mode, cfg.voices_per_bus = mode, voices_per_bus
         self._nodes = None
         if nodes is not None:
-            arr = (Node * len(nodes))(*[Node(t, s, m) for t, s, m in nodes])
+            arr = (Node * len(nodes))(*[_node(r) for r in nodes])
             self._nodes = arr
             cfg.nodes = arr
             cfg.n_nodes = len(nodes)

@@ -161,13 +161,7 @@ int cproc_cuda_alloc(cproc_cuda_ctx *ctx, const cproc_cuda_config *cfg, uint64_t
         nodes.assign(c.nodes, c.nodes + c.n_nodes);
         for (uint32_t k = 0; k < c.n_nodes; ++k) {
             const cproc_cuda_node &nd = nodes[k];
-            if (CPROC_CUDA_NODE_KIND(nd.type) > CPROC_CUDA_NODE_GLIDE || (nd.type >> 16)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: node %u has unknown type %u", k, nd.type);
-            if (CPROC_CUDA_NODE_KIND(nd.type) == CPROC_CUDA_NODE_GLIDE && (CPROC_CUDA_NODE_ARG(nd.type) < 1 || CPROC_CUDA_NODE_ARG(nd.type) > 24))
-                return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: glide node %u needs a control divider log2 of 1..24", k);
-            if (CPROC_CUDA_NODE_KIND(nd.type) != CPROC_CUDA_NODE_GLIDE && CPROC_CUDA_NODE_ARG(nd.type)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: node %u: acc / edge take no config word", k);
-            // ANF: a node may only read nodes bound before it (cproc.h:51-68)
-            if (nd.src >= (int32_t)k) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: node %u reads node %d which is not bound yet", k, nd.src);
-            if (nd.src < 0 && (uint32_t)(-(nd.src + 1)) >= c.n_inputs) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: node %u reads input %d of %u", k, -(nd.src + 1), c.n_inputs);
+            if (const char *why = cproc_node_check(nd, k, c.n_inputs)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: node %u (type 0x%x, src %d): %s", k, nd.type, nd.src, why);
         }
     }
     if (pdm_family || c.proc == CPROC_CUDA_PDM_V2) {

@@ -92,8 +92,28 @@ int cproc_check(cproc_cuda_ctx *ctx, cudaError_t e, const char *what);
 #define CK(ctx, call) do { int _rc = cproc_check((ctx), (call), #call); if (_rc) return _rc; } while (0)
 #define CK_LAUNCH(ctx, name) do { (ctx)->launches++; int _rc = cproc_check((ctx), cudaGetLastError(), name); if (_rc) return _rc; } while (0)
 
-static inline uint32_t cproc_node_words(uint32_t type) {   // acc {out}; edge {out, last}; glide {out, vel0, pos1, vel1, count}
-    switch (CPROC_CUDA_NODE_KIND(type)) { case CPROC_CUDA_NODE_EDGE: return 2u; case CPROC_CUDA_NODE_GLIDE: return 5u; default: return 1u; }
+static inline uint32_t cproc_node_words(uint32_t type) {   // acc {out}; edge {out, last}; glide {out, vel0, pos1, vel1, count}; pdm {out, s1..sK}
+    switch (CPROC_CUDA_NODE_KIND(type)) {
+    case CPROC_CUDA_NODE_EDGE: return 2u;
+    case CPROC_CUDA_NODE_GLIDE: return 5u;
+    case CPROC_CUDA_NODE_PDM: return 1u + (CPROC_CUDA_NODE_ARG(type) & 7u);
+    default: return 1u;
+    }
+}
+// Validity of one node row at position k of an ANF table (shared by alloc, the JIT and the patcher)
+static inline const char *cproc_node_check(const cproc_cuda_node &nd, uint32_t k, uint32_t n_inputs) {
+    const uint32_t kind = CPROC_CUDA_NODE_KIND(nd.type), arg = CPROC_CUDA_NODE_ARG(nd.type);
+    if (kind > CPROC_CUDA_NODE_PDM || (nd.type >> 16)) return "unknown node type";
+    if (kind == CPROC_CUDA_NODE_GLIDE && (arg < 1 || arg > 24)) return "glide needs a control divider log2 of 1..24";
+    if (kind == CPROC_CUDA_NODE_PDM && ((arg & 7u) < 1 || (arg & 7u) > 4)) return "pdm order must be 1..4";
+    if (kind <= CPROC_CUDA_NODE_EDGE && arg) return "acc / edge take no config word";
+    if (nd.src >= (int32_t)k) return "reads a node that is not bound yet (ANF)";
+    if (nd.src < 0 && (uint32_t)(-(nd.src + 1)) >= n_inputs) return "reads an input stream that does not exist";
+    if (kind == CPROC_CUDA_NODE_PDM) {
+        if (nd.src2 >= (int32_t)k) return "second input reads a node that is not bound yet (ANF)";
+        if (nd.src2 < 0 && (uint32_t)(-(nd.src2 + 1)) >= n_inputs) return "second input reads an input stream that does not exist";
+    }
+    return nullptr;
 }
 static inline uint64_t ceil_div_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 

@@ -171,6 +171,8 @@ extern "C" int cproc_cuda_graph_parse(const char *text, cproc_cuda_node *nodes, 
         else nd.cond_mask = 0xFFFFFFFFu;
         const std::string inst = trim(a[base]), type = trim(a[base + 1]), cfg = trim(a[base + 2]), prm = trim(a[base + 3]);
         bool cfg_null = cfg == "NULL" || cfg == "0";
+        nd.src2 = 0;
+        uint32_t n_in_expected = 1;
         if (type == "acc") nd.type = CPROC_CUDA_NODE_ACC;
         else if (type == "edge") nd.type = CPROC_CUDA_NODE_EDGE;
         else if (type == "glide") {
@@ -183,33 +185,58 @@ extern "C" int cproc_cuda_graph_parse(const char *text, cproc_cuda_node *nodes, 
             nd.type = CPROC_CUDA_NODE_GLIDE_L(L);
             cfg_null = true;
         }
-        else return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s' has unknown processor type '%s' (acc, edge, glide)", inst.c_str(), type.c_str());
+        else if (type.size() == 4 && type.compare(0, 3, "pdm") == 0 && type[3] >= '1' && type[3] <= '4') {
+            // pdmK_update(&s, in, out_shift, dither), pdm.h:13-77: &(pdm_config){ .out_shift = S }
+            const size_t f = cfg.find("out_shift");
+            uint64_t S = 0;
+            bool ok = f != std::string::npos;
+            if (ok) { Cursor q{cfg.c_str() + f + 9, ""}; ok = q.lit("=") && q.number(&S) && S <= 31; }
+            if (!ok) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': %s needs a config with .out_shift = 0..31", inst.c_str(), type.c_str());
+            nd.type = CPROC_CUDA_NODE_PDM_K(type[3] - '0', S);
+            cfg_null = true;
+            n_in_expected = type[3] == '1' ? 1 : 2;             // pdm1 takes no dither (pdm.h:13)
+        }
+        else return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s' has unknown processor type '%s' (acc, edge, glide, pdm1..pdm4)", inst.c_str(), type.c_str());
         if (!cfg_null || (prm != "NULL" && prm != "0"))
             return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': %s has empty config and param records, expected NULL", inst.c_str(), type.c_str());
         for (const std::string &nm : names) if (nm == inst) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s' bound twice", inst.c_str());
-        if (a.size() != base + 5) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': %s has exactly one input (.in)", inst.c_str(), type.c_str());
-        // .in = input[k]  |  .in = <node>.out
-        Cursor b{a[base + 4].c_str(), ""};
-        std::string f;
-        if (!b.lit(".") || !b.ident(&f) || f != "in" || !b.lit("=")) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': expected '.in = ...'", inst.c_str());
-        std::string s0;
-        if (!b.ident(&s0)) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': input expression not understood", inst.c_str());
-        if (b.lit("[")) {
-            uint64_t k;
-            if (s0 != "input" || !b.number(&k) || !b.lit("]")) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': expected input[<k>]", inst.c_str());
-            nd.src = -(int32_t)k - 1;
-            if (!any_input || k > max_input) max_input = (uint32_t)k;
-            any_input = true;
-        } else {
-            std::string fo;
-            if (!b.lit(".") || !b.ident(&fo) || fo != "out") return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': expected <node>.out", inst.c_str());
-            size_t k = 0;
-            while (k < names.size() && names[k] != s0) ++k;
-            if (k == names.size()) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s' reads '%s', which is not bound yet (ANF)", inst.c_str(), s0.c_str());
-            nd.src = (int32_t)k;
+        const bool is_pdm = CPROC_CUDA_NODE_KIND(nd.type) == CPROC_CUDA_NODE_PDM;
+        if (a.size() < base + 5 || a.size() > base + 4 + (is_pdm ? 2u : 1u))
+            return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': %s has exactly %u input%s (.in%s)", inst.c_str(), type.c_str(), n_in_expected, n_in_expected > 1 ? "s" : "", is_pdm ? ", .dither" : "");
+        // designated initialisers: .in = input[k] | <node>.out   (pdm: also .dither = ...)
+        bool have_in = false, have_dither = false;
+        for (size_t ai = base + 4; ai < a.size(); ++ai) {
+            Cursor b{a[ai].c_str(), ""};
+            std::string f;
+            if (!b.lit(".") || !b.ident(&f) || !b.lit("=") || (f != "in" && !(is_pdm && f == "dither")))
+                return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': expected '.in = ...'%s", inst.c_str(), is_pdm ? " / '.dither = ...'" : "");
+            int32_t srcv = 0;
+            std::string s0;
+            if (!b.ident(&s0)) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': input expression not understood", inst.c_str());
+            if (b.lit("[")) {
+                uint64_t k;
+                if (s0 != "input" || !b.number(&k) || !b.lit("]")) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': expected input[<k>]", inst.c_str());
+                srcv = -(int32_t)k - 1;
+                if (!any_input || k > max_input) max_input = (uint32_t)k;
+                any_input = true;
+            } else {
+                std::string fo;
+                if (!b.lit(".") || !b.ident(&fo) || fo != "out") return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': expected <node>.out", inst.c_str());
+                size_t k = 0;
+                while (k < names.size() && names[k] != s0) ++k;
+                if (k == names.size()) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s' reads '%s', which is not bound yet (ANF)", inst.c_str(), s0.c_str());
+                srcv = (int32_t)k;
+            }
+            b.ws();
+            if (*b.p) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': trailing text in the input expression", inst.c_str());
+            if (f == "in") { if (have_in) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': .in given twice", inst.c_str()); nd.src = srcv; have_in = true; }
+            else { if (have_dither) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': .dither given twice", inst.c_str()); nd.src2 = srcv; have_dither = true; }
         }
-        b.ws();
-        if (*b.p) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': trailing text in the input expression", inst.c_str());
+        if (!have_in) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': expected '.in = ...'", inst.c_str());
+        if (is_pdm && !have_dither) {
+            if (n_in_expected == 2) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': %s needs '.dither = ...'", inst.c_str(), type.c_str());
+            nd.src2 = nd.src;                                    // pdm1: unused, keep the row valid
+        }
         if (names.size() >= max_nodes) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: more than %u nodes", max_nodes);
         nodes[names.size()] = nd;
         names.push_back(inst);
@@ -385,15 +412,16 @@ extern "C" __global__ void __launch_bounds__(WARPS * 32) graph_planar(const Grap
         const uint32_t row = base + s * STAGEB + lane * ROWB;      // stream j of this lane: row + j * 32 * ROWB
         if (mine) {
             for (uint32_t c = 0; c < cols / 4; ++c) {
-                uint32_t x[4][GRAPH_NIN], g[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, o[4];
+                // four frames per 128-bit access; separate arrays and explicit ticks keep every index static
+                uint32_t xa[GRAPH_NIN], xb[GRAPH_NIN], xc[GRAPH_NIN], xd[GRAPH_NIN], ga = 0xFFFFFFFFu, gb = 0xFFFFFFFFu, gc = 0xFFFFFFFFu, gd = 0xFFFFFFFFu;
+                uint32_t oa, ob, oc, od;
 #pragma unroll
                 for (int j = 0; j < GRAPH_NIN; ++j)
-                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x[0][j]), "=r"(x[1][j]), "=r"(x[2][j]), "=r"(x[3][j]) : "r"(row + j * (32 * ROWB) + 16 * c));
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(xa[j]), "=r"(xb[j]), "=r"(xc[j]), "=r"(xd[j]) : "r"(row + j * (32 * ROWB) + 16 * c));
                 if (GRAPH_HAS_CHANGED)
-                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(g[0]), "=r"(g[1]), "=r"(g[2]), "=r"(g[3]) : "r"(row + GRAPH_NIN * (32 * ROWB) + 16 * c));
-#pragma unroll
-                for (int q = 0; q < 4; ++q) TICK(x[q], g[q], o[q]);
-                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(row + 16 * c), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ga), "=r"(gb), "=r"(gc), "=r"(gd) : "r"(row + GRAPH_NIN * (32 * ROWB) + 16 * c));
+                TICK(xa, ga, oa); TICK(xb, gb, ob); TICK(xc, gc, oc); TICK(xd, gd, od);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(row + 16 * c), "r"(oa), "r"(ob), "r"(oc), "r"(od) : "memory");
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out + i * p.F + (uint64_t)k * TF), "r"(row), "r"(cols * 4) : "memory");
@@ -442,12 +470,31 @@ std::string cproc_graph_jit_source(const std::vector<cproc_cuda_node> &nodes, ui
     std::string tick = "#define GRAPH_TICK(x, g)";
     for (size_t k = 0; k < nodes.size(); ++k) {
         const cproc_cuda_node &nd = nodes[k];
-        std::string in;
-        if (nd.src >= 0) { snprintf(buf, sizeof(buf), "s%u", off[nd.src]); in = buf; }
-        else { snprintf(buf, sizeof(buf), "(x)[%d]", -(nd.src + 1)); in = buf; }
+        auto operand = [&](int32_t src) {
+            char ob[64];
+            if (src >= 0) snprintf(ob, sizeof(ob), "s%u", off[src]);
+            else snprintf(ob, sizeof(ob), "(x)[%d]", -(src + 1));
+            return std::string(ob);
+        };
+        const std::string in = operand(nd.src);
         std::string cond;
         if (nd.cond_mask == 0xFFFFFFFFu && !has_changed) cond = "";
         else { snprintf(buf, sizeof(buf), "if ((g) & 0x%xu) ", nd.cond_mask); cond = buf; }
+        if (CPROC_CUDA_NODE_KIND(nd.type) == CPROC_CUDA_NODE_PDM) {
+            // pdm.h:13-77: q = sK >> sh; a = (q << sh) + dither; s1 += in - a; sk += s(k-1) - a; out = q
+            const uint32_t o = off[k], K = CPROC_CUDA_NODE_ARG(nd.type) & 7u, sh = CPROC_CUDA_NODE_ARG(nd.type) >> 3;
+            std::string body;
+            snprintf(buf, sizeof(buf), " %s{ const uint32_t vin = %s; const uint32_t q = s%u >> %u; const uint32_t a = (q << %u)", cond.c_str(), in.c_str(), o + K, sh, sh);
+            body = buf;
+            if (K > 1) body += " + " + operand(nd.src2);
+            snprintf(buf, sizeof(buf), "; s%u += vin - a;", o + 1);
+            body += buf;
+            for (uint32_t kk = 2; kk <= K; ++kk) { snprintf(buf, sizeof(buf), " s%u += s%u - a;", o + kk, o + kk - 1); body += buf; }
+            snprintf(buf, sizeof(buf), " s%u = q; }", o);
+            body += buf;
+            tick += body;
+            continue;
+        }
         if (CPROC_CUDA_NODE_KIND(nd.type) == CPROC_CUDA_NODE_GLIDE) {
             const uint32_t o = off[k], L = CPROC_CUDA_NODE_ARG(nd.type);                  // mod_pdm_pwm.c:129-143, mod_controlrate.c:28-40
             snprintf(buf, sizeof(buf), " %s{ if (s%u == 0) { s%u = s%u; s%u = s%u; s%u += s%u << %u; s%u = (uint32_t)((int32_t)(%s - s%u) >> %u); } s%u += s%u; s%u = (s%u + 1) & 0x%xu; }",
@@ -513,10 +560,8 @@ extern "C" int cproc_cuda_graph_jit_source(const cproc_cuda_node *nodes, uint32_
     if (!nodes || n_nodes == 0 || n_nodes > CPROC_CUDA_GRAPH_MAX_NODES || out_node >= n_nodes || n_inputs == 0)
         return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_jit_source: bad node table");
     for (uint32_t k = 0; k < n_nodes; ++k)
-        if (CPROC_CUDA_NODE_KIND(nodes[k].type) > CPROC_CUDA_NODE_GLIDE || (nodes[k].type >> 16) ||
-            (CPROC_CUDA_NODE_KIND(nodes[k].type) == CPROC_CUDA_NODE_GLIDE) != (CPROC_CUDA_NODE_ARG(nodes[k].type) != 0) || CPROC_CUDA_NODE_ARG(nodes[k].type) > 24 ||
-            nodes[k].src >= (int32_t)k || (nodes[k].src < 0 && (uint32_t)(-(nodes[k].src + 1)) >= n_inputs))
-            return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_jit_source: node %u invalid", k);
+        if (const char *why = cproc_node_check(nodes[k], k, n_inputs))
+            return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_jit_source: node %u: %s", k, why);
     const std::string s = cproc_graph_jit_source(std::vector<cproc_cuda_node>(nodes, nodes + n_nodes), n_inputs, out_node, has_changed != 0);
     if (dst && cap) { const size_t n = s.size() < cap - 1 ? s.size() : cap - 1; memcpy(dst, s.data(), n); dst[n] = 0; }
     return (int)s.size();

@@ -25,9 +25,17 @@ struct GraphParams {
 
 // acc_update (cproc.h:140-142) / edge_update (cproc.h:151-154) on register state
 // glide: mod_pdm_pwm.c:129-143 + mod_controlrate.c:28-40 on one parameter (see cproc_cuda.h)
-__device__ __forceinline__ void node_tick(uint32_t type, uint32_t *s, uint32_t x) {
+__device__ __forceinline__ void node_tick(uint32_t type, uint32_t *s, uint32_t x, uint32_t x2) {
     const uint32_t kind = type & 0xFFu;
     if (kind == CPROC_CUDA_NODE_EDGE) { s[0] = (x != s[1]); s[1] = x; }
+    else if (kind == CPROC_CUDA_NODE_PDM) {                 // pdm.h:13-77: s[0] = out_q, s[1..K] = s1..sK
+        const uint32_t K = (type >> 8) & 7u, sh = (type >> 11) & 31u;
+        const uint32_t q = s[K] >> sh;
+        const uint32_t a = (q << sh) + (K == 1 ? 0u : x2);
+        s[1] += x - a;
+        for (uint32_t k = 2; k <= K; ++k) s[k] += s[k - 1] - a;
+        s[0] = q;
+    }
     else if (kind == CPROC_CUDA_NODE_GLIDE) {
         const uint32_t L = (type >> 8) & 0xFFu;
         if (s[4] == 0) {
@@ -77,7 +85,7 @@ __global__ void k_graph_table(const GraphParams p) {
         for (uint32_t k = 0; k < p.n_nodes; ++k) {
             nodes[k] = p.nodes[k]; off[k] = o;
             const uint32_t kind = nodes[k].type & 0xFFu;
-            o += kind == CPROC_CUDA_NODE_EDGE ? 2u : (kind == CPROC_CUDA_NODE_GLIDE ? 5u : 1u);
+            o += kind == CPROC_CUDA_NODE_EDGE ? 2u : (kind == CPROC_CUDA_NODE_GLIDE ? 5u : (kind == CPROC_CUDA_NODE_PDM ? 1u + ((nodes[k].type >> 8) & 7u) : 1u));
         }
     }
     __syncthreads();
@@ -91,13 +99,14 @@ __global__ void k_graph_table(const GraphParams p) {
         const uint32_t g = p.changed ? p.changed[oidx] : 0xFFFFFFFFu;
         for (uint32_t k = 0; k < p.n_nodes; ++k) {
             if (!(g & nodes[k].cond_mask)) continue;
-            uint32_t x;
-            if (nodes[k].src >= 0) x = s[off[nodes[k].src]];
-            else {
-                const uint32_t j = (uint32_t)(-(nodes[k].src + 1));
-                x = p.in[il ? (t * p.n_inputs + j) * p.n + i : (i * p.n_inputs + j) * p.F + t];
-            }
-            node_tick(nodes[k].type, s + off[k], x);
+            auto fetch = [&](int32_t src) {
+                if (src >= 0) return s[off[src]];
+                const uint32_t j = (uint32_t)(-(src + 1));
+                return p.in[il ? (t * p.n_inputs + j) * p.n + i : (i * p.n_inputs + j) * p.F + t];
+            };
+            const uint32_t x = fetch(nodes[k].src);
+            const uint32_t x2 = (nodes[k].type & 0xFFu) == CPROC_CUDA_NODE_PDM ? fetch(nodes[k].src2) : 0u;
+            node_tick(nodes[k].type, s + off[k], x, x2);
         }
         p.out[oidx] = s[off[p.out_node]];
     }

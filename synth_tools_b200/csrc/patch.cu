@@ -20,7 +20,7 @@ namespace {
 struct ClassMeta {
     const char *name;
     uint32_t n_state; const char *state[5];
-    uint32_t n_input; const char *input[1];
+    uint32_t n_input; const char *input[2];
     uint32_t n_param;
     uint32_t n_config; const char *config[1];
 };
@@ -31,9 +31,10 @@ const ClassMeta k_classes[] = {
     {"edge",  2, {"out", "last"},                         1, {"in"}, 0, 0, {nullptr}},
     {"glide", 5, {"out", "vel0", "pos1", "vel1", "count"}, 1, {"in"}, 0, 1, {"div_log"}},
     {"input", 0, {nullptr},                               0, {nullptr}, 0, 1, {"index"}},
+    {"pdm",   5, {"out", "s1", "s2", "s3", "s4"},         2, {"in", "dither"}, 0, 1, {"order_shift"}},   // config = K | out_shift << 3; state fields 0..K
 };
 const uint32_t k_n_classes = sizeof(k_classes) / sizeof(k_classes[0]);
-enum { CLS_ACC = 0, CLS_EDGE = 1, CLS_GLIDE = 2, CLS_INPUT = 3 };
+enum { CLS_ACC = 0, CLS_EDGE = 1, CLS_GLIDE = 2, CLS_INPUT = 3, CLS_PDM = 4 };
 }  // namespace
 
 struct cproc_cuda_patch {
@@ -120,6 +121,14 @@ int cproc_cuda_patch_apply(cproc_cuda_patch *p, uint32_t cls, const uint32_t *in
         cproc_cuda_node row;
         row.cond_mask = 0xFFFFFFFFu;                        // tick() runs every instance (:71-77)
         row.src = src.table >= 0 ? src.table : -(int32_t)src.input - 1;
+        row.src2 = 0;
+        if (cls == CLS_PDM) {
+            if (in_nodes[1] >= p->nodes.size()) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch_apply: bad_node: %u", in_nodes[1]);
+            const cproc_cuda_patch::PNode &s2 = p->nodes[in_nodes[1]];
+            row.src2 = s2.table >= 0 ? s2.table : -(int32_t)s2.input - 1;
+            if ((config & 7u) < 1 || (config & 7u) > 4 || (config >> 3) > 31) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch_apply: pdm config must be order 1..4 | out_shift << 3");
+            row.type = CPROC_CUDA_NODE_PDM | (config << 8);
+        } else
         if (cls == CLS_GLIDE) {
             if (config < 1 || config > 24) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch_apply: glide div_log must be 1..24");
             row.type = CPROC_CUDA_NODE_GLIDE_L(config);
@@ -177,7 +186,8 @@ static int patch_word(cproc_cuda_patch *p, uint32_t node, uint32_t kind, uint32_
     if (node >= p->nodes.size()) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch: bad_ref: node %u", node);
     const cproc_cuda_patch::PNode &pn = p->nodes[node];
     if (kind != 1) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch: bad_ref: %s has no param fields", k_classes[pn.cls].name);   // params are not stored in the reference either (:166, :184)
-    if (field >= k_classes[pn.cls].n_state) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch: bad_ref: %s state field %u", k_classes[pn.cls].name, field);
+    const uint32_t n_fields = pn.table >= 0 ? cproc_node_words(p->rows[pn.table].type) : 0;   // pdm: 1 + order of this instance
+    if (field >= k_classes[pn.cls].n_state || field >= n_fields) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch: bad_ref: %s state field %u", k_classes[pn.cls].name, field);
     if (instance >= p->n) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch: bad_ref: instance %llu", (unsigned long long)instance);
     int rc = patch_build(p);
     if (rc) return rc;

@@ -24,13 +24,13 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert hasattr(raw, n), "libcproc_cuda.so does not export %s" % n
         assert n in abi.SYMBOLS, "abi.py does not bind %s" % n
     assert sorted(abi.SYMBOLS) == names
-    assert abi.lib.cproc_cuda_abi_version() == 1
+    assert abi.lib.cproc_cuda_abi_version() == 2
 
 
 def test_header_is_plain_c99(tmp_path):
     import subprocess
     c = tmp_path / "t.c"
-    c.write_text('#include "cproc_cuda.h"\nint main(void){ cproc_cuda_config c = {0}; cproc_cuda_io io = {0}; (void)c; (void)io; return sizeof(cproc_cuda_node) == 12 ? 0 : 1; }\n')
+    c.write_text('#include "cproc_cuda.h"\nint main(void){ cproc_cuda_config c = {0}; cproc_cuda_io io = {0}; (void)c; (void)io; return sizeof(cproc_cuda_node) == 16 ? 0 : 1; }\n')
     exe = tmp_path / "t"
     subprocess.check_call(["gcc", "-std=gnu99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
     assert subprocess.call([str(exe)]) == 0

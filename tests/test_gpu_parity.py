@@ -343,15 +343,16 @@ def test_pwm(st, ctx, oracle):
 
 # ------------------------------------------------------------------------- graphs
 def _graph_case(st, ctx, oracle, rows, layout, masked, N=150, F=64, out_node=None, jit=1):
-    n_in = max(1, max(-s for _, s, _ in rows))
+    n_in = max(1, max(max(-r[1], -r[3] if len(r) > 3 else 0) for r in rows))
     out_node = len(rows) - 1 if out_node is None else out_node
     inp = rng.integers(0, 2, (N, n_in, F), dtype=np.uint32)
     inp[::7] = rng.integers(0, 2**32, inp[::7].shape, dtype=np.uint32)
     changed = rng.integers(0, 8, (N, F), dtype=np.uint32) if masked else None
-    sw = sum(po.node_words(t) for t, _, _ in rows)
+    sw = sum(po.node_words(r[0]) for r in rows)
     s0 = rng.integers(0, 2**32, (N, sw), dtype=np.uint32)
     o = 0
-    for t, _, _ in rows:                                   # glide: the divider count lives below 2^L
+    for r in rows:                                         # glide: the divider count lives below 2^L
+        t = r[0]
         if t & 0xFF == po.NODE_GLIDE:
             s0[:, o + 4] &= (1 << (t >> 8)) - 1
         o += po.node_words(t)
@@ -392,15 +393,20 @@ def test_graph(st, ctx, oracle, rows, layout, masked, jit):
     _graph_case(st, ctx, oracle, rows, layout, masked, jit=jit)
 
 
-def _random_graph(n_nodes, n_in, seed, glide=False):
+def _random_graph(n_nodes, n_in, seed, glide=False, pdm=False):
     r = np.random.default_rng(seed)
     rows = []
     for k in range(n_nodes):
         src = int(r.integers(-n_in, k)) if k else -int(r.integers(1, n_in + 1))
-        t = int(r.integers(0, 3 if glide else 2))
+        t = int(r.integers(0, 4 if pdm else (3 if glide else 2)))
+        mask = int(r.choice([1, 2, 3, 4, 6, 0xFFFFFFFF]))
         if t == po.NODE_GLIDE:
-            t = po.node_glide(int(r.integers(1, 7)))
-        rows.append((t, src, int(r.choice([1, 2, 3, 4, 6, 0xFFFFFFFF]))))
+            rows.append((po.node_glide(int(r.integers(1, 7))), src, mask))
+        elif t == po.NODE_PDM:
+            src2 = int(r.integers(-n_in, k)) if k else -int(r.integers(1, n_in + 1))
+            rows.append((po.node_pdm(int(r.integers(1, 5)), int(r.choice([0, 8, 24, 31]))), src, mask, src2))
+        else:
+            rows.append((t, src, mask))
     return rows
 
 
@@ -422,8 +428,54 @@ def test_graph_with_glide_nodes(st, ctx, oracle, n_nodes, n_in, N, F, jit, layou
     """Graphs that contain glide nodes (control-rate -> audio-rate line interpolation,
     mod_pdm_pwm.c:97-143 / mod_controlrate.c:28-40) with dividers 2..64, JIT and table kernels."""
     rows = _random_graph(n_nodes, n_in, seed=n_nodes * 17 + n_in, glide=True)
-    assert any(t & 0xFF == po.NODE_GLIDE for t, _, _ in rows)
+    assert any(r[0] & 0xFF == po.NODE_GLIDE for r in rows)
     _graph_case(st, ctx, oracle, rows, layout, masked, N=N, F=F, out_node=n_nodes - 1, jit=jit)
+
+
+@pytest.mark.parametrize("n_nodes,n_in,N,F,jit", [(10, 2, 300, 256, 1), (8, 3, 100, 96, 0), (30, 3, 97, 100, 1)])
+@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
+@pytest.mark.parametrize("masked", [False, True])
+def test_graph_with_pdm_nodes(st, ctx, oracle, n_nodes, n_in, N, F, jit, layout, masked):
+    """Graphs with pdmK nodes (two inputs, orders 1..4, several shifts) mixed with acc / edge / glide."""
+    rows = _random_graph(n_nodes, n_in, seed=n_nodes * 29 + n_in, pdm=True)
+    assert any(r[0] & 0xFF == po.NODE_PDM for r in rows)
+    _graph_case(st, ctx, oracle, rows, layout, masked, N=N, F=F, out_node=n_nodes - 1, jit=jit)
+
+
+@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
+def test_v2_channel_as_a_generated_graph(st, ctx, oracle, layout):
+    """The firmware's whole v2 channel (mod_pdm_pwm.c:97-116) written as generated graph text --
+    glide(setpoint) -> pdm2(in, dither) -- and compiled by the JIT: its output stream is the duty
+    stream of the hand-written PDM v2 kernel and of the v2 channel oracle, byte for byte."""
+    N, F, L = 500, 2048, 6
+    rows, n_in, out_node, _ = st.graph_parse("""
+        #define CPROC_NB_INPUTS 2
+        void cproc_update(w *input, w g) {
+            PROC(line, glide, &(glide_config){ .div_log = 6 }, NULL, .in = input[0]);
+            PROC(mod, pdm2, &(pdm_config){ .out_shift = 24 }, NULL, .in = line.out, .dither = input[1]);
+            cproc_output(0, mod.out);
+        }""")
+    sp = po.pdm_setpoints(N, (F >> L) + 1)
+    dext = rng.integers(0, 2**32, (N, F), dtype=np.uint32)
+    chan = np.zeros((N, 7), np.uint32)
+    want, _ = oracle.pdm_v2_run(chan, 2, N, 1, np.ones(N, np.uint32), dext, 0x3FF, 0, L, 24, sp, F)
+    inp = np.zeros((N, 2, F), np.uint32)
+    inp[:, 0, :] = np.repeat(sp.T, 1 << L, axis=1)[:, :F]
+    inp[:, 1, :] = dext & 0x3FF
+    il = layout == "INTERLEAVED"
+    b = ctx.batch(st.GRAPH, N, nodes=rows, n_inputs=n_in, out_node=out_node, layout=getattr(st, layout))
+    out = np.zeros((F, N) if il else (N, F), np.uint32)
+    b.run(F, inp=np.ascontiguousarray(inp.transpose(2, 1, 0)) if il else inp, out=out)
+    got = out.T if il else out
+    assert got.max() < 256 and np.array_equal(got.astype(np.uint8), want)
+    gs = b.download_state()
+    assert np.array_equal(gs[:, 0:4], chan[:, 1:5]) and np.array_equal(gs[:, 6:8], chan[:, 5:7])
+    # and the hand-written v2 kernel with the same external dither
+    bv = ctx.batch(st.PDM_V2, N, order=2, bank_size=1, ctl_div_log=L, layout=st.PLANAR)
+    duty = np.zeros((N, F), np.uint8)
+    bv.run(F, in2=dext, ctl=sp, out=duty)
+    assert np.array_equal(duty, got.astype(np.uint8))
+    b.free(); bv.free()
 
 
 def test_glide_node_is_the_pdm_v2_line(st, ctx, oracle):

@@ -86,6 +86,32 @@ def test_patch_glide_portamento_and_reset(st, ctx, oracle):
     p.close()
 
 
+def test_patch_pdm_channel(st, ctx, oracle):
+    """apply(glide), apply(pdm): the v2 channel patched together at run time."""
+    N, F, L = 40, 640, 5
+    p = st.Patch(ctx, N, n_inputs=2)
+    sp_in, di_in = p.apply("input", config=0), p.apply("input", config=1)
+    line = p.apply("glide", sp_in, config=L)
+    mod = p.apply("pdm", line, di_in, config=2 | (24 << 3))
+    p.output(mod)
+    rows = [(po.node_glide(L), -1, 0xFFFFFFFF), (po.node_pdm(2, 24), 0, 0xFFFFFFFF, -2)]
+    inp = rng.integers(0, 2**32, (N, 2, F), dtype=np.uint32)
+    inp[:, 1] &= 0x3FF
+    state = np.zeros((N, 8), np.uint32)
+    want = oracle.graph_run(rows, 2, 1, state, N, F, inp)
+    out = np.zeros((N, F), np.uint32)
+    p.tick(F, inp, out)
+    assert np.array_equal(out, want)
+    assert p.get(mod, 1, 7) == state[7, 6] and p.get(mod, 2, 7) == state[7, 7]      # s1, s2 of instance 7
+    with pytest.raises(st.CprocCudaError):
+        p.get(mod, 3, 0)                                   # an order-2 instance has fields out, s1, s2
+    with pytest.raises(st.CprocCudaError):
+        p.apply("pdm", line, di_in, config=5 | (24 << 3))
+    with pytest.raises(st.CprocCudaError):
+        p.apply("pdm", line)
+    p.close()
+
+
 def test_patch_errors(st, ctx):
     p = st.Patch(ctx, 8, n_inputs=1)
     with pytest.raises(st.CprocCudaError):                 # bad_node (mod_bpmodular.c:106-110)
