@@ -145,6 +145,10 @@ enum { CPROC_CUDA_NODE_ACC = 0, CPROC_CUDA_NODE_EDGE = 1, CPROC_CUDA_NODE_GLIDE 
 enum { CPROC_CUDA_MIX_SAW = 0, CPROC_CUDA_MIX_SQUARE = 1 };
 enum { CPROC_CUDA_XVOICE_SEQ = 0, CPROC_CUDA_XVOICE_SCAN = 1 };
 enum { CPROC_CUDA_ONEPOLE_SEQ = 0, CPROC_CUDA_ONEPOLE_SCAN = 1 };
+/* GRAPH batches of acc / edge nodes only: cfg.mode = CPROC_CUDA_GRAPH_SCAN renders time-parallel
+ * and still bit-exact (prefix sums and an associative composition of the edge detector's maps
+ * over time chunks) -- for few instances and long streams, e.g. the reference's single voice. */
+enum { CPROC_CUDA_GRAPH_SEQ = 0, CPROC_CUDA_GRAPH_SCAN = 1 };
 
 /* Stream layouts (per-instance streams `x[inst][frame]`). */
 enum {

@@ -123,6 +123,7 @@ int cproc_io_bytes(const cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *i
 
 // Kernel launchers (one translation unit per family).
 int launch_graph(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
+int launch_graph_scan(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
 int cproc_graph_jit_get(cproc_cuda_batch *b, bool has_changed, cproc_graph_jit **out);
 int launch_pdm(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
 int launch_pdm_v1(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);

@@ -118,6 +118,7 @@ int launch_graph(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     if (!io->out || !io->in) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "graph: in/out is NULL");
     if (io->layout == CPROC_CUDA_TILED) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "graph: TILED layout not supported");
     if (F == 0) return 0;
+    if (b->cfg.mode == CPROC_CUDA_GRAPH_SCAN && F > 64) return launch_graph_scan(b, F, io);
     GraphParams p;
     p.st = b->d_state; p.npad = b->npad; p.n = b->n; p.nodes = b->d_nodes;
     p.n_nodes = b->cfg.n_nodes; p.n_inputs = b->cfg.n_inputs; p.out_node = b->cfg.out_node;

@@ -503,6 +503,48 @@ def test_glide_node_is_the_pdm_v2_line(st, ctx, oracle):
     b.free(); bp.free()
 
 
+@pytest.mark.parametrize("rows", [po.GRAPH_TEST_CPROC, po.GRAPH_BP5,
+                                  [(po.NODE_ACC, -1, 1), (po.NODE_EDGE, -2, 2), (po.NODE_EDGE, 1, 4), (po.NODE_ACC, 2, 3), (po.NODE_ACC, 0, 6), (po.NODE_EDGE, 3, 0xFFFFFFFF)],
+                                  [(po.NODE_EDGE, -1, 0)]])
+@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
+@pytest.mark.parametrize("masked", [False, True])
+@pytest.mark.parametrize("N,F,chunk", [(1, 50000, 0), (3, 4099, 64), (70, 1000, 7), (2, 65, 1)])
+def test_graph_scan(st, ctx, oracle, rows, layout, masked, N, F, chunk):
+    """Time-parallel acc / edge graphs: bit-exact against the sequential oracle, output stream and
+    every state word, for ragged chunkings, sparse masks (long runs without an executed tick), an
+    interior output node and a never-executed node."""
+    n_in = max(1, max(-r[1] for r in rows))
+    out_node = min(2, len(rows) - 1)
+    inp = rng.integers(0, 2, (N, n_in, F), dtype=np.uint32)
+    inp[:, :, ::17] = rng.integers(0, 2**32, inp[:, :, ::17].shape, dtype=np.uint32)
+    changed = None
+    if masked:
+        changed = rng.integers(0, 8, (N, F), dtype=np.uint32)
+        changed[:, F // 3: F // 3 + min(F // 3, 300)] = 0                 # a stretch where nothing executes
+    sw = sum(po.node_words(r[0]) for r in rows)
+    s0 = rng.integers(0, 2**32, (N, sw), dtype=np.uint32)
+    sa = s0.copy()
+    want = oracle.graph_run(rows, n_in, out_node, sa, N, F, inp, changed)
+    ctx.set_option("xvoice_chunk", chunk)
+    try:
+        b = ctx.batch(st.GRAPH, N, nodes=rows, n_inputs=n_in, out_node=out_node, layout=getattr(st, layout), mode=1)
+        b.upload_state(s0)
+        il = layout == "INTERLEAVED"
+        out = np.zeros((F, N) if il else (N, F), np.uint32)
+        l0 = ctx.launches
+        b.run(F, inp=np.ascontiguousarray(inp.transpose(2, 1, 0)) if il else inp,
+              in2=None if changed is None else (np.ascontiguousarray(changed.T) if il else changed), out=out)
+        assert ctx.launches - l0 >= 3 * len(rows)          # reduce, scan, apply per node
+        assert np.array_equal(out.T if il else out, want)
+        assert np.array_equal(b.download_state(), sa)
+        b.free()
+    finally:
+        ctx.set_option("xvoice_chunk", 0)
+    with pytest.raises(st.CprocCudaError):                 # glide / pdm are not scannable
+        bb = ctx.batch(st.GRAPH, 2, nodes=[(st.node_glide(4), -1, 1)], mode=1)
+        bb.run(128, inp=np.zeros((2, 1, 128), np.uint32), out=np.zeros((2, 128), np.uint32))
+
+
 def test_graph_from_generated_text(st, ctx, oracle):
     """The wire format end to end: the generated C text of the reference's two graphs
     (linux/test_cproc.c:11-17, stm32f103/bp5_plugin.c:1-9) -> parser -> batch -> render."""

@@ -106,3 +106,14 @@ elif which == "onepole_long":
         ms = timed(lambda: b.run_dev(F, inp=d_in, out=d_out))
         print("onepole %d x %d (%s): %.3f ms  %.2f G samples/s  %.0f GB/s" % (N, F, label, ms, N * F / ms / 1e6, 8 * N * F / ms / 1e6))
         b.free()
+elif which == "graph_long":
+    # the reference's own shape: ONE voice of the test_cproc chain, 16 Mi ticks
+    N, F = 1, 16 * 1024 * 1024
+    rows = [(st.NODE_EDGE, -1, 1), (st.NODE_ACC, 0, 1)]
+    d_in = ctx.dev_alloc(4 * N * F); d_out = ctx.dev_alloc(4 * N * F)
+    ctx.h2d(d_in, rng.integers(0, 2, (N, F), dtype=np.uint32))
+    for mode, label in ((0, "sequential (generated kernel)"), (1, "time-parallel scan")):
+        b = ctx.batch(st.GRAPH, N, nodes=rows, mode=mode)
+        ms = timed(lambda: b.run_dev(F, inp=d_in, out=d_out))
+        print("test_cproc graph %d x %d (%s): %.3f ms  %.2f G ticks/s" % (N, F, label, ms, N * F / ms / 1e6))
+        b.free()
