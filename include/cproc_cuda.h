@@ -66,7 +66,8 @@ enum cproc_cuda_proc {
      * pdm: K+1 words).
      * in:  uint32 [inst][n_inputs][F]; in2: changed mask uint32 [inst][F] or
      * NULL (= -1, mod_cproc_plugin.c:32); out: uint32 [inst][F], the value
-     * passed to cproc_output() each tick (test_cproc.c:16). */
+     * passed to cproc_output() each tick (test_cproc.c:16); with several
+     * cproc_output statements [inst][n_outputs][F]. */
     CPROC_CUDA_GRAPH = 1,
     /* pdmK_update, K = cfg.order (pdm.h).  state record: struct pdmK.
      * param record: {uint32 input} used when in == NULL.  in: uint32
@@ -182,8 +183,12 @@ typedef struct {
     /* graph */
     const cproc_cuda_node *nodes;
     uint32_t n_nodes, n_inputs, out_node;
-    uint32_t reserved;
+    uint32_t n_outputs;       /* 0 / 1: one output stream, the .out of node out_node          */
+    const uint32_t *out_nodes;/* n_outputs > 1: the nodes behind the cproc_output() calls, in
+                                 order; out is then uint32 [inst][n_outputs][F] (PLANAR) /
+                                 [F][n_outputs][inst] (INTERLEAVED), like the input streams   */
 } cproc_cuda_config;
+#define CPROC_CUDA_GRAPH_MAX_OUTPUTS 16
 
 /* Front end for the generated graph text.  `text` is what
  * epid_cproc.erl emits and the reference compiles as C (linux/test_cproc.c:11-17,
@@ -191,12 +196,14 @@ typedef struct {
  *   PROC_COND(<changed> & <mask>, <inst>, acc|edge, NULL, NULL, .in = input[k] | <inst>.out);
  *   PROC_COND(<changed> & <mask>, <inst>, glide, &(glide_config){.div_log = L}, NULL, .in = ...);
  *   PROC_COND(<changed> & <mask>, <inst>, pdm1..pdm4, &(pdm_config){.out_shift = S}, NULL, .in = ..., .dither = ...);
- * (or PROC(<inst>, ...), cproc.h:81) and one `cproc_output(<index>, <inst>.out);`.
+ * (or PROC(<inst>, ...), cproc.h:81) and one or more `cproc_output(<index>, <inst>.out);`.
  * Fills `nodes` (at most max_nodes rows) and `info`; the rows go into
  * cproc_cuda_config.nodes / n_nodes / n_inputs / out_node unchanged.  Needs no device. */
 typedef struct {
     uint32_t n_nodes, n_inputs, out_node;
     uint32_t out_index;       /* first argument of cproc_output (the TAG_U32 index, mod_cproc_plugin.c:40-43) */
+    uint32_t n_outputs;       /* number of cproc_output statements (out_node / out_index are the first)      */
+    uint32_t out_nodes[16], out_indices[16];
 } cproc_cuda_graph_info;
 int  cproc_cuda_graph_parse(const char *text, cproc_cuda_node *nodes, uint32_t max_nodes, cproc_cuda_graph_info *info);
 
@@ -266,8 +273,8 @@ int  cproc_cuda_run_stream(cproc_cuda_batch *b, uint64_t n_frames_total,
  * the generated CUDA source for a node table (returns its length; copies at most
  * cap-1 bytes; needs no device). */
 const char *cproc_cuda_graph_jit_log(const cproc_cuda_batch *b);
-int  cproc_cuda_graph_jit_source(const cproc_cuda_node *nodes, uint32_t n_nodes, uint32_t n_inputs, uint32_t out_node,
-                                 int has_changed, char *dst, size_t cap);
+int  cproc_cuda_graph_jit_source(const cproc_cuda_node *nodes, uint32_t n_nodes, uint32_t n_inputs,
+                                 const uint32_t *out_nodes, uint32_t n_outputs, int has_changed, char *dst, size_t cap);
 
 /* ---- dynamic patcher ---------------------------------------- */
 /* The run-time way to build a graph: the RPC tree of stm32f103/mod_bpmodular.c

@@ -85,6 +85,42 @@ void orc_graph_run(const orc_node *nodes, uint32_t n_nodes, uint32_t n_inputs,
     }
 }
 
+void orc_graph_run_multi(const orc_node *nodes, uint32_t n_nodes, uint32_t n_inputs,
+                         const uint32_t *out_nodes, uint32_t n_out, uint32_t *state, uint64_t N, uint64_t F,
+                         const uint32_t *in, const uint32_t *changed, uint32_t *out) {
+    uint32_t sw = orc_graph_state_words(nodes, n_nodes);
+    uint32_t off[64];
+    uint32_t o = 0;
+    for (uint32_t i = 0; i < n_nodes && i < 64; i++) { off[i] = o; o += orc_node_state_words(nodes[i].type); }
+#pragma omp parallel for schedule(static)
+    for (int64_t n = 0; n < (int64_t)N; n++) {
+        uint32_t *st = state + (uint64_t)n * sw;
+        for (uint64_t t = 0; t < F; t++) {
+            uint32_t g = changed ? changed[(uint64_t)n * F + t] : 0xFFFFFFFFu;
+            for (uint32_t i = 0; i < n_nodes; i++) {
+                if (!(g & nodes[i].cond_mask)) continue;
+                uint32_t x = nodes[i].src >= 0
+                    ? st[off[nodes[i].src]] /* .out is the first state word */
+                    : in[((uint64_t)n * n_inputs + (uint32_t)(-(nodes[i].src + 1))) * F + t];
+                if ((nodes[i].type & 0xFF) == ORC_NODE_PDM) {
+                    uint32_t d = nodes[i].src2 >= 0 ? st[off[nodes[i].src2]]
+                        : in[((uint64_t)n * n_inputs + (uint32_t)(-(nodes[i].src2 + 1))) * F + t];
+                    uint32_t order = (nodes[i].type >> 8) & 7u, sh = (nodes[i].type >> 11) & 31u;
+                    st[off[i]] = orc_pdm_update(st + off[i] + 1, order, x, sh, d);   /* pdm.h:13-77 */
+                    continue;
+                }
+                switch (nodes[i].type & 0xFF) {
+                case ORC_NODE_EDGE: orc_edge_update((orc_edge_state *)(st + off[i]), x); break;
+                case ORC_NODE_GLIDE: orc_glide_update((orc_glide_state *)(st + off[i]), x, (nodes[i].type >> 8) & 0xFF); break;
+                default: orc_acc_update((orc_acc_state *)(st + off[i]), x); break;
+                }
+            }
+            for (uint32_t q = 0; q < n_out; q++) out[((uint64_t)n * n_out + q) * F + t] = st[off[out_nodes[q]]];
+        }
+    }
+}
+
+
 /* ======================================================================= */
 /* stm32f103/pdm.h                                                          */
 

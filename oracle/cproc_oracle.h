@@ -74,6 +74,11 @@ void orc_graph_run(const orc_node *nodes, uint32_t n_nodes, uint32_t n_inputs,
                    uint32_t out_node, uint32_t *state, uint64_t N, uint64_t F,
                    const uint32_t *in, const uint32_t *changed, uint32_t *out);
 
+/* Several cproc_output() statements: out [N][n_out][F], out_nodes[q] = node behind output q. */
+void orc_graph_run_multi(const orc_node *nodes, uint32_t n_nodes, uint32_t n_inputs,
+                         const uint32_t *out_nodes, uint32_t n_out, uint32_t *state, uint64_t N, uint64_t F,
+                         const uint32_t *in, const uint32_t *changed, uint32_t *out);
+
 /* ---- stm32f103/pdm.h:10-77 -------------------------------------------- */
 /* s[0..order-1] = s1..sK.  order 1 ignores dither (pdm.h:13). */
 uint32_t orc_pdm_update(uint32_t *s, uint32_t order, uint32_t input,

@@ -107,6 +107,15 @@ class _Lib:
         f(_ptr(nodes), len(rows), n_inputs, out_node, _ptr(state), N, F, _ptr(inp), _ptr(changed), _ptr(out))
         return out
 
+    def graph_run_multi(self, rows, n_inputs, out_nodes, state, N, F, inp, changed=None):
+        """Several cproc_output statements: returns out [N][len(out_nodes)][F]."""
+        nodes = make_nodes(rows)
+        outs = np.asarray(out_nodes, np.uint32)
+        out = np.zeros((N, len(outs), F), np.uint32)
+        f = self._fn("graph_run_multi", None, [VP, C.c_uint32, C.c_uint32, VP, C.c_uint32, VP, C.c_uint64, C.c_uint64, VP, VP, VP])
+        f(_ptr(nodes), len(rows), n_inputs, _ptr(outs), len(outs), _ptr(state), N, F, _ptr(inp), _ptr(changed), _ptr(out))
+        return out
+
     def pdm_run(self, order, state, N, F, inp, in_const, out_shift, dither):
         out = np.zeros((N, F), np.uint32)
         f = self._fn("pdm_run", None, [C.c_uint32, VP, C.c_uint64, C.c_uint64, VP, VP, C.c_uint32, VP, VP])

@@ -49,11 +49,13 @@ class Config(C.Structure):
     _fields_ = [("proc", C.c_uint32), ("layout", C.c_uint32), ("order", C.c_uint32), ("out_shift", C.c_uint32),
                 ("bank_size", C.c_uint32), ("dither_mask", C.c_uint32), ("ctl_div_log", C.c_uint32),
                 ("mode", C.c_uint32), ("voices_per_bus", C.c_uint64), ("nodes", C.POINTER(Node)),
-                ("n_nodes", C.c_uint32), ("n_inputs", C.c_uint32), ("out_node", C.c_uint32), ("reserved", C.c_uint32)]
+                ("n_nodes", C.c_uint32), ("n_inputs", C.c_uint32), ("out_node", C.c_uint32), ("n_outputs", C.c_uint32),
+                ("out_nodes", C.POINTER(C.c_uint32))]
 
 
 class GraphInfo(C.Structure):
-    _fields_ = [("n_nodes", C.c_uint32), ("n_inputs", C.c_uint32), ("out_node", C.c_uint32), ("out_index", C.c_uint32)]
+    _fields_ = [("n_nodes", C.c_uint32), ("n_inputs", C.c_uint32), ("out_node", C.c_uint32), ("out_index", C.c_uint32),
+                ("n_outputs", C.c_uint32), ("out_nodes", C.c_uint32 * 16), ("out_indices", C.c_uint32 * 16)]
 
 
 GRAPH_MAX_NODES = 64
@@ -122,7 +124,7 @@ SYMBOLS = {
     "cproc_cuda_bus_destroy": (C.c_int, [C.c_void_p]),
     "cproc_cuda_graph_parse": (C.c_int, [C.c_char_p, C.POINTER(Node), C.c_uint32, C.POINTER(GraphInfo)]),
     "cproc_cuda_graph_jit_log": (C.c_char_p, [C.c_void_p]),
-    "cproc_cuda_graph_jit_source": (C.c_int, [C.POINTER(Node), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_char_p, C.c_size_t]),
+    "cproc_cuda_graph_jit_source": (C.c_int, [C.POINTER(Node), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.c_int, C.c_char_p, C.c_size_t]),
 }
 
 
@@ -159,14 +161,28 @@ def graph_parse(text):
     return rows, info.n_inputs, info.out_node, info.out_index
 
 
+def graph_parse_outputs(text):
+    """Like graph_parse, for graphs with several cproc_output statements:
+    (rows, n_inputs, [out_node...], [out_index...])."""
+    nodes = (Node * GRAPH_MAX_NODES)()
+    info = GraphInfo()
+    rc = lib.cproc_cuda_graph_parse(text.encode(), nodes, GRAPH_MAX_NODES, C.byref(info))
+    if rc:
+        raise CprocCudaError(rc, (lib.cproc_cuda_last_error(None) or b"").decode())
+    rows = [_row(nodes[k]) for k in range(info.n_nodes)]
+    return rows, info.n_inputs, list(info.out_nodes[:info.n_outputs]), list(info.out_indices[:info.n_outputs])
+
+
 def graph_jit_source(rows, n_inputs, out_node, has_changed=False):
     """The CUDA source the library generates (and NVRTC-compiles) for a node table."""
     arr = (Node * len(rows))(*[_node(r) for r in rows])
-    n = lib.cproc_cuda_graph_jit_source(arr, len(rows), n_inputs, out_node, int(has_changed), None, 0)
+    outs = [out_node] if isinstance(out_node, int) else list(out_node)
+    oarr = (C.c_uint32 * len(outs))(*outs)
+    n = lib.cproc_cuda_graph_jit_source(arr, len(rows), n_inputs, oarr, len(outs), int(has_changed), None, 0)
     if n < 0:
         raise CprocCudaError(n, (lib.cproc_cuda_last_error(None) or b"").decode())
     buf = C.create_string_buffer(n + 1)
-    lib.cproc_cuda_graph_jit_source(arr, len(rows), n_inputs, out_node, int(has_changed), buf, n + 1)
+    lib.cproc_cuda_graph_jit_source(arr, len(rows), n_inputs, oarr, len(outs), int(has_changed), buf, n + 1)
     return buf.value.decode()
 
 
@@ -284,7 +300,13 @@ class Batch:
             cfg.nodes = arr
             cfg.n_nodes = len(nodes)
             cfg.n_inputs = n_inputs
-            cfg.out_node = len(nodes) - 1 if out_node is None else out_node
+            if isinstance(out_node, (list, tuple)):               # several cproc_output statements
+                self._outs = (C.c_uint32 * len(out_node))(*out_node)
+                cfg.out_nodes = self._outs
+                cfg.n_outputs = len(out_node)
+                cfg.out_node = out_node[0]
+            else:
+                cfg.out_node = len(nodes) - 1 if out_node is None else out_node
         h = C.c_void_p()
         ctx._ck(lib.cproc_cuda_alloc(ctx.h, C.byref(cfg), n, C.byref(h)))
         self.h = h

@@ -154,10 +154,14 @@ int cproc_cuda_alloc(cproc_cuda_ctx *ctx, const cproc_cuda_config *cfg, uint64_t
     if (n == 0) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: n_instances is 0");
     cproc_cuda_config c = *cfg;
     std::vector<cproc_cuda_node> nodes;
+    std::vector<uint32_t> outs;
     bool pdm_family = c.proc == CPROC_CUDA_PDM || c.proc == CPROC_CUDA_PDM_V1 || c.proc == CPROC_CUDA_PDM_V2;
     if (c.proc == CPROC_CUDA_GRAPH) {
         if (!c.nodes || c.n_nodes == 0 || c.n_nodes > CPROC_CUDA_GRAPH_MAX_NODES) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph needs 1..%d nodes", CPROC_CUDA_GRAPH_MAX_NODES);
-        if (c.n_inputs == 0 || c.out_node >= c.n_nodes) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph n_inputs/out_node invalid");
+        if (c.n_inputs == 0) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph n_inputs is 0");
+        if (c.n_outputs > CPROC_CUDA_GRAPH_MAX_OUTPUTS || (c.n_outputs > 1 && !c.out_nodes)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph has 1..%d outputs (out_nodes)", CPROC_CUDA_GRAPH_MAX_OUTPUTS);
+        if (c.n_outputs > 1) outs.assign(c.out_nodes, c.out_nodes + c.n_outputs); else outs.assign(1, c.n_outputs == 1 && c.out_nodes ? c.out_nodes[0] : c.out_node);
+        for (uint32_t o : outs) if (o >= c.n_nodes) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph output node %u of %u", o, c.n_nodes);
         nodes.assign(c.nodes, c.nodes + c.n_nodes);
         for (uint32_t k = 0; k < c.n_nodes; ++k) {
             const cproc_cuda_node &nd = nodes[k];
@@ -179,6 +183,8 @@ int cproc_cuda_alloc(cproc_cuda_ctx *ctx, const cproc_cuda_config *cfg, uint64_t
     CK(ctx, cudaSetDevice(ctx->device));
     cproc_cuda_batch *b = new cproc_cuda_batch();
     b->ctx = ctx; b->cfg = c; b->nodes = nodes; b->cfg.nodes = nullptr; b->n = n;
+    b->outs = outs; b->cfg.out_nodes = nullptr;
+    if (c.proc == CPROC_CUDA_GRAPH) { b->cfg.n_outputs = (uint32_t)outs.size(); b->cfg.out_node = outs[0]; }
     b->state_words = sw; b->param_words = pw;
     bool banked = c.proc == CPROC_CUDA_PDM_V1 || c.proc == CPROC_CUDA_PDM_V2;
     if (banked) {
@@ -320,7 +326,7 @@ int cproc_io_bytes(const cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *i
     memset(s, 0, sizeof(*s));
     switch (c.proc) {
     case CPROC_CUDA_GRAPH:
-        s->in = 4 * n * c.n_inputs * F; s->in2 = io->in2 ? 4 * n * F : 0; s->out = 4 * n * F; break;
+        s->in = 4 * n * c.n_inputs * F; s->in2 = io->in2 ? 4 * n * F : 0; s->out = 4 * n * (c.n_outputs ? c.n_outputs : 1) * F; break;
     case CPROC_CUDA_PDM:
         s->in = io->in ? 4 * n * F : 0; s->in2 = io->in2 ? 4 * F : 0; s->out = 4 * n * F; break;
     case CPROC_CUDA_PDM_V1:

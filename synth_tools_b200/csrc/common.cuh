@@ -63,6 +63,7 @@ struct cproc_cuda_batch {
     cproc_cuda_config cfg{};
     std::vector<cproc_cuda_node> nodes;     // copy of cfg.nodes
     std::vector<uint32_t> node_off;         // state word offset per node
+    std::vector<uint32_t> outs;             // graph: output nodes, one per output stream (>= 1)
     uint64_t n = 0;                         // instances
     uint64_t npad = 0;                      // SoA row length (>= n)
     uint64_t n_banks = 0;

@@ -160,6 +160,8 @@ extern "C" int cproc_cuda_graph_parse(const char *text, cproc_cuda_node *nodes, 
             size_t k = 0;
             while (k < names.size() && names[k] != nm) ++k;
             if (k == names.size()) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: cproc_output reads unknown node '%s'", nm.c_str());
+            if (n_out >= CPROC_CUDA_GRAPH_MAX_OUTPUTS) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: more than %d cproc_output statements", CPROC_CUDA_GRAPH_MAX_OUTPUTS);
+            info->out_nodes[n_out] = (uint32_t)k; info->out_indices[n_out] = (uint32_t)idx;
             if (n_out++ == 0) { info->out_node = (uint32_t)k; info->out_index = (uint32_t)idx; }
             continue;
         }
@@ -243,7 +245,7 @@ extern "C" int cproc_cuda_graph_parse(const char *text, cproc_cuda_node *nodes, 
     }
     if (names.empty()) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: no PROC_COND / PROC statement found");
     if (n_out == 0) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: no cproc_output(index, node.out) statement found");
-    if (n_out > 1) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: %u cproc_output statements; a batch renders one output stream", n_out);
+    info->n_outputs = n_out;
     const uint32_t need = any_input ? max_input + 1 : 0;
     if (info->n_inputs == 0) info->n_inputs = need ? need : 1;
     if (info->n_inputs < need) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: input[%u] used but CPROC_NB_INPUTS is %u", max_input, info->n_inputs);
@@ -313,13 +315,16 @@ struct GraphParams {                       // must match k_graph.cu
     uint32_t *out;
     uint64_t F;
     uint32_t layout;
+    uint32_t n_outputs;
+    uint32_t out_nodes[16];
 };
 
-// one tick: x[] = this tick's inputs, g = changed mask; returns the output word
-#define TICK(x, g, o) do { GRAPH_TICK(x, g) o = GRAPH_OUT; } while (0)
+// one tick: x[] = this tick's inputs, g = changed mask; o[] = the output words (GRAPH_NOUT of them)
+#define TICK(x, g, o) do { GRAPH_TICK(x, g) GRAPH_OUTS(o) } while (0)
 
 // [F][n_inputs][inst] in, [F][inst] changed / out: coalesced as they are; 16-frame batches
 // make the independent loads explicit (in may alias out).
+#define GI_B (GRAPH_NIN + GRAPH_NOUT <= 3 ? 16 : 8)        // frames per batch: fewer when many streams are in flight
 extern "C" __global__ void __launch_bounds__(128) graph_interleaved(const GraphParams p) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
@@ -330,26 +335,29 @@ extern "C" __global__ void __launch_bounds__(128) graph_interleaved(const GraphP
     uint32_t *dst = p.out + i;
     const uint64_t n = p.n;
     uint64_t t = 0;
-    for (; t + 16 <= p.F; t += 16) {
-        uint32_t x[16][GRAPH_NIN], g[16], o[16];
+    for (; t + GI_B <= p.F; t += GI_B) {
+        uint32_t x[GI_B][GRAPH_NIN], g[GI_B], o[GI_B][GRAPH_NOUT];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < GI_B; ++k) {
 #pragma unroll
             for (int j = 0; j < GRAPH_NIN; ++j) x[k][j] = __ldcs(src + ((t + k) * GRAPH_NIN + j) * n);
             g[k] = GRAPH_HAS_CHANGED ? __ldcs(chg + (t + k) * n) : 0xFFFFFFFFu;
         }
 #pragma unroll
-        for (int k = 0; k < 16; ++k) TICK(x[k], g[k], o[k]);
+        for (int k = 0; k < GI_B; ++k) TICK(x[k], g[k], o[k]);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) __stcs(dst + (t + k) * n, o[k]);
+        for (int k = 0; k < GI_B; ++k)
+#pragma unroll
+            for (int q = 0; q < GRAPH_NOUT; ++q) __stcs(dst + ((t + k) * GRAPH_NOUT + q) * n, o[k][q]);
     }
     for (; t < p.F; ++t) {
-        uint32_t x[GRAPH_NIN], g, o;
+        uint32_t x[GRAPH_NIN], g, o[GRAPH_NOUT];
 #pragma unroll
         for (int j = 0; j < GRAPH_NIN; ++j) x[j] = __ldcs(src + (t * GRAPH_NIN + j) * n);
         g = GRAPH_HAS_CHANGED ? __ldcs(chg + t * n) : 0xFFFFFFFFu;
         TICK(x, g, o);
-        __stcs(dst + t * n, o);
+#pragma unroll
+        for (int q = 0; q < GRAPH_NOUT; ++q) __stcs(dst + (t * GRAPH_NOUT + q) * n, o[q]);
     }
     GRAPH_STORE_STATE(p.st, p.npad, i)
 }
@@ -360,7 +368,8 @@ extern "C" __global__ void __launch_bounds__(128) graph_interleaved(const GraphP
 // the output overwrites the row of input 0 in place and leaves with one bulk store.
 __device__ __forceinline__ uint32_t smem_u32(const void *q) { return (uint32_t)__cvta_generic_to_shared(q); }
 #define TF 64
-#define ROWS (GRAPH_NIN + (GRAPH_HAS_CHANGED ? 1 : 0))
+#define ROWS_IN (GRAPH_NIN + (GRAPH_HAS_CHANGED ? 1 : 0))
+#define ROWS (ROWS_IN > GRAPH_NOUT ? ROWS_IN : GRAPH_NOUT)   // output q overwrites row q in place
 #define ROWB (TF * 4 + 16)
 #define STAGEB (32 * ROWS * ROWB)
 #define STAGES 3
@@ -387,10 +396,10 @@ extern "C" __global__ void __launch_bounds__(WARPS * 32) graph_planar(const Grap
     auto cols_of = [&](uint32_t k) { const uint64_t left = p.F - (uint64_t)k * TF; return left < TF ? (uint32_t)left : (uint32_t)TF; };
     auto issue = [&](uint32_t k) {
         const uint32_t s = k % STAGES, bytes = cols_of(k) * 4;
-        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * s), "r"(rows * ROWS * bytes) : "memory");
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * s), "r"(rows * ROWS_IN * bytes) : "memory");
         if (mine) {
 #pragma unroll
-            for (int j = 0; j < ROWS; ++j) {
+            for (int j = 0; j < ROWS_IN; ++j) {
                 const uint32_t *srow = j < GRAPH_NIN ? p.in + (i * GRAPH_NIN + j) * p.F : p.changed + i * p.F;
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(base + s * STAGEB + (j * 32 + lane) * ROWB), "l"(srow + (uint64_t)k * TF), "r"(bytes), "r"(bar0 + 8 * s) : "memory");
@@ -414,17 +423,21 @@ extern "C" __global__ void __launch_bounds__(WARPS * 32) graph_planar(const Grap
             for (uint32_t c = 0; c < cols / 4; ++c) {
                 // four frames per 128-bit access; separate arrays and explicit ticks keep every index static
                 uint32_t xa[GRAPH_NIN], xb[GRAPH_NIN], xc[GRAPH_NIN], xd[GRAPH_NIN], ga = 0xFFFFFFFFu, gb = 0xFFFFFFFFu, gc = 0xFFFFFFFFu, gd = 0xFFFFFFFFu;
-                uint32_t oa, ob, oc, od;
+                uint32_t oa[GRAPH_NOUT], ob[GRAPH_NOUT], oc[GRAPH_NOUT], od[GRAPH_NOUT];
 #pragma unroll
                 for (int j = 0; j < GRAPH_NIN; ++j)
                     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(xa[j]), "=r"(xb[j]), "=r"(xc[j]), "=r"(xd[j]) : "r"(row + j * (32 * ROWB) + 16 * c));
                 if (GRAPH_HAS_CHANGED)
                     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ga), "=r"(gb), "=r"(gc), "=r"(gd) : "r"(row + GRAPH_NIN * (32 * ROWB) + 16 * c));
                 TICK(xa, ga, oa); TICK(xb, gb, ob); TICK(xc, gc, oc); TICK(xd, gd, od);
-                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(row + 16 * c), "r"(oa), "r"(ob), "r"(oc), "r"(od) : "memory");
+#pragma unroll
+                for (int q = 0; q < GRAPH_NOUT; ++q)
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(row + q * (32 * ROWB) + 16 * c), "r"(oa[q]), "r"(ob[q]), "r"(oc[q]), "r"(od[q]) : "memory");
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out + i * p.F + (uint64_t)k * TF), "r"(row), "r"(cols * 4) : "memory");
+#pragma unroll
+            for (int q = 0; q < GRAPH_NOUT; ++q)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out + (i * GRAPH_NOUT + q) * p.F + (uint64_t)k * TF), "r"(row + q * (32 * ROWB)), "r"(cols * 4) : "memory");
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
@@ -439,12 +452,13 @@ extern "C" __global__ void __launch_bounds__(128) graph_planar_simple(const Grap
     GRAPH_DECL_STATE
     GRAPH_LOAD_STATE(p.st, p.npad, i)
     for (uint64_t t = 0; t < p.F; ++t) {
-        uint32_t x[GRAPH_NIN], g, o;
+        uint32_t x[GRAPH_NIN], g, o[GRAPH_NOUT];
 #pragma unroll
         for (int j = 0; j < GRAPH_NIN; ++j) x[j] = p.in[(i * GRAPH_NIN + j) * p.F + t];
         g = GRAPH_HAS_CHANGED ? p.changed[i * p.F + t] : 0xFFFFFFFFu;
         TICK(x, g, o);
-        p.out[i * p.F + t] = o;
+#pragma unroll
+        for (int q = 0; q < GRAPH_NOUT; ++q) p.out[(i * GRAPH_NOUT + q) * p.F + t] = o[q];
     }
     GRAPH_STORE_STATE(p.st, p.npad, i)
 }
@@ -455,7 +469,7 @@ extern "C" __global__ void graph_planar_smem(uint32_t *out) { out[0] = WARPS * S
 }  // namespace
 
 // Source for one graph: state words s0..s{W-1} in node order (acc {out}; edge {out, last}).
-std::string cproc_graph_jit_source(const std::vector<cproc_cuda_node> &nodes, uint32_t n_inputs, uint32_t out_node, bool has_changed) {
+std::string cproc_graph_jit_source(const std::vector<cproc_cuda_node> &nodes, uint32_t n_inputs, const std::vector<uint32_t> &outs, bool has_changed) {
     std::vector<uint32_t> off(nodes.size());
     uint32_t words = 0;
     for (size_t k = 0; k < nodes.size(); ++k) { off[k] = words; words += cproc_node_words(nodes[k].type); }
@@ -505,8 +519,10 @@ std::string cproc_graph_jit_source(const std::vector<cproc_cuda_node> &nodes, ui
         tick += buf;
     }
     tick += "\n";
-    snprintf(buf, sizeof(buf), "#define GRAPH_OUT s%u\n#define GRAPH_NIN %u\n#define GRAPH_HAS_CHANGED %d\n", off[out_node], n_inputs, has_changed ? 1 : 0);
-    return decl + load + store + tick + buf + k_jit_tail;
+    std::string outm = "#define GRAPH_OUTS(o)";
+    for (size_t q = 0; q < outs.size(); ++q) { snprintf(buf, sizeof(buf), " (o)[%zu] = s%u;", q, off[outs[q]]); outm += buf; }
+    snprintf(buf, sizeof(buf), "\n#define GRAPH_NOUT %zu\n#define GRAPH_NIN %u\n#define GRAPH_HAS_CHANGED %d\n", outs.size(), n_inputs, has_changed ? 1 : 0);
+    return decl + load + store + tick + outm + buf + k_jit_tail;
 }
 
 // Compile (once per batch and `changed` presence) and return the two kernels.
@@ -517,7 +533,7 @@ int cproc_graph_jit_get(cproc_cuda_batch *b, bool has_changed, cproc_graph_jit *
     if (j.state == 0) {
         j.state = 2;
         if (!nvrtc_load()) { b->jit_log = "libnvrtc not found"; return -1; }
-        const std::string src = cproc_graph_jit_source(b->nodes, b->cfg.n_inputs, b->cfg.out_node, has_changed);
+        const std::string src = cproc_graph_jit_source(b->nodes, b->cfg.n_inputs, b->outs, has_changed);
         void *prog = nullptr;
         if (g_nvrtc.create(&prog, src.c_str(), "cproc_graph.cu", 0, nullptr, nullptr)) { b->jit_log = "nvrtcCreateProgram failed"; return -1; }
         const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
@@ -555,14 +571,15 @@ int cproc_graph_jit_get(cproc_cuda_batch *b, bool has_changed, cproc_graph_jit *
 }
 
 extern "C" const char *cproc_cuda_graph_jit_log(const cproc_cuda_batch *b) { return b ? b->jit_log.c_str() : ""; }
-extern "C" int cproc_cuda_graph_jit_source(const cproc_cuda_node *nodes, uint32_t n_nodes, uint32_t n_inputs, uint32_t out_node,
-                                           int has_changed, char *dst, size_t cap) {
-    if (!nodes || n_nodes == 0 || n_nodes > CPROC_CUDA_GRAPH_MAX_NODES || out_node >= n_nodes || n_inputs == 0)
+extern "C" int cproc_cuda_graph_jit_source(const cproc_cuda_node *nodes, uint32_t n_nodes, uint32_t n_inputs, const uint32_t *out_nodes,
+                                           uint32_t n_outputs, int has_changed, char *dst, size_t cap) {
+    if (!nodes || n_nodes == 0 || n_nodes > CPROC_CUDA_GRAPH_MAX_NODES || n_inputs == 0 || !out_nodes || n_outputs == 0 || n_outputs > CPROC_CUDA_GRAPH_MAX_OUTPUTS)
         return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_jit_source: bad node table");
+    for (uint32_t q = 0; q < n_outputs; ++q) if (out_nodes[q] >= n_nodes) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_jit_source: output node %u of %u", out_nodes[q], n_nodes);
     for (uint32_t k = 0; k < n_nodes; ++k)
         if (const char *why = cproc_node_check(nodes[k], k, n_inputs))
             return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_jit_source: node %u: %s", k, why);
-    const std::string s = cproc_graph_jit_source(std::vector<cproc_cuda_node>(nodes, nodes + n_nodes), n_inputs, out_node, has_changed != 0);
+    const std::string s = cproc_graph_jit_source(std::vector<cproc_cuda_node>(nodes, nodes + n_nodes), n_inputs, std::vector<uint32_t>(out_nodes, out_nodes + n_outputs), has_changed != 0);
     if (dst && cap) { const size_t n = s.size() < cap - 1 ? s.size() : cap - 1; memcpy(dst, s.data(), n); dst[n] = 0; }
     return (int)s.size();
 }

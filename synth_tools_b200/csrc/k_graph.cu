@@ -18,9 +18,11 @@ struct GraphParams {
     uint32_t n_nodes, n_inputs, out_node, state_words;
     const uint32_t *in;            // PLANAR [inst][n_inputs][F] / INTERLEAVED [F][n_inputs][inst]
     const uint32_t *changed;       // [inst][F] / [F][inst] or null
-    uint32_t *out;                 // [inst][F] / [F][inst]
+    uint32_t *out;                 // [inst][n_outputs][F] / [F][n_outputs][inst]
     uint64_t F;
     uint32_t layout;
+    uint32_t n_outputs;
+    uint32_t out_nodes[CPROC_CUDA_GRAPH_MAX_OUTPUTS];
 };
 
 // acc_update (cproc.h:140-142) / edge_update (cproc.h:151-154) on register state
@@ -108,7 +110,8 @@ __global__ void k_graph_table(const GraphParams p) {
             const uint32_t x2 = (nodes[k].type & 0xFFu) == CPROC_CUDA_NODE_PDM ? fetch(nodes[k].src2) : 0u;
             node_tick(nodes[k].type, s + off[k], x, x2);
         }
-        p.out[oidx] = s[off[p.out_node]];
+        for (uint32_t q = 0; q < p.n_outputs; ++q)
+            p.out[il ? (t * p.n_outputs + q) * p.n + i : (i * p.n_outputs + q) * p.F + t] = s[off[p.out_nodes[q]]];
     }
     for (uint32_t w = 0; w < p.state_words; ++w) p.st[w * p.npad + i] = s[w];
 }
@@ -123,6 +126,8 @@ int launch_graph(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     p.st = b->d_state; p.npad = b->npad; p.n = b->n; p.nodes = b->d_nodes;
     p.n_nodes = b->cfg.n_nodes; p.n_inputs = b->cfg.n_inputs; p.out_node = b->cfg.out_node;
     p.state_words = b->state_words;
+    p.n_outputs = (uint32_t)b->outs.size();
+    for (uint32_t q = 0; q < CPROC_CUDA_GRAPH_MAX_OUTPUTS; ++q) p.out_nodes[q] = q < p.n_outputs ? b->outs[q] : 0;
     p.in = (const uint32_t *)io->in; p.changed = (const uint32_t *)io->in2; p.out = (uint32_t *)io->out;
     p.F = F; p.layout = io->layout;
     const unsigned grid = (unsigned)ceil_div_u64(p.n, 128);
@@ -143,7 +148,7 @@ int launch_graph(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     // recognise edge -> acc [-> acc] chains under a single mask
     const std::vector<cproc_cuda_node> &nd = b->nodes;
     bool chain = nd.size() >= 2 && nd.size() <= 3 && nd[0].type == CPROC_CUDA_NODE_EDGE && nd[0].src == -1 &&
-                 p.n_inputs == 1 && p.out_node == nd.size() - 1;
+                 p.n_inputs == 1 && p.n_outputs == 1 && p.out_node == nd.size() - 1;
     for (size_t k = 1; chain && k < nd.size(); ++k)
         chain = nd[k].type == CPROC_CUDA_NODE_ACC && nd[k].src == (int32_t)k - 1 && nd[k].cond_mask == nd[0].cond_mask;
     if (chain && nd.size() == 2) k_graph_edge_acc<1><<<grid, 128, 0, ctx->stream>>>(p, nd[0].cond_mask);

@@ -157,8 +157,7 @@ int launch_graph_scan(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) 
             if (il) { p.x = (const uint32_t *)io->in + j * n; p.xs_i = 1; p.xs_t = (uint64_t)b->cfg.n_inputs * n; }      // [F][n_inputs][inst]
             else { p.x = (const uint32_t *)io->in + j * F; p.xs_i = (uint64_t)b->cfg.n_inputs * F; p.xs_t = 1; }          // [inst][n_inputs][F]
         }
-        if (k == b->cfg.out_node) { p.y = (uint32_t *)io->out; p.ys_i = il ? 1 : F; p.ys_t = il ? n : 1; }
-        else { p.y = val + k * n * F; p.ys_i = F; p.ys_t = 1; }
+        p.y = val + k * n * F; p.ys_i = F; p.ys_t = 1;          // every node's stream stays in scratch for later nodes
         p.g = (const uint32_t *)io->in2; p.gs_i = il ? 1 : F; p.gs_t = il ? n : 1;
         p.st = b->d_state + (uint64_t)off[k] * b->npad; p.npad = b->npad;
         p.n = n; p.F = F; p.L = L; p.C = C; p.part = part; p.start = start;
@@ -166,15 +165,14 @@ int launch_graph_scan(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) 
         k_gs_reduce<<<grid, 128, 0, ctx->stream>>>(p); CK_LAUNCH(ctx, "k_gs_reduce");
         k_gs_scan<<<(unsigned)n, GS_BLOCK, 0, ctx->stream>>>(p); CK_LAUNCH(ctx, "k_gs_scan");
         k_gs_apply<<<grid, 128, 0, ctx->stream>>>(p); CK_LAUNCH(ctx, "k_gs_apply");
-        if (k == b->cfg.out_node && k + 1 < nn) {
-            // a later node may read the output node: keep a planar copy of its stream in scratch
-            bool needed = false;
-            for (uint64_t q = k + 1; q < nn; ++q) needed = needed || b->nodes[q].src == (int32_t)k;
-            if (needed) {
-                GsNode c2 = p;
-                c2.y = val + k * n * F; c2.ys_i = F; c2.ys_t = 1;
-                k_gs_apply<<<grid, 128, 0, ctx->stream>>>(c2); CK_LAUNCH(ctx, "k_gs_apply");
-            }
+        // output streams: [inst][n_outputs][F] / [F][n_outputs][inst]; a node may feed several outputs
+        const uint64_t no = b->outs.size();
+        for (uint64_t q = 0; q < no; ++q) {
+            if (b->outs[q] != k) continue;
+            GsNode c2 = p;
+            if (il) { c2.y = (uint32_t *)io->out + q * n; c2.ys_i = 1; c2.ys_t = no * n; }
+            else { c2.y = (uint32_t *)io->out + q * F; c2.ys_i = no * F; c2.ys_t = 1; }
+            k_gs_apply<<<grid, 128, 0, ctx->stream>>>(c2); CK_LAUNCH(ctx, "k_gs_apply");
         }
     }
     return 0;

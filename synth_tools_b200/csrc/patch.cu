@@ -159,7 +159,7 @@ static int patch_build(cproc_cuda_patch *p) {
     memset(&cfg, 0, sizeof(cfg));
     cfg.proc = CPROC_CUDA_GRAPH; cfg.layout = p->layout;
     cfg.nodes = p->rows.data(); cfg.n_nodes = (uint32_t)p->rows.size(); cfg.n_inputs = p->n_inputs;
-    cfg.out_node = (uint32_t)p->nodes[p->out_node].table;
+    cfg.out_node = (uint32_t)p->nodes[p->out_node].table; cfg.n_outputs = 1; cfg.out_nodes = nullptr;
     cproc_cuda_batch *nb = nullptr;
     int rc = cproc_cuda_alloc(ctx, &cfg, p->n, &nb);
     if (rc) return rc;

@@ -545,6 +545,44 @@ def test_graph_scan(st, ctx, oracle, rows, layout, masked, N, F, chunk):
         bb.run(128, inp=np.zeros((2, 1, 128), np.uint32), out=np.zeros((2, 128), np.uint32))
 
 
+@pytest.mark.parametrize("n_nodes,n_in,outs,N,F", [(6, 1, [5, 2], 200, 256), (20, 2, [19, 0, 7, 7, 12], 97, 100), (9, 3, [8, 1, 2, 3, 4, 5, 6, 7], 64, 33),
+                                                 (12, 2, [3] * 16, 40, 64)])
+@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
+@pytest.mark.parametrize("masked", [False, True])
+@pytest.mark.parametrize("path", ["jit", "table", "scan"])
+def test_graph_several_outputs(st, ctx, oracle, n_nodes, n_in, outs, N, F, layout, masked, path):
+    """Graphs with several cproc_output statements (more outputs than inputs included): output
+    stream q is the .out of node outs[q]; generated kernels, table kernel and the time-parallel scan."""
+    rows = _random_graph(n_nodes, n_in, seed=n_nodes * 7 + len(outs), glide=path != "scan", pdm=path == "jit")
+    if path == "table" and (len(rows) > 16 or sum(po.node_words(r[0]) for r in rows) > 48):
+        pytest.skip("the table kernel holds 16 nodes / 48 state words")
+    n_in = max(1, max(max(-r[1], -r[3] if len(r) > 3 else 0) for r in rows))
+    inp = rng.integers(0, 3, (N, n_in, F), dtype=np.uint32)
+    changed = rng.integers(0, 8, (N, F), dtype=np.uint32) if masked else None
+    sw = sum(po.node_words(r[0]) for r in rows)
+    s0 = rng.integers(0, 2**32, (N, sw), dtype=np.uint32)
+    o = 0
+    for r in rows:
+        if r[0] & 0xFF == po.NODE_GLIDE:
+            s0[:, o + 4] &= (1 << (r[0] >> 8)) - 1
+        o += po.node_words(r[0])
+    sa = s0.copy()
+    want = oracle.graph_run_multi(rows, n_in, outs, sa, N, F, inp, changed)       # [N][n_out][F]
+    ctx.set_option("graph_jit", 0 if path == "table" else 1)
+    try:
+        b = ctx.batch(st.GRAPH, N, nodes=rows, n_inputs=n_in, out_node=outs, layout=getattr(st, layout), mode=1 if path == "scan" else 0)
+        b.upload_state(s0)
+        il = layout == "INTERLEAVED"
+        out = np.zeros((F, len(outs), N) if il else (N, len(outs), F), np.uint32)
+        b.run(F, inp=np.ascontiguousarray(inp.transpose(2, 1, 0)) if il else inp,
+              in2=None if changed is None else (np.ascontiguousarray(changed.T) if il else changed), out=out)
+        assert np.array_equal(out.transpose(2, 1, 0) if il else out, want)
+        assert np.array_equal(b.download_state(), sa)
+        b.free()
+    finally:
+        ctx.set_option("graph_jit", 1)
+
+
 def test_graph_from_generated_text(st, ctx, oracle):
     """The wire format end to end: the generated C text of the reference's two graphs
     (linux/test_cproc.c:11-17, stm32f103/bp5_plugin.c:1-9) -> parser -> batch -> render."""
