@@ -43,6 +43,7 @@ struct cproc_cuda_ctx {
     int grain_vec4 = 1;       // interleaved square_grain: four grains per thread when n % 4 == 0
     int grain_mix2 = 2;       // 0: float kernel; 1: register-accumulator / integer-threshold kernel; 2: predicate-state kernel
     int planar_bulk = 1;      // PLANAR pdm_raw / onepole streams through the bulk-staged template (planar_bulk.cuh)
+    int graph_vec4 = 1;       // interleaved generated graphs: four instances per thread when n % 4 == 0
     int graph_jit = 1;        // 1: generated graphs are compiled with NVRTC; 0: table-driven kernel
     int xvoice_block = 128;
     int xvoice_groups = 0;    // XVOICE_SCAN: variant groups pipelined over the two streams (0 = automatic)
@@ -54,7 +55,7 @@ struct cproc_graph_jit {
     int state = 0;
     std::vector<char> cubin;
     cudaLibrary_t lib = nullptr;
-    cudaKernel_t k_il = nullptr, k_pl = nullptr, k_ps = nullptr;
+    cudaKernel_t k_il = nullptr, k_il4 = nullptr, k_pl = nullptr, k_ps = nullptr;
     uint32_t pl_smem = 0, pl_block = 0;
 };
 

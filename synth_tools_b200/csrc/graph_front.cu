@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include <ctype.h>
 #include <dlfcn.h>
+#include <regex>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -300,10 +301,8 @@ bool nvrtc_load() {
 
 // The fixed part of the generated translation unit.  GRAPH_* macros and the two
 // generated code blocks (GRAPH_DECL_STATE .. GRAPH_TICK) come first.
+const char *k_jit_head = "typedef unsigned int uint32_t;\ntypedef unsigned long long uint64_t;\ntypedef int int32_t;\n";
 const char *k_jit_tail = R"SRC(
-typedef unsigned int uint32_t;
-typedef unsigned long long uint64_t;
-typedef int int32_t;
 
 struct GraphParams {                       // must match k_graph.cu
     uint32_t *st;
@@ -319,8 +318,9 @@ struct GraphParams {                       // must match k_graph.cu
     uint32_t out_nodes[16];
 };
 
-// one tick: x[] = this tick's inputs, g = changed mask; o[] = the output words (GRAPH_NOUT of them)
-#define TICK(x, g, o) do { GRAPH_TICK(x, g) GRAPH_OUTS(o) } while (0)
+// one tick of one instance: x[] = this tick's inputs, g = changed mask; o[] = the output words (GRAPH_NOUT of them)
+__device__ __forceinline__ void graph_tick(GState &S, const uint32_t *x, uint32_t g, uint32_t *o) { GRAPH_TICK(x, g) GRAPH_OUTS(o) }
+#define TICK(x, g, o) graph_tick(S, x, g, o)
 
 // [F][n_inputs][inst] in, [F][inst] changed / out: coalesced as they are; 16-frame batches
 // make the independent loads explicit (in may alias out).
@@ -360,6 +360,40 @@ extern "C" __global__ void __launch_bounds__(128) graph_interleaved(const GraphP
         for (int q = 0; q < GRAPH_NOUT; ++q) __stcs(dst + (t * GRAPH_NOUT + q) * n, o[q]);
     }
     GRAPH_STORE_STATE(p.st, p.npad, i)
+}
+
+// Four adjacent instances per thread (128-bit accesses): a block covers 2 KiB of every stream row
+// instead of 512 B -- fewer distant row segments and pages per block (see k_grain_interleaved4).
+// n % 4 == 0, 16-byte aligned streams.
+#define GI4_B 4
+extern "C" __global__ void __launch_bounds__(128) graph_interleaved4(const GraphParams p) {
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= p.n) return;
+    GState Sa = {}, Sb = {}, Sc = {}, Sd = {};
+    GRAPH_LOAD_STATE4(p.st, p.npad, i)
+    const uint32_t *src = p.in + i;
+    const uint32_t *chg = GRAPH_HAS_CHANGED ? p.changed + i : 0;
+    uint32_t *dst = p.out + i;
+    const uint64_t n = p.n;
+    auto frame = [&](uint64_t t) {
+        uint32_t xa[GRAPH_NIN], xb[GRAPH_NIN], xc[GRAPH_NIN], xd[GRAPH_NIN], oa[GRAPH_NOUT], ob[GRAPH_NOUT], oc[GRAPH_NOUT], od[GRAPH_NOUT];
+        uint4 g = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+#pragma unroll
+        for (int j = 0; j < GRAPH_NIN; ++j) { const uint4 v = __ldcs((const uint4 *)(src + (t * GRAPH_NIN + j) * n)); xa[j] = v.x; xb[j] = v.y; xc[j] = v.z; xd[j] = v.w; }
+        if (GRAPH_HAS_CHANGED) g = __ldcs((const uint4 *)(chg + t * n));
+        graph_tick(Sa, xa, g.x, oa); graph_tick(Sb, xb, g.y, ob); graph_tick(Sc, xc, g.z, oc); graph_tick(Sd, xd, g.w, od);
+#pragma unroll
+        for (int q = 0; q < GRAPH_NOUT; ++q) __stcs((uint4 *)(dst + (t * GRAPH_NOUT + q) * n), make_uint4(oa[q], ob[q], oc[q], od[q]));
+    };
+    uint64_t t = 0;
+    for (; t + GI4_B <= p.F; t += GI4_B) {
+        // loads of a batch are independent of the stores of the previous frames only if issued first: keep the
+        // batch short (the state of four instances is already in registers) and let the unroller interleave
+#pragma unroll
+        for (int k = 0; k < GI4_B; ++k) frame(t + k);
+    }
+    for (; t < p.F; ++t) frame(t);
+    GRAPH_STORE_STATE4(p.st, p.npad, i)
 }
 
 // [inst][n_inputs][F] in, [inst][F] changed / out (what a host hands over): lane r of a warp
@@ -474,13 +508,17 @@ std::string cproc_graph_jit_source(const std::vector<cproc_cuda_node> &nodes, ui
     uint32_t words = 0;
     for (size_t k = 0; k < nodes.size(); ++k) { off[k] = words; words += cproc_node_words(nodes[k].type); }
     char buf[512];
-    std::string decl = "#define GRAPH_DECL_STATE uint32_t", load = "#define GRAPH_LOAD_STATE(st, npad, i)", store = "#define GRAPH_STORE_STATE(st, npad, i)";
+    // state words live in a struct so that a kernel can keep several instances per thread
+    std::string decl = "struct GState { uint32_t", load = "#define GRAPH_LOAD_STATE(st, npad, i)", store = "#define GRAPH_STORE_STATE(st, npad, i)";
+    std::string load4 = "#define GRAPH_LOAD_STATE4(st, npad, i) { uint4 v;", store4 = "#define GRAPH_STORE_STATE4(st, npad, i) {";
     for (uint32_t w = 0; w < words; ++w) {
-        snprintf(buf, sizeof(buf), "%s s%u = 0", w ? "," : "", w); decl += buf;
-        snprintf(buf, sizeof(buf), " s%u = (st)[%uull * (npad) + (i)];", w, w); load += buf;
-        snprintf(buf, sizeof(buf), " (st)[%uull * (npad) + (i)] = s%u;", w, w); store += buf;
+        snprintf(buf, sizeof(buf), "%s s%u", w ? "," : "", w); decl += buf;
+        snprintf(buf, sizeof(buf), " S.s%u = (st)[%uull * (npad) + (i)];", w, w); load += buf;
+        snprintf(buf, sizeof(buf), " (st)[%uull * (npad) + (i)] = S.s%u;", w, w); store += buf;
+        snprintf(buf, sizeof(buf), " v = *(const uint4 *)((st) + %uull * (npad) + (i)); Sa.s%u = v.x; Sb.s%u = v.y; Sc.s%u = v.z; Sd.s%u = v.w;", w, w, w, w, w); load4 += buf;
+        snprintf(buf, sizeof(buf), " *(uint4 *)((st) + %uull * (npad) + (i)) = make_uint4(Sa.s%u, Sb.s%u, Sc.s%u, Sd.s%u);", w, w, w, w, w); store4 += buf;
     }
-    decl += ";\n"; load += "\n"; store += "\n";
+    decl += "; };\n#define GRAPH_DECL_STATE GState S = {};\n"; load += "\n"; store += "\n"; load4 += " }\n"; store4 += " }\n";
     std::string tick = "#define GRAPH_TICK(x, g)";
     for (size_t k = 0; k < nodes.size(); ++k) {
         const cproc_cuda_node &nd = nodes[k];
@@ -522,7 +560,11 @@ std::string cproc_graph_jit_source(const std::vector<cproc_cuda_node> &nodes, ui
     std::string outm = "#define GRAPH_OUTS(o)";
     for (size_t q = 0; q < outs.size(); ++q) { snprintf(buf, sizeof(buf), " (o)[%zu] = s%u;", q, off[outs[q]]); outm += buf; }
     snprintf(buf, sizeof(buf), "\n#define GRAPH_NOUT %zu\n#define GRAPH_NIN %u\n#define GRAPH_HAS_CHANGED %d\n", outs.size(), n_inputs, has_changed ? 1 : 0);
-    return decl + load + store + tick + outm + buf + k_jit_tail;
+    // the tick text names the state words s<k>: they are members of the GState `S` in scope
+    static const std::regex word("\\bs([0-9]+)\\b");
+    tick = std::regex_replace(tick, word, "S.s$1");
+    outm = std::regex_replace(outm, word, "S.s$1");
+    return k_jit_head + decl + load + store + load4 + store4 + tick + outm + buf + k_jit_tail;
 }
 
 // Compile (once per batch and `changed` presence) and return the two kernels.
@@ -551,6 +593,7 @@ int cproc_graph_jit_get(cproc_cuda_batch *b, bool has_changed, cproc_graph_jit *
         cudaKernel_t kq = nullptr;
         if (cudaLibraryGetKernel(&j.k_il, j.lib, "graph_interleaved") != cudaSuccess || cudaLibraryGetKernel(&j.k_pl, j.lib, "graph_planar") != cudaSuccess ||
             cudaLibraryGetKernel(&j.k_ps, j.lib, "graph_planar_simple") != cudaSuccess ||
+            cudaLibraryGetKernel(&j.k_il4, j.lib, "graph_interleaved4") != cudaSuccess ||
             cudaLibraryGetKernel(&kq, j.lib, "graph_planar_smem") != cudaSuccess) { cudaGetLastError(); b->jit_log = "cudaLibraryGetKernel failed"; return -1; }
         // shared-memory size and block size of the planar kernel are defined by the generated source: ask it
         uint32_t *d = nullptr, h[2] = {0, 0};

@@ -583,6 +583,39 @@ def test_graph_several_outputs(st, ctx, oracle, n_nodes, n_in, outs, N, F, layou
         ctx.set_option("graph_jit", 1)
 
 
+@pytest.mark.parametrize("vec4", [0, 1])
+@pytest.mark.parametrize("N,F", [(1024, 200), (300, 64), (4, 1000), (1001, 50)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_graph_interleaved_vec4(st, ctx, oracle, vec4, N, F, masked):
+    """INTERLEAVED generated kernels with one and with four instances per thread (the latter only
+    when n % 4 == 0: N = 1001 must take the scalar kernel either way), two inputs, three outputs."""
+    rows = _random_graph(9, 2, seed=123, glide=True, pdm=True)
+    ctx.set_option("graph_vec4", vec4)
+    try:
+        n_in = max(1, max(max(-r[1], -r[3] if len(r) > 3 else 0) for r in rows))
+        outs = [8, 2, 5]
+        inp = rng.integers(0, 3, (N, n_in, F), dtype=np.uint32)
+        changed = rng.integers(0, 8, (N, F), dtype=np.uint32) if masked else None
+        sw = sum(po.node_words(r[0]) for r in rows)
+        s0 = rng.integers(0, 2**32, (N, sw), dtype=np.uint32)
+        o = 0
+        for r in rows:
+            if r[0] & 0xFF == po.NODE_GLIDE:
+                s0[:, o + 4] &= (1 << (r[0] >> 8)) - 1
+            o += po.node_words(r[0])
+        sa = s0.copy()
+        want = oracle.graph_run_multi(rows, n_in, outs, sa, N, F, inp, changed)
+        b = ctx.batch(st.GRAPH, N, nodes=rows, n_inputs=n_in, out_node=outs, layout=st.INTERLEAVED)
+        b.upload_state(s0)
+        out = np.zeros((F, len(outs), N), np.uint32)
+        b.run(F, inp=np.ascontiguousarray(inp.transpose(2, 1, 0)), in2=None if changed is None else np.ascontiguousarray(changed.T), out=out)
+        assert np.array_equal(out.transpose(2, 1, 0), want)
+        assert np.array_equal(b.download_state(), sa)
+        b.free()
+    finally:
+        ctx.set_option("graph_vec4", 1)
+
+
 def test_graph_from_generated_text(st, ctx, oracle):
     """The wire format end to end: the generated C text of the reference's two graphs
     (linux/test_cproc.c:11-17, stm32f103/bp5_plugin.c:1-9) -> parser -> batch -> render."""
