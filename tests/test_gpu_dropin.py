@@ -58,3 +58,39 @@ def test_c_host_through_dropin_and_abi(tmp_path, oracle):
     assert tag("pdm") == [["rc", "0"]] + [[str(c), str(int(wsum[c]))] for c in range(6)]
     assert [[int(x) for x in r] for r in tag("pdmstate")] == chan.tolist()
     assert tag("err") == [["rc", "-1"]]
+
+
+def test_c_host_generated_text_patcher_bus(tmp_path, oracle):
+    """tests/c/test_graph_text.c: the generated graph text, the patcher and the mix bus from plain C."""
+    pkg = os.path.join(ROOT, "synth_tools_b200")
+    exe = str(tmp_path / "test_graph_text")
+    subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "test_graph_text.c"), "-o", exe, "-L", pkg, "-lcproc_cuda", "-Wl,-rpath," + pkg])
+    out = subprocess.check_output([exe], text=True).splitlines()
+    tag = lambda t: [l.split()[1:] for l in out if l.split() and l.split()[0] == t]
+    assert not tag("fail"), out
+    assert tag("parse") == [["0", "5", "2", "2"]] and tag("out") == [["2", "3"], ["4", "4"]]
+    rows = [(po.NODE_EDGE, -1, 1), (po.NODE_ACC, 0, 1), (po.NODE_ACC, 1, 1), (po.node_glide(3), 2, 0xFFFFFFFF), (po.node_pdm(2, 24), 3, 0xFFFFFFFF, -2)]
+    assert [[int(x, 0) for x in r] for r in tag("node")] == [[r[0], r[1], r[2], r[3] if len(r) > 3 else 0] for r in rows]
+    N, F = 3, 40
+    inp = np.zeros((N, 2, F), np.uint32); chg = np.zeros((N, F), np.uint32)
+    s = 99
+    for i in range(N):
+        for t in range(F):
+            s = xs(s)
+            inp[i, 0, t] = (s >> 7) & 1; inp[i, 1, t] = s & 0x3FF; chg[i, t] = (s >> 20) & 3
+    st = np.zeros((N, 12), np.uint32)
+    want = oracle.graph_run_multi(rows, 2, [2, 4], st, N, F, inp, chg)
+    got = {(int(r[0]), int(r[1])): [int(x) for x in r[2:]] for r in tag("stream")}
+    for i in range(N):
+        for q in range(2):
+            assert got[(i, q)] == want[i, q].tolist()
+    assert tag("jitlog") == [["[]"]]                       # compiled by NVRTC without a diagnostic
+    # patcher: bp5 graph, every instance runs (mask -1)
+    assert tag("patch") == [["0", "1", "2", "3", "edge"]]
+    prow = [(po.NODE_EDGE, -1, 0xFFFFFFFF), (po.NODE_ACC, 0, 0xFFFFFFFF), (po.NODE_ACC, 1, 0xFFFFFFFF)]
+    pst = np.zeros((N, 4), np.uint32)
+    pw = oracle.graph_run(prow, 1, 2, pst, N, F, np.ascontiguousarray(inp[:, :1, :]))
+    assert [[int(x) for x in r[1:]] for r in tag("pstream")] == pw.tolist()
+    assert tag("pget") == [[str(int(pst[2, 3]))]] and tag("pbad") == [["-1"]]
+    assert tag("bus") == [["1", "0", "64"]] and out[-1] == "done"
