@@ -202,6 +202,16 @@ def run_native(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = "unset"
+    try:
+        # run (and first-touch the pinned host ring) on the CPUs next to this GPU: the e2e leg is a
+        # PCIe / host-memory stream, and 8 ranks on the wrong socket share one inter-socket link
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(physical_gpu_index(local_rank)))
+        numa = "gpu-local cpus (%d)" % len(os.sched_getaffinity(0))
+    except Exception as e:
+        numa = "not set (%s)" % type(e).__name__
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     # a non-default torch stream: the library launches on it and torch's events time it
@@ -312,6 +322,7 @@ def run_native(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": "samples/s",
                     "h2d_bytes_per_step": e2e_rows * N_CH * 4, "d2h_bytes_per_step": N_CH * E2E_TICKS,
                     "sample": "65,536 ch x 1 Mi samples per step per GPU via cproc_cuda_run_stream (pinned ring of 4 x 1 GiB)",
+                    "cpu_affinity": numa,
                     "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
