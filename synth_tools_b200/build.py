@@ -44,7 +44,7 @@ def build(force=False, verbose=False, ptxas_v=False):
             objs.append(o)
             if not force and not _newer(o, [s] + deps[len(srcs):]):
                 continue
-            cmd = [NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O2",
+            cmd = [NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O2", *os.environ.get("CPROC_NVCC_DEFS", "").split(),
                    "-I", os.path.join(ROOT, "include"), "-c", s, "-o", o]
             if ptxas_v:
                 cmd += ["-Xptxas", "-v"]

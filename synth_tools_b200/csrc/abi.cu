@@ -89,6 +89,7 @@ int cproc_cuda_close(cproc_cuda_ctx *ctx) {
     for (uint32_t *j : ctx->d_jump) if (j) cudaFree(j);
     if (ctx->d_sm_rank) cudaFree(ctx->d_sm_rank);
     if (ctx->d_work) cudaFree(ctx->d_work);
+    if (ctx->d_jump16) cudaFree(ctx->d_jump16);
     delete ctx;
     return 0;
 }

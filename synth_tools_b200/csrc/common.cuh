@@ -33,6 +33,7 @@ struct cproc_cuda_ctx {
     int pdm_slots = 2;        // ws2: dither ring slots (2 or 4)
     int pdm_chains = 2;       // ws2: independent PRNG chains per producer lane (1, 2 or 4)
     uint32_t *d_jump[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // xorshift32 jump LUTs per chain count
+    uint32_t *d_jump16 = nullptr;   // M^16 (v1 two-chain PRNG)
     int pdm_persist = 1;      // 1: persistent McNaughton-scheduled kernels when thread == bank
     int pdm_warps_per_smsp = 1;
     int n_sm = CPROC_N_SM;

@@ -476,7 +476,10 @@ __global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws(const PdmV2Params p)
 //    P independent chains of its bank's generator, T/P ticks apart; the start
 //    of chain j+1 is the state T/P steps after chain j, obtained with a GF(2)
 //    jump table (xorshift is linear: M^(T/P) as 4 byte-indexed LUTs in smem).
-#define WS2_T 64
+#ifndef WS2_T_LOG
+#define WS2_T_LOG 6
+#endif
+#define WS2_T (1 << WS2_T_LOG)   // ticks per dither batch
 #define WS2_BAR_FULL 1           // barrier ids 1..NS
 #define WS2_BAR_EMPTY 5          // barrier ids 5..4+NS  (NS <= 4)
 template <int BASE, int N, int NS> __device__ __forceinline__ void bar_sync_slot(uint32_t s) {
@@ -625,8 +628,8 @@ __global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws2(const PdmV2Params p
 #pragma unroll
         for (int k = 0; k < K; ++k) r.s[0][k] = 0; }
     const uint32_t L = p.ctl_div_log;
-    const uint32_t period = 1u << (L - 6);                            // batches per control period (L >= 6)
-    uint32_t until = (p.count0 >> 6) == 0 ? 0 : period - (p.count0 >> 6);   // batches until the next boundary
+    const uint32_t period = 1u << (L - WS2_T_LOG);                    // batches per control period (L >= WS2_T_LOG)
+    uint32_t until = (p.count0 >> WS2_T_LOG) == 0 ? 0 : period - (p.count0 >> WS2_T_LOG);   // batches until the next boundary
     const uint32_t *sp_row = p.setpoints;
     const bool store = c < p.n;
     const uint32_t m1 = p.m1, m2 = ex.m2;
@@ -709,7 +712,7 @@ __global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws3(const PdmV2Params p
     const uint32_t cw = warp - (warp > prod_warp ? 1u : 0u);          // consumer index 0..B-1
     const uint32_t cl = cw * 32 + lane;                               // channel within the block
     const uint32_t bl = cl / B;                                       // its bank within the block
-    const uint32_t L = p.ctl_div_log, period = 1u << (L - 6);         // batches per control period (L >= 6)
+    const uint32_t L = p.ctl_div_log, period = 1u << (L - WS2_T_LOG); // batches per control period (L >= WS2_T_LOG)
     const uint32_t m1 = p.m1, m2 = ex.m2;
     const uint64_t batches_total = p.F / WS2_T;
     const uint32_t total = wk.groups * wk.slices;
@@ -745,7 +748,7 @@ __global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws3(const PdmV2Params p
 #pragma unroll
                 for (int k = 0; k < K; ++k) r.s[0][k] = 0; }
             // control divider at the first batch of the slice (count0 % WS2_T == 0)
-            const uint32_t cb = (uint32_t)(((p.count0 >> 6) + bt0) & (period - 1));
+            const uint32_t cb = (uint32_t)(((p.count0 >> WS2_T_LOG) + bt0) & (period - 1));
             uint32_t until = cb == 0 ? 0 : period - cb;               // batches until the next boundary
             const uint32_t *sp_row = p.setpoints ? p.setpoints + v2_rows_before(p.count0, 1u << L, bt0 * WS2_T) * p.n : nullptr;
             const bool store = c < p.n;
@@ -855,7 +858,7 @@ static int launch_v2_order(cproc_cuda_batch *b, PdmV2Params &p, bool fast, bool 
         return 0;
     }
     const uint64_t C = ceil_div_u64(p.n_banks, 32);
-    if (FASTQ && tpb && !dext && ctx->pdm_ws >= 2 && (p.F % WS2_T) == 0 && (p.count0 % WS2_T) == 0 && p.ctl_div_log >= 6) {
+    if (FASTQ && tpb && !dext && ctx->pdm_ws >= 2 && (p.F % WS2_T) == 0 && (p.count0 % WS2_T) == 0 && p.ctl_div_log >= WS2_T_LOG) {
         const unsigned grid = (unsigned)C;
         PdmV2Ws2Extra ex;
         ex.m2 = 0xFFFFFFFEu;
@@ -897,7 +900,8 @@ static int launch_v2_order(cproc_cuda_batch *b, PdmV2Params &p, bool fast, bool 
 #undef WS3_GO
             return 0;
         }
-#define WS2_GO(BB, FF, PP) do { if (ctx->pdm_slots >= 4) k_pdm_v2_ws2<K, BB, FF, PP, 4><<<grid, 32 * (BB + 1), 0, ctx->stream>>>(p, ex); \
+#define WS2_NS4 (WS2_T_LOG > 6 ? 2 : 4)      /* four slots of 128-tick batches exceed the static shared-memory limit */
+#define WS2_GO(BB, FF, PP) do { if (ctx->pdm_slots >= 4) k_pdm_v2_ws2<K, BB, FF, PP, WS2_NS4><<<grid, 32 * (BB + 1), 0, ctx->stream>>>(p, ex); \
                                 else k_pdm_v2_ws2<K, BB, FF, PP, 2><<<grid, 32 * (BB + 1), 0, ctx->stream>>>(p, ex); } while (0)
 #define WS2_P(BB, FF) do { if (P == 4) WS2_GO(BB, FF, 4); else if (P == 2) WS2_GO(BB, FF, 2); else WS2_GO(BB, FF, 1); } while (0)
 #define WS2_F(BB) do { if constexpr (K == 2) { if (form == 1) WS2_P(BB, 1); else if (form == 2) WS2_P(BB, 2); else WS2_P(BB, 0); } \
@@ -1177,10 +1181,14 @@ int launch_pdm_v1(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     const bool tpb = ctx->pdm_tpb && c.bank_size <= 4;
     const uint64_t C = ceil_div_u64(p.n_banks, 32);
     if (ctx->pdm_v1_chains == 2 && tpb && !dext && io->layout == CPROC_CUDA_TILED) {
-        const uint32_t *jt4 = nullptr;                        // jump_tables(4): tables for 16, 32, 48 steps; the first is M^16
-        int rc = jump_tables(ctx, 4, &jt4);
-        if (rc) return rc;
-        p.jump16 = jt4;
+        if (!ctx->d_jump16) {                                 // M^16 of xorshift32 as 4 byte-indexed LUTs
+            std::vector<uint32_t> h(1024);
+            jump_table_fill(h.data(), 16);
+            CK(ctx, cudaMalloc(&ctx->d_jump16, h.size() * 4));
+            CK(ctx, cudaMemcpyAsync(ctx->d_jump16, h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        p.jump16 = ctx->d_jump16;
     }
     if (tpb && !dext && (F & 127) == 0 && persist_wanted(ctx, C)) {
         int rc = sched_setup(b, &p.sched, C, F >> 7, 4 * ctx->pdm_warps_per_smsp);   // unit = 128 ticks = 4 words
