@@ -22,6 +22,7 @@
 #include <ctype.h>
 #include <dlfcn.h>
 #include <regex>
+#include <unordered_map>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -576,7 +577,13 @@ int cproc_graph_jit_get(cproc_cuda_batch *b, bool has_changed, cproc_graph_jit *
         j.state = 2;
         if (!nvrtc_load()) { b->jit_log = "libnvrtc not found"; return -1; }
         const std::string src = cproc_graph_jit_source(b->nodes, b->cfg.n_inputs, b->outs, has_changed);
+        // cubins are cached per process by their source text: a patcher that grows a graph node by
+        // node, or many batches of the same graph, compile once
+        static std::unordered_map<std::string, std::vector<char>> cubin_cache;
+        auto hit = cubin_cache.find(src);
+        if (hit != cubin_cache.end()) j.cubin = hit->second;
         void *prog = nullptr;
+        if (j.cubin.empty()) {
         if (g_nvrtc.create(&prog, src.c_str(), "cproc_graph.cu", 0, nullptr, nullptr)) { b->jit_log = "nvrtcCreateProgram failed"; return -1; }
         const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
         const int rc = g_nvrtc.compile(prog, 4, opts);
@@ -589,6 +596,8 @@ int cproc_graph_jit_get(cproc_cuda_batch *b, bool has_changed, cproc_graph_jit *
         j.cubin.resize(cs);
         g_nvrtc.cubin(prog, j.cubin.data());
         g_nvrtc.destroy(&prog);
+        cubin_cache[src] = j.cubin;
+        }
         if (cudaLibraryLoadData(&j.lib, j.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) { cudaGetLastError(); b->jit_log = "cudaLibraryLoadData failed"; return -1; }
         cudaKernel_t kq = nullptr;
         if (cudaLibraryGetKernel(&j.k_il, j.lib, "graph_interleaved") != cudaSuccess || cudaLibraryGetKernel(&j.k_pl, j.lib, "graph_planar") != cudaSuccess ||

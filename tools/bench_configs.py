@@ -217,11 +217,48 @@ def mix_bus_scaling(st, ctx, torch, dist, stream, dev, rank, world, reps=40):
             "note": "bit-exactness of both bus forms against the single-device oracle: tools/multi_gpu_mix.py"}
 
 
+def graph_bp5(st, ctx, hbm_peak, reps=3, layout="planar"):
+    """the reference's generated bp5 graph (edge -> acc -> acc, stm32f103/bp5_plugin.c:1-9),
+    parsed from its text and rendered by the kernel compiled for it."""
+    rng = np.random.default_rng(8)
+    rows, n_in, out_node, _ = st.graph_parse("""#define CPROC_NB_INPUTS 1
+        void cproc_update(w *input, w g) {
+            PROC_COND(g&0b1, n1, edge, NULL, NULL, .in = input[0]);
+            PROC_COND(g&0b1, n2, acc, NULL, NULL, .in = n1.out);
+            PROC_COND(g&0b1, n3, acc, NULL, NULL, .in = n2.out);
+            cproc_output(3, n3.out); }""")
+    N, F = 4 * 1024 * 1024, 256
+    d_in = ctx.dev_alloc(4 * N * F); d_out = ctx.dev_alloc(4 * N * F)
+    chunk = rng.integers(0, 2, (65536, F), dtype=np.uint32)
+    for k in range(N // 65536):
+        ctx.h2d(d_in + k * chunk.nbytes, chunk)
+    b = ctx.batch(st.GRAPH, N, nodes=rows, n_inputs=n_in, out_node=out_node, layout=st.PLANAR if layout == "planar" else st.INTERLEAVED)
+    ms = _time(ctx, lambda: b.run_dev(F, inp=d_in, out=d_out), reps)
+    b.free(); ctx.dev_free(d_in); ctx.dev_free(d_out)
+    return _hbm("generated cproc graph bp5 (edge -> acc -> acc), 4 Mi instances x 256 ticks, %s uint32 in/out, NVRTC kernel" % layout, N * F, "ticks", ms, 8.0,
+                hbm_peak, "4 B in + 4 B out per tick; 4 GiB in + 4 GiB out")
+
+
+def c1_long(st, ctx, reps=3):
+    """The reference's own shape made long: ONE voice of the test_cproc chain, 16 Mi ticks, time-parallel exact scan."""
+    rng = np.random.default_rng(9)
+    N, F = 1, 16 * 1024 * 1024
+    d_in = ctx.dev_alloc(4 * N * F); d_out = ctx.dev_alloc(4 * N * F)
+    ctx.h2d(d_in, rng.integers(0, 2, (N, F), dtype=np.uint32))
+    b = ctx.batch(st.GRAPH, N, nodes=[(st.NODE_EDGE, -1, 1), (st.NODE_ACC, 0, 1)], mode=1)
+    ms = _time(ctx, lambda: b.run_dev(F, inp=d_in, out=d_out), reps)
+    b.free(); ctx.dev_free(d_in); ctx.dev_free(d_out)
+    return {"config": "C1 long: test_cproc chain, 1 voice x 16 Mi ticks, time-parallel exact scan (CPROC_CUDA_GRAPH_SCAN)", "value": N * F / (ms * 1e-3),
+            "unit": "ticks/s", "ms": ms, "bound": "latency / launch (6 small kernels)", "note": "one thread walking the stream: 177 ms"}
+
+
 def run_all(st, ctx, hbm_peak):
     rows = []
     for fn in (lambda: c1(st, ctx), lambda: c2_v1(st, ctx), lambda: c3a(st, ctx, hbm_peak, layout="planar"), lambda: c3a(st, ctx, hbm_peak, layout="interleaved"),
                lambda: c3b(st, ctx), lambda: c4(st, ctx), lambda: c4p(st, ctx),
-               lambda: c5(st, ctx, hbm_peak, layout="tiled"), lambda: c5(st, ctx, hbm_peak, layout="planar")):
+               lambda: c5(st, ctx, hbm_peak, layout="tiled"), lambda: c5(st, ctx, hbm_peak, layout="planar"),
+               lambda: graph_bp5(st, ctx, hbm_peak, layout="planar"), lambda: graph_bp5(st, ctx, hbm_peak, layout="interleaved"),
+               lambda: c1_long(st, ctx)):
         try:
             rows.append(fn())
         except Exception as e:                       # never lose the headline line over a secondary row
