@@ -56,6 +56,18 @@ __device__ __forceinline__ float xvoice_tick_flag(XV &v, bool attack) {
     return __fmul_rn(lp, e);
 }
 
+// Tick of a chunk that lies entirely in the attack or entirely in the release phase, for an
+// envelope in [0, 1] and non-negative rates: e' = min(max(e + d, 0), 1) with d = +attack or
+// -release is then the same float as the two-branch form (the clamp that does not belong to the
+// phase is an identity), three instructions instead of two predicated pairs plus the predicate.
+__device__ __forceinline__ float xvoice_tick_uniform(XV &v, float d) {
+    float lp;
+    xvoice_svf(v, lp);
+    const float e = fminf(fmaxf(__fadd_rn(v.env, d), 0.0f), 1.0f);
+    v.env = e;
+    return __fmul_rn(lp, e);
+}
+
 __device__ __forceinline__ float xvoice_tick(XV &v) {
     const float xi = __int2float_rn((int32_t)v.phase);
     v.phase += v.inc;
@@ -184,7 +196,21 @@ __global__ void __launch_bounds__(XM_BLOCK, 4) k_xvoice_mix(const XVoiceParams p
                 amask = 0;
                 for (uint32_t k = 0; k < XM_CHUNK; ++k) amask |= (uint32_t)(v.t + k < v.gate) << k;
             }
-            if (cols == XM_CHUNK) {
+            // whole chunk in one phase (sustained or released voices: the steady state of a mix) for every
+            // lane still in the loop -> the three-instruction envelope
+            // (bit patterns: +0 <= env <= 1 and rates with a clear sign bit exclude NaN and -0.0, for which the
+            // extra clamp would not be an identity)
+            const bool uni = (amask == 0u || amask == 0xFFFFFFFFu) && __float_as_uint(v.att) <= 0x7F800000u && __float_as_uint(v.rel) <= 0x7F800000u &&
+                             __float_as_uint(v.env) <= 0x3F800000u;
+            if (cols == XM_CHUNK && __all_sync(__activemask(), uni)) {
+                const float d = amask ? v.att : -v.rel;
+#pragma unroll
+                for (int k = 0; k < XM_CHUNK; ++k) {
+                    const float y = xvoice_tick_uniform(v, d);
+                    aL[k] = __fmaf_rn(v.gl, y, aL[k]);
+                    aR[k] = __fmaf_rn(v.gr, y, aR[k]);
+                }
+            } else if (cols == XM_CHUNK) {
 #pragma unroll
                 for (int k = 0; k < XM_CHUNK; ++k) {
                     const float y = xvoice_tick_flag(v, (amask >> k) & 1u);

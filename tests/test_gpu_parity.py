@@ -970,6 +970,38 @@ def test_onepole_scan(st, ctx, oracle, layout, N, F, chunk):
         ctx.set_option("xvoice_chunk", 0)
 
 
+def test_xvoice_mix_uniform_phase_chunks(st, ctx, oracle):
+    """Mix-only render where whole warps sit in one envelope phase (sustain at 1, released at 0,
+    long attacks / releases) -- the three-instruction envelope path -- next to warps with gate
+    crossings, negative and -0.0 rates and out-of-range envelopes, which must take the general path:
+    final state of every voice bit-exact, mix within the stated tolerance."""
+    N, F = 148 * 4 * 128 * 2 + 77, 96
+    s0, prm = _xvoice_inputs(oracle, N)
+    third = N // 3
+    prm["gate_frames"][:third] = 10**6                       # attack for the whole render
+    prm["gate_frames"][third:2 * third] = 0                  # release from the first tick
+    s0["env"][:third:2] = 1.0                                # sustained
+    s0["env"][third:2 * third] = rng.uniform(0, 1, third).astype(np.float32)
+    s0["env"][third + 1:2 * third:5] = 0.0                   # already silent
+    s0["t"][third:2 * third] = rng.integers(0, 1000, third)
+    odd = slice(2 * third, N)                                 # general-path voices
+    prm["env_attack"][2 * third + 1:N:7] = -0.01
+    prm["env_release"][2 * third + 2:N:7] = np.float32(-0.0)
+    s0["env"][2 * third + 3:N:7] = 1.5
+    s0["env"][2 * third + 4:N:7] = np.float32(-0.0)
+    sa = s0.copy()
+    _, want_mix = oracle.xvoice_run(sa, prm, N, F, want_raw=False)
+    b = ctx.batch(st.XVOICE, N)
+    b.upload_state(s0.view(np.uint32).reshape(N, 5)); b.upload_param(prm.view(np.uint32).reshape(N, 8))
+    mix = np.zeros((2, F), np.float32)
+    b.run(F, mix=mix)
+    got = b.download_state().view(po.xvoice_state_dtype).reshape(N)
+    assert np.array_equal(got.view(np.uint32), sa.view(np.uint32))
+    w64, g64 = np.asarray(want_mix, np.float64).reshape(2, F), mix.astype(np.float64)
+    assert np.abs(g64 - w64).max() <= 1e-5 * np.abs(w64).max()
+    b.free()
+
+
 # ------------------------------------------------------------ device-resident path
 def test_run_dev_and_stream(st, ctx, oracle):
     """Device-pointer API and the chunked host stream give the same bytes as run()."""
