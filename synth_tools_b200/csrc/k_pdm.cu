@@ -1077,6 +1077,34 @@ __device__ __forceinline__ void v1_word2(const uint32_t (&sp)[B], uint32_t (&acc
     for (int j = 0; j < B; ++j) wv[j] = __brev(bits[j]);
 }
 
+// Software-pipelined form of the two-chain word: while the accumulators consume the 32 dither
+// values of word w (registers `cur`), the generator produces the 32 values of word w+1 (`nxt`) --
+// chain A ticks 0..15, chain B (started with the jump table M^16) ticks 16..31.  The accumulate
+// chain (one dependent add per tick) is then never paced by the 6-deep xorshift chain.
+// GEN = false for the last word of a group: nothing is generated beyond it.
+template <int B, bool GEN>
+__device__ __forceinline__ void v1_word_pipe(const uint32_t (&sp)[B], uint32_t (&acc)[B], const uint32_t (&cur)[32], uint32_t (&nxt)[32],
+                                             uint32_t &rng, const uint32_t (*jt)[256], uint32_t dmask, uint32_t (&wv)[B]) {
+    uint32_t bits[B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) bits[j] = 0;
+    uint32_t xa = rng, xb = GEN ? jump_apply(jt, rng) : 0u;          // rng = generator state at the start of word w+1
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (GEN) {
+            xa = xorshift32_step(xa); nxt[i] = xa & dmask;            // mod_pdm.c:261
+            xb = xorshift32_step(xb); nxt[16 + i] = xb & dmask;
+        }
+#pragma unroll
+        for (int j = 0; j < B; ++j) add_carry_shift(acc[j], bits[j], sp[j] + cur[2 * i]);       // :235-240
+#pragma unroll
+        for (int j = 0; j < B; ++j) add_carry_shift(acc[j], bits[j], sp[j] + cur[2 * i + 1]);
+    }
+    if (GEN) rng = xb;                                               // state at the start of word w+2
+#pragma unroll
+    for (int j = 0; j < B; ++j) wv[j] = __brev(bits[j]);
+}
+
 // words [w0, w1) of one thread's B channels
 template <int B, bool DEXT>
 __device__ __forceinline__ void v1_run_segment(const PdmV1Params &p, const uint32_t (&sp)[B], uint32_t (&acc)[B], uint32_t &rng,
@@ -1087,8 +1115,20 @@ __device__ __forceinline__ void v1_run_segment(const PdmV1Params &p, const uint3
         for (uint64_t g = w0; g < w1; g += 4) {
             uint32_t q[4][B];
             if (!DEXT && jt) {
+                // four words per TILED group; the first word's dither is generated up front, the last
+                // word of the group generates nothing (the next group starts over: one un-overlapped
+                // word in four keeps the generator state exact at every group boundary)
+                uint32_t da[32], db[32];
+                {
+                    uint32_t xa = rng, xb = jump_apply(jt, rng);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v1_word2<B>(sp, acc, rng, jt, p.dmask, q[k]);
+                    for (int i = 0; i < 16; ++i) { xa = xorshift32_step(xa); da[i] = xa & p.dmask; xb = xorshift32_step(xb); da[16 + i] = xb & p.dmask; }
+                    rng = xb;
+                }
+                v1_word_pipe<B, true>(sp, acc, da, db, rng, jt, p.dmask, q[0]);
+                v1_word_pipe<B, true>(sp, acc, db, da, rng, jt, p.dmask, q[1]);
+                v1_word_pipe<B, true>(sp, acc, da, db, rng, jt, p.dmask, q[2]);
+                v1_word_pipe<B, false>(sp, acc, db, da, rng, jt, p.dmask, q[3]);
             } else
 #pragma unroll
             for (int k = 0; k < 4; ++k) v1_word<B, DEXT>(sp, acc, rng, DEXT ? dext + ((g + k) << 5) : nullptr, p.dmask, q[k]);
