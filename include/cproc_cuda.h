@@ -34,6 +34,9 @@
  *
  * Threading: like the reference (one JACK RT thread / one ISR per graph), a
  * context and its batches have a single caller at a time.
+ *
+ * ABI version 2: cproc_cuda_node carries a second source (two-input processors),
+ * cproc_cuda_config an output-node list; graph front end, patcher and mix bus added.
  */
 #ifndef CPROC_CUDA_H
 #define CPROC_CUDA_H
