@@ -94,3 +94,48 @@ def test_c_host_generated_text_patcher_bus(tmp_path, oracle):
     assert [[int(x) for x in r[1:]] for r in tag("pstream")] == pw.tolist()
     assert tag("pget") == [[str(int(pst[2, 3]))]] and tag("pbad") == [["-1"]]
     assert tag("bus") == [["1", "0", "64"]] and out[-1] == "done"
+
+
+def test_jack_host_adapter_with_scripted_backend(tmp_path, oracle):
+    """synth_tools_b200/host/jack/jack_synth.c (16 parts x 64 voices, one batched render per
+    JACK period) built against tests/c/fakejack, which plays a fixed MIDI script through the process
+    callback.  Every part's audio must equal the oracle's sum_tick_saw replay bit for bit."""
+    pkg = os.path.join(ROOT, "synth_tools_b200")
+    exe = str(tmp_path / "jack_synth_fake")
+    subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "c", "fakejack"),
+                           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(pkg, "host", "jack"),
+                           os.path.join(pkg, "host", "jack", "jack_synth.c"), os.path.join(ROOT, "tests", "c", "fakejack", "fakejack.c"),
+                           "-o", exe, "-L", pkg, "-lcproc_cuda", "-Wl,-rpath," + pkg])
+    res = subprocess.run([exe], stdin=subprocess.DEVNULL, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    got = {}
+    for l in res.stdout.splitlines():
+        f = l.split()
+        if f and f[0] == "audio":
+            got[(int(f[1]), f[2])] = np.array([float.fromhex(x) for x in f[3:]], np.float32)
+    script = [(0, 0x90, 69, 100), (0, 0x90, 60, 100), (0, 0x93, 127, 1), (0, 0x9F, 0, 64), (1, 0x90, 72, 90), (2, 0x80, 60, 0),
+              (2, 0x93, 127, 0), (3, 0x9F, 12, 80), (4, 0x90, 69, 0), (4, 0x91, 40, 127), (5, 0x8F, 0, 0)]
+    F, P, V = 64, 16, 64
+    voices = np.zeros((P * V, 2), np.uint32)                  # {note_inc, note_state} per part, as struct synth
+    note2voice = np.zeros((P, 128), np.int64)
+    for period in range(6):
+        for (per, status, d1, d2) in script:
+            if per != period:
+                continue
+            part, kind = status & 0x0F, status & 0xF0
+            pv = voices[part * V:(part + 1) * V]
+            if kind == 0x90 and d2 != 0:                      # note on: first free voice, else voice 0 (synth.c:143-158)
+                free = np.flatnonzero(pv[:, 0] == 0)
+                v = int(free[0]) if len(free) else 0
+                note2voice[part, d1] = v
+                pv[v, 0] = oracle.note_to_inc(d1)
+            else:                                             # note off (:159-163)
+                v = note2voice[part, d1]
+                note2voice[part, d1] = 0
+                pv[v, 0] = 0
+        _, want = oracle.voice_bank_run(voices, P * V, V, po.MIX_SAW, F)      # advances the phases in place
+        for part in range(P):
+            g = got[(period, "part_%02d" % part)]
+            assert np.array_equal(g.view(np.uint32), want[part].view(np.uint32)), (period, part)
+    assert len(got) == 6 * 16
+    assert any(np.abs(got[(1, "part_00")]).max() > 0 for _ in [0]) and np.abs(got[(0, "part_07")]).max() == 0
