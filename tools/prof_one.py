@@ -42,7 +42,7 @@ def timed(fn):
     return best
 
 if which in ("grain", "grain_il"):
-    N, F = 1024 * 1024, 256
+    N, F = int(os.environ.get("GRAIN_N", 1024 * 1024)), 256
     d_in = ctx.dev_alloc(4 * N * F); d_out = ctx.dev_alloc(4 * N * F)
     chunk = rng.uniform(-1, 1, (65536, F)).astype(np.float32)
     for k in range(N // 65536):
