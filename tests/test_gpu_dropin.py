@@ -139,3 +139,40 @@ def test_jack_host_adapter_with_scripted_backend(tmp_path, oracle):
             assert np.array_equal(g.view(np.uint32), want[part].view(np.uint32)), (period, part)
     assert len(got) == 6 * 16
     assert any(np.abs(got[(1, "part_00")]).max() > 0 for _ in [0]) and np.abs(got[(0, "part_07")]).max() == 0
+
+
+def test_pd_external_with_scripted_backend(tmp_path, oracle):
+    """synth_tools_b200/host/pd/square_grain_b200~.c built against tests/c/fakepd.  Five
+    objects share one batch; a perform routine hands out the previous tick's result, so outlet block k
+    must equal the oracle's square_grain_proc output for inlet block k-1 (block 0 is silence), bit for
+    bit, including the in-place objects and the threshold message that arrives before tick 3."""
+    pkg = os.path.join(ROOT, "synth_tools_b200")
+    exe = str(tmp_path / "pd_fake")
+    subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "c", "fakepd"),
+                           "-I", os.path.join(ROOT, "include"), os.path.join(pkg, "host", "pd", "square_grain_b200~.c"),
+                           os.path.join(ROOT, "tests", "c", "fakepd", "fakepd.c"), "-o", exe, "-L", pkg, "-lcproc_cuda", "-lm", "-Wl,-rpath," + pkg])
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    got = {}
+    for l in res.stdout.splitlines():
+        f = l.split()
+        if f and f[0] == "out":
+            got[(int(f[1]), int(f[2]))] = np.array([float.fromhex(x) for x in f[3:]], np.float32)
+    G, B, T = 5, 64, 6
+    s = 2463534242
+    inp = np.zeros((T, G, B), np.float32)
+    for tick in range(T):
+        for g in range(G):
+            for t in range(B):
+                s = xs(s)
+                inp[tick, g, t] = np.float32(np.int32(np.uint32(s))) * np.float32(1.0 / 2147483648.0)
+    state = np.zeros(G, np.float32)
+    th = (np.float32(0.05) + np.float32(0.1) * np.arange(G, dtype=np.float32)).astype(np.float32)
+    for g in range(G):
+        assert np.all(got[(0, g)] == 0.0)
+    for tick in range(T - 1):                                 # inlet block `tick` comes out at tick + 1
+        if tick == 3:
+            th[2] = np.float32(0.4)                           # the message before tick 3: fabs(-0.4)
+        want = oracle.square_grain_run(state, th.copy(), G, B, np.ascontiguousarray(inp[tick]))
+        for g in range(G):
+            assert np.array_equal(got[(tick + 1, g)].view(np.uint32), want[g].view(np.uint32)), (tick, g)
