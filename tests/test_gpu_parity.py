@@ -89,6 +89,7 @@ def _v2_case(st, ctx, oracle, order, bank, N, F, layout, count0, use_setp, use_d
         ctx.set_option("pdm_slots", 2)
         ctx.set_option("pdm_ctas_per_sm", 4)
         ctx.set_option("pdm_slice_batches", 64)
+        ctx.set_option("pdm_planar_bulk", 1)
 
 
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
@@ -157,6 +158,14 @@ def test_pdm_v2_ws3_c2_shape(st, ctx, oracle, ctas, slice_b, F):
     """The C2 channel count (65,536 channels = 683 groups for 148 x ctas blocks)."""
     _v2_case(st, ctx, oracle, 2, 3, N=65536, F=F, layout=st.TILED, count0=0, use_setp=True, use_dext=False, ctl=7,
              opts={"pdm_ws": 3, "pdm_ctas_per_sm": ctas, "pdm_slice_batches": slice_b})
+
+
+@pytest.mark.parametrize("slice_b,F,bulk", [(4, 64 * 9, 1), (8, 64 * 21, 1), (4, 64 * 16, 1), (4, 64 * 9, 0)])
+def test_pdm_v2_ws3_planar_rows(st, ctx, oracle, slice_b, F, bulk):
+    """PLANAR duty rows of the dynamic-schedule kernel through the shared-memory row stage and bulk stores
+    (256-tick stages, a ragged last stage per slice, ragged channel count), and with the stage off."""
+    _v2_case(st, ctx, oracle, 2, 3, N=96 * 150 + 5, F=F, layout=st.PLANAR, count0=64, use_setp=True, use_dext=False, ctl=8,
+             opts={"pdm_ws": 3, "pdm_ctas_per_sm": 1, "pdm_slice_batches": slice_b, "pdm_planar_bulk": bulk})
 
 
 def test_pdm_v2_ws3_split_runs(st, ctx, oracle):
