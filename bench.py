@@ -13,7 +13,7 @@ tick, a fresh setpoint row every 4096 ticks; output one 8-bit duty per
 channel-sample.
 
 A "step" is one pass over the whole workload (2^40 channel-samples per GPU),
-rendered as 256 launches of 65,536 ticks into two alternating 4 GiB output
+rendered as 128 launches of 131,072 ticks into two alternating 8 GiB output
 slabs in HBM.  Multi-GPU is weak scaling: every rank renders its own 65,536
 channels (independent shards, no data-path collective).
 
@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 N_CH = 65536
 F_TOTAL = 16 * 1024 * 1024
-F_CHUNK = 65536
+F_CHUNK = 131072                     # ticks per launch: 8 GiB duty slab (two alternate); 36.9 rounds of work items per launch
 BANK = 3
 CTL_LOG = 12
 ALGO_BYTES_PER_SAMPLE = 1.0          # one uint8 duty per channel-sample
@@ -159,7 +159,7 @@ def workload_config():
     return {"workload": "C2 PDM v2 (mod_pdm_pwm.c glide + pdm2_update, banks of 3 share dither, setpoint row every "
                         "4096 ticks): 65,536 channels x 16 Mi samples per GPU, uint8 duty out",
             "channels_per_gpu": N_CH, "samples_per_channel": F_TOTAL, "launch_ticks": F_CHUNK,
-            "out_layout": "TILED [t/16][ch][16]", "l2": "inputs+outputs larger than L2 (4 GiB output slab per launch)"}
+            "out_layout": "TILED [t/16][ch][16]", "l2": "inputs+outputs larger than L2 (8 GiB output slab per launch)"}
 
 
 # --------------------------------------------------------------------------- native arm

@@ -10,7 +10,7 @@ python bench.py --steps 2 --warmup 3 > $O/bench_plain.json 2> $O/bench_plain.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/bench_launches.csv \
     python bench.py --steps 1 --warmup 1 > $O/bench_under_ncu.log 2>&1
 NCU="ncu --set full --clock-control none --import-source on -c 1"
-$NCU -k regex:k_pdm_v2_ws3 -s 2 -o $O/prof_pdm_v2_ws3 python tools/prof_pdm.py 65536 v2 > /dev/null 2>&1
+$NCU -k regex:k_pdm_v2_ws3 -s 2 -o $O/prof_pdm_v2_ws3 python tools/prof_pdm.py 131072 v2 > /dev/null 2>&1
 $NCU -k regex:k_grain_bulk -s 1 -o $O/prof_grain_bulk python tools/prof_one.py grain 1 > /dev/null 2>&1
 $NCU -k regex:k_grain_interleaved4 -s 1 -o $O/prof_grain_il4 python tools/prof_one.py grain_il 1 > /dev/null 2>&1
 $NCU -k regex:k_grain_mix3 -s 1 -o $O/prof_grain_mix3 python tools/prof_one.py gmix 1 > /dev/null 2>&1
