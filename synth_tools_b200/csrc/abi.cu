@@ -116,7 +116,7 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     else if (!strcmp(name, "planar_bulk")) ctx->planar_bulk = value != 0;
     else if (!strcmp(name, "graph_vec4")) ctx->graph_vec4 = value != 0;
     else if (!strcmp(name, "graph_jit")) ctx->graph_jit = value != 0;
-    else if (!strcmp(name, "grain_bulk")) { if (value < 0 || value > 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "grain_bulk must be 0..4"); ctx->grain_bulk = (int)value; }
+    else if (!strcmp(name, "grain_bulk")) { if (value < 0 || value > 5) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "grain_bulk must be 0..5"); ctx->grain_bulk = (int)value; }
     else if (!strcmp(name, "grain_vec4")) ctx->grain_vec4 = value != 0;
     else if (!strcmp(name, "grain_mix2")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "grain_mix2 must be 0..2"); ctx->grain_mix2 = (int)value; }
     else if (!strcmp(name, "xvoice_chunk")) { if (value < 0) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice_chunk must be >= 0"); ctx->xvoice_chunk = (int)value; }

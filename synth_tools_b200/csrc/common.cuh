@@ -41,7 +41,7 @@ struct cproc_cuda_ctx {
     int voice_block = 256;
     int grain_block = 128;
     int grain_blocks_per_sm = 2;
-    int grain_bulk = 1;       // planar square_grain: 0 register-transpose kernel; 1..4 bulk-copy kernel (tile/stage shapes)
+    int grain_bulk = 5;       // planar square_grain: 0 register-transpose kernel; 1..4 per-lane bulk-copy kernel (tile/stage shapes); 5 tensor-TMA kernel
     int grain_vec4 = 1;       // interleaved square_grain: four grains per thread when n % 4 == 0
     int grain_mix2 = 2;       // 0: float kernel; 1: register-accumulator / integer-threshold kernel; 2: predicate-state kernel
     int planar_bulk = 1;      // PLANAR pdm_raw / onepole streams through the bulk-staged template (planar_bulk.cuh)

@@ -17,6 +17,7 @@
 // k_grain_interleaved: [F][grain] streams are already coalesced.
 // k_grain_mix: config C3b -- input from a per-grain phasor, integer stereo mix.
 #include "common.cuh"
+#include <cuda.h>
 
 struct GrainParams {
     float *state;            // SoA [1][npad]
@@ -259,6 +260,126 @@ static int launch_grain_bulk(cproc_cuda_ctx *ctx, const GrainParams &p) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// k_grain_tma: the same lane-owns-a-row scheme with TENSOR TMA.  k_grain_bulk issues one bulk copy
+// per lane, which the hardware's uniform datapath executes one lane at a time (the SASS loops over
+// the 32 lanes around every UBLKCP: ~640 of the ~900 warp instructions per tile are copy issue).
+// Here the [grain][frame] stream is described once per launch by a 2-D tensor map (box = 32 frames
+// x 32 grains = one 128-byte row segment per lane, SWIZZLE_128B) and ONE elected lane issues two
+// cp.async.bulk.tensor loads and two stores per 64-frame tile.  The 128-byte swizzle XORs the
+// 16-byte chunk index with (row & 7): lane r finds chunk c of its row at r*128 + ((c ^ (r & 7)) << 4),
+// so the LDS.128 / STS.128 of eight consecutive lanes fall in eight different bank groups.
+// Out-of-range rows / frames are zero-filled on load and clipped on store by the TMA unit.
+#define GT_WARPS 2
+#define GT_STAGES 3
+#define GT_BOXB 4096                       // 32 rows x 128 B
+#define GT_STAGEB (2 * GT_BOXB)            // 64 frames
+__global__ void __launch_bounds__(GT_WARPS * 32) k_grain_tma(const GrainParams p, const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out) {
+    extern __shared__ __align__(1024) uint8_t gt_smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t g0 = ((uint64_t)blockIdx.x * GT_WARPS + warp) * 32;
+    if (g0 >= p.n) return;
+    const uint32_t rows = p.n - g0 < 32 ? (uint32_t)(p.n - g0) : 32u;
+    const bool mine = lane < rows;
+    const uint32_t sm0 = (smem_u32(gt_smem) + 1023u) & ~1023u;                 // swizzle atoms are 1 KiB
+    const uint32_t base = sm0 + warp * (GT_STAGES * GT_STAGEB);
+    const uint32_t bar0 = sm0 + GT_WARPS * GT_STAGES * GT_STAGEB + warp * (GT_STAGES * 8);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < GT_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    float state = mine ? p.state[g0 + lane] : 0.5f;
+    const float th = mine ? p.thresh[g0 + lane] : 0.0f;
+    const float nth = -th;
+    const uint32_t n_tiles = (uint32_t)((p.F + 63) / 64);
+    const uint64_t tmi = reinterpret_cast<uint64_t>(&tm_in), tmo = reinterpret_cast<uint64_t>(&tm_out);
+    auto cols_of = [&](uint32_t k) { const uint64_t left = p.F - (uint64_t)k * 64; return left < 64 ? (uint32_t)left : 64u; };
+    auto issue = [&](uint32_t k) {                                             // lane 0 only
+        const uint32_t s = k % GT_STAGES, nbox = cols_of(k) > 32 ? 2u : 1u;
+        mbar_expect_tx(bar0 + 8 * s, nbox * GT_BOXB);
+        for (uint32_t h = 0; h < nbox; ++h)
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(base + s * GT_STAGEB + h * GT_BOXB), "l"(tmi), "r"((int32_t)(k * 64 + h * 32)), "r"((int32_t)g0), "r"(bar0 + 8 * s) : "memory");
+    };
+    if (lane == 0) for (uint32_t k = 0; k < GT_STAGES - 2 && k < n_tiles; ++k) issue(k);
+#pragma unroll 1
+    for (uint32_t k = 0; k < n_tiles; ++k) {
+        if (k + GT_STAGES - 2 < n_tiles) {                                     // that stage last held tile k-2: its stores must have read it out
+            if (lane == 0) { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); issue(k + GT_STAGES - 2); }
+        }
+        const uint32_t s = k % GT_STAGES, cols = cols_of(k);
+        mbar_wait(bar0 + 8 * s, (k / GT_STAGES) & 1);
+        if (mine) {
+            const bool fast = (state == 0.5f || state == -0.5f) && th >= 0.0f;
+            bool neg = state < 0.0f;
+            for (uint32_t c = 0; c < cols / 4; ++c) {
+                const uint32_t a = base + s * GT_STAGEB + (c >> 3) * GT_BOXB + lane * 128 + (((c & 7) ^ (lane & 7)) << 4);
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+                if (fast) {
+                    v.x = grain_step_p(neg, v.x, th, nth); v.y = grain_step_p(neg, v.y, th, nth);
+                    v.z = grain_step_p(neg, v.z, th, nth); v.w = grain_step_p(neg, v.w, th, nth);
+                } else {                                                       // initial 0.0 (or any other) state value, negative threshold: literal form
+                    v.x = grain_step(state, v.x, th); v.y = grain_step(state, v.y, th);
+                    v.z = grain_step(state, v.z, th); v.w = grain_step(state, v.w, th);
+                }
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            }
+            if (fast) state = neg ? -0.5f : 0.5f;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t nbox = cols > 32 ? 2u : 1u;
+            for (uint32_t h = 0; h < nbox; ++h)
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                             ::"l"(tmo), "r"((int32_t)(k * 64 + h * 32)), "r"((int32_t)g0), "r"(base + s * GT_STAGEB + h * GT_BOXB) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    if (mine) p.state[g0 + lane] = state;
+}
+
+typedef CUresult (*cuTensorMapEncodeTiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                             const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static cuTensorMapEncodeTiled_t grain_encode_fn() {
+    static cuTensorMapEncodeTiled_t fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *q = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) fn = (cuTensorMapEncodeTiled_t)q;
+        else cudaGetLastError();
+    }
+    return fn;
+}
+
+// returns 1 when the TMA kernel was launched, 0 when the caller should use another kernel, < 0 on error
+static int launch_grain_tma(cproc_cuda_ctx *ctx, const GrainParams &p) {
+    cuTensorMapEncodeTiled_t enc = grain_encode_fn();
+    if (!enc) return 0;
+    CUtensorMap tin, tout;
+    const cuuint64_t dims[2] = {p.F, p.n}, strides[1] = {p.F * sizeof(float)};
+    const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+    if (enc(&tin, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)p.in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 0;
+    if (enc(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)p.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 0;
+    constexpr size_t smem = (size_t)GT_WARPS * GT_STAGES * GT_STAGEB + GT_WARPS * GT_STAGES * 8 + 1024;
+    static bool attr_set[64] = {};
+    if (!attr_set[ctx->device & 63]) {
+        CK(ctx, cudaFuncSetAttribute(k_grain_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[ctx->device & 63] = true;
+    }
+    k_grain_tma<<<(unsigned)ceil_div_u64(p.n, GT_WARPS * 32), GT_WARPS * 32, smem, ctx->stream>>>(p, tin, tout);
+    return 1;
+}
+
 int launch_square_grain(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     cproc_cuda_ctx *ctx = b->ctx;
     if (!io->in || !io->out) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "square_grain: in/out is NULL");
@@ -283,14 +404,20 @@ int launch_square_grain(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io
         if (vec4) k_grain_interleaved4<<<(unsigned)blocks, GI_BLOCK, smem, ctx->stream>>>(p);
         else k_grain_interleaved<<<(unsigned)blocks, GI_BLOCK, smem, ctx->stream>>>(p);
     } else if (bulk_ok) {
-        int rc;
-        switch (ctx->grain_bulk) {
+        int rc = 0;
+        // tensor TMA: rows of F * 4 bytes must be 16-byte multiples (F % 4, checked) and fewer than 2^32 elements per dimension
+        if (ctx->grain_bulk == 5 && p.F < (1ull << 31) && p.n < (1ull << 31)) {
+            rc = launch_grain_tma(ctx, p);
+            if (rc < 0) return rc;
+        }
+        if (rc == 1) { /* launched */ }
+        else switch (ctx->grain_bulk) {
         case 2: rc = launch_grain_bulk<128, 3>(ctx, p); break;
         case 3: rc = launch_grain_bulk<64, 4>(ctx, p); break;
         case 4: rc = launch_grain_bulk<32, 4>(ctx, p); break;
         default: rc = launch_grain_bulk<64, 3>(ctx, p); break;
         }
-        if (rc) return rc;
+        if (rc < 0) return rc;
     } else
         k_grain_planar<<<(unsigned)ceil_div_u64(p.n, GRAIN_WARPS * 32), GRAIN_WARPS * 32, 0, ctx->stream>>>(p);
     CK_LAUNCH(ctx, "k_grain");

@@ -762,7 +762,7 @@ def test_square_grain_interleaved_variants(st, ctx, oracle, vec4, N, F):
         ctx.set_option("grain_vec4", 1)
 
 
-@pytest.mark.parametrize("bulk", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("bulk", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("N,F,neg_th,odd", [(1000, 256, False, False), (77, 100, False, False), (300, 1024, True, False),
                                             (64, 4, False, True), (4097, 64, True, True), (31, 392, False, False)])
 def test_square_grain_bulk_variants(st, ctx, oracle, bulk, N, F, neg_th, odd):
@@ -773,7 +773,7 @@ def test_square_grain_bulk_variants(st, ctx, oracle, bulk, N, F, neg_th, odd):
     try:
         _square_grain_case(st, ctx, oracle, N, F, "PLANAR", neg_th, odd)
     finally:
-        ctx.set_option("grain_bulk", 1)
+        ctx.set_option("grain_bulk", 5)
 
 
 @pytest.mark.parametrize("gen", [0, 1, 2])

@@ -48,7 +48,7 @@ if "grain" in which:
         ctx.h2d(d_in + k * chunk.nbytes, chunk)
     th = rng.uniform(0.05, 0.5, (N, 1)).astype(np.float32)
     for layout, label, bulk in ((st.PLANAR, "planar (register transpose)", 0), (st.PLANAR, "planar (bulk 64x3)", 1), (st.PLANAR, "planar (bulk 128x3)", 2),
-                                (st.PLANAR, "planar (bulk 64x4)", 3), (st.PLANAR, "planar (bulk 32x4)", 4), (st.INTERLEAVED, "interleaved (1 grain/thread)", -1), (st.INTERLEAVED, "interleaved (4 grains/thread)", -2)):
+                                (st.PLANAR, "planar (bulk 64x4)", 3), (st.PLANAR, "planar (bulk 32x4)", 4), (st.PLANAR, "planar (tensor TMA 64x3)", 5), (st.INTERLEAVED, "interleaved (1 grain/thread)", -1), (st.INTERLEAVED, "interleaved (4 grains/thread)", -2)):
         if bulk >= 0: ctx.set_option("grain_bulk", bulk)
         else: ctx.set_option("grain_vec4", -bulk - 1)
         b = ctx.batch(st.SQUARE_GRAIN, N, layout=layout); b.upload_param(th)
