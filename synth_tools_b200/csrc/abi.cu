@@ -113,7 +113,7 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     else if (!strcmp(name, "pdm_slice_batches")) { if (value < 2 || value > 65536) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_slice_batches must be 2..65536"); ctx->pdm_slice_batches = (int)value; }
     else if (!strcmp(name, "pdm_form")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_form must be 0..2"); ctx->pdm_form = (int)value; }
     else if (!strcmp(name, "grain_blocks_per_sm")) { if (value < 1 || value > 16) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "grain_blocks_per_sm must be 1..16"); ctx->grain_blocks_per_sm = (int)value; }
-    else if (!strcmp(name, "planar_bulk")) ctx->planar_bulk = value != 0;
+    else if (!strcmp(name, "planar_bulk")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "planar_bulk must be 0..2"); ctx->planar_bulk = (int)value; }
     else if (!strcmp(name, "graph_vec4")) ctx->graph_vec4 = value != 0;
     else if (!strcmp(name, "graph_jit")) ctx->graph_jit = value != 0;
     else if (!strcmp(name, "grain_bulk")) { if (value < 0 || value > 5) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "grain_bulk must be 0..5"); ctx->grain_bulk = (int)value; }

@@ -44,7 +44,7 @@ struct cproc_cuda_ctx {
     int grain_bulk = 5;       // planar square_grain: 0 register-transpose kernel; 1..4 per-lane bulk-copy kernel (tile/stage shapes); 5 tensor-TMA kernel
     int grain_vec4 = 1;       // interleaved square_grain: four grains per thread when n % 4 == 0
     int grain_mix2 = 2;       // 0: float kernel; 1: register-accumulator / integer-threshold kernel; 2: predicate-state kernel
-    int planar_bulk = 1;      // PLANAR pdm_raw / onepole streams through the bulk-staged template (planar_bulk.cuh)
+    int planar_bulk = 2;      // PLANAR pdm_raw / onepole / pwm streams through planar_bulk.cuh: 0 off, 1 per-lane bulk copies, 2 tensor TMA
     int graph_vec4 = 1;       // interleaved generated graphs: four instances per thread when n % 4 == 0
     int graph_jit = 1;        // 1: generated graphs are compiled with NVRTC; 0: table-driven kernel
     int xvoice_block = 128;

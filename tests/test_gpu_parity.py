@@ -335,6 +335,49 @@ def test_pwm_layouts(st, ctx, oracle, N, F, layout):
     b.free()
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("N,F", [(130, 320), (33, 64), (1000, 1024), (70, 100), (5, 36)])
+def test_planar_template_modes(st, ctx, oracle, mode, N, F):
+    """pdm raw (with and without an input stream), one-pole and pwm through the scalar kernels (0), the
+    per-lane bulk-copy template (1) and its tensor-TMA form (2): ragged instance counts and tiles."""
+    ctx.set_option("planar_bulk", mode)
+    try:
+        for order in (1, 3):
+            s0 = rng.integers(0, 2**32, (N, order), dtype=np.uint32)
+            inp = rng.integers(0, 2**32, (N, F), dtype=np.uint32)
+            dith = rng.integers(0, 1024, F, dtype=np.uint32)
+            cst = rng.integers(0x40000000, 0xC0000000, (N, 1), dtype=np.uint32)
+            for use_in in (True, False):
+                sa = s0.copy()
+                want = oracle.pdm_run(order, sa, N, F, inp if use_in else None, cst[:, 0].copy(), 24, dith)
+                b = ctx.batch(st.PDM, N, order=order, out_shift=24)
+                b.upload_state(s0); b.upload_param(cst)
+                out = np.zeros((N, F), np.uint32)
+                b.run(F, inp=inp if use_in else None, in2=dith, out=out)
+                assert np.array_equal(out, want) and np.array_equal(b.download_state(), sa), (order, use_in)
+                b.free()
+        x = rng.uniform(-1, 1, (N, F)).astype(np.float32)
+        a = rng.uniform(0.001, 0.9, (N, 1)).astype(np.float32); y0 = rng.uniform(-1, 1, (N, 1)).astype(np.float32)
+        ya = y0[:, 0].copy()
+        want = oracle.onepole_run(ya, a[:, 0].copy(), N, F, x)
+        b = ctx.batch(st.ONEPOLE, N); b.upload_state(y0); b.upload_param(a)
+        out = np.zeros((N, F), np.float32)
+        b.run(F, inp=x, out=out)
+        assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
+        b.free()
+        if F % 16 == 0:
+            ph0 = rng.integers(0, 1 << 24, (N, 1), dtype=np.uint32); sp = rng.integers(0, 1 << 16, (N, 1), dtype=np.uint32)
+            pa = ph0[:, 0].copy()
+            want = oracle.pwm_run(pa, sp[:, 0].copy(), N, F)
+            b = ctx.batch(st.PWM, N); b.upload_state(ph0); b.upload_param(sp)
+            out = np.zeros((N, F), np.uint8)
+            b.run(F, out=out)
+            assert np.array_equal(out, want) and np.array_equal(b.download_state()[:, 0], pa)
+            b.free()
+    finally:
+        ctx.set_option("planar_bulk", 2)
+
+
 def test_pwm(st, ctx, oracle):
     N, F = 77, 500
     ph0 = rng.integers(0, 1 << 24, (N, 1), dtype=np.uint32)

@@ -117,3 +117,16 @@ elif which == "graph_long":
         ms = timed(lambda: b.run_dev(F, inp=d_in, out=d_out))
         print("test_cproc graph %d x %d (%s): %.3f ms  %.2f G ticks/s" % (N, F, label, ms, N * F / ms / 1e6))
         b.free()
+elif which == "pdmraw":
+    # pdm2_update on an input stream, 1 Mi channels x 1024 ticks, PLANAR uint32 in/out (8 B per sample)
+    N, F = 1024 * 1024, 1024
+    d_in = ctx.dev_alloc(4 * N * F); d_out = ctx.dev_alloc(4 * N * F)
+    chunk = rng.integers(0, 2**32, (16384, F), dtype=np.uint32)
+    for k in range(N // 16384):
+        ctx.h2d(d_in + k * chunk.nbytes, chunk)
+    for mode in (0, 1, 2):
+        ctx.set_option("planar_bulk", mode)
+        b = ctx.batch(st.PDM, N, order=2, out_shift=24)
+        ms = timed(lambda: b.run_dev(F, inp=d_in, out=d_out))
+        print("pdm raw planar_bulk=%d: %.3f ms  %.0f GB/s" % (mode, ms, 8 * N * F / ms / 1e6))
+        b.free()
