@@ -120,6 +120,7 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     else if (!strcmp(name, "grain_vec4")) ctx->grain_vec4 = value != 0;
     else if (!strcmp(name, "grain_mix2")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "grain_mix2 must be 0..2"); ctx->grain_mix2 = (int)value; }
     else if (!strcmp(name, "xvoice_chunk")) { if (value < 0) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice_chunk must be >= 0"); ctx->xvoice_chunk = (int)value; }
+    else if (!strcmp(name, "xvoice_closed")) ctx->xvoice_closed = value ? 1 : 0;
     else if (!strcmp(name, "xvoice_groups")) { if (value < 0 || value > 8) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice_groups must be 0..8"); ctx->xvoice_groups = (int)value; }
     else if (!strcmp(name, "pdm_slots")) { if (value != 2 && value != 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_slots must be 2 or 4"); ctx->pdm_slots = (int)value; }
     else if (!strcmp(name, "pdm_chains")) { if (value != 1 && value != 2 && value != 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_chains must be 1, 2 or 4"); ctx->pdm_chains = (int)value; }

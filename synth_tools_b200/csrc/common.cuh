@@ -50,6 +50,7 @@ struct cproc_cuda_ctx {
     int xvoice_block = 128;
     int xvoice_groups = 0;    // XVOICE_SCAN: variant groups pipelined over the two streams (0 = automatic)
     int xvoice_chunk = 0;     // XVOICE_SCAN: frames per time chunk (0 = automatic)
+    int xvoice_closed = 1;    // XVOICE_SCAN: zero-state pass in closed form per phase wrap (0: ticked in fp64)
 };
 
 // NVRTC-compiled kernels of one graph (graph_front.cu); state 0 = not tried, 1 = ready, 2 = failed

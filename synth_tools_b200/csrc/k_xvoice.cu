@@ -289,12 +289,14 @@ struct SweepParams {
     uint64_t L, C;
     uint64_t i0, i1;         // variants [i0, i1) of this launch (variant groups are pipelined over two streams)
     uint64_t zoff, zi1;      // fused render: thread (i, c) also runs the zero-state pass of variant i + zoff (< zi1)
-    double2 *z;              // [C-1][n] zero-state response of chunk c
+    double2 *z;              // [n][C-1] zero-state response of chunk c
     float2 *s0;              // [C][n]   (lp, bp) at the first frame of chunk c
     float *e0;               // [C][n]   env at the first frame of chunk c
     uint32_t *ph0, *t0;      // [n] snapshot of the initial phase / frame counter
     uint32_t *cst;           // [n] first chunk from which the envelope never changes again (C if none)
     float *est;              // [n] that final envelope value
+    double *tab;             // [10 + 6 nlev][n] per-variant segment maps of the closed-form zero-state pass (k_sweep_pre)
+    int nlev, closed;
 };
 
 // One fp64 tick of the zero-state recurrence on the integer-valued input.
@@ -305,6 +307,115 @@ __device__ __forceinline__ void zsr_tick(uint32_t &phase, uint32_t inc, double f
     const double u = fma(nq, bp, x);
     lp = fma(f, bp, lp);
     bp = fma(f, u - lp, bp);
+}
+
+// ---- closed-form zero-state response ------------------------------------------------------------
+// The SVF tick is s' = A s + b x with A = [[1, f], [-f, 1 - f q - f^2]], b = (0, f), and the input is
+// a sawtooth: x_t = x0 + t inc - 2^32 w_t, w_t = number of times the signed phase has wrapped up to
+// tick t.  By linearity the zero-state response after L ticks is
+//     s_L = P_L x0 + Q_L inc - 2^32 y_L,
+//     P_m = sum_{t<m} A^(m-1-t) b        (response to a unit step),
+//     Q_m = sum_{t<m} t A^(m-1-t) b      (response to a unit ramp),
+// and y is the response to the staircase w_t: constant between wraps, so it advances one whole gap at
+// a time, y <- A^g y + j P_g.  Consecutive wraps are k or k+1 ticks apart (k = floor(2^32 / inc)); a
+// remainder walk in integer arithmetic says which.  The last stretch up to L has an arbitrary length
+// e <= L and is applied from the per-variant table of the maps of 2^i ticks, one step per set bit of e.
+// k_sweep_pre builds, per variant: (P_L, Q_L), (A^k, P_k) when k < L, and (A^(2^i), P_(2^i)).
+// Cost per (variant, chunk): ~12 fp64 operations per WRAP instead of 4 per TICK (a 4 kHz voice wraps
+// every 11 ticks, a 32 Hz voice every 1500), and the tick's int -> float rounding of x (|err| <= 2^-25
+// of full scale, zero mean) is replaced by the exact integer: -150 dB, far inside the 120 dB bound.
+struct ZSeg { double a11, a12, a21, a22, p1, p2, q1, q2, m; };
+// `x` ticks, then `y` ticks
+__device__ __forceinline__ ZSeg zseg_then(const ZSeg &x, const ZSeg &y) {
+    ZSeg r;
+    r.a11 = y.a11 * x.a11 + y.a12 * x.a21; r.a12 = y.a11 * x.a12 + y.a12 * x.a22;
+    r.a21 = y.a21 * x.a11 + y.a22 * x.a21; r.a22 = y.a21 * x.a12 + y.a22 * x.a22;
+    r.p1 = y.a11 * x.p1 + y.a12 * x.p2 + y.p1; r.p2 = y.a21 * x.p1 + y.a22 * x.p2 + y.p2;
+    r.q1 = y.a11 * x.q1 + y.a12 * x.q2 + x.m * y.p1 + y.q1; r.q2 = y.a21 * x.q1 + y.a22 * x.q2 + x.m * y.p2 + y.q2;
+    r.m = x.m + y.m;
+    return r;
+}
+// k = floor(2^32 / inc) and rho = 2^32 - k inc, inc > 0
+__device__ __forceinline__ void wrap_period(uint32_t inc, uint64_t &k, uint32_t &rho) {
+    k = 0xFFFFFFFFu / inc; rho = 0u - (uint32_t)k * inc;
+    if (rho == inc) { ++k; rho = 0; }
+}
+#define ZT_FIXED 10
+__global__ void __launch_bounds__(128) k_sweep_pre(const SweepParams p) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, n = p.x.n;
+    if (i >= n) return;
+    const uint32_t inc = p.x.prm[i];
+    const double f = (double)__uint_as_float(p.x.prm[p.x.npad + i]), q = (double)__uint_as_float(p.x.prm[2 * p.x.npad + i]);
+    ZSeg lev = {1.0, f, -f, 1.0 - f * q - f * f, 0.0, f, 0.0, 0.0, 1.0};
+    const ZSeg id = {1.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    ZSeg sl = id, sk = id;
+    uint64_t k = 0; uint32_t rho = 0;
+    if (inc) wrap_period(inc, k, rho);
+    const bool kuse = inc && k < p.L;
+    double *t = p.tab + i;
+    for (int l = 0; l < p.nlev; ++l) {
+        double *d = t + (uint64_t)(ZT_FIXED + 6 * l) * n;
+        d[0] = lev.a11; d[n] = lev.a12; d[2 * n] = lev.a21; d[3 * n] = lev.a22; d[4 * n] = lev.p1; d[5 * n] = lev.p2;
+        if ((p.L >> l) & 1) sl = zseg_then(sl, lev);
+        if (kuse && ((k >> l) & 1)) sk = zseg_then(sk, lev);
+        lev = zseg_then(lev, lev);
+    }
+    t[0] = sl.p1; t[n] = sl.p2; t[2 * n] = sl.q1; t[3 * n] = sl.q2;
+    t[4 * n] = sk.a11; t[5 * n] = sk.a12; t[6 * n] = sk.a21; t[7 * n] = sk.a22; t[8 * n] = sk.p1; t[9 * n] = sk.p2;
+}
+
+// zero-state response of full chunk c of variant i, scaled like the ticked pass
+__device__ __noinline__ double2 zsr_closed(const SweepParams &p, uint64_t i, uint64_t c) {
+    const uint64_t n = p.x.n, L = p.L;
+    const uint32_t inc = __ldg(p.x.prm + i);
+    const uint32_t ph = p.x.st[i] + (uint32_t)(c * L) * inc;
+    const uint32_t u0 = ph ^ 0x80000000u;                       // signed phase + 2^31: wraps when it passes 2^32
+    const uint32_t W = (uint32_t)(((uint64_t)u0 + (L - 1) * (uint64_t)inc) >> 32);
+    const double *t = p.tab + i;
+    double y1 = 0.0, y2 = 0.0;
+    if (W) {
+        uint64_t at = (uint64_t)(~u0 / inc) + 1;               // tick of the first wrap: smallest t with u0 + t inc >= 2^32
+        if (W > 1) {
+            uint32_t r = u0 + (uint32_t)at * inc;              // remainder just after a wrap, in [0, inc)
+            uint64_t k; uint32_t rho;
+            wrap_period(inc, k, rho);
+            const double k11 = t[4 * n], k12 = t[5 * n], k21 = t[6 * n], k22 = t[7 * n], pk1 = t[8 * n], pk2 = t[9 * n];
+            const double *a = t + (uint64_t)ZT_FIXED * n;        // one tick
+            const double a12 = a[n], a21 = a[2 * n], a22 = a[3 * n], b2 = a[5 * n];
+            for (uint32_t j = 1; j < W; ++j) {
+                const double w = (double)j;
+                const double n1 = fma(k11, y1, fma(k12, y2, w * pk1)), n2 = fma(k21, y1, fma(k22, y2, w * pk2));
+                y1 = n1; y2 = n2; at += k;
+                if (r >= rho) r -= rho;
+                else {                                           // k + 1 ticks to the next wrap
+                    r = r - rho + inc; at += 1;
+                    const double m1 = fma(a12, y2, y1), m2 = fma(a21, y1, fma(a22, y2, w * b2));
+                    y1 = m1; y2 = m2;
+                }
+            }
+        }
+        const double w = (double)W;
+        const double *d = t + (uint64_t)ZT_FIXED * n;
+        for (uint64_t e = L - at; e; e >>= 1, d += 6 * n) {
+            if (e & 1) {
+                const double n1 = fma(d[0], y1, fma(d[n], y2, w * d[4 * n])), n2 = fma(d[2 * n], y1, fma(d[3 * n], y2, w * d[5 * n]));
+                y1 = n1; y2 = n2;
+            }
+        }
+    }
+    const double x0 = (double)(int32_t)ph, di = (double)inc;
+    const double lp = fma(t[0], x0, fma(t[2 * n], di, -4294967296.0 * y1)), bp = fma(t[n], x0, fma(t[3 * n], di, -4294967296.0 * y2));
+    return make_double2(lp * 0x1p-31, bp * 0x1p-31);
+}
+
+// Closed form, one thread per (variant, chunk) with the LANES OVER THE CHUNKS of one variant: every
+// lane of a warp has the same increment, hence the same number of wraps (+-1) and the same table rows
+// (broadcast loads) -- no divergence, where lanes over variants pay for the highest note of the 32.
+__global__ void __launch_bounds__(128) k_sweep_zsr_closed(const SweepParams p, uint32_t blocks_per_variant) {
+    const uint64_t i = p.i0 + blockIdx.x / blocks_per_variant;
+    const uint64_t c = (uint64_t)(blockIdx.x % blocks_per_variant) * 128 + threadIdx.x;
+    if (c + 1 >= p.C) return;
+    p.z[i * (p.C - 1) + c] = zsr_closed(p, i, c);
 }
 
 // Zero-state response of every full chunk, fp64.  The SVF is linear, so the recurrence is
@@ -323,7 +434,7 @@ __global__ void __launch_bounds__(128) k_sweep_zsr(const SweepParams p) {
     for (uint64_t k = 0; k < p.L; ++k) {                        // chunks 0..C-2 are full
         zsr_tick(phase, inc, f, nq, lp, bp);
     }
-    p.z[c * p.x.n + i] = make_double2(lp * 0x1p-31, bp * 0x1p-31);
+    p.z[i * (p.C - 1) + c] = make_double2(lp * 0x1p-31, bp * 0x1p-31);
 }
 
 // env after `count` more ticks, same operations as xvoice_tick, fixed points skipped
@@ -401,7 +512,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_sweep_scan(const SweepParam
     const uint64_t c0 = lane * K < p.C ? lane * K : p.C, c1 = c0 + K < p.C ? c0 + K : p.C;
     Aff t = {1.0, 0.0, 0.0, 1.0, 0.0, 0.0};
     for (uint64_t c = c0; c < c1 && c + 1 < p.C; ++c) {
-        const double2 z = p.z[c * n + i];
+        const double2 z = p.z[i * (p.C - 1) + c];
         const double w1 = m11 * t.w1 + m12 * t.w2 + z.x, w2 = m21 * t.w1 + m22 * t.w2 + z.y;
         const double p11 = m11 * t.p11 + m12 * t.p21, p12 = m11 * t.p12 + m12 * t.p22;
         const double p21 = m21 * t.p11 + m22 * t.p21, p22 = m21 * t.p12 + m22 * t.p22;
@@ -430,7 +541,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_sweep_scan(const SweepParam
     for (uint64_t c = c0; c < c1; ++c) {
         p.s0[c * n + i] = make_float2((float)lp, (float)bp);
         if (c + 1 < p.C) {
-            const double2 z = p.z[c * n + i];
+            const double2 z = p.z[i * (p.C - 1) + c];
             const double nl = m11 * lp + m12 * bp + z.x, nb = m21 * lp + m22 * bp + z.y;
             lp = nl; bp = nb;
         }
@@ -441,7 +552,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_sweep_scan(const SweepParam
 // variant of the group two renders ahead).  The render is HBM-write bound and leaves
 // ~40% of the issue slots and the whole DP pipe idle; the zero-state pass is pure
 // arithmetic, so inside the same instruction stream it is hidden behind the stores.
-template <bool TILED, bool ZSR>
+template <bool TILED, int ZSR>   // ZSR: 0 none, 1 ticked beside the render, 2 closed form before it
 __global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) {
     constexpr int PT = 32;                               // PLANAR: frames staged per pass (256-byte runs per stream; 128-byte runs cost 20% of the bandwidth)
     __shared__ __align__(16) float2 tile[TILED ? 1 : XV_WARPS][TILED ? 1 : 32][TILED ? 1 : PT + 1];   // [warp][stream][frame]
@@ -463,9 +574,13 @@ __global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) 
     }
     // zero-state duty: chunk c of variant j (chunks 0..C-2 are full, the last one needs no response)
     const uint64_t j = i + p.zoff;
-    const bool zmine = ZSR && mine && j < p.zi1 && c + 1 < p.C;
+    bool zmine = ZSR != 0 && mine && j < p.zi1 && c + 1 < p.C;
     uint32_t zph = 0, zinc = 0;
     double zf = 0.0, znq = 0.0, zlp = 0.0, zbp = 0.0;
+    if (ZSR == 2) {                                       // closed form: a few operations per wrap, done before the render loop
+        if (zmine) p.z[j * (p.C - 1) + c] = zsr_closed(p, j, c);
+        zmine = false;
+    }
     if (zmine) {
         zinc = __ldg(p.x.prm + j);
         zf = (double)__uint_as_float(__ldg(p.x.prm + npad + j));
@@ -478,7 +593,7 @@ __global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) 
             const float l0 = __fmul_rn(v.gl, y0), r0 = __fmul_rn(v.gr, y0);
             const float y1 = xvoice_tick(v);
             const float l1 = __fmul_rn(v.gl, y1), r1 = __fmul_rn(v.gr, y1);
-            if (ZSR) { zsr_tick(zph, zinc, zf, znq, zlp, zbp); zsr_tick(zph, zinc, zf, znq, zlp, zbp); }   // L is even
+            if (ZSR == 1) { zsr_tick(zph, zinc, zf, znq, zlp, zbp); zsr_tick(zph, zinc, zf, znq, zlp, zbp); }   // L is even
             if (mine) st_v4_stream(p.x.raw + (((t >> 1) * n + i) << 2),
                                    make_uint4(__float_as_uint(l0), __float_as_uint(r0), __float_as_uint(l1), __float_as_uint(r1)));
         }
@@ -489,7 +604,7 @@ __global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) 
             for (uint32_t k = 0; k < cols; ++k) {
                 const float y = xvoice_tick(v);
                 tile[warp][lane][k] = make_float2(__fmul_rn(v.gl, y), __fmul_rn(v.gr, y));
-                if (ZSR) zsr_tick(zph, zinc, zf, znq, zlp, zbp);
+                if (ZSR == 1) zsr_tick(zph, zinc, zf, znq, zlp, zbp);
             }
             __syncwarp();
             // PT/2 lanes x 16 B cover the PT frames of one stream; a warp instruction writes 64/PT streams
@@ -510,7 +625,7 @@ __global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) 
             __syncwarp();
         }
     }
-    if (zmine) p.z[c * n + j] = make_double2(zlp * 0x1p-31, zbp * 0x1p-31);
+    if (zmine) p.z[j * (p.C - 1) + c] = make_double2(zlp * 0x1p-31, zbp * 0x1p-31);
     if (mine && c == p.C - 1) {                          // the last chunk leaves the voice state
         uint32_t *s = p.x.st + i;
         s[0] = v.phase; s[npad] = __float_as_uint(v.lp); s[2 * npad] = __float_as_uint(v.bp);
@@ -527,7 +642,10 @@ static int launch_xvoice_scan(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_
     cproc_cuda_ctx *ctx = b->ctx;
     const uint64_t n = b->n, C = ceil_div_u64(F, L);
     const size_t bz = sizeof(double2) * (C - 1) * n, bs = sizeof(float2) * C * n, be = sizeof(float) * C * n, bw = sizeof(uint32_t) * n;
-    const size_t need = bz + bs + be + 4 * bw + 96;
+    int nlev = 0;
+    while ((L >> nlev) != 0) ++nlev;
+    const size_t bt = sizeof(double) * n * (ZT_FIXED + 6 * (size_t)nlev);
+    const size_t need = bz + bs + be + 4 * bw + bt + 128;
     if (b->cap_scratch < need) {
         if (b->d_scratch) cudaFree(b->d_scratch);
         b->d_scratch = nullptr; b->cap_scratch = 0;
@@ -545,7 +663,8 @@ static int launch_xvoice_scan(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_
     p.ph0 = (uint32_t *)w; w += (bw + 15) & ~(size_t)15;
     p.t0 = (uint32_t *)w; w += (bw + 15) & ~(size_t)15;
     p.cst = (uint32_t *)w; w += (bw + 15) & ~(size_t)15;
-    p.est = (float *)w;
+    p.est = (float *)w; w += (bw + 15) & ~(size_t)15;
+    p.tab = (double *)w; p.nlev = nlev; p.closed = ctx->xvoice_closed;
     if (groups > 8) groups = 8;
     if (groups < 1) groups = 1;
     const uint64_t per = ceil_div_u64(ceil_div_u64(n, groups), 128) * 128;
@@ -567,12 +686,19 @@ static int launch_xvoice_scan(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_
     p.i0 = 0; p.i1 = n;
     k_sweep_env<<<(unsigned)ceil_div_u64(n, 128), 128, 0, ctx->stream>>>(p);   // only the renders need it: beside the aux-stream passes
     CK_LAUNCH(ctx, "k_sweep_env");
+    if (p.closed && C > 1) {
+        k_sweep_pre<<<(unsigned)ceil_div_u64(n, 128), 128, 0, pre>>>(p);
+        CK_LAUNCH(ctx, "k_sweep_pre");
+    }
     // zero-state pass as its own kernel: every group when not pipelined, else the first two
     for (uint64_t g = 0; g < groups; ++g) {
         range(g, &p.i0, &p.i1);
         const unsigned gx = (unsigned)ceil_div_u64(p.i1 - p.i0, 128);
         if (C > 1 && (!piped || g < 2)) {
-            k_sweep_zsr<<<dim3(gx, (unsigned)(C - 1)), 128, 0, pre>>>(p);
+            if (p.closed) {
+                const uint32_t bpv = (uint32_t)ceil_div_u64(C - 1, 128);
+                k_sweep_zsr_closed<<<(unsigned)((p.i1 - p.i0) * bpv), 128, 0, pre>>>(p, bpv);
+            } else k_sweep_zsr<<<dim3(gx, (unsigned)(C - 1)), 128, 0, pre>>>(p);
             CK_LAUNCH(ctx, "k_sweep_zsr");
         }
         if (!piped || g < 2) {
@@ -589,11 +715,13 @@ static int launch_xvoice_scan(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_
         if (piped) CK(ctx, cudaStreamWaitEvent(ctx->stream, ev_scan[g], 0));     // join: start states of this group
         const dim3 grid(gx, (unsigned)C);
         if (io->layout == CPROC_CUDA_TILED) {
-            if (duty) k_sweep_render<true, true><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
-            else k_sweep_render<true, false><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
+            if (duty && p.closed) k_sweep_render<true, 2><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
+            else if (duty) k_sweep_render<true, 1><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
+            else k_sweep_render<true, 0><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
         } else {
-            if (duty) k_sweep_render<false, true><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
-            else k_sweep_render<false, false><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
+            if (duty && p.closed) k_sweep_render<false, 2><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
+            else if (duty) k_sweep_render<false, 1><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
+            else k_sweep_render<false, 0><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
         }
         CK_LAUNCH(ctx, "k_sweep_render");
         if (duty) {                                          // scan of group g+2 beside the render of group g+1
@@ -618,9 +746,7 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     if (b->cfg.mode == CPROC_CUDA_XVOICE_SCAN && io->out && !io->mix) {
         // variant groups of >= 128; chunk length: enough (variant, chunk) threads per group to
         // fill the chip, multiple of 32 frames
-        // (PLANAR stages rows through shared memory, which caps its occupancy: the fused render
-        // does not pay there, measured, so its pre-passes simply run first)
-        uint64_t groups = ctx->xvoice_groups > 0 ? (uint64_t)ctx->xvoice_groups : (io->layout == CPROC_CUDA_TILED ? 8 : 1);
+        uint64_t groups = ctx->xvoice_groups > 0 ? (uint64_t)ctx->xvoice_groups : 1;
         if (groups > ceil_div_u64(b->n, 128)) groups = ceil_div_u64(b->n, 128);
         // (one wave of the fused render, 1536 threads per SM, when the groups are pipelined)
         const uint64_t want_threads = groups >= 3 ? (uint64_t)ctx->n_sm * 1536 : (uint64_t)ctx->n_sm * 2048 * 2;

@@ -931,6 +931,65 @@ def test_xvoice_mix_only(st, ctx, oracle, N, F):
     b.free()
 
 
+@pytest.mark.parametrize("closed", [1, 0])
+@pytest.mark.parametrize("layout,groups", [("TILED", 4), ("PLANAR", 1), ("PLANAR", 3)])
+def test_xvoice_scan_zero_state_forms(st, ctx, oracle, closed, layout, groups):
+    """The closed-form zero-state pass (per phase wrap) and the ticked fp64 pass give chunk start states
+    inside the same tolerance, for every kind of increment: none, one wrap per 2^32 ticks, powers of two,
+    increments past 2^31 (a wrap nearly every tick), gaps of exactly k and of k+1 ticks."""
+    special = np.array([0, 1, 2, 3, 1 << 20, 1 << 24, (1 << 24) + 1, (1 << 24) - 1, 3 << 28, 1 << 31, (1 << 31) + 5, (1 << 31) - 1,
+                        0xFFFFFFFF, 0xFFFFFFFE, 0x12345678, 0x9ABCDEF0, 0x55555555, 0x55555556, 0x00F00F00, 715827883], np.uint32)
+    N, F = 512, 1536
+    s0, prm = _xvoice_inputs(oracle, N)
+    prm["inc"][:len(special)] = special
+    prm["inc"][len(special):2 * len(special)] = special
+    prm["gate_frames"] = rng.integers(0, F, N)
+    s0["lp"] = rng.uniform(-0.5, 0.5, N); s0["bp"] = rng.uniform(-0.5, 0.5, N)
+    sa = s0.copy()
+    want_raw, _ = oracle.xvoice_run(sa, prm, N, F)
+    ctx.set_option("xvoice_chunk", 96); ctx.set_option("xvoice_groups", groups); ctx.set_option("xvoice_closed", closed)
+    b = ctx.batch(st.XVOICE, N, layout=getattr(st, layout), mode=st.XVOICE_SCAN)
+    try:
+        b.upload_state(s0.view(np.uint32).reshape(N, 5)); b.upload_param(prm.view(np.uint32).reshape(N, 8))
+        raw = np.zeros(N * F * 2, np.float32)
+        b.run(F, out=raw)
+        got = raw.reshape(F // 2, N, 2, 2).transpose(1, 0, 2, 3).reshape(N, F, 2) if layout == "TILED" else raw.reshape(N, F, 2)
+        w64, g64 = want_raw.astype(np.float64), got.astype(np.float64)
+        err = np.abs(g64 - w64).reshape(N, -1).max(axis=1)
+        assert err.max() <= 1e-5 * np.abs(w64).max(), (int(err.argmax()), int(prm["inc"][err.argmax()]), float(err.max()))
+        assert 10 * np.log10((w64 ** 2).sum() / max(((g64 - w64) ** 2).sum(), 1e-300)) >= 120.0
+        got_state = b.download_state().view(po.xvoice_state_dtype).reshape(N)
+        assert np.array_equal(got_state["phase"], sa["phase"])
+    finally:
+        b.free()
+        ctx.set_option("xvoice_chunk", 0); ctx.set_option("xvoice_groups", 0); ctx.set_option("xvoice_closed", 1)
+
+
+@pytest.mark.parametrize("N,F,chunk,groups,mode", [(70, 1001, 32, 0, 2), (200, 3000, 96, 0, 1), (700, 2048, 32, 3, 1), (40, 2050, 64, 0, 2), (500, 998, 32, 4, 2)])
+def test_xvoice_scan_planar_store_paths(st, ctx, oracle, N, F, chunk, groups, mode):
+    """PLANAR render: tensor-TMA stores (planar_bulk 2, even F) and the staged-row kernel it falls back to
+    (odd F, planar_bulk 1) agree with the sequential oracle to the stated tolerance."""
+    s0, prm = _xvoice_inputs(oracle, N)
+    prm["gate_frames"] = rng.integers(0, F, N)
+    sa = s0.copy()
+    want_raw, _ = oracle.xvoice_run(sa, prm, N, F)
+    ctx.set_option("xvoice_chunk", chunk); ctx.set_option("xvoice_groups", groups); ctx.set_option("planar_bulk", mode)
+    b = ctx.batch(st.XVOICE, N, layout=st.PLANAR, mode=st.XVOICE_SCAN)
+    try:
+        b.upload_state(s0.view(np.uint32).reshape(N, 5)); b.upload_param(prm.view(np.uint32).reshape(N, 8))
+        raw = np.full(N * F * 2 + 64, 7.0, np.float32)
+        b.run(F, out=raw[:N * F * 2])
+        assert np.all(raw[N * F * 2:] == 7.0)
+        w64, g64 = want_raw.astype(np.float64), raw[:N * F * 2].reshape(N, F, 2).astype(np.float64)
+        assert np.abs(g64 - w64).max() <= 1e-5 * np.abs(w64).max()
+        assert 10 * np.log10((w64 ** 2).sum() / max(((g64 - w64) ** 2).sum(), 1e-300)) >= 120.0
+        got_state = b.download_state().view(po.xvoice_state_dtype).reshape(N)
+        assert np.array_equal(got_state["phase"], sa["phase"]) and np.array_equal(got_state["t"], sa["t"])
+    finally:
+        b.free()
+        ctx.set_option("xvoice_chunk", 0); ctx.set_option("xvoice_groups", 0); ctx.set_option("planar_bulk", 2)
+
+
 @pytest.mark.parametrize("layout", ["PLANAR", "TILED"])
 @pytest.mark.parametrize("N,F,chunk,groups", [(64, 4096, 256, 0), (200, 3000, 96, 0), (33, 8192, 0, 0), (5, 1000, 32, 0),
                                               (700, 2048, 64, 0), (700, 2048, 32, 3), (300, 1024, 512, 1), (129, 640, 64, 8), (1100, 1056, 96, 0), (1100, 1056, 96, 5)])
@@ -953,11 +1012,13 @@ def test_xvoice_scan(st, ctx, oracle, layout, N, F, chunk, groups):
         raw = np.zeros(N * F * 2, np.float32)
         l0 = ctx.launches
         b.run(F, out=raw)
-        g_req = min(groups or (8 if layout == "TILED" else 1), -(-N // 128))
+        g_req = min(groups or 1, -(-N // 128))
         per = -(-(-(-N // g_req)) // 128) * 128              # variants per group, multiple of 128
         g_eff = -(-N // per)
         piped = g_eff >= 3                                   # look-ahead-2 pipeline: zero-state passes fused into the renders
-        assert ctx.launches - l0 == 1 + (2 if piped else g_eff) + 2 * g_eff    # env; zsr; scan + render per group
+        # env; zsr (TILED pipeline: first two groups only, the rest is fused into the renders); scan + render per group
+        # (+ the table kernel of the closed-form zero-state pass)
+        assert ctx.launches - l0 == 2 + (2 if piped else g_eff) + 2 * g_eff
         got = raw.reshape(F // 2, N, 2, 2).transpose(1, 0, 2, 3).reshape(N, F, 2) if layout == "TILED" else raw.reshape(N, F, 2)
         w64, g64 = want_raw.astype(np.float64), got.astype(np.float64)
         peak = np.abs(w64).max()
