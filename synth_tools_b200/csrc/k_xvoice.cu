@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_sweep_scan(const SweepParam
 // variant of the group two renders ahead).  The render is HBM-write bound and leaves
 // ~40% of the issue slots and the whole DP pipe idle; the zero-state pass is pure
 // arithmetic, so inside the same instruction stream it is hidden behind the stores.
-template <bool TILED, int ZSR>   // ZSR: 0 none, 1 ticked beside the render, 2 closed form before it
+template <bool TILED, int ZSR>   // ZSR 1: ticked zero-state pass of a later group beside the render (xvoice_closed = 0)
 __global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) {
     constexpr int PT = 32;                               // PLANAR: frames staged per pass (256-byte runs per stream; 128-byte runs cost 20% of the bandwidth)
     __shared__ __align__(16) float2 tile[TILED ? 1 : XV_WARPS][TILED ? 1 : 32][TILED ? 1 : PT + 1];   // [warp][stream][frame]
@@ -574,13 +574,9 @@ __global__ void __launch_bounds__(XV_BLOCK) k_sweep_render(const SweepParams p) 
     }
     // zero-state duty: chunk c of variant j (chunks 0..C-2 are full, the last one needs no response)
     const uint64_t j = i + p.zoff;
-    bool zmine = ZSR != 0 && mine && j < p.zi1 && c + 1 < p.C;
+    const bool zmine = ZSR != 0 && mine && j < p.zi1 && c + 1 < p.C;
     uint32_t zph = 0, zinc = 0;
     double zf = 0.0, znq = 0.0, zlp = 0.0, zbp = 0.0;
-    if (ZSR == 2) {                                       // closed form: a few operations per wrap, done before the render loop
-        if (zmine) p.z[j * (p.C - 1) + c] = zsr_closed(p, j, c);
-        zmine = false;
-    }
     if (zmine) {
         zinc = __ldg(p.x.prm + j);
         zf = (double)__uint_as_float(__ldg(p.x.prm + npad + j));
@@ -669,7 +665,10 @@ static int launch_xvoice_scan(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_
     if (groups < 1) groups = 1;
     const uint64_t per = ceil_div_u64(ceil_div_u64(n, groups), 128) * 128;
     groups = ceil_div_u64(n, per);
-    const bool piped = groups >= 3 && C > 1;
+    const bool piped = groups >= (ctx->xvoice_closed ? 2 : 3) && C > 1;
+    // closed-form zero-state pass: cheap enough to stay a kernel of its own; for every group it runs on
+    // the auxiliary stream (with its scan) beside the renders of the groups before it
+    const bool ahead = piped && ctx->xvoice_closed;
     if (piped && !ctx->aux_stream) {
         int lo = 0, hi = 0;
         CK(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -694,14 +693,14 @@ static int launch_xvoice_scan(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_
     for (uint64_t g = 0; g < groups; ++g) {
         range(g, &p.i0, &p.i1);
         const unsigned gx = (unsigned)ceil_div_u64(p.i1 - p.i0, 128);
-        if (C > 1 && (!piped || g < 2)) {
+        if (C > 1 && (!piped || ahead || g < 2)) {
             if (p.closed) {
                 const uint32_t bpv = (uint32_t)ceil_div_u64(C - 1, 128);
                 k_sweep_zsr_closed<<<(unsigned)((p.i1 - p.i0) * bpv), 128, 0, pre>>>(p, bpv);
             } else k_sweep_zsr<<<dim3(gx, (unsigned)(C - 1)), 128, 0, pre>>>(p);
             CK_LAUNCH(ctx, "k_sweep_zsr");
         }
-        if (!piped || g < 2) {
+        if (!piped || ahead || g < 2) {
             k_sweep_scan<<<(unsigned)ceil_div_u64(p.i1 - p.i0, SCAN_WARPS), SCAN_WARPS * 32, 0, pre>>>(p);
             CK_LAUNCH(ctx, "k_sweep_scan");
             if (piped) CK(ctx, cudaEventRecord(ev_scan[g], pre));
@@ -710,17 +709,15 @@ static int launch_xvoice_scan(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_
     for (uint64_t g = 0; g < groups; ++g) {
         range(g, &p.i0, &p.i1);
         const unsigned gx = (unsigned)ceil_div_u64(p.i1 - p.i0, 128);
-        const bool duty = piped && g + 2 < groups;
+        const bool duty = piped && !ahead && g + 2 < groups;
         if (duty) { uint64_t z0; range(g + 2, &z0, &p.zi1); p.zoff = z0 - p.i0; } else { p.zoff = 0; p.zi1 = 0; }
         if (piped) CK(ctx, cudaStreamWaitEvent(ctx->stream, ev_scan[g], 0));     // join: start states of this group
         const dim3 grid(gx, (unsigned)C);
         if (io->layout == CPROC_CUDA_TILED) {
-            if (duty && p.closed) k_sweep_render<true, 2><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
-            else if (duty) k_sweep_render<true, 1><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
+            if (duty) k_sweep_render<true, 1><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
             else k_sweep_render<true, 0><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
         } else {
-            if (duty && p.closed) k_sweep_render<false, 2><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
-            else if (duty) k_sweep_render<false, 1><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
+            if (duty) k_sweep_render<false, 1><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
             else k_sweep_render<false, 0><<<grid, XV_BLOCK, 0, ctx->stream>>>(p);
         }
         CK_LAUNCH(ctx, "k_sweep_render");
@@ -749,7 +746,7 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
         uint64_t groups = ctx->xvoice_groups > 0 ? (uint64_t)ctx->xvoice_groups : 1;
         if (groups > ceil_div_u64(b->n, 128)) groups = ceil_div_u64(b->n, 128);
         // (one wave of the fused render, 1536 threads per SM, when the groups are pipelined)
-        const uint64_t want_threads = groups >= 3 ? (uint64_t)ctx->n_sm * 1536 : (uint64_t)ctx->n_sm * 2048 * 2;
+        const uint64_t want_threads = groups >= 3 && !ctx->xvoice_closed ? (uint64_t)ctx->n_sm * 1536 : (uint64_t)ctx->n_sm * 2048 * 2;
         uint64_t C = ceil_div_u64(want_threads, ceil_div_u64(b->n, groups));
         if (C > 65535) C = 65535;
         uint64_t L = ceil_div_u64(ceil_div_u64(F, C), 32) * 32;

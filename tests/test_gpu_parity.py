@@ -1015,7 +1015,7 @@ def test_xvoice_scan(st, ctx, oracle, layout, N, F, chunk, groups):
         g_req = min(groups or 1, -(-N // 128))
         per = -(-(-(-N // g_req)) // 128) * 128              # variants per group, multiple of 128
         g_eff = -(-N // per)
-        piped = g_eff >= 3                                   # look-ahead-2 pipeline: zero-state passes fused into the renders
+        piped = False                                        # closed-form zero-state pass: always a kernel of its own
         # env; zsr (TILED pipeline: first two groups only, the rest is fused into the renders); scan + render per group
         # (+ the table kernel of the closed-form zero-state pass)
         assert ctx.launches - l0 == 2 + (2 if piped else g_eff) + 2 * g_eff
