@@ -22,6 +22,7 @@
  *     stm32f103/mod_pdm_pwm.c:123-143,
  *     stm32f103/mod_controlrate.c:28-57
  *   pwm_update  stm32f103/mod_pdm.c:167-175     CPROC_CUDA_PWM batch
+ *   word clock  linux/clock.c:109-120           CPROC_CUDA_WORD_CLOCK batch
  *   synth_run / sum_tick_saw / sum_tick_square  CPROC_CUDA_VOICE_BANK batch
  *     linux/synth.c:169-202
  *   square_grain_proc linux/synth_tools.c:85-100 CPROC_CUDA_SQUARE_GRAIN batch
@@ -127,7 +128,13 @@ enum cproc_cuda_proc {
      * instances, long streams -- time-parallel render from a block scan of the affine
      * recurrence (fp64 chunk start states; <= 1e-5 of peak / >= 120 dB SNR against the
      * sequential render; in must not alias out). */
-    CPROC_CUDA_ONEPOLE = 10
+    CPROC_CUDA_ONEPOLE = 10,
+    /* word clock of linux/clock.c:109-120 (integer divisor of the sample clock): per sample
+     * `if (phase >= hperiod) { phase -= hperiod; pol ^= 1; } out = pol; phase += 1`.
+     * state {int32 phase; int32 pol}; param {int32 hperiod} (clock.c:58: sr*5 / (bpm*4));
+     * out float PLANAR [inst][F] / INTERLEAVED [F][inst].  The MIDI clock byte of clock.c:113-116
+     * goes out where pol turns 1: the host adapter reads those samples off its block. */
+    CPROC_CUDA_WORD_CLOCK = 11
 };
 
 /* Node kinds (bits 0..7 of cproc_cuda_node.type; bits 8..15 carry the node's config word).

@@ -405,3 +405,18 @@ void orc_onepole_run(float *y, const float *a, uint64_t N, uint64_t F,
         y[n] = s;
     }
 }
+
+/* linux/clock.c:109-120 (clock_phase, clock_pol, clock_hperiod :42,61-62) */
+void orc_word_clock_run(int32_t *state, const int32_t *hperiod, uint64_t N, uint64_t F, float *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t n = 0; n < (int64_t)N; n++) {
+        int32_t phase = state[2 * n], pol = state[2 * n + 1];
+        const int32_t h = hperiod[n];
+        for (uint64_t t = 0; t < F; t++) {
+            if (phase >= h) { phase = (int32_t)((uint32_t)phase - (uint32_t)h); pol ^= 1; }
+            out[(uint64_t)n * F + t] = (float)pol;
+            phase = (int32_t)((uint32_t)phase + 1u);
+        }
+        state[2 * n] = phase; state[2 * n + 1] = pol;
+    }
+}

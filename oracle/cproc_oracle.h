@@ -177,6 +177,9 @@ float orc_xvoice_tick(orc_xvoice_state *s, const orc_xvoice_param *p);
  * reference mix then rounded to float, or NULL. */
 void orc_xvoice_run(orc_xvoice_state *s, const orc_xvoice_param *p, uint64_t N,
                     uint64_t F, float *raw, float *mix);
+/* linux/clock.c:109-120: integer-divisor word clock.  state[n] = {phase, pol}; out [N][F] = pol as
+ * float.  Restated (the loop sits inside a JACK process callback); int arithmetic wraps. */
+void orc_word_clock_run(int32_t *state, const int32_t *hperiod, uint64_t N, uint64_t F, float *out);
 /* one-pole lowpass y += a*(x-y) as a stand-alone processor */
 void orc_onepole_run(float *y, const float *a, uint64_t N, uint64_t F,
                      const float *in, float *out);

@@ -194,6 +194,13 @@ class Oracle(_Lib):
         f(_ptr(state), _ptr(param), N, F, _ptr(raw), _ptr(mix))
         return raw, mix
 
+    def word_clock_run(self, state, hperiod, N, F):
+        """state int32 [N][2] = {phase, pol} (advanced in place); returns float [N][F]"""
+        out = np.zeros((N, F), np.float32)
+        f = self._fn("word_clock_run", None, [VP, VP, C.c_uint64, C.c_uint64, VP])
+        f(_ptr(state), _ptr(hperiod), N, F, _ptr(out))
+        return out
+
     def onepole_run(self, y, a, N, F, inp):
         out = np.zeros((N, F), np.float32)
         f = self._fn("onepole_run", None, [VP, VP, C.c_uint64, C.c_uint64, VP, VP])

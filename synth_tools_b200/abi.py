@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcproc_cuda.so")
 
 # enum cproc_cuda_proc
-GRAPH, PDM, PDM_V1, PDM_V2, PWM, VOICE_BANK, SQUARE_GRAIN, SQUARE_GRAIN_MIX, XVOICE, ONEPOLE = range(1, 11)
+GRAPH, PDM, PDM_V1, PDM_V2, PWM, VOICE_BANK, SQUARE_GRAIN, SQUARE_GRAIN_MIX, XVOICE, ONEPOLE, WORD_CLOCK = range(1, 12)
 NODE_ACC, NODE_EDGE, NODE_GLIDE, NODE_PDM = 0, 1, 2, 3
 
 

@@ -148,6 +148,7 @@ static int proc_words(const cproc_cuda_config &c, const std::vector<cproc_cuda_n
     case CPROC_CUDA_SQUARE_GRAIN_MIX: *sw = 2; *pw = 4; return 0;
     case CPROC_CUDA_XVOICE: *sw = 5; *pw = 8; return 0;
     case CPROC_CUDA_ONEPOLE: *sw = 1; *pw = 1; return 0;
+    case CPROC_CUDA_WORD_CLOCK: *sw = 2; *pw = 1; return 0;
     }
     return -1;
 }
@@ -342,6 +343,7 @@ int cproc_io_bytes(const cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *i
         s->out = io->out ? 4 * b->n_bus * F : 0; s->mix = io->mix ? 4 * b->n_bus * F : 0; break;
     case CPROC_CUDA_SQUARE_GRAIN: case CPROC_CUDA_ONEPOLE:
         s->in = 4 * n * F; s->out = 4 * n * F; break;
+    case CPROC_CUDA_WORD_CLOCK: s->out = 4 * n * F; break;
     case CPROC_CUDA_SQUARE_GRAIN_MIX:
         s->out = io->out ? 8 * F : 0; s->mix = io->mix ? 8 * F : 0; break;
     case CPROC_CUDA_XVOICE:
@@ -365,6 +367,7 @@ static int dispatch(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     case CPROC_CUDA_SQUARE_GRAIN_MIX: return launch_square_grain_mix(b, F, io);
     case CPROC_CUDA_XVOICE: return launch_xvoice(b, F, io);
     case CPROC_CUDA_ONEPOLE: return launch_onepole(b, F, io);
+    case CPROC_CUDA_WORD_CLOCK: return launch_word_clock(b, F, io);
     }
     return cproc_set_err(b->ctx, CPROC_CUDA_EINVAL, "run: unknown processor");
 }

@@ -139,6 +139,7 @@ int launch_square_grain(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io
 int launch_square_grain_mix(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
 int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
 int launch_onepole(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
+int launch_word_clock(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io);
 
 // small conversion kernels shared across translation units
 __global__ void k_imix_to_float(const int32_t *imix, float *mix, uint64_t count, float scale);

@@ -1,5 +1,5 @@
 /* A scripted stand-in for the part of the JACK API that synth_tools_b200/host/jack/jack_synth.c
- * uses (this image has no libjack).  Test infrastructure: see fakejack.c. */
+ * and jack_clock.c use (this image has no libjack).  Test infrastructure: see fakejack.c. */
 #ifndef FAKE_JACK_H
 #define FAKE_JACK_H
 #include <stdint.h>
@@ -18,6 +18,7 @@ typedef int (*JackProcessCallback)(jack_nframes_t nframes, void *arg);
 jack_client_t *jack_client_open(const char *name, jack_options_t options, jack_status_t *status, ...);
 int jack_client_close(jack_client_t *c);
 jack_nframes_t jack_get_buffer_size(jack_client_t *c);
+jack_nframes_t jack_get_sample_rate(jack_client_t *c);
 jack_port_t *jack_port_register(jack_client_t *c, const char *name, const char *type, unsigned long flags, unsigned long bufsize);
 void *jack_port_get_buffer(jack_port_t *p, jack_nframes_t nframes);
 int jack_set_process_callback(jack_client_t *c, JackProcessCallback cb, void *arg);

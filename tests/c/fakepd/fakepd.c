@@ -18,7 +18,7 @@ static t_class the_class;
 static struct { t_perfroutine f; t_int w[8]; } chain[64];
 static int chain_len;
 
-t_symbol *gensym(const char *s) { t_symbol *y = malloc(sizeof(*y)); y->name = strdup(s); return y; }
+t_symbol *gensym(const char *s) { t_symbol *y = malloc(sizeof(*y)); y->s_name = strdup(s); return y; }
 t_class *class_new(t_symbol *name, t_newmethod newmethod, t_method freemethod, size_t size, int flags, t_atomtype arg1, ...) {
     (void)name; (void)freemethod; (void)flags; (void)arg1;
     the_class.newm = newmethod; the_class.size = size;
@@ -26,8 +26,8 @@ t_class *class_new(t_symbol *name, t_newmethod newmethod, t_method freemethod, s
 }
 void class_addmethod(t_class *c, t_method fn, t_symbol *sel, t_atomtype arg1, ...) {
     (void)arg1;
-    if (!strcmp(sel->name, "dsp")) c->dsp = fn;
-    if (!strcmp(sel->name, "threshold")) c->threshold = fn;
+    if (!strcmp(sel->s_name, "dsp")) c->dsp = fn;
+    if (!strcmp(sel->s_name, "threshold")) c->threshold = fn;
 }
 void class_domainsignalin(t_class *c, int onset) { (void)c; (void)onset; }
 t_pd *pd_new(t_class *cls) { t_object *o = calloc(1, cls->size); o->ob_pd = cls; return (t_pd *)o; }

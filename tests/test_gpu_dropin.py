@@ -176,3 +176,46 @@ def test_pd_external_with_scripted_backend(tmp_path, oracle):
         want = oracle.square_grain_run(state, th.copy(), G, B, np.ascontiguousarray(inp[tick]))
         for g in range(G):
             assert np.array_equal(got[(tick + 1, g)].view(np.uint32), want[g].view(np.uint32)), (tick, g)
+
+
+def test_jack_clock_adapter_with_scripted_backend(tmp_path, oracle):
+    """synth_tools_b200/host/jack/jack_clock.c (the reference's linux/clock.c word-clock / MIDI-clock
+    master, one clock per BPM) against tests/c/fakejack.  Audio must equal the restated clock.c:109-120 loop bit for
+    bit over 24 periods; MIDI out must carry start / stop / continue first at time 0 (clock.c:83-95, other
+    realtime bytes filtered) and 0xF8 at exactly the samples where clock 0 turns positive (clock.c:113-116)."""
+    pkg = os.path.join(ROOT, "synth_tools_b200")
+    exe = str(tmp_path / "jack_clock_fake")
+    subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "c", "fakejack"),
+                           "-I", os.path.join(ROOT, "include"), os.path.join(pkg, "host", "jack", "jack_clock.c"),
+                           os.path.join(ROOT, "tests", "c", "fakejack", "fakejack.c"), "-o", exe, "-L", pkg, "-lcproc_cuda", "-Wl,-rpath," + pkg])
+    bpms = [960, 120, 7500]
+    env = dict(os.environ, FAKEJACK_SCRIPT="clock", FAKEJACK_PERIODS="24")
+    res = subprocess.run([exe] + [str(b) for b in bpms], stdin=subprocess.DEVNULL, capture_output=True, text=True, env=env)
+    assert res.returncode == 0, res.stderr
+    audio, midi = {}, {}
+    for l in res.stdout.splitlines():
+        f = l.split()
+        if f and f[0] == "audio":
+            audio[(int(f[1]), f[2])] = np.array([float.fromhex(x) for x in f[3:]], np.float32)
+        elif f and f[0] == "midi":
+            midi.setdefault(int(f[1]), []).append((int(f[3]), [int(x, 16) for x in f[4:]]))
+    F, P = 64, 24
+    hp = np.array([(48000 * 5) // (b * 4) for b in bpms], np.int32)            # BPM_TO_HPERIOD, clock.c:58
+    assert list(hp) == [62, 500, 8]
+    state = np.zeros((3, 2), np.int32); state[:, 1] = 1                       # clock_phase = 0, clock_pol = 1 (clock.c:61-62)
+    passed = {1: 0xFA, 3: 0xFC, 5: 0xFB}
+    last = 1
+    n_clock_bytes = 0
+    for period in range(P):
+        want = oracle.word_clock_run(state, hp, 3, F)
+        for k in range(3):
+            assert np.array_equal(audio[(period, "clock_%02d" % k)].view(np.uint32), want[k].view(np.uint32)), (period, k)
+        expect = [(0, [passed[period]])] if period in passed else []
+        for t in range(F):
+            pol = int(want[0, t])
+            if pol == 1 and last != 1:
+                expect.append((t, [0xF8]))
+            last = pol
+        n_clock_bytes += sum(1 for e in expect if e[1] == [0xF8])
+        assert midi.get(period, []) == expect, (period, midi.get(period), expect)
+    assert n_clock_bytes == (P * F) // 124                                   # one positive edge per 2 * 62 samples

@@ -1153,3 +1153,27 @@ def test_run_dev_and_stream(st, ctx, oracle):
     assert np.array_equal(b.download_state(), ca)
     ctx.host_free(ring_ptr)
     b.free()
+
+
+@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
+@pytest.mark.parametrize("N,F", [(300, 1000), (3, 64), (40, 1023), (1, 4096)])
+def test_word_clock(st, ctx, oracle, layout, N, F):
+    """linux/clock.c:109-120 as a batch: integer-divisor square waves, bit-exact against the restated loop
+    over two consecutive blocks (state carried), including half periods of 0, 1, negative and huge values."""
+    hp = rng.integers(1, 200, N).astype(np.int32)
+    special = np.array([0, 1, -5, 2**31 - 1, 2, 500, 62, 8], np.int32)
+    hp[:min(N, len(special))] = special[:min(N, len(special))]
+    s0 = np.zeros((N, 2), np.int32); s0[:, 0] = rng.integers(0, 300, N); s0[:, 1] = rng.integers(0, 2, N)
+    if N > 8:
+        s0[8] = (2**31 - 3, 7)                                 # the phase counter wraps; pol is any integer
+    sa = s0.copy()
+    b = ctx.batch(st.WORD_CLOCK, N, layout=getattr(st, layout))
+    b.upload_state(s0.view(np.uint32)); b.upload_param(hp.view(np.uint32).reshape(N, 1))
+    for blk in range(2):
+        want = oracle.word_clock_run(sa, hp, N, F)
+        out = np.zeros((N, F) if layout == "PLANAR" else (F, N), np.float32)
+        b.run(F, out=out)
+        got = out if layout == "PLANAR" else out.T
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), blk
+        assert np.array_equal(b.download_state().view(np.int32), sa)
+    b.free()

@@ -1,0 +1,62 @@
+"""CPU tests of host-side pieces that need no GPU: the restated word clock against its closed form and the
+Pd [scale] object (synth_tools.c:147-194) through the scripted Pd stand-in."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import pyoracle as po
+    return po.Oracle()
+
+
+def test_word_clock_oracle_is_an_integer_divisor_square_wave(oracle):
+    """clock.c:109-120 from phase 0, pol 1: out[t] = 1 ^ ((t // hperiod) & 1) for hperiod >= 1; the state carries
+    over block boundaries; BPM_TO_HPERIOD(48000, 120) = 500 samples = 24 ppqn at 2 beats per second."""
+    hp = np.array([1, 2, 3, 8, 62, 500, 1000], np.int32)
+    N, F = len(hp), 4096
+    state = np.zeros((N, 2), np.int32); state[:, 1] = 1
+    a = oracle.word_clock_run(state, hp, N, F // 2)
+    b = oracle.word_clock_run(state, hp, N, F // 2)
+    got = np.concatenate([a, b], axis=1)
+    t = np.arange(F)
+    for k in range(N):
+        assert np.array_equal(got[k], (1 ^ ((t // hp[k]) & 1)).astype(np.float32)), k
+    assert (48000 * 5) // (120 * 4) == 500
+    # hperiod 0: toggles every sample while the counter runs away, exactly as the C loop does
+    state = np.array([[0, 1]], np.int32)
+    z = oracle.word_clock_run(state, np.array([0], np.int32), 1, 8)
+    assert list(z[0]) == [0, 1, 0, 1, 0, 1, 0, 1] and state[0, 0] == 8
+
+
+def test_pd_scale_object(tmp_path):
+    """[scale exp 20 20000] and [scale lin -1 3]: every MIDI value 0..127 gives base * powf(max/min, v/127) resp.
+    base + (max-min) * v/127 in float arithmetic (bit-exact against libm's powf); unknown types are refused."""
+    exe = str(tmp_path / "pd_scale_fake")
+    subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "c", "fakepd"),
+                           os.path.join(ROOT, "synth_tools_b200", "host", "pd", "scale.c"),
+                           os.path.join(ROOT, "tests", "c", "fakepd", "fakepd_scale.c"), "-o", exe, "-lm"])
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    lines = [l.split() for l in res.stdout.splitlines()]
+    assert lines[0] == ["refused", "1"]
+    libm = ctypes.CDLL("libm.so.6")
+    libm.powf.restype = ctypes.c_float; libm.powf.argtypes = [ctypes.c_float, ctypes.c_float]
+    f32 = np.float32
+    got = {(int(l[1]), int(l[2])): (f32(float.fromhex(l[3])), int(l[4])) for l in lines[1:]}
+    assert len(got) == 256
+    for v in range(128):
+        frac = f32(v) * f32(1.0 / 127.0)
+        want_exp = f32(20.0) * f32(libm.powf(f32(20000.0) / f32(20.0), frac))
+        want_lin = f32(-1.0) + (f32(3.0) - f32(-1.0)) * frac
+        assert got[(0, v)] == (want_exp, 0), v
+        assert got[(1, v)] == (want_lin, 1), v
+    assert got[(0, 0)][0] == 20.0 and got[(0, 127)][0] == 20000.0 and got[(1, 127)][0] == 3.0
