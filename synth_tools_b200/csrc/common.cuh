@@ -58,8 +58,8 @@ struct cproc_graph_jit {
     int state = 0;
     std::vector<char> cubin;
     cudaLibrary_t lib = nullptr;
-    cudaKernel_t k_il = nullptr, k_il4 = nullptr, k_pl = nullptr, k_ps = nullptr;
-    uint32_t pl_smem = 0, pl_block = 0;
+    cudaKernel_t k_il = nullptr, k_il4 = nullptr, k_pl = nullptr, k_ps = nullptr, k_pt = nullptr;
+    uint32_t pl_smem = 0, pl_block = 0, pt_smem = 0;
 };
 
 struct cproc_cuda_batch {

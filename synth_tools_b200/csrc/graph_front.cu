@@ -480,6 +480,91 @@ extern "C" __global__ void __launch_bounds__(WARPS * 32) graph_planar(const Grap
     if (mine) { GRAPH_STORE_STATE(p.st, p.npad, i) }
 }
 
+// The same staging with TENSOR TMA (planar_bulk.cuh, k_planar_tma): the streams are 3-D tensors
+// [inst][stream][F], a box is 32 frames x 1 stream x 32 instances (SWIZZLE_128B), ONE elected lane moves
+// the two boxes of every stream of a 64-frame tile (the per-lane bulk copies above are executed one lane
+// at a time by the uniform datapath), lane r finds 16-byte chunk c of its row at r*128 + ((c ^ (r&7)) << 4).
+struct __align__(64) CUtensorMap { unsigned long long opaque[16]; };
+#define TT_BOXB 4096
+#define TT_STREAMB (2 * TT_BOXB)
+#define TT_STAGEB (ROWS * TT_STREAMB)
+extern "C" __global__ void __launch_bounds__(WARPS * 32) graph_planar_tma(const GraphParams p, const __grid_constant__ CUtensorMap tm_in,
+                                                                           const __grid_constant__ CUtensorMap tm_chg, const __grid_constant__ CUtensorMap tm_out) {
+    extern __shared__ __align__(1024) unsigned char sm[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t g0 = ((uint64_t)blockIdx.x * WARPS + warp) * 32;
+    if (g0 >= p.n) return;
+    const uint32_t rows = p.n - g0 < 32 ? (uint32_t)(p.n - g0) : 32u;
+    const bool mine = lane < rows;
+    const uint64_t i = g0 + lane;
+    const uint32_t sm0 = (smem_u32(sm) + 1023u) & ~1023u;
+    const uint32_t base = sm0 + warp * (STAGES * TT_STAGEB);
+    const uint32_t bar0 = sm0 + WARPS * STAGES * TT_STAGEB + warp * (STAGES * 8);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * s), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    GRAPH_DECL_STATE
+    if (mine) { GRAPH_LOAD_STATE(p.st, p.npad, i) }
+    const uint32_t n_tiles = (uint32_t)((p.F + TF - 1) / TF);
+    const unsigned long long tmi = (unsigned long long)&tm_in, tmc = (unsigned long long)&tm_chg, tmo = (unsigned long long)&tm_out;
+    auto cols_of = [&](uint32_t k) { const uint64_t left = p.F - (uint64_t)k * TF; return left < TF ? (uint32_t)left : (uint32_t)TF; };
+    auto issue = [&](uint32_t k) {                                    // lane 0 only
+        const uint32_t s = k % STAGES, nbox = cols_of(k) > 32 ? 2u : 1u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * s), "r"(ROWS_IN * nbox * TT_BOXB) : "memory");
+#pragma unroll
+        for (int j = 0; j < ROWS_IN; ++j)
+            for (uint32_t h = 0; h < nbox; ++h)
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             ::"r"(base + s * TT_STAGEB + j * TT_STREAMB + h * TT_BOXB), "l"(j < GRAPH_NIN ? tmi : tmc), "r"((int)(k * TF + h * 32)),
+                               "r"(j < GRAPH_NIN ? j : 0), "r"((int)g0), "r"(bar0 + 8 * s) : "memory");
+    };
+    if (lane == 0) for (uint32_t k = 0; k < STAGES - 2 && k < n_tiles; ++k) issue(k);
+#pragma unroll 1
+    for (uint32_t k = 0; k < n_tiles; ++k) {
+        if (k + STAGES - 2 < n_tiles && lane == 0) {                  // that stage last held tile k-2: its stores must have read it out
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            issue(k + STAGES - 2);
+        }
+        const uint32_t s = k % STAGES, cols = cols_of(k);
+        asm volatile("{\n\t.reg .pred q;\n\tW: mbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n\t@q bra D;\n\tbra W;\n\tD:\n\t}"
+                     ::"r"(bar0 + 8 * s), "r"((k / STAGES) & 1) : "memory");
+        const uint32_t row = base + s * TT_STAGEB + lane * 128;       // stream j, chunk c: row + j * TT_STREAMB + (c >> 3) * TT_BOXB + (((c & 7) ^ (lane & 7)) << 4)
+        if (mine) {
+            for (uint32_t c = 0; c < cols / 4; ++c) {
+                const uint32_t at = row + (c >> 3) * TT_BOXB + (((c & 7) ^ (lane & 7)) << 4);
+                uint32_t xa[GRAPH_NIN], xb[GRAPH_NIN], xc[GRAPH_NIN], xd[GRAPH_NIN], ga = 0xFFFFFFFFu, gb = 0xFFFFFFFFu, gc = 0xFFFFFFFFu, gd = 0xFFFFFFFFu;
+                uint32_t oa[GRAPH_NOUT], ob[GRAPH_NOUT], oc[GRAPH_NOUT], od[GRAPH_NOUT];
+#pragma unroll
+                for (int j = 0; j < GRAPH_NIN; ++j)
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(xa[j]), "=r"(xb[j]), "=r"(xc[j]), "=r"(xd[j]) : "r"(at + j * TT_STREAMB));
+                if (GRAPH_HAS_CHANGED)
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ga), "=r"(gb), "=r"(gc), "=r"(gd) : "r"(at + GRAPH_NIN * TT_STREAMB));
+                TICK(xa, ga, oa); TICK(xb, gb, ob); TICK(xc, gc, oc); TICK(xd, gd, od);
+#pragma unroll
+                for (int q = 0; q < GRAPH_NOUT; ++q)
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(at + q * TT_STREAMB), "r"(oa[q]), "r"(ob[q]), "r"(oc[q]), "r"(od[q]) : "memory");
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t nbox = cols > 32 ? 2u : 1u;
+#pragma unroll
+            for (int q = 0; q < GRAPH_NOUT; ++q)
+                for (uint32_t h = 0; h < nbox; ++h)
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                                 ::"l"(tmo), "r"((int)(k * TF + h * 32)), "r"(q), "r"((int)g0), "r"(base + s * TT_STAGEB + q * TT_STREAMB + h * TT_BOXB) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    if (mine) { GRAPH_STORE_STATE(p.st, p.npad, i) }
+}
+
 // planar streams of any length / alignment: one thread per instance, scalar accesses
 extern "C" __global__ void __launch_bounds__(128) graph_planar_simple(const GraphParams p) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -498,7 +583,7 @@ extern "C" __global__ void __launch_bounds__(128) graph_planar_simple(const Grap
     GRAPH_STORE_STATE(p.st, p.npad, i)
 }
 
-extern "C" __global__ void graph_planar_smem(uint32_t *out) { out[0] = WARPS * STAGES * STAGEB + WARPS * STAGES * 8; out[1] = WARPS * 32; }
+extern "C" __global__ void graph_planar_smem(uint32_t *out) { out[0] = WARPS * STAGES * STAGEB + WARPS * STAGES * 8; out[1] = WARPS * 32; out[2] = WARPS * STAGES * TT_STAGEB + WARPS * STAGES * 8 + 1024; }
 )SRC";
 
 }  // namespace
@@ -601,21 +686,23 @@ int cproc_graph_jit_get(cproc_cuda_batch *b, bool has_changed, cproc_graph_jit *
         if (cudaLibraryLoadData(&j.lib, j.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) { cudaGetLastError(); b->jit_log = "cudaLibraryLoadData failed"; return -1; }
         cudaKernel_t kq = nullptr;
         if (cudaLibraryGetKernel(&j.k_il, j.lib, "graph_interleaved") != cudaSuccess || cudaLibraryGetKernel(&j.k_pl, j.lib, "graph_planar") != cudaSuccess ||
-            cudaLibraryGetKernel(&j.k_ps, j.lib, "graph_planar_simple") != cudaSuccess ||
+            cudaLibraryGetKernel(&j.k_ps, j.lib, "graph_planar_simple") != cudaSuccess || cudaLibraryGetKernel(&j.k_pt, j.lib, "graph_planar_tma") != cudaSuccess ||
             cudaLibraryGetKernel(&j.k_il4, j.lib, "graph_interleaved4") != cudaSuccess ||
             cudaLibraryGetKernel(&kq, j.lib, "graph_planar_smem") != cudaSuccess) { cudaGetLastError(); b->jit_log = "cudaLibraryGetKernel failed"; return -1; }
         // shared-memory size and block size of the planar kernel are defined by the generated source: ask it
-        uint32_t *d = nullptr, h[2] = {0, 0};
-        if (cudaMalloc(&d, 8) != cudaSuccess) { cudaGetLastError(); return -1; }
+        uint32_t *d = nullptr, h[3] = {0, 0, 0};
+        if (cudaMalloc(&d, 12) != cudaSuccess) { cudaGetLastError(); return -1; }
         void *args[] = {&d};
         cudaError_t e = cudaLaunchKernel((const void *)kq, dim3(1), dim3(1), args, 0, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, 12, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         cudaFree(d);
         if (e != cudaSuccess) { cudaGetLastError(); b->jit_log = "graph_planar_smem query failed"; return -1; }
         j.pl_smem = h[0]; j.pl_block = h[1];
         if (j.pl_smem > 227 * 1024) { b->jit_log = "planar staging does not fit shared memory (too many input streams)"; j.k_pl = nullptr; }
         else if (cudaFuncSetAttribute((const void *)j.k_pl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)j.pl_smem) != cudaSuccess) { cudaGetLastError(); j.k_pl = nullptr; }
+        j.pt_smem = h[2];
+        if (j.pt_smem > 227 * 1024 || cudaFuncSetAttribute((const void *)j.k_pt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)j.pt_smem) != cudaSuccess) { cudaGetLastError(); j.k_pt = nullptr; }
         j.state = 1;
     }
     *out = &j;

@@ -7,6 +7,7 @@
 // node-state vector in registers across the frame block, the node table in
 // shared memory, F ticks per launch.
 #include "common.cuh"
+#include "planar_bulk.cuh"
 
 #define GRAPH_MAX_NODES 16
 #define GRAPH_MAX_STATE 48
@@ -136,11 +137,16 @@ int launch_graph(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     if (ctx->graph_jit && cproc_graph_jit_get(b, p.changed != nullptr, &j) == 0) {
         void *args[] = {&p};
         cudaError_t e;
+        CUtensorMap tin, tchg, tout;
         const bool aligned = F % 4 == 0 && ((uintptr_t)p.in & 15) == 0 && ((uintptr_t)p.out & 15) == 0 && (!p.changed || ((uintptr_t)p.changed & 15) == 0);
         const bool vec4 = ctx->graph_vec4 && p.n % 4 == 0 && ((uintptr_t)p.in & 15) == 0 && ((uintptr_t)p.out & 15) == 0 && (!p.changed || ((uintptr_t)p.changed & 15) == 0);
         if (io->layout == CPROC_CUDA_INTERLEAVED && vec4) e = cudaLaunchKernel((const void *)j->k_il4, dim3((unsigned)ceil_div_u64(p.n, 512)), dim3(128), args, 0, ctx->stream);
         else if (io->layout == CPROC_CUDA_INTERLEAVED) e = cudaLaunchKernel((const void *)j->k_il, dim3(grid), dim3(128), args, 0, ctx->stream);
-        else if (j->k_pl && aligned) e = cudaLaunchKernel((const void *)j->k_pl, dim3((unsigned)ceil_div_u64(p.n, j->pl_block)), dim3(j->pl_block), args, j->pl_smem, ctx->stream);
+        else if (j->k_pt && aligned && ctx->planar_bulk >= 2 && pbulk::encode_rows3_u32(&tin, p.in, F, p.n_inputs, p.n) &&
+                 pbulk::encode_rows3_u32(&tchg, p.changed ? p.changed : p.in, F, 1, p.n) && pbulk::encode_rows3_u32(&tout, p.out, F, p.n_outputs, p.n)) {
+            void *targs[] = {&p, &tin, &tchg, &tout};
+            e = cudaLaunchKernel((const void *)j->k_pt, dim3((unsigned)ceil_div_u64(p.n, j->pl_block)), dim3(j->pl_block), targs, j->pt_smem, ctx->stream);
+        } else if (j->k_pl && aligned) e = cudaLaunchKernel((const void *)j->k_pl, dim3((unsigned)ceil_div_u64(p.n, j->pl_block)), dim3(j->pl_block), args, j->pl_smem, ctx->stream);
         else e = cudaLaunchKernel((const void *)j->k_ps, dim3(grid), dim3(128), args, 0, ctx->stream);
         ctx->launches++;
         return cproc_check(ctx, e, "graph (jit)");

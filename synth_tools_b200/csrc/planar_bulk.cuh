@@ -124,6 +124,16 @@ inline bool encode_rows_u32(CUtensorMap *tm, const void *base, uint64_t words, u
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// [rows][mid][words]: box = 32 words x 1 x 32 rows (the generated graph kernels: [inst][stream][F])
+inline bool encode_rows3_u32(CUtensorMap *tm, const void *base, uint64_t words, uint64_t mid, uint64_t rows) {
+    encode_tiled_t enc = encode_fn();
+    if (!enc || words >= (1ull << 31) || rows >= (1ull << 31) || mid == 0 || mid >= (1ull << 31) || (words & 3) || ((uintptr_t)base & 15)) return false;
+    const cuuint64_t dims[3] = {words, mid, rows}, strides[2] = {words * 4, mid * words * 4};
+    const cuuint32_t box[3] = {32, 1, 32}, estr[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 constexpr int T_STAGES = 3;
 constexpr uint32_t T_BOXB = 4096, T_STAGEB = 2 * T_BOXB;           // 64 words per tile
 constexpr size_t t_smem_bytes() { return (size_t)WARPS * T_STAGES * T_STAGEB + WARPS * T_STAGES * 8 + 1024; }

@@ -161,7 +161,7 @@ def c5(st, ctx, hbm_peak, reps=3, layout="tiled"):
     b.free(); ctx.dev_free(d_out)
     return _hbm("C5 patch sweep shard, 2,048 variants x 480,000 frames (10 s @ 48 kHz) stereo float raw out, %s, time-parallel scan" % layout,
                 N * F, "variant-frames", ms, 8.0, hbm_peak, "8 B out per variant-frame (7.86 GB per launch, larger than L2); "
-                "timed region = envelope walk + zero-state passes + scans + renders")
+                "timed region = envelope walk + closed-form zero-state pass + scan + render")
 
 
 def mix_bus_scaling(st, ctx, torch, dist, stream, dev, rank, world, reps=40):
@@ -239,6 +239,21 @@ def graph_bp5(st, ctx, hbm_peak, reps=3, layout="planar"):
                 hbm_peak, "4 B in + 4 B out per tick; 4 GiB in + 4 GiB out")
 
 
+def pdm_raw(st, ctx, hbm_peak, reps=3):
+    """pdm2_update (stm32f103/pdm.h) on a caller-supplied input stream, planar uint32 in / out."""
+    rng = np.random.default_rng(10)
+    N, F = 1024 * 1024, 1024
+    d_in = ctx.dev_alloc(4 * N * F); d_out = ctx.dev_alloc(4 * N * F)
+    chunk = rng.integers(0, 2**32, (16384, F), dtype=np.uint32)
+    for k in range(N // 16384):
+        ctx.h2d(d_in + k * chunk.nbytes, chunk)
+    b = ctx.batch(st.PDM, N, order=2, out_shift=24)
+    ms = _time(ctx, lambda: b.run_dev(F, inp=d_in, out=d_out), reps)
+    b.free(); ctx.dev_free(d_in); ctx.dev_free(d_out)
+    return _hbm("pdm2_update on an input stream, 1 Mi channels x 1,024 ticks, planar uint32 in/out (tensor-TMA staging)", N * F, "samples", ms, 8.0,
+                hbm_peak, "4 B in + 4 B out per sample; 4 GiB in + 4 GiB out")
+
+
 def c1_long(st, ctx, reps=3):
     """The reference's own shape made long: ONE voice of the test_cproc chain, 16 Mi ticks, time-parallel exact scan."""
     rng = np.random.default_rng(9)
@@ -258,7 +273,7 @@ def run_all(st, ctx, hbm_peak):
                lambda: c3b(st, ctx), lambda: c4(st, ctx), lambda: c4p(st, ctx),
                lambda: c5(st, ctx, hbm_peak, layout="tiled"), lambda: c5(st, ctx, hbm_peak, layout="planar"),
                lambda: graph_bp5(st, ctx, hbm_peak, layout="planar"), lambda: graph_bp5(st, ctx, hbm_peak, layout="interleaved"),
-               lambda: c1_long(st, ctx)):
+               lambda: pdm_raw(st, ctx, hbm_peak), lambda: c1_long(st, ctx)):
         try:
             rows.append(fn())
         except Exception as e:                       # never lose the headline line over a secondary row

@@ -18,7 +18,7 @@ def tiled16(a, N, F):
     return a.reshape(F // 16, N, 16).transpose(1, 0, 2).reshape(N, F)
 
 for case in range(n_cases):
-    kind = rng.choice(["pdm", "pdm_big", "grain", "graph", "voice", "gmix", "pdm_v1", "xmix"])
+    kind = rng.choice(["pdm", "pdm_big", "grain", "graph", "voice", "gmix", "pdm_v1", "xmix", "planar", "sweep"])
     if kind in ("pdm", "pdm_big"):
         order = int(rng.integers(1, 5)) if kind == "pdm" else 2
         bank = int(rng.choice([1, 2, 3, 4, 7])) if kind == "pdm" else 3
@@ -123,6 +123,80 @@ for case in range(n_cases):
         ok = np.array_equal(got, want) and np.array_equal(b.download_state(), ca) and np.array_equal(b.download_bank()[0], pa)
         desc = "bank=%d N=%d F=%d layout=%d" % (bank, N, F, layout)
         b.free()
+    elif kind == "planar":
+        # the PLANAR staging template (tensor TMA / per-lane bulk / scalar by planar_bulk) under four processors
+        N, F = int(rng.integers(1, 3000)), int(rng.integers(1, 150)) * int(rng.choice([1, 4, 16]))
+        mode = int(rng.integers(0, 3)); which = str(rng.choice(["pdm", "onepole", "pwm", "clock"]))
+        ctx.set_option("planar_bulk", mode)
+        if which == "pdm":
+            order = int(rng.integers(1, 5)); use_in = bool(rng.random() < 0.6); sh = int(rng.choice([8, 24, 31]))
+            s0 = rng.integers(0, 2**32, (N, order), dtype=np.uint32); inp = rng.integers(0, 2**32, (N, F), dtype=np.uint32)
+            dith = rng.integers(0, 1 << min(sh, 12), F, dtype=np.uint32); cst = rng.integers(0, 2**32, (N, 1), dtype=np.uint32)
+            sa = s0.copy()
+            want = orc.pdm_run(order, sa, N, F, inp if use_in else None, cst[:, 0].copy(), sh, dith)
+            b = ctx.batch(st.PDM, N, order=order, out_shift=sh); b.upload_state(s0); b.upload_param(cst)
+            out = np.zeros((N, F), np.uint32)
+            b.run(F, inp=inp if use_in else None, in2=dith, out=out)
+            ok = np.array_equal(out, want) and np.array_equal(b.download_state(), sa)
+        elif which == "onepole":
+            x = rng.uniform(-1, 1, (N, F)).astype(np.float32); a = rng.uniform(0.001, 0.9, (N, 1)).astype(np.float32); y0 = rng.uniform(-1, 1, (N, 1)).astype(np.float32)
+            ya = y0[:, 0].copy()
+            want = orc.onepole_run(ya, a[:, 0].copy(), N, F, x)
+            b = ctx.batch(st.ONEPOLE, N); b.upload_state(y0); b.upload_param(a)
+            out = np.zeros((N, F), np.float32)
+            b.run(F, inp=x, out=out)
+            ok = np.array_equal(out.view(np.uint32), want.view(np.uint32)) and np.array_equal(b.download_state()[:, 0].view(np.uint32), ya.view(np.uint32))
+        elif which == "pwm":
+            F = (F + 15) // 16 * 16
+            ph0 = rng.integers(0, 1 << 24, (N, 1), dtype=np.uint32); sp = rng.integers(0, 1 << 16, (N, 1), dtype=np.uint32)
+            pa = ph0[:, 0].copy()
+            want = orc.pwm_run(pa, sp[:, 0].copy(), N, F)
+            b = ctx.batch(st.PWM, N); b.upload_state(ph0); b.upload_param(sp)
+            out = np.zeros((N, F), np.uint8)
+            b.run(F, out=out)
+            ok = np.array_equal(out, want) and np.array_equal(b.download_state()[:, 0], pa)
+        else:
+            hp = rng.integers(-2, 300, N).astype(np.int32)
+            s0 = np.zeros((N, 2), np.int32); s0[:, 0] = rng.integers(0, 400, N); s0[:, 1] = rng.integers(0, 2, N)
+            sa = s0.copy()
+            want = orc.word_clock_run(sa, hp, N, F)
+            b = ctx.batch(st.WORD_CLOCK, N); b.upload_state(s0.view(np.uint32)); b.upload_param(hp.view(np.uint32).reshape(N, 1))
+            out = np.zeros((N, F), np.float32)
+            b.run(F, out=out)
+            ok = np.array_equal(out.view(np.uint32), want.view(np.uint32)) and np.array_equal(b.download_state().view(np.int32), sa)
+        desc = "%s N=%d F=%d planar_bulk=%d" % (which, N, F, mode)
+        b.free()
+        ctx.set_option("planar_bulk", 2)
+    elif kind == "sweep":
+        # time-parallel raw render: closed-form / ticked zero-state pass, any increment
+        N, F = int(rng.integers(1, 700)), int(rng.integers(33, 3000)) * 2
+        layout = st.TILED if rng.random() < 0.5 else st.PLANAR
+        closed = int(rng.random() < 0.7); groups = int(rng.choice([0, 1, 2, 4, 8])); chunk = int(rng.choice([0, 32, 64, 96, 256, 1024]))
+        prm = np.zeros(N, po.xvoice_param_dtype)
+        prm["inc"] = np.where(rng.random(N) < 0.7, rng.integers(0, 2**29, N), rng.integers(0, 2**32, N)).astype(np.uint32)
+        prm["f"] = rng.uniform(0.01, 0.3, N); prm["q"] = rng.uniform(0.5, 2.0, N)
+        prm["env_attack"] = rng.uniform(1e-3, 1e-1, N); prm["env_release"] = rng.uniform(2e-4, 1e-2, N)
+        prm["gate_frames"] = rng.integers(0, F, N)
+        prm["gl"] = rng.uniform(0, 1, N); prm["gr"] = 1.0 - prm["gl"]
+        s0 = np.zeros(N, po.xvoice_state_dtype)
+        s0["phase"] = rng.integers(0, 2**32, N, dtype=np.uint32); s0["env"] = rng.uniform(0, 1, N); s0["t"] = rng.integers(0, 100, N)
+        s0["lp"] = rng.uniform(-0.5, 0.5, N); s0["bp"] = rng.uniform(-0.5, 0.5, N)
+        sa = s0.copy()
+        want_raw, _ = orc.xvoice_run(sa, prm, N, F, want_mix=False)
+        ctx.set_option("xvoice_closed", closed); ctx.set_option("xvoice_groups", groups); ctx.set_option("xvoice_chunk", chunk)
+        b = ctx.batch(st.XVOICE, N, layout=layout, mode=st.XVOICE_SCAN)
+        b.upload_state(s0.view(np.uint32).reshape(N, 5)); b.upload_param(prm.view(np.uint32).reshape(N, 8))
+        raw = np.zeros(N * F * 2, np.float32)
+        b.run(F, out=raw)
+        got = raw.reshape(F // 2, N, 2, 2).transpose(1, 0, 2, 3).reshape(N, F, 2) if layout == st.TILED else raw.reshape(N, F, 2)
+        w64, g64 = want_raw.astype(np.float64), got.astype(np.float64)
+        gs = b.download_state().view(po.xvoice_state_dtype).reshape(N)
+        snr = 10 * np.log10((w64 ** 2).sum() / max(((g64 - w64) ** 2).sum(), 1e-300))
+        ok = np.abs(g64 - w64).max() <= 1e-5 * max(np.abs(w64).max(), 1e-30) and snr >= 120.0 and np.array_equal(gs["phase"], sa["phase"]) \
+            and np.array_equal(gs["t"], sa["t"]) and np.array_equal(gs["env"].view(np.uint32), sa["env"].view(np.uint32))
+        desc = "N=%d F=%d layout=%d closed=%d groups=%d chunk=%d snr=%.1f" % (N, F, layout, closed, groups, chunk, snr)
+        b.free()
+        ctx.set_option("xvoice_closed", 1); ctx.set_option("xvoice_groups", 0); ctx.set_option("xvoice_chunk", 0)
     elif kind == "xmix":
         N, F = int(rng.integers(1, 200000)), int(rng.integers(1, 200))
         prm = np.zeros(N, po.xvoice_param_dtype)
@@ -168,14 +242,17 @@ for case in range(n_cases):
             o += po.node_words(r[0])
         sa = s0.copy()
         want = orc.graph_run_multi(rows, n_in, outs, sa, N, F, inp, changed)
+        pmode = int(rng.choice([1, 2]))                        # generated planar kernel: per-lane bulk copies / tensor TMA
+        ctx.set_option("planar_bulk", pmode)
         b = ctx.batch(st.GRAPH, N, nodes=rows, n_inputs=n_in, out_node=outs, layout=layout)
         b.upload_state(s0)
         il = layout == st.INTERLEAVED
         out = np.zeros((F, len(outs), N) if il else (N, len(outs), F), np.uint32)
         b.run(F, inp=np.ascontiguousarray(inp.transpose(2, 1, 0)) if il else inp, in2=None if changed is None else (np.ascontiguousarray(changed.T) if il else changed), out=out)
         ok = np.array_equal(out.transpose(2, 1, 0) if il else out, want) and np.array_equal(b.download_state(), sa)
-        desc = "nodes=%d n_in=%d outs=%d N=%d F=%d layout=%d masked=%d" % (nn, n_in, len(outs), N, F, layout, masked)
+        desc = "nodes=%d n_in=%d outs=%d N=%d F=%d layout=%d masked=%d planar_bulk=%d [%s]" % (nn, n_in, len(outs), N, F, layout, masked, pmode, b.jit_log.strip()[:60])
         b.free()
+        ctx.set_option("planar_bulk", 2)
     print("%s %-8s %s" % ("ok  " if ok else "FAIL", kind, desc), flush=True)
     if not ok:
         bad += 1
