@@ -23,3 +23,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 12 --csv --log-file
 ncu --metrics gpu__time_duration.sum --clock-control none -c 12 --csv --log-file $O/launches_sweep_planar.csv python tools/prof_one.py sweep_planar 1 > /dev/null 2>&1
 $NCU -k regex:graph_planar -s 1 -o $O/prof_graph_planar python tools/prof_one.py graph 1 > /dev/null 2>&1
 ls -la $O/*.ncu-rep
+# the reports together exceed what gpurun brings back: summarise here, keep only the headline report
+SUMMARY_DIR=$O/summaries python tools/summarize_ncu.py $O/prof_*.ncu-rep
+for f in $O/prof_*.ncu-rep; do case $f in *pdm_v2_ws3*) ;; *) rm -f $f ;; esac; done
+du -sh $O

@@ -64,6 +64,8 @@ if __name__ == "__main__":
     for rep in sys.argv[1:]:
         name = os.path.basename(rep).replace(".ncu-rep", "").replace("prof_", "")
         text, tot = summarize(rep)
-        dst = os.path.join(ROOT, "profiles", "r1_%s_summary.txt" % name)
+        out_dir = os.environ.get("SUMMARY_DIR", os.path.join(ROOT, "profiles"))      # on the GPU box: gpurun_out/summaries (reports are too big to bring back)
+        os.makedirs(out_dir, exist_ok=True)
+        dst = os.path.join(out_dir, "r1_%s_summary.txt" % name)
         open(dst, "w").write(text)
         print(dst, tot)
