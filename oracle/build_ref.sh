@@ -25,5 +25,12 @@ gcc $CFLAGS -I"$REF/stm32f103" -c "$HERE/ref/ref_pdm.c" -o "$OBJ/ref_pdm.o"
 # (4) linux/synth_tools.c:78-100 (struct square_grain + square_grain_proc)
 ( cat "$HERE/ref/ref_pre_pd.h"; sed -n 78,100p "$REF/linux/synth_tools.c"; cat "$HERE/ref/ref_grain_tail.c" ) \
   | gcc $CFLAGS -x c -c - -o "$OBJ/ref_grain.o"
-gcc -shared -fopenmp -o "$HERE/_ref/libref.so" "$OBJ/ref_cproc.o" "$OBJ/test_cproc.o" "$OBJ/ref_pdm.o" "$OBJ/ref_synth.o" "$OBJ/ref_grain.o" -lm
+# (5) stm32f103/mod_pdm_pwm.c + mod_controlrate.c, whole files, against a hosted stand-in for the hardware layer
+# (pdm.h's trailing always_inline attribute lands on the next external function: allow inlining it under -fPIC)
+gcc $CFLAGS -fno-semantic-interposition -I"$HERE/shim/stm32" -I"$REF/stm32f103" -c "$HERE/ref/ref_v2_isr.c" -o "$OBJ/ref_v2_isr.o"
+# (6) linux/clock.c:108-120 (the word-clock loop; JACK glue excluded)
+( cat "$HERE/ref/ref_clock_pre.h"; sed -n 108,120p "$REF/linux/clock.c"; cat "$HERE/ref/ref_clock_tail.c" ) \
+  | gcc $CFLAGS -x c -c - -o "$OBJ/ref_clock.o"
+gcc -shared -fopenmp -o "$HERE/_ref/libref.so" "$OBJ/ref_cproc.o" "$OBJ/test_cproc.o" "$OBJ/ref_pdm.o" "$OBJ/ref_synth.o" "$OBJ/ref_grain.o" \
+    "$OBJ/ref_v2_isr.o" "$OBJ/ref_clock.o" -lm
 echo "built $HERE/_ref/libref.so"

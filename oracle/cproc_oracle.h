@@ -13,9 +13,14 @@
  * Parity status:
  *   - acc, edge, edge->acc graph, pdm1..4, voice bank, note table,
  *     square_grain: PINNED (reference source compiled here).
- *   - v1 carry-bit channel (ARM inline asm), v2 ISR body, pdm_update_line,
- *     pwm_update: restated arithmetic; v2 calls are pinned through the
- *     real pdm2_update.
+ *   - v2 channel (ISR body, glide, PDM_COPY_LINE, pdm_update_line, control
+ *     divider): PINNED -- mod_pdm_pwm.c and mod_controlrate.c are compiled
+ *     whole against a hosted stand-in for the hardware layer and the timer
+ *     ISR is called per tick (oracle/ref/ref_v2_isr.c).
+ *   - word clock (linux/clock.c:108-120): PINNED (the loop is piped from the
+ *     reference file into the harness).
+ *   - v1 carry-bit channel (ARM inline asm) and pwm_update (volatile
+ *     hardware globals): restated arithmetic.
  *   - dither PRNG random_u32(): PARITY UNPINNED.  uc_tools xorshift.h
  *     (github:zwizwa/uc_tools rev c0853b29811c5d184d39b630b3c848a86d5d5e9e)
  *     is not vendored in the reference tree.  We restate Marsaglia's

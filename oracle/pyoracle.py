@@ -63,8 +63,11 @@ def build(force=False):
     if force or not os.path.exists(ORACLE_SO) or \
             os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(HERE, "cproc_oracle.c")):
         subprocess.check_call(["bash", os.path.join(HERE, "build_oracle.sh")])
-    if os.path.isdir(os.environ.get("REF", "/root/reference")) and (force or not os.path.exists(REF_SO)):
-        subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
+    if os.path.isdir(os.environ.get("REF", "/root/reference")):
+        recipe = [os.path.join(HERE, "build_ref.sh")] + [os.path.join(d, f) for d in (os.path.join(HERE, "ref"), os.path.join(HERE, "shim"), os.path.join(HERE, "shim", "stm32"))
+                                                         for f in os.listdir(d) if os.path.isfile(os.path.join(d, f))]
+        if force or not os.path.exists(REF_SO) or os.path.getmtime(REF_SO) < max(os.path.getmtime(f) for f in recipe):
+            subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
 
 
 def _ptr(a):
@@ -231,6 +234,28 @@ class Ref(_Lib):
 
     def synth_sizeof(self, what):
         return self._fn("synth_sizeof", C.c_uint32, [C.c_int])(what)
+
+    def v2_isr_config(self):
+        """(channels per MCU, sizeof(struct channel), CONTROL_DIV_LOG) of the compiled mod_pdm_pwm.c"""
+        return tuple(self._fn("v2_isr_" + k, C.c_uint32, [])() for k in ("nb_channels", "sizeof_channel", "control_div_log"))
+
+    def v2_isr_run(self, chan, prng, count, setpoints, F):
+        """The real TIM3 ISR of mod_pdm_pwm.c (+ mod_controlrate.c) called F times for ONE MCU.
+        chan uint32 [nb][7] in/out; returns (duty uint8 [nb][F], prng', count')."""
+        nb = chan.shape[0]
+        duty = np.zeros((nb, F), np.uint8)
+        pr, cn = C.c_uint32(int(prng)), C.c_uint32(int(count))
+        f = self._fn("v2_isr_run", None, [VP, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), VP, C.c_uint64, C.c_uint64, VP])
+        f(_ptr(chan), C.byref(pr), C.byref(cn), _ptr(setpoints), 0 if setpoints is None else setpoints.shape[0], F, _ptr(duty))
+        return duty, pr.value, cn.value
+
+    def word_clock_run(self, state, hperiod, N, F, ev_clock=0, ev_cap=4096):
+        """linux/clock.c:108-120 itself.  Returns (out float [N][F], sample times of the MIDI clock bytes of clock ev_clock)."""
+        out = np.zeros((N, F), np.float32)
+        ev = np.zeros(ev_cap, np.uint32)
+        f = self._fn("word_clock_run", C.c_uint32, [VP, VP, C.c_uint64, C.c_uint64, VP, C.c_uint64, VP, C.c_uint32])
+        n_ev = f(_ptr(state), _ptr(hperiod), N, F, _ptr(out), ev_clock, _ptr(ev), ev_cap)
+        return out, ev[:min(n_ev, ev_cap)].copy()
 
     def note_table(self):
         t = np.zeros(128, np.uint32)

@@ -97,6 +97,42 @@ def test_pdm_v2_oracle_vs_ref(ref, oracle, order, bank):
         assert na == (count0 + F) % (1 << ctl)
 
 
+@pytest.mark.parametrize("count0,with_setpoints", [(0, True), (1234, True), (4095, False), (0, False)])
+def test_pdm_v2_oracle_vs_the_firmware_isr(ref, oracle, count0, with_setpoints):
+    """The REAL stm32f103/mod_pdm_pwm.c + mod_controlrate.c, compiled against a hosted hardware stand-in
+    (oracle/ref/ref_v2_isr.c): TIM3 ISR called once per tick, duty captured at hw_multi_pwm_duty().  The oracle's
+    v2 channel (glide, PDM_COPY_LINE at the control boundary, pdm_update_line, dither & 0x3FF, out_shift 24,
+    the divider) must agree on every duty byte and on the whole final state over 5+ control periods."""
+    nb, size, L = ref.v2_isr_config()
+    assert (nb, size, L) == (3, 28, 12)                         # PDM_FOR_CHANNELS c(0) c(1) c(2); struct channel; CONTROL_DIV_LOG
+    F = 5 * 4096 + 777
+    chan0 = rng.integers(0, 2**32, (nb, 7), dtype=np.uint32)
+    prng0 = int(rng.integers(1, 2**32))
+    sp = rng.integers(0x40000000, 0xC0000000, (F // 4096 + 2, nb), dtype=np.uint32) if with_setpoints else None
+    ca, cb = chan0.copy(), chan0.copy()
+    pa = np.array([prng0], np.uint32)
+    da, na = oracle.pdm_v2_run(ca, 2, nb, 3, pa, None, 0x3FF, count0, L, 24, sp, F)
+    db, pb, nb_ = ref.v2_isr_run(cb, prng0, count0, sp, F)
+    assert np.array_equal(da, db)
+    assert np.array_equal(ca, cb) and int(pa[0]) == pb and na == nb_ == (count0 + F) % 4096
+
+
+def test_word_clock_oracle_vs_ref(ref, oracle):
+    """linux/clock.c:108-120 compiled from the reference (the loop only; JACK glue excluded) vs the restatement,
+    two consecutive blocks; the MIDI clock bytes leave at the samples where the polarity turns 1."""
+    hp = np.array([1, 2, 3, 8, 62, 500, 0, 7], np.int32)
+    N, F = len(hp), 3000
+    s0 = np.zeros((N, 2), np.int32); s0[:, 0] = rng.integers(0, 100, N); s0[:, 1] = rng.integers(0, 2, N)
+    sa, sb = s0.copy(), s0.copy()
+    for blk in range(2):
+        prev = int(sb[4, 1])
+        a = oracle.word_clock_run(sa, hp, N, F)
+        b, ev = ref.word_clock_run(sb, hp, N, F, ev_clock=4)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(sa, sb)
+        pol = np.concatenate([[prev], a[4].astype(np.int64)])
+        assert np.array_equal(ev, np.flatnonzero((pol[1:] == 1) & (pol[:-1] != 1)))
+
+
 def test_v2_mean_tracks_setpoint(oracle):
     """Domain property: after the glide settles the mean duty equals setpoint/2^24."""
     N, F = 8, 1 << 16
