@@ -31,6 +31,9 @@ gcc $CFLAGS -fno-semantic-interposition -I"$HERE/shim/stm32" -I"$REF/stm32f103" 
 # (6) linux/clock.c:108-120 (the word-clock loop; JACK glue excluded)
 ( cat "$HERE/ref/ref_clock_pre.h"; sed -n 108,120p "$REF/linux/clock.c"; cat "$HERE/ref/ref_clock_tail.c" ) \
   | gcc $CFLAGS -x c -c - -o "$OBJ/ref_clock.o"
+# (7) stm32f103/mod_pdm.c:159-175 (pwm_update and the globals it works on)
+( echo '#include <stdint.h>'; sed -n 159,175p "$REF/stm32f103/mod_pdm.c"; cat "$HERE/ref/ref_pwm_tail.c" ) \
+  | gcc $CFLAGS -Dcontrol_div_count=ref_pwm_control_div_count -x c -c - -o "$OBJ/ref_pwm.o"   # (:165 also defines the v1 divider; mod_pdm_pwm.c has its own)
 gcc -shared -fopenmp -o "$HERE/_ref/libref.so" "$OBJ/ref_cproc.o" "$OBJ/test_cproc.o" "$OBJ/ref_pdm.o" "$OBJ/ref_synth.o" "$OBJ/ref_grain.o" \
-    "$OBJ/ref_v2_isr.o" "$OBJ/ref_clock.o" -lm
+    "$OBJ/ref_v2_isr.o" "$OBJ/ref_clock.o" "$OBJ/ref_pwm.o" -lm
 echo "built $HERE/_ref/libref.so"

@@ -19,8 +19,9 @@
  *     ISR is called per tick (oracle/ref/ref_v2_isr.c).
  *   - word clock (linux/clock.c:108-120): PINNED (the loop is piped from the
  *     reference file into the harness).
- *   - v1 carry-bit channel (ARM inline asm) and pwm_update (volatile
- *     hardware globals): restated arithmetic.
+ *   - pwm_update (mod_pdm.c:159-175): PINNED (lines piped from the reference).
+ *   - v1 carry-bit channel (ARM inline asm, no ARM toolchain here): restated
+ *     arithmetic, checked against an independent 64-bit formulation.
  *   - dither PRNG random_u32(): PARITY UNPINNED.  uc_tools xorshift.h
  *     (github:zwizwa/uc_tools rev c0853b29811c5d184d39b630b3c848a86d5d5e9e)
  *     is not vendored in the reference tree.  We restate Marsaglia's

@@ -133,6 +133,19 @@ def test_word_clock_oracle_vs_ref(ref, oracle):
         assert np.array_equal(ev, np.flatnonzero((pol[1:] == 1) & (pol[:-1] != 1)))
 
 
+def test_pwm_update_oracle_vs_ref(ref, oracle):
+    """stm32f103/mod_pdm.c:159-175 (pwm_update and its globals) compiled from the reference vs the restatement."""
+    N, F = 64, 5000
+    ph = rng.integers(0, 1 << 24, N, dtype=np.uint32); sp = rng.integers(0, 1 << 16, N, dtype=np.uint32)
+    sp[0] = 256 * 13                                         # the firmware's default speed (:160)
+    pa, pb = ph.copy(), ph.copy()
+    a = oracle.pwm_run(pa, sp.copy(), N, F)
+    b = np.zeros((N, F), np.uint8)
+    f = ref._fn("pwm_run", None, [po.VP, po.VP, po.C.c_uint64, po.C.c_uint64, po.VP])
+    f(po._ptr(pb), po._ptr(sp), N, F, po._ptr(b))
+    assert np.array_equal(a, b) and np.array_equal(pa, pb)
+
+
 def test_v2_mean_tracks_setpoint(oracle):
     """Domain property: after the glide settles the mean duty equals setpoint/2^24."""
     N, F = 8, 1 << 16
