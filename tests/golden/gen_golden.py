@@ -5,9 +5,11 @@ oracle/build_ref.sh from /root/reference).  Run in the build container:
     python tests/golden/gen_golden.py
 
 The reference tree does not travel to the GPU box; these fixtures do.
-Entries whose source is "restated" (v1 carry-bit PDM: ARM inline asm;
-pwm_update: volatile globals) cannot be compiled from the reference and come
-from the oracle's restatement -- they pin regressions only.
+The v2 firmware vectors (v2fw_*) come from the real TIM3 ISR of mod_pdm_pwm.c +
+mod_controlrate.c (oracle/ref/ref_v2_isr.c), the pwm vectors from mod_pdm.c:159-175.
+The v1 carry-bit PDM (ARM inline asm, no ARM toolchain here) cannot be compiled from
+the reference: its entries ("restated_v1_*") come from the oracle's restatement and
+pin regressions only.  (The pwm keys keep their historical "restated_" prefix.)
 """
 import os
 import shutil
@@ -62,7 +64,11 @@ chan = np.zeros((N, 7), np.uint32)
 chan[:, 0] = [2000000000, 0x40000000, 0x40000000]          # pdm_init, mod_pdm_pwm.c:147-161
 prng = np.array([2463534242], np.uint32)
 sp = np.array([[0x60000000, 0x80000000, 0xA0000000], [0x50000000, 0x70000000, 0xC0000000], [0x40000000] * 3], np.uint32)
-duty, cnt = ref.pdm_v2_run(chan, 2, N, 3, prng, None, 0x3FF, 0, 12, 24, sp, F)
+chan_b, prng_b = chan.copy(), prng.copy()
+duty, p1, cnt = ref.v2_isr_run(chan, int(prng[0]), 0, sp, F)      # the firmware's own ISR, once per tick
+prng[0] = p1
+duty_b, cnt_b = ref.pdm_v2_run(chan_b, 2, N, 3, prng_b, None, 0x3FF, 0, 12, 24, sp, F)   # the batched harness around the real pdm2_update agrees
+assert np.array_equal(duty, duty_b) and np.array_equal(chan, chan_b) and np.array_equal(prng, prng_b) and cnt == cnt_b
 G["v2fw_setpoints"], G["v2fw_duty_tail"], G["v2fw_state"], G["v2fw_prng"] = sp, duty[:, -256:], chan, prng
 G["v2fw_duty_wsum"] = (duty.astype(np.uint64) * (np.arange(F, dtype=np.uint64) + 1)).sum(axis=1)
 G["v2fw_count"] = np.array([cnt], np.uint32)
@@ -97,7 +103,7 @@ G["grain_in"], G["grain_thresh"], G["grain_state0"] = gi, th, gs.copy()
 G["grain_out"] = ref.square_grain_run(gs, th, N, F, gi)
 G["grain_state"] = gs
 
-# 7. restated (not compilable from the reference): v1 carry-bit PDM, pwm_update
+# 7. v1 carry-bit PDM (restated: ARM inline asm) and pwm_update (reference lines)
 N, F = 6, 256
 ch = np.zeros((N, 2), np.uint32)
 ch[:, 0] = [2000000000, 0x40000000, 0x60000000, 0x80000000, 0xA0000000, 0xC0000000]
@@ -105,7 +111,9 @@ prng = np.array([2463534242, 5, 9], np.uint32)
 bits = orc.pdm_v1_run(ch, N, 2, prng, None, 0x0FFFFFFF, F)
 G["restated_v1_bits"], G["restated_v1_state"], G["restated_v1_prng"] = np.packbits(bits, axis=1, bitorder="little"), ch, prng
 ph = np.array([0, 0x123456], np.uint32); spd = np.array([256 * 13, 5000], np.uint32)
-G["restated_pwm_duty"] = orc.pwm_run(ph, spd, 2, 256)
+pwm_duty = np.zeros((2, 256), np.uint8)
+ref._fn("pwm_run", None, [po.VP, po.VP, po.C.c_uint64, po.C.c_uint64, po.VP])(po._ptr(ph), po._ptr(spd), 2, 256, po._ptr(pwm_duty))   # mod_pdm.c:159-175
+G["restated_pwm_duty"] = pwm_duty
 G["restated_pwm_phase"] = ph
 
 np.savez_compressed(os.path.join(HERE, "golden_r1.npz"), **G)
