@@ -107,7 +107,7 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     else if (!strcmp(name, "pdm_stage")) ctx->pdm_stage = value != 0;
     else if (!strcmp(name, "pdm_ws")) { if (value < 0 || value > 3) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_ws must be 0..3"); ctx->pdm_ws = (int)value; }
     else if (!strcmp(name, "pdm_v1_chains")) { if (value != 1 && value != 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_v1_chains must be 1 or 2"); ctx->pdm_v1_chains = (int)value; }
-    else if (!strcmp(name, "pdm_planar_bulk")) ctx->pdm_planar_bulk = value != 0;
+    else if (!strcmp(name, "pdm_planar_bulk")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_planar_bulk must be 0..2"); ctx->pdm_planar_bulk = (int)value; }
     else if (!strcmp(name, "pdm_prng_fma")) ctx->pdm_prng_fma = value != 0;
     else if (!strcmp(name, "pdm_ctas_per_sm")) { if (value < 1 || value > 8) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_ctas_per_sm must be 1..8"); ctx->pdm_ctas_per_sm = (int)value; }
     else if (!strcmp(name, "pdm_slice_batches")) { if (value < 2 || value > 65536) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_slice_batches must be 2..65536"); ctx->pdm_slice_batches = (int)value; }

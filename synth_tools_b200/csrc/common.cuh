@@ -25,7 +25,7 @@ struct cproc_cuda_ctx {
     int pdm_ws = 3;           // 1: warp-specialised v2 kernel (PRNG producer warp + channel consumer warps); 2: second generation; 3: + dynamic (group, slice) schedule
     int pdm_v1_chains = 2;    // v1 thread-per-bank TILED kernels: PRNG chains per lane (1 or 2)
     int pdm_prng_fma = 0;     // ws3 producer: 1 = xorshift shifts as IMAD / IMAD.HI (FMA pipe) instead of SHF (ALU pipe); measured slower (1.54 vs 1.50 ms: the producer chain is latency bound)
-    int pdm_planar_bulk = 1;  // ws3: PLANAR duty rows staged in shared memory and sent with bulk stores
+    int pdm_planar_bulk = 2;  // ws3: PLANAR duty rows staged in shared memory: 1 per-lane bulk stores, 2 tensor-TMA boxes
     int pdm_ctas_per_sm = 4;  // ws3: persistent blocks per SM
     int pdm_slice_batches = 64;   // ws3: dither batches (64 ticks each) per work item
     uint32_t *d_work = nullptr;   // ws3: work counter + exit counter

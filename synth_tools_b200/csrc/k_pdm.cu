@@ -689,10 +689,15 @@ struct PdmV2Work {
 // ticks of its channel (four dither batches) in its own 256-byte row and sends them with one bulk
 // store (cp.async.bulk), instead of sixteen scattered 16-byte stores.
 #define WS3_PL_BATCHES (256 / WS2_T)
-template <int K, int B, int FORM, int P, int NS, bool PL>
-__global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws3(const PdmV2Params p, const PdmV2Ws2Extra ex, const PdmV2Work wk) {
+// PL: how PLANAR duty rows [ch][F] leave the block.  0: not PLANAR (TILED: 16-byte stores).  1: every consumer lane
+// stages 256 ticks of its channel and sends them with one cp.async.bulk.  2: tensor TMA -- a consumer warp fills a box of
+// 128 ticks x 32 channels (SWIZZLE_128B: lane r writes 16-tick chunk c at r*128 + ((c ^ (r & 7)) << 4), conflict free),
+// one elected lane stores it through the 2-D map over the duty rows; two boxes per warp alternate.
+template <int K, int B, int FORM, int P, int NS, int PL>
+__global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws3(const PdmV2Params p, const PdmV2Ws2Extra ex, const PdmV2Work wk, const __grid_constant__ CUtensorMap tm_out) {
+    __shared__ __align__(1024) uint8_t pbox[PL == 2 ? B : 1][PL == 2 ? 2 : 1][PL == 2 ? 4096 : 16];
     __shared__ __align__(16) uint32_t dbuf[NS][WS2_T / 4][32][4];
-    __shared__ __align__(16) uint8_t prow[PL ? B * 32 : 1][PL ? 272 : 16];      // 256 duty bytes per consumer lane (+16: bank-group skew)
+    __shared__ __align__(16) uint8_t prow[PL == 1 ? B * 32 : 1][PL == 1 ? 272 : 16];      // 256 duty bytes per consumer lane (+16: bank-group skew)
     __shared__ uint32_t jt[P > 1 ? P - 1 : 1][4][256];
     constexpr int NT = 32 * (B + 1);
     if constexpr (P > 1) {
@@ -759,10 +764,15 @@ __global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws3(const PdmV2Params p
             const bool store = c < p.n;
             uint8_t *dst = p.layout == CPROC_CUDA_TILED ? p.out + ((bt0 * (WS2_T / 16) * p.n + c) << 4) : p.out + c * p.F + bt0 * WS2_T;
             const uint64_t dstep = p.layout == CPROC_CUDA_TILED ? p.n << 4 : 16;
-            const uint32_t prow_s = PL ? (uint32_t)__cvta_generic_to_shared(&prow[PL ? cl : 0][0]) : 0u;
+            const uint32_t prow_s = PL == 1 ? (uint32_t)__cvta_generic_to_shared(&prow[PL == 1 ? cl : 0][0]) : 0u;
+            const uint32_t pbox_s = PL == 2 ? (uint32_t)__cvta_generic_to_shared(&pbox[PL == 2 ? cw : 0][0][0]) : 0u;
             uint32_t s = 0;
             for (uint64_t bt = 0; bt < nb; ++bt) {
-                if (PL && (bt % WS3_PL_BATCHES) == 0 && bt) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the row has left
+                if (PL == 1 && (bt % WS3_PL_BATCHES) == 0 && bt) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the row has left
+                if (PL == 2 && (bt & 1) == 0 && bt >= 4) {            // this box last left two boxes ago
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                }
                 if (until == 0) {                                     // uniform over the block
                     r.boundary(sp_row, c, p.n, L);
                     if (sp_row) sp_row += p.n;
@@ -783,14 +793,28 @@ __global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws3(const PdmV2Params p
                         for (int i = 0; i < 4; ++i) a[i] = v2_tick_q24<K, FORM>(r.p0[0], r.v0[0], r.s[0], d[i], m1, m2);   // :108-116
                         w[i4] = pack_top_bytes(a[0], a[1], a[2], a[3]);
                     }
-                    if (PL) {
+                    if (PL == 1) {
                         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(prow_s + (uint32_t)(bt % WS3_PL_BATCHES) * WS2_T + gq * 16), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                    } else if (PL == 2) {
+                        const uint32_t ch = ((uint32_t)bt & 1u) * (WS2_T / 16) + gq;                  // 16-tick chunk within the 128-tick box
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(pbox_s + (((uint32_t)bt >> 1) & 1u) * 4096u + lane * 128u + ((ch ^ (lane & 7u)) << 4)),
+                                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
                     } else {
                         if (store) st_v4_stream(dst, make_uint4(w[0], w[1], w[2], w[3]));
                         dst += dstep;
                     }
                 }
-                if (PL && ((bt + 1) % WS3_PL_BATCHES == 0 || bt + 1 == nb)) {        // 256 ticks staged (or the slice ends)
+                if (PL == 2 && (bt & 1) == 1) {                       // 128 ticks x 32 channels staged (slices hold an even number of batches)
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                                     ::"l"(reinterpret_cast<uint64_t>(&tm_out)), "r"((int32_t)((bt0 + bt - 1) * WS2_T)), "r"((int32_t)(bank0 * B + cw * 32)),
+                                       "r"(pbox_s + (((uint32_t)bt >> 1) & 1u) * 4096u) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+                if (PL == 1 && ((bt + 1) % WS3_PL_BATCHES == 0 || bt + 1 == nb)) {        // 256 ticks staged (or the slice ends)
                     const uint32_t nbytes = (uint32_t)((bt % WS3_PL_BATCHES) + 1) * WS2_T;
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     if (store) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(prow_s), "r"(nbytes) : "memory");
@@ -801,6 +825,7 @@ __global__ void __launch_bounds__(32 * (B + 1)) k_pdm_v2_ws3(const PdmV2Params p
                 s = (s + 1 == NS) ? 0 : s + 1;
             }
             if (PL) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (PL == 2) __syncwarp();
             if (live) r.store(p.st, p.npad, c);
         }
         __syncthreads();                                              // every state word of the item is written
@@ -912,12 +937,18 @@ static int launch_v2_order(cproc_cuda_batch *b, PdmV2Params &p, bool fast, bool 
             wk.groups = (uint32_t)C; wk.bps = (uint32_t)ctx->pdm_slice_batches;
             wk.slices = (uint32_t)ceil_div_u64(batches, wk.bps);
             const int f = form;
-#define WS3_GO(FF, PP) k_pdm_v2_ws3<2, 3, FF, PP, 2, false><<<(unsigned)ctas, 128, 0, ctx->stream>>>(p, ex, wk)
+            CUtensorMap tm0;
+            memset(&tm0, 0, sizeof(tm0));
+#define WS3_GO(FF, PP) k_pdm_v2_ws3<2, 3, FF, PP, 2, 0><<<(unsigned)ctas, 128, 0, ctx->stream>>>(p, ex, wk, tm0)
             // PLANAR rows leave through shared memory (default variant only): 64-byte aligned rows, slices of whole 256-tick stages
             if (ctx->pdm_planar_bulk && p.layout == CPROC_CUDA_PLANAR && f == 1 && P == 2 && (p.F % 16) == 0 && ((uintptr_t)p.out & 15) == 0 &&
-                ((uint64_t)wk.bps % WS3_PL_BATCHES) == 0)
-                k_pdm_v2_ws3<2, 3, 1, 2, 2, true><<<(unsigned)ctas, 128, 0, ctx->stream>>>(p, ex, wk);
-            else
+                ((uint64_t)wk.bps % WS3_PL_BATCHES) == 0) {
+                // tensor TMA needs whole 128-tick boxes in every slice (bps is a multiple of 4 batches; the last slice ends at F)
+                if (ctx->pdm_planar_bulk >= 2 && (p.F % 128) == 0 && pbulk::encode_rows_u8(&tm0, p.out, p.F, p.n))
+                    k_pdm_v2_ws3<2, 3, 1, 2, 2, 2><<<(unsigned)ctas, 128, 0, ctx->stream>>>(p, ex, wk, tm0);
+                else
+                    k_pdm_v2_ws3<2, 3, 1, 2, 2, 1><<<(unsigned)ctas, 128, 0, ctx->stream>>>(p, ex, wk, tm0);
+            } else
             if (P == 4) { if (f == 1) WS3_GO(1, 4); else if (f == 2) WS3_GO(2, 4); else WS3_GO(0, 4); }
             else if (P == 2) { if (f == 1) WS3_GO(1, 2); else if (f == 2) WS3_GO(2, 2); else WS3_GO(0, 2); }
             else { if (f == 1) WS3_GO(1, 1); else if (f == 2) WS3_GO(2, 1); else WS3_GO(0, 1); }

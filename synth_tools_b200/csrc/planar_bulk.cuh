@@ -124,6 +124,16 @@ inline bool encode_rows_u32(CUtensorMap *tm, const void *base, uint64_t words, u
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// [rows][bytes] stream of bytes (PDM v2 duty rows): box = 128 bytes x 32 rows
+inline bool encode_rows_u8(CUtensorMap *tm, const void *base, uint64_t bytes, uint64_t rows) {
+    encode_tiled_t enc = encode_fn();
+    if (!enc || bytes >= (1ull << 31) || rows >= (1ull << 31) || (bytes & 15) || ((uintptr_t)base & 15)) return false;
+    const cuuint64_t dims[2] = {bytes, rows}, strides[1] = {bytes};
+    const cuuint32_t box[2] = {128, 32}, estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // [rows][mid][words]: box = 32 words x 1 x 32 rows (the generated graph kernels: [inst][stream][F])
 inline bool encode_rows3_u32(CUtensorMap *tm, const void *base, uint64_t words, uint64_t mid, uint64_t rows) {
     encode_tiled_t enc = encode_fn();

@@ -89,7 +89,7 @@ def _v2_case(st, ctx, oracle, order, bank, N, F, layout, count0, use_setp, use_d
         ctx.set_option("pdm_slots", 2)
         ctx.set_option("pdm_ctas_per_sm", 4)
         ctx.set_option("pdm_slice_batches", 64)
-        ctx.set_option("pdm_planar_bulk", 1)
+        ctx.set_option("pdm_planar_bulk", 2)
 
 
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
@@ -160,10 +160,12 @@ def test_pdm_v2_ws3_c2_shape(st, ctx, oracle, ctas, slice_b, F):
              opts={"pdm_ws": 3, "pdm_ctas_per_sm": ctas, "pdm_slice_batches": slice_b})
 
 
-@pytest.mark.parametrize("slice_b,F,bulk", [(4, 64 * 9, 1), (8, 64 * 21, 1), (4, 64 * 16, 1), (4, 64 * 9, 0)])
+@pytest.mark.parametrize("slice_b,F,bulk", [(4, 64 * 9, 1), (8, 64 * 21, 1), (4, 64 * 16, 1), (4, 64 * 9, 0),
+                                             (4, 64 * 16, 2), (8, 64 * 22, 2), (4, 64 * 10, 2), (12, 64 * 38, 2), (4, 64 * 9, 2)])
 def test_pdm_v2_ws3_planar_rows(st, ctx, oracle, slice_b, F, bulk):
-    """PLANAR duty rows of the dynamic-schedule kernel through the shared-memory row stage and bulk stores
-    (256-tick stages, a ragged last stage per slice, ragged channel count), and with the stage off."""
+    """PLANAR duty rows of the dynamic-schedule kernel: per-lane row stage and bulk stores (1: 256-tick stages, a
+    ragged last stage per slice), tensor-TMA boxes of 128 ticks x 32 channels (2: whole boxes only, F % 128 == 0,
+    else it falls back to 1), and with the stage off (0); ragged channel count (rows clipped by the tensor map)."""
     _v2_case(st, ctx, oracle, 2, 3, N=96 * 150 + 5, F=F, layout=st.PLANAR, count0=64, use_setp=True, use_dext=False, ctl=8,
              opts={"pdm_ws": 3, "pdm_ctas_per_sm": 1, "pdm_slice_batches": slice_b, "pdm_planar_bulk": bulk})
 

@@ -9,9 +9,10 @@ d_out = ctx.dev_alloc(N * F)
 rows = F // 4096
 sp = np.random.default_rng(0).integers(0x40000000, 0xC0000000, (rows, N), dtype=np.uint32)
 d_sp = ctx.dev_alloc(sp.nbytes); ctx.h2d(d_sp, sp)
-for layout, name in ((st.TILED, "TILED"), (st.PLANAR, "PLANAR")):
-    for ws in (3, 2, 0):
-        ctx.set_option("pdm_ws", ws)
+for layout, name, ws, pb in ((st.TILED, "TILED", 3, 2), (st.PLANAR, "PLANAR tensor-TMA boxes", 3, 2), (st.PLANAR, "PLANAR per-lane bulk", 3, 1),
+                             (st.PLANAR, "PLANAR direct stores", 3, 0), (st.TILED, "TILED", 2, 2), (st.PLANAR, "PLANAR", 2, 2)):
+    for _ in (0,):
+        ctx.set_option("pdm_ws", ws); ctx.set_option("pdm_planar_bulk", pb)
         b = ctx.batch(st.PDM_V2, N, order=2, bank_size=3, ctl_div_log=12, layout=layout)
         b.run_dev(F, ctl=d_sp, n_ctl=rows, out=d_out); ctx.sync()
         best = 1e9
