@@ -121,6 +121,7 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     else if (!strcmp(name, "grain_mix2")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "grain_mix2 must be 0..2"); ctx->grain_mix2 = (int)value; }
     else if (!strcmp(name, "xvoice_chunk")) { if (value < 0) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice_chunk must be >= 0"); ctx->xvoice_chunk = (int)value; }
     else if (!strcmp(name, "xvoice_closed")) ctx->xvoice_closed = value ? 1 : 0;
+    else if (!strcmp(name, "run_graph")) { if (value < 0 || value > 3) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "run_graph must be 0..3"); ctx->run_graph = (int)value; }
     else if (!strcmp(name, "xvoice_groups")) { if (value < 0 || value > 8) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice_groups must be 0..8"); ctx->xvoice_groups = (int)value; }
     else if (!strcmp(name, "pdm_slots")) { if (value != 2 && value != 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_slots must be 2 or 4"); ctx->pdm_slots = (int)value; }
     else if (!strcmp(name, "pdm_chains")) { if (value != 1 && value != 2 && value != 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_chains must be 1, 2 or 4"); ctx->pdm_chains = (int)value; }
@@ -235,6 +236,8 @@ int cproc_cuda_free(cproc_cuda_batch *b) {
     void *ptrs[] = { b->d_state, b->d_param, b->d_prng, b->d_nodes, b->d_in, b->d_in2, b->d_ctl, b->d_out, b->d_out2, b->d_mix, b->d_flags, b->d_scratch, b->d_aux };
     for (void *q : ptrs) if (q) cudaFree(q);
     for (cproc_graph_jit &j : b->jit) if (j.lib) cudaLibraryUnload(j.lib);
+    if (b->rg.exec) cudaGraphExecDestroy(b->rg.exec);
+    if (b->rg.h) cudaFreeHost(b->rg.h);
     delete b;
     return 0;
 }
@@ -399,6 +402,102 @@ int cproc_cuda_run(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     int rc;
     cproc_cuda_io d = *io;
     cudaStream_t st = ctx->stream;
+    // ---- small blocks (the JACK / Pd period: a few KB): one CUDA graph per (batch, shape) ----------------------
+    // A period of a real-time host is launch-latency bound: pageable H2D + kernels + pageable D2H + sync are 4-6
+    // driver calls.  For processors whose kernel arguments depend only on the batch and the shape (not on a
+    // per-call counter: the PDM processors carry control_div_count and epochs) the second call with a given shape
+    // captures [H2D from pinned staging, the launches of dispatch(), D2H to pinned staging] and every later call
+    // is two host memcpys around one cudaGraphLaunch.
+    const uint32_t proc = b->cfg.proc;
+    const bool graphable = ctx->run_graph && sz.in + sz.in2 + sz.ctl + sz.out + sz.mix <= (256u << 10) &&
+        ((proc == CPROC_CUDA_GRAPH && b->cfg.mode != CPROC_CUDA_GRAPH_SCAN) || proc == CPROC_CUDA_VOICE_BANK || proc == CPROC_CUDA_SQUARE_GRAIN ||
+         proc == CPROC_CUDA_WORD_CLOCK || proc == CPROC_CUDA_PWM || (proc == CPROC_CUDA_ONEPOLE && b->cfg.mode != CPROC_CUDA_ONEPOLE_SCAN));
+    // run_graph 3: no graph and no copies -- the kernels work on pinned staging directly (one launch + one sync per
+    // period; nothing is captured, so every processor qualifies)
+    if (ctx->run_graph >= 3 && sz.in + sz.in2 + sz.ctl + sz.out + sz.mix <= (64u << 10)) {
+        cproc_cuda_batch::run_graph &g = b->rg;
+        const size_t want[5] = {io->in ? sz.in : 0, io->in2 ? sz.in2 : 0, io->ctl ? sz.ctl : 0, io->out ? sz.out : 0, io->mix ? sz.mix : 0};
+        size_t off[5], total = 0;
+        for (int k = 0; k < 5; ++k) { off[k] = total; total += (want[k] + 255) & ~(size_t)255; }
+        if (g.cap < total) {
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.seen = 0; g.F = 0; }
+            CK(ctx, cudaStreamSynchronize(st));
+            if (g.h) cudaFreeHost(g.h);
+            g.h = nullptr; g.cap = 0;
+            CK(ctx, cudaHostAlloc((void **)&g.h, total < 4096 ? 4096 : total, cudaHostAllocDefault));
+            g.cap = total < 4096 ? 4096 : total;
+        }
+        const void *src[3] = {io->in, io->in2, io->ctl};
+        for (int k = 0; k < 3; ++k) if (want[k]) memcpy(g.h + off[k], src[k], want[k]);
+        if (want[0]) d.in = g.h + off[0];
+        if (want[1]) d.in2 = g.h + off[1];
+        if (want[2]) d.ctl = g.h + off[2];
+        if (want[3]) d.out = g.h + off[3];
+        if (want[4]) d.mix = g.h + off[4];
+        if ((rc = dispatch(b, F, &d))) return rc;
+        CK(ctx, cudaStreamSynchronize(st));
+        if (want[3]) memcpy(io->out, g.h + off[3], want[3]);
+        if (want[4]) memcpy(io->mix, g.h + off[4], want[4]);
+        return 0;
+    }
+    if (graphable) {
+        cproc_cuda_batch::run_graph &g = b->rg;
+        const size_t want[5] = {io->in ? sz.in : 0, io->in2 ? sz.in2 : 0, io->ctl ? sz.ctl : 0, io->out ? sz.out : 0, io->mix ? sz.mix : 0};
+        const bool same = g.F == F && g.layout == io->layout && !memcmp(g.sz, want, sizeof(want));
+        if (!same) {                                       // new shape: this call runs the ordinary way and warms every lazy allocation
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            g.F = F; g.layout = io->layout; memcpy(g.sz, want, sizeof(want)); g.seen = 0;
+        }
+        size_t off[5], total = 0;
+        for (int k = 0; k < 5; ++k) { off[k] = total; total += (want[k] + 255) & ~(size_t)255; }
+        if (same && g.seen == 1 && !g.exec) {              // second call with this shape: capture
+            if (g.cap < total) {
+                if (g.h) cudaFreeHost(g.h);
+                g.h = nullptr; g.cap = 0;
+                CK(ctx, cudaHostAlloc((void **)&g.h, total, cudaHostAllocDefault));
+                g.cap = total;
+            }
+            if (want[0] && (rc = grow(ctx, &b->d_in, &b->cap_in, sz.in))) return rc;
+            if (want[1] && (rc = grow(ctx, &b->d_in2, &b->cap_in2, sz.in2))) return rc;
+            if (want[2] && (rc = grow(ctx, &b->d_ctl, &b->cap_ctl, sz.ctl))) return rc;
+            if (want[3] && (rc = grow(ctx, &b->d_out, &b->cap_out, sz.out))) return rc;
+            if (want[4] && (rc = grow(ctx, &b->d_out2, &b->cap_out2, sz.mix))) return rc;
+            cudaGraph_t graph = nullptr;
+            const uint64_t launches0 = ctx->launches;
+            bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            // run_graph 2: no copy nodes at all -- the kernels read and write the pinned staging itself (pinned host memory
+            // is device-addressable at the same address under UVA; a block is a few hundred bytes, one PCIe round trip)
+            const bool zc = ctx->run_graph >= 2;
+            if (ok) {
+                if (want[0]) { if (zc) d.in = g.h + off[0]; else { ok = ok && cudaMemcpyAsync(b->d_in, g.h + off[0], want[0], cudaMemcpyHostToDevice, st) == cudaSuccess; d.in = b->d_in; } }
+                if (want[1]) { if (zc) d.in2 = g.h + off[1]; else { ok = ok && cudaMemcpyAsync(b->d_in2, g.h + off[1], want[1], cudaMemcpyHostToDevice, st) == cudaSuccess; d.in2 = b->d_in2; } }
+                if (want[2]) { if (zc) d.ctl = g.h + off[2]; else { ok = ok && cudaMemcpyAsync(b->d_ctl, g.h + off[2], want[2], cudaMemcpyHostToDevice, st) == cudaSuccess; d.ctl = b->d_ctl; } }
+                if (want[3]) d.out = zc ? (void *)(g.h + off[3]) : b->d_out;
+                if (want[4]) d.mix = zc ? (void *)(g.h + off[4]) : b->d_out2;
+                ok = ok && dispatch(b, F, &d) == 0;
+                if (want[3] && !zc) ok = ok && cudaMemcpyAsync(g.h + off[3], b->d_out, want[3], cudaMemcpyDeviceToHost, st) == cudaSuccess;
+                if (want[4] && !zc) ok = ok && cudaMemcpyAsync(g.h + off[4], b->d_out2, want[4], cudaMemcpyDeviceToHost, st) == cudaSuccess;
+                ok = (cudaStreamEndCapture(st, &graph) == cudaSuccess) && ok && graph;
+            }
+            if (ok) ok = cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            g.kernels = (uint32_t)(ctx->launches - launches0);
+            ctx->launches = launches0;                     // nothing has run yet: replays count below
+            if (!ok) { cudaGetLastError(); g.exec = nullptr; g.seen = 2; ctx->err.clear(); }
+            d = *io;
+        }
+        if (same && g.exec) {
+            const void *src[3] = {io->in, io->in2, io->ctl};
+            for (int k = 0; k < 3; ++k) if (want[k]) memcpy(g.h + off[k], src[k], want[k]);
+            CK(ctx, cudaGraphLaunch(g.exec, st));
+            ctx->launches += g.kernels;
+            CK(ctx, cudaStreamSynchronize(st));
+            if (want[3]) memcpy(io->out, g.h + off[3], want[3]);
+            if (want[4]) memcpy(io->mix, g.h + off[4], want[4]);
+            return 0;
+        }
+        if (g.seen == 0) g.seen = 1;
+    }
     if (io->in && sz.in) {
         if ((rc = grow(ctx, &b->d_in, &b->cap_in, sz.in))) return rc;
         CK(ctx, cudaMemcpyAsync(b->d_in, io->in, sz.in, cudaMemcpyHostToDevice, st));

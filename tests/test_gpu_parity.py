@@ -1179,3 +1179,68 @@ def test_word_clock(st, ctx, oracle, layout, N, F):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), blk
         assert np.array_equal(b.download_state().view(np.int32), sa)
     b.free()
+
+
+@pytest.mark.parametrize("use_graph", [1, 0, 2, 3])
+def test_small_blocks_replay_as_cuda_graph(st, ctx, oracle, use_graph):
+    """cproc_cuda_run with host buffers: from the third call with one shape on, a period is two memcpys around one
+    cudaGraphLaunch (captured at the second call: 1 = H2D, kernels, D2H; 2 = the kernels alone, working on the pinned
+    staging; 3 = no graph, direct launches on the pinned staging; 0 = staged copies).  Eight consecutive periods of five processors,
+    a shape change in the middle, state uploads between periods: bit-exact against the oracle either way, and the
+    launch counter keeps counting the kernels of the replays."""
+    ctx.set_option("run_graph", use_graph)
+    try:
+        F = 64
+        # test_cproc chain, 3 voices
+        b = ctx.batch(st.GRAPH, 3, nodes=po.GRAPH_TEST_CPROC)
+        s = np.zeros((3, 3), np.uint32); sa = s.copy(); b.upload_state(s)
+        per = []
+        for k in range(8):
+            f = F if k != 4 else 96                          # one period of another size
+            x = rng.integers(0, 2, (3, f), dtype=np.uint32)
+            want = oracle.graph_run(po.GRAPH_TEST_CPROC, 1, 1, sa, 3, f, x)
+            out = np.zeros((3, f), np.uint32)
+            l0 = ctx.launches
+            b.run(f, inp=x, out=out)
+            per.append(ctx.launches - l0)
+            assert np.array_equal(out, want), k
+        assert np.array_equal(b.download_state(), sa) and len(set(per)) == 1 and per[0] >= 1
+        b.free()
+        # voice bank with a note change between periods (state upload), word clock, square_grain in place, one-pole
+        V = 128
+        voices = np.zeros((V, 2), np.uint32); voices[::3, 0] = [oracle.note_to_inc(int(n)) for n in rng.integers(30, 90, len(voices[::3]))]
+        vb = ctx.batch(st.VOICE_BANK, V, voices_per_bus=64)
+        hp = np.array([62, 500, 8], np.int32); cs = np.zeros((3, 2), np.int32); cs[:, 1] = 1; csa = cs.copy()
+        cb = ctx.batch(st.WORD_CLOCK, 3); cb.upload_state(cs.view(np.uint32)); cb.upload_param(hp.view(np.uint32).reshape(3, 1))
+        G = 5
+        gth = rng.uniform(0.05, 0.5, (G, 1)).astype(np.float32); gst = np.zeros(G, np.float32)
+        gb = ctx.batch(st.SQUARE_GRAIN, G); gb.upload_param(gth)
+        a = rng.uniform(0.01, 0.5, (G, 1)).astype(np.float32); y = np.zeros(G, np.float32)
+        ob = ctx.batch(st.ONEPOLE, G); ob.upload_param(a)
+        for k in range(8):
+            if k == 5:
+                voices[1, 0] = oracle.note_to_inc(69)
+            vb.upload_state(voices)
+            _, want = oracle.voice_bank_run(voices, V, 64, po.MIX_SAW, F)
+            out = np.zeros((2, F), np.float32)
+            vb.run(F, out=out)
+            voices = vb.download_state()
+            assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), k
+            wantc = oracle.word_clock_run(csa, hp, 3, F)
+            outc = np.zeros((3, F), np.float32)
+            cb.run(F, out=outc)
+            assert np.array_equal(outc, wantc), k
+            x = rng.uniform(-1, 1, (G, F)).astype(np.float32)
+            wantg = oracle.square_grain_run(gst, gth[:, 0].copy(), G, F, x)
+            io = x.copy()
+            gb.run(F, inp=io, out=io)                        # in place, as Pd does
+            assert np.array_equal(io.view(np.uint32), wantg.view(np.uint32)), k
+            wanto = oracle.onepole_run(y, a[:, 0].copy(), G, F, x)
+            outo = np.zeros((G, F), np.float32)
+            ob.run(F, inp=x, out=outo)
+            assert np.array_equal(outo.view(np.uint32), wanto.view(np.uint32)), k
+        assert np.array_equal(cb.download_state().view(np.int32), csa)
+        for q in (vb, cb, gb, ob):
+            q.free()
+    finally:
+        ctx.set_option("run_graph", 2)

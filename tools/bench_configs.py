@@ -77,7 +77,7 @@ def c1(st, ctx):
     b.free()
     return {"config": "C1 test_cproc chain (edge -> acc), 1 voice x 64-frame blocks, 750 blocks through cproc_cuda_run (host buffers)",
             "value": us, "unit": "us/block", "bound": "launch latency", "block_period_us": 64 / 48000 * 1e6,
-            "note": "H2D 256 B + generated kernel + D2H 256 B + stream sync per block; a 64-frame period at 48 kHz is 1333 us"}
+            "note": "per block: memcpy 256 B to pinned staging, one cudaGraphLaunch (the generated kernel reads and writes the staging), stream sync, memcpy back; a 64-frame period at 48 kHz is 1333 us"}
 
 
 def c2_v1(st, ctx, reps=3):
