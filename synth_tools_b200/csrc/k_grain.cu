@@ -93,8 +93,13 @@ __global__ void __launch_bounds__(GI_BLOCK) k_grain_interleaved(const GrainParam
 
 // Four adjacent grains per thread (128-bit loads/stores): a block covers 2 KiB of every
 // frame row, which quarters the number of distant row segments (and pages) a block walks.
+#ifndef GI4_BATCH
 #define GI4_BATCH 8
-__global__ void __launch_bounds__(GI_BLOCK) k_grain_interleaved4(const GrainParams p) {
+#endif
+#ifndef GI4_MINB
+#define GI4_MINB 1
+#endif
+__global__ void __launch_bounds__(GI_BLOCK, GI4_MINB) k_grain_interleaved4(const GrainParams p) {
     const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (g >= p.n) return;                                    // n % 4 == 0
     float4 st = *(const float4 *)(p.state + g);
