@@ -102,6 +102,7 @@ int cproc_cuda_sync(cproc_cuda_ctx *ctx) {
 
 int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) {
     if (!ctx || !name) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "set_option: NULL argument");
+    ctx->opt_epoch++;                                        // captured period graphs (cproc_cuda_run) are re-captured
     if (!strcmp(name, "pdm_block")) { if (value < 32 || value > 128 || (value & 31)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_block must be 32, 64, 96 or 128"); ctx->pdm_block = (int)value; }
     else if (!strcmp(name, "pdm_tpb")) ctx->pdm_tpb = value != 0;
     else if (!strcmp(name, "pdm_stage")) ctx->pdm_stage = value != 0;
@@ -443,10 +444,10 @@ int cproc_cuda_run(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     if (graphable) {
         cproc_cuda_batch::run_graph &g = b->rg;
         const size_t want[5] = {io->in ? sz.in : 0, io->in2 ? sz.in2 : 0, io->ctl ? sz.ctl : 0, io->out ? sz.out : 0, io->mix ? sz.mix : 0};
-        const bool same = g.F == F && g.layout == io->layout && !memcmp(g.sz, want, sizeof(want));
+        const bool same = g.F == F && g.layout == io->layout && g.opt_epoch == ctx->opt_epoch && !memcmp(g.sz, want, sizeof(want));
         if (!same) {                                       // new shape: this call runs the ordinary way and warms every lazy allocation
             if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
-            g.F = F; g.layout = io->layout; memcpy(g.sz, want, sizeof(want)); g.seen = 0;
+            g.F = F; g.layout = io->layout; g.opt_epoch = ctx->opt_epoch; memcpy(g.sz, want, sizeof(want)); g.seen = 0;
         }
         size_t off[5], total = 0;
         for (int k = 0; k < 5; ++k) { off[k] = total; total += (want[k] + 255) & ~(size_t)255; }

@@ -50,6 +50,7 @@ struct cproc_cuda_ctx {
     int xvoice_block = 128;
     int xvoice_groups = 0;    // XVOICE_SCAN: variant groups pipelined over the two streams (0 = automatic)
     int xvoice_chunk = 0;     // XVOICE_SCAN: frames per time chunk (0 = automatic)
+    uint64_t opt_epoch = 0;   // bumped by every set_option
     int run_graph = 2;        // cproc_cuda_run, small blocks: 0 staged copies, 1 CUDA graph with copy nodes, 2 CUDA graph on pinned staging (zero copy), 3 direct launches on pinned staging
     int xvoice_closed = 1;    // XVOICE_SCAN: zero-state pass in closed form per phase wrap (0: ticked in fp64)
 };
@@ -93,6 +94,7 @@ struct cproc_cuda_batch {
     // small host-buffer runs replayed as one CUDA graph (H2D copies, the kernels, D2H copies): abi.cu
     struct run_graph {
         uint64_t F = 0; uint32_t layout = 0; size_t sz[5] = {0, 0, 0, 0, 0};   // key: in, in2, ctl, out, mix bytes (0 = absent)
+        uint64_t opt_epoch = 0;                    // ctx->opt_epoch at capture: an option change may select other kernels
         int seen = 0;                              // 1: ran once the ordinary way, 2: capture failed, keep the ordinary way
         cudaGraphExec_t exec = nullptr; uint32_t kernels = 0;
         uint8_t *h = nullptr; size_t cap = 0;      // pinned staging, the five regions back to back
