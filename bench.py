@@ -152,7 +152,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config():
@@ -352,7 +352,7 @@ def run_native(args, rank, local_rank, world):
             # raw-output >= 70 % HBM / mixed-down >= 60 % issue targets), outside every timed region above
             from tools import bench_configs
             line["other_configs"] = bench_configs.run_all(st, ctx, peak)
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -366,6 +366,9 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-other-configs", action="store_true", help="skip the secondary configuration rows (N=1)")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: libraries that write to fd 1 (NCCL prints its version
+    # banner there) are sent to stderr, the line goes to the saved descriptor.  The re-exec below inherits fd 1.
+    global _JSON_OUT
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -380,7 +383,18 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", port, os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
         sys.exit(subprocess.call(cmd))
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     run_native(args, rank, local_rank, world)
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
 
 
 if __name__ == "__main__":
