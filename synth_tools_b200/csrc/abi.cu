@@ -451,13 +451,13 @@ int cproc_cuda_run(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
         }
         size_t off[5], total = 0;
         for (int k = 0; k < 5; ++k) { off[k] = total; total += (want[k] + 255) & ~(size_t)255; }
+        if (same && g.seen == 1 && !g.exec && g.cap < total) {   // pinned staging; without it the ordinary path stays
+            if (g.h) cudaFreeHost(g.h);
+            g.h = nullptr; g.cap = 0;
+            if (cudaHostAlloc((void **)&g.h, total, cudaHostAllocDefault) == cudaSuccess) g.cap = total;
+            else { cudaGetLastError(); g.h = nullptr; g.seen = 2; }
+        }
         if (same && g.seen == 1 && !g.exec) {              // second call with this shape: capture
-            if (g.cap < total) {
-                if (g.h) cudaFreeHost(g.h);
-                g.h = nullptr; g.cap = 0;
-                CK(ctx, cudaHostAlloc((void **)&g.h, total, cudaHostAllocDefault));
-                g.cap = total;
-            }
             if (want[0] && (rc = grow(ctx, &b->d_in, &b->cap_in, sz.in))) return rc;
             if (want[1] && (rc = grow(ctx, &b->d_in2, &b->cap_in2, sz.in2))) return rc;
             if (want[2] && (rc = grow(ctx, &b->d_ctl, &b->cap_ctl, sz.ctl))) return rc;
