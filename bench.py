@@ -292,7 +292,11 @@ def run_native(args, rank, local_rank, world):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    e2e_ranks = [dt]
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        e2e_ranks = [float(x.item()) for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * N_CH * E2E_TICKS * e2e_steps / float(t.item())
     ctx.host_free(ring_ptr)
@@ -323,7 +327,7 @@ def run_native(args, rank, local_rank, world):
                     "h2d_bytes_per_step": e2e_rows * N_CH * 4, "d2h_bytes_per_step": N_CH * E2E_TICKS,
                     "sample": "65,536 ch x 1 Mi samples per step per GPU via cproc_cuda_run_stream (pinned ring of 4 x 1 GiB)",
                     "cpu_affinity": numa,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "seconds_per_rank": [round(x, 4) for x in e2e_ranks]},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "k_pdm_v2_ws3<K=2,B=3,FORM=1,P=2,NS=2>",
