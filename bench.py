@@ -37,7 +37,10 @@ CTL_LOG = 12
 ALGO_BYTES_PER_SAMPLE = 1.0          # one uint8 duty per channel-sample
 ALGO_INSTR_PER_SAMPLE = 10.0         # ~10 integer instructions per channel-sample
 E2E_TICKS = 1024 * 1024              # e2e step: 65,536 ch x 1 Mi samples through host buffers
-E2E_CHUNK = 16384                    # 1 GiB slabs, ring of 4 in pinned memory
+# 256 MiB slabs, ring of 4 in pinned memory.  Small on purpose: with 1 GiB slabs (4 GiB of pinned ring per rank) the
+# device-to-host stream of a rank drops from 57 to 46 GB/s as soon as a second rank streams too, and to 11 GB/s per rank
+# at eight (measured; plain concurrent copies into 1 GiB buffers do not show it) -- the DMA working set, not the fabric.
+E2E_CHUNK = int(os.environ.get("E2E_CHUNK_TICKS", "4096"))
 
 
 def measured_peaks():
@@ -325,7 +328,7 @@ def run_native(args, rank, local_rank, world):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s",
                     "h2d_bytes_per_step": e2e_rows * N_CH * 4, "d2h_bytes_per_step": N_CH * E2E_TICKS,
-                    "sample": "65,536 ch x 1 Mi samples per step per GPU via cproc_cuda_run_stream (pinned ring of 4 x 1 GiB)",
+                    "sample": "65,536 ch x 1 Mi samples per step per GPU via cproc_cuda_run_stream (pinned ring of 4 x %d MiB)" % (N_CH * E2E_CHUNK >> 20),
                     "cpu_affinity": numa,
                     "steps": e2e_steps, "seconds_per_rank": [round(x, 4) for x in e2e_ranks]},
             "gpu_launches": launches,
