@@ -413,9 +413,17 @@ int cproc_cuda_run(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     const bool graphable = ctx->run_graph && sz.in + sz.in2 + sz.ctl + sz.out + sz.mix <= (256u << 10) &&
         ((proc == CPROC_CUDA_GRAPH && b->cfg.mode != CPROC_CUDA_GRAPH_SCAN) || proc == CPROC_CUDA_VOICE_BANK || proc == CPROC_CUDA_SQUARE_GRAIN ||
          proc == CPROC_CUDA_WORD_CLOCK || proc == CPROC_CUDA_PWM || (proc == CPROC_CUDA_ONEPOLE && b->cfg.mode != CPROC_CUDA_ONEPOLE_SCAN));
-    // run_graph 3: no graph and no copies -- the kernels work on pinned staging directly (one launch + one sync per
-    // period; nothing is captured, so every processor qualifies)
-    if (ctx->run_graph >= 3 && sz.in + sz.in2 + sz.ctl + sz.out + sz.mix <= (64u << 10)) {
+    // Zero copy (the kernels work on the pinned staging itself) only where the kernel that will run moves its streams
+    // in bulk -- the PLANAR staging kernels (one PCIe round trip per tile) and the voice bank's coalesced stores.  The
+    // scalar fallbacks read a word per tick: over PCIe that is a round trip per tick.  An integer mix bus may be
+    // accumulated with atomics: device memory only.
+    const bool zc_ok = io->layout == CPROC_CUDA_PLANAR && ctx->planar_bulk >= 1 &&
+        (proc == CPROC_CUDA_VOICE_BANK ? io->mix == nullptr
+         : proc == CPROC_CUDA_PWM ? F % 16 == 0
+         : proc == CPROC_CUDA_SQUARE_GRAIN ? (F % 4 == 0 && ctx->grain_bulk != 0)
+         : F % 4 == 0);
+    // run_graph 3: no graph and no copies -- direct launches on the pinned staging (one launch + one sync per period)
+    if (ctx->run_graph >= 3 && graphable && zc_ok && sz.in + sz.in2 + sz.ctl + sz.out + sz.mix <= (64u << 10)) {
         cproc_cuda_batch::run_graph &g = b->rg;
         const size_t want[5] = {io->in ? sz.in : 0, io->in2 ? sz.in2 : 0, io->ctl ? sz.ctl : 0, io->out ? sz.out : 0, io->mix ? sz.mix : 0};
         size_t off[5], total = 0;
@@ -468,7 +476,7 @@ int cproc_cuda_run(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
             bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
             // run_graph 2: no copy nodes at all -- the kernels read and write the pinned staging itself (pinned host memory
             // is device-addressable at the same address under UVA; a block is a few hundred bytes, one PCIe round trip)
-            const bool zc = ctx->run_graph >= 2;
+            const bool zc = ctx->run_graph >= 2 && zc_ok;
             if (ok) {
                 if (want[0]) { if (zc) d.in = g.h + off[0]; else { ok = ok && cudaMemcpyAsync(b->d_in, g.h + off[0], want[0], cudaMemcpyHostToDevice, st) == cudaSuccess; d.in = b->d_in; } }
                 if (want[1]) { if (zc) d.in2 = g.h + off[1]; else { ok = ok && cudaMemcpyAsync(b->d_in2, g.h + off[1], want[1], cudaMemcpyHostToDevice, st) == cudaSuccess; d.in2 = b->d_in2; } }
