@@ -60,3 +60,21 @@ def test_pd_scale_object(tmp_path):
         assert got[(0, v)] == (want_exp, 0), v
         assert got[(1, v)] == (want_lin, 1), v
     assert got[(0, 0)][0] == 20.0 and got[(0, 127)][0] == 20000.0 and got[(1, 127)][0] == 3.0
+
+
+@pytest.mark.parametrize("name,srcs,incs,libs", [
+    ("jack_synth", ["synth_tools_b200/host/jack/jack_synth.c", "tests/c/fakejack/fakejack.c"], ["tests/c/fakejack", "synth_tools_b200/host/jack"], ["-lcproc_cuda"]),
+    ("jack_clock", ["synth_tools_b200/host/jack/jack_clock.c", "tests/c/fakejack/fakejack.c"], ["tests/c/fakejack"], ["-lcproc_cuda"]),
+    ("pd_square_grain", ["synth_tools_b200/host/pd/square_grain_b200~.c", "tests/c/fakepd/fakepd.c"], ["tests/c/fakepd"], ["-lcproc_cuda", "-lm"]),
+])
+def test_host_adapters_build_warning_free(tmp_path, name, srcs, incs, libs):
+    """The JACK / Pd adapters compile with -Wall -Werror and link against the in-tree C-ABI library (running them
+    needs a GPU: tests/test_gpu_dropin.py)."""
+    pkg = os.path.join(ROOT, "synth_tools_b200")
+    if not os.path.exists(os.path.join(pkg, "libcproc_cuda.so")):
+        pytest.skip("libcproc_cuda.so not built")
+    cmd = ["gcc", "-std=gnu99", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include")]
+    for i in incs:
+        cmd += ["-I", os.path.join(ROOT, i)]
+    cmd += [os.path.join(ROOT, s) for s in srcs] + ["-o", str(tmp_path / name), "-L", pkg, "-Wl,-rpath," + pkg] + libs
+    subprocess.check_call(cmd)
