@@ -78,3 +78,65 @@ def test_host_adapters_build_warning_free(tmp_path, name, srcs, incs, libs):
         cmd += ["-I", os.path.join(ROOT, i)]
     cmd += [os.path.join(ROOT, s) for s in srcs] + ["-o", str(tmp_path / name), "-L", pkg, "-Wl,-rpath," + pkg] + libs
     subprocess.check_call(cmd)
+
+
+def test_closed_form_zero_state_response_math():
+    """The derivation behind k_sweep_pre / k_sweep_zsr_closed, restated in numpy fp64: the zero-state
+    response of the SVF to the wrapped phase ramp, advanced per phase WRAP (gaps of k or k+1 ticks from an integer
+    remainder walk, the last stretch from the table of 2^i-tick maps), equals the ticked recurrence on the exact
+    integer input to 1e-9 of full scale -- for increments with none, few and many wraps, powers of two and >= 2^31."""
+    rng = np.random.default_rng(11)
+    L = 544
+    nlev = L.bit_length()
+
+    def seg_then(x, y):                      # x ticks, then y ticks: (A, P, Q, m)
+        return (y[0] @ x[0], y[0] @ x[1] + y[1], y[0] @ x[2] + x[3] * y[1] + y[2], x[3] + y[3])
+
+    for inc in [0, 1, 3, 1 << 20, (1 << 24) + 1, 39370533, 715827883, 0x55555556, 1 << 31, (1 << 31) + 5, 0xFFFFFFFF, 1 << 28, 3 << 28]:
+        f, q = float(np.float32(rng.uniform(0.01, 0.3))), float(np.float32(rng.uniform(0.5, 2.0)))
+        A = np.array([[1.0, f], [-f, 1.0 - f * q - f * f]]); b = np.array([0.0, f])
+        lev = (A, b, np.zeros(2), 1.0)
+        ident = (np.eye(2), np.zeros(2), np.zeros(2), 0.0)
+        table, sl, sk = [], ident, ident
+        k = rho = 0
+        if inc:
+            k = 0xFFFFFFFF // inc; rho = (-k * inc) & 0xFFFFFFFF
+            if rho == inc:
+                k += 1; rho = 0
+        for l in range(nlev):
+            table.append(lev)
+            if (L >> l) & 1:
+                sl = seg_then(sl, lev)
+            if inc and k < L and (k >> l) & 1:
+                sk = seg_then(sk, lev)
+            lev = seg_then(lev, lev)
+        for ph in [0, 0x7FFFFFF0, 0x80000000, int(rng.integers(0, 2**32)), 0xFFFFFFFF]:
+            # ticked reference on the exact integer input
+            s = np.zeros(2); p = ph
+            for _ in range(L):
+                x = float(p - (1 << 32) if p >= (1 << 31) else p)
+                lp = s[0] + f * s[1]; s = np.array([lp, s[1] + f * (x - q * s[1] - lp)]); p = (p + inc) & 0xFFFFFFFF
+            # closed form
+            u0 = ph ^ 0x80000000
+            W = (u0 + (L - 1) * inc) >> 32
+            y = np.zeros(2)
+            if W:
+                at = (~u0 & 0xFFFFFFFF) // inc + 1
+                if W > 1:
+                    r = (u0 + at * inc) & 0xFFFFFFFF
+                    for j in range(1, W):
+                        y = sk[0] @ y + j * sk[1]; at += k
+                        if r >= rho:
+                            r -= rho
+                        else:
+                            r = r - rho + inc; at += 1
+                            y = A @ y + j * b
+                e, l = L - at, 0
+                assert e >= 1
+                while e:
+                    if e & 1:
+                        y = table[l][0] @ y + W * table[l][1]
+                    e >>= 1; l += 1
+            x0 = float(ph - (1 << 32) if ph >= (1 << 31) else ph)
+            got = sl[1] * x0 + sl[2] * inc - 4294967296.0 * y
+            assert np.abs(got - s).max() <= 1e-9 * 2.0**31 * max(1.0, np.abs(s).max() / 2.0**31), (inc, ph, got, s)
