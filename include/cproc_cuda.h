@@ -355,7 +355,25 @@ int  cproc_cuda_memset(cproc_cuda_ctx *ctx, void *dev, int value, size_t bytes);
 /* CUDA-event stopwatch on the context stream. */
 int  cproc_cuda_timer_start(cproc_cuda_ctx *ctx);
 int  cproc_cuda_timer_stop(cproc_cuda_ctx *ctx, float *elapsed_ms);
-/* Tuning knob (block size etc.) by name; unknown names return EINVAL. */
+/* Tuning knob by name; unknown names and out-of-range values return EINVAL.  Every setting gives
+ * the same results (the tests sweep them); the defaults are the measured best on B200.
+ *   planar_bulk      0..2 [2]  PLANAR pdm / pwm / one-pole / word-clock / generated-graph streams: scalar
+ *                              kernels, per-lane cp.async.bulk staging, tensor-TMA staging
+ *   grain_bulk       0..5 [5]  PLANAR square_grain: register transpose, bulk-copy tile shapes 1..4, tensor TMA
+ *   grain_vec4, graph_vec4 0/1 [1]  INTERLEAVED: four instances per thread (128-bit accesses)
+ *   grain_mix2       0..2 [2]  square_grain mix kernel generation
+ *   graph_jit        0/1  [1]  generated graphs compiled with NVRTC (0: table-driven kernel, <= 16 nodes)
+ *   pdm_ws           0..3 [3]  PDM v2: thread per bank, warp-specialised producer/consumer (1, 2), + dynamic
+ *                              (group, time-slice) schedule (3)
+ *   pdm_ctas_per_sm [4], pdm_slice_batches [64], pdm_chains 1/2/4 [2], pdm_slots 2/4 [2], pdm_form 0..2 [1],
+ *   pdm_prng_fma 0/1 [0]       variants of the warp-specialised PDM v2 kernels
+ *   pdm_planar_bulk  0..2 [2]  PDM v2 PLANAR duty rows: direct stores, per-lane bulk rows, tensor-TMA boxes
+ *   pdm_v1_chains    1/2  [2]  PDM v1: PRNG chains per lane
+ *   pdm_block, pdm_tpb, pdm_stage, pdm_persist, pdm_warps_per_smsp   older PDM kernel generations
+ *   xvoice_chunk [0 = auto], xvoice_groups 0..8 [0 = one group], xvoice_closed 0/1 [1]
+ *                              XVOICE_SCAN: frames per time chunk, variant groups, closed-form zero-state pass
+ *   run_graph        0..3 [2]  cproc_cuda_run on small host buffers: staged copies, CUDA graph with copy nodes,
+ *                              CUDA graph on pinned staging, direct launches on pinned staging */
 int  cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value);
 
 #ifdef __cplusplus
