@@ -363,13 +363,13 @@ int  cproc_cuda_timer_stop(cproc_cuda_ctx *ctx, float *elapsed_ms);
  *   grain_vec4, graph_vec4 0/1 [1]  INTERLEAVED: four instances per thread (128-bit accesses)
  *   grain_mix2       0..2 [2]  square_grain mix kernel generation
  *   graph_jit        0/1  [1]  generated graphs compiled with NVRTC (0: table-driven kernel, <= 16 nodes)
- *   pdm_ws           0..3 [3]  PDM v2: thread per bank, warp-specialised producer/consumer (1, 2), + dynamic
- *                              (group, time-slice) schedule (3)
- *   pdm_ctas_per_sm [4], pdm_slice_batches [64], pdm_chains 1/2/4 [2], pdm_slots 2/4 [2], pdm_form 0..2 [1],
- *   pdm_prng_fma 0/1 [0]       variants of the warp-specialised PDM v2 kernels
- *   pdm_planar_bulk  0..2 [2]  PDM v2 PLANAR duty rows: direct stores, per-lane bulk rows, tensor-TMA boxes
+ *   pdm_ws           0/1  [1]  PDM v2: 1 = producer / consumer kernel under the dynamic (group, time-slice) schedule,
+ *                              0 = plain thread-per-bank / thread-per-channel kernels
+ *   pdm_tlog         6/7  [7]  PDM v2: log2 of the ticks per producer -> consumer hand-off
+ *   pdm_ctas_per_sm [4], pdm_slice_batches [64: work items of 64 x 64 ticks]   PDM v2 dynamic schedule
+ *   pdm_planar_bulk  0/2  [2]  PDM v2 PLANAR duty rows: scattered 16-byte stores, tensor-TMA boxes
  *   pdm_v1_chains    1/2  [2]  PDM v1: PRNG chains per lane
- *   pdm_block, pdm_tpb, pdm_stage, pdm_persist, pdm_warps_per_smsp   older PDM kernel generations
+ *   pdm_block, pdm_tpb [1: thread per bank when bank_size <= 4], pdm_persist, pdm_warps_per_smsp   plain PDM kernels, PDM v1 schedule
  *   xvoice_chunk [0 = auto], xvoice_groups 0..8 [0 = one group], xvoice_closed 0/1 [1]
  *                              XVOICE_SCAN: frames per time chunk, variant groups, closed-form zero-state pass
  *   run_graph        0..3 [2]  cproc_cuda_run on small host buffers: staged copies, CUDA graph with copy nodes,

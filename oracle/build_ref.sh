@@ -12,8 +12,14 @@ if [ ! -d "$REF" ]; then
     exit 0
 fi
 mkdir -p "$HERE/_ref"
+# Two builds of the same sources: libref.so with -O2 (the primary CPU baseline: the reference's own optimisation flags live in
+# uc_tools' build.sh, not in the tree) and libref_o3.so with -O3 for the x86-64-v3 level (AVX2, BMI2, FMA).  BASELINE.md 3 asks
+# for -march=native, but the library is built HERE (the reference sources do not travel to the GPU box) and must run on the
+# box's host CPU, whatever it is: v3 is what every host of a B200 has.
+build_one() {
+OUT="$1"; OPT="$2"
 OBJ="$(mktemp -d /tmp/cproc_ref_obj.XXXXXX)"
-CFLAGS="-std=gnu99 -O2 -fwrapv -ffp-contract=off -fPIC -fopenmp -w"
+CFLAGS="-std=gnu99 $OPT -fwrapv -ffp-contract=off -fPIC -fopenmp -w"
 # (1) generic/cproc.h + linux/test_cproc.c (whole file; main renamed)
 gcc $CFLAGS -I"$HERE/shim" -I"$REF/generic" -c "$HERE/ref/ref_cproc.c" -o "$OBJ/ref_cproc.o"
 gcc $CFLAGS -I"$HERE/shim" -I"$REF/generic" -Dmain=ref_test_cproc_main -c "$REF/linux/test_cproc.c" -o "$OBJ/test_cproc.o"
@@ -34,6 +40,10 @@ gcc $CFLAGS -fno-semantic-interposition -I"$HERE/shim/stm32" -I"$REF/stm32f103" 
 # (7) stm32f103/mod_pdm.c:159-175 (pwm_update and the globals it works on)
 ( echo '#include <stdint.h>'; sed -n 159,175p "$REF/stm32f103/mod_pdm.c"; cat "$HERE/ref/ref_pwm_tail.c" ) \
   | gcc $CFLAGS -Dcontrol_div_count=ref_pwm_control_div_count -x c -c - -o "$OBJ/ref_pwm.o"   # (:165 also defines the v1 divider; mod_pdm_pwm.c has its own)
-gcc -shared -fopenmp -o "$HERE/_ref/libref.so" "$OBJ/ref_cproc.o" "$OBJ/test_cproc.o" "$OBJ/ref_pdm.o" "$OBJ/ref_synth.o" "$OBJ/ref_grain.o" \
+gcc -shared -fopenmp -o "$HERE/_ref/$OUT" "$OBJ/ref_cproc.o" "$OBJ/test_cproc.o" "$OBJ/ref_pdm.o" "$OBJ/ref_synth.o" "$OBJ/ref_grain.o" \
     "$OBJ/ref_v2_isr.o" "$OBJ/ref_clock.o" "$OBJ/ref_pwm.o" -lm
-echo "built $HERE/_ref/libref.so"
+rm -rf "$OBJ"
+echo "built $HERE/_ref/$OUT ($OPT)"
+}
+build_one libref.so "-O2"
+build_one libref_o3.so "-O3 -march=x86-64-v3"

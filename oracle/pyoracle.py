@@ -13,6 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libref.so")
+REF_O3_SO = os.path.join(HERE, "_ref", "libref_o3.so")     # the same sources, -O3 -march=x86-64-v3 (build_ref.sh)
 
 u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
 i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -66,7 +67,7 @@ def build(force=False):
     if os.path.isdir(os.environ.get("REF", "/root/reference")):
         recipe = [os.path.join(HERE, "build_ref.sh")] + [os.path.join(d, f) for d in (os.path.join(HERE, "ref"), os.path.join(HERE, "shim"), os.path.join(HERE, "shim", "stm32"))
                                                          for f in os.listdir(d) if os.path.isfile(os.path.join(d, f))]
-        if force or not os.path.exists(REF_SO) or os.path.getmtime(REF_SO) < max(os.path.getmtime(f) for f in recipe):
+        if force or not os.path.exists(REF_SO) or not os.path.exists(REF_O3_SO) or os.path.getmtime(REF_O3_SO) < max(os.path.getmtime(f) for f in recipe):
             subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
 
 
@@ -126,10 +127,12 @@ class _Lib:
         return out
 
     def pdm_v2_run(self, chan, order, N, bank_size, prng, dither_ext, dither_mask, count,
-                   ctl_div_log, out_shift, setpoints, F):
+                   ctl_div_log, out_shift, setpoints, F, out=None):
         """chan [N][5+order] u32 (updated in place); prng [n_banks] u32 in place;
-        returns (duty [N][F] u8, new_count)."""
-        duty = np.zeros((N, F), np.uint8)
+        returns (duty [N][F] u8, new_count).  out: a preallocated (and touched) duty buffer -- timed loops pass one, so
+        that neither arm of a comparison pays for allocating and first-touching its output."""
+        duty = np.zeros((N, F), np.uint8) if out is None else out
+        assert duty.dtype == np.uint8 and duty.size >= N * F and duty.flags["C_CONTIGUOUS"]
         cnt = C.c_uint32(count)
         f = self._fn("pdm_v2_run", None, [VP, C.c_uint32, C.c_uint64, C.c_uint32, VP, VP, C.c_uint32,
                                           C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, VP, C.c_uint64, VP])

@@ -69,9 +69,12 @@ int cproc_cuda_open(int device, void *stream, cproc_cuda_ctx **out) {
         if ((rc = cproc_check(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate"))) { g_last_err = ctx->err; delete ctx; return rc; }
         ctx->own_stream = true;
     }
-    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-    cudaEventCreate(&ctx->ev0);
-    cudaEventCreate(&ctx->ev1);
+    if ((rc = cproc_check(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate(copy)")) ||
+        (rc = cproc_check(ctx, cudaEventCreate(&ctx->ev0), "cudaEventCreate")) || (rc = cproc_check(ctx, cudaEventCreate(&ctx->ev1), "cudaEventCreate"))) {
+        g_last_err = ctx->err;
+        cproc_cuda_close(ctx);
+        return rc;
+    }
     *out = ctx;
     return 0;
 }
@@ -106,13 +109,12 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     if (!strcmp(name, "pdm_block")) { if (value < 32 || value > 128 || (value & 31)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_block must be 32, 64, 96 or 128"); ctx->pdm_block = (int)value; }
     else if (!strcmp(name, "pdm_tpb")) ctx->pdm_tpb = value != 0;
     else if (!strcmp(name, "pdm_stage")) ctx->pdm_stage = value != 0;
-    else if (!strcmp(name, "pdm_ws")) { if (value < 0 || value > 3) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_ws must be 0..3"); ctx->pdm_ws = (int)value; }
+    else if (!strcmp(name, "pdm_ws")) ctx->pdm_ws = value != 0;
+    else if (!strcmp(name, "pdm_tlog")) { if (value < 6 || value > 7) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_tlog must be 6 or 7"); ctx->pdm_tlog = (int)value; }
     else if (!strcmp(name, "pdm_v1_chains")) { if (value != 1 && value != 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_v1_chains must be 1 or 2"); ctx->pdm_v1_chains = (int)value; }
-    else if (!strcmp(name, "pdm_planar_bulk")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_planar_bulk must be 0..2"); ctx->pdm_planar_bulk = (int)value; }
-    else if (!strcmp(name, "pdm_prng_fma")) ctx->pdm_prng_fma = value != 0;
+    else if (!strcmp(name, "pdm_planar_bulk")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_planar_bulk must be 0..2"); ctx->pdm_planar_bulk = value ? 2 : 0; }
     else if (!strcmp(name, "pdm_ctas_per_sm")) { if (value < 1 || value > 8) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_ctas_per_sm must be 1..8"); ctx->pdm_ctas_per_sm = (int)value; }
     else if (!strcmp(name, "pdm_slice_batches")) { if (value < 2 || value > 65536) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_slice_batches must be 2..65536"); ctx->pdm_slice_batches = (int)value; }
-    else if (!strcmp(name, "pdm_form")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_form must be 0..2"); ctx->pdm_form = (int)value; }
     else if (!strcmp(name, "grain_blocks_per_sm")) { if (value < 1 || value > 16) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "grain_blocks_per_sm must be 1..16"); ctx->grain_blocks_per_sm = (int)value; }
     else if (!strcmp(name, "planar_bulk")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "planar_bulk must be 0..2"); ctx->planar_bulk = (int)value; }
     else if (!strcmp(name, "graph_vec4")) ctx->graph_vec4 = value != 0;
@@ -124,8 +126,6 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     else if (!strcmp(name, "xvoice_closed")) ctx->xvoice_closed = value ? 1 : 0;
     else if (!strcmp(name, "run_graph")) { if (value < 0 || value > 3) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "run_graph must be 0..3"); ctx->run_graph = (int)value; }
     else if (!strcmp(name, "xvoice_groups")) { if (value < 0 || value > 8) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice_groups must be 0..8"); ctx->xvoice_groups = (int)value; }
-    else if (!strcmp(name, "pdm_slots")) { if (value != 2 && value != 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_slots must be 2 or 4"); ctx->pdm_slots = (int)value; }
-    else if (!strcmp(name, "pdm_chains")) { if (value != 1 && value != 2 && value != 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_chains must be 1, 2 or 4"); ctx->pdm_chains = (int)value; }
     else if (!strcmp(name, "pdm_persist")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_persist must be 0 (never), 1 (auto) or 2 (always)"); ctx->pdm_persist = (int)value; }
     else if (!strcmp(name, "pdm_warps_per_smsp")) { if (value < 1 || value > 4) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_warps_per_smsp must be 1..4"); ctx->pdm_warps_per_smsp = (int)value; }
     else return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "set_option: unknown option '%s'", name);
@@ -234,7 +234,7 @@ int cproc_cuda_free(cproc_cuda_batch *b) {
     if (!b) return 0;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    void *ptrs[] = { b->d_state, b->d_param, b->d_prng, b->d_nodes, b->d_in, b->d_in2, b->d_ctl, b->d_out, b->d_out2, b->d_mix, b->d_flags, b->d_scratch, b->d_aux };
+    void *ptrs[] = { b->d_state, b->d_param, b->d_prng, b->d_prng2, b->d_prng_g, b->d_nodes, b->d_in, b->d_in2, b->d_ctl, b->d_out, b->d_out2, b->d_mix, b->d_flags, b->d_scratch, b->d_aux };
     for (void *q : ptrs) if (q) cudaFree(q);
     for (cproc_graph_jit &j : b->jit) if (j.lib) cudaLibraryUnload(j.lib);
     if (b->rg.exec) cudaGraphExecDestroy(b->rg.exec);

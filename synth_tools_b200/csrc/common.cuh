@@ -22,20 +22,17 @@ struct cproc_cuda_ctx {
     int pdm_block = 64;       // threads per block of the PDM kernels
     int pdm_tpb = 1;          // 1: thread-per-bank when bank_size <= 4, 0: thread-per-channel
     int pdm_stage = 1;        // 1: smem-staged full-line stores for PLANAR
-    int pdm_ws = 3;           // 1: warp-specialised v2 kernel (PRNG producer warp + channel consumer warps); 2: second generation; 3: + dynamic (group, slice) schedule
+    int pdm_ws = 1;           // PDM v2: 1 = producer / consumer kernel under the dynamic (group, slice) schedule (k_pdm_v2_ws4), 0 = plain thread-per-bank / per-channel kernels
+    int pdm_tlog = 7;         // k_pdm_v2_ws4: log2 of the dither batch (ticks per FULL / EMPTY hand-off), 6 or 7
     int pdm_v1_chains = 2;    // v1 thread-per-bank TILED kernels: PRNG chains per lane (1 or 2)
-    int pdm_prng_fma = 0;     // ws3 producer: 1 = xorshift shifts as IMAD / IMAD.HI (FMA pipe) instead of SHF (ALU pipe); measured slower (1.54 vs 1.50 ms: the producer chain is latency bound)
-    int pdm_planar_bulk = 2;  // ws3: PLANAR duty rows staged in shared memory: 1 per-lane bulk stores, 2 tensor-TMA boxes
-    int pdm_ctas_per_sm = 4;  // ws3: persistent blocks per SM
-    int pdm_slice_batches = 64;   // ws3: dither batches (64 ticks each) per work item
-    uint32_t *d_work = nullptr;   // ws3: work counter + exit counter
-    int pdm_form = 1;         // ws2: order-2 tick formulation (see v2_tick_q24)
-    uint32_t *d_sm_rank = nullptr;   // per-SM block arrival counters (ws2 producer placement)
-    int pdm_slots = 2;        // ws2: dither ring slots (2 or 4)
-    int pdm_chains = 2;       // ws2: independent PRNG chains per producer lane (1, 2 or 4)
-    uint32_t *d_jump[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // xorshift32 jump LUTs per chain count
+    int pdm_planar_bulk = 2;  // k_pdm_v2_ws4: PLANAR duty rows staged in shared memory and stored as tensor-TMA boxes (0: scattered 16-byte stores)
+    int pdm_ctas_per_sm = 4;  // k_pdm_v2_ws4: persistent blocks per SM
+    int pdm_slice_batches = 64;   // k_pdm_v2_ws4: ticks per work item, in units of 64 ticks
+    uint32_t *d_work = nullptr;   // k_pdm_v2_ws4: work counter + exit counter
+    uint32_t *d_sm_rank = nullptr;   // per-SM block arrival counters (producer placement)
+    uint32_t *d_jump[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // xorshift32 jump LUTs M^(T/2) per batch length 2^(6+i)
     uint32_t *d_jump16 = nullptr;   // M^16 (v1 two-chain PRNG)
-    int pdm_persist = 1;      // 1: persistent McNaughton-scheduled kernels when thread == bank
+    int pdm_persist = 1;      // v1: persistent McNaughton-scheduled kernel when thread == bank (0 never, 1 auto, 2 always)
     int pdm_warps_per_smsp = 1;
     int n_sm = CPROC_N_SM;
     int voice_block = 256;
@@ -77,7 +74,9 @@ struct cproc_cuda_batch {
     uint32_t state_words = 0, param_words = 0;
     uint32_t *d_state = nullptr;            // [state_words][npad]
     uint32_t *d_param = nullptr;            // [param_words][npad]
-    uint32_t *d_prng = nullptr;             // [n_banks]
+    uint32_t *d_prng = nullptr;             // [n_banks] dither generator state
+    uint32_t *d_prng2 = nullptr;            // [n_banks] the other half of the double buffer (a launch reads one, writes the other)
+    uint32_t *d_prng_g = nullptr;           // [groups][32] generator state between the time slices of a group (k_pdm_v2_ws4)
     cproc_cuda_node *d_nodes = nullptr;
     uint32_t count = 0;                     // control_div_count
     // staging for host-buffer runs (grown on demand)

@@ -37,7 +37,7 @@ def test_c2_pdm_v2_full_launch_shape(st, ctx, oracle):
     """65,536 channels x 65,536 ticks (one launch of the headline bench), banks of 3, a setpoint
     row every 4096 ticks.  (1) the oracle on banks 0..31, 10,000..10,031 and the last 32 banks
     (with the ragged last bank) reproduces their duty bytes, state and PRNG words exactly;
-    (2) the dynamic-schedule kernel, the static one and the persistent thread-per-bank kernel
+    (2) k_pdm_v2_ws4 with 128-tick and with 64-tick dither batches and the plain thread-per-bank kernel
     write identical slabs (CRC of all 4 GiB); (3) mean duty tracks the glided setpoint."""
     N, F, L = 65536, 65536, 12
     nb = (N + 2) // 3
@@ -49,7 +49,7 @@ def test_c2_pdm_v2_full_launch_shape(st, ctx, oracle):
     host = np.zeros(N * F, np.uint8)
     crcs = {}
     keep = None
-    for name, opts in (("ws3", {"pdm_ws": 3}), ("ws2", {"pdm_ws": 2}), ("persist", {"pdm_ws": 0, "pdm_persist": 2})):
+    for name, opts in (("t128", {"pdm_ws": 1, "pdm_tlog": 7}), ("t64", {"pdm_ws": 1, "pdm_tlog": 6}), ("plain", {"pdm_ws": 0})):
         for k, v in opts.items():
             ctx.set_option(k, v)
         b = ctx.batch(st.PDM_V2, N, order=2, bank_size=3, ctl_div_log=L, layout=st.TILED)
@@ -58,11 +58,11 @@ def test_c2_pdm_v2_full_launch_shape(st, ctx, oracle):
         ctx.d2h(host, d_out)
         state, (prng1, cnt) = b.download_state(), b.download_bank()
         crcs[name] = (zlib.crc32(host), zlib.crc32(state.tobytes()), zlib.crc32(prng1.tobytes()), cnt)
-        if name == "ws3":
+        if name == "t128":
             keep = (host.reshape(F // 16, N, 16).copy(), state, prng1)
         b.free()
-        ctx.set_option("pdm_ws", 3); ctx.set_option("pdm_persist", 1)
-    assert crcs["ws3"] == crcs["ws2"] == crcs["persist"], crcs
+        ctx.set_option("pdm_ws", 1); ctx.set_option("pdm_tlog", 7)
+    assert crcs["t128"] == crcs["t64"] == crcs["plain"], crcs
     tiled, state, prng1 = keep
     for b0 in (0, 10000, nb - 32):
         c0, c1 = 3 * b0, min(N, 3 * (b0 + 32))

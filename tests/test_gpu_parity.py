@@ -53,7 +53,7 @@ def _v2_case(st, ctx, oracle, order, bank, N, F, layout, count0, use_setp, use_d
         if split is None:
             out = np.zeros(N * F, np.uint8)
             b.run(F, in2=dext, ctl=sp, out=out)
-            got = tiled16_to_planar(out, N, F) if layout == st.TILED else out.reshape(N, F)
+            got = tiled16_to_planar(out, N, F) if layout == st.TILED else out.reshape(F, N).T if layout == st.INTERLEAVED else out.reshape(N, F)
         else:
             # the same render in several calls must continue seamlessly (checkpoint semantics)
             assert dext is None
@@ -79,110 +79,101 @@ def _v2_case(st, ctx, oracle, order, bank, N, F, layout, count0, use_setp, use_d
             assert np.array_equal(p, pa)
     finally:
         b.free()
-        ctx.set_option("pdm_tpb", 1)
-        ctx.set_option("pdm_block", 64)
-        ctx.set_option("pdm_persist", 1)
-        ctx.set_option("pdm_warps_per_smsp", 1)
-        ctx.set_option("pdm_ws", 3)
-        ctx.set_option("pdm_form", 1)
-        ctx.set_option("pdm_chains", 2)
-        ctx.set_option("pdm_slots", 2)
-        ctx.set_option("pdm_ctas_per_sm", 4)
-        ctx.set_option("pdm_slice_batches", 64)
-        ctx.set_option("pdm_planar_bulk", 2)
+        for k, v in V2_DEFAULTS.items():
+            ctx.set_option(k, v)
+
+
+V2_DEFAULTS = {"pdm_tpb": 1, "pdm_block": 64, "pdm_ws": 1, "pdm_tlog": 7, "pdm_ctas_per_sm": 4,
+               "pdm_slice_batches": 64, "pdm_planar_bulk": 2}
 
 
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
 @pytest.mark.parametrize("bank", [1, 2, 3, 4, 7])
 def test_pdm_v2_orders_banks(st, ctx, oracle, order, bank):
+    """F not a whole dither batch: the plain thread-per-bank / thread-per-channel kernels."""
+    _v2_case(st, ctx, oracle, order, bank, N=203, F=48, layout=st.TILED, count0=0, use_setp=True, use_dext=False, ctl=4)
     _v2_case(st, ctx, oracle, order, bank, N=203, F=512, layout=st.TILED, count0=0, use_setp=True, use_dext=False)
 
 
 @pytest.mark.parametrize("layout", ["PLANAR", "TILED"])
-@pytest.mark.parametrize("tpb,persist,ws", [(0, 0, 0), (1, 0, 0), (1, 2, 0), (1, 1, 0), (1, 1, 1)])
+@pytest.mark.parametrize("tpb,ws", [(0, 0), (1, 0), (1, 1)])
 @pytest.mark.parametrize("blk", [32, 128])
-def test_pdm_v2_layouts_and_mappings(st, ctx, oracle, layout, tpb, persist, ws, blk):
+def test_pdm_v2_layouts_and_mappings(st, ctx, oracle, layout, tpb, ws, blk):
     _v2_case(st, ctx, oracle, 2, 3, N=1000, F=1024, layout=getattr(st, layout), count0=16, use_setp=True,
-             use_dext=False, opts={"pdm_tpb": tpb, "pdm_block": blk, "pdm_persist": persist, "pdm_ws": ws})
+             use_dext=False, opts={"pdm_tpb": tpb, "pdm_block": blk, "pdm_ws": ws})
 
 
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
-@pytest.mark.parametrize("bank", [1, 2, 3, 4])
-def test_pdm_v2_warp_specialised(st, ctx, oracle, order, bank):
-    """Producer/consumer kernel: ragged channel count, several dither batches,
-    control boundaries inside a batch."""
-    _v2_case(st, ctx, oracle, order, bank, N=3001, F=448, layout=st.TILED, count0=16, use_setp=True, use_dext=False,
-             ctl=5, opts={"pdm_ws": 1})
-
-
-@pytest.mark.parametrize("form", [0, 1, 2])
-@pytest.mark.parametrize("chains", [1, 2, 4])
-@pytest.mark.parametrize("slots", [2, 4])
-def test_pdm_v2_ws2_variants(st, ctx, oracle, form, chains, slots):
-    """Second-generation producer/consumer kernel: every tick formulation, PRNG chain
-    count (jump tables) and ring depth; a control boundary on every batch start."""
-    _v2_case(st, ctx, oracle, 2, 3, N=3001, F=64 * 13, layout=st.TILED, count0=0, use_setp=True, use_dext=False,
-             ctl=6, opts={"pdm_ws": 2, "pdm_form": form, "pdm_chains": chains, "pdm_slots": slots})
-
-
-@pytest.mark.parametrize("order", [1, 2, 3, 4])
-@pytest.mark.parametrize("bank", [1, 2, 3, 4])
+@pytest.mark.parametrize("bank", [1, 2, 3, 4, 5, 7, 33])
 @pytest.mark.parametrize("layout", ["PLANAR", "TILED"])
-def test_pdm_v2_ws2_orders_banks(st, ctx, oracle, order, bank, layout):
-    """ws2 for every order / bank size, ragged channel count, counter starting inside a
-    control period (count0 = 3 batches into a period of 4 batches)."""
-    _v2_case(st, ctx, oracle, order, bank, N=2999, F=64 * 11, layout=getattr(st, layout), count0=192, use_setp=True,
-             use_dext=False, ctl=8, opts={"pdm_ws": 2})
+def test_pdm_v2_ws4_orders_banks(st, ctx, oracle, order, bank, layout):
+    """k_pdm_v2_ws4 for every order and bank sizes on both sides of the aligned / unaligned split (banks of 1..4 are a
+    consumer warp each; larger banks straddle groups of 128 channels), ragged channel count, the counter starting
+    inside a control period (3 batches of 64 into a period of 4)."""
+    _v2_case(st, ctx, oracle, order, bank, N=2999, F=64 * 12, layout=getattr(st, layout), count0=192, use_setp=True,
+             use_dext=False, ctl=8, opts={"pdm_ctas_per_sm": 1, "pdm_slice_batches": 4})
 
 
-def test_pdm_v2_ws2_split_runs(st, ctx, oracle):
-    """Consecutive ws2 launches continue seamlessly (state, PRNG, control counter)."""
-    _v2_case(st, ctx, oracle, 2, 3, N=96 * 5 + 7, F=64 * 20, layout=st.TILED, count0=0, use_setp=True, use_dext=False,
-             ctl=7, split=[64 * 3, 64, 64 * 10, 64 * 6], opts={"pdm_ws": 2})
-
-
-@pytest.mark.parametrize("form", [0, 1, 2])
-@pytest.mark.parametrize("chains", [1, 2, 4])
+@pytest.mark.parametrize("tlog", [6, 7])
 @pytest.mark.parametrize("layout", ["PLANAR", "TILED"])
-def test_pdm_v2_ws3_dynamic_schedule(st, ctx, oracle, form, chains, layout):
-    """Dynamic (group, slice) schedule: more 32-bank groups (151) than persistent blocks
-    (148 x 1), slices of 2 dither batches with a ragged last slice (9 batches), the control
-    counter starting one batch into a 4-batch period, setpoint rows latched inside slices."""
-    _v2_case(st, ctx, oracle, 2, 3, N=96 * 150 + 5, F=64 * 9, layout=getattr(st, layout), count0=64, use_setp=True,
-             use_dext=False, ctl=8, opts={"pdm_ws": 3, "pdm_form": form, "pdm_chains": chains, "pdm_ctas_per_sm": 1,
-                                          "pdm_slice_batches": 2})
+@pytest.mark.parametrize("order,bank", [(2, 3), (3, 2), (4, 9), (1, 1)])
+def test_pdm_v2_ws4_batches_and_schedule(st, ctx, oracle, tlog, layout, order, bank):
+    """Both batch lengths; dynamic (group, slice) schedule: more groups than persistent blocks (148 x 1), slices of 512
+    ticks with a ragged last slice, setpoint rows latched inside slices, the counter starting inside a control period."""
+    _v2_case(st, ctx, oracle, order, bank, N=32 * bank * 150 + 5 if bank <= 4 else 128 * 150 + 5, F=256 * 9, layout=getattr(st, layout), count0=256,
+             use_setp=True, use_dext=False, ctl=9, opts={"pdm_tlog": tlog, "pdm_ctas_per_sm": 1, "pdm_slice_batches": 8})
+
+
+@pytest.mark.parametrize("mask", [0x3FF, 0xFFFF, 0x00FFFFFF, 0, 0x01000001])
+def test_pdm_v2_dither_masks(st, ctx, oracle, mask):
+    """Dither below bit 24 takes the one-LOP3 quantiser step; a mask that reaches the output byte takes the literal form."""
+    N, F, bank = 777, 64 * 6, 3
+    chan0 = rng.integers(0, 2**32, (N, 7), dtype=np.uint32)
+    prng0 = rng.integers(1, 2**32, (N + bank - 1) // bank, dtype=np.uint32)
+    sp = po.pdm_setpoints(N, F // 64 + 2)
+    ca, pa = chan0.copy(), prng0.copy()
+    want, _ = oracle.pdm_v2_run(ca, 2, N, bank, pa, None, mask, 0, 6, 24, sp, F)
+    b = ctx.batch(st.PDM_V2, N, order=2, bank_size=bank, ctl_div_log=6, out_shift=24, dither_mask=mask, layout=st.PLANAR)
+    b.upload_state(chan0); b.upload_bank(prng0, 0)
+    out = np.zeros((N, F), np.uint8)
+    b.run(F, ctl=sp, out=out)
+    assert np.array_equal(out, want) and np.array_equal(b.download_state(), ca) and np.array_equal(b.download_bank()[0], pa)
+    b.free()
 
 
 @pytest.mark.parametrize("ctas,slice_b,F", [(4, 2, 64 * 8), (4, 3, 64 * 8), (2, 4, 64 * 8), (4, 64, 64 * 128)])
-def test_pdm_v2_ws3_c2_shape(st, ctx, oracle, ctas, slice_b, F):
+def test_pdm_v2_ws4_c2_shape(st, ctx, oracle, ctas, slice_b, F):
     """The C2 channel count (65,536 channels = 683 groups for 148 x ctas blocks)."""
     _v2_case(st, ctx, oracle, 2, 3, N=65536, F=F, layout=st.TILED, count0=0, use_setp=True, use_dext=False, ctl=7,
-             opts={"pdm_ws": 3, "pdm_ctas_per_sm": ctas, "pdm_slice_batches": slice_b})
+             opts={"pdm_ctas_per_sm": ctas, "pdm_slice_batches": slice_b})
 
 
-@pytest.mark.parametrize("slice_b,F,bulk", [(4, 64 * 9, 1), (8, 64 * 21, 1), (4, 64 * 16, 1), (4, 64 * 9, 0),
-                                             (4, 64 * 16, 2), (8, 64 * 22, 2), (4, 64 * 10, 2), (12, 64 * 38, 2), (4, 64 * 9, 2)])
-def test_pdm_v2_ws3_planar_rows(st, ctx, oracle, slice_b, F, bulk):
-    """PLANAR duty rows of the dynamic-schedule kernel: per-lane row stage and bulk stores (1: 256-tick stages, a
-    ragged last stage per slice), tensor-TMA boxes of 128 ticks x 32 channels (2: whole boxes only, F % 128 == 0,
-    else it falls back to 1), and with the stage off (0); ragged channel count (rows clipped by the tensor map)."""
+@pytest.mark.parametrize("slice_b,F,bulk", [(4, 64 * 9, 2), (4, 64 * 16, 2), (8, 64 * 22, 2), (4, 64 * 10, 2), (12, 64 * 38, 2),
+                                             (3, 64 * 16, 2), (4, 64 * 16, 0)])
+def test_pdm_v2_ws4_planar_rows(st, ctx, oracle, slice_b, F, bulk):
+    """PLANAR duty rows: tensor-TMA boxes of 128 ticks x 32 channels (whole boxes only: F % 128 == 0, else scattered
+    16-byte stores), odd slice lengths rounded to whole boxes, ragged channel count (rows clipped by the tensor map)."""
     _v2_case(st, ctx, oracle, 2, 3, N=96 * 150 + 5, F=F, layout=st.PLANAR, count0=64, use_setp=True, use_dext=False, ctl=8,
-             opts={"pdm_ws": 3, "pdm_ctas_per_sm": 1, "pdm_slice_batches": slice_b, "pdm_planar_bulk": bulk})
+             opts={"pdm_ctas_per_sm": 1, "pdm_slice_batches": slice_b, "pdm_planar_bulk": bulk})
 
 
-def test_pdm_v2_ws3_split_runs(st, ctx, oracle):
-    """Consecutive dynamic launches (work counter, epochs and progress words are reused)."""
+def test_pdm_v2_ws4_split_runs(st, ctx, oracle):
+    """Consecutive launches (work counter, epochs, progress words and the double-buffered generator state are reused)."""
     _v2_case(st, ctx, oracle, 2, 3, N=96 * 150 + 5, F=64 * 22, layout=st.TILED, count0=0, use_setp=True, use_dext=False,
-             ctl=7, split=[64 * 5, 64 * 4, 64 * 9, 64 * 4], opts={"pdm_ws": 3, "pdm_ctas_per_sm": 1, "pdm_slice_batches": 2})
+             ctl=7, split=[64 * 5, 64 * 4, 64 * 9, 64 * 4], opts={"pdm_ctas_per_sm": 1, "pdm_slice_batches": 2})
+    _v2_case(st, ctx, oracle, 3, 7, N=1000, F=64 * 9, layout=st.PLANAR, count0=0, use_setp=True, use_dext=False,
+             ctl=6, split=[64, 16, 48, 64 * 5, 64 * 2])
 
 
-@pytest.mark.parametrize("N,bank,F,wps", [(65536, 3, 512, 1), (65536, 4, 256, 1), (3 * 32 * 1300 + 5, 3, 160, 1),
-                                          (3 * 32 * 1300 + 5, 3, 160, 2), (200000, 2, 64, 4), (32 * 593, 1, 1024, 1)])
-def test_pdm_v2_persistent_schedule(st, ctx, oracle, N, bank, F, wps):
-    """More chains than warp schedulers: the wrap-around schedule splits chains
-    between workers (head on one, tail on the next) and must stay bit-exact."""
-    _v2_case(st, ctx, oracle, 2, bank, N=N, F=F, layout=st.TILED, count0=48, use_setp=True, use_dext=False, ctl=6,
-             opts={"pdm_warps_per_smsp": wps, "pdm_persist": 2, "pdm_ws": 0})
+@pytest.mark.parametrize("N,bank,layout,F", [(1 << 20, 3, "INTERLEAVED", 48), (1 << 20, 7, "TILED", 64), (1 << 20, 4096, "TILED", 64),
+                                             ((1 << 20) + 11, 4096, "PLANAR", 40), (1 << 20, 1 << 20, "TILED", 64),
+                                             (400000, 400000, "INTERLEAVED", 32), (1 << 20, 7, "TILED", 48)])
+def test_pdm_v2_banks_wider_than_a_block(st, ctx, oracle, N, bank, layout, F):
+    """A bank that spans blocks (or the whole batch: one dither word for every channel) is replayed by every block
+    that holds one of its channels; the generator state is double buffered so that no block sees another's
+    write-back.  >= 1 Mi channels: more blocks than one resident wave.  Covers k_pdm_v2_any (INTERLEAVED, ragged F),
+    the thread-per-channel kernel (F % 64 != 0) and k_pdm_v2_ws4 (unaligned groups)."""
+    _v2_case(st, ctx, oracle, 2, bank, N=N, F=F, layout=getattr(st, layout), count0=0, use_setp=True, use_dext=False, ctl=5)
 
 
 def test_pdm_v2_external_dither(st, ctx, oracle):
@@ -272,6 +263,30 @@ def test_pdm_v1(st, ctx, oracle, bank, tpb, persist, N, layout, chains):
     ctx.set_option("pdm_tpb", 1)
     ctx.set_option("pdm_persist", 1)
     ctx.set_option("pdm_v1_chains", 2)
+
+
+@pytest.mark.parametrize("N,bank,layout", [(1 << 20, 7, "TILED"), (1 << 20, 4096, "INTERLEAVED"), ((1 << 20) + 3, 1 << 20, "PLANAR"), (1 << 20, 3, "INTERLEAVED")])
+def test_pdm_v1_banks_wider_than_a_block(st, ctx, oracle, N, bank, layout):
+    """Thread-per-channel v1 kernel with a bank replayed by many blocks (>= 1 Mi channels: more than one resident wave):
+    the generator state is double buffered, no block may see another's write-back."""
+    F = 128
+    nb = (N + bank - 1) // bank
+    ch0 = rng.integers(0, 2**32, (N, 2), dtype=np.uint32)
+    prng0 = rng.integers(1, 2**32, nb, dtype=np.uint32)
+    ca, pa = ch0.copy(), prng0.copy()
+    want = pack_bits(oracle.pdm_v1_run(ca, N, bank, pa, None, 0x0FFFFFFF, F))
+    ctx.set_option("pdm_tpb", 0 if bank <= 4 else 1)
+    b = ctx.batch(st.PDM_V1, N, bank_size=bank, dither_mask=0x0FFFFFFF, layout=getattr(st, layout))
+    b.upload_state(ch0); b.upload_bank(prng0)
+    out = np.zeros(N * F // 32, np.uint32)
+    for _ in range(1):
+        b.run(F, out=out)
+    ctx.set_option("pdm_tpb", 1)
+    got = out.reshape(N, F // 32) if layout == "PLANAR" else out.reshape(F // 32, N).T if layout == "INTERLEAVED" else \
+        out.reshape(F // 128, N, 4).transpose(1, 0, 2).reshape(N, F // 32)
+    assert np.array_equal(got, want)
+    assert np.array_equal(b.download_state(), ca) and np.array_equal(b.download_bank()[0], pa)
+    b.free()
 
 
 def test_pdm_v1_external_dither_and_density(st, ctx, oracle):
