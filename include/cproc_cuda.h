@@ -336,6 +336,16 @@ int  cproc_cuda_bus_allreduce(cproc_cuda_bus *bus, int32_t *imix_dev, float *out
  * the context stream wait for that slot's last exchange. */
 int  cproc_cuda_bus_allreduce_begin(cproc_cuda_bus *bus, uint32_t slot, int32_t *imix_dev, float *out_dev, uint64_t count, uint32_t op, uint32_t scale);
 int  cproc_cuda_bus_wait(cproc_cuda_bus *bus, uint32_t slot);
+/* The exchange as the tail of the render kernel.  After _attach, cproc_cuda_run_dev on the batch (VOICE_BANK, XVOICE mix) renders the
+ * shard's mix AND exchanges it in the same launch: the blocks that complete a piece of the local mix push it into every
+ * peer's bus buffer, the last one publishes the flags.  io.mix / io.out then receive the bus of ALL ranks (reduced integer
+ * words / scaled float), like after _allreduce.
+ * mode 1: the reduce runs at the end of the same launch -- io.mix / io.out are valid when it completes.
+ * mode 2: pipelined -- the reduce of block k runs beside the render of block k+1 (one extra thread block of that launch), or
+ *         in cproc_cuda_bus_flush; io.mix / io.out of call k must stay valid until then and are written there.
+ * mode 0 (or bus NULL) detaches.  Every rank makes the same sequence of calls. */
+int  cproc_cuda_bus_attach(cproc_cuda_bus *bus, cproc_cuda_batch *batch, uint32_t mode);
+int  cproc_cuda_bus_flush(cproc_cuda_bus *bus);
 int  cproc_cuda_bus_status(cproc_cuda_bus *bus, uint32_t *failed_epoch);
 int  cproc_cuda_bus_destroy(cproc_cuda_bus *bus);
 

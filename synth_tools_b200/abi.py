@@ -120,6 +120,8 @@ SYMBOLS = {
     "cproc_cuda_bus_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]),
     "cproc_cuda_bus_allreduce_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]),
     "cproc_cuda_bus_wait": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "cproc_cuda_bus_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "cproc_cuda_bus_flush": (C.c_int, [C.c_void_p]),
     "cproc_cuda_bus_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "cproc_cuda_bus_destroy": (C.c_int, [C.c_void_p]),
     "cproc_cuda_graph_parse": (C.c_int, [C.c_char_p, C.POINTER(Node), C.c_uint32, C.POINTER(GraphInfo)]),
@@ -456,6 +458,18 @@ class Bus:
 
     def wait(self, slot):
         self.ctx._ck(lib.cproc_cuda_bus_wait(self.h, slot))
+
+    IN_LAUNCH, PIPELINED = 1, 2
+
+    def attach(self, batch, mode=1):
+        """The batch's render launch exchanges its mix itself (mode 1: reduce in the same launch, 2: beside the next one)."""
+        self.ctx._ck(lib.cproc_cuda_bus_attach(self.h, batch.h, mode))
+
+    def detach(self, batch):
+        self.ctx._ck(lib.cproc_cuda_bus_attach(None, batch.h, 0))
+
+    def flush(self):
+        self.ctx._ck(lib.cproc_cuda_bus_flush(self.h))
 
     def status(self):
         v = C.c_uint32()

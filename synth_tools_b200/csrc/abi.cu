@@ -110,6 +110,7 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     else if (!strcmp(name, "pdm_tpb")) ctx->pdm_tpb = value != 0;
     else if (!strcmp(name, "pdm_stage")) ctx->pdm_stage = value != 0;
     else if (!strcmp(name, "pdm_ws")) ctx->pdm_ws = value != 0;
+    else if (!strcmp(name, "voice_fpt")) { if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "voice_fpt must be 0, 1, 2, 4, 8 or 16"); ctx->voice_fpt = (int)value; }
     else if (!strcmp(name, "pdm_tlog")) { if (value < 6 || value > 7) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_tlog must be 6 or 7"); ctx->pdm_tlog = (int)value; }
     else if (!strcmp(name, "pdm_v1_chains")) { if (value != 1 && value != 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_v1_chains must be 1 or 2"); ctx->pdm_v1_chains = (int)value; }
     else if (!strcmp(name, "pdm_planar_bulk")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_planar_bulk must be 0..2"); ctx->pdm_planar_bulk = value ? 2 : 0; }
@@ -123,6 +124,7 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     else if (!strcmp(name, "grain_vec4")) ctx->grain_vec4 = value != 0;
     else if (!strcmp(name, "grain_mix2")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "grain_mix2 must be 0..2"); ctx->grain_mix2 = (int)value; }
     else if (!strcmp(name, "xvoice_chunk")) { if (value < 0) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice_chunk must be >= 0"); ctx->xvoice_chunk = (int)value; }
+    else if (!strcmp(name, "xvoice_vpt")) { if (value < 0 || value > 65536) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice_vpt must be 0..65536"); ctx->xvoice_vpt = (int)value; }
     else if (!strcmp(name, "xvoice_closed")) ctx->xvoice_closed = value ? 1 : 0;
     else if (!strcmp(name, "run_graph")) { if (value < 0 || value > 3) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "run_graph must be 0..3"); ctx->run_graph = (int)value; }
     else if (!strcmp(name, "xvoice_groups")) { if (value < 0 || value > 8) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice_groups must be 0..8"); ctx->xvoice_groups = (int)value; }
@@ -234,7 +236,7 @@ int cproc_cuda_free(cproc_cuda_batch *b) {
     if (!b) return 0;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    void *ptrs[] = { b->d_state, b->d_param, b->d_prng, b->d_prng2, b->d_prng_g, b->d_nodes, b->d_in, b->d_in2, b->d_ctl, b->d_out, b->d_out2, b->d_mix, b->d_flags, b->d_scratch, b->d_aux };
+    void *ptrs[] = { b->d_state, b->d_param, b->d_prng, b->d_prng2, b->d_prng_g, b->d_nodes, b->d_in, b->d_in2, b->d_ctl, b->d_out, b->d_out2, b->d_mix, b->d_flags, b->d_scratch, b->d_aux, b->d_acc };
     for (void *q : ptrs) if (q) cudaFree(q);
     for (cproc_graph_jit &j : b->jit) if (j.lib) cudaLibraryUnload(j.lib);
     if (b->rg.exec) cudaGraphExecDestroy(b->rg.exec);
@@ -410,7 +412,7 @@ int cproc_cuda_run(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     // captures [H2D from pinned staging, the launches of dispatch(), D2H to pinned staging] and every later call
     // is two host memcpys around one cudaGraphLaunch.
     const uint32_t proc = b->cfg.proc;
-    const bool graphable = ctx->run_graph && sz.in + sz.in2 + sz.ctl + sz.out + sz.mix <= (256u << 10) &&
+    const bool graphable = ctx->run_graph && !b->bus && sz.in + sz.in2 + sz.ctl + sz.out + sz.mix <= (256u << 10) &&
         ((proc == CPROC_CUDA_GRAPH && b->cfg.mode != CPROC_CUDA_GRAPH_SCAN) || proc == CPROC_CUDA_VOICE_BANK || proc == CPROC_CUDA_SQUARE_GRAIN ||
          proc == CPROC_CUDA_WORD_CLOCK || proc == CPROC_CUDA_PWM || (proc == CPROC_CUDA_ONEPOLE && b->cfg.mode != CPROC_CUDA_ONEPOLE_SCAN));
     // Zero copy (the kernels work on the pinned staging itself) only where the kernel that will run moves its streams

@@ -12,19 +12,26 @@
 // block cannot overwrite what a slow rank still reads.  One process per GPU: the buffers
 // are shared with cudaIpc handles, which the host exchanges over whatever transport it
 // has (bench/tests: torch.distributed all_gather).
+//
+// Two ways to run the exchange: as its own launch (cproc_cuda_bus_allreduce[_begin]: k_bus_allreduce below), or
+// as the tail of the render kernel of a batch the bus is attached to (cproc_cuda_bus_attach: bus_fused.cuh).
 #include "common.cuh"
+#include "bus_fused.cuh"
 #include <string.h>
-
-#define BUS_MAX_WORLD 16
 
 struct cproc_cuda_bus {
     cproc_cuda_ctx *ctx = nullptr;
     int world = 1, rank = 0;
     uint64_t cap = 0;                    // int32 words per slot
-    uint8_t *local = nullptr;            // [2][world][cap] int32, then [2][world] uint32 flags, then status word
+    uint8_t *local = nullptr;            // [BUS_NPAR][world][cap] int32, then [BUS_NPAR][world] uint32 flags, status word, ticket, then [2][cap] staging
+    // fused exchanges (attach): the reduce of the last pushed epoch still to be done (mode 2)
+    uint32_t pend_epoch = 0, pend_op = 0, pend_scale = 0;
+    uint64_t pend_count = 0;
+    int32_t *pend_imix = nullptr; float *pend_out = nullptr; const uint32_t *pend_stage = nullptr;
+    uint32_t launches = 0;               // fused launches so far (staging row parity)
     uint8_t *peer[BUS_MAX_WORLD] = {};   // peer-mapped bases (peer[rank] == local)
     bool connected = false;
-    uint32_t epoch = 0;
+    uint32_t epoch = 0;                  // shared by both forms: every rank makes the same sequence of exchanges
     cudaStream_t stream = nullptr;       // high-priority side stream of the overlapped form
     cudaEvent_t ev_in[2] = {}, ev_done[2] = {};
     bool pending[2] = {false, false};
@@ -41,13 +48,15 @@ struct BusParams {
     float *out;
 };
 
-static size_t bus_bytes(int world, uint64_t cap) { return sizeof(int32_t) * 2 * world * cap + sizeof(uint32_t) * (2 * world + 4); }
+static size_t bus_flag_off(int world, uint64_t cap) { return sizeof(int32_t) * BUS_NPAR * world * cap; }
+static size_t bus_stage_off(int world, uint64_t cap) { return bus_flag_off(world, cap) + sizeof(uint32_t) * (BUS_NPAR * world + 4); }   // flags, status, ticket, pad
+static size_t bus_bytes(int world, uint64_t cap) { return bus_stage_off(world, cap) + sizeof(uint32_t) * 2 * cap; }                       // + two staging rows (mode 2)
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 __global__ void __launch_bounds__(256) k_bus_allreduce(const BusParams p) {
-    const uint32_t par = p.epoch & 1u;
+    const uint32_t par = p.epoch & (BUS_NPAR - 1);
     const uint64_t my_slot = ((uint64_t)par * p.world + p.rank) * p.cap;
     // 1. push: my mix into slot[rank] of every rank (NVLink stores; the own copy is local)
     for (int q = 0; q < p.world; ++q) {
@@ -201,10 +210,10 @@ static int bus_launch(cproc_cuda_bus *b, int32_t *imix_dev, float *out_dev, uint
     memset(&p, 0, sizeof(p));
     p.world = b->world; p.rank = b->rank; p.cap = b->cap; p.count = count;
     p.epoch = ++b->epoch; p.op = op; p.scale = scale;
-    if (p.epoch == 0) p.epoch = b->epoch = 2;                 // flags start at 0; keep the parity sequence
-    const size_t flag_off = sizeof(int32_t) * 2 * b->world * b->cap;
+    if (p.epoch == 0) p.epoch = b->epoch = BUS_NPAR;          // flags start at 0; keep the parity sequence
+    const size_t flag_off = bus_flag_off(b->world, b->cap);
     for (int q = 0; q < b->world; ++q) { p.slots[q] = (int32_t *)b->peer[q]; p.flags[q] = (uint32_t *)(b->peer[q] + flag_off); }
-    p.status = (uint32_t *)(b->local + flag_off) + 2 * b->world;
+    p.status = (uint32_t *)(b->local + flag_off) + BUS_NPAR * b->world;
     p.imix = imix_dev; p.out = scale ? out_dev : nullptr;
     k_bus_allreduce<<<1, 256, 0, st>>>(p);
     CK_LAUNCH(ctx, "k_bus_allreduce");
@@ -216,9 +225,82 @@ int cproc_cuda_bus_status(cproc_cuda_bus *b, uint32_t *failed_epoch) {
     if (!b || !failed_epoch) return cproc_set_err(b ? b->ctx : nullptr, CPROC_CUDA_EINVAL, "bus_status: NULL argument");
     cproc_cuda_ctx *ctx = b->ctx;
     CK(ctx, cudaSetDevice(ctx->device));
-    const size_t flag_off = sizeof(int32_t) * 2 * b->world * b->cap;
-    CK(ctx, cudaMemcpyAsync(failed_epoch, (uint32_t *)(b->local + flag_off) + 2 * b->world, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t flag_off = bus_flag_off(b->world, b->cap);
+    CK(ctx, cudaMemcpyAsync(failed_epoch, (uint32_t *)(b->local + flag_off) + BUS_NPAR * b->world, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- the exchange as the tail of the render kernel (bus_fused.cuh) -------------------------------------------
+
+__global__ void __launch_bounds__(256) k_bus_finish(const BusFused bf) { bus_exchange_block(bf); }
+
+static void bus_fill(const cproc_cuda_bus *b, BusFused *bf) {
+    memset(bf, 0, sizeof(*bf));
+    bf->world = b->world; bf->rank = b->rank; bf->cap = b->cap;
+    const size_t flag_off = bus_flag_off(b->world, b->cap);
+    for (int q = 0; q < b->world; ++q) { bf->slots[q] = (int32_t *)b->peer[q]; bf->flags[q] = (uint32_t *)(b->peer[q] + flag_off); }
+    bf->status = (uint32_t *)(b->local + flag_off) + BUS_NPAR * b->world;
+    bf->ticket = bf->status + 1;
+}
+
+int cproc_cuda_bus_attach(cproc_cuda_bus *bus, cproc_cuda_batch *batch, uint32_t mode) {
+    if (!batch) return cproc_set_err(bus ? bus->ctx : nullptr, CPROC_CUDA_EINVAL, "bus_attach: batch is NULL");
+    cproc_cuda_ctx *ctx = batch->ctx;
+    if (!bus || mode == 0) { batch->bus = nullptr; batch->bus_mode = 0; return 0; }
+    if (mode > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "bus_attach: mode must be 0 (detach), 1 (reduce inside the render launch) or 2 (pipelined)");
+    if (bus->ctx != ctx) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "bus_attach: bus and batch belong to different contexts");
+    if (!bus->connected) return cproc_set_err(ctx, CPROC_CUDA_ESTATE, "bus_attach: bus not connected (cproc_cuda_bus_connect)");
+    const uint32_t proc = batch->cfg.proc;
+    if (proc != CPROC_CUDA_VOICE_BANK && proc != CPROC_CUDA_XVOICE)
+        return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "bus_attach: only the voice bank and the xvoice mix exchange their bus in the render launch");
+    batch->bus = bus; batch->bus_mode = mode;
+    return 0;
+}
+
+}  // extern "C"
+
+int cproc_bus_fused_begin(cproc_cuda_batch *b, BusFused *bf, uint64_t count, uint32_t op, uint32_t scale, uint32_t n_pushers,
+                          int32_t *imix_out, float *float_out) {
+    cproc_cuda_bus *bus = b->bus;
+    if (!bus) { memset(bf, 0, sizeof(*bf)); return 0; }
+    cproc_cuda_ctx *ctx = b->ctx;
+    if (count > bus->cap) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "run: the mix is %llu words, the attached bus holds %llu", (unsigned long long)count, (unsigned long long)bus->cap);
+    bus_fill(bus, bf);
+    bf->mode = b->bus_mode;
+    uint32_t epoch = ++bus->epoch;
+    if (epoch == 0) epoch = bus->epoch = BUS_NPAR;
+    if (bf->mode == 1) {
+        if (bus->pend_epoch) return cproc_set_err(ctx, CPROC_CUDA_ESTATE, "run: a pipelined exchange is pending on this bus (cproc_cuda_bus_flush first)");
+        bf->epoch = epoch; bf->participants = n_pushers;
+        bf->fin_epoch = epoch; bf->fin_op = op; bf->fin_scale = scale; bf->fin_count = count; bf->fin_imix = imix_out; bf->fin_out = float_out;
+    } else {
+        uint32_t *stage = (uint32_t *)(bus->local + bus_stage_off(bus->world, bus->cap)) + (size_t)(bus->launches++ & 1u) * bus->cap;
+        bf->stage = stage;
+        bf->fin_epoch = bus->pend_epoch; bf->fin_op = bus->pend_op; bf->fin_scale = bus->pend_scale; bf->fin_count = bus->pend_count;
+        bf->fin_imix = bus->pend_imix; bf->fin_out = bus->pend_out; bf->fin_stage = bus->pend_stage;
+        bus->pend_epoch = epoch; bus->pend_op = op; bus->pend_scale = scale; bus->pend_count = count; bus->pend_imix = imix_out; bus->pend_out = float_out;
+        bus->pend_stage = stage;
+    }
+    return 0;
+}
+
+extern "C" {
+
+// mode 2: complete the exchange of the last rendered block (asynchronous on the context stream)
+int cproc_cuda_bus_flush(cproc_cuda_bus *bus) {
+    if (!bus) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "bus_flush: bus is NULL");
+    cproc_cuda_ctx *ctx = bus->ctx;
+    if (!bus->pend_epoch) return 0;
+    CK(ctx, cudaSetDevice(ctx->device));
+    BusFused bf;
+    bus_fill(bus, &bf);
+    bf.mode = 2;
+    bf.fin_epoch = bus->pend_epoch; bf.fin_op = bus->pend_op; bf.fin_scale = bus->pend_scale; bf.fin_count = bus->pend_count;
+    bf.fin_imix = bus->pend_imix; bf.fin_out = bus->pend_out; bf.fin_stage = bus->pend_stage;
+    bus->pend_epoch = 0;
+    k_bus_finish<<<1, 256, 0, ctx->stream>>>(bf);
+    CK_LAUNCH(ctx, "k_bus_finish");
     return 0;
 }
 

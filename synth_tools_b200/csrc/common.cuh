@@ -35,7 +35,7 @@ struct cproc_cuda_ctx {
     int pdm_persist = 1;      // v1: persistent McNaughton-scheduled kernel when thread == bank (0 never, 1 auto, 2 always)
     int pdm_warps_per_smsp = 1;
     int n_sm = CPROC_N_SM;
-    int voice_block = 256;
+    int voice_fpt = 0;        // voice bank: frames per thread (0 = by frame count; 1, 2, 4, 8)
     int grain_block = 128;
     int grain_blocks_per_sm = 2;
     int grain_bulk = 5;       // planar square_grain: 0 register-transpose kernel; 1..4 per-lane bulk-copy kernel (tile/stage shapes); 5 tensor-TMA kernel
@@ -44,7 +44,7 @@ struct cproc_cuda_ctx {
     int planar_bulk = 2;      // PLANAR pdm_raw / onepole / pwm streams through planar_bulk.cuh: 0 off, 1 per-lane bulk copies, 2 tensor TMA
     int graph_vec4 = 1;       // interleaved generated graphs: four instances per thread when n % 4 == 0
     int graph_jit = 1;        // 1: generated graphs are compiled with NVRTC; 0: table-driven kernel
-    int xvoice_block = 128;
+    int xvoice_vpt = 0;       // k_xvoice_mix: voices per thread per L2-resident tile (0 = default)
     int xvoice_groups = 0;    // XVOICE_SCAN: variant groups pipelined over the two streams (0 = automatic)
     int xvoice_chunk = 0;     // XVOICE_SCAN: frames per time chunk (0 = automatic)
     uint64_t opt_epoch = 0;   // bumped by every set_option
@@ -61,8 +61,10 @@ struct cproc_graph_jit {
     uint32_t pl_smem = 0, pl_block = 0, pt_smem = 0;
 };
 
+struct cproc_cuda_bus;
 struct cproc_cuda_batch {
     cproc_cuda_ctx *ctx = nullptr;
+    cproc_cuda_bus *bus = nullptr; uint32_t bus_mode = 0;   // mix bus attached to this batch (cproc_cuda_bus_attach): the render launch exchanges its mix itself
     cproc_cuda_config cfg{};
     std::vector<cproc_cuda_node> nodes;     // copy of cfg.nodes
     std::vector<uint32_t> node_off;         // state word offset per node
@@ -85,6 +87,7 @@ struct cproc_cuda_batch {
     void *d_out2 = nullptr; size_t cap_out2 = 0;   // second slab for run_stream
     uint32_t *d_aux = nullptr; bool aux_dirty = true; uint32_t aux_weird = 0;   // derived parameter rows (grain mix integer thresholds)
     void *d_scratch = nullptr; size_t cap_scratch = 0;   // per-chunk start-state tables (XVOICE_SCAN)
+    uint32_t *d_acc = nullptr; size_t cap_acc = 0;       // voice bank: integer accumulators of a bus split over tiles + tickets; all zero between launches
     unsigned long long *d_flags = nullptr;         // persistent-kernel progress words
     uint64_t n_flags = 0;
     unsigned long long epoch = 0;

@@ -13,6 +13,7 @@
 // pass), deterministic run to run, and compared with tolerance.
 #include "common.cuh"
 #include "planar_bulk.cuh"
+#include "bus_fused.cuh"
 
 struct XVoiceParams {
     uint32_t *st;            // SoA [5][npad]: phase, lp, bp, env, t
@@ -21,6 +22,10 @@ struct XVoiceParams {
     float *raw;              // PLANAR [inst][F][2] / TILED [F/2][inst][4] or null
     float *partial;          // [n_blocks][2][F] or null
     uint32_t layout;
+    float *mix;              // k_xvoice_mix: [2][F]
+    uint32_t *done;          // k_xvoice_mix: [2] blocks that left / finalisers done (zero between launches)
+    uint32_t n_render_blocks;// k_xvoice_mix: gridDim.x without the finisher block of a pipelined bus
+    uint32_t vpt;            // k_xvoice_mix: voices per thread per L2 tile
 };
 
 struct XV {
@@ -153,100 +158,170 @@ __global__ void __launch_bounds__(XV_BLOCK) k_xvoice(const XVoiceParams p) {
 // recurrence in time, so a voice stays on one thread; the reduction over voices is
 // taken out of the inner loop instead of being paid per voice-sample: a thread keeps
 // 2 x 32 bus accumulators (32 frames, left/right) in registers and walks ITS voices
-// (tid, tid + T, ...) through the same 32 frames one after the other, so the pan
-// multiply and the mix add fuse into one FFMA per channel and nothing crosses lanes
-// until all of the thread's voices are done.  Only then: one block reduction per 32
-// frames (smem columns, fixed order) and one partial row per block; k_xvoice_final
-// adds the block rows in a fixed order, so the result is deterministic run to run.
-// Voice state travels through HBM once per 32 frames (13 words in, 5 out per voice:
-// 2.25 B per voice-sample); the tick itself is the bit-exact xvoice_tick, so the
-// downloaded state equals the oracle's.
+// through the same 32 frames one after the other, so the pan multiply and the mix add
+// fuse into one FFMA per channel and nothing crosses lanes until all of the thread's
+// voices are done.  Only then: one block reduction per 32 frames (smem columns, fixed
+// order) into the block's partial row.
+//
+// Voice state travels through memory once per 32 frames (13 words in, 5 out per voice): 4.5 GB of DRAM traffic per
+// 4 Mi x 512 launch at 3.6 TB/s.  The voices can be walked in TILES of `vpt` voices per thread, all frame chunks of a
+// tile before the next tile, so that a tile (vpt = 12: 592 blocks x 128 threads x 12 voices x 72 B = 65 MB) stays in L2
+// and DRAM sees every voice once per launch (0.35 GB).  Measured (option xvoice_vpt, tools/xv_time.py): vpt 8 / 12 / 16 /
+// 64 = 1.357 / 1.323 / 1.310 / 1.264 ms -- every tile pays its own block reduction per chunk and the kernel is issue
+// bound, not bandwidth bound, so the default is one tile (vpt 64).  The loads of the next voice -- across the chunk
+// boundary too: the thread's first voice of the next chunk -- are in flight while the current one renders.
+//
+// The launch finishes its own mix: the last XM chunks' worth of blocks to leave (atomic
+// ticket) wait for the stragglers and add the block rows of one 32-frame chunk each, in a
+// fixed order, so the result is deterministic run to run; with a mix bus attached they
+// push their columns to the peers instead (float sum in rank order, bus_fused.cuh).
 #define XM_BLOCK 128
 #define XM_CHUNK 32
+#define XM_VPT 64
 __device__ __forceinline__ void xv_load(XV &v, const XVoiceParams &p, uint64_t i) {
     const uint32_t *s = p.st + i; const uint32_t *r = p.prm + i;
     v.phase = __ldcg(s); v.lp = __uint_as_float(__ldcg(s + p.npad)); v.bp = __uint_as_float(__ldcg(s + 2 * p.npad));
     v.env = __uint_as_float(__ldcg(s + 3 * p.npad)); v.t = __ldcg(s + 4 * p.npad);
-    v.inc = __ldg(r); v.f = __uint_as_float(__ldg(r + p.npad)); v.q = __uint_as_float(__ldg(r + 2 * p.npad));
-    v.att = __uint_as_float(__ldg(r + 3 * p.npad)); v.rel = __uint_as_float(__ldg(r + 4 * p.npad)); v.gate = __ldg(r + 5 * p.npad);
-    v.gl = __uint_as_float(__ldg(r + 6 * p.npad)); v.gr = __uint_as_float(__ldg(r + 7 * p.npad));
+    v.inc = __ldcg(r); v.f = __uint_as_float(__ldcg(r + p.npad)); v.q = __uint_as_float(__ldcg(r + 2 * p.npad));
+    v.att = __uint_as_float(__ldcg(r + 3 * p.npad)); v.rel = __uint_as_float(__ldcg(r + 4 * p.npad)); v.gate = __ldcg(r + 5 * p.npad);
+    v.gl = __uint_as_float(__ldcg(r + 6 * p.npad)); v.gr = __uint_as_float(__ldcg(r + 7 * p.npad));
 }
-__global__ void __launch_bounds__(XM_BLOCK, 4) k_xvoice_mix(const XVoiceParams p) {
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+__global__ void __launch_bounds__(XM_BLOCK, 4) k_xvoice_mix(const XVoiceParams p, const BusFused bf) {
     __shared__ float red[2 * XM_CHUNK][XM_BLOCK + 1];
-    const uint64_t T = (uint64_t)gridDim.x * XM_BLOCK;
+    __shared__ uint32_t tick_s;
+    if (blockIdx.x >= p.n_render_blocks) { bus_exchange_block(bf); return; }      // pipelined bus: the previous frame block's exchange
+    const uint64_t T = (uint64_t)p.n_render_blocks * XM_BLOCK;
     const uint64_t tid = (uint64_t)blockIdx.x * XM_BLOCK + threadIdx.x;
-    for (uint64_t t0 = 0; t0 < p.F; t0 += XM_CHUNK) {
-        const uint32_t cols = p.F - t0 < XM_CHUNK ? (uint32_t)(p.F - t0) : XM_CHUNK;
-        float aL[XM_CHUNK], aR[XM_CHUNK];
-#pragma unroll
-        for (int k = 0; k < XM_CHUNK; ++k) { aL[k] = 0.f; aR[k] = 0.f; }
-        // software pipeline: the 13 words of the thread's next voice are in flight
-        // while the current one renders its 32 frames
+    const uint32_t n_chunks = (uint32_t)((p.F + XM_CHUNK - 1) / XM_CHUNK);
+    for (uint64_t tile0 = 0; tile0 < p.n; tile0 += T * p.vpt) {
+        // this thread's voices of the tile: tile0 + tid + j*T, j < nvt
+        const uint64_t first = tile0 + tid;
+        uint32_t nvt = 0;
+        if (first < p.n) { const uint64_t left = (p.n - first + T - 1) / T; nvt = left < p.vpt ? (uint32_t)left : p.vpt; }
         XV nx = {};
-        if (tid < p.n) xv_load(nx, p, tid);
-        for (uint64_t i = tid; i < p.n; i += T) {
-            XV v = nx;
-            if (i + T < p.n) xv_load(nx, p, i + T);
-            // bit k: tick k of this chunk is in the attack phase, (t + k) mod 2^32 < gate
-            uint32_t amask;
-            if (v.t <= 0xFFFFFFFFu - XM_CHUNK) {
-                const uint32_t rem = v.t < v.gate ? v.gate - v.t : 0u;
-                amask = rem >= 32u ? 0xFFFFFFFFu : (1u << rem) - 1u;
-            } else {                                       // the frame counter wraps inside the chunk
-                amask = 0;
-                for (uint32_t k = 0; k < XM_CHUNK; ++k) amask |= (uint32_t)(v.t + k < v.gate) << k;
-            }
-            // whole chunk in one phase (sustained or released voices: the steady state of a mix) for every
-            // lane still in the loop -> the three-instruction envelope
-            // (bit patterns: +0 <= env <= 1 and rates with a clear sign bit exclude NaN and -0.0, for which the
-            // extra clamp would not be an identity)
-            const bool uni = (amask == 0u || amask == 0xFFFFFFFFu) && __float_as_uint(v.att) <= 0x7F800000u && __float_as_uint(v.rel) <= 0x7F800000u &&
-                             __float_as_uint(v.env) <= 0x3F800000u;
-            if (cols == XM_CHUNK && __all_sync(__activemask(), uni)) {
-                const float d = amask ? v.att : -v.rel;
+        if (nvt) xv_load(nx, p, first);
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            const uint64_t t0 = (uint64_t)c * XM_CHUNK;
+            const uint32_t cols = p.F - t0 < XM_CHUNK ? (uint32_t)(p.F - t0) : XM_CHUNK;
+            float aL[XM_CHUNK], aR[XM_CHUNK];
 #pragma unroll
-                for (int k = 0; k < XM_CHUNK; ++k) {
-                    const float y = xvoice_tick_uniform(v, d);
-                    aL[k] = __fmaf_rn(v.gl, y, aL[k]);
-                    aR[k] = __fmaf_rn(v.gr, y, aR[k]);
+            for (int k = 0; k < XM_CHUNK; ++k) { aL[k] = 0.f; aR[k] = 0.f; }
+            for (uint32_t j = 0; j < nvt; ++j) {
+                const uint64_t i = first + (uint64_t)j * T;
+                XV v = nx;
+                // next voice: the following one of this chunk, else the thread's first voice in the next chunk (stored earlier in
+                // this chunk, same thread: program order makes the reload see it) -- unless that is this very voice
+                const bool wrap = j + 1 == nvt;
+                if (!wrap) xv_load(nx, p, i + T);
+                else if (nvt > 1 && c + 1 < n_chunks) xv_load(nx, p, first);
+                // bit k: tick k of this chunk is in the attack phase, (t + k) mod 2^32 < gate
+                uint32_t amask;
+                if (v.t <= 0xFFFFFFFFu - XM_CHUNK) {
+                    const uint32_t rem = v.t < v.gate ? v.gate - v.t : 0u;
+                    amask = rem >= 32u ? 0xFFFFFFFFu : (1u << rem) - 1u;
+                } else {                                       // the frame counter wraps inside the chunk
+                    amask = 0;
+                    for (uint32_t k = 0; k < XM_CHUNK; ++k) amask |= (uint32_t)(v.t + k < v.gate) << k;
                 }
-            } else if (cols == XM_CHUNK) {
+                // whole chunk in one phase (sustained or released voices: the steady state of a mix) for every
+                // lane still in the loop -> the three-instruction envelope
+                // (bit patterns: +0 <= env <= 1 and rates with a clear sign bit exclude NaN and -0.0, for which the
+                // extra clamp would not be an identity)
+                const bool uni = (amask == 0u || amask == 0xFFFFFFFFu) && __float_as_uint(v.att) <= 0x7F800000u && __float_as_uint(v.rel) <= 0x7F800000u &&
+                                 __float_as_uint(v.env) <= 0x3F800000u;
+                if (cols == XM_CHUNK && __all_sync(__activemask(), uni)) {
+                    const float d = amask ? v.att : -v.rel;
 #pragma unroll
-                for (int k = 0; k < XM_CHUNK; ++k) {
-                    const float y = xvoice_tick_flag(v, (amask >> k) & 1u);
-                    aL[k] = __fmaf_rn(v.gl, y, aL[k]);
-                    aR[k] = __fmaf_rn(v.gr, y, aR[k]);
-                }
-            } else {
+                    for (int k = 0; k < XM_CHUNK; ++k) {
+                        const float y = xvoice_tick_uniform(v, d);
+                        aL[k] = __fmaf_rn(v.gl, y, aL[k]);
+                        aR[k] = __fmaf_rn(v.gr, y, aR[k]);
+                    }
+                } else if (cols == XM_CHUNK) {
 #pragma unroll
-                for (int k = 0; k < XM_CHUNK; ++k) {
-                    if (k < (int)cols) {
+                    for (int k = 0; k < XM_CHUNK; ++k) {
                         const float y = xvoice_tick_flag(v, (amask >> k) & 1u);
                         aL[k] = __fmaf_rn(v.gl, y, aL[k]);
                         aR[k] = __fmaf_rn(v.gr, y, aR[k]);
                     }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < XM_CHUNK; ++k) {
+                        if (k < (int)cols) {
+                            const float y = xvoice_tick_flag(v, (amask >> k) & 1u);
+                            aL[k] = __fmaf_rn(v.gl, y, aL[k]);
+                            aR[k] = __fmaf_rn(v.gr, y, aR[k]);
+                        }
+                    }
+                }
+                v.t += cols;
+                uint32_t *w = p.st + i;
+                __stcg(w, v.phase); __stcg(w + p.npad, __float_as_uint(v.lp)); __stcg(w + 2 * p.npad, __float_as_uint(v.bp));
+                __stcg(w + 3 * p.npad, __float_as_uint(v.env)); __stcg(w + 4 * p.npad, v.t);
+                if (wrap && nvt == 1) nx = v;                  // the thread's only voice stays in registers
+            }
+#pragma unroll
+            for (int k = 0; k < XM_CHUNK; ++k) { red[k][threadIdx.x] = aL[k]; red[XM_CHUNK + k][threadIdx.x] = aR[k]; }
+            __syncthreads();
+            {   // column sums: two threads per column (64 rows each, 4 chains), halves combined in a fixed order
+                const uint32_t col = threadIdx.x >> 1, half = threadIdx.x & 1u;
+                const float *row = &red[col][half * (XM_BLOCK / 2)];
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+                for (int j = 0; j < XM_BLOCK / 2; j += 4) {
+                    s0 = __fadd_rn(s0, row[j]); s1 = __fadd_rn(s1, row[j + 1]); s2 = __fadd_rn(s2, row[j + 2]); s3 = __fadd_rn(s3, row[j + 3]);
+                }
+                float s = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+                const float o = __shfl_xor_sync(0xFFFFFFFFu, s, 1);
+                s = half ? __fadd_rn(o, s) : __fadd_rn(s, o);   // low half + high half on both lanes
+                const uint32_t ch = col / XM_CHUNK, f = col % XM_CHUNK;
+                if (!half && f < cols) {
+                    float *dst = p.partial + ((uint64_t)blockIdx.x * 2 + ch) * p.F + t0 + f;
+                    *dst = tile0 ? __fadd_rn(*dst, s) : s;       // tiles accumulate in tile order
                 }
             }
-            v.t += cols;
-            uint32_t *w = p.st + i;
-            w[0] = v.phase; w[p.npad] = __float_as_uint(v.lp); w[2 * p.npad] = __float_as_uint(v.bp);
-            w[3 * p.npad] = __float_as_uint(v.env); w[4 * p.npad] = v.t;
+            __syncthreads();
         }
-#pragma unroll
-        for (int k = 0; k < XM_CHUNK; ++k) { red[k][threadIdx.x] = aL[k]; red[XM_CHUNK + k][threadIdx.x] = aR[k]; }
-        __syncthreads();
-        if (threadIdx.x < 2 * XM_CHUNK) {
-            const uint32_t ch = threadIdx.x / XM_CHUNK, f = threadIdx.x % XM_CHUNK;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 8
-            for (int j = 0; j < XM_BLOCK; j += 4) {
-                s0 = __fadd_rn(s0, red[threadIdx.x][j]); s1 = __fadd_rn(s1, red[threadIdx.x][j + 1]);
-                s2 = __fadd_rn(s2, red[threadIdx.x][j + 2]); s3 = __fadd_rn(s3, red[threadIdx.x][j + 3]);
-            }
-            if (f < cols) p.partial[((uint64_t)blockIdx.x * 2 + ch) * p.F + t0 + f] = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
-        }
-        __syncthreads();
     }
+    // ---- the launch's own final reduction: the last n_fin blocks to leave take one chunk (and every n_fin-th) each
+    const uint32_t nb = p.n_render_blocks;
+    const uint32_t n_fin = n_chunks < nb ? n_chunks : nb;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) tick_s = atomicAdd(p.done, 1u);
+    __syncthreads();
+    const uint32_t tk = tick_s;
+    if (tk < nb - n_fin) return;
+    if (threadIdx.x == 0) while (ld_acquire_gpu_u32(p.done) < nb) __nanosleep(64);       // the stragglers are resident: they arrive
+    __syncthreads();
+    for (uint32_t c = tk - (nb - n_fin); c < n_chunks; c += n_fin) {
+        const uint64_t t0 = (uint64_t)c * XM_CHUNK;
+        const uint32_t cols = p.F - t0 < XM_CHUNK ? (uint32_t)(p.F - t0) : XM_CHUNK;
+        const uint32_t col = threadIdx.x >> 1, half = threadIdx.x & 1u, ch = col / XM_CHUNK, f = col % XM_CHUNK;
+        const uint32_t b0 = half ? (nb + 1) / 2 : 0u, b1 = half ? nb : (nb + 1) / 2;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        if (f < cols) {
+            const float *src = p.partial + (uint64_t)ch * p.F + t0 + f;
+            uint32_t bq = b0;
+            for (; bq + 4 <= b1; bq += 4) {
+                s0 = __fadd_rn(s0, __ldcg(src + (uint64_t)(bq + 0) * 2 * p.F)); s1 = __fadd_rn(s1, __ldcg(src + (uint64_t)(bq + 1) * 2 * p.F));
+                s2 = __fadd_rn(s2, __ldcg(src + (uint64_t)(bq + 2) * 2 * p.F)); s3 = __fadd_rn(s3, __ldcg(src + (uint64_t)(bq + 3) * 2 * p.F));
+            }
+            for (; bq < b1; ++bq) s0 = __fadd_rn(s0, __ldcg(src + (uint64_t)bq * 2 * p.F));
+        }
+        float s = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+        const float o = __shfl_xor_sync(0xFFFFFFFFu, s, 1);
+        s = half ? __fadd_rn(o, s) : __fadd_rn(s, o);
+        if (!half && f < cols) {
+            const uint64_t idx = (uint64_t)ch * p.F + t0 + f;
+            if (bf.world) bus_emit_word(bf, idx, __float_as_uint(s)); else p.mix[idx] = s;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(p.done + 1, 1u) == n_fin - 1u) { p.done[0] = 0; p.done[1] = 0; __threadfence(); }   // ready for the next launch
+    if (bf.world) bus_participant_done(bf);
 }
 
 // mix[c][t] = SUM_b partial[b][c][t], fixed order, 4 independent chains
@@ -755,10 +830,13 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
         if (L < F) return launch_xvoice_scan(b, F, io, L, groups);
     }
     const bool mix_only = io->mix && !io->out;
-    const uint64_t n_blocks = mix_only ? (uint64_t)ctx->n_sm * 4 : ceil_div_u64(b->n, XV_BLOCK);
+    if (b->bus && !mix_only) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice: with a mix bus attached only the mix is rendered (out must be NULL)");
+    // (mix: four resident blocks per SM; a pipelined bus keeps one slot for the block that completes the previous exchange)
+    const uint64_t n_blocks = mix_only ? (uint64_t)ctx->n_sm * 4 - (b->bus && b->bus_mode == 2 ? 1 : 0) : ceil_div_u64(b->n, XV_BLOCK);
     XVoiceParams p;
     p.st = b->d_state; p.prm = b->d_param; p.npad = b->npad; p.n = b->n; p.F = F;
     p.raw = (float *)io->out; p.layout = io->layout; p.partial = nullptr;
+    p.mix = (float *)io->mix; p.done = nullptr; p.n_render_blocks = (uint32_t)n_blocks;
     if (io->mix) {
         size_t need = sizeof(float) * n_blocks * 2 * F;
         if (b->cap_mix < need) {
@@ -769,9 +847,24 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
         }
         p.partial = (float *)b->d_mix;
     }
+    if (mix_only) {
+        if (!b->d_acc) {
+            CK(ctx, cudaMalloc(&b->d_acc, 2 * sizeof(uint32_t)));
+            CK(ctx, cudaMemsetAsync(b->d_acc, 0, 2 * sizeof(uint32_t), ctx->stream));
+            b->cap_acc = 2 * sizeof(uint32_t);
+        }
+        p.done = b->d_acc;
+        p.vpt = ctx->xvoice_vpt > 0 ? (uint32_t)ctx->xvoice_vpt : XM_VPT;
+        const uint32_t n_chunks = (uint32_t)ceil_div_u64(F, XM_CHUNK);
+        BusFused bf;
+        int rc = cproc_bus_fused_begin(b, &bf, 2 * F, 2u, 0u, n_chunks < n_blocks ? n_chunks : (uint32_t)n_blocks, (int32_t *)io->mix, nullptr);
+        if (rc) return rc;
+        k_xvoice_mix<<<(unsigned)n_blocks + (bf.world && bf.mode == 2 ? 1u : 0u), XM_BLOCK, 0, ctx->stream>>>(p, bf);
+        CK_LAUNCH(ctx, "k_xvoice_mix");
+        return 0;
+    }
     if (io->out && io->mix) k_xvoice<true, true><<<(unsigned)n_blocks, XV_BLOCK, 0, ctx->stream>>>(p);
-    else if (io->out) k_xvoice<true, false><<<(unsigned)n_blocks, XV_BLOCK, 0, ctx->stream>>>(p);
-    else k_xvoice_mix<<<(unsigned)n_blocks, XM_BLOCK, 0, ctx->stream>>>(p);
+    else k_xvoice<true, false><<<(unsigned)n_blocks, XV_BLOCK, 0, ctx->stream>>>(p);
     CK_LAUNCH(ctx, "k_xvoice");
     if (io->mix) {
         k_xvoice_final<<<(unsigned)ceil_div_u64(2 * F, 128), 128, 0, ctx->stream>>>(p.partial, (float *)io->mix, n_blocks, 2 * F);

@@ -4,10 +4,13 @@ mix bus reduced across the GPUs of one box).  Run under torchrun, one rank per G
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/multi_gpu_mix.py
 
 Voices are sharded in contiguous ranges; each rank renders the INTEGER mix of its shard
-(k_voice_mix).  The bus is then formed twice: (A) NCCL all-reduce of the int32 mix + the
+(k_voice_mix).  The bus is then formed four ways: (A) NCCL all-reduce of the int32 mix + the
 conversion kernel, (B) cproc_cuda_bus_allreduce -- one kernel per rank over NVLink peer
-memory, reduce and float scale fused.  Both must equal the single-device oracle bit for bit.
-Prints one JSON line per measurement (rank 0)."""
+memory, reduce and float scale fused, (C) the exchange fused into the render launch
+(cproc_cuda_bus_attach mode 1: reduce at the end of the same launch), (D) the same, pipelined
+(mode 2: the reduce of block k beside the render of block k+1).  All must equal the
+single-device oracle bit for bit.  Prints one JSON line per measurement (rank 0).
+--check-only: parity checks at reduced sizes, no timing (tests/test_gpu_multi.py)."""
 import json
 import os
 import sys
@@ -87,10 +90,30 @@ def check(N, F, mode):
     torch.cuda.synchronize()
     ok_b = ok_b and bus.status() == 0 and np.array_equal(outs[0].cpu().numpy().view(np.uint32), wants[2].view(np.uint32)) and \
         np.array_equal(outs[1].cpu().numpy().view(np.uint32), wants[3].view(np.uint32))
+    # (C) / (D): the exchange as the tail of the render launch; six blocks continue the phases
+    ok_f = []
+    for bus_mode in (1, 2):
+        okm = True
+        b.upload_state(np.ascontiguousarray(v[lo:hi]))
+        full3 = v.copy()
+        bus.attach(b, bus_mode)
+        outs6 = [torch.zeros(F, dtype=torch.float32, device=dev) for _ in range(6)]
+        mixes6 = [torch.zeros(F, dtype=torch.int32, device=dev) for _ in range(6)]
+        wants6 = []
+        for k in range(6):
+            wants6.append(orc.voice_bank_run(full3, N, N, mode, F))
+            b.run_dev(F, mix=mixes6[k].data_ptr(), out=outs6[k].data_ptr())
+        bus.flush()
+        torch.cuda.synchronize()
+        for k in range(6):
+            okm = okm and np.array_equal(outs6[k].cpu().numpy().view(np.uint32), wants6[k][1][0].view(np.uint32)) and \
+                np.array_equal(mixes6[k].cpu().numpy().view(np.uint32), wants6[k][0][0].view(np.uint32))
+        bus.detach(b)
+        ok_f.append(okm and bus.status() == 0)
     bus.destroy(); b.free()
-    t = torch.tensor([int(ok_a), int(ok_b)], device=dev)
+    t = torch.tensor([int(ok_a), int(ok_b), int(ok_f[0]), int(ok_f[1])], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
-    return bool(t[0].item()), bool(t[1].item())
+    return [bool(x.item()) for x in t]
 
 
 def timing(N, F, reps=50):
@@ -126,8 +149,25 @@ def timing(N, F, reps=50):
         b.run_dev(F, mix=imix2[s].data_ptr())
         bus.begin(s, imix2[s].data_ptr(), F, out_dev=out2[s].data_ptr(), scale=st.Bus.SCALE_SAW)
 
+    def block_fused():
+        s = kblk[0] & 1
+        kblk[0] += 1
+        b.run_dev(F, mix=imix2[s].data_ptr(), out=out2[s].data_ptr())
+
+    def block_fused_k4():                                  # four frame blocks per launch, one exchange of 4 x 512 words
+        b.run_dev(4 * F, mix=imix4.data_ptr(), out=out4.data_ptr())
+
+    imix4 = torch.zeros(4 * F, dtype=torch.int32, device=dev)
+    out4 = torch.zeros(4 * F, dtype=torch.float32, device=dev)
     for name, fn in (("render_only", block_render_only), ("nccl_allreduce_plus_convert", block_nccl), ("peer_memory_bus_kernel", block_bus),
-                     ("peer_memory_bus_overlapped", block_bus_overlapped)):
+                     ("peer_memory_bus_overlapped", block_bus_overlapped), ("fused_in_launch", block_fused), ("fused_pipelined", block_fused),
+                     ("fused_pipelined_4_blocks_per_launch", block_fused_k4), ("render_only_4_blocks_per_launch", block_fused_k4)):
+        if name == "fused_in_launch":
+            bus.attach(b, 1)
+        elif name.startswith("fused_pipelined"):
+            bus.attach(b, 2)
+        else:
+            bus.detach(b)
         for _ in range(5):
             fn()
         dist.barrier(); torch.cuda.synchronize()
@@ -135,13 +175,14 @@ def timing(N, F, reps=50):
         e0.record(stream)
         for _ in range(reps):
             fn()
-        bus.wait(0); bus.wait(1)
+        bus.wait(0); bus.wait(1); bus.flush()
         e1.record(stream)
         dist.barrier(); torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        res[name] = float(t.item())
+        res[name] = float(t.item()) / (4 if name.endswith("4_blocks_per_launch") else 1)
     ok = bus.status() == 0
+    bus.detach(b)
     bus.destroy(); b.free()
     return res, ok
 
@@ -179,7 +220,29 @@ def xvoice_check_and_timing(N_check, N, F, reps=20):
     allmix = [torch.empty_like(mix) for _ in range(world)]
     dist.all_gather(allmix, mix)
     ok = ok and all(torch.equal(allmix[0], m) for m in allmix)          # every rank holds the same bits
+    # the exchange fused into the render launch: the same bits as the separate bus kernel, in both modes, over 3 blocks
+    for bus_mode in (1, 2):
+        b.upload_state(np.ascontiguousarray(s0[lo:hi]).view(np.uint32).reshape(hi - lo, 5))
+        bus.attach(b, bus_mode)
+        m3 = [torch.zeros(2 * F, dtype=torch.float32, device=dev) for _ in range(3)]
+        for k in range(3):
+            b.run_dev(F, mix=m3[k].data_ptr())
+        bus.flush()
+        torch.cuda.synchronize()
+        bus.detach(b)
+        ok = ok and torch.equal(m3[0], mix) and bus.status() == 0
+        # blocks 2 and 3 against the separate form
+        b.upload_state(np.ascontiguousarray(s0[lo:hi]).view(np.uint32).reshape(hi - lo, 5))
+        for k in range(3):
+            mk = torch.zeros(2 * F, dtype=torch.float32, device=dev)
+            b.run_dev(F, mix=mk.data_ptr())
+            bus.allreduce(mk.data_ptr(), 2 * F, op=st.Bus.FSUM)
+            torch.cuda.synchronize()
+            ok = ok and torch.equal(m3[k], mk)
     b.free()
+    if N == 0:
+        bus.destroy()
+        return ok, {}
     # timing at the full size
     s0, prm = xvoice_records(N, 6)
     lo, hi = shard.shard_range(N, rank, world)
@@ -203,8 +266,20 @@ def xvoice_check_and_timing(N_check, N, F, reps=20):
         b.run_dev(F, mix=mixes[s].data_ptr())
         bus.begin(s, mixes[s].data_ptr(), 2 * F, op=st.Bus.FSUM)
 
+    def fused():
+        s = k[0] & 1
+        k[0] += 1
+        b.run_dev(F, mix=mixes[s].data_ptr())
+
     res = {}
-    for name, fn in (("render_only", render_only), ("nccl_allreduce", nccl), ("peer_memory_bus_overlapped", overlapped)):
+    for name, fn in (("render_only", render_only), ("nccl_allreduce", nccl), ("peer_memory_bus_overlapped", overlapped), ("fused_in_launch", fused),
+                     ("fused_pipelined", fused)):
+        if name == "fused_in_launch":
+            bus.attach(b, 1)
+        elif name == "fused_pipelined":
+            bus.attach(b, 2)
+        else:
+            bus.detach(b)
         for _ in range(3):
             fn()
         dist.barrier(); torch.cuda.synchronize()
@@ -212,21 +287,31 @@ def xvoice_check_and_timing(N_check, N, F, reps=20):
         e0.record(stream)
         for _ in range(reps):
             fn()
-        bus.wait(0); bus.wait(1)
+        bus.wait(0); bus.wait(1); bus.flush()
         e1.record(stream)
         dist.barrier(); torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         res[name] = float(t.item())
     ok = ok and bus.status() == 0
+    bus.detach(b)
     bus.destroy(); b.free()
     return ok, res
 
 
+CHECK_ONLY = "--check-only" in sys.argv
 for mode in (0, 1):
-    a, bb = check(256 * 1024 + 77, 512, mode)
+    a, bb, c1, c2 = check(256 * 1024 + 77, 512, mode)
     if rank == 0:
-        print(json.dumps({"check": "voice bank mix bus, mode %d" % mode, "n_gpus": world, "nccl_bit_exact": a, "peer_bus_bit_exact": bb}), flush=True)
+        print(json.dumps({"check": "voice bank mix bus, mode %d" % mode, "n_gpus": world, "nccl_bit_exact": a, "peer_bus_bit_exact": bb,
+                          "fused_in_launch_bit_exact": c1, "fused_pipelined_bit_exact": c2}), flush=True)
+if CHECK_ONLY:
+    okx, _ = xvoice_check_and_timing(64 * 1024 + 5, 0, 512)
+    if rank == 0:
+        print(json.dumps({"check": "xvoice float bus", "n_gpus": world, "float_bus_within_tolerance_and_identical_on_all_ranks_ok": bool(okx)}), flush=True)
+    ctx.close()
+    dist.destroy_process_group()
+    sys.exit(0)
 res, ok = timing(4 * 1024 * 1024, 512)
 if rank == 0:
     N, F = 4 * 1024 * 1024, 512
