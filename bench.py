@@ -137,15 +137,17 @@ def run_reference(args, rank, world):
     chan = np.zeros((n_ch, 7), np.uint32)
     prng = (np.arange(n_ch // 3) + 1).astype(np.uint32)
     sp = po.pdm_setpoints(n_ch, ticks // 4096)
+    duty = np.zeros((n_ch, ticks), np.uint8)       # allocated and touched once: the timed loop renders, it does not page-fault
     count = 0
+    _, count = lib.pdm_v2_run(chan, 2, n_ch, 3, prng, None, 0x3FF, count, CTL_LOG, 24, sp, ticks, out=duty)
     for _ in range(args.warmup):
-        _, count = lib.pdm_v2_run(chan, 2, n_ch, 3, prng, None, 0x3FF, count, CTL_LOG, 24, sp, ticks)
+        _, count = lib.pdm_v2_run(chan, 2, n_ch, 3, prng, None, 0x3FF, count, CTL_LOG, 24, sp, ticks, out=duty)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, count = lib.pdm_v2_run(chan, 2, n_ch, 3, prng, None, 0x3FF, count, CTL_LOG, 24, sp, ticks)
+        _, count = lib.pdm_v2_run(chan, 2, n_ch, 3, prng, None, 0x3FF, count, CTL_LOG, 24, sp, ticks, out=duty)
     dt = time.perf_counter() - t0
     value = n_ch * ticks * args.steps / dt
-    sample = "%d ch x %d samples per step (same modulator, setpoints and dither as the native arm)" % (n_ch, ticks)
+    sample = "%d ch x %d samples per step (same modulator, setpoints and dither as the native arm), gcc -O2, output buffer preallocated" % (n_ch, ticks)
     line = {
         "impl": "reference", "metric": "voice-samples/sec", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -167,33 +169,57 @@ def workload_config():
 
 # --------------------------------------------------------------------------- native arm
 def cpu_baseline_sample():
+    """The reference's pdm2_update inside the v2 ISR (oracle/_ref) on the host cores: all cores at -O2 (the value), plus one
+    core, and the -O3 -march=x86-64-v3 build on all cores and on one.  The duty buffer is preallocated."""
     import numpy as np
     from oracle import pyoracle as po
-    po.set_threads(os.cpu_count() or 1)
+    cores = os.cpu_count() or 1
     kind = "reference"
     try:
         lib = po.Ref()
     except Exception:
         lib = po.Oracle()
         kind = "port"
-    cores = os.cpu_count() or 1
+    lib_o3 = None
+    try:
+        if kind == "reference" and os.path.exists(po.REF_O3_SO):
+            lib_o3 = po.Ref(po.REF_O3_SO)
+    except Exception:
+        lib_o3 = None
     n_ch = 3 * 2048 * max(1, cores // 8)
     ticks = 64 * 1024
-    chan = np.zeros((n_ch, 7), np.uint32)
-    prng = (np.arange(n_ch // 3) + 1).astype(np.uint32)
-    sp = po.pdm_setpoints(n_ch, 64)
-    count = 0
-    _, count = lib.pdm_v2_run(chan, 2, n_ch, 3, prng, None, 0x3FF, count, CTL_LOG, 24, sp[:16], ticks)   # warm, calibrate
-    t0 = time.perf_counter()
-    _, count = lib.pdm_v2_run(chan, 2, n_ch, 3, prng, None, 0x3FF, count, CTL_LOG, 24, sp[:16], ticks)
-    rate = n_ch * ticks / (time.perf_counter() - t0)
-    reps = max(1, min(48, int(12.0 * rate / (n_ch * ticks))))      # about 12 s of CPU work
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        _, count = lib.pdm_v2_run(chan, 2, n_ch, 3, prng, None, 0x3FF, count, CTL_LOG, 24, sp[:16], ticks)
-    dt = time.perf_counter() - t0
-    return {"value": n_ch * ticks * reps / dt, "unit": "samples/s", "cores": cores, "kind": kind,
-            "sample": "%d ch x %d samples, all host threads (OpenMP)" % (n_ch, ticks * reps)}
+    sp = po.pdm_setpoints(n_ch, 16)
+    duty = np.zeros((n_ch, ticks), np.uint8)
+
+    def rate(l, threads, n, seconds):
+        po.set_threads(threads)
+        chan = np.zeros((n, 7), np.uint32)
+        prng = (np.arange(n // 3) + 1).astype(np.uint32)
+        spn = np.ascontiguousarray(sp[:, :n])
+        d = duty[:n]
+        count = 0
+        _, count = l.pdm_v2_run(chan, 2, n, 3, prng, None, 0x3FF, count, CTL_LOG, 24, spn, ticks, out=d)   # warm, first touch
+        t0 = time.perf_counter()
+        _, count = l.pdm_v2_run(chan, 2, n, 3, prng, None, 0x3FF, count, CTL_LOG, 24, spn, ticks, out=d)
+        r = n * ticks / (time.perf_counter() - t0)
+        reps = max(1, min(48, int(seconds * r / (n * ticks))))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            _, count = l.pdm_v2_run(chan, 2, n, 3, prng, None, 0x3FF, count, CTL_LOG, 24, spn, ticks, out=d)
+        return n * ticks * reps / (time.perf_counter() - t0), reps
+
+    v, reps = rate(lib, cores, n_ch, 10.0)                       # about 10 s of CPU work
+    one, _ = rate(lib, 1, 3 * 256, 2.0)
+    res = {"value": v, "unit": "samples/s", "cores": cores, "kind": kind,
+           "sample": "%d ch x %d samples, all host threads (OpenMP), gcc -O2, output buffer preallocated" % (n_ch, ticks * reps),
+           "one_core": {"value": one, "sample": "768 ch x %d samples, one thread, gcc -O2" % ticks}}
+    if lib_o3 is not None:
+        v3, _ = rate(lib_o3, cores, n_ch, 3.0)
+        one3, _ = rate(lib_o3, 1, 3 * 256, 2.0)
+        res["o3"] = {"value": v3, "one_core": one3,
+                     "flags": "-O3 -march=x86-64-v3 (not -march=native: the library is built where the reference sources are, not on this box)"}
+    po.set_threads(cores)
+    return res
 
 
 def run_native(args, rank, local_rank, world):
@@ -314,11 +340,14 @@ def run_native(args, rank, local_rank, world):
         sm_hz = (clocks["sm_mhz"] or 1965) * 1e6
         issue_peak = 128.0 * 148 * sm_hz
         issue_ach = ALGO_INSTR_PER_SAMPLE * N_CH * F_CHUNK / (launch_ms * 1e-3)
-        traffic = None
+        traffic, traffic_src, executed = None, None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("k_pdm_v2_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("k_pdm_v2_bytes_per_launch")
+                traffic_src = tj.get("source")
+                executed = tj.get("k_pdm_v2_thread_instr_per_sample")
             except Exception:
                 traffic = None
         line = {
@@ -330,30 +359,36 @@ def run_native(args, rank, local_rank, world):
                     "h2d_bytes_per_step": e2e_rows * N_CH * 4, "d2h_bytes_per_step": N_CH * E2E_TICKS,
                     "sample": "65,536 ch x 1 Mi samples per step per GPU via cproc_cuda_run_stream (pinned ring of 4 x %d MiB)" % (N_CH * E2E_CHUNK >> 20),
                     "cpu_affinity": numa,
-                    "steps": e2e_steps, "seconds_per_rank": [round(x, 4) for x in e2e_ranks]},
+                    "steps": e2e_steps, "seconds_per_rank": [round(x, 4) for x in e2e_ranks],
+                    "d2h_gbs_per_rank": [round(N_CH * E2E_TICKS * e2e_steps / x / 1e9, 2) for x in e2e_ranks]},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_pdm_v2_ws3<K=2,B=3,FORM=1,P=2,NS=2>",
-                         "launch_ms": launch_ms, "algorithmic_bytes_per_launch": algo_bytes,
-                         "issue": {"achieved_tinstr_s": issue_ach / 1e12, "peak_tinstr_s": issue_peak / 1e12,
-                                   "frac": issue_ach / issue_peak,
-                                   "note": "SURVEY 8d: C2 is INT-issue bound; 10 algorithmic int instr per sample vs "
-                                           "128 thread-instr/clk/SM (measured, tools/ubench_int.cu) at the observed SM clock"}},
+            # The kernel is bound by integer instruction issue (two half-rate pipes shared by ~4 warps per scheduler), not by
+            # HBM: the roofline is stated against the issue peak at the observed SM clock, the HBM figure rides along.
+            "roofline": {"bound": "issue", "achieved": issue_ach / 1e12, "peak": issue_peak / 1e12, "unit": "T thread-instr/s",
+                         "frac": issue_ach / issue_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "k_pdm_v2_ws4<K=2,CW=3,TLOG=7,PL=0>", "launch_ms": launch_ms,
+                         "algorithmic_instr_per_sample": ALGO_INSTR_PER_SAMPLE,
+                         "executed_thread_instr_per_sample": executed,
+                         "note": "SURVEY 8d: C2 is INT-issue bound; 10 algorithmic int instr per sample against 128 thread-instr/clk/SM "
+                                 "(measured, tools/ubench_int.cu) at the observed SM clock; traffic = ncu dram bytes per launch of the same kernel",
+                         "hbm": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                                 "algorithmic_bytes_per_launch": algo_bytes}},
         }
         if world == 1:
             line["cpu_baseline"] = cpu_baseline_sample()
     batch.free()
-    mix_bus = None
-    if world > 1 and not args.no_other_configs:
-        # the one exchange step of the path, outside every timed region above; all ranks take part
+    scaling = None
+    if not args.no_other_configs:
+        # the configurations that shard over the GPUs of a box (C4', C4, C3b with the mix bus exchange, C5 without), at this N,
+        # strong scaling, outside every timed region above; all ranks take part
         try:
             from tools import bench_configs
-            mix_bus = bench_configs.mix_bus_scaling(st, ctx, torch, dist, stream, dev, rank, world)
+            scaling = bench_configs.scaling_rows(st, ctx, torch, stream, dev, rank, world, dist if world > 1 else None)
         except Exception as e:
-            mix_bus = {"error": "%s: %s" % (type(e).__name__, e)}
+            scaling = [{"error": "%s: %s" % (type(e).__name__, e)}]
     if rank == 0:
-        if mix_bus is not None:
-            line["mix_bus"] = mix_bus
+        if scaling is not None:
+            line["scaling_configs"] = scaling
         if world == 1 and not args.no_other_configs:
             # the other BASELINE.json configurations at full size (parity-test cases; reported for the
             # raw-output >= 70 % HBM / mixed-down >= 60 % issue targets), outside every timed region above

@@ -59,6 +59,91 @@ def _issue(name, units, unit_name, ms, instr_per_unit, note):
             "algorithmic_instr_per_unit": instr_per_unit, "note": note}
 
 
+# --------------------------------------------------------------------------- CPU baselines
+# The reference's own loops (oracle/_ref, kind "reference": compiled here from /root/reference by oracle/build_ref.sh) or,
+# where the processor is an extension or the reference code is ARM assembly, the oracle port (kind "port"), timed on this
+# box's host cores on a bounded sample of the row's workload (about 1 s of CPU work each).  Reported beside the GPU
+# number; not the optimisation target.
+def _cpu_time(fn, units, min_s=0.6):
+    import time
+    fn()                                           # warm: page in, first touch
+    reps, dt = 0, 0.0
+    t0 = time.perf_counter()
+    while dt < min_s and reps < 50:
+        fn(); reps += 1
+        dt = time.perf_counter() - t0
+    return units * reps / dt
+
+
+def cpu_baselines():
+    """name -> {"value", "unit", "cores", "kind", "sample"} for every row of run_all."""
+    from oracle import pyoracle as po
+    cores = os.cpu_count() or 1
+    po.set_threads(cores)
+    orc = po.Oracle()
+    try:
+        ref = po.Ref()
+    except Exception:
+        ref = None
+    rng = np.random.default_rng(11)
+    out = {}
+
+    def put(name, value, unit, used, kind, sample):
+        out[name] = {"value": value, "unit": unit, "cores": used, "kind": kind, "sample": sample}
+
+    # C1 / bp5 / C1 long: the generated graphs (generic/cproc.h acc_update / edge_update behind ref_graph_run: serial)
+    lib, kind = (ref, "reference") if ref else (orc, "port")
+    for name, rows in (("c1", po.GRAPH_TEST_CPROC), ("graph_bp5", po.GRAPH_BP5)):
+        N, F = 4096, 256
+        inp = rng.integers(0, 2, (N, 1, F), dtype=np.uint32)
+        stt = np.zeros((N, sum(po.node_words(r[0]) for r in rows)), np.uint32)
+        v = _cpu_time(lambda: lib.graph_run(rows, 1, len(rows) - 1, stt, N, F, inp), N * F)
+        put(name, v, "ticks/s", 1 if kind == "reference" else cores, kind, "%d instances x %d ticks (cproc.h acc_update / edge_update, one thread)" % (N, F))
+    out["c1_long"] = out["c1"]
+    # C2 v1: carry-bit PDM (ARM assembly in the reference: oracle port, OpenMP over banks)
+    N, F = 2048 * max(1, cores // 8), 16384
+    ch = np.zeros((N, 2), np.uint32); ch[:, 0] = rng.integers(0x40000000, 0xC0000000, N, dtype=np.uint32)
+    pr = (np.arange(N // 2) + 1).astype(np.uint32)
+    v = _cpu_time(lambda: orc.pdm_v1_run(ch, N, 2, pr, None, 0x0FFFFFFF, F), N * F)
+    put("c2_v1", v, "samples/s", cores, "port", "%d channels x %d ticks, banks of 2 (restated adds / rrx of mod_pdm.c:214-244), OpenMP" % (N, F))
+    # C3a: square_grain_proc itself
+    N, F = 4096 * max(1, cores // 8), 256
+    inp = rng.uniform(-1, 1, (N, F)).astype(np.float32); th = rng.uniform(0.05, 0.5, N).astype(np.float32)
+    stt = np.zeros(N, np.float32); o = np.zeros((N, F), np.float32)
+    v = _cpu_time(lambda: lib.square_grain_run(stt, th, N, F, inp, out=o), N * F)
+    put("c3a", v, "grain-samples/s", cores, kind, "%d grains x %d frames (square_grain_proc, synth_tools.c:85-100), OpenMP over grains" % (N, F))
+    # C3b: phasor -> trigger -> integer mix (oracle port, one thread: the mix is a serial sum)
+    N, F = 16384, 256
+    s0 = np.zeros(N, np.float32); ph = rng.integers(0, 2**32, N, dtype=np.uint32); inc = note_incs(rng, N, 36, 97)
+    gl = rng.integers(0, 65, N).astype(np.uint8); gr = (64 - gl).astype(np.uint8)
+    v = _cpu_time(lambda: orc.square_grain_mix_run(s0, th[:1].repeat(N), ph, inc, gl, gr, N, F), N * F)
+    put("c3b", v, "grain-samples/s", 1, "port", "%d grains x %d frames, one thread" % (N, F))
+    # C4: extension voice (oracle port, one thread)
+    N, F = 4096, 512
+    sx = np.zeros(N, po.xvoice_state_dtype); px = np.zeros(N, po.xvoice_param_dtype)
+    px["inc"] = note_incs(rng, N); px["f"] = 0.1; px["q"] = 1.0; px["env_attack"] = 0.01; px["env_release"] = 0.001; px["gate_frames"] = 200
+    px["gl"] = 0.5; px["gr"] = 0.5
+    v = _cpu_time(lambda: orc.xvoice_run(sx, px, N, F, want_raw=False), N * F)
+    put("c4", v, "voice-samples/s", 1, "port", "%d voices x %d frames, stereo mix, one thread" % (N, F))
+    vr = _cpu_time(lambda: orc.xvoice_run(sx, px, N, F, want_mix=False), N * F)
+    put("c5", vr, "variant-frames/s", 1, "port", "%d variants x %d frames, raw stereo out, one thread (sequential in time)" % (N, F))
+    # C4': synth_run / sum_tick_saw of linux/synth.c:169-202, 64-voice synths
+    NS, F = 2048 * max(1, cores // 8), 512
+    vv = np.zeros((NS * 64, 2), np.uint32); vv[:, 0] = note_incs(rng, NS * 64); vv[:, 1] = rng.integers(0, 2**32, NS * 64, dtype=np.uint32)
+    if ref:
+        v = _cpu_time(lambda: ref.voice_bank_run(vv, NS, 0, F), NS * 64 * F)
+        put("c4p", v, "voice-samples/s", cores, "reference", "%d synths x 64 voices x %d frames (synth_run), OpenMP over synths" % (NS, F))
+    else:
+        v = _cpu_time(lambda: orc.voice_bank_run(vv, NS * 64, 64, 0, F), NS * 64 * F)
+        put("c4p", v, "voice-samples/s", cores, "port", "%d synths x 64 voices x %d frames, OpenMP over synths" % (NS, F))
+    # pdm2_update on an input stream
+    N, F = 2048 * max(1, cores // 8), 4096
+    inp = rng.integers(0, 2**32, (N, F), dtype=np.uint32); stt = np.zeros((N, 2), np.uint32)
+    v = _cpu_time(lambda: lib.pdm_run(2, stt, N, F, inp, None, 24, None), N * F)
+    put("pdm_raw", v, "samples/s", cores, kind, "%d channels x %d samples (pdm2_update, pdm.h:32-40), OpenMP over channels" % (N, F))
+    return out
+
+
 def c1(st, ctx):
     """BASELINE.json configs[0]: the linux/test_cproc.c chain (edge -> acc), 1 voice, 64-frame blocks,
     750 blocks (1 s at 48 kHz) through the host-buffer call a JACK period makes: latency, not throughput."""
@@ -164,57 +249,265 @@ def c5(st, ctx, hbm_peak, reps=3, layout="tiled"):
                 "timed region = envelope walk + closed-form zero-state pass + scan + render")
 
 
-def mix_bus_scaling(st, ctx, torch, dist, stream, dev, rank, world, reps=40):
-    """BASELINE.json config 4 at N > 1: 4 Mi reference voices x 512-frame blocks sharded over the ranks,
-    the int32 mix bus formed (a) by NCCL all-reduce + conversion kernel, (b) by the one-kernel
-    peer-memory bus overlapped with the next block's render.  Strong scaling (total work fixed).
-    Device time, max over ranks."""
+def scaling_rows(st, ctx, torch, stream, dev, rank, world, dist=None):
+    """The BASELINE.json configurations that shard over the GPUs of a box, at N = `world` (1 included, so that the per-N
+    lines of a scaling run carry their own 1-GPU denominator).  STRONG scaling: the total work is fixed (4 Mi voices,
+    1 Mi grains, 16,384 variants) and split in contiguous shards.  C4', C4, C3b end in the shared mix bus (the only
+    exchange of the path); C5 has none.  Device time (CUDA events on the render stream), max over ranks.  Every mix is
+    checked on rank 0 against the single-device oracle (integer buses bit for bit, the float bus within the stated
+    tolerance and identical on all ranks)."""
     from synth_tools_b200 import shard
-    rng = np.random.default_rng(99)
-    N, F = 4 * 1024 * 1024, 512
-    lo, hi = shard.shard_range(N, rank, world)
-    v = np.zeros((hi - lo, 2), np.uint32)
-    v[:, 0] = note_incs(rng, hi - lo, 0, 128); v[:, 1] = rng.integers(0, 2**32, hi - lo, dtype=np.uint32)
-    b = ctx.batch(st.VOICE_BANK, hi - lo, voices_per_bus=0)
-    b.upload_state(v)
-    imix = [torch.zeros(F, dtype=torch.int32, device=dev) for _ in range(2)]
-    out = [torch.zeros(F, dtype=torch.float32, device=dev) for _ in range(2)]
-    bus = shard.connect_bus(st.Bus(ctx, 4096, world, rank))
-    k = [0]
+    from oracle import pyoracle as po
+    orc = po.Oracle()
+    po.set_threads(os.cpu_count() or 1)
+    rows = []
 
-    def nccl():
-        b.run_dev(F, mix=imix[0].data_ptr())
-        dist.all_reduce(imix[0])
-        b.mix_to_float(imix[0].data_ptr(), out[0].data_ptr(), F)
-
-    def peer():
-        s = k[0] & 1
-        k[0] += 1
-        bus.wait(s)
-        b.run_dev(F, mix=imix[s].data_ptr())
-        bus.begin(s, imix[s].data_ptr(), F, out_dev=out[s].data_ptr(), scale=st.Bus.SCALE_SAW)
-
-    res = {}
-    for name, fn in (("nccl_allreduce_plus_convert", nccl), ("peer_memory_bus_overlapped", peer)):
-        for _ in range(5):
+    def timed(fn, reps, after=None):
+        for _ in range(3):
             fn()
-        dist.barrier(); torch.cuda.synchronize()
+        if after:
+            after()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(reps):
             fn()
-        bus.wait(0); bus.wait(1)
+        if after:
+            after()
         e1.record(stream)
-        dist.barrier(); torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        res[name] = float(t.item())
-    ok = bus.status() == 0
-    bus.destroy(); b.free()
-    return {"config": "C4' reference voice bank, 4 Mi voices x 512-frame blocks sharded over %d GPUs (strong scaling), int32 mix bus" % world,
-            "n_gpus": world, "bus_ok": ok, "ms_per_block": res,
-            "voice_samples_per_s": {kk: N * F / (vv * 1e-3) for kk, vv in res.items()},
-            "note": "bit-exactness of both bus forms against the single-device oracle: tools/multi_gpu_mix.py"}
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(flag):
+        t = torch.tensor([int(bool(flag))], device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    bus = shard.connect_bus(st.Bus(ctx, 8192, world, rank)) if world > 1 else None
+
+    # ---- C4': reference voice bank, int32 mix bus ------------------------------------------------------------------
+    try:
+        N, F = 4 * 1024 * 1024, 512
+        rng = np.random.default_rng(99)
+        v = np.zeros((N, 2), np.uint32)
+        v[:, 0] = note_incs(rng, N, 0, 128); v[:, 1] = rng.integers(0, 2**32, N, dtype=np.uint32)
+        lo, hi = shard.shard_range(N, rank, world)
+        b = ctx.batch(st.VOICE_BANK, hi - lo, voices_per_bus=0)
+
+        def oracle_blocks(n_frames):                      # 64 pseudo-buses in parallel, integer wrap-around sum of the rows: exact
+            w = v.copy()
+            isum, _ = orc.voice_bank_run(w, N, N // 64, 0, n_frames, want_vec=False)
+            tot = isum.view(np.uint32).sum(axis=0, dtype=np.uint64).astype(np.uint32)
+            return tot.view(np.int32), (tot.view(np.int32).astype(np.float32) * np.float32(2.0 ** -32))
+
+        want_i, want_f = oracle_blocks(4 * F) if rank == 0 else (None, None)
+        res, exact = {}, {}
+        imix = [torch.zeros(4 * F, dtype=torch.int32, device=dev) for _ in range(2)]
+        out = [torch.zeros(4 * F, dtype=torch.float32, device=dev) for _ in range(2)]
+        k = [0]
+
+        def check(name, frames, blocks):
+            """render `blocks` launches of `frames` from the initial state and compare the concatenation with the oracle"""
+            b.upload_state(np.ascontiguousarray(v[lo:hi]))
+            gi = [torch.zeros(frames, dtype=torch.int32, device=dev) for _ in range(blocks)]
+            go = [torch.zeros(frames, dtype=torch.float32, device=dev) for _ in range(blocks)]
+            for q in range(blocks):
+                if name == "nccl":
+                    b.run_dev(frames, mix=gi[q].data_ptr())
+                    if dist is not None:
+                        dist.all_reduce(gi[q])
+                    b.mix_to_float(gi[q].data_ptr(), go[q].data_ptr(), frames)
+                else:
+                    b.run_dev(frames, mix=gi[q].data_ptr(), out=go[q].data_ptr())
+            if bus is not None:
+                bus.flush()
+            torch.cuda.synchronize()
+            ok = True
+            if rank == 0:
+                ci = torch.cat(gi).cpu().numpy(); co = torch.cat(go).cpu().numpy()
+                ok = np.array_equal(ci, want_i[:frames * blocks]) and np.array_equal(co.view(np.uint32), want_f[:frames * blocks].view(np.uint32))
+            return all_ok(ok and (bus is None or bus.status() == 0))
+
+        def block(frames):
+            def fn():
+                s_ = k[0] & 1
+                k[0] += 1
+                b.run_dev(frames, mix=imix[s_].data_ptr(), out=out[s_].data_ptr())
+            return fn
+
+        def block_nccl():
+            b.run_dev(F, mix=imix[0].data_ptr())
+            dist.all_reduce(imix[0][:F])
+            b.mix_to_float(imix[0].data_ptr(), out[0].data_ptr(), F)
+
+        variants = [("one 512-frame block per launch, exchange inside the launch", 1, F, 4), ("one 512-frame block per launch, exchange pipelined beside the next launch", 2, F, 4),
+                    ("four 512-frame blocks per launch, exchange pipelined", 2, 4 * F, 1)]
+        for name, mode, frames, blocks in variants:
+            if bus is not None:
+                bus.attach(b, mode)
+            exact[name] = check(name, frames, blocks)
+            res[name] = timed(block(frames), 40, after=(bus.flush if bus is not None else None)) * F / frames
+        if bus is not None:
+            bus.detach(b)
+            exact["NCCL all-reduce + conversion kernel (baseline)"] = check("nccl", F, 2)
+            res["NCCL all-reduce + conversion kernel (baseline)"] = timed(block_nccl, 40)
+        b.free()
+        rows.append({"config": "C4' reference voice bank (sum_tick_saw, linux/synth.c:169-181), 4 Mi voices x 512-frame blocks over %d GPU%s, int32 mix bus" % (world, "s" if world > 1 else ""),
+                     "n_gpus": world, "scaling": "strong", "unit": "voice-samples/s", "ms_per_512_frame_block": res,
+                     "value": {kk: N * F / (vv * 1e-3) for kk, vv in res.items()}, "bit_exact": exact,
+                     "note": "the bus of ALL ranks (int32 words and the float scale) compared with the single-device oracle on rank 0; "
+                             "1 GPU: the same launches without a bus"})
+    except Exception as e:
+        rows.append({"config": "C4'", "error": "%s: %s" % (type(e).__name__, e)})
+
+    # ---- C4: extension voices, float stereo bus (rank-order float sum) ---------------------------------------------
+    try:
+        N, F, NC = 4 * 1024 * 1024, 512, 64 * 1024 + 5
+        rng = np.random.default_rng(5)
+        stt, prm = xvoice_records(rng, N)
+        # parity on a 64 Ki-voice subset against the oracle (float mix: tolerance; identical bits on all ranks)
+        lo, hi = shard.shard_range(NC, rank, world)
+        sa = np.ascontiguousarray(stt[:NC]).view(po.xvoice_state_dtype).reshape(NC).copy()
+        pa = np.ascontiguousarray(prm[:NC]).view(po.xvoice_param_dtype).reshape(NC)
+        _, want = orc.xvoice_run(sa, pa, NC, F, want_raw=False) if rank == 0 else (None, None)
+        b = ctx.batch(st.XVOICE, hi - lo)
+        b.upload_state(np.ascontiguousarray(stt[lo:hi])); b.upload_param(np.ascontiguousarray(prm[lo:hi]))
+        mix = torch.zeros(2 * F, dtype=torch.float32, device=dev)
+        if bus is not None:
+            bus.attach(b, 1)
+        b.run_dev(F, mix=mix.data_ptr())
+        torch.cuda.synchronize()
+        ok, same = True, True
+        if rank == 0:
+            g64, w64 = mix.cpu().numpy().astype(np.float64), np.asarray(want, np.float64).reshape(-1)
+            ok = bool(np.abs(g64 - w64).max() <= 1e-5 * np.abs(w64).max() and
+                      10 * np.log10((w64 ** 2).sum() / max(((g64 - w64) ** 2).sum(), 1e-300)) >= 120.0)
+        if dist is not None:
+            allmix = [torch.empty_like(mix) for _ in range(world)]
+            dist.all_gather(allmix, mix)
+            same = all(torch.equal(allmix[0], m) for m in allmix)
+        if bus is not None:
+            bus.detach(b)
+        b.free()
+        lo, hi = shard.shard_range(N, rank, world)
+        b = ctx.batch(st.XVOICE, hi - lo)
+        b.upload_state(np.ascontiguousarray(stt[lo:hi])); b.upload_param(np.ascontiguousarray(prm[lo:hi]))
+        mixes = [torch.zeros(2 * F, dtype=torch.float32, device=dev) for _ in range(2)]
+        k = [0]
+
+        def xblock():
+            s_ = k[0] & 1
+            k[0] += 1
+            b.run_dev(F, mix=mixes[s_].data_ptr())
+
+        def xnccl():
+            b.run_dev(F, mix=mixes[0].data_ptr())
+            dist.all_reduce(mixes[0])
+
+        res = {}
+        for name, mode in (("exchange inside the launch", 1), ("exchange pipelined beside the next launch", 2)):
+            if bus is not None:
+                bus.attach(b, mode)
+            res[name] = timed(xblock, 10, after=(bus.flush if bus is not None else None))
+        if bus is not None:
+            bus.detach(b)
+            res["NCCL all-reduce (baseline)"] = timed(xnccl, 10)
+        b.free()
+        rows.append({"config": "C4 poly voice (phasor + SVF + AR envelope + pan), 4 Mi voices x 512-frame blocks over %d GPU%s, float stereo mix bus" % (world, "s" if world > 1 else ""),
+                     "n_gpus": world, "scaling": "strong", "unit": "voice-samples/s", "ms_per_512_frame_block": res,
+                     "value": {kk: N * F / (vv * 1e-3) for kk, vv in res.items()},
+                     "within_tolerance": all_ok(ok), "identical_bits_on_all_ranks": all_ok(same),
+                     "note": "parity on a %d-voice subset: <= 1e-5 of peak and >= 120 dB SNR against the C oracle; the bus is a float sum in rank order" % NC})
+    except Exception as e:
+        rows.append({"config": "C4", "error": "%s: %s" % (type(e).__name__, e)})
+
+    # ---- C3b: square_grain mix, integer bus in units of 2^-7 --------------------------------------------------------
+    try:
+        N, F = 1024 * 1024, 256
+        rng = np.random.default_rng(4)
+        s_rec = np.zeros((N, 2), np.uint32); s_rec[:, 1] = rng.integers(0, 2**32, N, dtype=np.uint32)
+        p_rec = np.zeros((N, 4), np.uint32)
+        th = rng.uniform(0.05, 0.5, N).astype(np.float32)
+        p_rec[:, 0] = th.view(np.uint32); p_rec[:, 1] = note_incs(rng, N, 36, 97)
+        gl = rng.integers(0, 65, N); p_rec[:, 2] = gl; p_rec[:, 3] = 64 - gl
+        lo, hi = shard.shard_range(N, rank, world)
+        b = ctx.batch(st.SQUARE_GRAIN_MIX, hi - lo)
+        b.upload_state(np.ascontiguousarray(s_rec[lo:hi])); b.upload_param(np.ascontiguousarray(p_rec[lo:hi]))
+        imix = [torch.zeros(2 * F, dtype=torch.int32, device=dev) for _ in range(2)]
+        out = [torch.zeros(2 * F, dtype=torch.float32, device=dev) for _ in range(2)]
+        # block 0 against the oracle
+        b.run_dev(F, out=out[0].data_ptr(), mix=imix[0].data_ptr())
+        if bus is not None:
+            bus.allreduce(imix[0].data_ptr(), 2 * F, out_dev=out[0].data_ptr(), scale=st.Bus.SCALE_GRAIN)
+        torch.cuda.synchronize()
+        ok = True
+        if rank == 0:
+            wi, wf = orc.square_grain_mix_run(np.zeros(N, np.float32), th, s_rec[:, 1].copy(), p_rec[:, 1].copy(), gl.astype(np.uint8), (64 - gl).astype(np.uint8), N, F)
+            ok = np.array_equal(imix[0].cpu().numpy().reshape(2, F), wi) and np.array_equal(out[0].cpu().numpy().reshape(2, F).view(np.uint32), wf.view(np.uint32))
+        k = [0]
+
+        def gblock():
+            s_ = k[0] & 1
+            k[0] += 1
+            if bus is not None:
+                bus.wait(s_)
+            b.run_dev(F, out=out[s_].data_ptr(), mix=imix[s_].data_ptr())
+            if bus is not None:
+                bus.begin(s_, imix[s_].data_ptr(), 2 * F, out_dev=out[s_].data_ptr(), scale=st.Bus.SCALE_GRAIN)
+
+        def gafter():
+            if bus is not None:
+                bus.wait(0); bus.wait(1)
+
+        ms = timed(gblock, 20, after=gafter)
+        b.free()
+        rows.append({"config": "C3b square_grain phasor -> trigger -> stereo integer mix, 1 Mi grains x 256-frame blocks over %d GPU%s" % (world, "s" if world > 1 else ""),
+                     "n_gpus": world, "scaling": "strong", "unit": "grain-samples/s", "ms_per_block": ms, "value": N * F / (ms * 1e-3),
+                     "bit_exact": all_ok(ok and (bus is None or bus.status() == 0)),
+                     "note": "exchange: the bus kernel over NVLink peer memory on its own stream, overlapped with the next block's render"})
+    except Exception as e:
+        rows.append({"config": "C3b", "error": "%s: %s" % (type(e).__name__, e)})
+    if bus is not None:
+        bus.destroy()
+
+    # ---- C5: patch sweep, 16,384 variants x 480,000 frames raw stereo out, no collective -------------------------------
+    try:
+        NV, F, SH = 16384, 480000, 2048
+        lo, hi = shard.shard_range(NV, rank, world)
+        rng = np.random.default_rng(7)
+        stt, prm = xvoice_records(rng, NV)
+        d_out = ctx.dev_alloc(8 * SH * F)
+        batches = []
+        for a in range(lo, hi, SH):
+            e = min(hi, a + SH)
+            bb = ctx.batch(st.XVOICE, e - a, layout=st.TILED, mode=st.XVOICE_SCAN)
+            bb.upload_state(np.ascontiguousarray(stt[a:e])); bb.upload_param(np.ascontiguousarray(prm[a:e]))
+            batches.append(bb)
+
+        def sweep():
+            for bb in batches:
+                bb.run_dev(F, out=d_out)
+
+        ms = timed(sweep, 2)
+        for bb in batches:
+            bb.free()
+        ctx.dev_free(d_out)
+        rows.append({"config": "C5 patch sweep, 16,384 variants x 480,000 frames (10 s @ 48 kHz) stereo float raw out over %d GPU%s, TILED, time-parallel scan" % (world, "s" if world > 1 else ""),
+                     "n_gpus": world, "scaling": "strong", "unit": "variant-frames/s", "ms": ms, "value": NV * F / (ms * 1e-3),
+                     "variants_per_gpu": hi - lo, "launch_shards_per_gpu": len(batches), "collective": None,
+                     "achieved_gbs_per_gpu": 8.0 * (hi - lo) * F / ms / 1e6,
+                     "note": "independent variants: no exchange; each GPU renders its variants in shards of 2,048 (7.86 GB of output each, the slab is reused); parity: tests/test_gpu_fullsize.py"})
+    except Exception as e:
+        rows.append({"config": "C5", "error": "%s: %s" % (type(e).__name__, e)})
+    return rows
 
 
 def graph_bp5(st, ctx, hbm_peak, reps=3, layout="planar"):
@@ -268,14 +561,24 @@ def c1_long(st, ctx, reps=3):
 
 
 def run_all(st, ctx, hbm_peak):
+    try:
+        cpu = cpu_baselines()
+    except Exception as e:
+        cpu = {"error": "%s: %s" % (type(e).__name__, e)}
     rows = []
-    for fn in (lambda: c1(st, ctx), lambda: c2_v1(st, ctx), lambda: c3a(st, ctx, hbm_peak, layout="planar"), lambda: c3a(st, ctx, hbm_peak, layout="interleaved"),
-               lambda: c3b(st, ctx), lambda: c4(st, ctx), lambda: c4p(st, ctx),
-               lambda: c5(st, ctx, hbm_peak, layout="tiled"), lambda: c5(st, ctx, hbm_peak, layout="planar"),
-               lambda: graph_bp5(st, ctx, hbm_peak, layout="planar"), lambda: graph_bp5(st, ctx, hbm_peak, layout="interleaved"),
-               lambda: pdm_raw(st, ctx, hbm_peak), lambda: c1_long(st, ctx)):
+    for key, fn in (("c1", lambda: c1(st, ctx)), ("c2_v1", lambda: c2_v1(st, ctx)), ("c3a", lambda: c3a(st, ctx, hbm_peak, layout="planar")),
+                    ("c3a", lambda: c3a(st, ctx, hbm_peak, layout="interleaved")),
+                    ("c3b", lambda: c3b(st, ctx)), ("c4", lambda: c4(st, ctx)), ("c4p", lambda: c4p(st, ctx)),
+                    ("c5", lambda: c5(st, ctx, hbm_peak, layout="tiled")), ("c5", lambda: c5(st, ctx, hbm_peak, layout="planar")),
+                    ("graph_bp5", lambda: graph_bp5(st, ctx, hbm_peak, layout="planar")), ("graph_bp5", lambda: graph_bp5(st, ctx, hbm_peak, layout="interleaved")),
+                    ("pdm_raw", lambda: pdm_raw(st, ctx, hbm_peak)), ("c1_long", lambda: c1_long(st, ctx))):
         try:
-            rows.append(fn())
+            row = fn()
+            if key in cpu:
+                row["cpu_baseline"] = cpu[key]
+            elif "error" in cpu:
+                row["cpu_baseline"] = cpu
+            rows.append(row)
         except Exception as e:                       # never lose the headline line over a secondary row
             rows.append({"error": "%s: %s" % (type(e).__name__, e)})
     return rows
