@@ -277,6 +277,19 @@ typedef void (*cproc_cuda_chunk_fn)(void *user, uint64_t chunk_index, const void
 int  cproc_cuda_run_stream(cproc_cuda_batch *b, uint64_t n_frames_total,
                            uint64_t n_frames_chunk, const cproc_cuda_io *io,
                            uint32_t ring_chunks, cproc_cuda_chunk_fn on_chunk, void *user);
+/* Evented driver of a GRAPH batch == handle_tag_u32 of stm32f103/mod_cproc_plugin.c:24-38,
+ *     cproc_input[i] = v; cproc_update(cproc_input, -1);
+ * The batch keeps the reference's persistent `w cproc_input[CPROC_NB_INPUTS]` (:20) per instance,
+ * zero when the batch is allocated.  _set_input writes input[i] of one instance, or of every
+ * instance when instance == CPROC_CUDA_ALL_INSTANCES; i >= n_inputs returns CPROC_CUDA_EINVAL
+ * where the reference returns -1 (:29,35-36).  _tick runs ONE tick of every instance on those
+ * inputs under the `changed` mask (-1 in the reference, :32) and copies the values handed to
+ * cproc_output() to out: uint32 [inst][n_outputs] (out may be NULL).  _event is the two in one
+ * call for a single instance: what one TAG_U32 message [i, v] does; out: uint32 [n_outputs]. */
+#define CPROC_CUDA_ALL_INSTANCES (~(uint64_t)0)
+int  cproc_cuda_graph_set_input(cproc_cuda_batch *b, uint64_t instance, uint32_t i, uint32_t v);
+int  cproc_cuda_graph_tick(cproc_cuda_batch *b, uint32_t changed, uint32_t *out);
+int  cproc_cuda_graph_event(cproc_cuda_batch *b, uint64_t instance, uint32_t i, uint32_t v, uint32_t *out);
 /* Graph batches are compiled for their node table with NVRTC when first run (one
  * kernel per graph: node states in registers, sources and masks as literals).  The
  * compiler log (warnings, or the reason the table-driven kernel is used instead) and

@@ -40,8 +40,11 @@ gcc $CFLAGS -fno-semantic-interposition -I"$HERE/shim/stm32" -I"$REF/stm32f103" 
 # (7) stm32f103/mod_pdm.c:159-175 (pwm_update and the globals it works on)
 ( echo '#include <stdint.h>'; sed -n 159,175p "$REF/stm32f103/mod_pdm.c"; cat "$HERE/ref/ref_pwm_tail.c" ) \
   | gcc $CFLAGS -Dcontrol_div_count=ref_pwm_control_div_count -x c -c - -o "$OBJ/ref_pwm.o"   # (:165 also defines the v1 divider; mod_pdm_pwm.c has its own)
+# (8) stm32f103/pixi.c:279,282-285 (the PIXI demo LFO bank: inc = adc[0] >> 5; dac = (dac + inc) & 0xFFF)
+( cat "$HERE/ref/ref_pixi_pre.h"; sed -n '279p;282,285p' "$REF/stm32f103/pixi.c"; cat "$HERE/ref/ref_pixi_tail.c" ) \
+  | gcc $CFLAGS -x c -c - -o "$OBJ/ref_pixi.o"
 gcc -shared -fopenmp -o "$HERE/_ref/$OUT" "$OBJ/ref_cproc.o" "$OBJ/test_cproc.o" "$OBJ/ref_pdm.o" "$OBJ/ref_synth.o" "$OBJ/ref_grain.o" \
-    "$OBJ/ref_v2_isr.o" "$OBJ/ref_clock.o" "$OBJ/ref_pwm.o" -lm
+    "$OBJ/ref_v2_isr.o" "$OBJ/ref_clock.o" "$OBJ/ref_pwm.o" "$OBJ/ref_pixi.o" -lm
 rm -rf "$OBJ"
 echo "built $HERE/_ref/$OUT ($OPT)"
 }

@@ -282,6 +282,13 @@ class Ref(_Lib):
         self._fn("synth_play", None, [VP, C.c_int, C.c_uint64, VP, VP])(_ptr(notes), len(notes), F, _ptr(vec), _ptr(voices))
         return vec, voices
 
+    def pixi_lfo_run(self, dac, adc0, ticks):
+        """stm32f103/pixi.c:279,282-285 itself: `ticks` timer interrupts of the demo LFO bank.  dac uint16 [12] in/out;
+        returns the DAC values after each tick, uint16 [ticks][12]."""
+        trace = np.zeros((ticks, 12), np.uint16)
+        self._fn("pixi_lfo_run", None, [VP, C.c_uint16, C.c_uint64, VP])(_ptr(dac), adc0, ticks, _ptr(trace))
+        return trace
+
     def grain_sizeof(self):
         return self._fn("grain_sizeof", C.c_uint32, [])()
 

@@ -126,6 +126,9 @@ SYMBOLS = {
     "cproc_cuda_bus_destroy": (C.c_int, [C.c_void_p]),
     "cproc_cuda_graph_parse": (C.c_int, [C.c_char_p, C.POINTER(Node), C.c_uint32, C.POINTER(GraphInfo)]),
     "cproc_cuda_graph_jit_log": (C.c_char_p, [C.c_void_p]),
+    "cproc_cuda_graph_set_input": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]),
+    "cproc_cuda_graph_tick": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "cproc_cuda_graph_event": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]),
     "cproc_cuda_graph_jit_source": (C.c_int, [C.POINTER(Node), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.c_int, C.c_char_p, C.c_size_t]),
 }
 
@@ -354,6 +357,23 @@ class Batch:
             n_ctl = ctl.shape[0] if isinstance(ctl, np.ndarray) else 0
         io.n_ctl = n_ctl
         return io
+
+    # evented graph driver (handle_tag_u32 of stm32f103/mod_cproc_plugin.c:24-38)
+    def set_input(self, i, v, instance=None):
+        """cproc_input[i] = v for one instance (None: every instance)."""
+        self.ctx._ck(lib.cproc_cuda_graph_set_input(self.h, 0xFFFFFFFFFFFFFFFF if instance is None else instance, i, v))
+
+    def tick(self, changed=0xFFFFFFFF, n_outputs=1):
+        """cproc_update(cproc_input, changed) once per instance -> uint32 [inst][n_outputs]."""
+        out = np.zeros((self.n, n_outputs), np.uint32)
+        self.ctx._ck(lib.cproc_cuda_graph_tick(self.h, changed, _vp(out)))
+        return out
+
+    def event(self, instance, i, v, n_outputs=1):
+        """One TAG_U32 message [i, v] to one graph instance -> its cproc_output values."""
+        out = np.zeros(n_outputs, np.uint32)
+        self.ctx._ck(lib.cproc_cuda_graph_event(self.h, instance, i, v, _vp(out)))
+        return out
 
     def run(self, F, inp=None, in2=None, ctl=None, out=None, mix=None, layout=None, n_ctl=None):
         """Host buffers (numpy), synchronous."""

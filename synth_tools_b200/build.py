@@ -58,9 +58,16 @@ def build(force=False, verbose=False, ptxas_v=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
+    # m_pd.h present (PD_INCLUDE=<dir>, or a system Pd): the drop-in library also exports square_grain_proc under the
+    # reference's own name and prototype (linux/synth_tools.c:85-86); host/dropin.c, CPROC_HAVE_PD
+    pd_flags = []
+    for d in [os.environ.get("PD_INCLUDE"), "/usr/include", "/usr/include/pd", "/usr/local/include", "/usr/local/include/pd"]:
+        if d and os.path.exists(os.path.join(d, "m_pd.h")):
+            pd_flags = ["-DCPROC_HAVE_PD", "-I", d]
+            break
     host_srcs = sorted(os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".c")) if os.path.isdir(HOST) else []
     if host_srcs and (force or _newer(DROPIN, host_srcs + [LIB])):
-        cmd = ["gcc", "-std=gnu99", "-O2", "-fPIC", "-shared", "-Wall", "-I", os.path.join(ROOT, "include"),
+        cmd = ["gcc", "-std=gnu99", "-O2", "-fPIC", "-shared", "-Wall", "-I", os.path.join(ROOT, "include"), *pd_flags,
                *host_srcs, "-o", DROPIN, "-L", HERE, "-lcproc_cuda", "-Wl,-rpath,$ORIGIN"]
         if verbose:
             print(" ".join(cmd))

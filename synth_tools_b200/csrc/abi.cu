@@ -609,6 +609,64 @@ int cproc_cuda_run_stream(cproc_cuda_batch *b, uint64_t F_total, uint64_t F_chun
     return 0;
 }
 
+// ---- evented graph driver (mod_cproc_plugin.c:20-38) ---------------------------
+static int ev_check(cproc_cuda_batch *b, const char *who) {
+    if (!b) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "%s: batch is NULL", who);
+    if (b->cfg.proc != CPROC_CUDA_GRAPH) return cproc_set_err(b->ctx, CPROC_CUDA_EINVAL, "%s: not a graph batch", who);
+    if (b->ev_in.empty()) b->ev_in.assign((size_t)b->n * b->cfg.n_inputs, 0u);   // w cproc_input[CPROC_NB_INPUTS], static storage: zero
+    return 0;
+}
+
+int cproc_cuda_graph_set_input(cproc_cuda_batch *b, uint64_t instance, uint32_t i, uint32_t v) {
+    int rc;
+    if ((rc = ev_check(b, "graph_set_input"))) return rc;
+    if (i >= b->cfg.n_inputs) return cproc_set_err(b->ctx, CPROC_CUDA_EINVAL, "graph_set_input: input %u of %u", i, b->cfg.n_inputs);
+    if (instance == CPROC_CUDA_ALL_INSTANCES) { for (uint64_t k = 0; k < b->n; ++k) b->ev_in[(size_t)k * b->cfg.n_inputs + i] = v; return 0; }
+    if (instance >= b->n) return cproc_set_err(b->ctx, CPROC_CUDA_EINVAL, "graph_set_input: instance %llu of %llu", (unsigned long long)instance, (unsigned long long)b->n);
+    b->ev_in[(size_t)instance * b->cfg.n_inputs + i] = v;
+    return 0;
+}
+
+static int ev_tick(cproc_cuda_batch *b, const uint32_t *changed_rows, uint32_t *out) {
+    const uint32_t n_out = b->cfg.n_outputs ? b->cfg.n_outputs : 1;
+    b->ev_out.resize((size_t)b->n * n_out);
+    cproc_cuda_io io;
+    memset(&io, 0, sizeof(io));
+    io.in = b->ev_in.data();          // [inst][n_inputs][F = 1]
+    io.in2 = changed_rows;            // [inst][F = 1] or NULL (= -1)
+    io.out = b->ev_out.data();        // [inst][n_outputs][F = 1]
+    io.layout = CPROC_CUDA_PLANAR;
+    int rc = cproc_cuda_run(b, 1, &io);
+    if (rc) return rc;
+    if (out) memcpy(out, b->ev_out.data(), sizeof(uint32_t) * b->ev_out.size());
+    return 0;
+}
+
+int cproc_cuda_graph_tick(cproc_cuda_batch *b, uint32_t changed, uint32_t *out) {
+    int rc;
+    if ((rc = ev_check(b, "graph_tick"))) return rc;
+    if (changed == 0xFFFFFFFFu) return ev_tick(b, nullptr, out);
+    b->ev_chg.assign((size_t)b->n, changed);
+    return ev_tick(b, b->ev_chg.data(), out);
+}
+
+int cproc_cuda_graph_event(cproc_cuda_batch *b, uint64_t instance, uint32_t i, uint32_t v, uint32_t *out) {
+    int rc;
+    if ((rc = ev_check(b, "graph_event"))) return rc;
+    if (instance >= b->n) return cproc_set_err(b->ctx, CPROC_CUDA_EINVAL, "graph_event: instance %llu of %llu", (unsigned long long)instance, (unsigned long long)b->n);
+    if ((rc = cproc_cuda_graph_set_input(b, instance, i, v))) return rc;
+    const uint32_t n_out = b->cfg.n_outputs ? b->cfg.n_outputs : 1;
+    if (b->n == 1) rc = ev_tick(b, nullptr, nullptr);
+    else {                                                   // only the addressed graph ticks: the others see changed = 0
+        b->ev_chg.assign((size_t)b->n, 0u);
+        b->ev_chg[(size_t)instance] = 0xFFFFFFFFu;
+        rc = ev_tick(b, b->ev_chg.data(), nullptr);
+    }
+    if (rc) return rc;
+    if (out) memcpy(out, b->ev_out.data() + (size_t)instance * n_out, sizeof(uint32_t) * n_out);
+    return 0;
+}
+
 int cproc_cuda_mix_to_float(cproc_cuda_batch *b, const void *imix_dev, float *out_dev, uint64_t count) {
     if (!b || !imix_dev || !out_dev) return cproc_set_err(b ? b->ctx : nullptr, CPROC_CUDA_EINVAL, "mix_to_float: NULL argument");
     cproc_cuda_ctx *ctx = b->ctx;

@@ -92,6 +92,7 @@ struct cproc_cuda_batch {
     uint64_t n_flags = 0;
     unsigned long long epoch = 0;
     cproc_graph_jit jit[2];                        // [changed stream present]
+    std::vector<uint32_t> ev_in, ev_chg, ev_out;   // evented driver (cproc_cuda_graph_set_input / _tick): cproc_input[] per instance, changed, outputs
     std::string jit_log;
     // small host-buffer runs replayed as one CUDA graph (H2D copies, the kernels, D2H copies): abi.cu
     struct run_graph {

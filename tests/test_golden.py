@@ -210,3 +210,21 @@ def test_golden_restated_v1_and_pwm(be):
     ph = np.array([0, 0x123456], np.uint32)
     duty = be.pwm(ph, np.array([256 * 13, 5000], np.uint32), 256)
     assert np.array_equal(duty, G["restated_pwm_duty"]) and np.array_equal(ph, G["restated_pwm_phase"])
+
+
+G2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_r2.npz"))
+
+
+def test_golden_pixi_lfo_bank_is_acc_under_a_12_bit_mask(be):
+    """the PIXI demo LFO bank (stm32f103/pixi.c:279,282-285), `dac = (dac + inc) & 0xFFF` with
+    inc = adc[0] >> 5 on 12 uint16 channels, is the `acc` processor (cproc.h:134-142) read through a 12-bit
+    mask: (acc.out & 0xFFF) equals the reference's DAC values tick for tick, for every knob position."""
+    adc, dac0, trace, dac1 = G2["pixi_adc0"], G2["pixi_dac0"], G2["pixi_trace"], G2["pixi_dac1"]
+    K, T, D = trace.shape
+    N = K * D                                                # one acc instance per (knob position, DAC channel)
+    inc = np.repeat(adc.astype(np.uint32) >> 5, D)
+    inp = np.ascontiguousarray(np.broadcast_to(inc[:, None, None], (N, 1, T))).astype(np.uint32)
+    state = dac0.astype(np.uint32).reshape(N, 1).copy()
+    out = be.graph([(po.NODE_ACC, -1, 0xFFFFFFFF)], state, inp, None)
+    assert np.array_equal((out & 0xFFF).reshape(K, D, T).transpose(0, 2, 1), trace.astype(np.uint32))
+    assert np.array_equal((state[:, 0] & 0xFFF).reshape(K, D), dac1.astype(np.uint32))

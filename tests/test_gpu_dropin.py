@@ -60,6 +60,65 @@ def test_c_host_through_dropin_and_abi(tmp_path, oracle):
     assert tag("err") == [["rc", "-1"]]
 
 
+def test_c_host_square_grain_proc_by_name_and_tag_u32_events(tmp_path, oracle):
+    """tests/c/test_dropin_pd.c + host/dropin.c under -DCPROC_HAVE_PD: square_grain_proc(struct square_grain *,
+    t_int, t_float *, t_float *) by the reference's name (synth_tools.c:85-86) from a perform routine, the
+    TAG_U32 message handler (mod_cproc_plugin.c:24-38) and cproc_cuda_graph_event / _tick."""
+    pkg = os.path.join(ROOT, "synth_tools_b200")
+    exe = str(tmp_path / "test_dropin_pd")
+    subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-Wall", "-Werror", "-DCPROC_HAVE_PD", "-I", os.path.join(ROOT, "tests", "c", "fakepd"),
+                           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "test_dropin_pd.c"),
+                           os.path.join(pkg, "host", "dropin.c"), "-o", exe, "-L", pkg, "-lcproc_cuda", "-Wl,-rpath," + pkg])
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    out = res.stdout.splitlines()
+    tag = lambda t: [l.split()[1:] for l in out if l.split() and l.split()[0] == t]
+    assert not tag("fail"), out
+    # (1) square_grain_proc by name: two objects, three in-place blocks, threshold message after block 1
+    s = 4242
+    state = np.zeros(2, np.float32)
+    th = np.array([0.25, 0.05], np.float32)
+    want = [[], []]
+    for blk in range(3):
+        for o in range(2):
+            inp = np.zeros((1, 64), np.float32)
+            for i in range(64):
+                s = xs(s)
+                inp[0, i] = np.float32(np.int32(np.uint32(s))) * np.float32(1.0 / 2147483648.0)
+            st1 = state[o:o + 1].copy()
+            want[o].append(oracle.square_grain_run(st1, th[o:o + 1].copy(), 1, 64, inp)[0])
+            state[o] = st1[0]
+        if blk == 1:
+            th[0] = np.float32(0.4)
+    for o in range(2):
+        got = np.array([float.fromhex(x[0]) for x in tag("grain%d" % o)], np.float32)
+        assert np.array_equal(got.view(np.uint32), np.concatenate(want[o]).view(np.uint32)), o
+    assert [float.fromhex(x) for x in tag("state")[0]] == state.tolist()
+    assert tag("offset") == [["12"]]                           # x_f, brightness, threshold in front of state (synth_tools.c:78-84)
+    # (2) TAG_U32 messages: test_cproc.c's graph, one tick per message under changed = -1
+    rows = [(po.NODE_EDGE, -1, 1), (po.NODE_ACC, 0, 1)]
+    seq = [0, 1, 1, 0, 1, 0, 0, 1, 0]
+    wantc = oracle.graph_run(rows, 1, 1, np.zeros((1, 3), np.uint32), 1, len(seq), np.array(seq, np.uint32).reshape(1, 1, -1))
+    assert [(int(a), int(b)) for a, b in tag("output")] == [(2, int(x)) for x in wantc[0]]
+    assert [int(x[0]) for x in tag("msg")] == [0] * 9 + [-1, -1, -1]
+    assert tag("status") == [["0"]]
+    # (3) cproc_cuda_graph_event on a 3-instance batch: only the addressed instance ticks
+    hist = {0: [], 1: [], 2: []}
+    ev = []
+    for k in range(12):
+        inst = 2 if k % 3 == 2 else k & 1
+        hist[inst].append((k >> 1) & 1)
+        w = oracle.graph_run(rows, 1, 1, np.zeros((1, 3), np.uint32), 1, len(hist[inst]), np.array(hist[inst], np.uint32).reshape(1, 1, -1))
+        ev.append(["0", str(inst), str(int(w[0, -1]))])
+    assert tag("event") == ev
+    last = []
+    for inst in range(3):
+        h = hist[inst] + [hist[inst][-1]]                      # the final tick re-reads the persistent cproc_input
+        last.append(str(int(oracle.graph_run(rows, 1, 1, np.zeros((1, 3), np.uint32), 1, len(h), np.array(h, np.uint32).reshape(1, 1, -1))[0, -1])))
+    assert tag("tick") == [["0"] + last]
+    assert tag("bad") == [["-1", "-1"]]
+
+
 def test_c_host_generated_text_patcher_bus(tmp_path, oracle):
     """tests/c/test_graph_text.c: the generated graph text, the patcher and the mix bus from plain C."""
     pkg = os.path.join(ROOT, "synth_tools_b200")

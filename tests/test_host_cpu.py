@@ -66,6 +66,7 @@ def test_pd_scale_object(tmp_path):
     ("jack_synth", ["synth_tools_b200/host/jack/jack_synth.c", "tests/c/fakejack/fakejack.c"], ["tests/c/fakejack", "synth_tools_b200/host/jack"], ["-lcproc_cuda"]),
     ("jack_clock", ["synth_tools_b200/host/jack/jack_clock.c", "tests/c/fakejack/fakejack.c"], ["tests/c/fakejack"], ["-lcproc_cuda"]),
     ("pd_square_grain", ["synth_tools_b200/host/pd/square_grain_b200~.c", "tests/c/fakepd/fakepd.c"], ["tests/c/fakepd"], ["-lcproc_cuda", "-lm"]),
+    ("dropin_pd", ["tests/c/test_dropin_pd.c", "synth_tools_b200/host/dropin.c"], ["tests/c/fakepd"], ["-DCPROC_HAVE_PD", "-lcproc_cuda"]),
 ])
 def test_host_adapters_build_warning_free(tmp_path, name, srcs, incs, libs):
     """The JACK / Pd adapters compile with -Wall -Werror and link against the in-tree C-ABI library (running them
@@ -78,6 +79,27 @@ def test_host_adapters_build_warning_free(tmp_path, name, srcs, incs, libs):
         cmd += ["-I", os.path.join(ROOT, i)]
     cmd += [os.path.join(ROOT, s) for s in srcs] + ["-o", str(tmp_path / name), "-L", pkg, "-Wl,-rpath," + pkg] + libs
     subprocess.check_call(cmd)
+
+
+def test_dropin_exports_reference_names(tmp_path):
+    """host/dropin.c built as a shared object exports the reference's own entry points: synth_run (synth.c:45),
+    cproc_update (test_cproc.c:13), cproc_input (mod_cproc_plugin.c:20) and -- with m_pd.h on the include path --
+    square_grain_proc (synth_tools.c:85-86).  Symbols only: calling them needs a GPU."""
+    import ctypes
+    pkg = os.path.join(ROOT, "synth_tools_b200")
+    if not os.path.exists(os.path.join(pkg, "libcproc_cuda.so")):
+        pytest.skip("libcproc_cuda.so not built")
+    so = str(tmp_path / "libdropin_pd.so")
+    subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-fPIC", "-shared", "-Wall", "-Werror", "-DCPROC_HAVE_PD", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "tests", "c", "fakepd"), os.path.join(pkg, "host", "dropin.c"), "-o", so,
+                           "-L", pkg, "-lcproc_cuda", "-Wl,-rpath," + pkg])
+    lib = ctypes.CDLL(so)
+    for name in ["synth_run", "cproc_update", "cproc_input", "square_grain_proc", "cproc_dropin_square_grain_proc", "cproc_dropin_handle_tag_u32",
+                 "cproc_dropin_last_status", "cproc_dropin_shutdown"]:
+        assert hasattr(lib, name), name
+    shipped = ctypes.CDLL(os.path.join(pkg, "libcproc_dropin.so"))
+    for name in ["synth_run", "cproc_update", "cproc_input", "cproc_dropin_square_grain_proc", "cproc_dropin_handle_tag_u32"]:
+        assert hasattr(shipped, name), name
 
 
 def test_closed_form_zero_state_response_math():

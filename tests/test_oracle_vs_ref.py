@@ -253,3 +253,16 @@ def test_xorshift_and_pwm(oracle):
             assert duty[i, t] == (p[i] >> 16)
             p[i] = (p[i] + int(sp[i]) + (p[i] >> 9)) & 0xFFFFFF
     assert ph.tolist() == p
+
+
+def test_pixi_lfo_bank_vs_acc(ref, oracle):
+    """a-20: stm32f103/pixi.c:279,282-285 compiled from the reference against the oracle's acc under a 12-bit mask."""
+    rng = np.random.default_rng(3)
+    for adc0 in [0, 37, 2048, 4095, 51234]:
+        dac = rng.integers(0, 0x1000, 12).astype(np.uint16)
+        st = dac.astype(np.uint32).reshape(12, 1).copy()
+        trace = ref.pixi_lfo_run(dac, adc0, 500)
+        inp = np.full((12, 1, 500), adc0 >> 5, np.uint32)
+        out = oracle.graph_run([(po.NODE_ACC, -1, 0xFFFFFFFF)], 1, 0, st, 12, 500, inp)
+        assert np.array_equal((out & 0xFFF).T, trace.astype(np.uint32))
+        assert np.array_equal(st[:, 0] & 0xFFF, dac.astype(np.uint32))

@@ -1,6 +1,6 @@
 """Summarise `ncu --set full` reports into the text files committed under profiles/.
 
-    python tools/summarize_ncu.py gpurun_out/prof_X.ncu-rep [...]  -> profiles/r1_<name>_summary.txt
+    python tools/summarize_ncu.py gpurun_out/prof_X.ncu-rep [...]  -> profiles/r2_<name>_summary.txt (ROUND=rN)
 
 Reads the raw page of each report (`ncu -i ... --page raw --csv`) and keeps the metrics the
 roofline discussion in DESIGN.md uses: duration, DRAM bytes, issue activity, pipe
@@ -66,6 +66,6 @@ if __name__ == "__main__":
         text, tot = summarize(rep)
         out_dir = os.environ.get("SUMMARY_DIR", os.path.join(ROOT, "profiles"))      # on the GPU box: gpurun_out/summaries (reports are too big to bring back)
         os.makedirs(out_dir, exist_ok=True)
-        dst = os.path.join(out_dir, "r1_%s_summary.txt" % name)
+        dst = os.path.join(out_dir, "%s_%s_summary.txt" % (os.environ.get("ROUND", "r2"), name))
         open(dst, "w").write(text)
         print(dst, tot)
