@@ -38,6 +38,9 @@
  *
  * ABI version 2: cproc_cuda_node carries a second source (two-input processors),
  * cproc_cuda_config an output-node list; graph front end, patcher and mix bus added.
+ * ABI version 3: float processors as graph nodes (phasor_f, svf, env, onepole, gain,
+ * asfloat; include/cproc_ext.h), graph batches carry a param record, cproc_cuda_graph_info
+ * grows (param words and initialisers, output types), evented graph driver.
  */
 #ifndef CPROC_CUDA_H
 #define CPROC_CUDA_H
@@ -49,7 +52,7 @@
 extern "C" {
 #endif
 
-#define CPROC_CUDA_ABI_VERSION 2
+#define CPROC_CUDA_ABI_VERSION 3
 
 /* ---- error codes -------------------------------------------------------- */
 #define CPROC_CUDA_OK        0
@@ -71,7 +74,10 @@ enum cproc_cuda_proc {
      * in:  uint32 [inst][n_inputs][F]; in2: changed mask uint32 [inst][F] or
      * NULL (= -1, mod_cproc_plugin.c:32); out: uint32 [inst][F], the value
      * passed to cproc_output() each tick (test_cproc.c:16); with several
-     * cproc_output statements [inst][n_outputs][F]. */
+     * cproc_output statements [inst][n_outputs][F].  A graph that reads no
+     * input[] (a free-running phasor_f voice) has n_inputs == 0 and in == NULL.
+     * param record: the nodes' param structs concatenated in ANF order (only the
+     * extension processors have one, see the node kinds below). */
     CPROC_CUDA_GRAPH = 1,
     /* pdmK_update, K = cfg.order (pdm.h).  state record: struct pdmK.
      * param record: {uint32 input} used when in == NULL.  in: uint32
@@ -146,8 +152,34 @@ enum cproc_cuda_proc {
  * PDM is pdmK_update (stm32f103/pdm.h:13-77) as a processor: .in the modulator input,
  * .dither the second input (src2), .out the quantiser output; state record {out, s1..sK};
  * config word = K | out_shift << 3.  glide -> pdm2 is the firmware's whole v2 channel
- * (mod_pdm_pwm.c:97-116) as a graph. */
-enum { CPROC_CUDA_NODE_ACC = 0, CPROC_CUDA_NODE_EDGE = 1, CPROC_CUDA_NODE_GLIDE = 2, CPROC_CUDA_NODE_PDM = 3 };
+ * (mod_pdm_pwm.c:97-116) as a graph.
+ *
+ * Extension processors (SURVEY 8 a-X; not in the reference): the DEF_PROC definitions are
+ * include/cproc_ext.h, written against the reference's generic/cproc.h:89-103 so that the same
+ * graph text compiles as C on a CPU host.  Their `float` fields are IEEE binary32 carried in the
+ * same 32-bit words as `w` (state rows, param rows and output streams hold the bit patterns);
+ * every float operation is one rounding in a fixed order (fmaf where cproc_ext.h says fmaf), so
+ * results are bit-identical to the C definitions compiled with -ffp-contract=off (for non-NaN data: a NaN
+ * result is the canonical 0x7FFFFFFF on the GPU where an x86 host propagates the operand's payload).
+ *   phasor_f  state {float out; w phase}          param {w inc}   input {w mod}
+ *             out = (float)(int32_t)phase * 2^-31; phase += inc + mod    (signed saw, read before advance)
+ *   svf       state {float out; float bp}         param {float f; float q}   input {float in}
+ *             Chamberlin: lp = fmaf(f, bp, out); hp = in - lp; hp = fmaf(-q, bp, hp); bp = fmaf(f, hp, bp); out = lp
+ *   env       state {float out; float env; w t}   param {float attack; float release; w gate_frames}   input {float in}
+ *             linear attack / release: t < gate_frames ? env = min(env + attack, 1) : env = max(env - release, 0); t += 1; out = in * env
+ *   onepole   state {float out}                   param {float a}   input {float in}     out = fmaf(a, in - out, out)
+ *   gain      state {float out}                   param {float g}   input {float in}     out = g * in
+ *   asfloat   state {float out}                   input {w in}      out = the float whose bits are `in` (external float streams)
+ * Connecting a `w` output (or input[k]) to a float input converts by value, (float)(uint32_t)x, as the
+ * C assignment in PROC_COND's designated initialiser does (cproc.h:75); a float output feeding a `w`
+ * input is rejected (undefined in C for negative values).  An input the statement does not name reads
+ * 0, like the omitted member of the C initialiser: src = CPROC_CUDA_SRC_ZERO.
+ * The param record of a graph batch is the concatenation of its nodes' param structs in ANF order
+ * (cproc_cuda_upload_param; cproc_cuda_param_bytes). */
+enum { CPROC_CUDA_NODE_ACC = 0, CPROC_CUDA_NODE_EDGE = 1, CPROC_CUDA_NODE_GLIDE = 2, CPROC_CUDA_NODE_PDM = 3,
+       CPROC_CUDA_NODE_PHASOR_F = 4, CPROC_CUDA_NODE_SVF = 5, CPROC_CUDA_NODE_ENV = 6, CPROC_CUDA_NODE_ONEPOLE = 7,
+       CPROC_CUDA_NODE_GAIN = 8, CPROC_CUDA_NODE_ASFLOAT = 9, CPROC_CUDA_NODE_KINDS = 10 };
+#define CPROC_CUDA_SRC_ZERO ((int32_t)0x80000000)
 #define CPROC_CUDA_NODE_KIND(t) ((t) & 0xFFu)
 #define CPROC_CUDA_NODE_ARG(t)  (((t) >> 8) & 0xFFu)
 #define CPROC_CUDA_NODE_GLIDE_L(L) (CPROC_CUDA_NODE_GLIDE | ((uint32_t)(L) << 8))
@@ -206,7 +238,12 @@ typedef struct {
  *   PROC_COND(<changed> & <mask>, <inst>, acc|edge, NULL, NULL, .in = input[k] | <inst>.out);
  *   PROC_COND(<changed> & <mask>, <inst>, glide, &(glide_config){.div_log = L}, NULL, .in = ...);
  *   PROC_COND(<changed> & <mask>, <inst>, pdm1..pdm4, &(pdm_config){.out_shift = S}, NULL, .in = ..., .dither = ...);
- * (or PROC(<inst>, ...), cproc.h:81) and one or more `cproc_output(<index>, <inst>.out);`.
+ *   PROC(<inst>, phasor_f|svf|env|onepole|gain|asfloat, NULL, <param>, .in = ... [, .mod = ...]);
+ *     <param>: &<identifier> (the host uploads the record) or a compound literal whose members become the
+ *     record's initial value for every instance, e.g. (&(svf_param){ .f = 0.1f, .q = 1.5f }) -- in parentheses, or
+ *     the C preprocessor splits the macro argument at the literal's commas; NULL for asfloat
+ * (or PROC(<inst>, ...), cproc.h:81) and one or more `cproc_output(<index>, <inst>.out);` -- for a float
+ * node `cproc_output_f(<index>, <inst>.out);` (the stream then carries the float's bits).
  * Fills `nodes` (at most max_nodes rows) and `info`; the rows go into
  * cproc_cuda_config.nodes / n_nodes / n_inputs / out_node unchanged.  Needs no device. */
 typedef struct {
@@ -214,7 +251,11 @@ typedef struct {
     uint32_t out_index;       /* first argument of cproc_output (the TAG_U32 index, mod_cproc_plugin.c:40-43) */
     uint32_t n_outputs;       /* number of cproc_output statements (out_node / out_index are the first)      */
     uint32_t out_nodes[16], out_indices[16];
+    uint32_t out_is_float;    /* bit q: output q came from cproc_output_f                                    */
+    uint32_t n_param_words;   /* words of the batch's param record                                           */
+    uint32_t param_init[192]; /* the record's initial value: compound-literal members, 0 elsewhere           */
 } cproc_cuda_graph_info;
+#define CPROC_CUDA_GRAPH_MAX_PARAM_WORDS 192
 int  cproc_cuda_graph_parse(const char *text, cproc_cuda_node *nodes, uint32_t max_nodes, cproc_cuda_graph_info *info);
 
 /* Buffers of one run.  Host pointers for cproc_cuda_run, device pointers for

@@ -21,8 +21,10 @@ OUT="$1"; OPT="$2"
 OBJ="$(mktemp -d /tmp/cproc_ref_obj.XXXXXX)"
 CFLAGS="-std=gnu99 $OPT -fwrapv -ffp-contract=off -fPIC -fopenmp -w"
 # (1) generic/cproc.h + linux/test_cproc.c (whole file; main renamed)
-gcc $CFLAGS -I"$HERE/shim" -I"$REF/generic" -c "$HERE/ref/ref_cproc.c" -o "$OBJ/ref_cproc.o"
+gcc $CFLAGS -I"$HERE/shim" -I"$REF/generic" -I"$HERE/../include" -c "$HERE/ref/ref_cproc.c" -o "$OBJ/ref_cproc.o"
 gcc $CFLAGS -I"$HERE/shim" -I"$REF/generic" -Dmain=ref_test_cproc_main -c "$REF/linux/test_cproc.c" -o "$OBJ/test_cproc.o"
+# (1b) the graph texts of tests/golden/*.cproc compiled as C against the real cproc.h + include/cproc_ext.h
+gcc $CFLAGS -I"$HERE/shim" -I"$REF/generic" -I"$HERE/../include" -I"$HERE/../tests/golden" -c "$HERE/ref/ref_ext_voice.c" -o "$OBJ/ref_ext_voice.o"
 # (2) stm32f103/pdm.h
 gcc $CFLAGS -I"$REF/stm32f103" -c "$HERE/ref/ref_pdm.c" -o "$OBJ/ref_pdm.o"
 # (3) linux/synth.c:29-206 (voice bank DSP; JACK glue excluded)
@@ -43,7 +45,7 @@ gcc $CFLAGS -fno-semantic-interposition -I"$HERE/shim/stm32" -I"$REF/stm32f103" 
 # (8) stm32f103/pixi.c:279,282-285 (the PIXI demo LFO bank: inc = adc[0] >> 5; dac = (dac + inc) & 0xFFF)
 ( cat "$HERE/ref/ref_pixi_pre.h"; sed -n '279p;282,285p' "$REF/stm32f103/pixi.c"; cat "$HERE/ref/ref_pixi_tail.c" ) \
   | gcc $CFLAGS -x c -c - -o "$OBJ/ref_pixi.o"
-gcc -shared -fopenmp -o "$HERE/_ref/$OUT" "$OBJ/ref_cproc.o" "$OBJ/test_cproc.o" "$OBJ/ref_pdm.o" "$OBJ/ref_synth.o" "$OBJ/ref_grain.o" \
+gcc -shared -fopenmp -o "$HERE/_ref/$OUT" "$OBJ/ref_cproc.o" "$OBJ/ref_ext_voice.o" "$OBJ/test_cproc.o" "$OBJ/ref_pdm.o" "$OBJ/ref_synth.o" "$OBJ/ref_grain.o" \
     "$OBJ/ref_v2_isr.o" "$OBJ/ref_clock.o" "$OBJ/ref_pwm.o" "$OBJ/ref_pixi.o" -lm
 rm -rf "$OBJ"
 echo "built $HERE/_ref/$OUT ($OPT)"

@@ -37,8 +37,23 @@ uint32_t orc_node_state_words(uint32_t type) {
     case ORC_NODE_EDGE: return 2u;
     case ORC_NODE_GLIDE: return 5u;
     case ORC_NODE_PDM: return 1u + ((type >> 8) & 7u);
+    case ORC_NODE_PHASOR_F: case ORC_NODE_SVF: return 2u;   /* cproc_ext.h: {out, phase}, {out, bp} */
+    case ORC_NODE_ENV: return 3u;                           /* {out, env, t} */
     default: return 1u;
     }
+}
+uint32_t orc_node_param_words(uint32_t type) {
+    switch (type & 0xFF) {
+    case ORC_NODE_PHASOR_F: case ORC_NODE_ONEPOLE: case ORC_NODE_GAIN: return 1u;   /* {inc}, {a}, {g} */
+    case ORC_NODE_SVF: return 2u;                                                   /* {f, q} */
+    case ORC_NODE_ENV: return 3u;                                                   /* {attack, release, gate_frames} */
+    default: return 0u;
+    }
+}
+uint32_t orc_graph_param_words(const orc_node *nodes, uint32_t n_nodes) {
+    uint32_t w = 0;
+    for (uint32_t i = 0; i < n_nodes; i++) w += orc_node_param_words(nodes[i].type);
+    return w;
 }
 uint32_t orc_graph_state_words(const orc_node *nodes, uint32_t n_nodes) {
     uint32_t w = 0;
@@ -120,6 +135,82 @@ void orc_graph_run_multi(const orc_node *nodes, uint32_t n_nodes, uint32_t n_inp
     }
 }
 
+
+/* Extension processors as graph nodes: the update bodies of include/cproc_ext.h restated on word arrays
+ * (floats as bit patterns); each statement one IEEE rounding, fmaf fused. */
+static float orc_bits_f(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
+static uint32_t orc_f_bits(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
+static int orc_kind_in_float(uint32_t kind) { return kind == ORC_NODE_SVF || kind == ORC_NODE_ENV || kind == ORC_NODE_ONEPOLE || kind == ORC_NODE_GAIN; }
+static int orc_kind_out_float(uint32_t kind) { return kind >= ORC_NODE_PHASOR_F && kind < ORC_NODE_KINDS; }
+static void orc_ext_update(uint32_t kind, uint32_t *s, const uint32_t *p, uint32_t x) {
+    switch (kind) {
+    case ORC_NODE_PHASOR_F:                                  /* cproc_ext.h phasor_f: read, then advance */
+        s[0] = orc_f_bits((float)(int32_t)s[1] * (1.0f / 2147483648.0f));
+        s[1] += p[0] + x;
+        break;
+    case ORC_NODE_SVF: {                                     /* cproc_ext.h svf */
+        float f = orc_bits_f(p[0]), q = orc_bits_f(p[1]), bp = orc_bits_f(s[1]);
+        float lp = fmaf(f, bp, orc_bits_f(s[0]));
+        float hp = orc_bits_f(x) - lp;
+        hp = fmaf(-q, bp, hp);
+        s[1] = orc_f_bits(fmaf(f, hp, bp));
+        s[0] = orc_f_bits(lp);
+        break; }
+    case ORC_NODE_ENV: {                                     /* cproc_ext.h env */
+        float e = orc_bits_f(s[1]);
+        if (s[2] < p[2]) { e = e + orc_bits_f(p[0]); if (e > 1.0f) e = 1.0f; }
+        else { e = e - orc_bits_f(p[1]); if (e < 0.0f) e = 0.0f; }
+        s[1] = orc_f_bits(e);
+        s[2] += 1;
+        s[0] = orc_f_bits(orc_bits_f(x) * e);
+        break; }
+    case ORC_NODE_ONEPOLE: { float y = orc_bits_f(s[0]); s[0] = orc_f_bits(fmaf(orc_bits_f(p[0]), orc_bits_f(x) - y, y)); break; }
+    case ORC_NODE_GAIN: s[0] = orc_f_bits(orc_bits_f(p[0]) * orc_bits_f(x)); break;
+    case ORC_NODE_ASFLOAT: s[0] = x; break;
+    }
+}
+
+void orc_graph_run_ext(const orc_node *nodes, uint32_t n_nodes, uint32_t n_inputs,
+                       const uint32_t *out_nodes, uint32_t n_out, uint32_t *state, const uint32_t *param, uint64_t N, uint64_t F,
+                       const uint32_t *in, const uint32_t *changed, uint32_t *out) {
+    uint32_t sw = orc_graph_state_words(nodes, n_nodes), pw = orc_graph_param_words(nodes, n_nodes);
+    uint32_t off[64], poff[64];
+    uint32_t o = 0, q = 0;
+    for (uint32_t i = 0; i < n_nodes && i < 64; i++) { off[i] = o; o += orc_node_state_words(nodes[i].type); poff[i] = q; q += orc_node_param_words(nodes[i].type); }
+#pragma omp parallel for schedule(static)
+    for (int64_t n = 0; n < (int64_t)N; n++) {
+        uint32_t *st = state + (uint64_t)n * sw;
+        const uint32_t *pr = param ? param + (uint64_t)n * pw : NULL;
+        for (uint64_t t = 0; t < F; t++) {
+            uint32_t g = changed ? changed[(uint64_t)n * F + t] : 0xFFFFFFFFu;
+            for (uint32_t i = 0; i < n_nodes; i++) {
+                if (!(g & nodes[i].cond_mask)) continue;
+                uint32_t kind = nodes[i].type & 0xFF;
+                uint32_t xs[2] = {0, 0};
+                for (int j = 0; j < (kind == ORC_NODE_PDM ? 2 : 1); j++) {
+                    int32_t src = j ? nodes[i].src2 : nodes[i].src;
+                    if (src == ORC_SRC_ZERO) continue;                       /* 0 / +0.0f */
+                    uint32_t v; int is_f = 0;
+                    if (src >= 0) { v = st[off[src]]; is_f = orc_kind_out_float(nodes[src].type & 0xFF); }   /* .out is the first state word */
+                    else v = in[((uint64_t)n * n_inputs + (uint32_t)(-(src + 1))) * F + t];
+                    /* `.in = <w expression>` into a float member converts by value (cproc.h:75) */
+                    xs[j] = (orc_kind_in_float(kind) && !is_f) ? orc_f_bits((float)v) : v;
+                }
+                switch (kind) {
+                case ORC_NODE_PDM: {
+                    uint32_t order = (nodes[i].type >> 8) & 7u, sh = (nodes[i].type >> 11) & 31u;
+                    st[off[i]] = orc_pdm_update(st + off[i] + 1, order, xs[0], sh, xs[1]);   /* pdm.h:13-77 */
+                    break; }
+                case ORC_NODE_EDGE: orc_edge_update((orc_edge_state *)(st + off[i]), xs[0]); break;
+                case ORC_NODE_GLIDE: orc_glide_update((orc_glide_state *)(st + off[i]), xs[0], (nodes[i].type >> 8) & 0xFF); break;
+                case ORC_NODE_ACC: orc_acc_update((orc_acc_state *)(st + off[i]), xs[0]); break;
+                default: orc_ext_update(kind, st + off[i], pr ? pr + poff[i] : NULL, xs[0]); break;
+                }
+            }
+            for (uint32_t k = 0; k < n_out; k++) out[((uint64_t)n * n_out + k) * F + t] = st[off[out_nodes[k]]];
+        }
+    }
+}
 
 /* ======================================================================= */
 /* stm32f103/pdm.h                                                          */

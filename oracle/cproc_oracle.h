@@ -49,7 +49,10 @@ void orc_edge_update(orc_edge_state *s, orc_w in);      /* cproc.h:151-154 */
 
 /* A generated cproc graph (linux/test_cproc.c:12-17, stm32f103/bp5_plugin.c:4-9)
  * as a table: one row per PROC_COND statement, in ANF order. */
-enum { ORC_NODE_ACC = 0, ORC_NODE_EDGE = 1, ORC_NODE_GLIDE = 2, ORC_NODE_PDM = 3 };
+enum { ORC_NODE_ACC = 0, ORC_NODE_EDGE = 1, ORC_NODE_GLIDE = 2, ORC_NODE_PDM = 3,
+       /* extension processors (include/cproc_ext.h is the definition; restated in cproc_oracle.c, parity unpinned by the reference) */
+       ORC_NODE_PHASOR_F = 4, ORC_NODE_SVF = 5, ORC_NODE_ENV = 6, ORC_NODE_ONEPOLE = 7, ORC_NODE_GAIN = 8, ORC_NODE_ASFLOAT = 9, ORC_NODE_KINDS = 10 };
+#define ORC_SRC_ZERO ((int32_t)0x80000000)   /* an input the PROC statement does not name: 0 (C initialiser) */
 /* pdm node: pdmK_update (pdm.h:13-77) as a processor, state {out, s1..sK}; .in = src, .dither = src2;
  * type = 3 | (K | out_shift << 3) << 8. */
 /* glide: the control-rate -> audio-rate parameter interpolation of the firmware
@@ -84,6 +87,14 @@ void orc_graph_run(const orc_node *nodes, uint32_t n_nodes, uint32_t n_inputs,
 void orc_graph_run_multi(const orc_node *nodes, uint32_t n_nodes, uint32_t n_inputs,
                          const uint32_t *out_nodes, uint32_t n_out, uint32_t *state, uint64_t N, uint64_t F,
                          const uint32_t *in, const uint32_t *changed, uint32_t *out);
+
+/* Graphs with extension processors: param [N][param_words] = the nodes' param structs in ANF order (NULL if none);
+ * n_inputs may be 0 (in == NULL).  Float fields travel as their bit patterns. */
+uint32_t orc_node_param_words(uint32_t type);
+uint32_t orc_graph_param_words(const orc_node *nodes, uint32_t n_nodes);
+void orc_graph_run_ext(const orc_node *nodes, uint32_t n_nodes, uint32_t n_inputs,
+                       const uint32_t *out_nodes, uint32_t n_out, uint32_t *state, const uint32_t *param, uint64_t N, uint64_t F,
+                       const uint32_t *in, const uint32_t *changed, uint32_t *out);
 
 /* ---- stm32f103/pdm.h:10-77 -------------------------------------------- */
 /* s[0..order-1] = s1..sK.  order 1 ignores dither (pdm.h:13). */

@@ -22,6 +22,8 @@ f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 VP = C.c_void_p
 
 NODE_ACC, NODE_EDGE, NODE_GLIDE, NODE_PDM = 0, 1, 2, 3
+NODE_PHASOR_F, NODE_SVF, NODE_ENV, NODE_ONEPOLE, NODE_GAIN, NODE_ASFLOAT = 4, 5, 6, 7, 8, 9   # include/cproc_ext.h
+SRC_ZERO = -0x80000000
 
 
 def node_glide(div_log):
@@ -37,7 +39,11 @@ def node_pdm(order, out_shift):
 def node_words(t):
     if t & 0xFF == NODE_PDM:
         return 1 + ((t >> 8) & 7)
-    return {NODE_EDGE: 2, NODE_GLIDE: 5}.get(t & 0xFF, 1)
+    return {NODE_EDGE: 2, NODE_GLIDE: 5, NODE_PHASOR_F: 2, NODE_SVF: 2, NODE_ENV: 3}.get(t & 0xFF, 1)
+
+
+def node_param_words(t):
+    return {NODE_PHASOR_F: 1, NODE_SVF: 2, NODE_ENV: 3, NODE_ONEPOLE: 1, NODE_GAIN: 1}.get(t & 0xFF, 0)
 
 MIX_SAW, MIX_SQUARE = 0, 1
 
@@ -109,6 +115,17 @@ class _Lib:
         f = self._fn("graph_run", None, [VP, C.c_uint32, C.c_uint32, C.c_uint32, VP, C.c_uint64,
                                          C.c_uint64, VP, VP, VP])
         f(_ptr(nodes), len(rows), n_inputs, out_node, _ptr(state), N, F, _ptr(inp), _ptr(changed), _ptr(out))
+        return out
+
+    def graph_run_ext(self, rows, n_inputs, out_nodes, state, param, N, F, inp=None, changed=None):
+        """Graphs with extension processors: param uint32 [N][param_words] (floats as bits) or None; returns out
+        uint32 [N][len(out_nodes)][F].  liboracle: the restatement; libref: the DEF_PROC bodies of include/cproc_ext.h
+        compiled against the reference's cproc.h (acc / edge / extension kinds only)."""
+        nodes = make_nodes(rows)
+        outs = np.asarray(out_nodes, np.uint32)
+        out = np.zeros((N, len(outs), F), np.uint32)
+        f = self._fn("graph_run_ext", None, [VP, C.c_uint32, C.c_uint32, VP, C.c_uint32, VP, VP, C.c_uint64, C.c_uint64, VP, VP, VP])
+        f(_ptr(nodes), len(rows), n_inputs, _ptr(outs), len(outs), _ptr(state), _ptr(param), N, F, _ptr(inp), _ptr(changed), _ptr(out))
         return out
 
     def graph_run_multi(self, rows, n_inputs, out_nodes, state, N, F, inp, changed=None):
@@ -281,6 +298,17 @@ class Ref(_Lib):
         voices = np.zeros((64, 2), np.uint32)
         self._fn("synth_play", None, [VP, C.c_int, C.c_uint64, VP, VP])(_ptr(notes), len(notes), F, _ptr(vec), _ptr(voices))
         return vec, voices
+
+    def ext_sizeof(self, what):
+        """sizeof of the DEF_PROC_STRUCTS-generated structs of include/cproc_ext.h: 3 * kind + {0 state, 1 param, 2 input}."""
+        return self._fn("ext_sizeof", C.c_uint32, [C.c_int])(what)
+
+    def ext_text_run(self, which, inp, changed, F, n_out):
+        """tests/golden/ext_voice.cproc (0) / ext_chain.cproc (1) compiled as C against the reference's cproc.h: F ticks of
+        the ONE instance of this loaded library copy.  inp uint32 [n_in][F]; returns uint32 [n_out][F]."""
+        out = np.zeros((n_out, F), np.uint32)
+        self._fn("ext_text_run", None, [C.c_int, VP, VP, C.c_uint64, VP])(which, _ptr(inp), _ptr(changed), F, _ptr(out))
+        return out
 
     def pixi_lfo_run(self, dac, adc0, ticks):
         """stm32f103/pixi.c:279,282-285 itself: `ticks` timer interrupts of the demo LFO bank.  dac uint16 [12] in/out;

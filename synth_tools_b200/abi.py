@@ -15,6 +15,9 @@ LIB_PATH = os.path.join(HERE, "libcproc_cuda.so")
 # enum cproc_cuda_proc
 GRAPH, PDM, PDM_V1, PDM_V2, PWM, VOICE_BANK, SQUARE_GRAIN, SQUARE_GRAIN_MIX, XVOICE, ONEPOLE, WORD_CLOCK = range(1, 12)
 NODE_ACC, NODE_EDGE, NODE_GLIDE, NODE_PDM = 0, 1, 2, 3
+# extension processors (include/cproc_ext.h)
+NODE_PHASOR_F, NODE_SVF, NODE_ENV, NODE_ONEPOLE, NODE_GAIN, NODE_ASFLOAT = 4, 5, 6, 7, 8, 9
+SRC_ZERO = -0x80000000          # CPROC_CUDA_SRC_ZERO: an input the PROC statement does not name
 
 
 def node_glide(div_log):
@@ -55,7 +58,8 @@ class Config(C.Structure):
 
 class GraphInfo(C.Structure):
     _fields_ = [("n_nodes", C.c_uint32), ("n_inputs", C.c_uint32), ("out_node", C.c_uint32), ("out_index", C.c_uint32),
-                ("n_outputs", C.c_uint32), ("out_nodes", C.c_uint32 * 16), ("out_indices", C.c_uint32 * 16)]
+                ("n_outputs", C.c_uint32), ("out_nodes", C.c_uint32 * 16), ("out_indices", C.c_uint32 * 16),
+                ("out_is_float", C.c_uint32), ("n_param_words", C.c_uint32), ("param_init", C.c_uint32 * 192)]
 
 
 GRAPH_MAX_NODES = 64
@@ -176,6 +180,20 @@ def graph_parse_outputs(text):
         raise CprocCudaError(rc, (lib.cproc_cuda_last_error(None) or b"").decode())
     rows = [_row(nodes[k]) for k in range(info.n_nodes)]
     return rows, info.n_inputs, list(info.out_nodes[:info.n_outputs]), list(info.out_indices[:info.n_outputs])
+
+
+def graph_parse_ex(text):
+    """Everything cproc_cuda_graph_parse reports: {rows, n_inputs, out_nodes, out_indices, out_is_float: [bool],
+    param_init: uint32 [n_param_words] (the param record's initial value from the text's compound literals)}."""
+    nodes = (Node * GRAPH_MAX_NODES)()
+    info = GraphInfo()
+    rc = lib.cproc_cuda_graph_parse(text.encode(), nodes, GRAPH_MAX_NODES, C.byref(info))
+    if rc:
+        raise CprocCudaError(rc, (lib.cproc_cuda_last_error(None) or b"").decode())
+    return {"rows": [_row(nodes[k]) for k in range(info.n_nodes)], "n_inputs": info.n_inputs,
+            "out_nodes": list(info.out_nodes[:info.n_outputs]), "out_indices": list(info.out_indices[:info.n_outputs]),
+            "out_is_float": [bool((info.out_is_float >> q) & 1) for q in range(info.n_outputs)],
+            "param_init": np.array(info.param_init[:info.n_param_words], np.uint32)}
 
 
 def graph_jit_source(rows, n_inputs, out_node, has_changed=False):

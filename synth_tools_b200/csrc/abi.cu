@@ -139,9 +139,9 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
 static int proc_words(const cproc_cuda_config &c, const std::vector<cproc_cuda_node> &nodes, uint32_t *sw, uint32_t *pw) {
     switch (c.proc) {
     case CPROC_CUDA_GRAPH: {
-        uint32_t w = 0;
-        for (auto &nd : nodes) w += cproc_node_words(nd.type);
-        *sw = w; *pw = 0; return 0;
+        uint32_t w = 0, q = 0;
+        for (auto &nd : nodes) { w += cproc_node_words(nd.type); q += cproc_node_param_words(nd.type); }
+        *sw = w; *pw = q; return 0;
     }
     case CPROC_CUDA_PDM: *sw = c.order; *pw = 1; return 0;
     case CPROC_CUDA_PDM_V1: *sw = 2; *pw = 0; return 0;
@@ -167,14 +167,13 @@ int cproc_cuda_alloc(cproc_cuda_ctx *ctx, const cproc_cuda_config *cfg, uint64_t
     bool pdm_family = c.proc == CPROC_CUDA_PDM || c.proc == CPROC_CUDA_PDM_V1 || c.proc == CPROC_CUDA_PDM_V2;
     if (c.proc == CPROC_CUDA_GRAPH) {
         if (!c.nodes || c.n_nodes == 0 || c.n_nodes > CPROC_CUDA_GRAPH_MAX_NODES) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph needs 1..%d nodes", CPROC_CUDA_GRAPH_MAX_NODES);
-        if (c.n_inputs == 0) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph n_inputs is 0");
         if (c.n_outputs > CPROC_CUDA_GRAPH_MAX_OUTPUTS || (c.n_outputs > 1 && !c.out_nodes)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph has 1..%d outputs (out_nodes)", CPROC_CUDA_GRAPH_MAX_OUTPUTS);
         if (c.n_outputs > 1) outs.assign(c.out_nodes, c.out_nodes + c.n_outputs); else outs.assign(1, c.n_outputs == 1 && c.out_nodes ? c.out_nodes[0] : c.out_node);
         for (uint32_t o : outs) if (o >= c.n_nodes) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph output node %u of %u", o, c.n_nodes);
         nodes.assign(c.nodes, c.nodes + c.n_nodes);
         for (uint32_t k = 0; k < c.n_nodes; ++k) {
             const cproc_cuda_node &nd = nodes[k];
-            if (const char *why = cproc_node_check(nd, k, c.n_inputs)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: node %u (type 0x%x, src %d): %s", k, nd.type, nd.src, why);
+            if (const char *why = cproc_node_check(nodes.data(), k, c.n_inputs)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: node %u (type 0x%x, src %d): %s", k, nd.type, nd.src, why);
         }
     }
     if (pdm_family || c.proc == CPROC_CUDA_PDM_V2) {
@@ -188,6 +187,7 @@ int cproc_cuda_alloc(cproc_cuda_ctx *ctx, const cproc_cuda_config *cfg, uint64_t
     uint32_t sw = 0, pw = 0;
     if (proc_words(c, nodes, &sw, &pw)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: unknown processor %u", c.proc);
     if (sw > 5 * CPROC_CUDA_GRAPH_MAX_NODES) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph state too large (%u words)", sw);
+    if (pw > CPROC_CUDA_GRAPH_MAX_PARAM_WORDS) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "alloc: graph param record too large (%u words)", pw);
 
     CK(ctx, cudaSetDevice(ctx->device));
     cproc_cuda_batch *b = new cproc_cuda_batch();

@@ -110,26 +110,52 @@ int cproc_check(cproc_cuda_ctx *ctx, cudaError_t e, const char *what);
 #define CK(ctx, call) do { int _rc = cproc_check((ctx), (call), #call); if (_rc) return _rc; } while (0)
 #define CK_LAUNCH(ctx, name) do { (ctx)->launches++; int _rc = cproc_check((ctx), cudaGetLastError(), name); if (_rc) return _rc; } while (0)
 
-static inline uint32_t cproc_node_words(uint32_t type) {   // acc {out}; edge {out, last}; glide {out, vel0, pos1, vel1, count}; pdm {out, s1..sK}
-    switch (CPROC_CUDA_NODE_KIND(type)) {
-    case CPROC_CUDA_NODE_EDGE: return 2u;
-    case CPROC_CUDA_NODE_GLIDE: return 5u;
-    case CPROC_CUDA_NODE_PDM: return 1u + (CPROC_CUDA_NODE_ARG(type) & 7u);
-    default: return 1u;
-    }
+// One row per node kind: the field lists of the processor's DEF_PROC structs (cproc.h:134-148 for acc / edge, include/cproc_ext.h for
+// the extension processors; glide / pdm: cproc_cuda.h).  *_f: bit k set = field k is a float.  pdm's state is {out, s1..sK}: 1 + K words.
+struct cproc_kind_meta {
+    const char *name;
+    uint32_t n_state; const char *state[5]; uint32_t state_f;
+    uint32_t n_param; const char *param[3]; uint32_t param_f;
+    uint32_t n_input; const char *input[2]; uint32_t input_f;
+    uint32_t n_config; const char *config[1];
+};
+static const cproc_kind_meta k_cproc_kinds[CPROC_CUDA_NODE_KINDS] = {
+    {"acc",      1, {"out"}, 0,                                    0, {nullptr}, 0,                               1, {"in"}, 0,           0, {nullptr}},
+    {"edge",     2, {"out", "last"}, 0,                            0, {nullptr}, 0,                               1, {"in"}, 0,           0, {nullptr}},
+    {"glide",    5, {"out", "vel0", "pos1", "vel1", "count"}, 0,   0, {nullptr}, 0,                               1, {"in"}, 0,           1, {"div_log"}},
+    {"pdm",      5, {"out", "s1", "s2", "s3", "s4"}, 0,            0, {nullptr}, 0,                               2, {"in", "dither"}, 0, 1, {"order_shift"}},
+    {"phasor_f", 2, {"out", "phase"}, 1,                           1, {"inc"}, 0,                                 1, {"mod"}, 0,          0, {nullptr}},
+    {"svf",      2, {"out", "bp"}, 3,                              2, {"f", "q"}, 3,                              1, {"in"}, 1,           0, {nullptr}},
+    {"env",      3, {"out", "env", "t"}, 3,                        3, {"attack", "release", "gate_frames"}, 3,    1, {"in"}, 1,           0, {nullptr}},
+    {"onepole",  1, {"out"}, 1,                                    1, {"a"}, 1,                                   1, {"in"}, 1,           0, {nullptr}},
+    {"gain",     1, {"out"}, 1,                                    1, {"g"}, 1,                                   1, {"in"}, 1,           0, {nullptr}},
+    {"asfloat",  1, {"out"}, 1,                                    0, {nullptr}, 0,                               1, {"in"}, 0,           0, {nullptr}},
+};
+static inline bool cproc_kind_out_float(uint32_t type) { const uint32_t k = CPROC_CUDA_NODE_KIND(type); return k < CPROC_CUDA_NODE_KINDS && (k_cproc_kinds[k].state_f & 1u); }
+static inline uint32_t cproc_node_words(uint32_t type) {   // acc {out}; edge {out, last}; glide {out, vel0, pos1, vel1, count}; pdm {out, s1..sK}; extension processors: cproc_ext.h
+    const uint32_t kind = CPROC_CUDA_NODE_KIND(type);
+    if (kind == CPROC_CUDA_NODE_PDM) return 1u + (CPROC_CUDA_NODE_ARG(type) & 7u);
+    return kind < CPROC_CUDA_NODE_KINDS ? k_cproc_kinds[kind].n_state : 1u;
 }
-// Validity of one node row at position k of an ANF table (shared by alloc, the JIT and the patcher)
-static inline const char *cproc_node_check(const cproc_cuda_node &nd, uint32_t k, uint32_t n_inputs) {
+static inline uint32_t cproc_node_param_words(uint32_t type) {
+    const uint32_t kind = CPROC_CUDA_NODE_KIND(type);
+    return kind < CPROC_CUDA_NODE_KINDS ? k_cproc_kinds[kind].n_param : 0u;
+}
+// Validity of row k of an ANF table (shared by alloc, the JIT and the patcher); `nodes` = the whole table (source types)
+static inline const char *cproc_node_check(const cproc_cuda_node *nodes, uint32_t k, uint32_t n_inputs) {
+    const cproc_cuda_node &nd = nodes[k];
     const uint32_t kind = CPROC_CUDA_NODE_KIND(nd.type), arg = CPROC_CUDA_NODE_ARG(nd.type);
-    if (kind > CPROC_CUDA_NODE_PDM || (nd.type >> 16)) return "unknown node type";
+    if (kind >= CPROC_CUDA_NODE_KINDS || (nd.type >> 16)) return "unknown node type";
     if (kind == CPROC_CUDA_NODE_GLIDE && (arg < 1 || arg > 24)) return "glide needs a control divider log2 of 1..24";
     if (kind == CPROC_CUDA_NODE_PDM && ((arg & 7u) < 1 || (arg & 7u) > 4)) return "pdm order must be 1..4";
-    if (kind <= CPROC_CUDA_NODE_EDGE && arg) return "acc / edge take no config word";
-    if (nd.src >= (int32_t)k) return "reads a node that is not bound yet (ANF)";
-    if (nd.src < 0 && (uint32_t)(-(nd.src + 1)) >= n_inputs) return "reads an input stream that does not exist";
-    if (kind == CPROC_CUDA_NODE_PDM) {
-        if (nd.src2 >= (int32_t)k) return "second input reads a node that is not bound yet (ANF)";
-        if (nd.src2 < 0 && (uint32_t)(-(nd.src2 + 1)) >= n_inputs) return "second input reads an input stream that does not exist";
+    if (kind != CPROC_CUDA_NODE_GLIDE && kind != CPROC_CUDA_NODE_PDM && arg) return "this processor takes no config word";
+    const cproc_kind_meta &m = k_cproc_kinds[kind];
+    for (uint32_t j = 0; j < m.n_input; ++j) {
+        const int32_t src = j ? nd.src2 : nd.src;
+        if (src == CPROC_CUDA_SRC_ZERO) { if (kind <= CPROC_CUDA_NODE_PDM) return "input not connected"; continue; }   // the reference processors' inputs are always named
+        if (src >= (int32_t)k) return j ? "second input reads a node that is not bound yet (ANF)" : "reads a node that is not bound yet (ANF)";
+        if (src < 0 && (uint32_t)(-(src + 1)) >= n_inputs) return j ? "second input reads an input stream that does not exist" : "reads an input stream that does not exist";
+        if (src >= 0 && cproc_kind_out_float(nodes[src].type) && !((m.input_f >> j) & 1u)) return "a float output feeds an integer input (undefined in C for negative values)";
     }
     return nullptr;
 }

@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert hasattr(raw, n), "libcproc_cuda.so does not export %s" % n
         assert n in abi.SYMBOLS, "abi.py does not bind %s" % n
     assert sorted(abi.SYMBOLS) == names
-    assert abi.lib.cproc_cuda_abi_version() == 2
+    assert abi.lib.cproc_cuda_abi_version() == 3
 
 
 def test_header_is_plain_c99(tmp_path):

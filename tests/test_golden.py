@@ -21,6 +21,10 @@ class OracleBackend:
         N, n_in, F = inp.shape
         return self.o.graph_run(rows, n_in, len(rows) - 1, state, N, F, np.ascontiguousarray(inp), changed)
 
+    def graph_ext(self, rows, n_in, outs, state, prm, inp, changed):
+        N, F = state.shape[0], inp.shape[-1]
+        return self.o.graph_run_ext(rows, n_in, outs, state, prm, N, F, inp, changed)
+
     def pdm(self, order, state, inp, dither):
         N, F = inp.shape
         return self.o.pdm_run(order, state, N, F, inp, None, 24, dither)
@@ -58,6 +62,19 @@ class CudaBackend:
         b = self.ctx.batch(st.GRAPH, N, nodes=rows, n_inputs=n_in)
         b.upload_state(state)
         out = np.zeros((N, F), np.uint32)
+        b.run(F, inp=np.ascontiguousarray(inp), in2=changed, out=out)
+        state[:] = b.download_state()
+        b.free()
+        return out
+
+    def graph_ext(self, rows, n_in, outs, state, prm, inp, changed):
+        st = self.st
+        N, F = state.shape[0], inp.shape[-1]
+        b = self.ctx.batch(st.GRAPH, N, nodes=rows, n_inputs=n_in, out_node=list(outs))
+        b.upload_state(state)
+        if prm is not None and prm.shape[1]:
+            b.upload_param(prm)
+        out = np.zeros((N, len(outs), F), np.uint32)
         b.run(F, inp=np.ascontiguousarray(inp), in2=changed, out=out)
         state[:] = b.download_state()
         b.free()
@@ -228,3 +245,28 @@ def test_golden_pixi_lfo_bank_is_acc_under_a_12_bit_mask(be):
     out = be.graph([(po.NODE_ACC, -1, 0xFFFFFFFF)], state, inp, None)
     assert np.array_equal((out & 0xFFF).reshape(K, D, T).transpose(0, 2, 1), trace.astype(np.uint32))
     assert np.array_equal((state[:, 0] & 0xFFF).reshape(K, D), dac1.astype(np.uint32))
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_golden_extension_processor_graphs(be, k):
+    """include/cproc_ext.h compiled against the reference's cproc.h (DEF_PROC bodies), on node tables that mix the
+    extension processors with acc / edge."""
+    rows = [tuple(int(x) for x in r) for r in G2["ext%d_rows" % k]]
+    prm, inp, chg = G2["ext%d_param" % k].copy(), G2["ext%d_in" % k].copy(), G2["ext%d_changed" % k]
+    state = np.zeros_like(G2["ext%d_state" % k])
+    outs = list(range(len(rows)))[-3:]
+    out = be.graph_ext(rows, 2, outs, state, prm if prm.shape[1] else None, inp, chg.copy() if chg.size else None)
+    assert np.array_equal(out, G2["ext%d_out" % k]) and np.array_equal(state, G2["ext%d_state" % k])
+
+
+def test_golden_graph_texts_compiled_as_c(be):
+    """tests/golden/ext_voice.cproc / ext_chain.cproc compiled as C with the reference's PROC / PROC_COND macros."""
+    from synth_tools_b200 import abi
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name, n_in in (("voice", 1), ("chain", 2)):
+        g = abi.graph_parse_ex(open(os.path.join(here, "ext_%s.cproc" % name)).read())
+        inp = G2["ext%s_in" % name].reshape(1, n_in, -1).copy()
+        chg = G2["extchain_changed"].reshape(1, -1).copy() if name == "chain" else None
+        state = np.zeros((1, sum(po.node_words(r[0]) for r in g["rows"])), np.uint32)
+        out = be.graph_ext(g["rows"], n_in, g["out_nodes"], state, g["param_init"].reshape(1, -1).copy(), inp, chg)
+        assert np.array_equal(out[0], G2["ext%s_out" % name]), name

@@ -127,6 +127,12 @@ def cpu_baselines():
     put("c4", v, "voice-samples/s", 1, "port", "%d voices x %d frames, stereo mix, one thread" % (N, F))
     vr = _cpu_time(lambda: orc.xvoice_run(sx, px, N, F, want_mix=False), N * F)
     put("c5", vr, "variant-frames/s", 1, "port", "%d variants x %d frames, raw stereo out, one thread (sequential in time)" % (N, F))
+    # the same voice as a graph of DEF_PROC processors (include/cproc_ext.h compiled against the reference's cproc.h), one thread
+    N, F = 2048, 512
+    grows = [(po.NODE_PHASOR_F, po.SRC_ZERO, 0xFFFFFFFF), (po.NODE_SVF, 0, 0xFFFFFFFF), (po.NODE_ENV, 1, 0xFFFFFFFF), (po.NODE_GAIN, 2, 0xFFFFFFFF), (po.NODE_GAIN, 2, 0xFFFFFFFF)]
+    gp = np.ascontiguousarray(px[:N].view(np.uint32).reshape(N, 8)); gs = np.zeros((N, 9), np.uint32)
+    v = _cpu_time(lambda: lib.graph_run_ext(grows, 0, [3, 4], gs, gp, N, F), N * F)
+    put("graph_voice", v, "ticks/s", 1 if kind == "reference" else cores, "port", "%d instances x %d ticks (cproc_ext.h DEF_PROC bodies behind a node table%s)" % (N, F, ", one thread" if kind == "reference" else ", OpenMP"))
     # C4': synth_run / sum_tick_saw of linux/synth.c:169-202, 64-voice synths
     NS, F = 2048 * max(1, cores // 8), 512
     vv = np.zeros((NS * 64, 2), np.uint32); vv[:, 0] = note_incs(rng, NS * 64); vv[:, 1] = rng.integers(0, 2**32, NS * 64, dtype=np.uint32)
@@ -532,6 +538,34 @@ def graph_bp5(st, ctx, hbm_peak, reps=3, layout="planar"):
                 hbm_peak, "4 B in + 4 B out per tick; 4 GiB in + 4 GiB out")
 
 
+VOICE_GRAPH_TEXT = """#define CPROC_NB_INPUTS 0
+    void cproc_update(w *input, w g) {
+        PROC(osc, phasor_f, NULL, &osc_p);
+        PROC(flt, svf, NULL, &flt_p, .in = osc.out);
+        PROC(amp, env, NULL, &amp_p, .in = flt.out);
+        PROC(left, gain, NULL, &left_p, .in = amp.out);
+        PROC(right, gain, NULL, &right_p, .in = amp.out);
+        cproc_output_f(0, left.out);
+        cproc_output_f(1, right.out); }"""
+
+
+def graph_voice(st, ctx, hbm_peak, reps=3, layout="planar"):
+    """SURVEY 8 a-X as cproc processors: the C4 voice (phasor_f -> svf -> env -> pan gains, include/cproc_ext.h) written as
+    generated graph text, parsed and rendered by the kernel NVRTC compiles for it; raw stereo float out, no input stream."""
+    rng = np.random.default_rng(12)
+    g = st.graph_parse_ex(VOICE_GRAPH_TEXT)
+    N, F = 2 * 1024 * 1024, 512
+    stt, prm = xvoice_records(rng, N)
+    gst = np.zeros((N, 9), np.uint32); gst[:, 1] = stt[:, 0]
+    d_out = ctx.dev_alloc(8 * N * F)
+    b = ctx.batch(st.GRAPH, N, nodes=g["rows"], n_inputs=0, out_node=g["out_nodes"], layout=st.PLANAR if layout == "planar" else st.INTERLEAVED)
+    b.upload_state(gst); b.upload_param(prm)
+    ms = _time(ctx, lambda: b.run_dev(F, out=d_out), reps)
+    b.free(); ctx.dev_free(d_out)
+    return _hbm("C4 voice as a generated cproc graph (phasor_f -> svf -> env -> 2 x gain, cproc_ext.h), 2 Mi instances x 512 ticks, %s float out x 2, NVRTC kernel" % layout,
+                N * F, "ticks", ms, 8.0, hbm_peak, "0 B in + 8 B out per tick (8 GiB out); bit-identical to k_xvoice raw output (tests/test_graph_ext.py)")
+
+
 def pdm_raw(st, ctx, hbm_peak, reps=3):
     """pdm2_update (stm32f103/pdm.h) on a caller-supplied input stream, planar uint32 in / out."""
     rng = np.random.default_rng(10)
@@ -571,6 +605,7 @@ def run_all(st, ctx, hbm_peak):
                     ("c3b", lambda: c3b(st, ctx)), ("c4", lambda: c4(st, ctx)), ("c4p", lambda: c4p(st, ctx)),
                     ("c5", lambda: c5(st, ctx, hbm_peak, layout="tiled")), ("c5", lambda: c5(st, ctx, hbm_peak, layout="planar")),
                     ("graph_bp5", lambda: graph_bp5(st, ctx, hbm_peak, layout="planar")), ("graph_bp5", lambda: graph_bp5(st, ctx, hbm_peak, layout="interleaved")),
+                    ("graph_voice", lambda: graph_voice(st, ctx, hbm_peak, layout="planar")), ("graph_voice", lambda: graph_voice(st, ctx, hbm_peak, layout="interleaved")),
                     ("pdm_raw", lambda: pdm_raw(st, ctx, hbm_peak)), ("c1_long", lambda: c1_long(st, ctx))):
         try:
             row = fn()

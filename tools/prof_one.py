@@ -94,6 +94,18 @@ elif which in ("graph", "graph_il"):
     b = ctx.batch(st.GRAPH, N, nodes=rows, layout=st.INTERLEAVED if which == "graph_il" else st.PLANAR)
     ms = timed(lambda: b.run_dev(F, inp=d_in, out=d_out))
     print("%s: %.3f ms  %.0f GB/s  %.1f G ticks/s  [%s]" % (which, ms, 8 * N * F / ms / 1e6, N * F / ms / 1e6, b.jit_log.strip()))
+elif which in ("gvoice", "gvoice_il"):
+    # the C4 voice as a generated graph of extension processors: no input stream, two float output streams
+    from tools.bench_configs import VOICE_GRAPH_TEXT
+    g = st.graph_parse_ex(VOICE_GRAPH_TEXT)
+    N, F = 2 * 1024 * 1024, 512
+    stt, prm = xvoice_records(N)
+    gst = np.zeros((N, 9), np.uint32); gst[:, 1] = stt[:, 0]
+    d_out = ctx.dev_alloc(8 * N * F)
+    b = ctx.batch(st.GRAPH, N, nodes=g["rows"], n_inputs=0, out_node=g["out_nodes"], layout=st.INTERLEAVED if which == "gvoice_il" else st.PLANAR)
+    b.upload_state(gst); b.upload_param(prm)
+    ms = timed(lambda: b.run_dev(F, out=d_out))
+    print("%s: %.3f ms  %.0f GB/s  %.1f G ticks/s  [%s]" % (which, ms, 8 * N * F / ms / 1e6, N * F / ms / 1e6, b.jit_log.strip()))
 elif which == "onepole_long":
     # 4 instances x 16 Mi frames: sequential kernel vs time-parallel scan
     N, F = 4, 16 * 1024 * 1024
