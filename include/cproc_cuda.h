@@ -434,6 +434,8 @@ int  cproc_cuda_timer_stop(cproc_cuda_ctx *ctx, float *elapsed_ms);
  *   pdm_planar_bulk  0/2  [2]  PDM v2 PLANAR duty rows: scattered 16-byte stores, tensor-TMA boxes
  *   pdm_v1_chains    1/2  [2]  PDM v1: PRNG chains per lane
  *   pdm_block, pdm_tpb [1: thread per bank when bank_size <= 4], pdm_persist, pdm_warps_per_smsp   plain PDM kernels, PDM v1 schedule
+ *   xvoice_mix2      0/1  [1]  XVOICE mix-only render: voice pairs on the packed fp32 pipe (FFMA2) with state tiles in shared
+ *                              memory; 0 = the scalar kernel (state through L2 once per 32-frame chunk)
  *   xvoice_chunk [0 = auto], xvoice_groups 0..8 [0 = one group], xvoice_closed 0/1 [1]
  *                              XVOICE_SCAN: frames per time chunk, variant groups, closed-form zero-state pass
  *   run_graph        0..3 [2]  cproc_cuda_run on small host buffers: staged copies, CUDA graph with copy nodes,

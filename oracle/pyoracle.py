@@ -73,6 +73,8 @@ def build(force=False):
     if os.path.isdir(os.environ.get("REF", "/root/reference")):
         recipe = [os.path.join(HERE, "build_ref.sh")] + [os.path.join(d, f) for d in (os.path.join(HERE, "ref"), os.path.join(HERE, "shim"), os.path.join(HERE, "shim", "stm32"))
                                                          for f in os.listdir(d) if os.path.isfile(os.path.join(d, f))]
+        root = os.path.dirname(HERE)                       # the extension processors and the graph texts are compiled into libref too
+        recipe += [os.path.join(root, "include", "cproc_ext.h")] + [os.path.join(root, "tests", "golden", f) for f in os.listdir(os.path.join(root, "tests", "golden")) if f.endswith(".cproc")]
         if force or not os.path.exists(REF_SO) or not os.path.exists(REF_O3_SO) or os.path.getmtime(REF_O3_SO) < max(os.path.getmtime(f) for f in recipe):
             subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
 

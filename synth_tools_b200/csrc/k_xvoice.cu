@@ -33,12 +33,17 @@ struct XV {
     float lp, bp, env, f, q, att, rel, gl, gr;
 };
 
+// phase += inc on the ALU pipe.  ptxas turns a plain 32-bit add into IMAD.IADD half of the time to "balance" the pipes; here the FMA
+// pipe is the busy one (FFMA2 / FADD2 / FMUL2 / I2FP hold it for two cycles each): 24 % of the kernel's stall samples sat on those
+// IMADs (profiles/r2_xvoice_mix2_summary.txt).  An add with carry-out can only be an IADD3.
+__device__ __forceinline__ void xv_add_alu(uint32_t &x, uint32_t inc) { asm("add.cc.u32 %0, %0, %1;" : "+r"(x) : "r"(inc)); }
+
 // x = (float)(int)phase * 2^-31 is exact (a power-of-two scale of a 24-bit float, no
 // underflow), so hp = x - lp (one rounding) is computed as fma(xi, 2^-31, -lp): the
 // same bits, one instruction less.
 __device__ __forceinline__ void xvoice_svf(XV &v, float &lp_out) {
     const float xi = __int2float_rn((int32_t)v.phase);
-    v.phase += v.inc;
+    xv_add_alu(v.phase, v.inc);
     const float lp = __fmaf_rn(v.f, v.bp, v.lp);
     float hp = __fmaf_rn(xi, 0x1p-31f, -lp);
     hp = __fmaf_rn(-v.q, v.bp, hp);
@@ -188,6 +193,47 @@ __device__ __forceinline__ void xv_load(XV &v, const XVoiceParams &p, uint64_t i
 }
 __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
+// The launch's own final reduction (shared by both mix kernels): the last n_fin blocks to leave take one chunk (and every
+// n_fin-th) each and add the block rows in a fixed order; with a mix bus attached they push their columns to the peers.
+__device__ __forceinline__ void xm_finish(const XVoiceParams &p, const BusFused &bf, const uint32_t n_chunks, uint32_t &tick_s) {
+    const uint32_t nb = p.n_render_blocks;
+    const uint32_t n_fin = n_chunks < nb ? n_chunks : nb;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) tick_s = atomicAdd(p.done, 1u);
+    __syncthreads();
+    const uint32_t tk = tick_s;
+    if (tk < nb - n_fin) return;
+    if (threadIdx.x == 0) while (ld_acquire_gpu_u32(p.done) < nb) __nanosleep(64);       // the stragglers are resident: they arrive
+    __syncthreads();
+    for (uint32_t c = tk - (nb - n_fin); c < n_chunks; c += n_fin) {
+        const uint64_t t0 = (uint64_t)c * XM_CHUNK;
+        const uint32_t cols = p.F - t0 < XM_CHUNK ? (uint32_t)(p.F - t0) : XM_CHUNK;
+        const uint32_t col = threadIdx.x >> 1, half = threadIdx.x & 1u, ch = col / XM_CHUNK, f = col % XM_CHUNK;
+        const uint32_t b0 = half ? (nb + 1) / 2 : 0u, b1 = half ? nb : (nb + 1) / 2;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        if (f < cols) {
+            const float *src = p.partial + (uint64_t)ch * p.F + t0 + f;
+            uint32_t bq = b0;
+            for (; bq + 4 <= b1; bq += 4) {
+                s0 = __fadd_rn(s0, __ldcg(src + (uint64_t)(bq + 0) * 2 * p.F)); s1 = __fadd_rn(s1, __ldcg(src + (uint64_t)(bq + 1) * 2 * p.F));
+                s2 = __fadd_rn(s2, __ldcg(src + (uint64_t)(bq + 2) * 2 * p.F)); s3 = __fadd_rn(s3, __ldcg(src + (uint64_t)(bq + 3) * 2 * p.F));
+            }
+            for (; bq < b1; ++bq) s0 = __fadd_rn(s0, __ldcg(src + (uint64_t)bq * 2 * p.F));
+        }
+        float s = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+        const float o = __shfl_xor_sync(0xFFFFFFFFu, s, 1);
+        s = half ? __fadd_rn(o, s) : __fadd_rn(s, o);
+        if (!half && f < cols) {
+            const uint64_t idx = (uint64_t)ch * p.F + t0 + f;
+            if (bf.world) bus_emit_word(bf, idx, __float_as_uint(s)); else p.mix[idx] = s;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(p.done + 1, 1u) == n_fin - 1u) { p.done[0] = 0; p.done[1] = 0; __threadfence(); }   // ready for the next launch
+    if (bf.world) bus_participant_done(bf);
+}
+
 __global__ void __launch_bounds__(XM_BLOCK, 4) k_xvoice_mix(const XVoiceParams p, const BusFused bf) {
     __shared__ float red[2 * XM_CHUNK][XM_BLOCK + 1];
     __shared__ uint32_t tick_s;
@@ -285,43 +331,235 @@ __global__ void __launch_bounds__(XM_BLOCK, 4) k_xvoice_mix(const XVoiceParams p
             __syncthreads();
         }
     }
-    // ---- the launch's own final reduction: the last n_fin blocks to leave take one chunk (and every n_fin-th) each
-    const uint32_t nb = p.n_render_blocks;
-    const uint32_t n_fin = n_chunks < nb ? n_chunks : nb;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) tick_s = atomicAdd(p.done, 1u);
-    __syncthreads();
-    const uint32_t tk = tick_s;
-    if (tk < nb - n_fin) return;
-    if (threadIdx.x == 0) while (ld_acquire_gpu_u32(p.done) < nb) __nanosleep(64);       // the stragglers are resident: they arrive
-    __syncthreads();
-    for (uint32_t c = tk - (nb - n_fin); c < n_chunks; c += n_fin) {
-        const uint64_t t0 = (uint64_t)c * XM_CHUNK;
-        const uint32_t cols = p.F - t0 < XM_CHUNK ? (uint32_t)(p.F - t0) : XM_CHUNK;
-        const uint32_t col = threadIdx.x >> 1, half = threadIdx.x & 1u, ch = col / XM_CHUNK, f = col % XM_CHUNK;
-        const uint32_t b0 = half ? (nb + 1) / 2 : 0u, b1 = half ? nb : (nb + 1) / 2;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        if (f < cols) {
-            const float *src = p.partial + (uint64_t)ch * p.F + t0 + f;
-            uint32_t bq = b0;
-            for (; bq + 4 <= b1; bq += 4) {
-                s0 = __fadd_rn(s0, __ldcg(src + (uint64_t)(bq + 0) * 2 * p.F)); s1 = __fadd_rn(s1, __ldcg(src + (uint64_t)(bq + 1) * 2 * p.F));
-                s2 = __fadd_rn(s2, __ldcg(src + (uint64_t)(bq + 2) * 2 * p.F)); s3 = __fadd_rn(s3, __ldcg(src + (uint64_t)(bq + 3) * 2 * p.F));
-            }
-            for (; bq < b1; ++bq) s0 = __fadd_rn(s0, __ldcg(src + (uint64_t)bq * 2 * p.F));
-        }
-        float s = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
-        const float o = __shfl_xor_sync(0xFFFFFFFFu, s, 1);
-        s = half ? __fadd_rn(o, s) : __fadd_rn(s, o);
-        if (!half && f < cols) {
-            const uint64_t idx = (uint64_t)ch * p.F + t0 + f;
-            if (bf.world) bus_emit_word(bf, idx, __float_as_uint(s)); else p.mix[idx] = s;
-        }
+    xm_finish(p, bf, n_chunks, tick_s);
+}
+
+// ---- mix kernel, second generation: voice PAIRS on the packed fp32 pipe, state tiles resident in shared memory ----------
+// (1) Blackwell's fma / add / mul .f32x2 (SASS FFMA2 / FADD2 / FMUL2) work on two floats in an aligned register pair: one
+//     instruction slot, the FMA pipe busy for two (tools/ubench_f32x2.cu: 63 /clk/SM against 117 for FFMA, and an ALU-pipe
+//     instruction issues beside it for free).  The scalar kernel is ISSUE bound (14.5 instructions per voice-sample at 67 %
+//     issue, FMA pipe 45 %, profiles/r2_xvoice_mix_summary.txt): a thread now walks its voices two at a time, the SVF (4),
+//     the envelope add (1) and the output multiply (1) of both voices in six packed instructions instead of twelve; every
+//     lane of a packed operation is the same single IEEE rounding as the scalar one, so results stay bit-exact per voice.
+//     The pipe has no operand negation in PTX, so a chunk works on -lp and -env (exact mirror images: rounding is
+//     sign-symmetric; the zero cases are spelled out at the clamp) and flips them back when it stores.
+// (2) The scalar kernel moves every voice's state and parameters through L2 / DRAM once per 32-frame chunk (4.4 GB per
+//     4 Mi x 512 launch, 18 x the algorithmic bytes).  Here a block owns a contiguous range of voices, cuts it into tiles
+//     whose STATE (5 words per voice) sits in shared memory for all the chunks of the launch, and DRAM sees the state once
+//     in and once out; the parameters (read-only, 8 words) come through L1 / L2 per chunk.  Ranges are dealt in groups of
+//     256 voices (one pair per thread) so that every block has 36 or 37 pair-chunks per thread and chunk at 4 Mi voices.
+// Per tile and chunk the block reduces its 2 x 32 accumulators per thread through a 16 KB column buffer (left, then right)
+// into its partial row; the launch's final reduction and the bus exchange are those of the first kernel (xm_finish).
+#define XM2_BLOCK 128
+#ifndef XM2_GMAX
+#define XM2_GMAX 11                                  // groups (of 256 voices) per tile: 11 x 5 KB of state
+#endif
+#ifndef XM2_MINB
+#define XM2_MINB 3                                   // resident blocks per SM (register cap 168)
+#endif
+typedef unsigned long long xv2_t;                    // {lo: voice A, hi: voice B}
+__device__ __forceinline__ xv2_t xv2_pack(float lo, float hi) { xv2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ xv2_t xv2_packu(uint32_t lo, uint32_t hi) { xv2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ float xv2_lo(xv2_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float xv2_hi(xv2_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ xv2_t xv2_fma(xv2_t a, xv2_t b, xv2_t c) { xv2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ xv2_t xv2_add(xv2_t a, xv2_t b) { xv2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ xv2_t xv2_mul(xv2_t a, xv2_t b) { xv2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ xv2_t xv2_neg(xv2_t a) { return a ^ 0x8000000080000000ull; }
+
+// attack mask of one voice for a chunk (bit k: tick k is in the attack phase) and whether the chunk is uniform
+__device__ __forceinline__ uint32_t xv_amask(uint32_t t, uint32_t gate) {
+    if (t <= 0xFFFFFFFFu - XM_CHUNK) {
+        const uint32_t rem = t < gate ? gate - t : 0u;
+        return rem >= 32u ? 0xFFFFFFFFu : (1u << rem) - 1u;
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(p.done + 1, 1u) == n_fin - 1u) { p.done[0] = 0; p.done[1] = 0; __threadfence(); }   // ready for the next launch
-    if (bf.world) bus_participant_done(bf);
+    uint32_t m = 0;                                    // the frame counter wraps inside the chunk
+    for (uint32_t k = 0; k < XM_CHUNK; ++k) m |= (uint32_t)(t + k < gate) << k;
+    return m;
+}
+
+__global__ void __launch_bounds__(XM2_BLOCK, XM2_MINB) k_xvoice_mix2(const XVoiceParams p, const BusFused bf) {
+    extern __shared__ __align__(16) uint32_t xm2_tile[];            // [5][256 * ng]: phase, lp, bp, env, t of the tile's voices
+    // column buffer of the block reduction: element (frame k, thread t) at k * 161 + (t >> 5) * 40 + (t & 31).  Writers (a warp: one
+    // k, 32 consecutive t) and readers (a warp: 8 columns x 4 quarters of 32 rows, the same row offset) both touch 32 distinct banks:
+    // bank = k + 8 * (t >> 5) + (t & 31) mod 32.
+    __shared__ float red[XM_CHUNK * 161];
+    __shared__ uint32_t tick_s;
+    if (blockIdx.x >= p.n_render_blocks) { bus_exchange_block(bf); return; }      // pipelined bus: the previous frame block's exchange
+    const uint32_t nb = p.n_render_blocks, tid = threadIdx.x;
+    const uint32_t n_chunks = (uint32_t)((p.F + XM_CHUNK - 1) / XM_CHUNK);
+    const uint64_t G = (p.n + 255) / 256;
+    const uint64_t g_lo = G * blockIdx.x / nb, g_hi = G * (blockIdx.x + 1) / nb;
+    const uint32_t kg = (uint32_t)(g_hi - g_lo), nt = (kg + XM2_GMAX - 1) / XM2_GMAX;
+    if (kg == 0)                                                    // more blocks than groups: an all-zero partial row
+        for (uint64_t idx = tid; idx < 2 * p.F; idx += XM2_BLOCK) p.partial[(uint64_t)blockIdx.x * 2 * p.F + idx] = 0.0f;
+    const xv2_t c31 = xv2_pack(0x1p-31f, 0x1p-31f);
+    for (uint32_t ti = 0; ti < nt; ++ti) {
+        const uint64_t ga = g_lo + (uint64_t)kg * ti / nt, gb = g_lo + (uint64_t)kg * (ti + 1) / nt;
+        const uint32_t ng = (uint32_t)(gb - ga), TV = ng * 256;
+        const uint64_t v0 = ga * 256;
+        // ---- tile state in: [5][npad] rows -> shared memory, two adjacent voices per thread and group
+        for (uint32_t w = 0; w < 5; ++w)
+            for (uint32_t j = 0; j < ng; ++j) {
+                const uint32_t idx = 2 * (tid + XM2_BLOCK * j);
+                const uint64_t gi = v0 + idx;
+                uint2 val = make_uint2(0u, 0u);
+                if (gi < p.npad) val = __ldcs((const uint2 *)(p.st + (uint64_t)w * p.npad + gi));     // npad % 4 == 0: the pair never straddles the row end; [n, npad) is zero
+                *(uint2 *)(xm2_tile + w * TV + idx) = val;
+            }
+        __syncthreads();
+        auto load_prm = [&](uint32_t j, uint2 (&q)[8]) {
+            const uint64_t gi = v0 + 2 * (tid + XM2_BLOCK * j);
+#pragma unroll
+            for (int w = 0; w < 8; ++w) q[w] = gi < p.npad ? __ldg((const uint2 *)(p.prm + (uint64_t)w * p.npad + gi)) : make_uint2(0u, 0u);
+        };
+        uint2 nq[8];
+        load_prm(0, nq);
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            const uint64_t t0 = (uint64_t)c * XM_CHUNK;
+            const uint32_t cols = p.F - t0 < XM_CHUNK ? (uint32_t)(p.F - t0) : XM_CHUNK;
+            float aL[XM_CHUNK], aR[XM_CHUNK];
+#pragma unroll
+            for (int k = 0; k < XM_CHUNK; ++k) { aL[k] = 0.f; aR[k] = 0.f; }
+#pragma unroll 1
+            for (uint32_t j = 0; j < ng; ++j) {
+                uint2 q[8];
+#pragma unroll
+                for (int w = 0; w < 8; ++w) q[w] = nq[w];
+                if (j + 1 < ng) load_prm(j + 1, nq); else if (c + 1 < n_chunks) load_prm(0, nq);
+                uint32_t *sp = xm2_tile + 2 * (tid + XM2_BLOCK * j);
+                uint2 ph = *(uint2 *)sp, slp = *(uint2 *)(sp + TV), sbp = *(uint2 *)(sp + 2 * TV), sen = *(uint2 *)(sp + 3 * TV), stt = *(uint2 *)(sp + 4 * TV);
+                const uint32_t mA = xv_amask(stt.x, q[5].x), mB = xv_amask(stt.y, q[5].y);
+                // The clamped envelope e' = min(max(e + d, +0), 1), d = +attack or -release, is the two-branch envelope of the oracle
+                // whenever the rates have a clear sign bit and +0 <= env <= 1 (bit patterns below; excludes NaN and -0.0): the clamp
+                // that does not belong to the phase is an identity.  `sane`: true for both voices of every lane of the warp.
+                const bool sane = q[3].x <= 0x7F800000u && q[3].y <= 0x7F800000u && q[4].x <= 0x7F800000u && q[4].y <= 0x7F800000u &&
+                                  sen.x <= 0x3F800000u && sen.y <= 0x3F800000u;
+                // `uni`: moreover the whole chunk lies in one envelope phase for every voice (sustained or released voices: the
+                // steady state of a mix), so d is a chunk constant; otherwise it is selected per tick from the attack mask
+                const bool uni = (mA == 0u || mA == 0xFFFFFFFFu) && (mB == 0u || mB == 0xFFFFFFFFu);
+                const bool all_sane = __all_sync(0xFFFFFFFFu, sane), all_uni = __all_sync(0xFFFFFFFFu, uni);
+                if (cols == XM_CHUNK && all_sane) {
+                    uint32_t phA = ph.x, phB = ph.y;
+                    const uint32_t incA = q[0].x, incB = q[0].y;
+                    const xv2_t f2 = xv2_packu(q[1].x, q[1].y), nf2 = xv2_neg(f2), nq2 = xv2_neg(xv2_packu(q[2].x, q[2].y));
+                    xv2_t nlp = xv2_neg(xv2_packu(slp.x, slp.y)), bp = xv2_packu(sbp.x, sbp.y);
+                    float neA = -__uint_as_float(sen.x), neB = -__uint_as_float(sen.y);
+                    const float glA = __uint_as_float(q[6].x), glB = __uint_as_float(q[6].y), grA = __uint_as_float(q[7].x), grB = __uint_as_float(q[7].y);
+                    // one tick of the pair; nd = {-dA, -dB}   (XM2_EXP_*: timing experiments of tools/sweep_xmix2.sh, wrong results)
+#ifdef XM2_EXP_NO_I2F
+#define XM2_XI(a, b) xv2_packu(a, b)
+#else
+#define XM2_XI(a, b) xv2_pack(__int2float_rn((int32_t)(a)), __int2float_rn((int32_t)(b)))
+#endif
+#ifdef XM2_EXP_NO_ENV
+#define XM2_ENV(nd)
+#else
+#define XM2_ENV(nd) const xv2_t sm_ = xv2_add(xv2_pack(neA, neB), nd); \
+                        neA = fmaxf(fminf(xv2_lo(sm_), -0.0f), -1.0f); neB = fmaxf(fminf(xv2_hi(sm_), -0.0f), -1.0f);
+#endif
+#ifdef XM2_EXP_NO_MIX
+#define XM2_MIX(k) aL[k & 1] = __fadd_rn(aL[k & 1], yA); aR[k & 1] = __fadd_rn(aR[k & 1], yB);
+#else
+#define XM2_MIX(k) aL[k] = __fmaf_rn(glA, yA, aL[k]); aR[k] = __fmaf_rn(grA, yA, aR[k]); \
+                        aL[k] = __fmaf_rn(glB, yB, aL[k]); aR[k] = __fmaf_rn(grB, yB, aR[k]);
+#endif
+#define XM2_TICK(k, nd) { \
+                        const xv2_t xi = XM2_XI(phA, phB); \
+                        xv_add_alu(phA, incA); xv_add_alu(phB, incB); \
+                        nlp = xv2_fma(nf2, bp, nlp);                    /* -(lp + f bp) */ \
+                        xv2_t hp = xv2_fma(xi, c31, nlp);               /* x - lp */ \
+                        hp = xv2_fma(nq2, bp, hp); \
+                        bp = xv2_fma(f2, hp, bp); \
+                        /* e' = min(max(e + d, +0), 1) mirrored: -e' = max(min(-e - d, -0), -1); a sum that is +0 where the mirror */ \
+                        /* image is -0 (e + d == 0) is put right by the clamp at -0 (min(+0, -0) = -0) */ \
+                        XM2_ENV(nd) \
+                        const xv2_t y = xv2_mul(nlp, xv2_pack(neA, neB));   /* (-lp)(-e) = lp e */ \
+                        const float yA = xv2_lo(y), yB = xv2_hi(y); \
+                        XM2_MIX(k) }
+                    if (all_uni) {
+                        const xv2_t nd = xv2_packu(mA ? q[3].x ^ 0x80000000u : q[4].x, mB ? q[3].y ^ 0x80000000u : q[4].y);
+#pragma unroll
+                        for (int k = 0; k < XM_CHUNK; ++k) XM2_TICK(k, nd)
+                    } else {
+                        const uint32_t naA = q[3].x ^ 0x80000000u, naB = q[3].y ^ 0x80000000u;       // -attack
+#pragma unroll
+                        for (int k = 0; k < XM_CHUNK; ++k) {
+                            const xv2_t nd = xv2_packu((mA >> k) & 1u ? naA : q[4].x, (mB >> k) & 1u ? naB : q[4].y);
+                            XM2_TICK(k, nd)
+                        }
+                    }
+#undef XM2_TICK
+#undef XM2_XI
+#undef XM2_ENV
+#undef XM2_MIX
+                    const xv2_t lp = xv2_neg(nlp);
+                    ph = make_uint2(phA, phB);
+                    slp = make_uint2(__float_as_uint(xv2_lo(lp)), __float_as_uint(xv2_hi(lp)));
+                    sbp = make_uint2(__float_as_uint(xv2_lo(bp)), __float_as_uint(xv2_hi(bp)));
+                    sen = make_uint2(__float_as_uint(-neA), __float_as_uint(-neB));
+                } else {
+                    // mixed envelope phases (or a short last chunk): the scalar tick of the first kernel, voice A then voice B
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        XV v;
+                        v.phase = h ? ph.y : ph.x; v.lp = __uint_as_float(h ? slp.y : slp.x); v.bp = __uint_as_float(h ? sbp.y : sbp.x);
+                        v.env = __uint_as_float(h ? sen.y : sen.x); v.t = 0; v.gate = 0;
+                        v.inc = h ? q[0].y : q[0].x; v.f = __uint_as_float(h ? q[1].y : q[1].x); v.q = __uint_as_float(h ? q[2].y : q[2].x);
+                        v.att = __uint_as_float(h ? q[3].y : q[3].x); v.rel = __uint_as_float(h ? q[4].y : q[4].x);
+                        v.gl = __uint_as_float(h ? q[6].y : q[6].x); v.gr = __uint_as_float(h ? q[7].y : q[7].x);
+                        const uint32_t am = h ? mB : mA;
+#pragma unroll
+                        for (int k = 0; k < XM_CHUNK; ++k) {
+                            if (k < (int)cols) {
+                                const float y = xvoice_tick_flag(v, (am >> k) & 1u);
+                                aL[k] = __fmaf_rn(v.gl, y, aL[k]);
+                                aR[k] = __fmaf_rn(v.gr, y, aR[k]);
+                            }
+                        }
+                        if (h) { ph.y = v.phase; slp.y = __float_as_uint(v.lp); sbp.y = __float_as_uint(v.bp); sen.y = __float_as_uint(v.env); }
+                        else { ph.x = v.phase; slp.x = __float_as_uint(v.lp); sbp.x = __float_as_uint(v.bp); sen.x = __float_as_uint(v.env); }
+                    }
+                }
+                stt.x += cols; stt.y += cols;
+                *(uint2 *)sp = ph; *(uint2 *)(sp + TV) = slp; *(uint2 *)(sp + 2 * TV) = sbp; *(uint2 *)(sp + 3 * TV) = sen; *(uint2 *)(sp + 4 * TV) = stt;
+            }
+            // ---- block reduction of the chunk: left, then right; 4 threads per column (32 rows each, 4 chains), combined in a fixed order
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+                for (int k = 0; k < XM_CHUNK; ++k) red[k * 161 + (tid >> 5) * 40 + (tid & 31)] = ch ? aR[k] : aL[k];
+                __syncthreads();
+                const uint32_t col = tid >> 2, qd = tid & 3u;
+                const float *row = &red[col * 161 + qd * 40];
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                for (int r = 0; r < XM2_BLOCK / 4; r += 4) {
+                    s0 = __fadd_rn(s0, row[r]); s1 = __fadd_rn(s1, row[r + 1]); s2 = __fadd_rn(s2, row[r + 2]); s3 = __fadd_rn(s3, row[r + 3]);
+                }
+                float sm = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+                sm = __fadd_rn(sm, __shfl_xor_sync(0xFFFFFFFFu, sm, 1));         // (q0 + q1), (q2 + q3): the same bits on both lanes of a pair
+                sm = __fadd_rn(sm, __shfl_xor_sync(0xFFFFFFFFu, sm, 2));         // (q0 + q1) + (q2 + q3)
+                if (qd == 0 && col < cols) {
+                    float *dst = p.partial + ((uint64_t)blockIdx.x * 2 + ch) * p.F + t0 + col;
+                    *dst = ti ? __fadd_rn(*dst, sm) : sm;                        // tiles accumulate in tile order
+                }
+                __syncthreads();
+            }
+        }
+        // ---- tile state out
+        for (uint32_t w = 0; w < 5; ++w)
+            for (uint32_t j = 0; j < ng; ++j) {
+                const uint32_t idx = 2 * (tid + XM2_BLOCK * j);
+                const uint64_t gi = v0 + idx;
+                const uint2 val = *(const uint2 *)(xm2_tile + w * TV + idx);
+                uint32_t *dst = p.st + (uint64_t)w * p.npad + gi;
+                if (gi + 1 < p.n) __stcs((uint2 *)dst, val);
+                else if (gi < p.n) dst[0] = val.x;
+            }
+        __syncthreads();
+    }
+    xm_finish(p, bf, n_chunks, tick_s);
 }
 
 // mix[c][t] = SUM_b partial[b][c][t], fixed order, 4 independent chains
@@ -832,7 +1070,9 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     const bool mix_only = io->mix && !io->out;
     if (b->bus && !mix_only) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice: with a mix bus attached only the mix is rendered (out must be NULL)");
     // (mix: four resident blocks per SM; a pipelined bus keeps one slot for the block that completes the previous exchange)
-    const uint64_t n_blocks = mix_only ? (uint64_t)ctx->n_sm * 4 - (b->bus && b->bus_mode == 2 ? 1 : 0) : ceil_div_u64(b->n, XV_BLOCK);
+    // (second-generation kernel: three blocks per SM, each with a 55 KB state tile)
+    const bool mix2 = mix_only && ctx->xvoice_mix2;
+    const uint64_t n_blocks = mix_only ? (uint64_t)ctx->n_sm * (mix2 ? XM2_MINB : 4) - (b->bus && b->bus_mode == 2 ? 1 : 0) : ceil_div_u64(b->n, XV_BLOCK);
     XVoiceParams p;
     p.st = b->d_state; p.prm = b->d_param; p.npad = b->npad; p.n = b->n; p.F = F;
     p.raw = (float *)io->out; p.layout = io->layout; p.partial = nullptr;
@@ -859,6 +1099,12 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
         BusFused bf;
         int rc = cproc_bus_fused_begin(b, &bf, 2 * F, 2u, 0u, n_chunks < n_blocks ? n_chunks : (uint32_t)n_blocks, (int32_t *)io->mix, nullptr);
         if (rc) return rc;
+        if (mix2) {
+            const size_t smem = sizeof(uint32_t) * 5 * 256 * XM2_GMAX;
+            static bool attr_set = false;
+            if (!attr_set) { CK(ctx, cudaFuncSetAttribute(k_xvoice_mix2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+            k_xvoice_mix2<<<(unsigned)n_blocks + (bf.world && bf.mode == 2 ? 1u : 0u), XM2_BLOCK, smem, ctx->stream>>>(p, bf);
+        } else
         k_xvoice_mix<<<(unsigned)n_blocks + (bf.world && bf.mode == 2 ? 1u : 0u), XM_BLOCK, 0, ctx->stream>>>(p, bf);
         CK_LAUNCH(ctx, "k_xvoice_mix");
         return 0;

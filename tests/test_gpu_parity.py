@@ -921,8 +921,17 @@ def _mix_close(mix, want_mix):
     assert snr >= 120.0
 
 
-@pytest.mark.parametrize("N,F", [(1000, 512), (77, 45), (148 * 4 * 128 + 333, 96), (1, 32)])
-def test_xvoice_mix_only(st, ctx, oracle, N, F):
+@pytest.fixture(params=[1, 0], ids=["mix2", "mix1"])
+def mixgen(request, ctx):
+    """Both generations of the mix-only XVOICE kernel: k_xvoice_mix2 (voice pairs on the packed fp32 pipe, state tiles in
+    shared memory; the default) and k_xvoice_mix."""
+    ctx.set_option("xvoice_mix2", request.param)
+    yield request.param
+    ctx.set_option("xvoice_mix2", 1)
+
+
+@pytest.mark.parametrize("N,F", [(1000, 512), (77, 45), (148 * 4 * 128 + 333, 96), (1, 32), (148 * 3 * 256 * 12 + 257, 64), (255, 33), (256, 32), (257, 70)])
+def test_xvoice_mix_only(st, ctx, oracle, N, F, mixgen):
     """Mix-only render (register accumulators per thread, voices walked per 32-frame
     chunk): mix within the stated tolerance of the oracle's double-accumulated mix
     (<= 1e-5 of the peak, >= 120 dB SNR), voice state bit-exact, deterministic."""
@@ -1100,7 +1109,7 @@ def test_onepole_scan(st, ctx, oracle, layout, N, F, chunk):
         ctx.set_option("xvoice_chunk", 0)
 
 
-def test_xvoice_mix_uniform_phase_chunks(st, ctx, oracle):
+def test_xvoice_mix_uniform_phase_chunks(st, ctx, oracle, mixgen):
     """Mix-only render where whole warps sit in one envelope phase (sustain at 1, released at 0,
     long attacks / releases) -- the three-instruction envelope path -- next to warps with gate
     crossings, negative and -0.0 rates and out-of-range envelopes, which must take the general path:
