@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(XM_BLOCK, 4) k_xvoice_mix(const XVoiceParams p
 // into its partial row; the launch's final reduction and the bus exchange are those of the first kernel (xm_finish).
 #define XM2_BLOCK 128
 #ifndef XM2_GMAX
-#define XM2_GMAX 11                                  // groups (of 256 voices) per tile: 11 x 5 KB of state
+#define XM2_GMAX 10                                  // groups (of 256 voices) per tile: 10 x 5 KB of state (+ 20 KB column buffer: three blocks per SM)
 #endif
 #ifndef XM2_MINB
 #define XM2_MINB 3                                   // resident blocks per SM (register cap 168)
@@ -1070,9 +1070,21 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     const bool mix_only = io->mix && !io->out;
     if (b->bus && !mix_only) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice: with a mix bus attached only the mix is rendered (out must be NULL)");
     // (mix: four resident blocks per SM; a pipelined bus keeps one slot for the block that completes the previous exchange)
-    // (second-generation kernel: three blocks per SM, each with a 55 KB state tile)
+    // (second-generation kernel: three blocks per SM, each with a 50 KB state tile; the launch's final reduction waits for the
+    // stragglers, so the grid must be co-resident: ask the runtime how many blocks really fit)
     const bool mix2 = mix_only && ctx->xvoice_mix2;
-    const uint64_t n_blocks = mix_only ? (uint64_t)ctx->n_sm * (mix2 ? XM2_MINB : 4) - (b->bus && b->bus_mode == 2 ? 1 : 0) : ceil_div_u64(b->n, XV_BLOCK);
+    static int mix2_per_sm = 0;
+    const size_t mix2_smem = sizeof(uint32_t) * 5 * 256 * XM2_GMAX;
+    if (mix2 && !mix2_per_sm) {
+        CK(ctx, cudaFuncSetAttribute(k_xvoice_mix2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mix2_smem));
+        CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mix2_per_sm, k_xvoice_mix2, XM2_BLOCK, mix2_smem));
+        if (mix2_per_sm < 1) return cproc_set_err(ctx, CPROC_CUDA_ECUDA, "xvoice: k_xvoice_mix2 does not fit an SM");
+        if (mix2_per_sm > XM2_MINB) mix2_per_sm = XM2_MINB;
+    }
+    // (the float mix depends on which block sums which voices: k_xvoice_mix2 always leaves the slot a pipelined bus needs for its
+    // exchange block free, so that the bits of the mix do not depend on whether, or how, a bus is attached)
+    const uint64_t n_blocks = !mix_only ? ceil_div_u64(b->n, XV_BLOCK)
+                            : mix2 ? (uint64_t)ctx->n_sm * mix2_per_sm - 1 : (uint64_t)ctx->n_sm * 4 - (b->bus && b->bus_mode == 2 ? 1 : 0);
     XVoiceParams p;
     p.st = b->d_state; p.prm = b->d_param; p.npad = b->npad; p.n = b->n; p.F = F;
     p.raw = (float *)io->out; p.layout = io->layout; p.partial = nullptr;
@@ -1100,10 +1112,7 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
         int rc = cproc_bus_fused_begin(b, &bf, 2 * F, 2u, 0u, n_chunks < n_blocks ? n_chunks : (uint32_t)n_blocks, (int32_t *)io->mix, nullptr);
         if (rc) return rc;
         if (mix2) {
-            const size_t smem = sizeof(uint32_t) * 5 * 256 * XM2_GMAX;
-            static bool attr_set = false;
-            if (!attr_set) { CK(ctx, cudaFuncSetAttribute(k_xvoice_mix2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-            k_xvoice_mix2<<<(unsigned)n_blocks + (bf.world && bf.mode == 2 ? 1u : 0u), XM2_BLOCK, smem, ctx->stream>>>(p, bf);
+            k_xvoice_mix2<<<(unsigned)n_blocks + (bf.world && bf.mode == 2 ? 1u : 0u), XM2_BLOCK, mix2_smem, ctx->stream>>>(p, bf);
         } else
         k_xvoice_mix<<<(unsigned)n_blocks + (bf.world && bf.mode == 2 ? 1u : 0u), XM_BLOCK, 0, ctx->stream>>>(p, bf);
         CK_LAUNCH(ctx, "k_xvoice_mix");

@@ -215,11 +215,14 @@ def xvoice_check_and_timing(N_check, N, F, reps=20):
     bus.allreduce(mix.data_ptr(), 2 * F, op=st.Bus.FSUM)
     torch.cuda.synchronize()
     g64, w64 = mix.cpu().numpy().astype(np.float64), np.asarray(want, np.float64).reshape(-1)
+    detail = {}
     ok = bus.status() == 0 and np.abs(g64 - w64).max() <= 1e-5 * np.abs(w64).max() and \
         10 * np.log10((w64 ** 2).sum() / max(((g64 - w64) ** 2).sum(), 1e-300)) >= 120.0
+    detail["separate_bus_within_tolerance"] = bool(ok)
     allmix = [torch.empty_like(mix) for _ in range(world)]
     dist.all_gather(allmix, mix)
-    ok = ok and all(torch.equal(allmix[0], m) for m in allmix)          # every rank holds the same bits
+    detail["identical_on_all_ranks"] = all(torch.equal(allmix[0], m) for m in allmix)
+    ok = ok and detail["identical_on_all_ranks"]          # every rank holds the same bits
     # the exchange fused into the render launch: the same bits as the separate bus kernel, in both modes, over 3 blocks
     for bus_mode in (1, 2):
         b.upload_state(np.ascontiguousarray(s0[lo:hi]).view(np.uint32).reshape(hi - lo, 5))
@@ -230,7 +233,9 @@ def xvoice_check_and_timing(N_check, N, F, reps=20):
         bus.flush()
         torch.cuda.synchronize()
         bus.detach(b)
-        ok = ok and torch.equal(m3[0], mix) and bus.status() == 0
+        detail["fused_mode%d_block0_equals_separate" % bus_mode] = bool(torch.equal(m3[0], mix)) and bus.status() == 0
+        detail["fused_mode%d_block0_max_abs_diff" % bus_mode] = float((m3[0] - mix).abs().max().item())
+        ok = ok and detail["fused_mode%d_block0_equals_separate" % bus_mode]
         # blocks 2 and 3 against the separate form
         b.upload_state(np.ascontiguousarray(s0[lo:hi]).view(np.uint32).reshape(hi - lo, 5))
         for k in range(3):
@@ -238,11 +243,12 @@ def xvoice_check_and_timing(N_check, N, F, reps=20):
             b.run_dev(F, mix=mk.data_ptr())
             bus.allreduce(mk.data_ptr(), 2 * F, op=st.Bus.FSUM)
             torch.cuda.synchronize()
+            detail["fused_mode%d_block%d_equals_separate" % (bus_mode, k)] = bool(torch.equal(m3[k], mk))
             ok = ok and torch.equal(m3[k], mk)
     b.free()
     if N == 0:
         bus.destroy()
-        return ok, {}
+        return ok, detail
     # timing at the full size
     s0, prm = xvoice_records(N, 6)
     lo, hi = shard.shard_range(N, rank, world)
@@ -306,9 +312,9 @@ for mode in (0, 1):
         print(json.dumps({"check": "voice bank mix bus, mode %d" % mode, "n_gpus": world, "nccl_bit_exact": a, "peer_bus_bit_exact": bb,
                           "fused_in_launch_bit_exact": c1, "fused_pipelined_bit_exact": c2}), flush=True)
 if CHECK_ONLY:
-    okx, _ = xvoice_check_and_timing(64 * 1024 + 5, 0, 512)
+    okx, detail = xvoice_check_and_timing(64 * 1024 + 5, 0, 512)
     if rank == 0:
-        print(json.dumps({"check": "xvoice float bus", "n_gpus": world, "float_bus_within_tolerance_and_identical_on_all_ranks_ok": bool(okx)}), flush=True)
+        print(json.dumps({"check": "xvoice float bus", "n_gpus": world, "float_bus_within_tolerance_and_identical_on_all_ranks_ok": bool(okx), "detail": detail}), flush=True)
     ctx.close()
     dist.destroy_process_group()
     sys.exit(0)
