@@ -314,6 +314,19 @@ def run_native(args, rank, local_rank, world):
     for _ in range(min(args.warmup, 3)):
         e2e_step()
     barrier()
+    # the ceiling of this leg: plain device -> pinned-host copies of the same ring, all ranks at once (the ranks of one box share
+    # the host's PCIe uplinks; tools/d2h_probe.py, profiles/r2_d2h_probe_8gpu.json).  Untimed for the metric.
+    tp0 = time.perf_counter()
+    for _ in range(8):
+        ctx.d2h(ring, slabs[0].data_ptr())
+    probe_gbs = 8 * ring.nbytes / (time.perf_counter() - tp0) / 1e9
+    tpr = torch.tensor([probe_gbs], device=dev, dtype=torch.float64)
+    probe_ranks = [probe_gbs]
+    if world > 1:
+        allp = [torch.zeros_like(tpr) for _ in range(world)]
+        dist.all_gather(allp, tpr)
+        probe_ranks = [float(x.item()) for x in allp]
+    barrier()
     e2e_steps = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -360,7 +373,10 @@ def run_native(args, rank, local_rank, world):
                     "sample": "65,536 ch x 1 Mi samples per step per GPU via cproc_cuda_run_stream (pinned ring of 4 x %d MiB)" % (N_CH * E2E_CHUNK >> 20),
                     "cpu_affinity": numa,
                     "steps": e2e_steps, "seconds_per_rank": [round(x, 4) for x in e2e_ranks],
-                    "d2h_gbs_per_rank": [round(N_CH * E2E_TICKS * e2e_steps / x / 1e9, 2) for x in e2e_ranks]},
+                    "d2h_gbs_per_rank": [round(N_CH * E2E_TICKS * e2e_steps / x / 1e9, 2) for x in e2e_ranks],
+                    "d2h_copy_ceiling_gbs_per_rank": [round(x, 2) for x in probe_ranks],
+                    "fraction_of_copy_ceiling_per_rank": [round(N_CH * E2E_TICKS * e2e_steps / x / 1e9 / max(pr, 1e-9), 3) for x, pr in zip(e2e_ranks, probe_ranks)],
+                    "ceiling_note": "plain device -> pinned host copies of the same ring, all ranks at once, measured in this run before the e2e leg"},
             "gpu_launches": launches,
             # The kernel is bound by integer instruction issue (two half-rate pipes shared by ~4 warps per scheduler), not by
             # HBM: the roofline is stated against the issue peak at the observed SM clock, the HBM figure rides along.

@@ -436,6 +436,7 @@ int  cproc_cuda_timer_stop(cproc_cuda_ctx *ctx, float *elapsed_ms);
  *   pdm_block, pdm_tpb [1: thread per bank when bank_size <= 4], pdm_persist, pdm_warps_per_smsp   plain PDM kernels, PDM v1 schedule
  *   xvoice_mix2      0/1  [1]  XVOICE mix-only render: voice pairs on the packed fp32 pipe (FFMA2) with state tiles in shared
  *                              memory; 0 = the scalar kernel (state through L2 once per 32-frame chunk)
+ *   xvoice_mix2_blocks 0..3 [0] its resident blocks per SM (0 = chosen from the voice count)
  *   xvoice_chunk [0 = auto], xvoice_groups 0..8 [0 = one group], xvoice_closed 0/1 [1]
  *                              XVOICE_SCAN: frames per time chunk, variant groups, closed-form zero-state pass
  *   run_graph        0..3 [2]  cproc_cuda_run on small host buffers: staged copies, CUDA graph with copy nodes,

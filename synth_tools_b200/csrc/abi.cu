@@ -127,6 +127,7 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     else if (!strcmp(name, "xvoice_vpt")) { if (value < 0 || value > 65536) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice_vpt must be 0..65536"); ctx->xvoice_vpt = (int)value; }
     else if (!strcmp(name, "xvoice_closed")) ctx->xvoice_closed = value ? 1 : 0;
     else if (!strcmp(name, "xvoice_mix2")) ctx->xvoice_mix2 = value ? 1 : 0;
+    else if (!strcmp(name, "xvoice_mix2_blocks")) { if (value < 0 || value > 3) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice_mix2_blocks must be 0..3"); ctx->xvoice_mix2_blocks = (int)value; }
     else if (!strcmp(name, "run_graph")) { if (value < 0 || value > 3) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "run_graph must be 0..3"); ctx->run_graph = (int)value; }
     else if (!strcmp(name, "xvoice_groups")) { if (value < 0 || value > 8) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "xvoice_groups must be 0..8"); ctx->xvoice_groups = (int)value; }
     else if (!strcmp(name, "pdm_persist")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_persist must be 0 (never), 1 (auto) or 2 (always)"); ctx->pdm_persist = (int)value; }

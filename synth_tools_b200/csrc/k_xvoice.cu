@@ -1083,8 +1083,14 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     }
     // (the float mix depends on which block sums which voices: k_xvoice_mix2 always leaves the slot a pipelined bus needs for its
     // exchange block free, so that the bits of the mix do not depend on whether, or how, a bus is attached)
+    // Blocks per SM.  A block's work comes in rounds of 256 voices (one pair per thread, all chunks of the launch: ~38 us): 4 Mi voices
+    // are 36.9 rounds per block at three blocks per SM (0.3 % lost to the last, uneven round), a 512 Ki-voice shard of an 8-GPU render
+    // is 4.62 -> 5 rounds (8 % lost: the residual limiter of the C4 strong-scaling row).  Two blocks per SM do not help (6.94 -> 7
+    // rounds of 0.74 of the time: 0.187 against 0.189 ms measured); option xvoice_mix2_blocks is there for the experiment.
+    int per_sm = mix2_per_sm;
+    if (mix2 && ctx->xvoice_mix2_blocks && ctx->xvoice_mix2_blocks < mix2_per_sm) per_sm = ctx->xvoice_mix2_blocks;
     const uint64_t n_blocks = !mix_only ? ceil_div_u64(b->n, XV_BLOCK)
-                            : mix2 ? (uint64_t)ctx->n_sm * mix2_per_sm - 1 : (uint64_t)ctx->n_sm * 4 - (b->bus && b->bus_mode == 2 ? 1 : 0);
+                            : mix2 ? (uint64_t)ctx->n_sm * per_sm - 1 : (uint64_t)ctx->n_sm * 4 - (b->bus && b->bus_mode == 2 ? 1 : 0);
     XVoiceParams p;
     p.st = b->d_state; p.prm = b->d_param; p.npad = b->npad; p.n = b->n; p.F = F;
     p.raw = (float *)io->out; p.layout = io->layout; p.partial = nullptr;

@@ -62,7 +62,7 @@ elif which == "gmix":
     ms = timed(lambda: b.run_dev(F, out=d_out, mix=d_mix))
     print("gmix: %.3f ms  %.1f G grain-samples/s" % (ms, N * F / ms / 1e6))
 elif which == "xvoice":
-    N, F = 4 * 1024 * 1024, 512
+    N, F = int(os.environ.get("XV_N", 4 * 1024 * 1024)), 512
     stt, prm = xvoice_records(N)
     if os.environ.get("XV_GATE"):                     # every voice in one envelope phase: the uniform-chunk path
         prm[:, 5] = int(os.environ["XV_GATE"])
