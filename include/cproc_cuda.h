@@ -170,6 +170,11 @@ enum cproc_cuda_proc {
  *   onepole   state {float out}                   param {float a}   input {float in}     out = fmaf(a, in - out, out)
  *   gain      state {float out}                   param {float g}   input {float in}     out = g * in
  *   asfloat   state {float out}                   input {w in}      out = the float whose bits are `in` (external float streams)
+ *   glide_f   state {float out; float step; w count}   config {w div_log}   input {float in}
+ *             control rate -> audio rate: every 2^div_log ticks step = (in - out) * 2^-div_log; every tick out += step
+ *   mul       state {float out}                   input {float in; float gain}      out = in * gain
+ *             glide_f -> mul is the "representative example" of doc/combinators.org:28-34 (a control-rate gain amount applied
+ *             to an audio-rate signal) for float signals, as glide is for the firmware's uint32 setpoints
  * Connecting a `w` output (or input[k]) to a float input converts by value, (float)(uint32_t)x, as the
  * C assignment in PROC_COND's designated initialiser does (cproc.h:75); a float output feeding a `w`
  * input is rejected (undefined in C for negative values).  An input the statement does not name reads
@@ -178,7 +183,9 @@ enum cproc_cuda_proc {
  * (cproc_cuda_upload_param; cproc_cuda_param_bytes). */
 enum { CPROC_CUDA_NODE_ACC = 0, CPROC_CUDA_NODE_EDGE = 1, CPROC_CUDA_NODE_GLIDE = 2, CPROC_CUDA_NODE_PDM = 3,
        CPROC_CUDA_NODE_PHASOR_F = 4, CPROC_CUDA_NODE_SVF = 5, CPROC_CUDA_NODE_ENV = 6, CPROC_CUDA_NODE_ONEPOLE = 7,
-       CPROC_CUDA_NODE_GAIN = 8, CPROC_CUDA_NODE_ASFLOAT = 9, CPROC_CUDA_NODE_KINDS = 10 };
+       CPROC_CUDA_NODE_GAIN = 8, CPROC_CUDA_NODE_ASFLOAT = 9, CPROC_CUDA_NODE_GLIDE_F = 10, CPROC_CUDA_NODE_MUL = 11,
+       CPROC_CUDA_NODE_KINDS = 12 };
+#define CPROC_CUDA_NODE_GLIDE_F_L(L) (CPROC_CUDA_NODE_GLIDE_F | ((uint32_t)(L) << 8))
 #define CPROC_CUDA_SRC_ZERO ((int32_t)0x80000000)
 #define CPROC_CUDA_NODE_KIND(t) ((t) & 0xFFu)
 #define CPROC_CUDA_NODE_ARG(t)  (((t) >> 8) & 0xFFu)
@@ -238,6 +245,7 @@ typedef struct {
  *   PROC_COND(<changed> & <mask>, <inst>, acc|edge, NULL, NULL, .in = input[k] | <inst>.out);
  *   PROC_COND(<changed> & <mask>, <inst>, glide, &(glide_config){.div_log = L}, NULL, .in = ...);
  *   PROC_COND(<changed> & <mask>, <inst>, pdm1..pdm4, &(pdm_config){.out_shift = S}, NULL, .in = ..., .dither = ...);
+ *   PROC(<inst>, glide_f, &(glide_f_config){.div_log = L}, NULL, .in = ...);   PROC(<inst>, mul, NULL, NULL, .in = ..., .gain = ...);
  *   PROC(<inst>, phasor_f|svf|env|onepole|gain|asfloat, NULL, <param>, .in = ... [, .mod = ...]);
  *     <param>: &<identifier> (the host uploads the record) or a compound literal whose members become the
  *     record's initial value for every instance, e.g. (&(svf_param){ .f = 0.1f, .q = 1.5f }) -- in parentheses, or

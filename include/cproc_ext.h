@@ -86,6 +86,28 @@ DEF_PROC(asfloat, s, c, p, i) {
     memcpy(&s->out, &bits, sizeof(bits));
 }
 
+/* Control rate -> audio rate interpolation of a float parameter (doc/combinators.org:28-34; the float counterpart of the
+ * firmware's struct line / pdm_update_line, mod_controlrate.c:28-40): .in is read once per 2^div_log ticks, .out ramps towards
+ * it.  The scale by a power of two is exact, so a tick is one rounding (the add) and a boundary two (the subtract, the add). */
+#define for_glide_f_state(m)  m(float,out) m(float,step) m(w,count)
+#define for_glide_f_input(m)  m(float,in)
+#define for_glide_f_config(m) m(w,div_log)
+#define for_glide_f_param(m)
+DEF_PROC(glide_f, s, c, p, i) {
+    if (s->count == 0) s->step = (i->in - s->out) * (1.0f / (float)(1u << c->div_log));
+    s->out = s->out + s->step;
+    s->count = (s->count + 1) & ((1u << c->div_log) - 1u);
+}
+
+/* Two audio-rate signals multiplied: glide_f -> mul applies a control-rate gain amount to an audio-rate signal. */
+#define for_mul_state(m)  m(float,out)
+#define for_mul_input(m)  m(float,in) m(float,gain)
+#define for_mul_config(m)
+#define for_mul_param(m)
+DEF_PROC(mul, s, c, p, i) {
+    s->out = i->in * i->gain;
+}
+
 /* Float results leave through their own upcall: cproc_output(uint32_t index, w value)
  * (test_cproc.c:5-7, mod_cproc_plugin.c:40-43) would convert a float by value. */
 void cproc_output_f(uint32_t index, float value);

@@ -38,7 +38,7 @@ uint32_t orc_node_state_words(uint32_t type) {
     case ORC_NODE_GLIDE: return 5u;
     case ORC_NODE_PDM: return 1u + ((type >> 8) & 7u);
     case ORC_NODE_PHASOR_F: case ORC_NODE_SVF: return 2u;   /* cproc_ext.h: {out, phase}, {out, bp} */
-    case ORC_NODE_ENV: return 3u;                           /* {out, env, t} */
+    case ORC_NODE_ENV: case ORC_NODE_GLIDE_F: return 3u;    /* {out, env, t}, {out, step, count} */
     default: return 1u;
     }
 }
@@ -140,10 +140,18 @@ void orc_graph_run_multi(const orc_node *nodes, uint32_t n_nodes, uint32_t n_inp
  * (floats as bit patterns); each statement one IEEE rounding, fmaf fused. */
 static float orc_bits_f(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
 static uint32_t orc_f_bits(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
-static int orc_kind_in_float(uint32_t kind) { return kind == ORC_NODE_SVF || kind == ORC_NODE_ENV || kind == ORC_NODE_ONEPOLE || kind == ORC_NODE_GAIN; }
+static int orc_kind_in_float(uint32_t kind) { return kind == ORC_NODE_SVF || kind == ORC_NODE_ENV || kind == ORC_NODE_ONEPOLE || kind == ORC_NODE_GAIN || kind == ORC_NODE_GLIDE_F || kind == ORC_NODE_MUL; }
 static int orc_kind_out_float(uint32_t kind) { return kind >= ORC_NODE_PHASOR_F && kind < ORC_NODE_KINDS; }
-static void orc_ext_update(uint32_t kind, uint32_t *s, const uint32_t *p, uint32_t x) {
+static void orc_ext_update(uint32_t type, uint32_t *s, const uint32_t *p, uint32_t x, uint32_t x2) {
+    const uint32_t kind = type & 0xFF;
     switch (kind) {
+    case ORC_NODE_GLIDE_F: {                                 /* cproc_ext.h glide_f: the scale by 2^-L is exact */
+        uint32_t L = (type >> 8) & 0xFF;
+        if (s[2] == 0) s[1] = orc_f_bits((orc_bits_f(x) - orc_bits_f(s[0])) * (1.0f / (float)(1u << L)));
+        s[0] = orc_f_bits(orc_bits_f(s[0]) + orc_bits_f(s[1]));
+        s[2] = (s[2] + 1) & ((1u << L) - 1u);
+        break; }
+    case ORC_NODE_MUL: s[0] = orc_f_bits(orc_bits_f(x) * orc_bits_f(x2)); break;
     case ORC_NODE_PHASOR_F:                                  /* cproc_ext.h phasor_f: read, then advance */
         s[0] = orc_f_bits((float)(int32_t)s[1] * (1.0f / 2147483648.0f));
         s[1] += p[0] + x;
@@ -187,7 +195,7 @@ void orc_graph_run_ext(const orc_node *nodes, uint32_t n_nodes, uint32_t n_input
                 if (!(g & nodes[i].cond_mask)) continue;
                 uint32_t kind = nodes[i].type & 0xFF;
                 uint32_t xs[2] = {0, 0};
-                for (int j = 0; j < (kind == ORC_NODE_PDM ? 2 : 1); j++) {
+                for (int j = 0; j < (kind == ORC_NODE_PDM || kind == ORC_NODE_MUL ? 2 : 1); j++) {
                     int32_t src = j ? nodes[i].src2 : nodes[i].src;
                     if (src == ORC_SRC_ZERO) continue;                       /* 0 / +0.0f */
                     uint32_t v; int is_f = 0;
@@ -204,7 +212,7 @@ void orc_graph_run_ext(const orc_node *nodes, uint32_t n_nodes, uint32_t n_input
                 case ORC_NODE_EDGE: orc_edge_update((orc_edge_state *)(st + off[i]), xs[0]); break;
                 case ORC_NODE_GLIDE: orc_glide_update((orc_glide_state *)(st + off[i]), xs[0], (nodes[i].type >> 8) & 0xFF); break;
                 case ORC_NODE_ACC: orc_acc_update((orc_acc_state *)(st + off[i]), xs[0]); break;
-                default: orc_ext_update(kind, st + off[i], pr ? pr + poff[i] : NULL, xs[0]); break;
+                default: orc_ext_update(nodes[i].type, st + off[i], pr ? pr + poff[i] : NULL, xs[0], xs[1]); break;
                 }
             }
             for (uint32_t k = 0; k < n_out; k++) out[((uint64_t)n * n_out + k) * F + t] = st[off[out_nodes[k]]];

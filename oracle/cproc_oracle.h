@@ -51,7 +51,7 @@ void orc_edge_update(orc_edge_state *s, orc_w in);      /* cproc.h:151-154 */
  * as a table: one row per PROC_COND statement, in ANF order. */
 enum { ORC_NODE_ACC = 0, ORC_NODE_EDGE = 1, ORC_NODE_GLIDE = 2, ORC_NODE_PDM = 3,
        /* extension processors (include/cproc_ext.h is the definition; restated in cproc_oracle.c, parity unpinned by the reference) */
-       ORC_NODE_PHASOR_F = 4, ORC_NODE_SVF = 5, ORC_NODE_ENV = 6, ORC_NODE_ONEPOLE = 7, ORC_NODE_GAIN = 8, ORC_NODE_ASFLOAT = 9, ORC_NODE_KINDS = 10 };
+       ORC_NODE_PHASOR_F = 4, ORC_NODE_SVF = 5, ORC_NODE_ENV = 6, ORC_NODE_ONEPOLE = 7, ORC_NODE_GAIN = 8, ORC_NODE_ASFLOAT = 9, ORC_NODE_GLIDE_F = 10, ORC_NODE_MUL = 11, ORC_NODE_KINDS = 12 };
 #define ORC_SRC_ZERO ((int32_t)0x80000000)   /* an input the PROC statement does not name: 0 (C initialiser) */
 /* pdm node: pdmK_update (pdm.h:13-77) as a processor, state {out, s1..sK}; .in = src, .dither = src2;
  * type = 3 | (K | out_shift << 3) << 8. */

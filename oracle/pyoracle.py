@@ -22,13 +22,18 @@ f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 VP = C.c_void_p
 
 NODE_ACC, NODE_EDGE, NODE_GLIDE, NODE_PDM = 0, 1, 2, 3
-NODE_PHASOR_F, NODE_SVF, NODE_ENV, NODE_ONEPOLE, NODE_GAIN, NODE_ASFLOAT = 4, 5, 6, 7, 8, 9   # include/cproc_ext.h
+NODE_PHASOR_F, NODE_SVF, NODE_ENV, NODE_ONEPOLE, NODE_GAIN, NODE_ASFLOAT, NODE_GLIDE_F, NODE_MUL = 4, 5, 6, 7, 8, 9, 10, 11   # include/cproc_ext.h
 SRC_ZERO = -0x80000000
 
 
 def node_glide(div_log):
     """glide node type word: kind | (control divider log2 << 8)."""
     return NODE_GLIDE | (div_log << 8)
+
+
+def node_glide_f(div_log):
+    """glide_f node type word (include/cproc_ext.h): kind | (control divider log2 << 8)."""
+    return NODE_GLIDE_F | (div_log << 8)
 
 
 def node_pdm(order, out_shift):
@@ -39,7 +44,7 @@ def node_pdm(order, out_shift):
 def node_words(t):
     if t & 0xFF == NODE_PDM:
         return 1 + ((t >> 8) & 7)
-    return {NODE_EDGE: 2, NODE_GLIDE: 5, NODE_PHASOR_F: 2, NODE_SVF: 2, NODE_ENV: 3}.get(t & 0xFF, 1)
+    return {NODE_EDGE: 2, NODE_GLIDE: 5, NODE_PHASOR_F: 2, NODE_SVF: 2, NODE_ENV: 3, NODE_GLIDE_F: 3}.get(t & 0xFF, 1)
 
 
 def node_param_words(t):

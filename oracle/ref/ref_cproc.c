@@ -78,11 +78,15 @@ uint32_t ref_ext_sizeof(int what) {
     case 9: return sizeof(onepole_state);  case 10: return sizeof(onepole_param); case 11: return sizeof(onepole_input);
     case 12: return sizeof(gain_state);    case 13: return sizeof(gain_param);    case 14: return sizeof(gain_input);
     case 15: return sizeof(asfloat_state); case 16: return sizeof(asfloat_param); case 17: return sizeof(asfloat_input);
+    case 18: return sizeof(glide_f_state); case 19: return sizeof(glide_f_param); case 20: return sizeof(glide_f_input);
+    case 21: return sizeof(mul_state);     case 22: return sizeof(mul_param);     case 23: return sizeof(mul_input);
+    case 24: return sizeof(glide_f_config);
     }
     return 0xFFFFFFFFu;
 }
-static const uint8_t ext_sw[10] = {1, 2, 0, 0, sizeof(phasor_f_state) / 4, sizeof(svf_state) / 4, sizeof(env_state) / 4, sizeof(onepole_state) / 4, sizeof(gain_state) / 4, sizeof(asfloat_state) / 4};
-static const uint8_t ext_pw[10] = {0, 0, 0, 0, sizeof(phasor_f_param) / 4, sizeof(svf_param) / 4, sizeof(env_param) / 4, sizeof(onepole_param) / 4, sizeof(gain_param) / 4, 0};
+static const uint8_t ext_sw[12] = {1, 2, 0, 0, sizeof(phasor_f_state) / 4, sizeof(svf_state) / 4, sizeof(env_state) / 4, sizeof(onepole_state) / 4, sizeof(gain_state) / 4, sizeof(asfloat_state) / 4,
+                                   sizeof(glide_f_state) / 4, sizeof(mul_state) / 4};
+static const uint8_t ext_pw[12] = {0, 0, 0, 0, sizeof(phasor_f_param) / 4, sizeof(svf_param) / 4, sizeof(env_param) / 4, sizeof(onepole_param) / 4, sizeof(gain_param) / 4, 0, 0, 0};
 static float w_as_f(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
 void ref_graph_run_ext(const ref_node *nodes, uint32_t n_nodes, uint32_t n_inputs,
                        const uint32_t *out_nodes, uint32_t n_out, uint32_t *state, const uint32_t *param, uint64_t N, uint64_t F,
@@ -116,6 +120,15 @@ void ref_graph_run_ext(const ref_node *nodes, uint32_t n_nodes, uint32_t n_input
                 case 7: { const onepole_input vi = { .in = src_f ? xf : (float)xw }; onepole_update(s, NULL, p, &vi); break; }
                 case 8: { const gain_input vi = { .in = src_f ? xf : (float)xw }; gain_update(s, NULL, p, &vi); break; }
                 case 9: { const asfloat_input vi = { .in = xw }; asfloat_update(s, NULL, NULL, &vi); break; }
+                case 10: { const glide_f_config gc = { .div_log = (nodes[i].type >> 8) & 0xFF }; const glide_f_input vi = { .in = src_f ? xf : (float)xw }; glide_f_update(s, &gc, NULL, &vi); break; }
+                case 11: {                                       /* second input: the same conversion rule */
+                    const int32_t s2 = nodes[i].src2; int s2_f = 0; w yw = 0; float yf = 0.0f;
+                    if (s2 != (int32_t)0x80000000) {
+                        if (s2 >= 0) { yw = st[off[s2]]; s2_f = (nodes[s2].type & 0xFF) >= 4; if (s2_f) yf = w_as_f(yw); }
+                        else yw = in[(n * n_inputs + (uint32_t)(-(s2 + 1))) * F + t];
+                    }
+                    const mul_input vi = { .in = src_f ? xf : (float)xw, .gain = s2_f ? yf : (float)yw };
+                    mul_update(s, NULL, NULL, &vi); break; }
                 }
             }
             for (uint32_t k = 0; k < n_out; k++) out[(n * n_out + k) * F + t] = st[off[out_nodes[k]]];

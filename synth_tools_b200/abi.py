@@ -16,13 +16,18 @@ LIB_PATH = os.path.join(HERE, "libcproc_cuda.so")
 GRAPH, PDM, PDM_V1, PDM_V2, PWM, VOICE_BANK, SQUARE_GRAIN, SQUARE_GRAIN_MIX, XVOICE, ONEPOLE, WORD_CLOCK = range(1, 12)
 NODE_ACC, NODE_EDGE, NODE_GLIDE, NODE_PDM = 0, 1, 2, 3
 # extension processors (include/cproc_ext.h)
-NODE_PHASOR_F, NODE_SVF, NODE_ENV, NODE_ONEPOLE, NODE_GAIN, NODE_ASFLOAT = 4, 5, 6, 7, 8, 9
+NODE_PHASOR_F, NODE_SVF, NODE_ENV, NODE_ONEPOLE, NODE_GAIN, NODE_ASFLOAT, NODE_GLIDE_F, NODE_MUL = 4, 5, 6, 7, 8, 9, 10, 11
 SRC_ZERO = -0x80000000          # CPROC_CUDA_SRC_ZERO: an input the PROC statement does not name
 
 
 def node_glide(div_log):
     """CPROC_CUDA_NODE_GLIDE_L(L)"""
     return NODE_GLIDE | (div_log << 8)
+
+
+def node_glide_f(div_log):
+    """CPROC_CUDA_NODE_GLIDE_F_L(L)"""
+    return NODE_GLIDE_F | (div_log << 8)
 
 
 def node_pdm(order, out_shift):
@@ -36,7 +41,7 @@ def _node(r):
 
 def _row(n):
     """Node -> (type, src, cond_mask) for one-input kinds, (type, src, cond_mask, src2) for pdm."""
-    return (n.type, n.src, n.cond_mask, n.src2) if n.type & 0xFF == NODE_PDM else (n.type, n.src, n.cond_mask)
+    return (n.type, n.src, n.cond_mask, n.src2) if n.type & 0xFF in (NODE_PDM, NODE_MUL) else (n.type, n.src, n.cond_mask)
 
 MIX_SAW, MIX_SQUARE = 0, 1
 XVOICE_SEQ, XVOICE_SCAN = 0, 1

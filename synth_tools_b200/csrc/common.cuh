@@ -132,6 +132,8 @@ static const cproc_kind_meta k_cproc_kinds[CPROC_CUDA_NODE_KINDS] = {
     {"onepole",  1, {"out"}, 1,                                    1, {"a"}, 1,                                   1, {"in"}, 1,           0, {nullptr}},
     {"gain",     1, {"out"}, 1,                                    1, {"g"}, 1,                                   1, {"in"}, 1,           0, {nullptr}},
     {"asfloat",  1, {"out"}, 1,                                    0, {nullptr}, 0,                               1, {"in"}, 0,           0, {nullptr}},
+    {"glide_f",  3, {"out", "step", "count"}, 3,                   0, {nullptr}, 0,                               1, {"in"}, 1,           1, {"div_log"}},
+    {"mul",      1, {"out"}, 1,                                    0, {nullptr}, 0,                               2, {"in", "gain"}, 3,   0, {nullptr}},
 };
 static inline bool cproc_kind_out_float(uint32_t type) { const uint32_t k = CPROC_CUDA_NODE_KIND(type); return k < CPROC_CUDA_NODE_KINDS && (k_cproc_kinds[k].state_f & 1u); }
 static inline uint32_t cproc_node_words(uint32_t type) {   // acc {out}; edge {out, last}; glide {out, vel0, pos1, vel1, count}; pdm {out, s1..sK}; extension processors: cproc_ext.h
@@ -148,9 +150,9 @@ static inline const char *cproc_node_check(const cproc_cuda_node *nodes, uint32_
     const cproc_cuda_node &nd = nodes[k];
     const uint32_t kind = CPROC_CUDA_NODE_KIND(nd.type), arg = CPROC_CUDA_NODE_ARG(nd.type);
     if (kind >= CPROC_CUDA_NODE_KINDS || (nd.type >> 16)) return "unknown node type";
-    if (kind == CPROC_CUDA_NODE_GLIDE && (arg < 1 || arg > 24)) return "glide needs a control divider log2 of 1..24";
+    if ((kind == CPROC_CUDA_NODE_GLIDE || kind == CPROC_CUDA_NODE_GLIDE_F) && (arg < 1 || arg > 24)) return "glide needs a control divider log2 of 1..24";
     if (kind == CPROC_CUDA_NODE_PDM && ((arg & 7u) < 1 || (arg & 7u) > 4)) return "pdm order must be 1..4";
-    if (kind != CPROC_CUDA_NODE_GLIDE && kind != CPROC_CUDA_NODE_PDM && arg) return "this processor takes no config word";
+    if (kind != CPROC_CUDA_NODE_GLIDE && kind != CPROC_CUDA_NODE_GLIDE_F && kind != CPROC_CUDA_NODE_PDM && arg) return "this processor takes no config word";
     const cproc_kind_meta &m = k_cproc_kinds[kind];
     for (uint32_t j = 0; j < m.n_input; ++j) {
         const int32_t src = j ? nd.src2 : nd.src;

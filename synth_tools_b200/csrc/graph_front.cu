@@ -183,14 +183,14 @@ extern "C" int cproc_cuda_graph_parse(const char *text, cproc_cuda_node *nodes, 
         uint32_t n_in_expected = 1;
         uint32_t kind = CPROC_CUDA_NODE_KINDS;
         for (uint32_t q = 0; q < CPROC_CUDA_NODE_KINDS; ++q) if (q != CPROC_CUDA_NODE_PDM && type == k_cproc_kinds[q].name) kind = q;
-        if (kind == CPROC_CUDA_NODE_GLIDE) {
+        if (kind == CPROC_CUDA_NODE_GLIDE || kind == CPROC_CUDA_NODE_GLIDE_F) {
             // const glide_config: &(glide_config){ .div_log = L }  (any spelling that names div_log = <number>)
             const size_t f = cfg.find("div_log");
             uint64_t L = 0;
             bool ok = f != std::string::npos;
             if (ok) { Cursor q{cfg.c_str() + f + 7, ""}; ok = q.lit("=") && q.number(&L) && L >= 1 && L <= 24; }
-            if (!ok) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': glide needs a config with .div_log = 1..24", inst.c_str());
-            nd.type = CPROC_CUDA_NODE_GLIDE_L(L);
+            if (!ok) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': %s needs a config with .div_log = 1..24", inst.c_str(), type.c_str());
+            nd.type = kind | ((uint32_t)L << 8);
             cfg_null = true;
         }
         else if (type.size() == 4 && type.compare(0, 3, "pdm") == 0 && type[3] >= '1' && type[3] <= '4') {
@@ -206,7 +206,7 @@ extern "C" int cproc_cuda_graph_parse(const char *text, cproc_cuda_node *nodes, 
             n_in_expected = type[3] == '1' ? 1 : 2;             // pdm1 takes no dither (pdm.h:13)
         }
         else if (kind < CPROC_CUDA_NODE_KINDS) nd.type = kind;
-        else return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s' has unknown processor type '%s' (acc, edge, glide, pdm1..pdm4, phasor_f, svf, env, onepole, gain, asfloat)", inst.c_str(), type.c_str());
+        else return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s' has unknown processor type '%s' (acc, edge, glide, pdm1..pdm4, phasor_f, svf, env, onepole, gain, asfloat, glide_f, mul)", inst.c_str(), type.c_str());
         const cproc_kind_meta &meta = k_cproc_kinds[kind];
         const bool ext = kind > CPROC_CUDA_NODE_PDM;
         if (!cfg_null || (meta.n_param == 0 && prm != "NULL" && prm != "0"))
@@ -305,7 +305,7 @@ extern "C" int cproc_cuda_graph_parse(const char *text, cproc_cuda_node *nodes, 
             if (n_in_expected == 2) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: node '%s': %s needs '.dither = ...'", inst.c_str(), type.c_str());
             nd.src2 = nd.src;                                    // pdm1: unused, keep the row valid
         }
-        if (!is_pdm) nd.src2 = 0;                                // one-input processors: src2 is ignored
+        if (meta.n_input < 2) nd.src2 = 0;                       // one-input processors: src2 is ignored
         if (names.size() >= max_nodes) return cproc_set_err(nullptr, CPROC_CUDA_EINVAL, "graph_parse: more than %u nodes", max_nodes);
         nodes[names.size()] = nd;
         names.push_back(inst);
@@ -766,6 +766,14 @@ std::string cproc_graph_jit_source(const std::vector<cproc_cuda_node> &nodes, ui
         case CPROC_CUDA_NODE_ASFLOAT:
             snprintf(buf, sizeof(buf), " %s{ s%u = %s; }", cond.c_str(), o, in.c_str());
             break;
+        case CPROC_CUDA_NODE_GLIDE_F: {
+            const uint32_t L = CPROC_CUDA_NODE_ARG(nd.type);
+            snprintf(buf, sizeof(buf), " %s{ if (s%u == 0) s%u = __float_as_uint(__fmul_rn(__fsub_rn(%s, __uint_as_float(s%u)), %.9ef)); s%u = __float_as_uint(__fadd_rn(__uint_as_float(s%u), __uint_as_float(s%u)));"
+                     " s%u = (s%u + 1) & 0x%xu; }", cond.c_str(), o + 2, o + 1, in.c_str(), o, 1.0 / (double)(1u << L), o, o, o + 1, o + 2, o + 2, (1u << L) - 1u);
+            break; }
+        case CPROC_CUDA_NODE_MUL:
+            snprintf(buf, sizeof(buf), " %s{ s%u = __float_as_uint(__fmul_rn(%s, %s)); }", cond.c_str(), o, in.c_str(), operand(nd.src2, true).c_str());
+            break;
         default: snprintf(buf, sizeof(buf), " %s{ s%u += %s; }", cond.c_str(), o, in.c_str()); break;                                                                            // cproc.h:140-142
         }
         tick += buf;
@@ -776,7 +784,7 @@ std::string cproc_graph_jit_source(const std::vector<cproc_cuda_node> &nodes, ui
     // Block shape of the PLANAR staging kernels.  A tick of a float voice is ~20 dependent instructions and its graph has no input
     // stream: measured on the C4 voice graph (tools/sweep_graph_tiles.sh, profiles/r2_sweep_graph_tiles.txt) one warp per block with
     // 64-frame tiles is the best shape (5.43 TB/s; two warps 5.08, 32-frame tiles 5.03-5.09, 128-frame tiles leave two warps per SM).
-    static const uint8_t k_cost[CPROC_CUDA_NODE_KINDS] = {1, 2, 6, 7, 3, 5, 6, 2, 1, 0};
+    static const uint8_t k_cost[CPROC_CUDA_NODE_KINDS] = {1, 2, 6, 7, 3, 5, 6, 2, 1, 0, 4, 1};
     uint32_t cost = 0;
     for (const cproc_cuda_node &nd : nodes) cost += k_cost[CPROC_CUDA_NODE_KIND(nd.type)];
     int tf = 64, stages = 3, warps = cost >= 12 ? 1 : 2;

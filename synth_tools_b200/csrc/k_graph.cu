@@ -57,6 +57,13 @@ __device__ __forceinline__ void node_tick(uint32_t type, uint32_t *s, const uint
     else if (kind == CPROC_CUDA_NODE_ONEPOLE) { const float y = __uint_as_float(s[0]); s[0] = __float_as_uint(__fmaf_rn(__uint_as_float(pr[0]), __fsub_rn(__uint_as_float(x), y), y)); }
     else if (kind == CPROC_CUDA_NODE_GAIN) s[0] = __float_as_uint(__fmul_rn(__uint_as_float(pr[0]), __uint_as_float(x)));
     else if (kind == CPROC_CUDA_NODE_ASFLOAT) s[0] = x;
+    else if (kind == CPROC_CUDA_NODE_GLIDE_F) {
+        const uint32_t L = (type >> 8) & 0xFFu;
+        if (s[2] == 0) s[1] = __float_as_uint(__fmul_rn(__fsub_rn(__uint_as_float(x), __uint_as_float(s[0])), 1.0f / (float)(1u << L)));
+        s[0] = __float_as_uint(__fadd_rn(__uint_as_float(s[0]), __uint_as_float(s[1])));
+        s[2] = (s[2] + 1) & ((1u << L) - 1u);
+    }
+    else if (kind == CPROC_CUDA_NODE_MUL) s[0] = __float_as_uint(__fmul_rn(__uint_as_float(x), __uint_as_float(x2)));
     else if (kind == CPROC_CUDA_NODE_PDM) {                 // pdm.h:13-77: s[0] = out_q, s[1..K] = s1..sK
         const uint32_t K = (type >> 8) & 7u, sh = (type >> 11) & 31u;
         const uint32_t q = s[K] >> sh;
@@ -111,8 +118,8 @@ __global__ void k_graph_table(const GraphParams p) {
     __shared__ uint32_t off[GRAPH_MAX_NODES], poff[GRAPH_MAX_NODES], inf[GRAPH_MAX_NODES], outf[GRAPH_MAX_NODES], n_pw;
     if (threadIdx.x == 0) {
         // words per kind: state / param; float-typed first input / float-typed out (cproc_kind_meta in common.cuh, restated for the device)
-        const uint8_t sw[CPROC_CUDA_NODE_KINDS] = {1, 2, 5, 0, 2, 2, 3, 1, 1, 1}, pw[CPROC_CUDA_NODE_KINDS] = {0, 0, 0, 0, 1, 2, 3, 1, 1, 0};
-        const uint8_t fin[CPROC_CUDA_NODE_KINDS] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 0}, fout[CPROC_CUDA_NODE_KINDS] = {0, 0, 0, 0, 1, 1, 1, 1, 1, 1};
+        const uint8_t sw[CPROC_CUDA_NODE_KINDS] = {1, 2, 5, 0, 2, 2, 3, 1, 1, 1, 3, 1}, pw[CPROC_CUDA_NODE_KINDS] = {0, 0, 0, 0, 1, 2, 3, 1, 1, 0, 0, 0};
+        const uint8_t fin[CPROC_CUDA_NODE_KINDS] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 0, 1, 1}, fout[CPROC_CUDA_NODE_KINDS] = {0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1};
         uint32_t o = 0, q = 0;
         for (uint32_t k = 0; k < p.n_nodes; ++k) {
             nodes[k] = p.nodes[k]; off[k] = o; poff[k] = q;
@@ -143,7 +150,8 @@ __global__ void k_graph_table(const GraphParams p) {
                 return want_f && !is_f ? __float_as_uint(__uint2float_rn(v)) : v;
             };
             const uint32_t x = fetch(nodes[k].src, inf[k] != 0);
-            const uint32_t x2 = (nodes[k].type & 0xFFu) == CPROC_CUDA_NODE_PDM ? fetch(nodes[k].src2, false) : 0u;
+            const uint32_t kd = nodes[k].type & 0xFFu;
+            const uint32_t x2 = kd == CPROC_CUDA_NODE_PDM ? fetch(nodes[k].src2, false) : kd == CPROC_CUDA_NODE_MUL ? fetch(nodes[k].src2, true) : 0u;
             node_tick(nodes[k].type, s + off[k], pr + poff[k], x, x2);
         }
         for (uint32_t q = 0; q < p.n_outputs; ++q)

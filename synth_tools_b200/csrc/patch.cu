@@ -21,10 +21,11 @@ namespace {
 // cproc.h:134-148, glide / pdm of cproc_cuda.h, the extension processors of include/cproc_ext.h) plus `input`, an external
 // stream as a source node (the role gpin plays on the microcontroller, hw_cproc_stm32f103.h:8-14).  Class numbers 0..4 are
 // those of ABI version 2.
-enum { CLS_ACC = 0, CLS_EDGE = 1, CLS_GLIDE = 2, CLS_INPUT = 3, CLS_PDM = 4, CLS_PHASOR_F = 5, CLS_SVF = 6, CLS_ENV = 7, CLS_ONEPOLE = 8, CLS_GAIN = 9, CLS_ASFLOAT = 10 };
-const uint32_t k_n_classes = 11;
+enum { CLS_ACC = 0, CLS_EDGE = 1, CLS_GLIDE = 2, CLS_INPUT = 3, CLS_PDM = 4, CLS_PHASOR_F = 5, CLS_SVF = 6, CLS_ENV = 7, CLS_ONEPOLE = 8, CLS_GAIN = 9, CLS_ASFLOAT = 10, CLS_GLIDE_F = 11, CLS_MUL = 12 };
+const uint32_t k_n_classes = 13;
 const int k_class_kind[k_n_classes] = {CPROC_CUDA_NODE_ACC, CPROC_CUDA_NODE_EDGE, CPROC_CUDA_NODE_GLIDE, -1, CPROC_CUDA_NODE_PDM, CPROC_CUDA_NODE_PHASOR_F,
-                                       CPROC_CUDA_NODE_SVF, CPROC_CUDA_NODE_ENV, CPROC_CUDA_NODE_ONEPOLE, CPROC_CUDA_NODE_GAIN, CPROC_CUDA_NODE_ASFLOAT};
+                                       CPROC_CUDA_NODE_SVF, CPROC_CUDA_NODE_ENV, CPROC_CUDA_NODE_ONEPOLE, CPROC_CUDA_NODE_GAIN, CPROC_CUDA_NODE_ASFLOAT,
+                                       CPROC_CUDA_NODE_GLIDE_F, CPROC_CUDA_NODE_MUL};
 const cproc_kind_meta k_input_class = {"input", 0, {nullptr}, 0, 0, {nullptr}, 0, 0, {nullptr}, 0, 1, {"index"}};
 const cproc_kind_meta &class_meta(uint32_t cls) { return k_class_kind[cls] < 0 ? k_input_class : k_cproc_kinds[k_class_kind[cls]]; }
 }  // namespace
@@ -123,9 +124,9 @@ int cproc_cuda_patch_apply(cproc_cuda_patch *p, uint32_t cls, const uint32_t *in
         if (cls == CLS_PDM) {
             if ((config & 7u) < 1 || (config & 7u) > 4 || (config >> 3) > 31) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch_apply: pdm config must be order 1..4 | out_shift << 3");
             row.type = CPROC_CUDA_NODE_PDM | (config << 8);
-        } else if (cls == CLS_GLIDE) {
+        } else if (cls == CLS_GLIDE || cls == CLS_GLIDE_F) {
             if (config < 1 || config > 24) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch_apply: glide div_log must be 1..24");
-            row.type = CPROC_CUDA_NODE_GLIDE_L(config);
+            row.type = (uint32_t)k_class_kind[cls] | (config << 8);
         } else {
             if (config) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "patch_apply: %s takes no config word", m.name);
             row.type = (uint32_t)k_class_kind[cls];

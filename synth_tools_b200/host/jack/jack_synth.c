@@ -116,6 +116,22 @@ int main(void) {
         snprintf(name, sizeof(name), "part_%02d", k);
         audio_out[k] = jack_port_register(client, name, JACK_DEFAULT_AUDIO_TYPE, JackPortIsOutput, 0);
     }
+    /* Warm the period path before the RT callback exists: the first call with a shape allocates the staging buffers, the second
+       captures the period's CUDA graph (cproc_cuda_run, run_graph), and neither belongs on the JACK thread.  The voice table is
+       silent (note_inc == 0 everywhere), so the warm-up leaves every phase where it was. */
+    {
+        const jack_nframes_t period = jack_get_buffer_size(client);
+        cproc_cuda_io io;
+        memset(&io, 0, sizeof(io));
+        io.out = mixbuf; io.layout = CPROC_CUDA_PLANAR;
+        memset(flat, 0, sizeof(flat));
+        for (int k = 0; k < 3 && period && period <= max_frames; k++) {
+            int rc = cproc_cuda_upload_state(bank, flat, sizeof(struct voice));
+            if (!rc) rc = cproc_cuda_run(bank, period, &io);
+            if (!rc) rc = cproc_cuda_download_state(bank, flat, sizeof(struct voice));
+            if (rc) { fprintf(stderr, "jack_synth_b200: warm-up failed (%d): %s\n", rc, cproc_cuda_last_error(ctx)); return 1; }
+        }
+    }
     jack_set_process_callback(client, process, 0);
     if (jack_activate(client)) { fprintf(stderr, "jack_synth_b200: cannot activate\n"); return 1; }
     for (;;) {                            /* stdin is only used to signal exit (synth.c:305-310) */

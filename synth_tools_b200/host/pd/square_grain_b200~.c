@@ -7,8 +7,9 @@
  * objects of the library share ONE batch: a perform routine copies its inlet block into its row of
  * the shared input buffer and hands out its row of the previous tick's result; the first perform of
  * a tick renders the rows collected during the previous tick in one cproc_cuda_run (N grains x n
- * frames).  Cost: one block of latency; state, threshold changes and block-size changes stay exact
- * (the batch is the reference loop, bit for bit, delayed by one block).
+ * frames).  Cost: one block of latency; state and threshold changes stay exact (the batch is the
+ * reference loop, bit for bit, delayed by one block).  Objects in switched-off subpatches and objects
+ * running at another block size do not disturb the others (see struct sg_pipe).
  *
  * Build (with Pd headers):  gcc -std=gnu99 -O2 -fPIC -shared square_grain_b200~.c -I<repo>/include \
  *     -L<repo>/synth_tools_b200 -lcproc_cuda -o square_grain_b200~.pd_linux
@@ -22,56 +23,90 @@
 
 #define SG_MAX_GRAINS 4096
 #define SG_MAX_BLOCK 4096
+#define SG_MAX_PIPES 4
 
 struct square_grain_b200 {
     t_object x_obj;
     t_float x_f;
     t_float brightness;
     t_float threshold;
-    int slot;                 /* row in the shared batch */
+    int slot;                 /* row in the shared batches */
 };
 
 static t_class *square_grain_b200_class;
 
-/* the shared batch */
+/* One pipeline per block size in use (objects under a [block~] run at another size): rows of its size collected in the
+ * running tick, the rendered rows of the previous one.  A tick ends for a pipeline when an object that has already
+ * performed in it performs again -- not when a count is reached, so objects in a switched-off subpatch (whose perform
+ * routine is not called) neither stall the others nor advance: a row that was not collected is not rendered, its state
+ * stays, and the object gets silence for the first block after it comes back. */
+struct sg_pipe {
+    int block;                              /* frames per row; 0 = free */
+    float *in, *out;                        /* [slot][block] */
+    unsigned char ran[SG_MAX_GRAINS];       /* collected in the running tick */
+    unsigned char have[SG_MAX_GRAINS];      /* out row holds the render of the previous tick */
+    int any;                                /* rows collected in the running tick */
+    cproc_cuda_batch *batch;
+    int capacity;
+};
+static struct sg_pipe sg_pipes[SG_MAX_PIPES];
 static cproc_cuda_ctx *sg_ctx;
-static cproc_cuda_batch *sg_batch;
-static int sg_capacity;                 /* grains the batch was allocated for */
 static int sg_count;                    /* objects alive (slots 0..sg_count-1) */
 static struct square_grain_b200 *sg_obj[SG_MAX_GRAINS];
-static float *sg_in, *sg_out;           /* [slot][block] rows collected in this tick / rendered for the previous one */
 static float sg_state[SG_MAX_GRAINS];   /* grain state carried on the host between renders (the struct's `state`) */
 static float sg_th[SG_MAX_GRAINS];      /* threshold in force when the row was collected (messages arrive between ticks) */
-static int sg_block;                    /* frames per row */
-static int sg_filled;                   /* rows written since the last render */
-static int sg_have_out;                 /* sg_out holds a rendered tick */
 static int sg_failed;
 
-static void sg_render(void) {
-    /* renders the rows collected during the previous tick */
-    if (sg_failed || sg_count == 0 || sg_block == 0) return;
+static struct sg_pipe *sg_pipe_for(int n) {
+    struct sg_pipe *free_pipe = NULL;
+    for (int k = 0; k < SG_MAX_PIPES; k++) {
+        if (sg_pipes[k].block == n) return &sg_pipes[k];
+        if (!sg_pipes[k].block && !free_pipe) free_pipe = &sg_pipes[k];
+    }
+    if (!free_pipe) {                                        /* every pipeline is taken: recycle one with nothing pending */
+        for (int k = 0; k < SG_MAX_PIPES && !free_pipe; k++) if (!sg_pipes[k].any) free_pipe = &sg_pipes[k];
+        if (!free_pipe) return NULL;
+        free(free_pipe->in); free(free_pipe->out);
+        if (free_pipe->batch) cproc_cuda_free(free_pipe->batch);
+        memset(free_pipe, 0, sizeof(*free_pipe));
+    }
+    free_pipe->block = n;
+    free_pipe->in = (float *)calloc((size_t)SG_MAX_GRAINS * (size_t)n, sizeof(float));
+    free_pipe->out = (float *)calloc((size_t)SG_MAX_GRAINS * (size_t)n, sizeof(float));
+    if (!free_pipe->in || !free_pipe->out) { free(free_pipe->in); free(free_pipe->out); memset(free_pipe, 0, sizeof(*free_pipe)); return NULL; }
+    return free_pipe;
+}
+
+/* renders the rows the pipeline collected during the tick that just ended */
+static void sg_render(struct sg_pipe *p) {
+    memset(p->have, 0, sizeof(p->have));
+    if (sg_failed || sg_count == 0 || !p->any) { memset(p->ran, 0, sizeof(p->ran)); p->any = 0; return; }
     int rc = 0;
     if (!sg_ctx) rc = cproc_cuda_open(0, NULL, &sg_ctx);
-    if (!rc && (!sg_batch || sg_capacity != sg_count)) {
-        if (sg_batch) cproc_cuda_free(sg_batch);
-        sg_batch = NULL;
+    if (!rc && (!p->batch || p->capacity != sg_count)) {
+        if (p->batch) cproc_cuda_free(p->batch);
+        p->batch = NULL;
         cproc_cuda_config cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.proc = CPROC_CUDA_SQUARE_GRAIN; cfg.layout = CPROC_CUDA_PLANAR;
-        rc = cproc_cuda_alloc(sg_ctx, &cfg, (uint64_t)sg_count, &sg_batch);
-        sg_capacity = sg_count;
+        rc = cproc_cuda_alloc(sg_ctx, &cfg, (uint64_t)sg_count, &p->batch);
+        p->capacity = sg_count;
     }
     if (!rc) {
-        rc = cproc_cuda_upload_state(sg_batch, sg_state, sizeof(float));
-        if (!rc) rc = cproc_cuda_upload_param(sg_batch, sg_th, sizeof(float));
+        static float before[SG_MAX_GRAINS];
+        memcpy(before, sg_state, sizeof(float) * (size_t)sg_count);
+        rc = cproc_cuda_upload_state(p->batch, sg_state, sizeof(float));
+        if (!rc) rc = cproc_cuda_upload_param(p->batch, sg_th, sizeof(float));
         cproc_cuda_io io;
         memset(&io, 0, sizeof(io));
-        io.in = sg_in; io.out = sg_out; io.layout = CPROC_CUDA_PLANAR;
-        if (!rc) rc = cproc_cuda_run(sg_batch, (uint64_t)sg_block, &io);
-        if (!rc) rc = cproc_cuda_download_state(sg_batch, sg_state, sizeof(float));
+        io.in = p->in; io.out = p->out; io.layout = CPROC_CUDA_PLANAR;
+        if (!rc) rc = cproc_cuda_run(p->batch, (uint64_t)p->block, &io);
+        if (!rc) rc = cproc_cuda_download_state(p->batch, sg_state, sizeof(float));
+        if (!rc) for (int g = 0; g < sg_count; g++) { if (p->ran[g]) p->have[g] = 1; else sg_state[g] = before[g]; }   /* rows that were not collected did not run */
     }
-    if (rc) { sg_failed = rc; post("square_grain_b200~: render failed (%d): %s", rc, cproc_cuda_last_error(sg_ctx)); return; }
-    sg_have_out = 1;
+    memset(p->ran, 0, sizeof(p->ran));
+    p->any = 0;
+    if (rc) { sg_failed = rc; memset(p->have, 0, sizeof(p->have)); post("square_grain_b200~: render failed (%d): %s", rc, cproc_cuda_last_error(sg_ctx)); }
 }
 
 static t_int *square_grain_b200_perform(t_int *w) {
@@ -79,24 +114,16 @@ static t_int *square_grain_b200_perform(t_int *w) {
     const int n = (int)(w[2]);
     t_float *in = (t_float *)(w[3]);
     t_float *out = (t_float *)(w[4]);
-    if (n != sg_block || n > SG_MAX_BLOCK) {                 /* block size changed: restart the pipeline */
-        sg_block = n <= SG_MAX_BLOCK ? n : 0; sg_filled = 0; sg_have_out = 0;
-        free(sg_in); free(sg_out);
-        sg_in = (float *)calloc((size_t)SG_MAX_GRAINS * (size_t)(sg_block ? sg_block : 1), sizeof(float));
-        sg_out = (float *)calloc((size_t)SG_MAX_GRAINS * (size_t)(sg_block ? sg_block : 1), sizeof(float));
-    }
-    if (sg_filled >= sg_count) {                             /* first perform of a new tick: render the previous one */
-        sg_render();
-        sg_filled = 0;
-    }
-    /* in may alias out (Pd in-place DSP): hand out the previous tick first into a scratch copy */
-    float prev[SG_MAX_BLOCK];
-    if (sg_have_out && sg_block) memcpy(prev, sg_out + (size_t)x->slot * sg_block, sizeof(float) * n);
-    else memset(prev, 0, sizeof(float) * n);
-    if (sg_block) memcpy(sg_in + (size_t)x->slot * sg_block, in, sizeof(float) * n);
+    struct sg_pipe *p = n > 0 && n <= SG_MAX_BLOCK ? sg_pipe_for(n) : NULL;
+    if (!p) { memset(out, 0, sizeof(t_float) * (size_t)(n > 0 ? n : 0)); return w + 5; }
+    if (p->ran[x->slot]) sg_render(p);                       /* this object again: the pipeline's tick is over */
+    /* in may alias out (Pd in-place DSP): take the inlet block before handing out the previous tick's result */
+    float *row_in = p->in + (size_t)x->slot * n, *row_out = p->out + (size_t)x->slot * n;
+    memcpy(row_in, in, sizeof(float) * (size_t)n);
     sg_th[x->slot] = x->threshold;
-    memcpy(out, prev, sizeof(float) * n);
-    sg_filled++;
+    if (p->have[x->slot]) memcpy(out, row_out, sizeof(float) * (size_t)n);
+    else memset(out, 0, sizeof(float) * (size_t)n);
+    p->ran[x->slot] = 1; p->any = 1;
     return w + 5;
 }
 
@@ -113,8 +140,8 @@ static void *square_grain_b200_new(t_floatarg threshold) {
     x->brightness = 1.0f;
     x->slot = sg_count;
     sg_state[sg_count] = 0.0f;                               /* :129 */
+    for (int k = 0; k < SG_MAX_PIPES; k++) { sg_pipes[k].ran[sg_count] = 0; sg_pipes[k].have[sg_count] = 0; }
     sg_obj[sg_count++] = x;
-    sg_filled = sg_count;                                    /* the next perform starts a fresh tick */
     inlet_new(&x->x_obj, &x->x_obj.ob_pd, gensym("float"), gensym("threshold"));
     outlet_new(&x->x_obj, gensym("signal"));
     return x;
@@ -126,13 +153,16 @@ static void square_grain_b200_free(struct square_grain_b200 *x) {
     if (x->slot != last) {
         sg_obj[x->slot] = sg_obj[last]; sg_obj[x->slot]->slot = x->slot;
         sg_state[x->slot] = sg_state[last]; sg_th[x->slot] = sg_th[last];
-        if (sg_block) {
-            memcpy(sg_in + (size_t)x->slot * sg_block, sg_in + (size_t)last * sg_block, sizeof(float) * sg_block);
-            memcpy(sg_out + (size_t)x->slot * sg_block, sg_out + (size_t)last * sg_block, sizeof(float) * sg_block);
+        for (int k = 0; k < SG_MAX_PIPES; k++) {
+            struct sg_pipe *p = &sg_pipes[k];
+            if (!p->block) continue;
+            memcpy(p->in + (size_t)x->slot * p->block, p->in + (size_t)last * p->block, sizeof(float) * (size_t)p->block);
+            memcpy(p->out + (size_t)x->slot * p->block, p->out + (size_t)last * p->block, sizeof(float) * (size_t)p->block);
+            p->ran[x->slot] = p->ran[last]; p->have[x->slot] = p->have[last];
         }
     }
+    for (int k = 0; k < SG_MAX_PIPES; k++) { sg_pipes[k].ran[last] = 0; sg_pipes[k].have[last] = 0; }
     sg_count = last;
-    sg_filled = sg_count;
 }
 
 void square_grain_b200_tilde_setup(void) {

@@ -2,7 +2,8 @@
  * GRAINS objects with different thresholds, builds the DSP chain by calling each object's "dsp"
  * method, then runs TICKS DSP ticks of BLOCK samples -- objects 0 and 1 in place (inlet vector ==
  * outlet vector, as Pd does) -- with inputs from xorshift32, sends a "threshold" message half way,
- * and prints every outlet block as hex floats:   out <tick> <grain> <f0> ...  */
+ * and prints every outlet block as hex floats:   out <tick> <grain> <f0> ...   A second scene switches one object off for three
+ * ticks (out2 lines). */
 #include <stdarg.h>
 #include <stddef.h>
 #include <stdio.h>
@@ -65,6 +66,21 @@ int main(void) {
         for (int g = 0; g < GRAINS; g++) {
             const float *o = g < 2 ? vin[g] : vout[g];
             printf("out %d %d", tick, g);
+            for (int t = 0; t < BLOCK; t++) printf(" %a", o[t]);
+            printf("\n");
+        }
+    }
+    /* second scene: object 1 sits in a switched-off subpatch for ticks TICKS .. TICKS+2 (its perform routine is not called), then
+       comes back; the others carry on.  Printed as out2 <tick> <grain>. */
+    for (int tick = TICKS; tick < TICKS + 5; tick++) {
+        const int off = tick < TICKS + 3;
+        for (int g = 0; g < GRAINS; g++)
+            for (int t = 0; t < BLOCK; t++) { s ^= s << 13; s ^= s >> 17; s ^= s << 5; vin[g][t] = (float)(int32_t)s * (1.0f / 2147483648.0f); }
+        for (int k = 0; k < chain_len; k++) if (!(off && k == 1)) chain[k].f(chain[k].w);
+        for (int g = 0; g < GRAINS; g++) {
+            if (off && g == 1) continue;
+            const float *o = g < 2 ? vin[g] : vout[g];
+            printf("out2 %d %d", tick, g);
             for (int t = 0; t < BLOCK; t++) printf(" %a", o[t]);
             printf("\n");
         }

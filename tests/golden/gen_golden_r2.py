@@ -48,7 +48,7 @@ for k in range(3):
     st = np.zeros((N, state_words(rows)), np.uint32)
     outs = list(range(len(rows)))[-3:]
     out = ref.graph_run_ext(rows, n_in, outs, st, prm, N, F, inp, chg if k == 2 else None)
-    G["ext%d_rows" % k] = np.array([[r[0], r[1], r[2]] for r in rows], np.int64)
+    G["ext%d_rows" % k] = np.array([[r[0], r[1], r[2], r[3] if len(r) > 3 else 0] for r in rows], np.int64)
     G["ext%d_param" % k] = prm if prm is not None else np.zeros((N, 0), np.uint32)
     G["ext%d_in" % k], G["ext%d_changed" % k], G["ext%d_out" % k], G["ext%d_state" % k] = inp, chg, out, st
 # the graph texts compiled as C (one instance each, from zero state; private copies: node state is function-static)
@@ -64,6 +64,8 @@ cin = np.zeros((2, F), np.uint32)
 cin[0] = rng.integers(0, 2, F); cin[1] = rng.integers(0, 1 << 20, F)
 cch = rng.integers(0, 4, F).astype(np.uint32)
 G["extchain_in"], G["extchain_changed"], G["extchain_out"] = cin, cch, r1.ext_text_run(1, cin, cch, F, 3)
+gin = np.repeat(rng.uniform(0, 1, F // 64 + 1).astype(np.float32), 64)[:F].view(np.uint32).reshape(1, F).copy()
+G["extgain_in"], G["extgain_out"] = gin, r1.ext_text_run(2, gin, None, F, 1)
 
 np.savez_compressed(os.path.join(HERE, "golden_r2.npz"), **G)
 print("wrote golden_r2.npz,", len(G), "arrays")

@@ -263,7 +263,7 @@ def test_golden_graph_texts_compiled_as_c(be):
     """tests/golden/ext_voice.cproc / ext_chain.cproc compiled as C with the reference's PROC / PROC_COND macros."""
     from synth_tools_b200 import abi
     here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-    for name, n_in in (("voice", 1), ("chain", 2)):
+    for name, n_in in (("voice", 1), ("chain", 2), ("gain", 1)):
         g = abi.graph_parse_ex(open(os.path.join(here, "ext_%s.cproc" % name)).read())
         inp = G2["ext%s_in" % name].reshape(1, n_in, -1).copy()
         chg = G2["extchain_changed"].reshape(1, -1).copy() if name == "chain" else None

@@ -235,6 +235,36 @@ def test_pd_external_with_scripted_backend(tmp_path, oracle):
         want = oracle.square_grain_run(state, th.copy(), G, B, np.ascontiguousarray(inp[tick]))
         for g in range(G):
             assert np.array_equal(got[(tick + 1, g)].view(np.uint32), want[g].view(np.uint32)), (tick, g)
+    # second scene: object 1 switched off for ticks T .. T+2 (a global count would stall every object)
+    got2 = {}
+    for l in res.stdout.splitlines():
+        f = l.split()
+        if f and f[0] == "out2":
+            got2[(int(f[1]), int(f[2]))] = np.array([float.fromhex(x) for x in f[3:]], np.float32)
+    # the last block of scene one (tick T-1) is rendered when scene two starts
+    want = oracle.square_grain_run(state, th.copy(), G, B, np.ascontiguousarray(inp[T - 1]))
+    inp2 = np.zeros((5, G, B), np.float32)
+    for tick in range(5):
+        for g in range(G):
+            for t in range(B):
+                s = xs(s)
+                inp2[tick, g, t] = np.float32(np.int32(np.uint32(s))) * np.float32(1.0 / 2147483648.0)
+    for tick in range(5):
+        off = tick < 3
+        for g in range(G):
+            if off and g == 1:
+                assert (T + tick, g) not in got2
+                continue
+            if g == 1 and tick == 3:
+                assert np.all(got2[(T + tick, g)] == 0.0)        # not collected in the previous tick: silence, state kept
+            else:
+                assert np.array_equal(got2[(T + tick, g)].view(np.uint32), want[g].view(np.uint32)), (tick, g)
+        active = [g for g in range(G) if not (off and g == 1)]
+        sub_state = state[active].copy()
+        w = oracle.square_grain_run(sub_state, th[active].copy(), len(active), B, np.ascontiguousarray(inp2[tick][active]))
+        state[active] = sub_state
+        want = np.zeros((G, B), np.float32)
+        want[active] = w
 
 
 def test_jack_clock_adapter_with_scripted_backend(tmp_path, oracle):

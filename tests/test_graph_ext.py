@@ -18,8 +18,9 @@ from synth_tools_b200 import abi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VOICE_TEXT = open(os.path.join(ROOT, "tests", "golden", "ext_voice.cproc")).read()
 CHAIN_TEXT = open(os.path.join(ROOT, "tests", "golden", "ext_chain.cproc")).read()
-EXT_KINDS = [po.NODE_PHASOR_F, po.NODE_SVF, po.NODE_ENV, po.NODE_ONEPOLE, po.NODE_GAIN, po.NODE_ASFLOAT]
-IN_FLOAT = {po.NODE_SVF, po.NODE_ENV, po.NODE_ONEPOLE, po.NODE_GAIN}
+GAIN_TEXT = open(os.path.join(ROOT, "tests", "golden", "ext_gain.cproc")).read()
+EXT_KINDS = [po.NODE_PHASOR_F, po.NODE_SVF, po.NODE_ENV, po.NODE_ONEPOLE, po.NODE_GAIN, po.NODE_ASFLOAT, po.NODE_GLIDE_F, po.NODE_MUL]
+IN_FLOAT = {po.NODE_SVF, po.NODE_ENV, po.NODE_ONEPOLE, po.NODE_GAIN, po.NODE_GLIDE_F, po.NODE_MUL}
 F32 = lambda x: np.float32(x).view(np.uint32)
 
 
@@ -43,7 +44,12 @@ def random_ext_graph(rng, n_nodes, n_inputs, with_int_nodes=True, masks=False):
         if not cands:
             kind, cands = po.NODE_PHASOR_F, [po.SRC_ZERO]
         mask = int(rng.choice([1, 2, 3, 6, 0xFFFFFFFF])) if masks else 0xFFFFFFFF
-        rows.append((kind, int(rng.choice(cands)), mask))
+        if kind == po.NODE_GLIDE_F:
+            rows.append((po.node_glide_f(int(rng.integers(1, 7))), int(rng.choice(cands)), mask))
+        elif kind == po.NODE_MUL:                                # two float inputs
+            rows.append((kind, int(rng.choice(cands)), mask, int(rng.choice(cands))))
+        else:
+            rows.append((kind, int(rng.choice(cands)), mask))
     return rows
 
 
@@ -77,7 +83,8 @@ def test_ext_structs_compile_against_the_reference_cproc_h(ref):
     """DEF_PROC_STRUCTS (cproc.h:99-103) of include/cproc_ext.h: struct sizes = the word counts every layer uses
     (GNU C: an empty field list gives size 0, like acc_config)."""
     want = {po.NODE_PHASOR_F: (8, 4, 4), po.NODE_SVF: (8, 8, 4), po.NODE_ENV: (12, 12, 4), po.NODE_ONEPOLE: (4, 4, 4),
-            po.NODE_GAIN: (4, 4, 4), po.NODE_ASFLOAT: (4, 0, 4)}
+            po.NODE_GAIN: (4, 4, 4), po.NODE_ASFLOAT: (4, 0, 4), po.NODE_GLIDE_F: (12, 0, 4), po.NODE_MUL: (4, 0, 8)}
+    assert ref.ext_sizeof(24) == 4                               # glide_f_config {w div_log}
     for kind, (s, p, i) in want.items():
         k = kind - po.NODE_PHASOR_F
         assert (ref.ext_sizeof(3 * k), ref.ext_sizeof(3 * k + 1), ref.ext_sizeof(3 * k + 2)) == (s, p, i), kind
@@ -141,6 +148,17 @@ def test_graph_text_compiled_as_c_equals_the_parsed_table(ref, oracle, tmp_path)
     got = oracle.graph_run_ext(g["rows"], 2, g["out_nodes"], st, g["param_init"].reshape(1, -1).copy(), 1, F, inp, chg)
     assert np.array_equal(got[0], want)
     assert want[0].max() > 10 and np.array_equal(want[2].view(np.float32)[-1], np.float32(0.5) * np.float32(want[0][-1]))
+    # gain: a control-rate gain amount through glide_f, applied by mul (doc/combinators.org:28-34)
+    g = abi.graph_parse_ex(GAIN_TEXT)
+    assert g["rows"] == [(po.NODE_PHASOR_F, po.SRC_ZERO, 0xFFFFFFFF), (po.NODE_ASFLOAT, -1, 0xFFFFFFFF), (po.node_glide_f(6), 1, 0xFFFFFFFF),
+                         (po.NODE_MUL, 0, 0xFFFFFFFF, 2)] and g["n_inputs"] == 1 and g["out_is_float"] == [True]
+    amt = np.repeat(rng.uniform(0, 1, F // 64 + 1).astype(np.float32), 64)[:F].view(np.uint32).reshape(1, 1, F).copy()
+    want = r.ext_text_run(2, np.ascontiguousarray(amt[0]), None, F, 1)
+    st = np.zeros((1, state_words(g["rows"])), np.uint32)
+    got = oracle.graph_run_ext(g["rows"], 1, g["out_nodes"], st, g["param_init"].reshape(1, -1).copy(), 1, F, amt)
+    assert np.array_equal(got[0], want)
+    a = amt.view(np.float32)[0, 0]                               # ramp.out after 700 ticks: 60 of the 64 steps from the target of tick 576 to that of tick 640
+    assert abs(float(st[0, 3:4].view(np.float32)[0]) - (float(a[576]) + (float(a[640]) - float(a[576])) * 60 / 64)) < 1e-3
 
 
 def voice_graph_and_records(rng, N):
@@ -255,7 +273,7 @@ def test_gpu_ext_graphs_bit_exact(ctx, oracle, seed, layout, N, F, jit):
         w = po.node_words(r[0])
         if (r[0] & 0xFF) >= po.NODE_PHASOR_F:
             st0[:, o] = rng.uniform(-1, 1, N).astype(np.float32).view(np.uint32)
-            if (r[0] & 0xFF) in (po.NODE_SVF, po.NODE_ENV):
+            if (r[0] & 0xFF) in (po.NODE_SVF, po.NODE_ENV, po.NODE_GLIDE_F):
                 st0[:, o + 1] = rng.uniform(0, 1, N).astype(np.float32).view(np.uint32)
         o += w
     sa = st0.copy()
@@ -298,13 +316,15 @@ def test_gpu_graph_text_to_render(ctx, oracle):
     """The .cproc texts end to end on the GPU: parse -> alloc -> param record from the text's literals -> render."""
     import synth_tools_b200 as st
     rng = np.random.default_rng(9)
-    for text, n_out in ((VOICE_TEXT, 2), (CHAIN_TEXT, 3)):
+    for text, n_out in ((VOICE_TEXT, 2), (CHAIN_TEXT, 3), (GAIN_TEXT, 1)):
         g = st.graph_parse_ex(text)
         N, F = 500, 384
         n_in = g["n_inputs"]
         inp = rng.integers(0, 1 << 20, (N, n_in, F)).astype(np.uint32)
         if n_in == 2:
             inp[:, 0] = rng.integers(0, 2, (N, F))
+        if text is GAIN_TEXT:
+            inp[:, 0] = rng.uniform(0, 1, (N, F)).astype(np.float32).view(np.uint32)
         chg = rng.integers(0, 4, (N, F)).astype(np.uint32) if n_in == 2 else None
         prm = np.ascontiguousarray(np.tile(g["param_init"], (N, 1)))
         prm[:, 0] = rng.integers(1 << 20, 1 << 27, N)             # per-instance pitch
@@ -359,14 +379,16 @@ def test_gpu_patcher_with_extension_classes(ctx, oracle):
     p.close()
 
 
-@pytest.mark.parametrize("which", ["voice", "chain", "free", "random"])
+@pytest.mark.parametrize("which", ["voice", "chain", "gain", "free", "random"])
 def test_ext_generated_source_compiles_for_sm_100a_without_a_diagnostic(which):
     """The JIT path without a device: the source the library generates for graphs with extension processors (also
     with no input stream at all) compiles with NVRTC exactly as graph_front.cu compiles it, with an empty log."""
     import ctypes as C
     from tests.test_graph_front import _nvrtc
     rng = np.random.default_rng(12)
-    if which == "voice":
+    if which == "gain":
+        g = abi.graph_parse_ex(GAIN_TEXT); rows, n_in, outs, chg = g["rows"], g["n_inputs"], g["out_nodes"], False
+    elif which == "voice":
         g = abi.graph_parse_ex(VOICE_TEXT); rows, n_in, outs, chg = g["rows"], g["n_inputs"], g["out_nodes"], False
     elif which == "chain":
         g = abi.graph_parse_ex(CHAIN_TEXT); rows, n_in, outs, chg = g["rows"], g["n_inputs"], g["out_nodes"], True
