@@ -73,7 +73,7 @@ def build(force=False):
     """Compile the oracle (always possible) and oracle/_ref (only where the
     reference tree is present; elsewhere the prebuilt .so is used)."""
     if force or not os.path.exists(ORACLE_SO) or \
-            os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(HERE, "cproc_oracle.c")):
+            os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(os.path.join(HERE, f)) for f in ("cproc_oracle.c", "arm_v1_model.c", "build_oracle.sh")):
         subprocess.check_call(["bash", os.path.join(HERE, "build_oracle.sh")])
     if os.path.isdir(os.environ.get("REF", "/root/reference")):
         recipe = [os.path.join(HERE, "build_ref.sh")] + [os.path.join(d, f) for d in (os.path.join(HERE, "ref"), os.path.join(HERE, "shim"), os.path.join(HERE, "shim", "stm32"))
@@ -191,6 +191,17 @@ class Oracle(_Lib):
         f = self._fn("pdm_v1_run", None, [VP, C.c_uint64, C.c_uint32, VP, VP, C.c_uint32, C.c_uint64, VP])
         f(_ptr(ch), N, bank_size, _ptr(prng), _ptr(dither_ext), dither_mask, F, _ptr(bits))
         return bits
+
+    def arm_v1_mcu_run(self, chan, pin_chan0, rng, dmask, F):
+        """oracle/arm_v1_model.c: the reference's adds / rrx sequence (mod_pdm.c:214-275) on a model of the ARM flags, ONE MCU of
+        chan.shape[0] channels.  chan uint32 [n][2] in/out; returns (gpio set_bits uint32 [F], rng')."""
+        gpio = np.zeros(F, np.uint32)
+        r = C.c_uint32(int(rng))
+        f = getattr(self.lib, "arm_v1_mcu_run")
+        f.restype = None
+        f.argtypes = [VP, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint64, VP]
+        f(_ptr(chan), chan.shape[0], pin_chan0, C.byref(r), dmask, F, _ptr(gpio))
+        return gpio, r.value
 
     def pwm_run(self, phase, speed, N, F):
         duty = np.zeros((N, F), np.uint8)

@@ -266,3 +266,28 @@ def test_pixi_lfo_bank_vs_acc(ref, oracle):
         out = oracle.graph_run([(po.NODE_ACC, -1, 0xFFFFFFFF)], 1, 0, st, 12, 500, inp)
         assert np.array_equal((out & 0xFFF).T, trace.astype(np.uint32))
         assert np.array_equal(st[:, 0] & 0xFFF, dac.astype(np.uint32))
+
+
+@pytest.mark.parametrize("n_ch,pin0", [(2, 0), (3, 5), (8, 2), (16, 16), (32, 0)])
+def test_v1_restatement_against_the_arm_instruction_model(oracle, n_ch, pin0):
+    """SURVEY 8 a-14 (ARM inline asm, no ARM toolchain here: restated).  Two independent readings of `adds` + `rrx`
+    (mod_pdm.c:214-244) must agree: the add-with-carry restatement behind every v1 parity test (carry = a < x, bits laid out
+    per channel over time) and oracle/arm_v1_model.c (AddWithCarry's 33-bit sum, RRX through the C flag, ONE shift register
+    per tick over the MCU's channels and the GPIO alignment shift of pdm_update, :254-275)."""
+    rng = np.random.default_rng(n_ch)
+    F = 2000
+    ch = np.zeros((n_ch, 2), np.uint32)
+    ch[:, 0] = rng.integers(0, 2**32, n_ch, dtype=np.uint32)
+    ch[0, 0] = 0xFFFFFFFF                                       # setpoint + dither wraps
+    ch[:, 1] = rng.integers(0, 2**32, n_ch, dtype=np.uint32)
+    seed = 2463534242
+    a = ch.copy()
+    gpio, rng1 = oracle.arm_v1_mcu_run(a, pin0, seed, 0x0FFFFFFF, F)
+    b = ch.copy()
+    prng = np.array([seed], np.uint32)
+    bits = oracle.pdm_v1_run(b, n_ch, n_ch, prng, None, 0x0FFFFFFF, F)     # one bank = the MCU's channels, one dither word per tick
+    assert np.array_equal(a, b) and rng1 == int(prng[0])
+    for c in range(n_ch):
+        assert np.array_equal((gpio >> np.uint32(pin0 + c)) & 1, bits[c].astype(np.uint32)), c
+    if pin0 + n_ch < 32:
+        assert not np.any(gpio >> np.uint32(pin0 + n_ch))       # nothing above the last channel's pin
