@@ -45,6 +45,7 @@ struct cproc_cuda_ctx {
     int graph_vec4 = 1;       // interleaved generated graphs: four instances per thread when n % 4 == 0
     int graph_jit = 1;        // 1: generated graphs are compiled with NVRTC; 0: table-driven kernel
     int xvoice_vpt = 0;       // k_xvoice_mix: voices per thread per L2-resident tile (0 = default)
+    int xvoice_mix2_per_sm = 0;   // k_xvoice_mix2: co-resident blocks per SM on this device (occupancy API, cached at the first launch)
     int xvoice_mix2_blocks = 0;   // k_xvoice_mix2: resident blocks per SM (0 = by the round model in launch_xvoice, else 1..3)
     int xvoice_mix2 = 1;      // mix-only XVOICE render: 1 = k_xvoice_mix2 (voice pairs on the packed fp32 pipe, state tiles in shared memory), 0 = k_xvoice_mix
     int xvoice_groups = 0;    // XVOICE_SCAN: variant groups pipelined over the two streams (0 = automatic)

@@ -1073,16 +1073,18 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     // (second-generation kernel: three blocks per SM, each with a 50 KB state tile; the launch's final reduction waits for the
     // stragglers, so the grid must be co-resident: ask the runtime how many blocks really fit)
     const bool mix2 = mix_only && ctx->xvoice_mix2;
-    static int mix2_per_sm = 0;
     const size_t mix2_smem = sizeof(uint32_t) * 5 * 256 * XM2_GMAX;
-    if (mix2 && !mix2_per_sm) {
+    if (mix2) {
+        // (function attributes are per device: set on every launch, like the other staging kernels; the occupancy is cached per context)
         CK(ctx, cudaFuncSetAttribute(k_xvoice_mix2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mix2_smem));
-        CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mix2_per_sm, k_xvoice_mix2, XM2_BLOCK, mix2_smem));
-        if (mix2_per_sm < 1) return cproc_set_err(ctx, CPROC_CUDA_ECUDA, "xvoice: k_xvoice_mix2 does not fit an SM");
-        if (mix2_per_sm > XM2_MINB) mix2_per_sm = XM2_MINB;
+        if (!ctx->xvoice_mix2_per_sm) {
+            int occ = 0;
+            CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_xvoice_mix2, XM2_BLOCK, mix2_smem));
+            if (occ < 1) return cproc_set_err(ctx, CPROC_CUDA_ECUDA, "xvoice: k_xvoice_mix2 does not fit an SM");
+            ctx->xvoice_mix2_per_sm = occ > XM2_MINB ? XM2_MINB : occ;
+        }
     }
-    // (the float mix depends on which block sums which voices: k_xvoice_mix2 always leaves the slot a pipelined bus needs for its
-    // exchange block free, so that the bits of the mix do not depend on whether, or how, a bus is attached)
+    const int mix2_per_sm = ctx->xvoice_mix2_per_sm;
     // Blocks per SM.  A block's work comes in rounds of 256 voices (one pair per thread, all chunks of the launch: ~38 us): 4 Mi voices
     // are 36.9 rounds per block at three blocks per SM (0.3 % lost to the last, uneven round), a 512 Ki-voice shard of an 8-GPU render
     // is 4.62 -> 5 rounds (8 % lost: the residual limiter of the C4 strong-scaling row).  Two blocks per SM do not help (6.94 -> 7

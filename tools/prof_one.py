@@ -107,7 +107,8 @@ elif which in ("gvoice", "gvoice_il"):
     # the C4 voice as a generated graph of extension processors: no input stream, two float output streams
     from tools.bench_configs import VOICE_GRAPH_TEXT
     g = st.graph_parse_ex(VOICE_GRAPH_TEXT)
-    N, F = 2 * 1024 * 1024, 512
+    F = int(os.environ.get("GV_F", 512))            # frames per launch: the row length of the PLANAR output
+    N = 2 * 1024 * 1024 * 512 // F
     stt, prm = xvoice_records(N)
     gst = np.zeros((N, 9), np.uint32); gst[:, 1] = stt[:, 0]
     d_out = ctx.dev_alloc(8 * N * F)
