@@ -204,6 +204,7 @@ int cproc_cuda_alloc(cproc_cuda_ctx *ctx, const cproc_cuda_config *cfg, uint64_t
         b->npad = b->n_banks * b->cfg.bank_size;
     } else { b->n_banks = 0; b->npad = n; }
     b->npad = (b->npad + 3) & ~3ull;        // rows 16-byte aligned
+    if (c.proc == CPROC_CUDA_XVOICE) b->npad = (b->npad + 255) & ~255ull;   // k_xvoice_mix2 walks whole groups of 256 voices without bounds checks (rows are zero past n)
     if (c.proc == CPROC_CUDA_VOICE_BANK) {
         if (b->cfg.voices_per_bus == 0 || b->cfg.voices_per_bus > n) b->cfg.voices_per_bus = n;
         b->n_bus = ceil_div_u64(n, b->cfg.voices_per_bus);

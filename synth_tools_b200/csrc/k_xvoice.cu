@@ -26,6 +26,7 @@ struct XVoiceParams {
     uint32_t *done;          // k_xvoice_mix: [2] blocks that left / finalisers done (zero between launches)
     uint32_t n_render_blocks;// k_xvoice_mix: gridDim.x without the finisher block of a pipelined bus
     uint32_t vpt;            // k_xvoice_mix: voices per thread per L2 tile
+    uint32_t rows_per_block; // partial rows a block writes per channel pair: 1 (k_xvoice_mix), 4 = one per warp (k_xvoice_mix2)
 };
 
 struct XV {
@@ -197,6 +198,7 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t *p) { uint
 // n_fin-th) each and add the block rows in a fixed order; with a mix bus attached they push their columns to the peers.
 __device__ __forceinline__ void xm_finish(const XVoiceParams &p, const BusFused &bf, const uint32_t n_chunks, uint32_t &tick_s) {
     const uint32_t nb = p.n_render_blocks;
+    const uint32_t n_rows = nb * p.rows_per_block;               // partial rows of the launch: one per block, or one per warp (k_xvoice_mix2)
     const uint32_t n_fin = n_chunks < nb ? n_chunks : nb;
     __threadfence();
     __syncthreads();
@@ -210,7 +212,7 @@ __device__ __forceinline__ void xm_finish(const XVoiceParams &p, const BusFused 
         const uint64_t t0 = (uint64_t)c * XM_CHUNK;
         const uint32_t cols = p.F - t0 < XM_CHUNK ? (uint32_t)(p.F - t0) : XM_CHUNK;
         const uint32_t col = threadIdx.x >> 1, half = threadIdx.x & 1u, ch = col / XM_CHUNK, f = col % XM_CHUNK;
-        const uint32_t b0 = half ? (nb + 1) / 2 : 0u, b1 = half ? nb : (nb + 1) / 2;
+        const uint32_t b0 = half ? (n_rows + 1) / 2 : 0u, b1 = half ? n_rows : (n_rows + 1) / 2;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         if (f < cols) {
             const float *src = p.partial + (uint64_t)ch * p.F + t0 + f;
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(XM_BLOCK, 4) k_xvoice_mix(const XVoiceParams p
 // into its partial row; the launch's final reduction and the bus exchange are those of the first kernel (xm_finish).
 #define XM2_BLOCK 128
 #ifndef XM2_GMAX
-#define XM2_GMAX 10                                  // groups (of 256 voices) per tile: 10 x 5 KB of state (+ 20 KB column buffer: three blocks per SM)
+#define XM2_GMAX 14                                  // groups (of 256 voices) per tile: 14 x 5 KB of state, three blocks per SM
 #endif
 #ifndef XM2_MINB
 #define XM2_MINB 3                                   // resident blocks per SM (register cap 168)
@@ -380,10 +382,6 @@ __device__ __forceinline__ uint32_t xv_amask(uint32_t t, uint32_t gate) {
 
 __global__ void __launch_bounds__(XM2_BLOCK, XM2_MINB) k_xvoice_mix2(const XVoiceParams p, const BusFused bf) {
     extern __shared__ __align__(16) uint32_t xm2_tile[];            // [5][256 * ng]: phase, lp, bp, env, t of the tile's voices
-    // column buffer of the block reduction: element (frame k, thread t) at k * 161 + (t >> 5) * 40 + (t & 31).  Writers (a warp: one
-    // k, 32 consecutive t) and readers (a warp: 8 columns x 4 quarters of 32 rows, the same row offset) both touch 32 distinct banks:
-    // bank = k + 8 * (t >> 5) + (t & 31) mod 32.
-    __shared__ float red[XM_CHUNK * 161];
     __shared__ uint32_t tick_s;
     if (blockIdx.x >= p.n_render_blocks) { bus_exchange_block(bf); return; }      // pipelined bus: the previous frame block's exchange
     const uint32_t nb = p.n_render_blocks, tid = threadIdx.x;
@@ -391,30 +389,44 @@ __global__ void __launch_bounds__(XM2_BLOCK, XM2_MINB) k_xvoice_mix2(const XVoic
     const uint64_t G = (p.n + 255) / 256;
     const uint64_t g_lo = G * blockIdx.x / nb, g_hi = G * (blockIdx.x + 1) / nb;
     const uint32_t kg = (uint32_t)(g_hi - g_lo), nt = (kg + XM2_GMAX - 1) / XM2_GMAX;
-    if (kg == 0)                                                    // more blocks than groups: an all-zero partial row
-        for (uint64_t idx = tid; idx < 2 * p.F; idx += XM2_BLOCK) p.partial[(uint64_t)blockIdx.x * 2 * p.F + idx] = 0.0f;
+    if (kg == 0)                                                    // more blocks than groups: all-zero partial rows
+        for (uint64_t idx = tid; idx < 2 * p.F * (XM2_BLOCK / 32); idx += XM2_BLOCK) p.partial[(uint64_t)blockIdx.x * (XM2_BLOCK / 32) * 2 * p.F + idx] = 0.0f;
     const xv2_t c31 = xv2_pack(0x1p-31f, 0x1p-31f);
     for (uint32_t ti = 0; ti < nt; ++ti) {
         const uint64_t ga = g_lo + (uint64_t)kg * ti / nt, gb = g_lo + (uint64_t)kg * (ti + 1) / nt;
-        const uint32_t ng = (uint32_t)(gb - ga), TV = ng * 256;
+        const uint32_t ng = (uint32_t)(gb - ga);
         const uint64_t v0 = ga * 256;
-        // ---- tile state in: [5][npad] rows -> shared memory, two adjacent voices per thread and group
-        for (uint32_t w = 0; w < 5; ++w)
-            for (uint32_t j = 0; j < ng; ++j) {
-                const uint32_t idx = 2 * (tid + XM2_BLOCK * j);
-                const uint64_t gi = v0 + idx;
-                uint2 val = make_uint2(0u, 0u);
-                if (gi < p.npad) val = __ldcs((const uint2 *)(p.st + (uint64_t)w * p.npad + gi));     // npad % 4 == 0: the pair never straddles the row end; [n, npad) is zero
-                *(uint2 *)(xm2_tile + w * TV + idx) = val;
-            }
-        __syncthreads();
-        auto load_prm = [&](uint32_t j, uint2 (&q)[8]) {
+        // ---- tile state in: [5][npad] rows -> shared memory.  A thread only ever touches the state of ITS pairs, so the tile is laid out
+        // pair-major, 5 x uint2 (40 bytes) per pair: the five accesses of a pair are one base + immediate offsets (no dependent address
+        // chain in front of the tick loop), 64-bit accesses at a 40-byte lane stride are conflict free per half-warp, and no barrier is
+        // needed between the tile phases.
+        for (uint32_t j = 0; j < ng; ++j) {
             const uint64_t gi = v0 + 2 * (tid + XM2_BLOCK * j);
+            uint32_t *sp = xm2_tile + (size_t)(tid + XM2_BLOCK * j) * 10;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) q[w] = gi < p.npad ? __ldg((const uint2 *)(p.prm + (uint64_t)w * p.npad + gi)) : make_uint2(0u, 0u);
+            for (uint32_t w = 0; w < 5; ++w) *(uint2 *)(sp + 2 * w) = __ldcs((const uint2 *)(p.st + (uint64_t)w * p.npad + gi));     // npad % 256 == 0: whole groups; [n, npad) is zero
+        }
+        // (npad is a multiple of 256 for this processor and the rows are zero past n: whole groups, no bounds checks; one 64-bit base per
+        // tile and a row pitch in uint2 units keep the address arithmetic of the 8 loads to a handful of instructions -- written as
+        // `p.prm + w * npad + gi` with a predicate it was ~60 instructions of IMAD.WIDE / LEA.HI.X per pair and chunk)
+        const uint2 *tile_prm = (const uint2 *)(p.prm + v0) + tid;
+        const uint64_t row2 = p.npad >> 1;
+        auto load_prm = [&](uint32_t j, uint2 (&q)[8]) {
+            const uint2 *pp = tile_prm + XM2_BLOCK * j;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) q[w] = __ldg(pp + (uint64_t)w * row2);
         };
-        uint2 nq[8];
+        // a pair's five state words out of the tile; issued one pair ahead like the parameters, so that the shared-memory latency, the
+        // attack masks and the path decision of pair j+1 do not sit between two tick loops (profiles/r2_xvoice_mix2_summary.txt: the
+        // ~150 instructions around a 32-tick loop took 35 % of the kernel's samples at 2.5 warps per scheduler)
+        auto load_st = [&](uint32_t j, uint2 (&st)[5]) {
+            const uint32_t *sp = xm2_tile + (size_t)(tid + XM2_BLOCK * j) * 10;
+#pragma unroll
+            for (int w = 0; w < 5; ++w) st[w] = *(const uint2 *)(sp + 2 * w);
+        };
+        uint2 nq[8], nst[5];
         load_prm(0, nq);
+        load_st(0, nst);
         for (uint32_t c = 0; c < n_chunks; ++c) {
             const uint64_t t0 = (uint64_t)c * XM_CHUNK;
             const uint32_t cols = p.F - t0 < XM_CHUNK ? (uint32_t)(p.F - t0) : XM_CHUNK;
@@ -426,9 +438,12 @@ __global__ void __launch_bounds__(XM2_BLOCK, XM2_MINB) k_xvoice_mix2(const XVoic
                 uint2 q[8];
 #pragma unroll
                 for (int w = 0; w < 8; ++w) q[w] = nq[w];
-                if (j + 1 < ng) load_prm(j + 1, nq); else if (c + 1 < n_chunks) load_prm(0, nq);
-                uint32_t *sp = xm2_tile + 2 * (tid + XM2_BLOCK * j);
-                uint2 ph = *(uint2 *)sp, slp = *(uint2 *)(sp + TV), sbp = *(uint2 *)(sp + 2 * TV), sen = *(uint2 *)(sp + 3 * TV), stt = *(uint2 *)(sp + 4 * TV);
+                uint2 ph = nst[0], slp = nst[1], sbp = nst[2], sen = nst[3], stt = nst[4];
+                uint32_t *sp = xm2_tile + (size_t)(tid + XM2_BLOCK * j) * 10;
+                // the next pair: j + 1, or this thread's first pair in the next chunk (its state was stored earlier in this chunk, by this
+                // thread: program order) -- unless that is this very pair (ng == 1: its state stays in registers, below)
+                if (j + 1 < ng) { load_prm(j + 1, nq); load_st(j + 1, nst); }
+                else if (c + 1 < n_chunks) { load_prm(0, nq); if (ng > 1) load_st(0, nst); }
                 const uint32_t mA = xv_amask(stt.x, q[5].x), mB = xv_amask(stt.y, q[5].y);
                 // The clamped envelope e' = min(max(e + d, +0), 1), d = +attack or -release, is the two-branch envelope of the oracle
                 // whenever the rates have a clear sign bit and +0 <= env <= 1 (bit patterns below; excludes NaN and -0.0): the clamp
@@ -522,42 +537,46 @@ __global__ void __launch_bounds__(XM2_BLOCK, XM2_MINB) k_xvoice_mix2(const XVoic
                     }
                 }
                 stt.x += cols; stt.y += cols;
-                *(uint2 *)sp = ph; *(uint2 *)(sp + TV) = slp; *(uint2 *)(sp + 2 * TV) = sbp; *(uint2 *)(sp + 3 * TV) = sen; *(uint2 *)(sp + 4 * TV) = stt;
+                *(uint2 *)sp = ph; *(uint2 *)(sp + 2) = slp; *(uint2 *)(sp + 4) = sbp; *(uint2 *)(sp + 6) = sen; *(uint2 *)(sp + 8) = stt;
+                if (ng == 1) { nst[0] = ph; nst[1] = slp; nst[2] = sbp; nst[3] = sen; nst[4] = stt; }
             }
-            // ---- block reduction of the chunk: left, then right; 4 threads per column (32 rows each, 4 chains), combined in a fixed order
+            // ---- reduction of the chunk, PER WARP and without a block barrier: a butterfly over the lanes that transposes while it adds
+            // (stage `st`: a lane keeps the half of its values whose index has bit `st` equal to its own lane bit and receives the partner's
+            // copy of that half) leaves lane l with frame l's sum over the warp's 32 lanes -- a fixed order, deterministic.  62 shuffles for
+            // the 2 x 32 accumulators, no shared memory; the warps of a block drift apart freely between tile boundaries.  (A column
+            // buffer in shared memory with four __syncthreads per chunk was 17 % of the kernel's stall samples for 4 % of its instructions.)
+            {
+                const uint32_t lane = tid & 31u, warp = tid >> 5;
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
+                for (int st = 16; st >= 1; st >>= 1) {
+                    const bool up = (lane & st) != 0;
 #pragma unroll
-                for (int k = 0; k < XM_CHUNK; ++k) red[k * 161 + (tid >> 5) * 40 + (tid & 31)] = ch ? aR[k] : aL[k];
-                __syncthreads();
-                const uint32_t col = tid >> 2, qd = tid & 3u;
-                const float *row = &red[col * 161 + qd * 40];
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-                for (int r = 0; r < XM2_BLOCK / 4; r += 4) {
-                    s0 = __fadd_rn(s0, row[r]); s1 = __fadd_rn(s1, row[r + 1]); s2 = __fadd_rn(s2, row[r + 2]); s3 = __fadd_rn(s3, row[r + 3]);
+                    for (int q = 0; q < st; ++q) {
+                        const float sendL = up ? aL[q] : aL[q + st], keepL = up ? aL[q + st] : aL[q];
+                        const float sendR = up ? aR[q] : aR[q + st], keepR = up ? aR[q + st] : aR[q];
+                        aL[q] = __fadd_rn(keepL, __shfl_xor_sync(0xFFFFFFFFu, sendL, st));
+                        aR[q] = __fadd_rn(keepR, __shfl_xor_sync(0xFFFFFFFFu, sendR, st));
+                    }
                 }
-                float sm = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
-                sm = __fadd_rn(sm, __shfl_xor_sync(0xFFFFFFFFu, sm, 1));         // (q0 + q1), (q2 + q3): the same bits on both lanes of a pair
-                sm = __fadd_rn(sm, __shfl_xor_sync(0xFFFFFFFFu, sm, 2));         // (q0 + q1) + (q2 + q3)
-                if (qd == 0 && col < cols) {
-                    float *dst = p.partial + ((uint64_t)blockIdx.x * 2 + ch) * p.F + t0 + col;
-                    *dst = ti ? __fadd_rn(*dst, sm) : sm;                        // tiles accumulate in tile order
+                if (lane < cols) {
+                    float *dst = p.partial + ((uint64_t)(blockIdx.x * (XM2_BLOCK / 32) + warp) * 2) * p.F + t0 + lane;
+                    dst[0] = ti ? __fadd_rn(dst[0], aL[0]) : aL[0];           // tiles accumulate in tile order
+                    dst[p.F] = ti ? __fadd_rn(dst[p.F], aR[0]) : aR[0];
                 }
-                __syncthreads();
             }
         }
         // ---- tile state out
-        for (uint32_t w = 0; w < 5; ++w)
-            for (uint32_t j = 0; j < ng; ++j) {
-                const uint32_t idx = 2 * (tid + XM2_BLOCK * j);
-                const uint64_t gi = v0 + idx;
-                const uint2 val = *(const uint2 *)(xm2_tile + w * TV + idx);
+        for (uint32_t j = 0; j < ng; ++j) {
+            const uint64_t gi = v0 + 2 * (tid + XM2_BLOCK * j);
+            const uint32_t *sp = xm2_tile + (size_t)(tid + XM2_BLOCK * j) * 10;
+#pragma unroll
+            for (uint32_t w = 0; w < 5; ++w) {
+                const uint2 val = *(const uint2 *)(sp + 2 * w);
                 uint32_t *dst = p.st + (uint64_t)w * p.npad + gi;
                 if (gi + 1 < p.n) __stcs((uint2 *)dst, val);
                 else if (gi < p.n) dst[0] = val.x;
             }
-        __syncthreads();
+        }
     }
     xm_finish(p, bf, n_chunks, tick_s);
 }
@@ -1097,8 +1116,9 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     p.st = b->d_state; p.prm = b->d_param; p.npad = b->npad; p.n = b->n; p.F = F;
     p.raw = (float *)io->out; p.layout = io->layout; p.partial = nullptr;
     p.mix = (float *)io->mix; p.done = nullptr; p.n_render_blocks = (uint32_t)n_blocks;
+    p.rows_per_block = mix2 ? XM2_BLOCK / 32 : 1;
     if (io->mix) {
-        size_t need = sizeof(float) * n_blocks * 2 * F;
+        size_t need = sizeof(float) * n_blocks * p.rows_per_block * 2 * F;
         if (b->cap_mix < need) {
             if (b->d_mix) cudaFree(b->d_mix);
             b->d_mix = nullptr; b->cap_mix = 0;
