@@ -369,6 +369,11 @@ __device__ __forceinline__ xv2_t xv2_add(xv2_t a, xv2_t b) { xv2_t r; asm("add.r
 __device__ __forceinline__ xv2_t xv2_mul(xv2_t a, xv2_t b) { xv2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ xv2_t xv2_neg(xv2_t a) { return a ^ 0x8000000080000000ull; }
 
+// explicit shared-space accesses on a 32-bit address (a generic pointer into the dynamic shared array made ptxas rebuild the shared
+// window base -- S2R SR_CgaCtaId, UMOV, ULEA -- in front of every pair)
+__device__ __forceinline__ uint2 xv_lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void xv_sts64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+
 // attack mask of one voice for a chunk (bit k: tick k is in the attack phase) and whether the chunk is uniform
 __device__ __forceinline__ uint32_t xv_amask(uint32_t t, uint32_t gate) {
     if (t <= 0xFFFFFFFFu - XM_CHUNK) {
@@ -400,11 +405,11 @@ __global__ void __launch_bounds__(XM2_BLOCK, XM2_MINB) k_xvoice_mix2(const XVoic
         // pair-major, 5 x uint2 (40 bytes) per pair: the five accesses of a pair are one base + immediate offsets (no dependent address
         // chain in front of the tick loop), 64-bit accesses at a 40-byte lane stride are conflict free per half-warp, and no barrier is
         // needed between the tile phases.
+        const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(xm2_tile) + tid * 40u;     // this thread's pair 0; pair j: + j * 128 * 40
         for (uint32_t j = 0; j < ng; ++j) {
             const uint64_t gi = v0 + 2 * (tid + XM2_BLOCK * j);
-            uint32_t *sp = xm2_tile + (size_t)(tid + XM2_BLOCK * j) * 10;
 #pragma unroll
-            for (uint32_t w = 0; w < 5; ++w) *(uint2 *)(sp + 2 * w) = __ldcs((const uint2 *)(p.st + (uint64_t)w * p.npad + gi));     // npad % 256 == 0: whole groups; [n, npad) is zero
+            for (uint32_t w = 0; w < 5; ++w) xv_sts64(tile_s + j * (XM2_BLOCK * 40u) + 8 * w, __ldcs((const uint2 *)(p.st + (uint64_t)w * p.npad + gi)));     // npad % 256 == 0: whole groups; [n, npad) is zero
         }
         // (npad is a multiple of 256 for this processor and the rows are zero past n: whole groups, no bounds checks; one 64-bit base per
         // tile and a row pitch in uint2 units keep the address arithmetic of the 8 loads to a handful of instructions -- written as
@@ -420,9 +425,9 @@ __global__ void __launch_bounds__(XM2_BLOCK, XM2_MINB) k_xvoice_mix2(const XVoic
         // attack masks and the path decision of pair j+1 do not sit between two tick loops (profiles/r2_xvoice_mix2_summary.txt: the
         // ~150 instructions around a 32-tick loop took 35 % of the kernel's samples at 2.5 warps per scheduler)
         auto load_st = [&](uint32_t j, uint2 (&st)[5]) {
-            const uint32_t *sp = xm2_tile + (size_t)(tid + XM2_BLOCK * j) * 10;
+            const uint32_t sa = tile_s + j * (XM2_BLOCK * 40u);
 #pragma unroll
-            for (int w = 0; w < 5; ++w) st[w] = *(const uint2 *)(sp + 2 * w);
+            for (int w = 0; w < 5; ++w) st[w] = xv_lds64(sa + 8 * w);
         };
         uint2 nq[8], nst[5];
         load_prm(0, nq);
@@ -439,7 +444,7 @@ __global__ void __launch_bounds__(XM2_BLOCK, XM2_MINB) k_xvoice_mix2(const XVoic
 #pragma unroll
                 for (int w = 0; w < 8; ++w) q[w] = nq[w];
                 uint2 ph = nst[0], slp = nst[1], sbp = nst[2], sen = nst[3], stt = nst[4];
-                uint32_t *sp = xm2_tile + (size_t)(tid + XM2_BLOCK * j) * 10;
+                const uint32_t sp = tile_s + j * (XM2_BLOCK * 40u);
                 // the next pair: j + 1, or this thread's first pair in the next chunk (its state was stored earlier in this chunk, by this
                 // thread: program order) -- unless that is this very pair (ng == 1: its state stays in registers, below)
                 if (j + 1 < ng) { load_prm(j + 1, nq); load_st(j + 1, nst); }
@@ -537,7 +542,7 @@ __global__ void __launch_bounds__(XM2_BLOCK, XM2_MINB) k_xvoice_mix2(const XVoic
                     }
                 }
                 stt.x += cols; stt.y += cols;
-                *(uint2 *)sp = ph; *(uint2 *)(sp + 2) = slp; *(uint2 *)(sp + 4) = sbp; *(uint2 *)(sp + 6) = sen; *(uint2 *)(sp + 8) = stt;
+                xv_sts64(sp, ph); xv_sts64(sp + 8, slp); xv_sts64(sp + 16, sbp); xv_sts64(sp + 24, sen); xv_sts64(sp + 32, stt);
                 if (ng == 1) { nst[0] = ph; nst[1] = slp; nst[2] = sbp; nst[3] = sen; nst[4] = stt; }
             }
             // ---- reduction of the chunk, PER WARP and without a block barrier: a butterfly over the lanes that transposes while it adds
@@ -568,10 +573,9 @@ __global__ void __launch_bounds__(XM2_BLOCK, XM2_MINB) k_xvoice_mix2(const XVoic
         // ---- tile state out
         for (uint32_t j = 0; j < ng; ++j) {
             const uint64_t gi = v0 + 2 * (tid + XM2_BLOCK * j);
-            const uint32_t *sp = xm2_tile + (size_t)(tid + XM2_BLOCK * j) * 10;
 #pragma unroll
             for (uint32_t w = 0; w < 5; ++w) {
-                const uint2 val = *(const uint2 *)(sp + 2 * w);
+                const uint2 val = xv_lds64(tile_s + j * (XM2_BLOCK * 40u) + 8 * w);
                 uint32_t *dst = p.st + (uint64_t)w * p.npad + gi;
                 if (gi + 1 < p.n) __stcs((uint2 *)dst, val);
                 else if (gi < p.n) dst[0] = val.x;
