@@ -26,7 +26,8 @@ struct XVoiceParams {
     uint32_t *done;          // k_xvoice_mix: [2] blocks that left / finalisers done (zero between launches)
     uint32_t n_render_blocks;// k_xvoice_mix: gridDim.x without the finisher block of a pipelined bus
     uint32_t vpt;            // k_xvoice_mix: voices per thread per L2 tile
-    uint32_t rows_per_block; // partial rows a block writes per channel pair: 1 (k_xvoice_mix), 4 = one per warp (k_xvoice_mix2)
+    uint32_t rows_per_block; // partial rows a block leaves per channel pair for the final reduction (1)
+    float *partial_w;        // k_xvoice_mix2: [n_blocks][4 warps][2][F] per-warp rows, summed into the block's row of `partial` when the block is done
 };
 
 struct XV {
@@ -394,8 +395,8 @@ __global__ void __launch_bounds__(XM2_BLOCK, XM2_MINB) k_xvoice_mix2(const XVoic
     const uint64_t G = (p.n + 255) / 256;
     const uint64_t g_lo = G * blockIdx.x / nb, g_hi = G * (blockIdx.x + 1) / nb;
     const uint32_t kg = (uint32_t)(g_hi - g_lo), nt = (kg + XM2_GMAX - 1) / XM2_GMAX;
-    if (kg == 0)                                                    // more blocks than groups: all-zero partial rows
-        for (uint64_t idx = tid; idx < 2 * p.F * (XM2_BLOCK / 32); idx += XM2_BLOCK) p.partial[(uint64_t)blockIdx.x * (XM2_BLOCK / 32) * 2 * p.F + idx] = 0.0f;
+    if (kg == 0)                                                    // more blocks than groups: an all-zero partial row
+        for (uint64_t idx = tid; idx < 2 * p.F; idx += XM2_BLOCK) p.partial[(uint64_t)blockIdx.x * 2 * p.F + idx] = 0.0f;
     const xv2_t c31 = xv2_pack(0x1p-31f, 0x1p-31f);
     for (uint32_t ti = 0; ti < nt; ++ti) {
         const uint64_t ga = g_lo + (uint64_t)kg * ti / nt, gb = g_lo + (uint64_t)kg * (ti + 1) / nt;
@@ -564,7 +565,7 @@ __global__ void __launch_bounds__(XM2_BLOCK, XM2_MINB) k_xvoice_mix2(const XVoic
                     }
                 }
                 if (lane < cols) {
-                    float *dst = p.partial + ((uint64_t)(blockIdx.x * (XM2_BLOCK / 32) + warp) * 2) * p.F + t0 + lane;
+                    float *dst = p.partial_w + ((uint64_t)(blockIdx.x * (XM2_BLOCK / 32) + warp) * 2) * p.F + t0 + lane;
                     dst[0] = ti ? __fadd_rn(dst[0], aL[0]) : aL[0];           // tiles accumulate in tile order
                     dst[p.F] = ti ? __fadd_rn(dst[p.F], aR[0]) : aR[0];
                 }
@@ -580,6 +581,18 @@ __global__ void __launch_bounds__(XM2_BLOCK, XM2_MINB) k_xvoice_mix2(const XVoic
                 if (gi + 1 < p.n) __stcs((uint2 *)dst, val);
                 else if (gi < p.n) dst[0] = val.x;
             }
+        }
+    }
+    // the block's four warp rows -> its one row for the launch's final reduction (which would otherwise walk four times as many rows
+    // at the tail of the launch, with the whole chip waiting: +30 us on a 190 us shard of an 8-GPU render), warps in a fixed order
+    if (kg) {
+        __syncthreads();
+        const float *w0 = p.partial_w + (uint64_t)blockIdx.x * (XM2_BLOCK / 32) * 2 * p.F;
+        for (uint64_t idx = tid; idx < 2 * p.F; idx += XM2_BLOCK) {
+            float sm = __ldcg(w0 + idx);
+#pragma unroll
+            for (int r = 1; r < XM2_BLOCK / 32; ++r) sm = __fadd_rn(sm, __ldcg(w0 + (uint64_t)r * 2 * p.F + idx));
+            p.partial[(uint64_t)blockIdx.x * 2 * p.F + idx] = sm;
         }
     }
     xm_finish(p, bf, n_chunks, tick_s);
@@ -1120,9 +1133,9 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     p.st = b->d_state; p.prm = b->d_param; p.npad = b->npad; p.n = b->n; p.F = F;
     p.raw = (float *)io->out; p.layout = io->layout; p.partial = nullptr;
     p.mix = (float *)io->mix; p.done = nullptr; p.n_render_blocks = (uint32_t)n_blocks;
-    p.rows_per_block = mix2 ? XM2_BLOCK / 32 : 1;
+    p.rows_per_block = 1; p.partial_w = nullptr;
     if (io->mix) {
-        size_t need = sizeof(float) * n_blocks * p.rows_per_block * 2 * F;
+        size_t need = sizeof(float) * n_blocks * (mix2 ? 1 + XM2_BLOCK / 32 : 1) * 2 * F;
         if (b->cap_mix < need) {
             if (b->d_mix) cudaFree(b->d_mix);
             b->d_mix = nullptr; b->cap_mix = 0;
@@ -1130,6 +1143,7 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
             b->cap_mix = need;
         }
         p.partial = (float *)b->d_mix;
+        if (mix2) p.partial_w = p.partial + n_blocks * 2 * F;
     }
     if (mix_only) {
         if (!b->d_acc) {
