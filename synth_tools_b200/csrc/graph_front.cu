@@ -514,7 +514,7 @@ extern "C" __global__ void __launch_bounds__(WARPS * 32) graph_planar(const Grap
         }
     };
 #pragma unroll 1
-    for (uint32_t k = 0; k < STAGES - 2 && k < n_tiles; ++k) issue(k);
+    for (uint32_t k = 0; k + 2 < STAGES && k < n_tiles; ++k) issue(k);
 #pragma unroll 1
     for (uint32_t k = 0; k < n_tiles; ++k) {
         if (k + STAGES - 2 < n_tiles) {                   // that stage last held tile k-2: its bulk store must have read it out
@@ -582,12 +582,14 @@ extern "C" __global__ void __launch_bounds__(WARPS * 32) graph_planar_tma(const 
     GParam P = {};
     if (mine) { GRAPH_LOAD_STATE(p.st, p.npad, i) GRAPH_LOAD_PARAM(p.prm, p.npad, i) }
     const uint32_t n_tiles = (uint32_t)((p.F + TF - 1) / TF);
-    const unsigned long long tmi = (unsigned long long)&tm_in, tmc = (unsigned long long)&tm_chg, tmo = (unsigned long long)&tm_out;
+    const unsigned long long tmo = (unsigned long long)&tm_out;
 #if GRAPH_ST_HINT
     unsigned long long st_policy;                                     // write-once output: evict-first in L2
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(st_policy));
 #endif
     auto cols_of = [&](uint32_t k) { const uint64_t left = p.F - (uint64_t)k * TF; return left < TF ? (uint32_t)left : (uint32_t)TF; };
+#if ROWS_IN != 0
+    const unsigned long long tmi = (unsigned long long)&tm_in, tmc = (unsigned long long)&tm_chg;
     auto issue = [&](uint32_t k) {                                    // lane 0 only
         const uint32_t s = k % STAGES, nbox = (cols_of(k) + 31) / 32;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * s), "r"(ROWS_IN * nbox * TT_BOXB) : "memory");
@@ -598,16 +600,25 @@ extern "C" __global__ void __launch_bounds__(WARPS * 32) graph_planar_tma(const 
                              ::"r"(base + s * TT_STAGEB + j * TT_STREAMB + h * TT_BOXB), "l"(j < GRAPH_NIN ? tmi : tmc), "r"((int)(k * TF + h * 32)),
                                "r"(j < GRAPH_NIN ? j : 0), "r"((int)g0), "r"(bar0 + 8 * s) : "memory");
     };
-    if (lane == 0) for (uint32_t k = 0; k < STAGES - 2 && k < n_tiles; ++k) issue(k);
+    if (lane == 0) for (uint32_t k = 0; k + 2 < STAGES && k < n_tiles; ++k) issue(k);
+#endif
 #pragma unroll 1
     for (uint32_t k = 0; k < n_tiles; ++k) {
+        const uint32_t s = k % STAGES, cols = cols_of(k);
+#if ROWS_IN == 0
+        // a graph without input streams only stores: every stage is a store buffer, tile k needs the store of tile k-STAGES read out
+        if (k >= STAGES) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(STAGES - 1) : "memory");
+            __syncwarp();
+        }
+#else
         if (k + STAGES - 2 < n_tiles && lane == 0) {                  // that stage last held tile k-2: its stores must have read it out
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             issue(k + STAGES - 2);
         }
-        const uint32_t s = k % STAGES, cols = cols_of(k);
         asm volatile("{\n\t.reg .pred q;\n\tW: mbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n\t@q bra D;\n\tbra W;\n\tD:\n\t}"
                      ::"r"(bar0 + 8 * s), "r"((k / STAGES) & 1) : "memory");
+#endif
         const uint32_t row = base + s * TT_STAGEB + lane * 128;       // stream j, chunk c: row + j * TT_STREAMB + (c >> 3) * TT_BOXB + (((c & 7) ^ (lane & 7)) << 4)
         if (mine) {
             for (uint32_t c = 0; c < cols / 4; ++c) {
@@ -783,14 +794,15 @@ std::string cproc_graph_jit_source(const std::vector<cproc_cuda_node> &nodes, ui
     for (size_t q = 0; q < outs.size(); ++q) { snprintf(buf, sizeof(buf), " (o)[%zu] = s%u;", q, off[outs[q]]); outm += buf; }
     // Block shape of the PLANAR staging kernels.  A tick of a float voice is ~20 dependent instructions and its graph has no input
     // stream: measured on the C4 voice graph (tools/sweep_graph_tiles.sh, profiles/r2_sweep_graph_tiles.txt) one warp per block with
-    // 64-frame tiles is the best shape (5.43 TB/s; two warps 5.08, 32-frame tiles 5.03-5.09, 128-frame tiles leave two warps per SM).
+    // 64-frame tiles and three stages is the best shape (5.74 TB/s with every stage a store buffer -- a store-only graph waits for the
+    // store of tile k-3, not k-2; two stages x two warps 5.68, 32-frame tiles 4.9-5.4, profiles/r2_sweep_graph_tiles.txt).
     static const uint8_t k_cost[CPROC_CUDA_NODE_KINDS] = {1, 2, 6, 7, 3, 5, 6, 2, 1, 0, 4, 1};
     uint32_t cost = 0;
     for (const cproc_cuda_node &nd : nodes) cost += k_cost[CPROC_CUDA_NODE_KIND(nd.type)];
     int tf = 64, stages = 3, warps = cost >= 12 ? 1 : 2;
     // experiments: CPROC_GRAPH_TF / _STAGES / _WARPS override the tile shape of the generated PLANAR kernels
     if (const char *e = getenv("CPROC_GRAPH_TF")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128) tf = v; }
-    if (const char *e = getenv("CPROC_GRAPH_STAGES")) { const int v = atoi(e); if (v >= 3 && v <= 6) stages = v; }
+    if (const char *e = getenv("CPROC_GRAPH_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 6) stages = v; }
     if (const char *e = getenv("CPROC_GRAPH_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= 8) warps = v; }
     int hint = 0;
     if (const char *e = getenv("CPROC_GRAPH_ST_HINT")) hint = atoi(e) != 0;
