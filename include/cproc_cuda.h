@@ -313,6 +313,12 @@ int  cproc_cuda_download_bank(cproc_cuda_batch *b, uint32_t *prng, uint32_t *cou
  * _run_dev: device buffers, asynchronous on the context stream. */
 int  cproc_cuda_run(cproc_cuda_batch *b, uint64_t n_frames, const cproc_cuda_io *io);
 int  cproc_cuda_run_dev(cproc_cuda_batch *b, uint64_t n_frames, const cproc_cuda_io *io);
+/* One period of a real-time host that keeps the state in ITS structs -- synth_run(struct synth *x, ...) renders from
+ * x->voice[] and leaves the phases there (linux/synth.c:196-202), note_on / note_off write the same structs between
+ * periods (:143-165).  Equivalent to upload_state(state_aos, stride); run(n_frames, io); download_state(state_aos,
+ * stride), but as one stream sequence with ONE synchronisation and, after the first call with a batch, no allocation
+ * (pinned record staging owned by the batch): call it once before the real-time thread starts. */
+int  cproc_cuda_run_period(cproc_cuda_batch *b, uint64_t n_frames, const cproc_cuda_io *io, void *state_aos, size_t stride);
 /* Long renders into host memory: F_total frames in chunks of F_chunk, the
  * device->host copy of chunk k overlapped with the render of chunk k+1.
  * io->out is a PINNED host buffer (cproc_cuda_host_alloc) of `ring_chunks`

@@ -97,6 +97,7 @@ SYMBOLS = {
     "cproc_cuda_download_bank": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
     "cproc_cuda_run": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(IO)]),
     "cproc_cuda_run_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(IO)]),
+    "cproc_cuda_run_period": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(IO), C.c_void_p, C.c_size_t]),
     "cproc_cuda_run_stream": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(IO), C.c_uint32, CHUNK_FN, C.c_void_p]),
     "cproc_cuda_mix_to_float": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "cproc_cuda_dev_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -402,6 +403,12 @@ class Batch:
         """Host buffers (numpy), synchronous."""
         io = self._io(inp, in2, ctl, out, mix, layout, n_ctl)
         self.ctx._ck(lib.cproc_cuda_run(self.h, F, C.byref(io)))
+
+    def run_period(self, F, state, stride=0, inp=None, in2=None, ctl=None, out=None, mix=None, layout=None, n_ctl=None):
+        """One real-time period with the state in the host's records: records in, render, records out, one synchronisation
+        (`state` is updated in place)."""
+        io = self._io(inp, in2, ctl, out, mix, layout, n_ctl)
+        self.ctx._ck(lib.cproc_cuda_run_period(self.h, F, C.byref(io), _vp(state), stride))
 
     def run_dev(self, F, inp=None, in2=None, ctl=None, out=None, mix=None, layout=None, n_ctl=0):
         """Device pointers (ints), asynchronous on the context stream."""

@@ -244,6 +244,7 @@ int cproc_cuda_free(cproc_cuda_batch *b) {
     for (cproc_graph_jit &j : b->jit) if (j.lib) cudaLibraryUnload(j.lib);
     if (b->rg.exec) cudaGraphExecDestroy(b->rg.exec);
     if (b->rg.h) cudaFreeHost(b->rg.h);
+    if (b->st_h) cudaFreeHost(b->st_h);
     delete b;
     return 0;
 }
@@ -449,6 +450,7 @@ int cproc_cuda_run(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
         if (want[3]) d.out = g.h + off[3];
         if (want[4]) d.mix = g.h + off[4];
         if ((rc = dispatch(b, F, &d))) return rc;
+        if (b->ride_state) CK(ctx, cudaMemcpyAsync(b->st_h, b->d_state, sizeof(uint32_t) * b->state_words * b->npad, cudaMemcpyDeviceToHost, st));
         CK(ctx, cudaStreamSynchronize(st));
         if (want[3]) memcpy(io->out, g.h + off[3], want[3]);
         if (want[4]) memcpy(io->mix, g.h + off[4], want[4]);
@@ -505,6 +507,7 @@ int cproc_cuda_run(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
             for (int k = 0; k < 3; ++k) if (want[k]) memcpy(g.h + off[k], src[k], want[k]);
             CK(ctx, cudaGraphLaunch(g.exec, st));
             ctx->launches += g.kernels;
+            if (b->ride_state) CK(ctx, cudaMemcpyAsync(b->st_h, b->d_state, sizeof(uint32_t) * b->state_words * b->npad, cudaMemcpyDeviceToHost, st));
             CK(ctx, cudaStreamSynchronize(st));
             if (want[3]) memcpy(io->out, g.h + off[3], want[3]);
             if (want[4]) memcpy(io->mix, g.h + off[4], want[4]);
@@ -541,7 +544,39 @@ int cproc_cuda_run(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     if ((rc = dispatch(b, F, &d))) return rc;
     if (io->out && sz.out) CK(ctx, cudaMemcpyAsync(io->out, d.out, sz.out, cudaMemcpyDeviceToHost, st));
     if (io->mix && sz.mix) CK(ctx, cudaMemcpyAsync(io->mix, d_mix_user, sz.mix, cudaMemcpyDeviceToHost, st));
+    if (b->ride_state) CK(ctx, cudaMemcpyAsync(b->st_h, b->d_state, sizeof(uint32_t) * b->state_words * b->npad, cudaMemcpyDeviceToHost, st));
     CK(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+// One period of a real-time host whose state lives in the HOST's structs (synth.c: struct voice inside struct synth, note_on /
+// note_off write it between periods): records in, render, records out -- as ONE stream sequence with one synchronisation.
+// The records travel through a pinned SoA staging buffer owned by the batch (allocated by the first call: warm up before the
+// real-time thread exists); nothing is allocated afterwards and the only blocking driver call is the period's own sync.
+int cproc_cuda_run_period(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io, void *state_aos, size_t stride) {
+    if (!b || !io) return cproc_set_err(b ? b->ctx : nullptr, CPROC_CUDA_EINVAL, "run_period: NULL argument");
+    cproc_cuda_ctx *ctx = b->ctx;
+    if (!state_aos) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "run_period: state is NULL");
+    const uint32_t words = b->state_words;
+    if (stride == 0) stride = 4u * words;
+    if (words == 0 || stride < 4u * words) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "run_period: stride %zu smaller than the state record (%u bytes)", stride, 4u * words);
+    if (F == 0) return 0;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = sizeof(uint32_t) * words * b->npad;
+    if (!b->st_h) {
+        CK(ctx, cudaHostAlloc((void **)&b->st_h, bytes, cudaHostAllocDefault));
+        memset(b->st_h, 0, bytes);
+    }
+    uint8_t *rec = (uint8_t *)state_aos;
+    for (uint64_t i = 0; i < b->n; ++i)
+        for (uint32_t w = 0; w < words; ++w) memcpy(b->st_h + (size_t)w * b->npad + i, rec + i * stride + 4u * w, 4);
+    CK(ctx, cudaMemcpyAsync(b->d_state, b->st_h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    b->ride_state = true;
+    const int rc = cproc_cuda_run(b, F, io);               // ends with the records' D2H copy and the period's one sync
+    b->ride_state = false;
+    if (rc) return rc;
+    for (uint64_t i = 0; i < b->n; ++i)
+        for (uint32_t w = 0; w < words; ++w) memcpy(rec + i * stride + 4u * w, b->st_h + (size_t)w * b->npad + i, 4);
     return 0;
 }
 

@@ -105,6 +105,8 @@ struct cproc_cuda_batch {
         cudaGraphExec_t exec = nullptr; uint32_t kernels = 0;
         uint8_t *h = nullptr; size_t cap = 0;      // pinned staging, the five regions back to back
     } rg;
+    // cproc_cuda_run_period: the state records ride along with the period (pinned SoA staging, no call of its own)
+    uint32_t *st_h = nullptr; bool ride_state = false;
 };
 
 int cproc_set_err(cproc_cuda_ctx *ctx, int code, const char *fmt, ...);

@@ -80,9 +80,8 @@ static void process_audio(jack_nframes_t nframes) {
     cproc_cuda_io io;
     memset(&io, 0, sizeof(io));
     io.out = mixbuf; io.layout = CPROC_CUDA_PLANAR;                       /* float [part][nframes] */
-    int rc = cproc_cuda_upload_state(bank, flat, sizeof(struct voice));
-    if (!rc) rc = cproc_cuda_run(bank, nframes, &io);
-    if (!rc) rc = cproc_cuda_download_state(bank, flat, sizeof(struct voice));
+    /* voice records in, render, records out: one stream sequence, one synchronisation, no allocation (cproc_cuda_run_period) */
+    int rc = cproc_cuda_run_period(bank, nframes, &io, flat, sizeof(struct voice));
     if (rc) { failed = rc; fprintf(stderr, "jack_synth_b200: render failed (%d): %s\n", rc, cproc_cuda_last_error(ctx)); return; }
     for (int k = 0; k < N_PARTS; k++) {
         memcpy(parts[k].voice, flat + k * N_VOICES, sizeof(parts[k].voice));
@@ -116,7 +115,7 @@ int main(void) {
         snprintf(name, sizeof(name), "part_%02d", k);
         audio_out[k] = jack_port_register(client, name, JACK_DEFAULT_AUDIO_TYPE, JackPortIsOutput, 0);
     }
-    /* Warm the period path before the RT callback exists: the first call with a shape allocates the staging buffers, the second
+    /* Warm the period path before the RT callback exists: the first call with a shape allocates the staging buffers (the pinned record staging included), the second
        captures the period's CUDA graph (cproc_cuda_run, run_graph), and neither belongs on the JACK thread.  The voice table is
        silent (note_inc == 0 everywhere), so the warm-up leaves every phase where it was. */
     {
@@ -126,9 +125,7 @@ int main(void) {
         io.out = mixbuf; io.layout = CPROC_CUDA_PLANAR;
         memset(flat, 0, sizeof(flat));
         for (int k = 0; k < 3 && period && period <= max_frames; k++) {
-            int rc = cproc_cuda_upload_state(bank, flat, sizeof(struct voice));
-            if (!rc) rc = cproc_cuda_run(bank, period, &io);
-            if (!rc) rc = cproc_cuda_download_state(bank, flat, sizeof(struct voice));
+            int rc = cproc_cuda_run_period(bank, period, &io, flat, sizeof(struct voice));
             if (rc) { fprintf(stderr, "jack_synth_b200: warm-up failed (%d): %s\n", rc, cproc_cuda_last_error(ctx)); return 1; }
         }
     }

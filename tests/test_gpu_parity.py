@@ -772,6 +772,52 @@ def test_voice_bank_synth_anchor(st, ctx):
     b.free()
 
 
+@pytest.mark.parametrize("run_graph", [0, 1, 2, 3])
+def test_run_period_state_rides_along(st, ctx, oracle, run_graph):
+    """cproc_cuda_run_period == upload_state; run; download_state (the JACK / synth_run period: the host's structs hold the
+    state, note_on / note_off write them between periods) on every period path of cproc_cuda_run -- staged copies, the
+    captured CUDA graph, zero copy, direct launches on pinned staging -- and with a record stride (struct voice in a larger struct)."""
+    ctx.set_option("run_graph", run_graph)
+    try:
+        V, F = 128, 64
+        rec = np.zeros((V, 4), np.uint32)                          # stride 16: {inc, phase, unrelated, unrelated}
+        rec[::3, 0] = [oracle.note_to_inc(int(n)) for n in rng.integers(30, 90, len(rec[::3]))]
+        rec[:, 2:] = rng.integers(0, 2**32, (V, 2), dtype=np.uint32)
+        tail = rec[:, 2:].copy()
+        vb = ctx.batch(st.VOICE_BANK, V, voices_per_bus=64)
+        syncs = []
+        for k in range(6):
+            if k == 3:
+                rec[1, 0] = oracle.note_to_inc(69)                 # note on between periods
+            voices = np.ascontiguousarray(rec[:, :2])
+            _, want = oracle.voice_bank_run(voices, V, 64, po.MIX_SAW, F)   # advances `voices`
+            out = np.zeros((2, F), np.float32)
+            vb.run_period(F, rec, stride=16, out=out)
+            assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), k
+            assert np.array_equal(rec[:, :2], voices) and np.array_equal(rec[:, 2:], tail), k
+        assert np.array_equal(vb.download_state(), rec[:, :2])
+        vb.free()
+        # a graph batch (edge -> acc of test_cproc.c) with input stream and packed records
+        N = 3
+        stt = np.zeros((N, 3), np.uint32); sa = stt.copy()
+        b = ctx.batch(st.GRAPH, N, nodes=po.GRAPH_TEST_CPROC, n_inputs=1)
+        for k in range(4):
+            x = rng.integers(0, 2, (N, 1, F), dtype=np.uint32)
+            want = oracle.graph_run(po.GRAPH_TEST_CPROC, 1, 1, sa, N, F, x)
+            out = np.zeros((N, F), np.uint32)
+            b.run_period(F, stt, inp=x, out=out)
+            assert np.array_equal(out, want) and np.array_equal(stt, sa), k
+        b.free()
+        with pytest.raises(st.CprocCudaError):
+            vb2 = ctx.batch(st.VOICE_BANK, 8, voices_per_bus=8)
+            try:
+                vb2.run_period(8, np.zeros((8, 1), np.uint32), stride=4, out=np.zeros((1, 8), np.float32))   # stride smaller than the record
+            finally:
+                vb2.free()
+    finally:
+        ctx.set_option("run_graph", 2)
+
+
 # -------------------------------------------------------------------- square_grain
 def _square_grain_case(st, ctx, oracle, N, F, layout, neg_th=False, odd_state=False):
     inp = rng.uniform(-1, 1, (N, F)).astype(np.float32)
