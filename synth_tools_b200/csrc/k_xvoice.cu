@@ -393,7 +393,11 @@ __global__ void __launch_bounds__(XM2_BLOCK, XM2_MINB) k_xvoice_mix2(const XVoic
     const uint32_t nb = p.n_render_blocks, tid = threadIdx.x;
     const uint32_t n_chunks = (uint32_t)((p.F + XM_CHUNK - 1) / XM_CHUNK);
     const uint64_t G = (p.n + 255) / 256;
-    const uint64_t g_lo = G * blockIdx.x / nb, g_hi = G * (blockIdx.x + 1) / nb;
+    // Blocks with one group more than the others are the LOWEST block indices: the hardware deals blocks to the SMs breadth first, so the
+    // uneven last round (a 512 Ki-voice shard: 276 of 443 blocks have a fifth group) is spread two blocks per SM over the SMs instead of
+    // three on some and none on others -- that round is latency bound and runs faster with fewer warps per SM.
+    const uint64_t g_each = G / nb, g_more = G % nb;
+    const uint64_t g_lo = g_each * blockIdx.x + (blockIdx.x < g_more ? blockIdx.x : g_more), g_hi = g_lo + g_each + (blockIdx.x < g_more ? 1 : 0);
     const uint32_t kg = (uint32_t)(g_hi - g_lo), nt = (kg + XM2_GMAX - 1) / XM2_GMAX;
     if (kg == 0)                                                    // more blocks than groups: an all-zero partial row
         for (uint64_t idx = tid; idx < 2 * p.F; idx += XM2_BLOCK) p.partial[(uint64_t)blockIdx.x * 2 * p.F + idx] = 0.0f;
