@@ -195,12 +195,19 @@ __device__ __forceinline__ void xv_load(XV &v, const XVoiceParams &p, uint64_t i
 }
 __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
-// The launch's own final reduction (shared by both mix kernels): the last n_fin blocks to leave take one chunk (and every
-// n_fin-th) each and add the block rows in a fixed order; with a mix bus attached they push their columns to the peers.
+// The launch's own final reduction (shared by both mix kernels): it starts when the last block has left its render, with the whole
+// chip waiting, so it is spread wide -- the last n_fin = min(4 n_chunks, blocks) blocks to leave take a QUARTER chunk (16 of its 64
+// columns, and every n_fin-th unit) each; a thread adds an eighth of the block rows of one column (four chains, the loads of 16 rows
+// in flight), the eight partial sums meet in a fixed order (lane pairs, then the four warps through shared memory).  One thread
+// pair per column walking all rows took ~10 us at 443 rows; this form ~3.  With a mix bus attached the finishers push their
+// columns to the peers.
+#define XM_FIN_UNITS 4                               // units per chunk
+__host__ __device__ __forceinline__ uint32_t xm_n_fin(uint32_t n_chunks, uint32_t nb) { return XM_FIN_UNITS * n_chunks < nb ? XM_FIN_UNITS * n_chunks : nb; }
 __device__ __forceinline__ void xm_finish(const XVoiceParams &p, const BusFused &bf, const uint32_t n_chunks, uint32_t &tick_s) {
+    __shared__ float fin_red[XM_BLOCK / 32][16];
     const uint32_t nb = p.n_render_blocks;
     const uint32_t n_rows = nb * p.rows_per_block;               // partial rows of the launch: one per block, or one per warp (k_xvoice_mix2)
-    const uint32_t n_fin = n_chunks < nb ? n_chunks : nb;
+    const uint32_t n_fin = xm_n_fin(n_chunks, nb);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) tick_s = atomicAdd(p.done, 1u);
@@ -209,15 +216,18 @@ __device__ __forceinline__ void xm_finish(const XVoiceParams &p, const BusFused 
     if (tk < nb - n_fin) return;
     if (threadIdx.x == 0) while (ld_acquire_gpu_u32(p.done) < nb) __nanosleep(64);       // the stragglers are resident: they arrive
     __syncthreads();
-    for (uint32_t c = tk - (nb - n_fin); c < n_chunks; c += n_fin) {
+    const uint32_t col16 = threadIdx.x & 15u, slice = threadIdx.x >> 4, warp = threadIdx.x >> 5;      // XM_BLOCK == 128: slices 0..7
+    const uint32_t b0 = (uint32_t)((uint64_t)n_rows * slice / 8), b1 = (uint32_t)((uint64_t)n_rows * (slice + 1) / 8);
+    for (uint32_t u = tk - (nb - n_fin); u < XM_FIN_UNITS * n_chunks; u += n_fin) {
+        const uint32_t c = u / XM_FIN_UNITS, colc = (u % XM_FIN_UNITS) * 16u + col16;       // column of the chunk: channel, frame
         const uint64_t t0 = (uint64_t)c * XM_CHUNK;
         const uint32_t cols = p.F - t0 < XM_CHUNK ? (uint32_t)(p.F - t0) : XM_CHUNK;
-        const uint32_t col = threadIdx.x >> 1, half = threadIdx.x & 1u, ch = col / XM_CHUNK, f = col % XM_CHUNK;
-        const uint32_t b0 = half ? (n_rows + 1) / 2 : 0u, b1 = half ? n_rows : (n_rows + 1) / 2;
+        const uint32_t ch = colc / XM_CHUNK, f = colc % XM_CHUNK;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         if (f < cols) {
             const float *src = p.partial + (uint64_t)ch * p.F + t0 + f;
             uint32_t bq = b0;
+#pragma unroll 4
             for (; bq + 4 <= b1; bq += 4) {
                 s0 = __fadd_rn(s0, __ldcg(src + (uint64_t)(bq + 0) * 2 * p.F)); s1 = __fadd_rn(s1, __ldcg(src + (uint64_t)(bq + 1) * 2 * p.F));
                 s2 = __fadd_rn(s2, __ldcg(src + (uint64_t)(bq + 2) * 2 * p.F)); s3 = __fadd_rn(s3, __ldcg(src + (uint64_t)(bq + 3) * 2 * p.F));
@@ -225,12 +235,15 @@ __device__ __forceinline__ void xm_finish(const XVoiceParams &p, const BusFused 
             for (; bq < b1; ++bq) s0 = __fadd_rn(s0, __ldcg(src + (uint64_t)bq * 2 * p.F));
         }
         float s = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
-        const float o = __shfl_xor_sync(0xFFFFFFFFu, s, 1);
-        s = half ? __fadd_rn(o, s) : __fadd_rn(s, o);
-        if (!half && f < cols) {
+        const float o = __shfl_xor_sync(0xFFFFFFFFu, s, 16);       // slices 2w (lanes 0..15) and 2w+1 of warp w
+        if ((threadIdx.x & 16u) == 0) fin_red[warp][col16] = __fadd_rn(s, o);
+        __syncthreads();
+        if (threadIdx.x < 16u && f < cols) {
+            s = __fadd_rn(__fadd_rn(fin_red[0][col16], fin_red[1][col16]), __fadd_rn(fin_red[2][col16], fin_red[3][col16]));
             const uint64_t idx = (uint64_t)ch * p.F + t0 + f;
             if (bf.world) bus_emit_word(bf, idx, __float_as_uint(s)); else p.mix[idx] = s;
         }
+        __syncthreads();
     }
     __syncthreads();
     if (threadIdx.x == 0 && atomicAdd(p.done + 1, 1u) == n_fin - 1u) { p.done[0] = 0; p.done[1] = 0; __threadfence(); }   // ready for the next launch
@@ -411,11 +424,15 @@ __global__ void __launch_bounds__(XM2_BLOCK, XM2_MINB) k_xvoice_mix2(const XVoic
         // chain in front of the tick loop), 64-bit accesses at a 40-byte lane stride are conflict free per half-warp, and no barrier is
         // needed between the tile phases.
         const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(xm2_tile) + tid * 40u;     // this thread's pair 0; pair j: + j * 128 * 40
+        // (asynchronous copies: the 5 x ng 8-byte pieces of a thread are all in flight at once -- through registers the groups came one
+        // DRAM round trip after the other, ~1 us each, in front of the tile's first tick)
         for (uint32_t j = 0; j < ng; ++j) {
             const uint64_t gi = v0 + 2 * (tid + XM2_BLOCK * j);
 #pragma unroll
-            for (uint32_t w = 0; w < 5; ++w) xv_sts64(tile_s + j * (XM2_BLOCK * 40u) + 8 * w, __ldcs((const uint2 *)(p.st + (uint64_t)w * p.npad + gi)));     // npad % 256 == 0: whole groups; [n, npad) is zero
+            for (uint32_t w = 0; w < 5; ++w)                          // npad % 256 == 0: whole groups; [n, npad) is zero
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tile_s + j * (XM2_BLOCK * 40u) + 8 * w), "l"(__cvta_generic_to_global(p.st + (uint64_t)w * p.npad + gi)) : "memory");
         }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
         // (npad is a multiple of 256 for this processor and the rows are zero past n: whole groups, no bounds checks; one 64-bit base per
         // tile and a row pitch in uint2 units keep the address arithmetic of the 8 loads to a handful of instructions -- written as
         // `p.prm + w * npad + gi` with a predicate it was ~60 instructions of IMAD.WIDE / LEA.HI.X per pair and chunk)
@@ -1159,7 +1176,7 @@ int launch_xvoice(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
         p.vpt = ctx->xvoice_vpt > 0 ? (uint32_t)ctx->xvoice_vpt : XM_VPT;
         const uint32_t n_chunks = (uint32_t)ceil_div_u64(F, XM_CHUNK);
         BusFused bf;
-        int rc = cproc_bus_fused_begin(b, &bf, 2 * F, 2u, 0u, n_chunks < n_blocks ? n_chunks : (uint32_t)n_blocks, (int32_t *)io->mix, nullptr);
+        int rc = cproc_bus_fused_begin(b, &bf, 2 * F, 2u, 0u, xm_n_fin(n_chunks, (uint32_t)n_blocks), (int32_t *)io->mix, nullptr);
         if (rc) return rc;
         if (mix2) {
             k_xvoice_mix2<<<(unsigned)n_blocks + (bf.world && bf.mode == 2 ? 1u : 0u), XM2_BLOCK, mix2_smem, ctx->stream>>>(p, bf);
