@@ -192,11 +192,17 @@ __device__ __forceinline__ void v1_run_segment(const PdmV1Params &p, const uint3
                                                uint64_t c0, uint64_t bank, uint64_t w0, uint64_t w1, const uint32_t (*jt)[256] = nullptr) {
     const uint64_t words = p.F >> 5;
     const uint32_t *dext = DEXT ? p.dither_ext + bank * p.F : nullptr;
-    if (p.layout == CPROC_CUDA_TILED) {
+    // Groups of four words (128 ticks): the TILED layout's unit, and -- with the two-chain generator -- the unit of the software
+    // pipeline for the other layouts too when the run is whole groups (PLANAR: one 128-bit store per channel and group when the
+    // rows allow it; INTERLEAVED: four coalesced word stores).
+    const bool tiled = p.layout == CPROC_CUDA_TILED, il = p.layout == CPROC_CUDA_INTERLEAVED;
+    const bool groups4 = tiled || (!DEXT && jt && ((w0 | w1 | words) & 3) == 0);
+    if (groups4) {
+        const bool row16 = !tiled && !il && (((uintptr_t)p.out) & 15) == 0;       // PLANAR rows of whole groups from an aligned base
         for (uint64_t g = w0; g < w1; g += 4) {
             uint32_t q[4][B];
             if (!DEXT && jt) {
-                // four words per TILED group; the first word's dither is generated up front, the last
+                // four words per group; the first word's dither is generated up front, the last
                 // word of the group generates nothing (the next group starts over: one un-overlapped
                 // word in four keeps the generator state exact at every group boundary)
                 uint32_t da[32], db[32];
@@ -214,11 +220,20 @@ __device__ __forceinline__ void v1_run_segment(const PdmV1Params &p, const uint3
 #pragma unroll
             for (int k = 0; k < 4; ++k) v1_word<B, DEXT>(sp, acc, rng, DEXT ? dext + ((g + k) << 5) : nullptr, p.dmask, q[k]);
 #pragma unroll
-            for (int j = 0; j < B; ++j)
-                if (c0 + j < p.n) st_v4_stream(p.out + (((g >> 2) * p.n + c0 + j) << 2), make_uint4(q[0][j], q[1][j], q[2][j], q[3][j]));
+            for (int j = 0; j < B; ++j) {
+                if (c0 + j >= p.n) continue;
+                if (tiled) st_v4_stream(p.out + (((g >> 2) * p.n + c0 + j) << 2), make_uint4(q[0][j], q[1][j], q[2][j], q[3][j]));
+                else if (il) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) __stcs(p.out + (g + k) * p.n + c0 + j, q[k][j]);
+                } else if (row16) st_v4_stream(p.out + (c0 + j) * words + g, make_uint4(q[0][j], q[1][j], q[2][j], q[3][j]));
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) __stcs(p.out + (c0 + j) * words + g + k, q[k][j]);
+                }
+            }
         }
     } else {
-        const bool il = p.layout == CPROC_CUDA_INTERLEAVED;
         for (uint64_t g = w0; g < w1; ++g) {
             uint32_t wv[B];
             v1_word<B, DEXT>(sp, acc, rng, DEXT ? dext + (g << 5) : nullptr, p.dmask, wv);
@@ -304,7 +319,7 @@ int launch_pdm_v1(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     const bool tpb = ctx->pdm_tpb && c.bank_size <= 4;
     const uint64_t C = ceil_div_u64(p.n_banks, 32);
     bool swap_prng = false;
-    if (ctx->pdm_v1_chains == 2 && tpb && !dext && io->layout == CPROC_CUDA_TILED) {
+    if (ctx->pdm_v1_chains == 2 && tpb && !dext && (F & 127) == 0) {            // whole 128-tick groups: the two-chain, software-pipelined words in every layout
         if (!ctx->d_jump16) {                                 // M^16 of xorshift32 as 4 byte-indexed LUTs
             std::vector<uint32_t> h(1024);
             jump_table_fill(h.data(), 16);
