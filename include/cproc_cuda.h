@@ -97,7 +97,8 @@ enum cproc_cuda_proc {
      * ctl: setpoints uint32 [n_ctl][ch] (one row latched at every control
      * boundary met during the run, before the line copy) or NULL.
      * in2: external dither uint32 [bank][F] or NULL (xorshift32 per bank).
-     * out: uint8 duty.  PLANAR [ch][F], TILED [F/16][ch][16]. */
+     * out: uint8 duty.  PLANAR [ch][F], TILED [F/16][ch][16], INTERLEAVED
+     * [F][ch] (the order the ISR emits: one byte per channel per tick). */
     CPROC_CUDA_PDM_V2 = 4,
     /* pwm_update (mod_pdm.c:167-175).  state {uint32 phase}; param {uint32
      * speed}; out uint8 duty: PLANAR [inst][F], INTERLEAVED [F][inst], TILED

@@ -275,9 +275,15 @@ __device__ __noinline__ uint32_t ws4_producer_arith(uint4 *dbuf, const uint32_t 
 }
 
 constexpr size_t ws4_smem_bytes(int CW, int TLOG, int PL) {      // boxes, two dither slots, the jump table, alignment slack
-    return (size_t)(PL == 2 ? CW * 2 * 4096 : 0) + 2 * ((1u << TLOG) / 4) * 32 * 16 + 4096 + 1024;
+    return (size_t)(PL == 2 ? CW * 2 * 4096 : PL == 1 ? CW * 4096 : 0) + 2 * ((1u << TLOG) / 4) * 32 * 16 + 4096 + 1024;
 }
 
+// PL 1: INTERLEAVED duty [tick][ch] -- the order the firmware's ISR produces (one byte per channel per tick).  The consumer warps write
+// their byte of every tick into ONE [128 ticks][32 CW channels] tile per block in shared memory (lane == channel: 32 consecutive bytes
+// per warp, conflict free); when the batch is done they meet at a consumers-only barrier and move the tile out together as 16-byte
+// pieces, consecutive lanes on consecutive pieces of a tick row -- 32 CW contiguous bytes per tick and block (96 for banks of 3: one
+// or two L2 requests per row; per-warp rows of 32 bytes, a request each, ran 17 % slower: the pattern is bound by L2 requests, not
+// bytes).  n % 16 == 0, 16-byte aligned base.  One shift and one byte store per tick instead of 0.75 PRMT: ~7.4 instead of 6 instructions.
 // PL 0: 16-byte stores (TILED [F/16][ch][16], or PLANAR rows as scattered stores).  PL 2: PLANAR duty rows
 // [ch][F] leave through shared memory -- a consumer warp fills a box of 128 ticks x 32 channels (SWIZZLE_128B: lane r
 // writes 16-tick chunk c at r*128 + ((c ^ (r & 7)) << 4), conflict free), one elected lane stores it through the 2-D
@@ -290,7 +296,7 @@ __global__ void __launch_bounds__(32 * (CW + 1)) k_pdm_v2_ws4(const PdmV2Params 
     // 1024-byte alignment for the swizzled boxes, computed on the shared-window offset so that every pointer below stays an LDS / STS address
     uint8_t *base = ws4_smem + ((1024u - ((uint32_t)__cvta_generic_to_shared(ws4_smem) & 1023u)) & 1023u);
     uint8_t *pbox = base;                                             // [CW][2][4096]
-    uint4 *dbuf = reinterpret_cast<uint4 *>(base + (PL == 2 ? CW * 2 * 4096 : 0));   // [2][QW][32]
+    uint4 *dbuf = reinterpret_cast<uint4 *>(base + (PL == 2 ? CW * 2 * 4096 : PL == 1 ? CW * 4096 : 0));   // [2][QW][32]
     uint32_t *tab = reinterpret_cast<uint32_t *>(dbuf + 2 * QW * 32);
     for (uint32_t i = threadIdx.x; i < 1024; i += NT) tab[i] = __ldg(wk.jump + i);
     // Producer placement.  A warp runs on scheduler (%warpid % 4), and the hardware staggers the warp slots of
@@ -362,7 +368,7 @@ __global__ void __launch_bounds__(32 * (CW + 1)) k_pdm_v2_ws4(const PdmV2Params 
             const bool store = c < p.n;
             uint8_t *dst = p.layout == CPROC_CUDA_TILED ? p.out + (((bt0 << (TLOG - 4)) * p.n + c) << 4) : p.out + c * p.F + (bt0 << TLOG);
             const uint64_t dstep = p.layout == CPROC_CUDA_TILED ? p.n << 4 : 16;
-            const uint32_t pbox_s = PL == 2 ? (uint32_t)__cvta_generic_to_shared(pbox + cw * 8192) : 0u;
+            const uint32_t pbox_s = PL == 2 ? (uint32_t)__cvta_generic_to_shared(pbox + cw * 8192) : PL == 1 ? (uint32_t)__cvta_generic_to_shared(pbox) : 0u;   // PL 1: the block's tile
             const uint4 *dlane = dbuf + bl;
             uint32_t s = 0;
             for (uint64_t bt = 0; bt < nb; ++bt) {
@@ -384,9 +390,29 @@ __global__ void __launch_bounds__(32 * (CW + 1)) k_pdm_v2_ws4(const PdmV2Params 
                         uint32_t a[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) a[i] = ws4_tick<K>(r.p0[0], r.v0[0], r.s[0], d[i], m1);   // :108-116
-                        w[i4] = pack_top_bytes(a[0], a[1], a[2], a[3]);
+                        if constexpr (PL == 1) {
+                            const uint32_t row = (((uint32_t)bt << TLOG) + g16 * 16 + i4 * 4) & 127u;         // tick within the tile
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                asm volatile("st.shared.u8 [%0], %1;" ::"r"(pbox_s + (row + i) * (32u * CW) + cl), "r"(a[i] >> 24) : "memory");
+                        } else w[i4] = pack_top_bytes(a[0], a[1], a[2], a[3]);
                     }
-                    if constexpr (PL == 2) {
+                    if constexpr (PL == 1) {
+                        const uint32_t tk = ((uint32_t)bt << TLOG) + g16 * 16;          // ticks since the start of the slice (slices hold whole tiles)
+                        if ((tk & 127u) == 112u) {                                      // 128 ticks x 32 CW channels staged
+                            bar_sync_i<5, 32 * CW>();                                   // the consumers of the block (the next FULL barrier orders the tile's reuse)
+                            const uint64_t tick0 = (bt0 << TLOG) + tk - 112;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const uint32_t piece = i * (32u * CW) + cl, row = piece / (2u * CW), col = piece % (2u * CW);
+                                if (c_lo + col * 16 < p.n) {                            // n % 16 == 0: whole pieces
+                                    uint4 v;
+                                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(pbox_s + piece * 16u));
+                                    st_v4_stream(p.out + (tick0 + row) * p.n + c_lo + col * 16, v);
+                                }
+                            }
+                        }
+                    } else if constexpr (PL == 2) {
                         const uint32_t tk = ((uint32_t)bt << TLOG) + g16 * 16;          // ticks since the start of the slice
                         const uint32_t box = (tk >> 7) & 1u, ch = (tk >> 4) & 7u;
                         if (ch == 0 && tk >= 256) {                   // this box last left two boxes ago
@@ -459,8 +485,8 @@ static int ws4_go(cproc_cuda_ctx *ctx, const PdmV2Params &p, PdmV2Work &wk, cons
     }
     const uint64_t batches = p.F >> TLOG;
     uint64_t bps = slice_ticks >> TLOG;
-    if (PL == 2 && TLOG < 7) bps &= ~(uint64_t)((128 >> TLOG) - 1);   // slices hold whole 128-tick boxes
-    if (bps < 1) bps = PL == 2 && TLOG < 7 ? (128 >> TLOG) : 1;
+    if (PL != 0 && TLOG < 7) bps &= ~(uint64_t)((128 >> TLOG) - 1);   // slices hold whole 128-tick boxes / tiles
+    if (bps < 1) bps = PL != 0 && TLOG < 7 ? (128 >> TLOG) : 1;
     wk.bps = (uint32_t)bps;
     wk.slices = (uint32_t)ceil_div_u64(batches, bps);
     if ((uint64_t)wk.groups * wk.slices >= 0xFFFFFFFFull) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_v2: too many work items; render fewer ticks per call");
@@ -473,6 +499,7 @@ static int ws4_go(cproc_cuda_ctx *ctx, const PdmV2Params &p, PdmV2Work &wk, cons
 
 template <int K, int CW>
 static int ws4_dispatch(cproc_cuda_ctx *ctx, const PdmV2Params &p, PdmV2Work &wk, const CUtensorMap &tm, int tlog, int pl, uint64_t slice_ticks) {
+    if (pl == 1) return ws4_go<K, CW, 7, 1>(ctx, p, wk, tm, slice_ticks);   // INTERLEAVED tiles (the caller has checked that 128-tick batches apply)
     if (pl == 2) return ws4_go<K, CW, 6, 2>(ctx, p, wk, tm, slice_ticks);   // boxes + 64-tick slots: four blocks per SM still fit
     if (tlog >= 7) return ws4_go<K, CW, 7, 0>(ctx, p, wk, tm, slice_ticks);
     return ws4_go<K, CW, 6, 0>(ctx, p, wk, tm, slice_ticks);
@@ -487,8 +514,9 @@ static int launch_v2_ws4(cproc_cuda_batch *b, PdmV2Params &p) {
     memset(&tm, 0, sizeof(tm));
     int pl = 0;
     if (p.layout == CPROC_CUDA_PLANAR && ctx->pdm_planar_bulk && (p.F % 128) == 0 && pbulk::encode_rows_u8(&tm, p.out, p.F, p.n)) pl = 2;
+    if (p.layout == CPROC_CUDA_INTERLEAVED) pl = 1;                   // launch_pdm_v2 has checked v2_interleaved_fast()
     // batch length (ticks per FULL / EMPTY hand-off): 128 when F, the counter and the control period allow, else 64
-    int tlog = pl == 2 ? 6 : ctx->pdm_tlog;
+    int tlog = pl == 2 ? 6 : pl == 1 ? 7 : ctx->pdm_tlog;
     if (tlog > 6 && (((p.F | p.count0) & 127u) || p.ctl_div_log < 7)) tlog = 6;
     PdmV2Work wk;
     memset(&wk, 0, sizeof(wk));
@@ -570,10 +598,12 @@ int launch_pdm_v2(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     p.out = (uint8_t *)io->out; p.F = F; p.count0 = b->count; p.ctl_div_log = c.ctl_div_log; p.sh = c.out_shift;
     p.dmask = c.dither_mask; p.layout = io->layout; p.m1 = 0xFFFFFFFFu;
     const bool aligned_ptr = ((uintptr_t)io->out & 15) == 0 && (!io->in2 || ((uintptr_t)io->in2 & 15) == 0);
-    const bool fast = (F & 15) == 0 && (b->count & 15) == 0 && c.ctl_div_log >= 4 && aligned_ptr &&
-                      (io->layout == CPROC_CUDA_TILED || io->layout == CPROC_CUDA_PLANAR);
     const bool fastq = c.out_shift == 24 && (c.dither_mask & 0xFF000000u) == 0;
     const bool dext = io->in2 != nullptr;
+    // INTERLEAVED [tick][ch]: only through k_pdm_v2_ws4's tile path (whole 128-tick batches, channels in sixteens); the conformance kernel otherwise
+    const bool il_fast = io->layout == CPROC_CUDA_INTERLEAVED && fastq && !dext && ctx->pdm_ws && ((F | b->count) & 127) == 0 && c.ctl_div_log >= 7 && (b->n & 15) == 0;
+    const bool fast = (F & 15) == 0 && (b->count & 15) == 0 && c.ctl_div_log >= 4 && aligned_ptr &&
+                      (io->layout == CPROC_CUDA_TILED || io->layout == CPROC_CUDA_PLANAR || il_fast);
     int rc;
 #define V2_ORDER(KK) (fastq ? launch_v2_order<KK, true>(b, p, fast, dext) : launch_v2_order<KK, false>(b, p, fast, dext))
     switch (c.order) {

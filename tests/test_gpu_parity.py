@@ -114,6 +114,20 @@ def test_pdm_v2_ws4_orders_banks(st, ctx, oracle, order, bank, layout):
              use_dext=False, ctl=8, opts={"pdm_ctas_per_sm": 1, "pdm_slice_batches": 4})
 
 
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+@pytest.mark.parametrize("bank", [1, 2, 3, 4, 7, 33])
+def test_pdm_v2_ws4_interleaved_tiles(st, ctx, oracle, order, bank):
+    """INTERLEAVED duty [tick][ch] (the order the ISR emits) through k_pdm_v2_ws4's shared-memory tiles: every order, aligned and
+    straddling banks, slices of two batches with a ragged last slice, the counter starting inside a control period; then a channel
+    count that is not whole sixteens, which must take the conformance kernel and give the same bytes."""
+    _v2_case(st, ctx, oracle, order, bank, N=16 * 191, F=128 * 7, layout=st.INTERLEAVED, count0=128, use_setp=True,
+             use_dext=False, ctl=8, opts={"pdm_ctas_per_sm": 1, "pdm_slice_batches": 4})
+    if order == 2:
+        _v2_case(st, ctx, oracle, order, bank, N=32 * 95 + 5, F=128 * 3, layout=st.INTERLEAVED, count0=0, use_setp=True, use_dext=False, ctl=7)
+        _v2_case(st, ctx, oracle, order, bank, N=32 * 20, F=128 * 40, layout=st.INTERLEAVED, count0=0, use_setp=True, use_dext=False, ctl=9,
+                 split=None, opts={"pdm_ctas_per_sm": 4, "pdm_slice_batches": 64})
+
+
 @pytest.mark.parametrize("tlog", [6, 7])
 @pytest.mark.parametrize("layout", ["PLANAR", "TILED"])
 @pytest.mark.parametrize("order,bank", [(2, 3), (3, 2), (4, 9), (1, 1)])
