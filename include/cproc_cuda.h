@@ -448,7 +448,7 @@ int  cproc_cuda_timer_stop(cproc_cuda_ctx *ctx, float *elapsed_ms);
  *   pdm_ctas_per_sm [4], pdm_slice_batches [64: work items of 64 x 64 ticks]   PDM v2 dynamic schedule
  *   pdm_planar_bulk  0/2  [2]  PDM v2 PLANAR duty rows: scattered 16-byte stores, tensor-TMA boxes
  *   pdm_v1_chains    1/2  [2]  PDM v1: PRNG chains per lane
- *   pdm_block, pdm_tpb [1: thread per bank when bank_size <= 4], pdm_persist, pdm_warps_per_smsp   plain PDM kernels, PDM v1 schedule
+ *   pdm_block, pdm_tpb [2: auto; 1 thread per bank when bank_size <= 4; 0 thread per channel], pdm_persist, pdm_warps_per_smsp   plain PDM kernels, PDM v1 schedule
  *   xvoice_mix2      0/1  [1]  XVOICE mix-only render: voice pairs on the packed fp32 pipe (FFMA2) with state tiles in shared
  *                              memory; 0 = the scalar kernel (state through L2 once per 32-frame chunk)
  *   xvoice_mix2_blocks 0..3 [0] its resident blocks per SM (0 = chosen from the voice count)

@@ -107,7 +107,7 @@ int cproc_cuda_set_option(cproc_cuda_ctx *ctx, const char *name, int64_t value) 
     if (!ctx || !name) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "set_option: NULL argument");
     ctx->opt_epoch++;                                        // captured period graphs (cproc_cuda_run) are re-captured
     if (!strcmp(name, "pdm_block")) { if (value < 32 || value > 128 || (value & 31)) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_block must be 32, 64, 96 or 128"); ctx->pdm_block = (int)value; }
-    else if (!strcmp(name, "pdm_tpb")) ctx->pdm_tpb = value != 0;
+    else if (!strcmp(name, "pdm_tpb")) { if (value < 0 || value > 2) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_tpb must be 0 (thread per channel), 1 (thread per bank) or 2 (auto)"); ctx->pdm_tpb = (int)value; }
     else if (!strcmp(name, "pdm_stage")) ctx->pdm_stage = value != 0;
     else if (!strcmp(name, "pdm_ws")) ctx->pdm_ws = value != 0;
     else if (!strcmp(name, "voice_fpt")) { if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "voice_fpt must be 0, 1, 2, 4, 8 or 16"); ctx->voice_fpt = (int)value; }

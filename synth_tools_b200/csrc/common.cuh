@@ -20,7 +20,7 @@ struct cproc_cuda_ctx {
     uint64_t launches = 0;
     // tuning knobs (cproc_cuda_set_option)
     int pdm_block = 64;       // threads per block of the PDM kernels
-    int pdm_tpb = 1;          // 1: thread-per-bank when bank_size <= 4, 0: thread-per-channel
+    int pdm_tpb = 2;          // plain PDM kernels, banks of <= 4: 1 thread per bank, 0 thread per channel (every thread replays its bank's generator), 2 auto
     int pdm_stage = 1;        // 1: smem-staged full-line stores for PLANAR
     int pdm_ws = 1;           // PDM v2: 1 = producer / consumer kernel under the dynamic (group, slice) schedule (k_pdm_v2_ws4), 0 = plain thread-per-bank / per-channel kernels
     int pdm_tlog = 7;         // k_pdm_v2_ws4: log2 of the dither batch (ticks per FULL / EMPTY hand-off), 6 or 7

@@ -316,7 +316,12 @@ int launch_pdm_v1(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     p.jump16 = nullptr;
     const int blk = ctx->pdm_block;
     const bool dext = io->in2 != nullptr;
-    const bool tpb = ctx->pdm_tpb && c.bank_size <= 4;
+    // Thread per bank (3 instructions per channel-tick + 7 for the generator, once per bank) or thread per channel (every thread replays
+    // the generator: 10 per channel-tick, but bank_size times the warps).  Auto: per bank unless the banks are fewer warps than the chip
+    // has schedulers while the channels are not -- 65,536 channels in banks of 4 are 512 bank-warps on 592 schedulers: 1.89e12 per bank,
+    // 2.21e12 per channel (tools/layout_matrix.py).
+    bool tpb = ctx->pdm_tpb && c.bank_size <= 4;
+    if (ctx->pdm_tpb == 2 && tpb && c.bank_size >= 2 && ceil_div_u64(p.n_banks, 32) < 4ull * ctx->n_sm) tpb = false;
     const uint64_t C = ceil_div_u64(p.n_banks, 32);
     bool swap_prng = false;
     if (ctx->pdm_v1_chains == 2 && tpb && !dext && (F & 127) == 0) {            // whole 128-tick groups: the two-chain, software-pipelined words in every layout
@@ -424,6 +429,17 @@ static int launch_pdm_raw_bulk(cproc_cuda_ctx *ctx, const PdmRawParams &p) {
     return pbulk::launch<64, 3>(ctx, op, p.out, p.out, p.n, p.F);
 }
 
+template <int K>
+static void launch_pdm_raw_il4(cproc_cuda_ctx *ctx, const PdmRawParams &p) {
+    if (p.in) {
+        PdmRawOp<K, 1> op; op.st = p.st; op.param = p.param; op.dither = p.dither; op.npad = p.npad; op.sh = p.sh;
+        pbulk::launch_interleaved4(ctx, op, p.in, p.out, p.n, p.F);
+    } else {
+        PdmRawOp<K, 0> op; op.st = p.st; op.param = p.param; op.dither = p.dither; op.npad = p.npad; op.sh = p.sh;
+        pbulk::launch_interleaved4(ctx, op, p.out, p.out, p.n, p.F);
+    }
+}
+
 int launch_pdm(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
     cproc_cuda_ctx *ctx = b->ctx;
     if (!io->out) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm: out is NULL");
@@ -444,6 +460,16 @@ int launch_pdm(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
         }
         if (rc) return rc;
         CK_LAUNCH(ctx, "k_pdm_raw (bulk)");
+        return 0;
+    }
+    if (ctx->planar_bulk && io->layout == CPROC_CUDA_INTERLEAVED && pbulk::usable_interleaved4(p.n, p.in, p.out)) {
+        switch (b->cfg.order) {
+        case 1: launch_pdm_raw_il4<1>(ctx, p); break;
+        case 2: launch_pdm_raw_il4<2>(ctx, p); break;
+        case 3: launch_pdm_raw_il4<3>(ctx, p); break;
+        default: launch_pdm_raw_il4<4>(ctx, p); break;
+        }
+        CK_LAUNCH(ctx, "k_pdm_raw (interleaved4)");
         return 0;
     }
     switch (b->cfg.order) {

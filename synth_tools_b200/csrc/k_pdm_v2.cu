@@ -490,7 +490,9 @@ static int ws4_go(cproc_cuda_ctx *ctx, const PdmV2Params &p, PdmV2Work &wk, cons
     wk.bps = (uint32_t)bps;
     wk.slices = (uint32_t)ceil_div_u64(batches, bps);
     if ((uint64_t)wk.groups * wk.slices >= 0xFFFFFFFFull) return cproc_set_err(ctx, CPROC_CUDA_EINVAL, "pdm_v2: too many work items; render fewer ticks per call");
-    const int per_sm = ctx->pdm_ctas_per_sm < occ ? ctx->pdm_ctas_per_sm : occ;
+    int want_per_sm = ctx->pdm_ctas_per_sm;
+    if (CW == 1 && want_per_sm < 6) want_per_sm = 6;                 // banks of 1: a block is two warps -- six blocks per SM (1.48e12 -> 1.60e12 at the C2 shape)
+    const int per_sm = want_per_sm < occ ? want_per_sm : occ;
     uint64_t grid = (uint64_t)ctx->n_sm * per_sm;
     if (grid > wk.groups) grid = wk.groups;
     kern<<<(unsigned)grid, 32 * (CW + 1), smem, ctx->stream>>>(p, wk, tm);

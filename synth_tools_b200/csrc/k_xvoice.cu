@@ -1364,6 +1364,12 @@ int launch_onepole(cproc_cuda_batch *b, uint64_t F, const cproc_cuda_io *io) {
         CK_LAUNCH(ctx, "k_onepole (bulk)");
         return 0;
     }
+    if (ctx->planar_bulk && io->layout == CPROC_CUDA_INTERLEAVED && pbulk::usable_interleaved4(b->n, io->in, io->out)) {
+        OnepoleOp op; op.y = (float *)b->d_state; op.a = (const float *)b->d_param; op.s = 0.f; op.c = 0.f;
+        pbulk::launch_interleaved4(ctx, op, (const uint32_t *)io->in, (uint32_t *)io->out, b->n, F);
+        CK_LAUNCH(ctx, "k_onepole (interleaved4)");
+        return 0;
+    }
     k_onepole<<<(unsigned)ceil_div_u64(b->n, 128), 128, 0, ctx->stream>>>((float *)b->d_state, (const float *)b->d_param, b->n, F,
                                                                        (const float *)io->in, (float *)io->out, io->layout);
     CK_LAUNCH(ctx, "k_onepole");

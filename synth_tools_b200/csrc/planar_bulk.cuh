@@ -243,4 +243,42 @@ int launch(cproc_cuda_ctx *ctx, const Op &op, const uint32_t *in, uint32_t *out,
     return 0;
 }
 
+// ---- INTERLEAVED streams [F][inst]: four adjacent instances per thread ---------------------------------------------------
+// Rows are coalesced as they are; what a thread-per-instance kernel lacks is bytes in flight (one 4-byte load per thread and tick).
+// Here a thread owns instances i..i+3 (128-bit accesses: a block covers 2 KiB of every row) and loads a batch of four frames
+// before it ticks them.  n % 4 == 0, 16-byte aligned streams; `in` may alias `out`.
+template <class Op>
+__global__ void __launch_bounds__(128) k_interleaved4(Op op0, const uint32_t *in, uint32_t *out, uint64_t n, uint64_t F) {
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    Op a = op0, b = op0, c = op0, d = op0;
+    a.load(i); b.load(i + 1); c.load(i + 2); d.load(i + 3);
+    const uint4 *src = reinterpret_cast<const uint4 *>(in + i);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + i);
+    const uint64_t row = n >> 2;                                     // row pitch in uint4
+    uint64_t t = 0;
+    for (; t + 4 <= F; t += 4) {
+        uint4 x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = Op::NIN ? __ldcs(src + (t + k) * row) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            __stcs(dst + (t + k) * row, make_uint4(a.tick(x[k].x, t + k), b.tick(x[k].y, t + k), c.tick(x[k].z, t + k), d.tick(x[k].w, t + k)));
+    }
+    for (; t < F; ++t) {
+        const uint4 x = Op::NIN ? __ldcs(src + t * row) : make_uint4(0u, 0u, 0u, 0u);
+        __stcs(dst + t * row, make_uint4(a.tick(x.x, t), b.tick(x.y, t), c.tick(x.z, t), d.tick(x.w, t)));
+    }
+    a.store(i); b.store(i + 1); c.store(i + 2); d.store(i + 3);
+}
+
+inline bool usable_interleaved4(uint64_t n, const void *in, const void *out) {
+    return n % 4 == 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0;
+}
+
+template <class Op>
+void launch_interleaved4(cproc_cuda_ctx *ctx, const Op &op, const uint32_t *in, uint32_t *out, uint64_t n, uint64_t F) {
+    k_interleaved4<Op><<<(unsigned)ceil_div_u64(n / 4, 128), 128, 0, ctx->stream>>>(op, in, out, n, F);
+}
+
 }  // namespace pbulk

@@ -83,7 +83,7 @@ def _v2_case(st, ctx, oracle, order, bank, N, F, layout, count0, use_setp, use_d
             ctx.set_option(k, v)
 
 
-V2_DEFAULTS = {"pdm_tpb": 1, "pdm_block": 64, "pdm_ws": 1, "pdm_tlog": 7, "pdm_ctas_per_sm": 4,
+V2_DEFAULTS = {"pdm_tpb": 2, "pdm_block": 64, "pdm_ws": 1, "pdm_tlog": 7, "pdm_ctas_per_sm": 4,
                "pdm_slice_batches": 64, "pdm_planar_bulk": 2}
 
 
@@ -272,7 +272,7 @@ def test_pdm_v1(st, ctx, oracle, bank, tpb, persist, N, layout, chains):
     assert np.array_equal(b.download_state(), ca)
     assert np.array_equal(b.download_bank()[0], pa)
     b.free()
-    ctx.set_option("pdm_tpb", 1)
+    ctx.set_option("pdm_tpb", 2)
     ctx.set_option("pdm_persist", 1)
     ctx.set_option("pdm_v1_chains", 2)
 
@@ -293,7 +293,7 @@ def test_pdm_v1_banks_wider_than_a_block(st, ctx, oracle, N, bank, layout):
     out = np.zeros(N * F // 32, np.uint32)
     for _ in range(1):
         b.run(F, out=out)
-    ctx.set_option("pdm_tpb", 1)
+    ctx.set_option("pdm_tpb", 2)
     got = out.reshape(N, F // 32) if layout == "PLANAR" else out.reshape(F // 32, N).T if layout == "INTERLEAVED" else \
         out.reshape(F // 128, N, 4).transpose(1, 0, 2).reshape(N, F // 32)
     assert np.array_equal(got, want)
@@ -323,9 +323,10 @@ def test_pdm_v1_external_dither_and_density(st, ctx, oracle):
 
 # --------------------------------------------------------------------- pdm raw, pwm
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
-@pytest.mark.parametrize("layout", ["PLANAR", "INTERLEAVED"])
-def test_pdm_raw(st, ctx, oracle, order, layout):
-    N, F, sh = 130, 300, 24
+@pytest.mark.parametrize("layout,N,F", [("PLANAR", 130, 300), ("INTERLEAVED", 130, 300), ("INTERLEAVED", 132, 301), ("INTERLEAVED", 4 * 700, 64)])
+def test_pdm_raw(st, ctx, oracle, order, layout, N, F):
+    """PLANAR through the staging template; INTERLEAVED four instances per thread when the count allows (n % 4 == 0), else a thread each."""
+    sh = 24
     s0 = rng.integers(0, 2**32, (N, order), dtype=np.uint32)
     inp = rng.integers(0, 2**32, (N, F), dtype=np.uint32)
     dith = rng.integers(0, 1024, F, dtype=np.uint32)
@@ -1121,18 +1122,20 @@ def test_xvoice_scan(st, ctx, oracle, layout, N, F, chunk, groups):
         ctx.set_option("xvoice_groups", 0)
 
 
-def test_onepole(st, ctx, oracle):
-    N, F = 300, 200
+@pytest.mark.parametrize("layout,N,F", [("PLANAR", 300, 200), ("INTERLEAVED", 300, 201), ("INTERLEAVED", 301, 200), ("INTERLEAVED", 4 * 513, 37)])
+def test_onepole(st, ctx, oracle, layout, N, F):
     inp = rng.uniform(-1, 1, (N, F)).astype(np.float32)
     a = rng.uniform(0.001, 0.9, (N, 1)).astype(np.float32)
     y0 = rng.uniform(-1, 1, (N, 1)).astype(np.float32)
     ya = y0[:, 0].copy()
     want = oracle.onepole_run(ya, a[:, 0].copy(), N, F, inp)
-    b = ctx.batch(st.ONEPOLE, N)
+    b = ctx.batch(st.ONEPOLE, N, layout=getattr(st, layout))
     b.upload_state(y0); b.upload_param(a)
-    out = np.zeros((N, F), np.float32)
-    b.run(F, inp=inp, out=out)
-    assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
+    il = layout == "INTERLEAVED"
+    out = np.zeros((F, N) if il else (N, F), np.float32)
+    b.run(F, inp=np.ascontiguousarray(inp.T) if il else inp, out=out)
+    assert np.array_equal((out.T if il else out).view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(b.download_state().view(np.float32)[:, 0], ya)
     b.free()
 
 
