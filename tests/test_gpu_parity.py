@@ -104,6 +104,16 @@ def test_pdm_v2_layouts_and_mappings(st, ctx, oracle, layout, tpb, ws, blk):
 
 
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
+@pytest.mark.parametrize("bank", [1, 2, 3, 4, 7, 33])
+@pytest.mark.parametrize("planar_bulk", [0, 2])
+def test_pdm_v2_ws4_planar_paths(st, ctx, oracle, order, bank, planar_bulk):
+    """PLANAR duty rows out of k_pdm_v2_ws4 both ways -- scattered 16-byte stores, tensor-TMA boxes per warp (64-tick batches) --
+    over ragged channel counts, straddling banks and a ragged last slice."""
+    _v2_case(st, ctx, oracle, order, bank, N=2999, F=128 * 7, layout=st.PLANAR, count0=128, use_setp=True,
+             use_dext=False, ctl=8, opts={"pdm_ctas_per_sm": 1, "pdm_slice_batches": 4, "pdm_planar_bulk": planar_bulk})
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
 @pytest.mark.parametrize("bank", [1, 2, 3, 4, 5, 7, 33])
 @pytest.mark.parametrize("layout", ["PLANAR", "TILED"])
 def test_pdm_v2_ws4_orders_banks(st, ctx, oracle, order, bank, layout):
