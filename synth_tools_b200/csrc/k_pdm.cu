@@ -186,6 +186,25 @@ __device__ __forceinline__ void v1_word_pipe(const uint32_t (&sp)[B], uint32_t (
     for (int j = 0; j < B; ++j) wv[j] = __brev(bits[j]);
 }
 
+// One group of four words with the two-chain generator, software pipelined: the first word's dither is generated up front, the last
+// word of the group generates nothing (the next group starts over: one un-overlapped word in four keeps the generator state exact
+// at every group boundary).
+template <int B>
+__device__ __forceinline__ void v1_group_pipe(const PdmV1Params &p, const uint32_t (&sp)[B], uint32_t (&acc)[B], uint32_t &rng, const uint32_t (*jt)[256],
+                                              uint32_t (&q)[4][B]) {
+    uint32_t da[32], db[32];
+    {
+        uint32_t xa = rng, xb = jump_apply(jt, rng);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { xa = xorshift32_step(xa); da[i] = xa & p.dmask; xb = xorshift32_step(xb); da[16 + i] = xb & p.dmask; }
+        rng = xb;
+    }
+    v1_word_pipe<B, true>(sp, acc, da, db, rng, jt, p.dmask, q[0]);
+    v1_word_pipe<B, true>(sp, acc, db, da, rng, jt, p.dmask, q[1]);
+    v1_word_pipe<B, true>(sp, acc, da, db, rng, jt, p.dmask, q[2]);
+    v1_word_pipe<B, false>(sp, acc, db, da, rng, jt, p.dmask, q[3]);
+}
+
 // words [w0, w1) of one thread's B channels
 template <int B, bool DEXT>
 __device__ __forceinline__ void v1_run_segment(const PdmV1Params &p, const uint32_t (&sp)[B], uint32_t (&acc)[B], uint32_t &rng,
@@ -194,36 +213,31 @@ __device__ __forceinline__ void v1_run_segment(const PdmV1Params &p, const uint3
     const uint32_t *dext = DEXT ? p.dither_ext + bank * p.F : nullptr;
     // Groups of four words (128 ticks): the TILED layout's unit, and -- with the two-chain generator -- the unit of the software
     // pipeline for the other layouts too when the run is whole groups (PLANAR: one 128-bit store per channel and group when the
-    // rows allow it; INTERLEAVED: four coalesced word stores).
-    const bool tiled = p.layout == CPROC_CUDA_TILED, il = p.layout == CPROC_CUDA_INTERLEAVED;
-    const bool groups4 = tiled || (!DEXT && jt && ((w0 | w1 | words) & 3) == 0);
-    if (groups4) {
-        const bool row16 = !tiled && !il && (((uintptr_t)p.out) & 15) == 0;       // PLANAR rows of whole groups from an aligned base
+    // rows allow it; INTERLEAVED: four coalesced word stores).  The TILED loop is kept on its own: it is the measured one
+    // (sharing it with the other layouts' store selection cost it 3.5 %).
+    if (p.layout == CPROC_CUDA_TILED) {
         for (uint64_t g = w0; g < w1; g += 4) {
             uint32_t q[4][B];
-            if (!DEXT && jt) {
-                // four words per group; the first word's dither is generated up front, the last
-                // word of the group generates nothing (the next group starts over: one un-overlapped
-                // word in four keeps the generator state exact at every group boundary)
-                uint32_t da[32], db[32];
-                {
-                    uint32_t xa = rng, xb = jump_apply(jt, rng);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { xa = xorshift32_step(xa); da[i] = xa & p.dmask; xb = xorshift32_step(xb); da[16 + i] = xb & p.dmask; }
-                    rng = xb;
-                }
-                v1_word_pipe<B, true>(sp, acc, da, db, rng, jt, p.dmask, q[0]);
-                v1_word_pipe<B, true>(sp, acc, db, da, rng, jt, p.dmask, q[1]);
-                v1_word_pipe<B, true>(sp, acc, da, db, rng, jt, p.dmask, q[2]);
-                v1_word_pipe<B, false>(sp, acc, db, da, rng, jt, p.dmask, q[3]);
-            } else
+            if (!DEXT && jt) v1_group_pipe<B>(p, sp, acc, rng, jt, q);
+            else
 #pragma unroll
             for (int k = 0; k < 4; ++k) v1_word<B, DEXT>(sp, acc, rng, DEXT ? dext + ((g + k) << 5) : nullptr, p.dmask, q[k]);
 #pragma unroll
+            for (int j = 0; j < B; ++j)
+                if (c0 + j < p.n) st_v4_stream(p.out + (((g >> 2) * p.n + c0 + j) << 2), make_uint4(q[0][j], q[1][j], q[2][j], q[3][j]));
+        }
+        return;
+    }
+    const bool il = p.layout == CPROC_CUDA_INTERLEAVED;
+    if (!DEXT && jt && ((w0 | w1 | words) & 3) == 0) {
+        const bool row16 = !il && (((uintptr_t)p.out) & 15) == 0;        // PLANAR rows of whole groups from an aligned base
+        for (uint64_t g = w0; g < w1; g += 4) {
+            uint32_t q[4][B];
+            v1_group_pipe<B>(p, sp, acc, rng, jt, q);
+#pragma unroll
             for (int j = 0; j < B; ++j) {
                 if (c0 + j >= p.n) continue;
-                if (tiled) st_v4_stream(p.out + (((g >> 2) * p.n + c0 + j) << 2), make_uint4(q[0][j], q[1][j], q[2][j], q[3][j]));
-                else if (il) {
+                if (il) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) __stcs(p.out + (g + k) * p.n + c0 + j, q[k][j]);
                 } else if (row16) st_v4_stream(p.out + (c0 + j) * words + g, make_uint4(q[0][j], q[1][j], q[2][j], q[3][j]));
@@ -233,14 +247,14 @@ __device__ __forceinline__ void v1_run_segment(const PdmV1Params &p, const uint3
                 }
             }
         }
-    } else {
-        for (uint64_t g = w0; g < w1; ++g) {
-            uint32_t wv[B];
-            v1_word<B, DEXT>(sp, acc, rng, DEXT ? dext + (g << 5) : nullptr, p.dmask, wv);
+        return;
+    }
+    for (uint64_t g = w0; g < w1; ++g) {
+        uint32_t wv[B];
+        v1_word<B, DEXT>(sp, acc, rng, DEXT ? dext + (g << 5) : nullptr, p.dmask, wv);
 #pragma unroll
-            for (int j = 0; j < B; ++j)
-                if (c0 + j < p.n) __stcs(p.out + (il ? g * p.n + c0 + j : (c0 + j) * words + g), wv[j]);
-        }
+        for (int j = 0; j < B; ++j)
+            if (c0 + j < p.n) __stcs(p.out + (il ? g * p.n + c0 + j : (c0 + j) * words + g), wv[j]);
     }
 }
 
