@@ -95,13 +95,12 @@ static void sg_render(struct sg_pipe *p) {
     if (!rc) {
         static float before[SG_MAX_GRAINS];
         memcpy(before, sg_state, sizeof(float) * (size_t)sg_count);
-        rc = cproc_cuda_upload_state(p->batch, sg_state, sizeof(float));
-        if (!rc) rc = cproc_cuda_upload_param(p->batch, sg_th, sizeof(float));
+        rc = cproc_cuda_upload_param(p->batch, sg_th, sizeof(float));
         cproc_cuda_io io;
         memset(&io, 0, sizeof(io));
         io.in = p->in; io.out = p->out; io.layout = CPROC_CUDA_PLANAR;
-        if (!rc) rc = cproc_cuda_run(p->batch, (uint64_t)p->block, &io);
-        if (!rc) rc = cproc_cuda_download_state(p->batch, sg_state, sizeof(float));
+        /* the objects' states travel with the tick: records in, render, records out, one synchronisation */
+        if (!rc) rc = cproc_cuda_run_period(p->batch, (uint64_t)p->block, &io, sg_state, sizeof(float));
         if (!rc) for (int g = 0; g < sg_count; g++) { if (p->ran[g]) p->have[g] = 1; else sg_state[g] = before[g]; }   /* rows that were not collected did not run */
     }
     memset(p->ran, 0, sizeof(p->ran));
