@@ -190,6 +190,21 @@ def c2_v1(st, ctx, reps=3):
                   "SURVEY 8d: 4 int instr per channel-sample + 6 PRNG instr per bank-tick / 2 channels; 1/8 B per sample out")
 
 
+def c2_layout(st, ctx, layout, reps=3):
+    """C2 PDM v2 at the headline's channel count with the duty bytes in another layout (the headline is TILED): PLANAR rows through
+    tensor-TMA boxes, INTERLEAVED [tick][ch] -- the order the ISR of mod_pdm_pwm.c produces them -- through block tiles."""
+    N, F, L = 65536, 32768, 12
+    d_out = ctx.dev_alloc(N * F)
+    rows = F >> L
+    sp = np.random.default_rng(6).integers(0x40000000, 0xC0000000, (rows, N), dtype=np.uint32)
+    d_sp = ctx.dev_alloc(sp.nbytes); ctx.h2d(d_sp, sp)
+    b = ctx.batch(st.PDM_V2, N, order=2, bank_size=3, ctl_div_log=L, layout=getattr(st, layout.upper()))
+    ms = _time(ctx, lambda: b.run_dev(F, ctl=d_sp, n_ctl=rows, out=d_out), reps)
+    b.free(); ctx.dev_free(d_out); ctx.dev_free(d_sp)
+    return _issue("C2 PDM v2, 65,536 ch x 32,768 ticks per launch, %s duty out" % ("PLANAR [ch][F]" if layout == "planar" else "INTERLEAVED [tick][ch]"),
+                  N * F, "samples", ms, 10.0, "the headline's modulator in the other two duty layouts (DESIGN 4.1)")
+
+
 def c3a(st, ctx, hbm_peak, reps=5, layout="planar"):
     rng = np.random.default_rng(3)
     N, F = 1024 * 1024, 256
@@ -634,7 +649,8 @@ def run_all(st, ctx, hbm_peak):
     except Exception as e:
         cpu = {"error": "%s: %s" % (type(e).__name__, e)}
     rows = []
-    for key, fn in (("c1", lambda: c1(st, ctx)), ("c2_v1", lambda: c2_v1(st, ctx)), ("c3a", lambda: c3a(st, ctx, hbm_peak, layout="planar")),
+    for key, fn in (("c1", lambda: c1(st, ctx)), ("c2_v1", lambda: c2_v1(st, ctx)), ("c2", lambda: c2_layout(st, ctx, "planar")), ("c2", lambda: c2_layout(st, ctx, "interleaved")),
+                    ("c3a", lambda: c3a(st, ctx, hbm_peak, layout="planar")),
                     ("c3a", lambda: c3a(st, ctx, hbm_peak, layout="interleaved")),
                     ("c3b", lambda: c3b(st, ctx)), ("c4", lambda: c4(st, ctx)), ("c4p", lambda: c4p(st, ctx)),
                     ("c5", lambda: c5(st, ctx, hbm_peak, layout="tiled")), ("c5", lambda: c5(st, ctx, hbm_peak, layout="planar")),
