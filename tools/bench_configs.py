@@ -615,18 +615,20 @@ def graph_voice(st, ctx, hbm_peak, reps=3, layout="planar"):
                 N * F, "ticks", ms, 8.0, hbm_peak, "0 B in + 8 B out per tick (8 GiB out); bit-identical to k_xvoice raw output (tests/test_graph_ext.py)")
 
 
-def pdm_raw(st, ctx, hbm_peak, reps=3):
-    """pdm2_update (stm32f103/pdm.h) on a caller-supplied input stream, planar uint32 in / out."""
+def pdm_raw(st, ctx, hbm_peak, reps=3, layout="planar"):
+    """pdm2_update (stm32f103/pdm.h) on a caller-supplied input stream, uint32 in / out, planar [ch][F] or interleaved [F][ch]
+    (random words: the layout only decides who reads which)."""
     rng = np.random.default_rng(10)
     N, F = 1024 * 1024, 1024
     d_in = ctx.dev_alloc(4 * N * F); d_out = ctx.dev_alloc(4 * N * F)
     chunk = rng.integers(0, 2**32, (16384, F), dtype=np.uint32)
     for k in range(N // 16384):
         ctx.h2d(d_in + k * chunk.nbytes, chunk)
-    b = ctx.batch(st.PDM, N, order=2, out_shift=24)
+    b = ctx.batch(st.PDM, N, order=2, out_shift=24, layout=st.PLANAR if layout == "planar" else st.INTERLEAVED)
     ms = _time(ctx, lambda: b.run_dev(F, inp=d_in, out=d_out), reps)
     b.free(); ctx.dev_free(d_in); ctx.dev_free(d_out)
-    return _hbm("pdm2_update on an input stream, 1 Mi channels x 1,024 ticks, planar uint32 in/out (tensor-TMA staging)", N * F, "samples", ms, 8.0,
+    how = "planar uint32 in/out (tensor-TMA staging)" if layout == "planar" else "interleaved uint32 in/out (four channels per thread)"
+    return _hbm("pdm2_update on an input stream, 1 Mi channels x 1,024 ticks, " + how, N * F, "samples", ms, 8.0,
                 hbm_peak, "4 B in + 4 B out per sample; 4 GiB in + 4 GiB out")
 
 
@@ -656,7 +658,7 @@ def run_all(st, ctx, hbm_peak):
                     ("c5", lambda: c5(st, ctx, hbm_peak, layout="tiled")), ("c5", lambda: c5(st, ctx, hbm_peak, layout="planar")),
                     ("graph_bp5", lambda: graph_bp5(st, ctx, hbm_peak, layout="planar")), ("graph_bp5", lambda: graph_bp5(st, ctx, hbm_peak, layout="interleaved")),
                     ("graph_voice", lambda: graph_voice(st, ctx, hbm_peak, layout="planar")), ("graph_voice", lambda: graph_voice(st, ctx, hbm_peak, layout="interleaved")),
-                    ("pdm_raw", lambda: pdm_raw(st, ctx, hbm_peak)), ("c1_long", lambda: c1_long(st, ctx))):
+                    ("pdm_raw", lambda: pdm_raw(st, ctx, hbm_peak)), ("pdm_raw", lambda: pdm_raw(st, ctx, hbm_peak, layout="interleaved")), ("c1_long", lambda: c1_long(st, ctx))):
         try:
             row = fn()
             if key in cpu:
